@@ -1,0 +1,757 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU (numpy/scipy) restatement of the PEUQSE log-posterior hot path.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may import
+this module.  The product (peuqse_b200/) never does; it fails loudly without its CUDA library.
+
+Parity status: PINNED.  tests/test_oracle_golden.py checks every function here against
+  * the reference's own stored outputs (Examples/Example00 and Example26 multistart CSV rows),
+  * fixtures produced by importing and running the UNMODIFIED reference in the build container
+    (tests/golden/make_golden.py, outputs tests/golden/*.npz).
+Exception: ensemble slice sampling (`ess_*`) restates the published algorithm of zeus-mcmc
+(Karamanis & Beutler, arXiv:2002.06212; zeus-mcmc >= 2.4.0 per the reference's setup.py:36, cited
+at InverseProblem.py:2356-2359).  zeus is not vendored in the reference and not installed here, so
+for ESS "parity unpinned" -- it is checked statistically against closed-form posteriors only.
+
+All file:line citations are to /root/reference/PEUQSE/InverseProblem.py ("IP.py") unless stated.
+Two flavours of every evaluation are kept:
+  *_point   -- one theta at a time through scipy.stats.multivariate_normal.logpdf, exactly as the
+               reference does it (eigh per call).  This is the timed CPU baseline ("port").
+  *_batch   -- vectorised numpy with the eigendecomposition hoisted out (done once), same
+               floating-point operation order per point, for parity checks at larger sizes.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+import scipy.linalg
+from scipy.stats import multivariate_normal
+
+LOG2PI = float(np.log(2 * np.pi))  # scipy/stats/_multivariate.py:42
+
+
+# --------------------------------------------------------------------------------------------
+# Host-side normalisation (IP.py:146-350): turns user input into the constants of the hot path
+# --------------------------------------------------------------------------------------------
+@dataclass
+class Whitening:
+    """scipy _PSD of one covariance (scipy/stats/_multivariate.py:208-236), computed once."""
+    rank: int
+    log_pdet: float
+    U: np.ndarray                     # (n, n) = u * sqrt(1/s)
+    is_perm: bool = False             # U has exactly one non-zero per column (diagonal cov)
+    perm: Optional[np.ndarray] = None  # row of the non-zero in column j
+    w: Optional[np.ndarray] = None     # |U[perm[j], j]|
+
+
+def psd_whitening(cov) -> Whitening:
+    """What multivariate_normal.logpdf builds from `cov` on every call (allow_singular=False)."""
+    cov = np.asarray(cov, dtype=float)
+    if cov.ndim == 0:
+        cov = cov.reshape(1, 1)
+    elif cov.ndim == 1:
+        cov = np.diag(cov)          # _multivariate.py:533
+    s, u = scipy.linalg.eigh(cov, lower=True, check_finite=True)
+    eps = 1e6 * np.finfo('d').eps * np.max(np.abs(s))   # _eigvalsh_to_eps
+    if np.min(s) < -eps:
+        raise ValueError("The input matrix must be symmetric positive semidefinite.")
+    d = s[s > eps]
+    if len(d) < len(s):
+        raise np.linalg.LinAlgError("singular covariance (allow_singular=False)")
+    s_pinv = np.array([0 if abs(x) <= eps else 1 / x for x in s], dtype=float)  # _pinv_1d
+    U = np.multiply(u, np.sqrt(s_pinv))
+    wh = Whitening(rank=len(d), log_pdet=float(np.sum(np.log(d))), U=U)
+    nz = U != 0
+    if np.all(nz.sum(axis=0) == 1):
+        wh.is_perm = True
+        wh.perm = np.argmax(nz, axis=0).astype(np.int64)
+        wh.w = np.abs(U[wh.perm, np.arange(U.shape[1])])
+    return wh
+
+
+@dataclass
+class ResponseBlock:
+    """One response dimension of the likelihood (IP.py:2949-2979)."""
+    y: np.ndarray                 # observed (transformed) values, (n,)
+    cov: np.ndarray               # variances (n,) or full covariance (n,n), sim-uncertainty already added
+    per_value: bool               # True: n > responses_observed_max_covmat_size (IP.py:2951)
+    wh: Optional[Whitening] = None          # mvn path
+    w_val: Optional[np.ndarray] = None      # per-value path: sqrt(1/V_j)
+    c_val: Optional[np.ndarray] = None      # per-value path: 1*LOG2PI + ln V_j
+
+
+@dataclass
+class OracleProblem:
+    k: int
+    mu_prior: np.ndarray
+    std_prior: np.ndarray         # 1-D sigma (IP.py:173) or elementwise sqrt of covmat (IP.py:179)
+    covmat_prior: np.ndarray
+    scaling: Optional[np.ndarray]  # None == 'off'
+    mu_prior_scaled: np.ndarray
+    var_prior_scaled: np.ndarray
+    covmat_prior_scaled: np.ndarray
+    uniform_idx: Optional[List[int]]      # None: attribute absent (no -1 uncertainties)
+    lb: Optional[np.ndarray]              # object arrays with None entries, or None when list empty
+    ub: Optional[np.ndarray]
+    responses: List[ResponseBlock] = field(default_factory=list)
+    prior_wh: Optional[Whitening] = None  # of the (possibly truncated) scaled prior covariance
+    gauss_idx: Optional[np.ndarray] = None
+    max_covmat_size: int = 100
+    Q_covmat: Optional[np.ndarray] = None
+
+
+def build_problem(prior_values, prior_uncertainties, observed, observed_uncertainties,
+                  lower_bounds=(), upper_bounds=(), scaling_type="std",
+                  simulation_uncertainties=None, max_covmat_size=100) -> OracleProblem:
+    """Restates parameter_estimation.__init__ for the hot-path constants.
+
+    prior: IP.py:146-179; scaling: IP.py:311-339; observed covmat: IP.py:343-346 + 3591-3606;
+    simulation uncertainties added as variances: IP.py:2895, 2931; Q: IP.py:349-350.
+    `observed`, `observed_uncertainties`: 1-D (single response) or list of 1-D / 2-D per response.
+    """
+    mu = np.array(prior_values, dtype=float)
+    unc = np.array(prior_uncertainties, dtype=float)
+    k = len(mu)
+    lb = np.array(list(lower_bounds), dtype=object) if len(lower_bounds) else None
+    ub = np.array(list(upper_bounds), dtype=object) if len(upper_bounds) else None
+    uniform_idx = None
+    if -1.0 in unc:                                           # IP.py:149
+        uniform_idx = []
+        for i, u in enumerate(unc):
+            if u == -1.0:
+                uniform_idx.append(i)
+                if lb is None or ub is None:
+                    raise SystemExit("uniform prior needs both bounds (IP.py:164-165)")
+                unc[i] = (ub[i] - lb[i]) / (12 ** 0.5)        # IP.py:166
+                mu[i] = (ub[i] + lb[i]) / 2                   # IP.py:169
+    if unc.ndim == 1:                                         # IP.py:172-175
+        std = np.array(unc, dtype=float)
+        var = np.power(unc, 2)
+        covmat = np.diagflat(var)
+    else:                                                     # IP.py:176-179
+        covmat = np.array(unc, dtype=float)
+        var = np.diagonal(covmat)
+        std = np.power(covmat, 0.5)
+    if scaling_type == "off":                                 # IP.py:311-314
+        scaling = None
+        mu_s, var_s, cov_s = mu * 1.0, var * 1.0, covmat * 1.0
+    else:
+        if scaling_type == "std":
+            scaling = std
+        elif scaling_type == "mu":
+            scaling = mu
+        else:
+            scaling = (mu / mu) * float(scaling_type)         # IP.py:321-322
+        if np.ndim(scaling) == 2:                             # IP.py:327-328
+            scaling = np.diagonal(scaling) ** 0.5
+        mu_s = np.array(mu / scaling)                         # IP.py:333
+        var_s = np.array(var / (scaling * scaling))           # IP.py:334
+        cov_s = covmat * 1.0
+        for i, sv in enumerate(scaling):                      # IP.py:336-339
+            cov_s[i, :] = cov_s[i, :] / sv
+            cov_s[:, i] = cov_s[:, i] / sv
+
+    P = OracleProblem(k=k, mu_prior=mu, std_prior=std, covmat_prior=covmat, scaling=scaling,
+                      mu_prior_scaled=mu_s, var_prior_scaled=var_s, covmat_prior_scaled=cov_s,
+                      uniform_idx=uniform_idx, lb=lb, ub=ub, max_covmat_size=max_covmat_size,
+                      Q_covmat=covmat)
+    # prior whitening, hoisted (IP.py:2772-2785)
+    if uniform_idx is None:
+        P.gauss_idx = np.arange(k)
+        P.prior_wh = psd_whitening(cov_s)
+    else:
+        P.gauss_idx = np.delete(np.arange(k), uniform_idx)
+        if len(P.gauss_idx):
+            P.prior_wh = psd_whitening(np.diagflat(np.delete(var_s, uniform_idx)))  # IP.py:2778-2781
+
+    # responses: make 2-D nested
+    obs = _nest(observed)
+    ounc = _nest_unc(observed_uncertainties, len(obs))
+    sunc = None if simulation_uncertainties is None else _nest_unc(simulation_uncertainties, len(obs))
+    single = len(obs) == 1
+    for r, y in enumerate(obs):
+        cov = _shaped_response_cov(ounc, r)
+        if sunc is not None:
+            cov = cov + _shaped_response_cov(sunc, r)                     # IP.py:2931
+        if single and cov.ndim == 2:
+            raise NotImplementedError("single-response full covariance is dead code in the reference "
+                                      "(SURVEY Q2); use >= 2 responses")
+        per_value = len(y) > max_covmat_size                              # IP.py:2951
+        blk = ResponseBlock(y=np.asarray(y, dtype=float), cov=cov, per_value=per_value)
+        if per_value:
+            if cov.ndim != 1:
+                raise NotImplementedError("per-value path needs variances (IP.py:2971)")
+            wl = [psd_whitening(v) for v in cov] if len(cov) <= 4096 else None
+            # scalar logpdf: U = sqrt(1/V), log_pdet = ln V, rank 1
+            blk.w_val = np.sqrt(1.0 / cov)
+            blk.c_val = 1 * LOG2PI + np.log(cov)
+            if wl is not None:   # guard: hoisted constants equal what scipy builds per value
+                assert np.array_equal(blk.w_val, np.array([abs(w.U[0, 0]) for w in wl]))
+                assert np.array_equal(blk.c_val, np.array([w.rank * LOG2PI + w.log_pdet for w in wl]))
+        else:
+            blk.wh = psd_whitening(cov)
+        P.responses.append(blk)
+    return P
+
+
+def _shaped_response_cov(unc_list, r):
+    """returnShapedResponseCovMat, IP.py:3591-3606.
+
+    One response: a 1-D list of sigmas arrives as shape (1, n) and is squared into variances (3595-3596);
+    anything else is taken as a covariance matrix.
+    Two or more responses (reference quirk, kept for parity; verified against the fixtures): entry r is
+    squared only if np.shape(entry)[0] == 1, and the array is re-created on every loop iteration (3601),
+    so only the LAST response can ever be squared and only when it holds a single value.  A vector of n > 1
+    sigmas is therefore used AS IF it were variances.
+    """
+    u = np.asarray(unc_list[r], dtype=float)
+    nresp = len(unc_list)
+    if nresp == 1:
+        return np.square(u) if u.ndim == 1 else u
+    if r == nresp - 1 and u.shape[0] == 1:
+        return np.square(u)
+    return u
+
+
+def _nest(x):
+    a = np.asarray(x, dtype=object) if _is_ragged(x) else np.asarray(x, dtype=float)
+    if a.dtype != object and a.ndim == 1:
+        return [np.asarray(a, dtype=float)]
+    return [np.asarray(r, dtype=float) for r in x]
+
+
+def _nest_unc(x, nresp):
+    if nresp == 1:
+        a = np.asarray(x, dtype=float)
+        if a.ndim == 1:
+            return [a]
+        if a.ndim == 2 and a.shape[0] == 1:
+            return [a[0]]
+        return [a]            # full covariance for the single response
+    return [np.asarray(r, dtype=float) for r in x]
+
+
+def _is_ragged(x):
+    try:
+        np.asarray(x, dtype=float)
+        return False
+    except (ValueError, TypeError):
+        return True
+
+
+# --------------------------------------------------------------------------------------------
+# Faithful per-point path (what the reference executes; the timed CPU baseline)
+# --------------------------------------------------------------------------------------------
+def bounds_check(values, bounds, kind):
+    """boundsCheck, IP.py:3608-3633 (inclusive; None = unbounded)."""
+    values = np.array(values).flatten()
+    bounds = np.array(bounds).flatten()
+    v = values[bounds != None].flatten()       # noqa: E711  (numpy elementwise, as in the reference)
+    b = bounds[bounds != None].flatten()       # noqa: E711
+    if kind == 'upper':
+        if False in (v <= b):
+            return False
+    if kind == 'lower':
+        if False in (v >= b):
+            return False
+    return True
+
+
+def log_prior_point(P: OracleProblem, theta) -> float:
+    """getLogPrior, IP.py:2756-2794 (custom_logPrior and undo_scaling omitted)."""
+    if P.ub is not None and not bounds_check(theta, P.ub, 'upper'):     # IP.py:2797-2800
+        return float('-inf')
+    if P.lb is not None and not bounds_check(theta, P.lb, 'lower'):     # IP.py:2801-2804
+        return float('-inf')
+    if P.scaling is None:
+        ts = np.array(theta) * 1.0                                      # IP.py:2764
+    else:
+        ts = np.array(theta) / P.scaling                                # IP.py:2767
+    if P.uniform_idx is None:
+        return multivariate_normal.logpdf(x=ts, mean=P.mu_prior_scaled, cov=P.covmat_prior_scaled)  # IP.py:2773
+    ts_t = np.delete(ts, P.uniform_idx)
+    mu_t = np.delete(P.mu_prior_scaled, P.uniform_idx)
+    cov_t = np.diagflat(np.delete(P.var_prior_scaled, P.uniform_idx))
+    if len(cov_t) == 0:
+        return 0                                                        # IP.py:2782-2783
+    return multivariate_normal.logpdf(x=ts_t, mean=mu_t, cov=cov_t)     # IP.py:2785
+
+
+def log_likelihood_point(P: OracleProblem, sim) -> float:
+    """getLogLikelihood + getLogLikelihood_byResponses, IP.py:2850-2980, given simulated responses.
+
+    `sim`: None / 1-D (single response) / list of 1-D per response.
+    """
+    if sim is None:
+        return float('-inf')                                            # IP.py:2863-2865
+    sims = _nest(sim)
+    if any(np.isnan(s).any() for s in sims):
+        return float('-inf')                                            # IP.py:2880-2882
+    total = 0                                                           # IP.py:2948
+    for r, blk in enumerate(P.responses):
+        if not blk.per_value:
+            ll = multivariate_normal.logpdf(mean=sims[r], x=blk.y, cov=blk.cov)     # IP.py:2960
+        else:
+            ll = 0                                                      # IP.py:2968
+            for j in range(len(sims[r])):                               # IP.py:2969-2978
+                cur = multivariate_normal.logpdf(mean=sims[r][j], x=blk.y[j], cov=blk.cov[j])
+                if float(cur) == float('-inf'):
+                    cur = -1E100
+                ll = cur + ll
+        total = total + ll                                              # IP.py:2979
+    return total
+
+
+def log_p_point(P: OracleProblem, theta, simulate: Callable) -> float:
+    """getLogP, IP.py:1647-1654."""
+    lp = log_prior_point(P, theta)
+    if lp == float('-inf'):
+        return float('-inf')
+    ll = log_likelihood_point(P, simulate(tuple(np.ndarray.copy(np.array(theta)))))   # IP.py:2851
+    return ll + lp
+
+
+# --------------------------------------------------------------------------------------------
+# Vectorised path: same per-point operation order, eigendecompositions hoisted
+# --------------------------------------------------------------------------------------------
+def _np_rowsum(a):
+    """np.sum(a, axis=-1) on a C-contiguous (B, n) array == numpy pairwise order per row, which is
+    what scipy's `np.sum(np.square(...), axis=-1)` does for its (1, n) input (_multivariate.py:590)."""
+    return np.sum(np.ascontiguousarray(a), axis=-1)
+
+
+def _maha(dev, wh: Whitening):
+    if wh.is_perm:
+        q = np.square(dev[:, wh.perm] * wh.w)       # (dev @ U)_j = dev[perm_j] * (+-w_j): exact
+    else:
+        q = np.square(dev @ wh.U)                   # BLAS order: tolerance, not bit parity
+    return _np_rowsum(q)
+
+
+def log_prior_batch(P: OracleProblem, thetas) -> np.ndarray:
+    th = np.atleast_2d(np.asarray(thetas, dtype=float))
+    B = th.shape[0]
+    ok = np.ones(B, dtype=bool)
+    if P.ub is not None:
+        for i, b in enumerate(P.ub):
+            if b is not None:
+                ok &= th[:, i] <= float(b)
+    if P.lb is not None:
+        for i, b in enumerate(P.lb):
+            if b is not None:
+                ok &= th[:, i] >= float(b)
+    ts = th * 1.0 if P.scaling is None else th / P.scaling
+    if P.prior_wh is None:
+        lp = np.zeros(B)
+    else:
+        dev = ts[:, P.gauss_idx] - P.mu_prior_scaled[P.gauss_idx]
+        wh = P.prior_wh
+        lp = -0.5 * (wh.rank * LOG2PI + wh.log_pdet + _maha(dev, wh))     # _multivariate.py:591
+    return np.where(ok, lp, -np.inf)
+
+
+def log_likelihood_batch(P: OracleProblem, sims: Sequence[np.ndarray]) -> np.ndarray:
+    """sims: list over responses of (B, n_r) arrays."""
+    B = sims[0].shape[0]
+    bad = np.zeros(B, dtype=bool)
+    total = np.zeros(B)
+    for r, blk in enumerate(P.responses):
+        s = np.asarray(sims[r], dtype=float)
+        bad |= np.isnan(s).any(axis=1)
+        dev = blk.y - s                                                   # x - mean, IP.py:2960
+        with np.errstate(invalid='ignore', over='ignore'):
+            if not blk.per_value:
+                wh = blk.wh
+                ll = -0.5 * (wh.rank * LOG2PI + wh.log_pdet + _maha(dev, wh))
+            else:
+                terms = -0.5 * (blk.c_val + np.square(dev * blk.w_val))   # scalar logpdf per value
+                terms = np.where(terms == -np.inf, -1E100, terms)         # IP.py:2975-2977
+                ll = np.zeros(B)
+                for j in range(terms.shape[1]):                           # sequential, IP.py:2978
+                    ll = terms[:, j] + ll
+            total = total + ll
+    return np.where(bad, -np.inf, total)
+
+
+def log_p_batch(P: OracleProblem, thetas, simulate_batch: Callable):
+    """-> (logP, logPrior, logLik); logLik is computed for every row (as MH does) while
+    logP short-circuits to -inf for out-of-bounds rows (IP.py:1649)."""
+    th = np.atleast_2d(np.asarray(thetas, dtype=float))
+    lp = log_prior_batch(P, th)
+    with np.errstate(all='ignore'):
+        sims = simulate_batch(th)
+    if isinstance(sims, np.ndarray):
+        sims = [sims]
+    ll = log_likelihood_batch(P, sims)
+    logp = np.where(lp == -np.inf, -np.inf, ll + lp)
+    return logp, lp, ll
+
+
+# --------------------------------------------------------------------------------------------
+# Built-in simulation models (the "user plugin" side, L0 in SURVEY section 1)
+# --------------------------------------------------------------------------------------------
+def sim_quadratic(x):
+    """Examples/Example00/simulation_model_00.py:6-10, 19-24: y = (x-a)**2 + b."""
+    x = np.asarray(x)
+
+    def point(theta):
+        return (x - theta[0]) ** 2 + theta[1]
+
+    def batch(th):
+        return (x[None, :] - th[:, 0:1]) ** 2 + th[:, 1:2]
+    return point, batch
+
+
+KB_KJ = 1.380649e-26 * 6.0221409e+23   # Examples/Example01/tprmodel.py:17
+
+
+def tpd2site_constants(n=1024):
+    """prescribed coverages, linear temperature ramp."""
+    t = np.linspace(0, 400, n)
+    T = 150 + 0.5 * t
+    cov1 = 0.5 * np.exp(-t / 150)
+    cov2 = 0.5 * np.exp(-t / 300)
+    return KB_KJ * T, cov1, cov2
+
+
+def sim_tpd2site(kBT, cov1, cov2):
+    """Rate law of Examples/Example01/tprmodel.py:20 with prescribed coverages, summed over the
+    two sites: sim_j = sum_i cov_ij*exp(-(Ea_i - kBT_j*logA_i - gamma_i*cov_ij)/kBT_j).
+    theta = (Ea1, Ea2, logA1, logA2, gamma1, gamma2)."""
+    def batch(th):
+        th = np.atleast_2d(th)
+        Ea1, Ea2, lA1, lA2, g1, g2 = (th[:, i:i + 1] for i in range(6))
+        r1 = cov1 * np.exp(-(Ea1 - kBT * lA1 - g1 * cov1) / kBT)
+        r2 = cov2 * np.exp(-(Ea2 - kBT * lA2 - g2 * cov2) / kBT)
+        return r1 + r2
+
+    def point(theta):
+        return batch(np.asarray(theta, dtype=float)[None, :])[0]
+    return point, batch
+
+
+def sim_linear(Phi):
+    """sim = Phi @ theta, accumulated parameter by parameter in index order (the kernels' order)."""
+    Phi = np.asarray(Phi, dtype=float)
+
+    def batch(th):
+        th = np.atleast_2d(th)
+        acc = Phi[None, :, 0] * th[:, 0:1]
+        for d in range(1, Phi.shape[1]):
+            acc = acc + Phi[None, :, d] * th[:, d:d + 1]
+        return acc
+
+    def point(theta):
+        return batch(np.asarray(theta, dtype=float)[None, :])[0]
+    return point, batch
+
+
+def cos_basis(n, k):
+    x = np.linspace(0, 1, n)
+    return np.cos(np.pi * np.arange(k)[None, :] * x[:, None])
+
+
+# --------------------------------------------------------------------------------------------
+# Multistart: grid order, uniform points, best-of, permutations -> samples, statistics
+# --------------------------------------------------------------------------------------------
+def combination_generator(center, interval, radii):
+    """CombinationGeneratorModule.py:40-81 ("Addition" spread), literal list construction."""
+    combos = [np.asarray(center, dtype=float)]
+    for p in range(len(center)):
+        for base_i in range(len(combos)):
+            base = combos[base_i]
+            if radii[p] > 0:
+                for i in range(1, radii[p] + 1):
+                    lo = list(base)
+                    lo[p] = base[p] - (interval[p] * i)      # :59
+                    combos.append(tuple(lo))
+                    hi = list(base)
+                    hi[p] = base[p] + (interval[p] * i)      # :71
+                    combos.append(tuple(hi))
+    return combos
+
+
+def grid_size(radii) -> int:
+    n = 1
+    for r in radii:
+        n *= 2 * int(r) + 1
+    return n
+
+
+def grid_decode(center, interval, radii, idx) -> np.ndarray:
+    """Closed-form element `idx` of combination_generator's list."""
+    center = np.asarray(center, dtype=float)
+    interval = np.asarray(interval, dtype=float)
+    g = np.asarray(idx, dtype=np.int64).copy()
+    k = len(center)
+    out = np.empty(g.shape + (k,))
+    M = [1]
+    for d in range(k):
+        M.append(M[-1] * (2 * int(radii[d]) + 1))
+    for p in range(k - 1, -1, -1):
+        r2 = 2 * int(radii[p])
+        inner = g < M[p]
+        gp = np.where(inner, 0, g - M[p])
+        if r2 > 0:
+            base = gp // r2
+            j = gp % r2
+        else:
+            base, j = gp, np.zeros_like(gp)
+        i = j // 2 + 1
+        step = interval[p] * i.astype(float)                 # (BaseFactor * i) first, then +/-
+        val = np.where(j % 2 == 0, center[p] - step, center[p] + step)
+        out[..., p] = np.where(inner, center[p], val)
+        g = np.where(inner, g, base)
+    return out
+
+
+def uniform_points(u01, spread, std_prior, center):
+    """generateInitialPoints('uniform'), IP.py:706 + 749, from given U[0,1) draws.
+    np.random.uniform(-2,2) == -2 + 4*u (numpy legacy: low + (high-low)*random_sample)."""
+    first = -2.0 + 4.0 * np.asarray(u01)
+    return spread * first * np.asarray(std_prior) + np.asarray(center)
+
+
+def first_max(logp):
+    """Best-of loop, IP.py:824, 933-938: strict '>' from -inf; NaN never selected."""
+    best, idx = float('-inf'), -1
+    for i, v in enumerate(logp):
+        if v > best:
+            best, idx = v, i
+    return idx, best
+
+
+def first_max_np(logp):
+    lp = np.where(np.isnan(logp), -np.inf, logp)
+    i = int(np.argmax(lp))
+    return (i, float(lp[i])) if lp[i] > -np.inf else (-1, float('-inf'))
+
+
+def permutation_weights(logp, max_logp, coef=2.0):
+    """convertPermutationsToSamples, IP.py:3463-3491: copies = int(exp(logP - thr)) for logP > thr."""
+    thr = max_logp + np.log(10 ** (-1 * coef))               # IP.py:1016, 3477
+    with np.errstate(over='ignore', invalid='ignore'):
+        reps = np.exp(np.asarray(logp) - thr)
+    w = np.where(np.asarray(logp) > thr, np.floor(reps), 0.0)
+    return w.astype(np.int64), thr
+
+
+def convert_permutations_to_samples(logp_and_params, max_logp, coef=2.0):
+    """The literal expansion (small inputs only)."""
+    w, _ = permutation_weights(logp_and_params[:, 0], max_logp, coef)
+    return np.repeat(logp_and_params, w, axis=0)
+
+
+def weighted_statistics(logp, thetas, w, nbins=10):
+    """calculatePostBurnInStatistics on the expanded array (IP.py:1923-1931) expressed with weights;
+    histograms as plotting_functions.py:135 (ax.hist default: 10 equal bins over [min,max])."""
+    w = np.asarray(w, dtype=float)
+    keep = w > 0
+    W = w.sum()
+    mu = (w[:, None] * thetas).sum(axis=0) / W
+    std = np.sqrt((w[:, None] * (thetas - mu) ** 2).sum(axis=0) / W)
+    evidence = ((w * np.exp(logp)).sum() / W) / np.sqrt((w[:, None] * thetas ** 2).sum())
+    hists, edges = [], []
+    for d in range(thetas.shape[1]):
+        lo, hi = thetas[keep, d].min(), thetas[keep, d].max()
+        h, e = np.histogram(thetas[keep, d], bins=nbins, range=(lo, hi), weights=w[keep])
+        hists.append(h)
+        edges.append(e)
+    return dict(W=W, mu_AP=mu, stdap=std, evidence=evidence, hist=np.array(hists), edges=np.array(edges))
+
+
+# --------------------------------------------------------------------------------------------
+# Metropolis-Hastings with injected draws (IP.py:2606-2675, 2715-2727)
+# --------------------------------------------------------------------------------------------
+def mh_chain_point(P: OracleProblem, theta0, deltas, us, simulate: Callable, modulate=0.0):
+    """Literal restatement: re-evaluates the current point each step, one point at a
+    time through scipy.  deltas[(L-1),k]: proposal increments; us[L-1]: accept uniforms."""
+    L = len(us) + 1
+    k = len(theta0)
+    samples = np.zeros((L, k))
+    logp = np.zeros((L, 1))
+    lps = np.zeros((L, 1))
+    lls = np.zeros((L, 1))
+    acc = np.zeros(L, dtype=bool)
+    samples[0] = theta0
+    logp[0] = log_p_point(P, samples[0], simulate)                     # IP.py:2625
+    for i in range(1, L):
+        prop = samples[i - 1] + deltas[i - 1]                          # IP.py:2630
+        lp_p = log_prior_point(P, prop)
+        ll_p = log_likelihood_point(P, simulate(tuple(prop)))
+        lp_c = log_prior_point(P, samples[i - 1])
+        ll_c = log_likelihood_point(P, simulate(tuple(samples[i - 1])))
+        with np.errstate(invalid='ignore'):
+            la = (ll_p + lp_p) - (ll_c + lp_c)                         # IP.py:2641
+        if modulate != 0:
+            la = (1 / float(modulate)) * la                            # IP.py:2649
+        with np.errstate(divide='ignore'):
+            lu = np.log(us[i - 1])                                     # IP.py:2651
+        if la > lu:                                                    # IP.py:2652
+            samples[i], logp[i], lls[i], lps[i], acc[i] = prop, ll_p + lp_p, ll_p, lp_p, True
+        else:
+            samples[i], logp[i], lls[i], lps[i] = samples[i - 1], ll_c + lp_c, ll_c, lp_c
+    return dict(samples=samples, logP=logp, log_priors=lps, log_likelihoods=lls, accepted=acc)
+
+
+def mh_chains_batch(P: OracleProblem, theta0, deltas, us, simulate_batch: Callable, modulate=0.0):
+    """C chains advanced together with cached current values (bit-identical to the literal loop
+    because re-evaluating the unchanged current point reproduces the same doubles).
+    theta0[C,k], deltas[L-1,C,k], us[L-1,C]."""
+    theta = np.array(theta0, dtype=float)
+    C, k = theta.shape
+    L = us.shape[0] + 1
+    samples = np.zeros((L, C, k))
+    logp = np.zeros((L, C))
+    lps = np.zeros((L, C))
+    lls = np.zeros((L, C))
+    acc = np.zeros((L, C), dtype=bool)
+    cur_p, cur_lp, cur_ll = log_p_batch(P, theta, simulate_batch)
+    samples[0], logp[0] = theta, cur_p
+    cur_sum = cur_ll + cur_lp                       # MH uses ll+lp even when lp == -inf (Q5)
+    for i in range(1, L):
+        prop = theta + deltas[i - 1]
+        _, lp_p, ll_p = log_p_batch(P, prop, simulate_batch)
+        with np.errstate(invalid='ignore', divide='ignore'):
+            la = (ll_p + lp_p) - cur_sum
+            if modulate != 0:
+                la = (1 / float(modulate)) * la
+            a = la > np.log(us[i - 1])
+        theta = np.where(a[:, None], prop, theta)
+        cur_lp = np.where(a, lp_p, cur_lp)
+        cur_ll = np.where(a, ll_p, cur_ll)
+        cur_sum = np.where(a, ll_p + lp_p, cur_sum)
+        samples[i], logp[i], lps[i], lls[i], acc[i] = theta, cur_sum, cur_lp, cur_ll, a
+    return dict(samples=samples, logP=logp, log_priors=lps, log_likelihoods=lls, accepted=acc)
+
+
+def post_burn_in_statistics(samples, logp):
+    """IP.py:1923-1931 without the tail filter."""
+    mu = np.mean(samples, axis=0)
+    sd = np.std(samples, axis=0)
+    lp = np.asarray(logp).reshape(-1)
+    m = max(lp)
+    idx = list(lp).index(m)
+    evidence = np.mean(np.exp(lp)) / np.linalg.norm(samples)
+    return dict(mu_AP=mu, stdap=sd, map_logP=m, map_index=idx, map_parameter_set=samples[idx],
+                evidence=evidence)
+
+
+# --------------------------------------------------------------------------------------------
+# Ensemble slice sampling -- published algorithm (parity unpinned, see module header)
+# --------------------------------------------------------------------------------------------
+def ess_run(logp_batch: Callable, start, nsteps, rng: np.random.Generator, mu0=1.0, maxiter=10000,
+            tune=True, tolerance=0.05, patience=5, maxsteps=10000):
+    """Karamanis & Beutler 2020 (arXiv:2002.06212) Algorithms 2-4 with the differential move, as
+    implemented by zeus.EnsembleSampler.run_mcmc which the reference calls at IP.py:2495-2498.
+    logp_batch(X[B,k]) -> logp[B].  Returns chain[nsteps,W,k], logp[nsteps,W], neval."""
+    X = np.array(start, dtype=float)
+    W, k = X.shape
+    Z = logp_batch(X)
+    if not np.all(np.isfinite(Z)):
+        raise ValueError("Invalid walker initial positions! Initialise walkers from positions of finite log probability.")
+    chain = np.empty((nsteps, W, k))
+    chain_lp = np.empty((nsteps, W))
+    mu = mu0
+    neval = W
+    tuning = tune
+    n_tuned = 0
+    half = W // 2
+    for it in range(nsteps):
+        perm = rng.permutation(W)
+        sets = [perm[:half], perm[half:]]
+        nexp = ncon = 0
+        for s in range(2):
+            active, inactive = sets[s], sets[1 - s]
+            na = len(active)
+            # differential move: direction from two distinct complementary walkers
+            pairs = np.array([rng.choice(len(inactive), 2, replace=False) for _ in range(na)])
+            directions = 2.0 * mu * (X[inactive[pairs[:, 0]]] - X[inactive[pairs[:, 1]]])
+            Z0 = Z[active] - rng.exponential(size=na)
+            Lb = -rng.uniform(size=na)
+            Rb = Lb + 1.0
+            Jl = np.floor(maxsteps * rng.uniform(size=na)).astype(int)
+            Kr = (maxsteps - 1) - Jl
+            X0 = X[active]
+            # stepping out, left
+            mask = np.ones(na, dtype=bool)
+            cnt = 0
+            while mask.any():
+                mask = mask & (Jl >= 1)
+                if not mask.any():
+                    break
+                zl = logp_batch(X0[mask] + Lb[mask, None] * directions[mask])
+                neval += int(mask.sum())
+                out = zl < Z0[mask]
+                idx = np.where(mask)[0]
+                Lb[idx[~out]] -= 1.0
+                Jl[idx[~out]] -= 1
+                nexp += int((~out).sum())
+                mask[idx[out]] = False
+                cnt += 1
+                if cnt > maxiter:
+                    raise RuntimeError("Number of expansions exceeded maximum limit! maxiter")
+            mask = np.ones(na, dtype=bool)
+            cnt = 0
+            while mask.any():
+                mask = mask & (Kr >= 1)
+                if not mask.any():
+                    break
+                zr = logp_batch(X0[mask] + Rb[mask, None] * directions[mask])
+                neval += int(mask.sum())
+                out = zr < Z0[mask]
+                idx = np.where(mask)[0]
+                Rb[idx[~out]] += 1.0
+                Kr[idx[~out]] -= 1
+                nexp += int((~out).sum())
+                mask[idx[out]] = False
+                cnt += 1
+                if cnt > maxiter:
+                    raise RuntimeError("Number of expansions exceeded maximum limit! maxiter")
+            # shrinking
+            mask = np.ones(na, dtype=bool)
+            Wd = np.zeros(na)
+            Xn = X0.copy()
+            Zn = Z[active].copy()
+            cnt = 0
+            while mask.any():
+                idx = np.where(mask)[0]
+                Wd[idx] = Lb[idx] + rng.uniform(size=len(idx)) * (Rb[idx] - Lb[idx])
+                cand = X0[idx] + Wd[idx, None] * directions[idx]
+                zc = logp_batch(cand)
+                neval += len(idx)
+                ok = zc >= Z0[idx]
+                Xn[idx[ok]] = cand[ok]
+                Zn[idx[ok]] = zc[ok]
+                mask[idx[ok]] = False
+                rej = idx[~ok]
+                neg = Wd[rej] < 0
+                Lb[rej[neg]] = Wd[rej[neg]]
+                Rb[rej[~neg]] = Wd[rej[~neg]]
+                ncon += len(rej)
+                cnt += 1
+                if cnt > maxiter:
+                    raise RuntimeError("Number of contractions exceeded maximum limit! maxiter")
+            X[active] = Xn
+            Z[active] = Zn
+        if tuning:
+            nexp_eff = max(1, nexp)
+            mu = mu * 2.0 * nexp_eff / (nexp_eff + ncon)
+            if abs(nexp_eff / (nexp_eff + ncon) - 0.5) < tolerance:
+                n_tuned += 1
+            else:
+                n_tuned = 0
+            if n_tuned >= patience:
+                tuning = False
+        chain[it] = X
+        chain_lp[it] = Z
+    return chain, chain_lp, neval, mu
+
+
+def linear_gaussian_posterior(Phi, Sigma_inv_Phi, y, prior_var):
+    """Closed form for y ~ N(Phi theta, Sigma), theta ~ N(0, prior_var I): (mean, cov)."""
+    A = Phi.T @ Sigma_inv_Phi + np.eye(Phi.shape[1]) / prior_var
+    cov = np.linalg.inv(A)
+    return cov @ (Sigma_inv_Phi.T @ y), cov

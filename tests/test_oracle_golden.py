@@ -1,0 +1,263 @@
+"""Pins oracle/ against the reference: stored CSV rows of the reference repo and fixtures produced by
+running the unmodified reference (tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+from oracle import peuqse_oracle as orc
+from oracle import philox_np
+
+X00 = [600, 1100, 1400]
+Y00 = [360500, 580500, 1620500]
+S00 = [200000, 300000, 200000]
+
+
+def ex00(**kw):
+    return orc.build_problem(kw.pop('mu', [200, 500]), kw.pop('unc', [100, 200]), Y00, S00, **kw)
+
+
+def check_vals(P, sim_point, sim_batch, thetas, vals, exact=True, rtol=1e-13):
+    """vals[:, 0:3] = reference getLogP, getLogPrior, getLogLikelihood."""
+    lp_b, pr_b, ll_b = orc.log_p_batch(P, thetas, sim_batch)
+    for i, th in enumerate(thetas):
+        p = orc.log_p_point(P, th, sim_point)
+        assert p == vals[i, 0] or (np.isnan(p) and np.isnan(vals[i, 0])), (i, p, vals[i, 0])
+        assert orc.log_prior_point(P, th) == vals[i, 1]
+    if exact:
+        assert np.array_equal(lp_b, vals[:, 0])
+        assert np.array_equal(pr_b, vals[:, 1])
+        assert np.array_equal(ll_b, vals[:, 2])
+    else:
+        fin = np.isfinite(vals[:, 0])
+        assert np.array_equal(np.isfinite(lp_b), fin)
+        np.testing.assert_allclose(lp_b[fin], vals[fin, 0], rtol=rtol)
+        np.testing.assert_allclose(ll_b, vals[:, 2], rtol=rtol)
+        np.testing.assert_allclose(pr_b, vals[:, 1], rtol=rtol)
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors for philox4x32-10
+    assert [int(x) for x in philox_np.philox4x32_10([0, 0, 0, 0], [0, 0])] == \
+        [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert [int(x) for x in philox_np.philox4x32_10([0xffffffff] * 4, [0xffffffff] * 2)] == \
+        [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert [int(x) for x in philox_np.philox4x32_10([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344],
+                                                    [0xa4093822, 0x299f31d0])] == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+    ua, ub = philox_np.uniform_pair(7, 2, np.arange(10000), 0)
+    assert ua.min() >= 0 and ua.max() < 1 and abs(ua.mean() - 0.5) < 0.02 and abs(ub.mean() - 0.5) < 0.02
+    z, u = philox_np.mh_draws(0, np.arange(4000)[:, None], np.arange(1, 6)[None, :], 6)
+    assert z.shape == (4000, 5, 6) and abs(z.mean()) < 0.02 and abs(z.std() - 1) < 0.02
+
+
+def test_example00_stored_csv_rows(golden):
+    """The reference repo's own stored (logP, a, b) rows: Examples/Example00/logs_and_csvs/
+    multistart_MAP_logP_and_parameters_values.csv (bit-exact)."""
+    g = golden("example00")
+    P = ex00()
+    pt, bt = orc.sim_quadratic(X00)
+    rows = g['ex00_csv_rows']
+    for r in rows:
+        assert orc.log_p_point(P, r[1:], pt) == r[0]
+    assert np.array_equal(orc.log_p_batch(P, rows[:, 1:], bt)[0], rows[:, 0])
+    # SURVEY 8c closed-form known answers
+    assert orc.log_p_point(P, [200, 500], pt) == -42.81726459961094
+    assert orc.log_p_point(P, [150, 400], pt) == -42.797773932944274
+    assert orc.log_p_point(P, [255, 139153], pt) == -240350.85630424548
+
+
+def test_example00_points(golden):
+    g = golden("example00")
+    pt, bt = orc.sim_quadratic(X00)
+    check_vals(ex00(), pt, bt, g['ex00_thetas'], g['ex00_logP_prior_lik'])
+
+
+def test_grid_order(golden):
+    g = golden("example00")
+    for name in ("g3", "g3d"):
+        c, h, r = g[f'grid_{name}_center'], g[f'grid_{name}_interval'], g[f'grid_{name}_radii']
+        ref = g[f'grid_{name}_list']
+        lst = np.array([np.array(x, dtype=float) for x in orc.combination_generator(c, h, r)])
+        assert np.array_equal(lst, ref)
+        assert orc.grid_size(r) == len(ref)
+        assert np.array_equal(orc.grid_decode(c, h, r, np.arange(len(ref))), ref)
+
+
+def test_example00_grid_multistart(golden):
+    g = golden("example00")
+    arr = g['ex00_grid_logP_theta']
+    P = ex00()
+    _, bt = orc.sim_quadratic(X00)
+    th = orc.grid_decode([200., 500.], [5., 5.], [50, 50], np.arange(10201))
+    assert np.array_equal(th, arr[:, 1:])
+    logp = orc.log_p_batch(P, th, bt)[0]
+    assert np.array_equal(logp, arr[:, 0])
+    idx, best = orc.first_max(logp)
+    assert (idx, best) == orc.first_max_np(logp)
+    assert idx == 13 and best == float(g['ex00_grid_map_logP']) == -42.637391007597046
+    assert np.array_equal(th[idx], g['ex00_grid_map_theta'])
+    w, thr = orc.permutation_weights(logp, best, 2.0)
+    assert np.array_equal(w, g['ex00_grid_multiplicity'])
+    assert w.sum() == int(g['ex00_grid_nrows_expanded']) == 225166
+    st = orc.weighted_statistics(logp, th, w)
+    np.testing.assert_allclose(st['mu_AP'], g['ex00_grid_mu_AP'], rtol=1e-12)
+    np.testing.assert_allclose(st['stdap'], g['ex00_grid_stdap'], rtol=1e-11)
+    np.testing.assert_allclose(st['evidence'], float(g['ex00_grid_evidence']), rtol=1e-11)
+    exp = orc.convert_permutations_to_samples(arr, best, 2.0)
+    assert exp.shape == (225166, 3)
+    np.testing.assert_allclose(exp[:, 1:].mean(axis=0), g['ex00_grid_mu_AP'], rtol=1e-13)
+
+
+def test_example26_stored_rows(golden):
+    """Examples/Example26 stored multistart rows; model = Example26/simulation_model_00.py (same quadratic,
+    same data), prior from its runfile: mu [200,500], sigma [100,200]."""
+    g = golden("example00")
+    P = ex00()
+    pt, _ = orc.sim_quadratic(X00)
+    for key in ("ex26_perm_csv", "ex26_ms_csv"):
+        for r in g[key]:
+            np.testing.assert_allclose(orc.log_p_point(P, r[1:], pt), r[0], rtol=1e-12)
+
+
+def test_priors_and_bounds(golden):
+    g = golden("priors")
+    pt, bt = orc.sim_quadratic(X00)
+    P = ex00(mu=[200, 500], unc=[100, -1], upper_bounds=[None, 900], lower_bounds=[None, 100])
+    check_vals(P, pt, bt, g['unif_thetas'], g['unif_vals'])
+    assert orc.log_prior_point(P, [250, 500]) == -1.0439385332046727      # SURVEY 8c (z = 0.5)
+    assert orc.log_prior_point(P, [200, 900]) > -np.inf and orc.log_prior_point(P, [200, np.nextafter(900, 1e9)]) == -np.inf
+    P = ex00(mu=[200, 500], unc=[-1, -1], upper_bounds=[400, 900], lower_bounds=[0, 100])
+    check_vals(P, pt, bt, g['unif2_thetas'], g['unif2_vals'])
+    P = ex00(upper_bounds=[300, None], lower_bounds=[100, 0])
+    check_vals(P, pt, bt, g['bnd_thetas'], g['bnd_vals'])
+    P = ex00(mu=[1.0, 2.0], unc=[[1, .3], [.3, 4]])
+    assert orc.log_prior_point(P, [1.5, 1.0]) == -2.467189810186834
+    check_vals(P, pt, bt, g['covp_thetas'], g['covp_vals'], exact=False, rtol=1e-13)
+    for tag, sc in [("off", "off"), ("mu", "mu"), ("fix", 3.0)]:
+        check_vals(ex00(scaling_type=sc), pt, bt, g[f'scal_{tag}_thetas'], g[f'scal_{tag}_vals'],
+                   exact=False, rtol=1e-13)
+    P = ex00(simulation_uncertainties=[1e5, 5e4, 2e5])
+    check_vals(P, pt, bt, g['simunc_thetas'], g['simunc_vals'])
+
+
+def _check_vals_loose(P, sim_point, sim_batch, thetas, vals, rtol):
+    lp_b, pr_b, ll_b = orc.log_p_batch(P, thetas, sim_batch)
+    np.testing.assert_allclose(lp_b, vals[:, 0], rtol=rtol)
+    np.testing.assert_allclose(pr_b, vals[:, 1], rtol=rtol)
+    np.testing.assert_allclose(ll_b, vals[:, 2], rtol=rtol)
+    for i in range(0, len(thetas), 7):
+        np.testing.assert_allclose(orc.log_p_point(P, thetas[i], sim_point), vals[i, 0], rtol=rtol)
+
+
+@pytest.mark.parametrize("n", [1024, 96])
+def test_tpd_points(golden, n):
+    g = golden("tpd")
+    kBT, c1, c2 = orc.tpd2site_constants(n)
+    pt, bt = orc.sim_tpd2site(kBT, c1, c2)
+    P = orc.build_problem([41.5, 41.5, 13.0, 13.0, 0.1, 0.1], [20, 20, 13, 13, 0.1, 0.1],
+                          g[f'tpd{n}_y'], np.full(n, float(g[f'tpd{n}_sigma'])))
+    assert P.responses[0].per_value == (n > 100)
+    th, vals = g[f'tpd{n}_thetas'], g[f'tpd{n}_vals']
+    lp_b, pr_b, ll_b = orc.log_p_batch(P, th, bt)
+    assert np.array_equal(pr_b, vals[:, 1])
+    if n > 100:      # per-value path: same sequential order -> bit exact
+        assert np.array_equal(ll_b, vals[:, 2]) and np.array_equal(lp_b, vals[:, 0])
+        assert vals[0, 0] == -7571.424324564999      # SURVEY 8c known answer
+    else:
+        np.testing.assert_allclose(ll_b, vals[:, 2], rtol=1e-14)
+    assert orc.log_p_point(P, th[0], pt) == vals[0, 0]
+
+
+def test_multiresponse(golden):
+    g = golden("multiresponse")
+    for tag, n, full in [("mr_diag", 7, False), ("mr_full5", 5, True), ("mr_full50", 50, True), ("mr_diag40", 40, False)]:
+        Phi, y, unc = g[f'{tag}_Phi'], g[f'{tag}_y'], g[f'{tag}_unc']
+        pt, bt = orc.sim_linear(Phi)
+        P = orc.build_problem([0., 0., 0.], [2., 2., 3.], [y[:n], y[n:]], [unc[0], unc[1]])
+
+        def spt(th, pt=pt, n=n):
+            s = pt(th)
+            return [s[:n], s[n:]]
+
+        def sbt(th, bt=bt, n=n):
+            s = bt(th)
+            return [s[:, :n], s[:, n:]]
+        _check_vals_loose(P, spt, sbt, g[f'{tag}_thetas'], g[f'{tag}_vals'], rtol=1e-13 if not full else 1e-12)
+
+
+def test_uniform_multistart(golden):
+    g = golden("uniform_multistart")
+    k, n = 10, 64
+    Phi = orc.cos_basis(n, k)
+    pt, bt = orc.sim_linear(Phi)
+    P = orc.build_problem([0.0] * k, [1.0] * k, g['c5_y'], np.full(n, 0.1))
+    u01 = philox_np.sweep_uniforms(0, 0, 400, k)
+    assert np.array_equal(u01, g['c5_u01'])
+    th = orc.uniform_points(u01, 0.866, P.std_prior, np.zeros(k))
+    arr = g['c5_logP_theta']
+    assert np.array_equal(th, arr[:, 1:])
+    logp = orc.log_p_batch(P, th, bt)[0]
+    np.testing.assert_allclose(logp, arr[:, 0], rtol=1e-13)
+    idx, best = orc.first_max_np(logp)
+    assert np.array_equal(th[idx], g['c5_map_theta'])
+    w, _ = orc.permutation_weights(arr[:, 0], float(g['c5_map_logP']), 2.0)
+    st = orc.weighted_statistics(arr[:, 0], th, w)
+    np.testing.assert_allclose(st['mu_AP'], g['c5_mu_AP'], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(st['stdap'], g['c5_stdap'], rtol=1e-10, atol=1e-14)
+
+
+def test_mh_step_for_step_example00(golden):
+    g = golden("mh_example00")
+    P = ex00()
+    pt, bt = orc.sim_quadratic(X00)
+    deltas, us = g['mh00_deltas'], g['mh00_us']
+    z, u2 = philox_np.mh_draws(0, 0, np.arange(1, 1500), 2)
+    assert np.array_equal(u2, us) and np.array_equal(z * (np.sqrt(0.1) * np.array([100., 200.])), deltas)
+    res = orc.mh_chains_batch(P, np.array([[200., 500.]]), deltas[:, None, :], us[:, None], bt)
+    burn = 100
+    assert np.array_equal(res['samples'][burn:, 0], g['mh00_post_samples'])
+    assert np.array_equal(res['samples'][:burn, 0], g['mh00_burn_samples'])
+    assert np.array_equal(res['logP'][burn:, 0], g['mh00_post_logP'][:, 0])
+    assert np.array_equal(res['log_priors'][burn:, 0], g['mh00_post_log_priors'][:, 0])
+    assert np.array_equal(res['log_likelihoods'][burn:, 0], g['mh00_post_log_likelihoods'][:, 0])
+    lit = orc.mh_chain_point(P, [200., 500.], deltas[:300], us[:300], pt)
+    assert np.array_equal(lit['samples'], res['samples'][:301, 0])
+    assert np.array_equal(lit['accepted'], res['accepted'][:301, 0])
+    st = orc.post_burn_in_statistics(res['samples'][burn:, 0], res['logP'][burn:, 0])
+    assert np.array_equal(st['mu_AP'], g['mh00_mu_AP']) and np.array_equal(st['stdap'], g['mh00_stdap'])
+    assert st['map_logP'] == float(g['mh00_map_logP'])
+    assert np.array_equal(st['map_parameter_set'], g['mh00_map_theta'])
+    assert st['evidence'] == float(g['mh00_evidence'])
+    acc = res['accepted'][1:, 0].mean()
+    assert 0.1 < acc < 0.95
+
+
+def test_mh_step_for_step_tpd(golden):
+    g = golden("tpd")
+    kBT, c1, c2 = orc.tpd2site_constants(1024)
+    _, bt = orc.sim_tpd2site(kBT, c1, c2)
+    P = orc.build_problem([41.5, 41.5, 13.0, 13.0, 0.1, 0.1], [20, 20, 13, 13, 0.1, 0.1],
+                          g['tpd1024_y'], np.full(1024, float(g['tpd1024_sigma'])))
+    truth = np.array([[41.5, 45, 13, 13, 0.1, 0.1]])
+    res = orc.mh_chains_batch(P, truth, g['tpdmh_deltas'][:, None, :], g['tpdmh_us'][:, None], bt)
+    assert np.array_equal(res['samples'][:, 0], g['tpdmh_samples'])
+    assert np.array_equal(res['logP'][:, 0], g['tpdmh_logP'][:, 0])
+    assert 0.05 < res['accepted'][1:, 0].mean() < 0.95
+
+
+def test_ess_linear_gaussian_statistics():
+    """ESS restatement (parity unpinned): recovers the closed-form posterior of a linear-Gaussian model."""
+    rng = np.random.default_rng(3)
+    k, n = 4, 30
+    Phi = orc.cos_basis(n, k)
+    truth = rng.standard_normal(k)
+    y = Phi @ truth + 0.3 * rng.standard_normal(n)
+    P = orc.build_problem([0.] * k, [2.] * k, y, np.full(n, 0.3))
+    _, bt = orc.sim_linear(Phi)
+    mean, cov = orc.linear_gaussian_posterior(Phi, Phi / 0.09, y, 4.0)
+    start = 0.866 * 2.0 * (rng.random((16, k)) * 4 - 2)
+    chain, lp, neval, mu = orc.ess_run(lambda X: orc.log_p_batch(P, X, bt)[0], start, 600, rng)
+    s = chain[150:].reshape(-1, k)
+    se = np.sqrt(np.diag(cov) / (len(s) / 20.0))
+    assert np.all(np.abs(s.mean(axis=0) - mean) < 5 * se)
+    d = np.sqrt(np.diag(cov))
+    np.testing.assert_allclose(np.cov(s.T) / np.outer(d, d), cov / np.outer(d, d), atol=0.15)
