@@ -1,0 +1,273 @@
+/*
+ * peuqse_b200.h -- C ABI of the B200-native PEUQSE posterior-evaluation engine.
+ *
+ * Drop-in boundary for ONE hot path of the reference (AdityaSavara/PEUQSE): the fp64 log-posterior
+ * evaluation behind PEUQSE.parameter_estimation (PEUQSE/InverseProblem.py, "IP.py" below) and its three
+ * data-parallel drivers.  Each entry point names the reference code it replaces.  The reference is pure
+ * Python, so the "FFI" a maintainer adds is a ctypes binding; INTEGRATION.md shows it.
+ *
+ * Conventions
+ *   - every pointer named d_* is DEVICE memory owned by the caller (e.g. a torch tensor's data_ptr());
+ *     every pointer inside peuqse_problem_desc is HOST memory, copied at create time;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work is stream-ordered
+ *     and asynchronous unless stated; no entry point synchronises the device except peuqse_problem_create;
+ *   - return value: 0 = PEUQSE_OK, otherwise a PEUQSE_ERR_* code; peuqse_last_error() gives the text;
+ *   - numerical failure is a VALUE, never a trap: out-of-bounds parameters give logPrior = -inf
+ *     (IP.py:2760-2762), NaN simulated responses give logLikelihood = -inf (IP.py:2880-2882);
+ *   - one handle per device; calls on one handle must not run concurrently from several host threads.
+ */
+#ifndef PEUQSE_B200_H
+#define PEUQSE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PEUQSE_MAX_K 16          /* parameters */
+#define PEUQSE_MAX_RESP 8        /* response dimensions */
+
+enum {
+    PEUQSE_OK = 0,
+    PEUQSE_ERR_INVALID = 1,      /* bad argument / unsupported combination */
+    PEUQSE_ERR_CUDA = 2,         /* CUDA runtime error (text in peuqse_last_error) */
+    PEUQSE_ERR_NOMEM = 3
+};
+
+/* built-in simulation models ("simulateByInputParametersOnlyFunction", UserInput.py:38) */
+enum {
+    PEUQSE_MODEL_EXTERNAL = 0,   /* simulated responses are supplied by the caller (torch callable path) */
+    PEUQSE_MODEL_QUADRATIC = 1,  /* Examples/Example00/simulation_model_00.py:6-10: (x_j - th0)^2 + th1; const = x[n] */
+    PEUQSE_MODEL_TPD2SITE = 2,   /* rate law of Examples/Example01/tprmodel.py:20, prescribed coverages;
+                                    const = kBT[n], cov1[n], cov2[n]; theta = Ea1,Ea2,logA1,logA2,g1,g2 */
+    PEUQSE_MODEL_LINEAR = 3      /* sim_j = sum_d Phi[j][d]*th_d (d ascending); const = Phi[n][k] row-major */
+};
+
+/* likelihood evaluation mode of one response dimension (IP.py:2949-2979) */
+enum {
+    PEUQSE_RESP_MVN_DIAG = 0,    /* one logpdf, variances only (IP.py:2960, 1-D cov)            */
+    PEUQSE_RESP_PER_VALUE = 1,   /* n > responses_observed_max_covmat_size: IP.py:2969-2978      */
+    PEUQSE_RESP_MVN_FULL = 2     /* one logpdf with a full covariance matrix (IP.py:2960, 2-D)   */
+};
+
+/* prior mode (IP.py:2756-2794) */
+enum {
+    PEUQSE_PRIOR_NONE = 0,       /* every parameter uniform: logPrior = 0 inside the bounds (IP.py:2782-2783) */
+    PEUQSE_PRIOR_DIAG = 1,       /* whitening is a (signed) permutation: diagonal scaled covariance */
+    PEUQSE_PRIOR_DENSE = 2       /* covariance-matrix prior: dense whitening U (kp x kp)            */
+};
+
+/*
+ * The constants parameter_estimation.__init__ derives (IP.py:146-350), with scipy's per-call
+ * eigendecomposition (_PSD, scipy/stats/_multivariate.py:208-236) hoisted to set-up time by the host.
+ * Arrays in "eigen order" are ordered like the columns of scipy's whitening matrix U = u*sqrt(1/s)
+ * so that the kernels add the squared whitened deviations in the same order scipy does.
+ */
+typedef struct peuqse_problem_desc {
+    int32_t k;                   /* number of parameters, <= PEUQSE_MAX_K */
+    int32_t scaling_on;          /* 0: scaling_uncertainties_type == 'off' (IP.py:2763-2764) */
+    int32_t has_lb, has_ub;      /* bounds lists non-empty (IP.py:2797, 2801) */
+    const double* lb;            /* [k] lower bounds, -inf where None */
+    const double* ub;            /* [k] upper bounds, +inf where None */
+    const double* scale;         /* [k] scaling_uncertainties (IP.py:317-328) */
+    const double* mu_scaled;     /* [k] mu_prior_scaled (IP.py:333) */
+    int32_t prior_mode;          /* PEUQSE_PRIOR_* */
+    int32_t kp;                  /* number of Gaussian (non-uniform) parameters */
+    const int32_t* prior_gidx;   /* [kp] DIAG: parameter index feeding whitened column j (eigen order);
+                                         DENSE: parameter index of Gaussian parameter i */
+    const double* prior_w;       /* [kp] DIAG: |U[.,j]| in eigen order */
+    const double* prior_U;       /* [kp*kp] DENSE: row-major U, whitened_j = sum_i dev_i*U[i][j] */
+    double prior_c;              /* rank*log(2pi) + log_pdet */
+
+    int32_t n_resp;              /* response dimensions, <= PEUQSE_MAX_RESP */
+    int32_t n_total;             /* sum of resp_n */
+    const int32_t* resp_n;       /* [n_resp] */
+    const int32_t* resp_mode;    /* [n_resp] PEUQSE_RESP_* */
+    const double* resp_c;        /* [n_resp] MVN modes: rank*log(2pi) + log_pdet */
+    const double* y;             /* [n_total] observed values; MVN_DIAG responses in eigen order */
+    const double* w;             /* [n_total] MVN_DIAG: |U[.,j]| eigen order; PER_VALUE: sqrt(1/V_j) */
+    const double* cval;          /* [n_total] PER_VALUE: log(2pi) + ln V_j (else ignored) */
+    const int32_t* src;          /* [n_total] position of this entry in the caller's flat (natural order)
+                                              simulated-response vector (EXTERNAL model) */
+    const double* const* resp_U; /* [n_resp] MVN_FULL: row-major n_r x n_r whitening, else NULL */
+
+    int32_t model_id;            /* PEUQSE_MODEL_* */
+    int32_t n_model_const;       /* doubles in model_const */
+    const double* model_const;   /* per-observation constants, rows ordered like y (see enum) */
+} peuqse_problem_desc;
+
+typedef struct peuqse_problem peuqse_problem;   /* opaque; owns immutable device copies of the constants */
+
+const char* peuqse_last_error(void);
+int peuqse_version(void);
+/* device properties the host layer sizes grids with: out[0]=SM count, out[1]=max smem/block (opt-in), out[2]=cc major*10+minor */
+int peuqse_device_info(int32_t* out3);
+
+/* replaces: parameter_estimation.__init__ hand-off of constants (IP.py:38-438) */
+int peuqse_problem_create(const peuqse_problem_desc* desc, peuqse_problem** out);
+int peuqse_problem_destroy(peuqse_problem* p);
+
+/*
+ * replaces: getLogP / getLogPrior / getLogLikelihood called in a Python loop (IP.py:1647-1654, 2756-2794,
+ * 2850-2980) for a built-in model.  d_theta[B][k] row-major.  Outputs (each nullable): d_logp[B],
+ * d_logprior[B], d_loglik[B].  logP short-circuits to -inf where logPrior == -inf (IP.py:1649);
+ * d_loglik is evaluated for every row regardless (what the MH loop does, IP.py:2636-2639).
+ */
+int peuqse_logp_batch(const peuqse_problem* p, const double* d_theta, int64_t B,
+                      double* d_logp, double* d_logprior, double* d_loglik, void* stream);
+
+/*
+ * replaces: the same functions when the simulator is a user (torch) callable: the caller simulated
+ * d_sim[B][n_total] (responses concatenated in natural order) and the kernel does prior + likelihood.
+ * d_theta may be NULL when only d_loglik is wanted.  Full-covariance responses run the DMMA contraction.
+ */
+int peuqse_logp_from_sim(const peuqse_problem* p, const double* d_theta, const double* d_sim, int64_t B,
+                         double* d_logp, double* d_logprior, double* d_loglik, void* stream);
+
+/* simulate only (getSimulatedResponses, IP.py:2822-2848) for a built-in model: d_sim[B][n_total], natural order */
+int peuqse_simulate_batch(const peuqse_problem* p, const double* d_theta, int64_t B, double* d_sim, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Multistart sweeps: doMultiStart / doListOfPermutationsSearch (IP.py:1077-1117, 772-1074) over
+ * CombinationGeneratorModule.combinationGenerator's grid (CombinationGeneratorModule.py:40-81) or
+ * generateInitialPoints('uniform') (IP.py:706, 749).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct peuqse_sweep_spec {
+    int32_t kind;                /* 0 = grid, 1 = uniform (Philox) */
+    int32_t k;
+    double center[PEUQSE_MAX_K];
+    /* grid: point = center -/+ (interval*i) per axis, list order of combinationGenerator */
+    double interval[PEUQSE_MAX_K];
+    int64_t radii[PEUQSE_MAX_K];
+    /* uniform: theta = spread*(-2+4u)*std + center, u = Philox(seed, point index) */
+    double spread;
+    double std_prior[PEUQSE_MAX_K];
+    uint64_t seed;
+} peuqse_sweep_spec;
+
+/* per-launch result of pass 1 (lives in device memory, 16 bytes) */
+typedef struct peuqse_best {
+    double logp;                 /* highest logP in [first, first+count), -inf if none is > -inf */
+    int64_t index;               /* lowest global index attaining it (strict '>' in list order, IP.py:933), -1 if none */
+} peuqse_best;
+
+/*
+ * Pass 1: evaluate points first..first+count-1 of the sweep, keep the first strict maximum.
+ * d_logp (nullable): logP of every point, d_logp[i] for global index first+i (the first column of
+ * permutations_MAP_logP_and_parameters_values, IP.py:947).  d_best: one peuqse_best.
+ * d_work: scratch of peuqse_sweep_work_bytes() bytes.
+ */
+int64_t peuqse_sweep_work_bytes(void);
+int peuqse_sweep_pass1(const peuqse_problem* p, const peuqse_sweep_spec* spec, int64_t first, int64_t count,
+                       double* d_logp, peuqse_best* d_best, void* d_work, void* stream);
+
+/* decode points of a sweep without evaluating them: d_theta[count][k] (listOfPermutations, IP.py:776) */
+int peuqse_sweep_points(const peuqse_sweep_spec* spec, int64_t first, int64_t count, double* d_theta, void* stream);
+
+/*
+ * Pass 2: convertPermutationsToSamples + calculatePostBurnInStatistics as weighted reductions
+ * (IP.py:3463-3491, 1923-1931).  weight_g = (int)exp(logP_g - threshold) for logP_g > threshold.
+ * d_logp: pass-1 logP (nullable: recompute).  d_acc: PEUQSE_ACC_DOUBLES(k) doubles, see layout below;
+ * sums are ACCUMULATED into d_acc (zero it first; min/max slots start at +/-inf).
+ * d_keep_index/d_keep_logp (nullable, capacity keep_capacity): compacted list of retained points,
+ * unordered; d_keep_count: one int64 (running count; may exceed the capacity, extra rows are dropped).
+ */
+#define PEUQSE_ACC_W 0                                  /* sum w                                   */
+#define PEUQSE_ACC_WEXP 1                               /* sum w*exp(logP)                         */
+#define PEUQSE_ACC_NKEPT 2                              /* number of retained points               */
+#define PEUQSE_ACC_S1 3                                 /* [k]   sum w*(th-center)                 */
+#define PEUQSE_ACC_S2(k) (3 + (k))                      /* [k*k] sum w*(th-center)(th-center)^T    */
+#define PEUQSE_ACC_MIN(k) (3 + (k) + (k) * (k))         /* [k]   min retained theta                */
+#define PEUQSE_ACC_MAX(k) (3 + 2 * (k) + (k) * (k))     /* [k]   max retained theta                */
+#define PEUQSE_ACC_DOUBLES(k) (3 + 3 * (k) + (k) * (k))
+int peuqse_sweep_pass2(const peuqse_problem* p, const peuqse_sweep_spec* spec, int64_t first, int64_t count,
+                       const double* d_logp, double threshold, double* d_acc,
+                       int64_t* d_keep_index, double* d_keep_logp, int64_t keep_capacity, int64_t* d_keep_count,
+                       void* d_work, void* stream);
+
+/*
+ * Pass 3: weighted marginal histograms of the retained points (plotting_functions.py:135 -> ax.hist ->
+ * np.histogram with equal bins over [min, max] of the retained values, last bin closed).
+ * d_edges[k][nbins+1]: bin edges (np.linspace(lo_d, hi_d, nbins+1)); d_hist[k][nbins]: integer weight
+ * sums, accumulated (zero it first).
+ */
+int peuqse_sweep_hist(const peuqse_problem* p, const peuqse_sweep_spec* spec, int64_t first, int64_t count,
+                      const double* d_logp, double threshold, const double* d_edges, int32_t nbins,
+                      uint64_t* d_hist, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Metropolis-Hastings: doMetropolisHastings (IP.py:2563-2754), C independent chains
+ * (mcmc_parallel_sampling, IP.py:1282-1319) advanced by one persistent kernel.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct peuqse_mh_spec {
+    int64_t n_chains;
+    int64_t n_steps;             /* rows produced per chain INCLUDING row 0 = start point (mcmc_length, IP.py:2606-2626) */
+    int64_t burn_in;             /* rows [burn_in, n_steps) enter the statistics (IP.py:2718) */
+    int64_t first_step;          /* draws for row i use Philox step index first_step + i (continue sampling) */
+    int64_t chain_offset;        /* global index of chain 0 of this launch (multi-GPU sharding) */
+    uint64_t seed;
+    double modulate;             /* mcmc_modulate_accept_probability (0 = off, IP.py:2644-2649) */
+    int32_t k;
+    int32_t thin;                /* store every thin-th row (1 = all) */
+    double step_chol[PEUQSE_MAX_K * PEUQSE_MAX_K]; /* row-major lower Cholesky factor of Q_covmat*step (IP.py:2630) */
+} peuqse_mh_spec;
+
+/* per-chain statistics block written by the kernel: PEUQSE_MH_STAT_DOUBLES(k) doubles per chain */
+#define PEUQSE_MH_STAT_NACC 0                           /* accepted proposals                      */
+#define PEUQSE_MH_STAT_MAPLOGP 1                        /* highest logP among rows >= burn_in      */
+#define PEUQSE_MH_STAT_MAPROW 2                         /* first row attaining it                  */
+#define PEUQSE_MH_STAT_LASTLOGP 3
+#define PEUQSE_MH_STAT_SUMEXP 4                         /* sum exp(logP) over rows >= burn_in      */
+#define PEUQSE_MH_STAT_MAPTHETA 5                       /* [k]                                     */
+#define PEUQSE_MH_STAT_LAST(k) (5 + (k))                /* [k] last state                          */
+#define PEUQSE_MH_STAT_S1(k) (5 + 2 * (k))              /* [k] sum (th - th0) over rows >= burn_in */
+#define PEUQSE_MH_STAT_S2(k) (5 + 3 * (k))              /* [k*k] sum (th-th0)(th-th0)^T            */
+#define PEUQSE_MH_STAT_DOUBLES(k) (5 + 3 * (k) + (k) * (k))
+
+/*
+ * d_theta0[C][k]: start points.  Outputs, all nullable except d_stats:
+ *   d_samples[R][C][k], d_logp[R][C], d_logprior[R][C], d_loglik[R][C] with R = ceil(n_steps/thin) stored rows
+ *   (layout = discrete_chains_post_burn_in_samples (nsteps, nchains, k), IP.py:2719);
+ *   d_deltas[n_steps-1][C][k], d_us[n_steps-1][C]: the proposal increments and accept uniforms actually
+ *   used (for feeding the reference the same draws); d_stats[C][PEUQSE_MH_STAT_DOUBLES(k)].
+ */
+int peuqse_mh_run(const peuqse_problem* p, const peuqse_mh_spec* spec, const double* d_theta0,
+                  double* d_samples, double* d_logp, double* d_logprior, double* d_loglik,
+                  double* d_deltas, double* d_us, double* d_stats, void* stream);
+
+/* raw generator access (tests): d_out[count][4] uint32 Philox4x32-10 blocks for (seed, stream, idx=first+i, block) */
+int peuqse_philox_blocks(uint64_t seed, uint32_t rng_stream, int64_t first, int64_t count, uint32_t block,
+                         uint32_t* d_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Ensemble slice sampling: doEnsembleSliceSampling -> zeus.EnsembleSampler.run_mcmc (IP.py:2362-2547,
+ * zeus call sites 2495-2518).  One ensemble iteration = two half-ensemble sweeps, each a sequence of
+ * batched stepping-out / shrinking rounds whose log-posteriors are evaluated by one kernel launch.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct peuqse_ess_spec {
+    int64_t n_walkers;           /* even */
+    int64_t n_iters;
+    int64_t first_iter;          /* Philox iteration offset (continue sampling) */
+    uint64_t seed;
+    double mu0;                  /* initial scale factor (zeus default 1.0) */
+    int32_t tune;                /* adapt mu during the run */
+    int32_t max_rounds;          /* stepping-out / shrink rounds bound (mcmc_maxiter) */
+    int32_t k;
+    int32_t reserved;
+} peuqse_ess_spec;
+
+/*
+ * d_x[W][k], d_logp_x[W]: in = start positions and their logP, out = final positions.
+ * d_chain[n_iters][W][k], d_chain_logp[n_iters][W] (nullable).  d_info[4]: neval, final mu, n_expand, n_contract.
+ * d_work: peuqse_ess_work_bytes(W,k).  Built-in models only (EXTERNAL: drive the rounds from the host
+ * with peuqse_logp_from_sim).  Returns PEUQSE_ERR_INVALID if a start point has non-finite logP.
+ */
+int64_t peuqse_ess_work_bytes(int64_t n_walkers, int32_t k);
+int peuqse_ess_run(const peuqse_problem* p, const peuqse_ess_spec* spec, double* d_x, double* d_logp_x,
+                   double* d_chain, double* d_chain_logp, double* d_info, void* d_work, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PEUQSE_B200_H */

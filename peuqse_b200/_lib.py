@@ -1,0 +1,145 @@
+"""ctypes binding of libpeuqse_b200.so (the C ABI declared in include/peuqse_b200.h).
+
+There is no CPU fallback: if the shared library is missing or a call fails, an exception is raised.
+PyTorch is used by the callers only for device memory and streams; no torch type crosses this boundary.
+"""
+import ctypes as C
+import os
+
+MAX_K = 16
+MAX_RESP = 8
+
+MODEL_EXTERNAL, MODEL_QUADRATIC, MODEL_TPD2SITE, MODEL_LINEAR = 0, 1, 2, 3
+RESP_MVN_DIAG, RESP_PER_VALUE, RESP_MVN_FULL = 0, 1, 2
+PRIOR_NONE, PRIOR_DIAG, PRIOR_DENSE = 0, 1, 2
+
+c_double_p = C.POINTER(C.c_double)
+c_int32_p = C.POINTER(C.c_int32)
+
+
+class ProblemDesc(C.Structure):
+    _fields_ = [
+        ("k", C.c_int32), ("scaling_on", C.c_int32), ("has_lb", C.c_int32), ("has_ub", C.c_int32),
+        ("lb", c_double_p), ("ub", c_double_p), ("scale", c_double_p), ("mu_scaled", c_double_p),
+        ("prior_mode", C.c_int32), ("kp", C.c_int32),
+        ("prior_gidx", c_int32_p), ("prior_w", c_double_p), ("prior_U", c_double_p), ("prior_c", C.c_double),
+        ("n_resp", C.c_int32), ("n_total", C.c_int32),
+        ("resp_n", c_int32_p), ("resp_mode", c_int32_p), ("resp_c", c_double_p),
+        ("y", c_double_p), ("w", c_double_p), ("cval", c_double_p), ("src", c_int32_p),
+        ("resp_U", C.POINTER(c_double_p)),
+        ("model_id", C.c_int32), ("n_model_const", C.c_int32), ("model_const", c_double_p),
+    ]
+
+
+class SweepSpec(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("k", C.c_int32),
+        ("center", C.c_double * MAX_K), ("interval", C.c_double * MAX_K), ("radii", C.c_int64 * MAX_K),
+        ("spread", C.c_double), ("std_prior", C.c_double * MAX_K), ("seed", C.c_uint64),
+    ]
+
+
+class Best(C.Structure):
+    _fields_ = [("logp", C.c_double), ("index", C.c_int64)]
+
+
+class MHSpec(C.Structure):
+    _fields_ = [
+        ("n_chains", C.c_int64), ("n_steps", C.c_int64), ("burn_in", C.c_int64), ("first_step", C.c_int64),
+        ("chain_offset", C.c_int64), ("seed", C.c_uint64), ("modulate", C.c_double),
+        ("k", C.c_int32), ("thin", C.c_int32), ("step_chol", C.c_double * (MAX_K * MAX_K)),
+    ]
+
+
+class ESSSpec(C.Structure):
+    _fields_ = [
+        ("n_walkers", C.c_int64), ("n_iters", C.c_int64), ("first_iter", C.c_int64), ("seed", C.c_uint64),
+        ("mu0", C.c_double), ("tune", C.c_int32), ("max_rounds", C.c_int32), ("k", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+def acc_layout(k):
+    """Offsets inside the pass-2 accumulator (PEUQSE_ACC_* macros)."""
+    return dict(W=0, WEXP=1, NKEPT=2, S1=3, S2=3 + k, MIN=3 + k + k * k, MAX=3 + 2 * k + k * k,
+                SIZE=3 + 3 * k + k * k)
+
+
+def mh_stat_layout(k):
+    """Offsets inside one chain's statistics block (PEUQSE_MH_STAT_* macros)."""
+    return dict(NACC=0, MAPLOGP=1, MAPROW=2, LASTLOGP=3, SUMEXP=4, MAPTHETA=5, LAST=5 + k, S1=5 + 2 * k,
+                S2=5 + 3 * k, SIZE=5 + 3 * k + k * k)
+
+
+EXPORTS = [
+    "peuqse_last_error", "peuqse_version", "peuqse_device_info", "peuqse_problem_create", "peuqse_problem_destroy",
+    "peuqse_logp_batch", "peuqse_logp_from_sim", "peuqse_simulate_batch", "peuqse_sweep_work_bytes",
+    "peuqse_sweep_pass1", "peuqse_sweep_points", "peuqse_sweep_pass2", "peuqse_sweep_hist", "peuqse_mh_run",
+    "peuqse_philox_blocks", "peuqse_ess_work_bytes", "peuqse_ess_run",
+]
+
+_lib = None
+
+
+class PeuqseError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpeuqse_b200.so")
+
+
+def load():
+    """Load the CUDA library (once). Raises if it is not built: there is no other implementation."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise PeuqseError(f"{path} not found: build it with ./build.sh (python -c 'import __graft_entry__ as g; g.build()'). "
+                          "peuqse_b200 has no CPU fallback.")
+    L = C.CDLL(path)
+    vp, i64, i32, u64, u32, dbl = C.c_void_p, C.c_int64, C.c_int32, C.c_uint64, C.c_uint32, C.c_double
+    L.peuqse_last_error.restype = C.c_char_p
+    L.peuqse_last_error.argtypes = []
+    L.peuqse_version.restype = C.c_int
+    L.peuqse_device_info.argtypes = [c_int32_p]
+    L.peuqse_problem_create.argtypes = [C.POINTER(ProblemDesc), C.POINTER(vp)]
+    L.peuqse_problem_destroy.argtypes = [vp]
+    L.peuqse_logp_batch.argtypes = [vp, vp, i64, vp, vp, vp, vp]
+    L.peuqse_logp_from_sim.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp]
+    L.peuqse_simulate_batch.argtypes = [vp, vp, i64, vp, vp]
+    L.peuqse_sweep_work_bytes.restype = i64
+    L.peuqse_sweep_work_bytes.argtypes = []
+    L.peuqse_sweep_pass1.argtypes = [vp, C.POINTER(SweepSpec), i64, i64, vp, vp, vp, vp]
+    L.peuqse_sweep_points.argtypes = [C.POINTER(SweepSpec), i64, i64, vp, vp]
+    L.peuqse_sweep_pass2.argtypes = [vp, C.POINTER(SweepSpec), i64, i64, vp, dbl, vp, vp, vp, i64, vp, vp, vp]
+    L.peuqse_sweep_hist.argtypes = [vp, C.POINTER(SweepSpec), i64, i64, vp, dbl, vp, i32, vp, vp]
+    L.peuqse_mh_run.argtypes = [vp, C.POINTER(MHSpec), vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.peuqse_philox_blocks.argtypes = [u64, u32, i64, i64, u32, vp, vp]
+    L.peuqse_ess_work_bytes.restype = i64
+    L.peuqse_ess_work_bytes.argtypes = [i64, i32]
+    L.peuqse_ess_run.argtypes = [vp, C.POINTER(ESSSpec), vp, vp, vp, vp, vp, vp, vp]
+    for name in EXPORTS:
+        if name not in ("peuqse_last_error", "peuqse_version", "peuqse_sweep_work_bytes", "peuqse_ess_work_bytes"):
+            getattr(L, name).restype = C.c_int
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().peuqse_last_error().decode(errors="replace")
+        raise PeuqseError(f"libpeuqse_b200 error {rc}: {msg}")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "device tensors must be contiguous CUDA tensors"
+    return C.c_void_p(t.data_ptr())
+
+
+def current_stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,188 @@
+// Batched log-posterior from parameter vectors in memory (kernel K2 of SURVEY section 2):
+// replaces getLogP / getLogPrior / getLogLikelihood called once per point from Python loops
+// (IP.py:1647-1654, 2756-2794, 2850-2980).
+#include "common.cuh"
+#include "eval.cuh"
+#include "launch.cuh"
+
+// thread shape: one point per thread, theta rows read with stride k (each 128 B line is fully used by
+// neighbouring threads and stays in L1), outputs written coalesced.
+template <int MODEL, int KT>
+__global__ void __launch_bounds__(256) k_logp_thread(const __grid_constant__ DevProblem P, const double* __restrict__ theta,
+                                                     const double* __restrict__ sim, long long B,
+                                                     double* __restrict__ logp, double* __restrict__ lprior,
+                                                     double* __restrict__ llik, int use_smem) {
+    extern __shared__ double smem[];
+    const ObsView O = stage_obs(P, smem, use_smem);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += stride) {
+        double th[KT];
+#pragma unroll
+        for (int d = 0; d < KT; ++d) th[d] = (theta != nullptr && d < P.k) ? theta[i * P.k + d] : 0.0;
+        const double lp = theta ? eval_prior<KT>(P, th) : 0.0;
+        const double ll = eval_loglik_thread<MODEL, KT>(P, O, th, sim ? sim + i * P.n_total : nullptr);
+        if (logp) logp[i] = combine_logp(lp, ll);
+        if (lprior) lprior[i] = lp;
+        if (llik) llik[i] = ll;
+    }
+}
+
+// warp shape: one point per warp
+template <int MODEL, int KT>
+__global__ void __launch_bounds__(256) k_logp_warp(const __grid_constant__ DevProblem P, const double* __restrict__ theta,
+                                                   const double* __restrict__ sim, long long B,
+                                                   double* __restrict__ logp, double* __restrict__ lprior,
+                                                   double* __restrict__ llik, int use_smem) {
+    extern __shared__ double smem[];
+    const ObsView O = stage_obs(P, smem, use_smem);
+    const int lane = threadIdx.x & 31;
+    const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long i = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < B; i += wstride) {
+        double th[KT];
+#pragma unroll
+        for (int d = 0; d < KT; ++d) th[d] = (theta != nullptr && d < P.k) ? theta[i * P.k + d] : 0.0;
+        const double lp = theta ? eval_prior<KT>(P, th) : 0.0;
+        const double ll = eval_loglik_warp<MODEL, KT>(P, O, th, sim ? sim + i * P.n_total : nullptr, lane);
+        if (lane == 0) {
+            if (logp) logp[i] = combine_logp(lp, ll);
+            if (lprior) lprior[i] = lp;
+            if (llik) llik[i] = ll;
+        }
+    }
+}
+
+// getSimulatedResponses (IP.py:2822-2848): d_sim[B][n_total] in natural order
+template <int MODEL, int KT>
+__global__ void __launch_bounds__(256) k_simulate(const __grid_constant__ DevProblem P, const double* __restrict__ theta,
+                                                  long long B, double* __restrict__ sim, int use_smem) {
+    extern __shared__ double smem[];
+    const ObsView O = stage_obs(P, smem, use_smem);
+    const long long total = B * P.n_total;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const long long i = e / P.n_total;
+        const int j = (int)(e - i * P.n_total);
+        double th[KT];
+#pragma unroll
+        for (int d = 0; d < KT; ++d) th[d] = (d < P.k) ? theta[i * P.k + d] : 0.0;
+        sim[i * P.n_total + P.src[j]] = Sim<MODEL, KT>::at(P, O, th, nullptr, j);
+    }
+}
+
+namespace {
+
+template <int MODEL, int KT>
+int launch_logp(const peuqse_problem* p, const double* th, const double* sim, long long B, double* logp, double* lpr,
+                double* llk, cudaStream_t st) {
+    const bool warp_shape = p->d.n_total > PQ_THREAD_SHAPE_MAX_N;
+    int use_smem;
+    const size_t smem = pq_pick_smem(p, &use_smem);
+    if (warp_shape) {
+        auto kern = k_logp_warp<MODEL, KT>;
+        PQ_CUDA_OK(pq_allow_smem((const void*)kern, smem));
+        const long long blocks = (B + 7) / 8;
+        const int grid = (int)std::min<long long>(blocks, (long long)p->sm_count * 8);
+        kern<<<grid, 256, smem, st>>>(p->d, th, sim, B, logp, lpr, llk, use_smem);
+    } else {
+        auto kern = k_logp_thread<MODEL, KT>;
+        PQ_CUDA_OK(pq_allow_smem((const void*)kern, smem));
+        const long long blocks = (B + 255) / 256;
+        const int grid = (int)std::min<long long>(blocks, (long long)p->sm_count * 8);
+        kern<<<grid, 256, smem, st>>>(p->d, th, sim, B, logp, lpr, llk, use_smem);
+    }
+    PQ_CUDA_OK(cudaGetLastError());
+    return PEUQSE_OK;
+}
+
+template <int MODEL, int KT>
+int launch_sim(const peuqse_problem* p, const double* th, long long B, double* sim, cudaStream_t st) {
+    int use_smem;
+    const size_t smem = pq_pick_smem(p, &use_smem);
+    auto kern = k_simulate<MODEL, KT>;
+    PQ_CUDA_OK(pq_allow_smem((const void*)kern, smem));
+    const long long blocks = (B * p->d.n_total + 255) / 256;
+    const int grid = (int)std::min<long long>(blocks, (long long)p->sm_count * 8);
+    kern<<<grid, 256, smem, st>>>(p->d, th, B, sim, use_smem);
+    PQ_CUDA_OK(cudaGetLastError());
+    return PEUQSE_OK;
+}
+
+}  // namespace
+
+// prior + diagonal / per-value responses of caller-supplied simulated rows (full-covariance responses skipped)
+int pq_logp_external(const peuqse_problem* p, const double* th, const double* sim, long long B, double* logp, double* lpr,
+                     double* llk, cudaStream_t st) {
+    const int kb = pq_k_bucket(p->d.k);
+#define PQ_LOGP_EXT2(KT, ...) return launch_logp<PEUQSE_MODEL_EXTERNAL, KT>(p, th, sim, B, logp, lpr, llk, st)
+    PQ_DISPATCH_K(kb, PQ_LOGP_EXT2, 0)
+#undef PQ_LOGP_EXT2
+    return PEUQSE_OK;
+}
+
+int pq_fullcov_logp(const peuqse_problem* p, const double* d_theta, const double* d_sim, long long B, double* d_logp,
+                    double* d_logprior, double* d_loglik, cudaStream_t st);
+
+extern "C" int peuqse_simulate_batch(const peuqse_problem* p, const double* d_theta, int64_t B, double* d_sim,
+                                     void* stream) {
+    if (!p || !d_theta || !d_sim || B < 0) return pq_set_error(PEUQSE_ERR_INVALID, "bad argument");
+    if (B == 0) return PEUQSE_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int kb = pq_k_bucket(p->d.k);
+    switch (p->d.model_id) {
+        case PEUQSE_MODEL_QUADRATIC: return launch_sim<PEUQSE_MODEL_QUADRATIC, 2>(p, d_theta, B, d_sim, st);
+        case PEUQSE_MODEL_TPD2SITE: return launch_sim<PEUQSE_MODEL_TPD2SITE, 6>(p, d_theta, B, d_sim, st);
+        case PEUQSE_MODEL_LINEAR:
+#define PQ_SIM_LIN(KT, ...) return launch_sim<PEUQSE_MODEL_LINEAR, KT>(p, d_theta, B, d_sim, st)
+            PQ_DISPATCH_K(kb, PQ_SIM_LIN, 0)
+#undef PQ_SIM_LIN
+            break;
+        default: break;
+    }
+    return pq_set_error(PEUQSE_ERR_INVALID, "simulate_batch needs a built-in model");
+}
+
+extern "C" int peuqse_logp_batch(const peuqse_problem* p, const double* d_theta, int64_t B, double* d_logp,
+                                 double* d_logprior, double* d_loglik, void* stream) {
+    if (!p || !d_theta || B < 0) return pq_set_error(PEUQSE_ERR_INVALID, "bad argument");
+    if (B == 0) return PEUQSE_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p->d.model_id == PEUQSE_MODEL_EXTERNAL)
+        return pq_set_error(PEUQSE_ERR_INVALID, "logp_batch needs a built-in model; use peuqse_logp_from_sim");
+    if (p->d.any_full) {
+        // built-in simulate -> full-covariance contraction on the simulated block
+        double* sim = nullptr;
+        PQ_CUDA_OK(cudaMallocAsync((void**)&sim, (size_t)B * p->d.n_total * sizeof(double), st));
+        int rc = peuqse_simulate_batch(p, d_theta, B, sim, stream);
+        if (rc == PEUQSE_OK) rc = pq_fullcov_logp(p, d_theta, sim, B, d_logp, d_logprior, d_loglik, st);
+        cudaFreeAsync(sim, st);
+        return rc;
+    }
+    const int kb = pq_k_bucket(p->d.k);
+    switch (p->d.model_id) {
+        case PEUQSE_MODEL_QUADRATIC:
+            return launch_logp<PEUQSE_MODEL_QUADRATIC, 2>(p, d_theta, nullptr, B, d_logp, d_logprior, d_loglik, st);
+        case PEUQSE_MODEL_TPD2SITE:
+            return launch_logp<PEUQSE_MODEL_TPD2SITE, 6>(p, d_theta, nullptr, B, d_logp, d_logprior, d_loglik, st);
+        case PEUQSE_MODEL_LINEAR:
+#define PQ_LOGP_LIN(KT, ...) return launch_logp<PEUQSE_MODEL_LINEAR, KT>(p, d_theta, nullptr, B, d_logp, d_logprior, d_loglik, st)
+            PQ_DISPATCH_K(kb, PQ_LOGP_LIN, 0)
+#undef PQ_LOGP_LIN
+            break;
+        default: break;
+    }
+    return pq_set_error(PEUQSE_ERR_INVALID, "unknown model");
+}
+
+extern "C" int peuqse_logp_from_sim(const peuqse_problem* p, const double* d_theta, const double* d_sim, int64_t B,
+                                    double* d_logp, double* d_logprior, double* d_loglik, void* stream) {
+    if (!p || !d_sim || B < 0) return pq_set_error(PEUQSE_ERR_INVALID, "bad argument");
+    if (!d_theta && (d_logp || d_logprior)) return pq_set_error(PEUQSE_ERR_INVALID, "logp/logprior need d_theta");
+    if (B == 0) return PEUQSE_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p->d.any_full) return pq_fullcov_logp(p, d_theta, d_sim, B, d_logp, d_logprior, d_loglik, st);
+    const int kb = pq_k_bucket(p->d.k);
+#define PQ_LOGP_EXT(KT, ...) return launch_logp<PEUQSE_MODEL_EXTERNAL, KT>(p, d_theta, d_sim, B, d_logp, d_logprior, d_loglik, st)
+    PQ_DISPATCH_K(kb, PQ_LOGP_EXT, 0)
+#undef PQ_LOGP_EXT
+    return PEUQSE_OK;
+}

@@ -1,0 +1,278 @@
+// Persistent Metropolis-Hastings (kernel K3 of SURVEY section 2): every chain lives in registers for the
+// whole run; proposal draws come from Philox keyed on (seed, chain, step), so a chain's trajectory does not
+// depend on how chains are mapped to threads or GPUs.
+// Replaces doMetropolisHastings' Python loop (IP.py:2626-2675): proposal = theta + N(0, Q*step) (2630),
+// log_accept = (ll_p + lp_p) - (ll_c + lp_c) (2641), optional 1/N flattening (2644-2649),
+// accept iff log_accept > log(u) (2650-2652).  The reference re-simulates the current point each step
+// (2638-2639); re-evaluating an unchanged point reproduces the same doubles, so the cached value is used.
+#include "common.cuh"
+#include "eval.cuh"
+#include "launch.cuh"
+#include "philox.cuh"
+
+struct DevMH {
+    long long n_chains, n_steps, burn_in, first_step, chain_offset;
+    unsigned long long seed;
+    double modulate;
+    int k, thin, chol_diag, pad;
+    double chol[PQ_MAXK * PQ_MAXK];
+};
+
+struct MHOut {
+    double* samples;
+    double* logp;
+    double* lprior;
+    double* llik;
+    double* deltas;
+    double* us;
+    double* stats;
+};
+
+// per-chain running statistics (rows >= burn_in)
+template <int KT>
+struct ChainStats {
+    double nacc, maplogp, maprow, sumexp;
+    double maptheta[KT], s1[KT], s2[KT * (KT + 1) / 2];
+    __device__ __forceinline__ void init() {
+        nacc = 0.0; maplogp = pq_neg_inf(); maprow = -1.0; sumexp = 0.0;
+#pragma unroll
+        for (int d = 0; d < KT; ++d) { maptheta[d] = 0.0; s1[d] = 0.0; }
+#pragma unroll
+        for (int e = 0; e < KT * (KT + 1) / 2; ++e) s2[e] = 0.0;
+    }
+    __device__ __forceinline__ void add_row(int k, long long row, const double (&th)[KT], const double (&th0)[KT], double lp) {
+        if (lp > maplogp) {                                    // first maximum (list.index of max, IP.py:1925-1927)
+            maplogp = lp; maprow = (double)row;
+#pragma unroll
+            for (int d = 0; d < KT; ++d) maptheta[d] = th[d];
+        }
+        sumexp += exp(lp);
+        int e = 0;
+#pragma unroll
+        for (int d = 0; d < KT; ++d) {
+            const double dd = th[d] - th0[d];
+            if (d < k) s1[d] += dd;
+#pragma unroll
+            for (int d2 = d; d2 < KT; ++d2) {
+                if (d < k && d2 < k) s2[e] = fma(dd, th[d2] - th0[d2], s2[e]);
+                ++e;
+            }
+        }
+    }
+    __device__ void store(int k, double* out, const double (&th)[KT], double lastlp) const {
+        out[PEUQSE_MH_STAT_NACC] = nacc;
+        out[PEUQSE_MH_STAT_MAPLOGP] = maplogp;
+        out[PEUQSE_MH_STAT_MAPROW] = maprow;
+        out[PEUQSE_MH_STAT_LASTLOGP] = lastlp;
+        out[PEUQSE_MH_STAT_SUMEXP] = sumexp;
+        int e = 0;
+#pragma unroll
+        for (int d = 0; d < KT; ++d) {
+            if (d < k) {
+                out[PEUQSE_MH_STAT_MAPTHETA + d] = maptheta[d];
+                out[PEUQSE_MH_STAT_LAST(k) + d] = th[d];
+                out[PEUQSE_MH_STAT_S1(k) + d] = s1[d];
+            }
+#pragma unroll
+            for (int d2 = d; d2 < KT; ++d2) {
+                if (d < k && d2 < k) {
+                    out[PEUQSE_MH_STAT_S2(k) + d * k + d2] = s2[e];
+                    out[PEUQSE_MH_STAT_S2(k) + d2 * k + d] = s2[e];
+                }
+                ++e;
+            }
+        }
+    }
+};
+
+// proposal increment delta = L z (L lower-triangular Cholesky factor of Q_covmat*step, row-major)
+template <int KT>
+__device__ __forceinline__ void make_delta(const DevMH& M, const double (&z)[KT], double (&delta)[KT]) {
+#pragma unroll
+    for (int d = 0; d < KT; ++d) {
+        double a = 0.0;
+        if (d < M.k) {
+            if (M.chol_diag) {
+                a = M.chol[d * M.k + d] * z[d];
+            } else {
+#pragma unroll
+                for (int e = 0; e < KT; ++e)
+                    if (e <= d) a = fma(M.chol[d * M.k + e], z[e], a);
+            }
+        }
+        delta[d] = a;
+    }
+}
+
+// draws for (chain, step): normals from blocks 8*step + j, accept uniform from block 8*step + 7
+template <int KT>
+__device__ __forceinline__ void draws_thread(const DevMH& M, unsigned long long chain, unsigned long long step,
+                                             double (&z)[KT], double& u) {
+#pragma unroll
+    for (int b = 0; b < (KT + 1) / 2; ++b) {
+        double z0 = 0.0, z1 = 0.0;
+        if (2 * b < M.k) philox_normal_pair(philox_block(M.seed, PQ_STREAM_MH, chain, (uint32_t)(8ULL * step + b)), z0, z1);
+        z[2 * b] = z0;
+        if (2 * b + 1 < KT) z[2 * b + 1] = z1;
+    }
+    const Philox4 r = philox_block(M.seed, PQ_STREAM_MH, chain, (uint32_t)(8ULL * step + 7ULL));
+    u = philox_u53(r.x, r.y);
+}
+
+// warp version: lane b < 7 makes normal pair b, lane 7 the uniform; everything is then broadcast
+template <int KT>
+__device__ __forceinline__ void draws_warp(const DevMH& M, unsigned long long chain, unsigned long long step, int lane,
+                                           double (&z)[KT], double& u) {
+    double a = 0.0, b2 = 0.0;
+    if (lane < 7) {
+        if (2 * lane < M.k) philox_normal_pair(philox_block(M.seed, PQ_STREAM_MH, chain, (uint32_t)(8ULL * step + lane)), a, b2);
+    } else if (lane == 7) {
+        const Philox4 r = philox_block(M.seed, PQ_STREAM_MH, chain, (uint32_t)(8ULL * step + 7ULL));
+        a = philox_u53(r.x, r.y);
+    }
+#pragma unroll
+    for (int j = 0; j < (KT + 1) / 2; ++j) {
+        z[2 * j] = __shfl_sync(0xffffffffu, a, j);
+        const double zb = __shfl_sync(0xffffffffu, b2, j);
+        if (2 * j + 1 < KT) z[2 * j + 1] = zb;
+    }
+    u = __shfl_sync(0xffffffffu, a, 7);
+}
+
+template <int MODEL, int KT, bool WARP>
+__global__ void __launch_bounds__(WARP ? 256 : 128) k_mh(const __grid_constant__ DevProblem P, const __grid_constant__ DevMH M,
+                                                         const double* __restrict__ theta0, const MHOut out, int use_smem) {
+    extern __shared__ double smem[];
+    const ObsView O = stage_obs(P, smem, use_smem);
+    const int lane = threadIdx.x & 31;
+    const long long c = WARP ? ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5))
+                             : ((long long)blockIdx.x * blockDim.x + threadIdx.x);
+    if (c >= M.n_chains) return;
+    const bool writer = WARP ? (lane == 0) : true;
+    const int k = P.k;
+    const long long C = M.n_chains;
+    const unsigned long long gchain = (unsigned long long)(M.chain_offset + c);
+
+    double th[KT], th0[KT];
+#pragma unroll
+    for (int d = 0; d < KT; ++d) { th[d] = (d < k) ? theta0[c * k + d] : 0.0; th0[d] = th[d]; }
+    double cur_lp = eval_prior<KT>(P, th);
+    double cur_ll = WARP ? eval_loglik_warp<MODEL, KT>(P, O, th, nullptr, lane) : eval_loglik_thread<MODEL, KT>(P, O, th, nullptr);
+    double cur_sum = cur_ll + cur_lp;                            // what the accept test uses (IP.py:2641)
+    ChainStats<KT> st;
+    st.init();
+    // row 0: samples[0] = start, logP[0] = getLogP(start); log_priors[0] = log_likelihoods[0] = 0 (IP.py:2610-2625)
+    {
+        const double lp0 = combine_logp(cur_lp, cur_ll);
+        if (writer) {
+            if (out.samples) {
+#pragma unroll
+                for (int d = 0; d < KT; ++d) if (d < k) out.samples[c * k + d] = th[d];
+            }
+            if (out.logp) out.logp[c] = lp0;
+            if (out.lprior) out.lprior[c] = 0.0;
+            if (out.llik) out.llik[c] = 0.0;
+        }
+        if (M.burn_in <= 0) st.add_row(k, 0, th, th0, lp0);
+    }
+    for (long long i = 1; i < M.n_steps; ++i) {
+        double z[KT], delta[KT], prop[KT], u;
+        const unsigned long long step = (unsigned long long)(M.first_step + i);
+        if (WARP) draws_warp<KT>(M, gchain, step, lane, z, u);
+        else draws_thread<KT>(M, gchain, step, z, u);
+        make_delta<KT>(M, z, delta);
+#pragma unroll
+        for (int d = 0; d < KT; ++d) prop[d] = th[d] + delta[d];  // IP.py:2630
+        const double lp_p = eval_prior<KT>(P, prop);
+        const double ll_p = WARP ? eval_loglik_warp<MODEL, KT>(P, O, prop, nullptr, lane)
+                                 : eval_loglik_thread<MODEL, KT>(P, O, prop, nullptr);   // evaluated even if lp_p == -inf (IP.py:2637)
+        const double sum_p = ll_p + lp_p;
+        double la = sum_p - cur_sum;                              // IP.py:2641
+        if (M.modulate != 0.0) la = (1.0 / M.modulate) * la;      // IP.py:2649
+        const bool acc = la > log(u);                             // IP.py:2651-2652; NaN -> reject
+        if (acc) {
+#pragma unroll
+            for (int d = 0; d < KT; ++d) th[d] = prop[d];
+            cur_lp = lp_p; cur_ll = ll_p; cur_sum = sum_p;
+            st.nacc += 1.0;
+        }
+        if (writer) {
+            if (out.deltas) {
+#pragma unroll
+                for (int d = 0; d < KT; ++d) if (d < k) out.deltas[((i - 1) * C + c) * k + d] = delta[d];
+            }
+            if (out.us) out.us[(i - 1) * C + c] = u;
+            if (i % M.thin == 0) {
+                const long long row = i / M.thin;
+                if (out.samples) {
+#pragma unroll
+                    for (int d = 0; d < KT; ++d) if (d < k) out.samples[(row * C + c) * k + d] = th[d];
+                }
+                if (out.logp) out.logp[row * C + c] = cur_sum;      // IP.py:2661, 2673
+                if (out.lprior) out.lprior[row * C + c] = cur_lp;
+                if (out.llik) out.llik[row * C + c] = cur_ll;
+            }
+        }
+        if (i >= M.burn_in) st.add_row(k, i, th, th0, cur_sum);
+    }
+    if (writer) st.store(k, out.stats + c * PEUQSE_MH_STAT_DOUBLES(k), th, cur_sum);
+}
+
+namespace {
+template <int MODEL, int KT>
+int launch_mh(const peuqse_problem* p, const DevMH& M, const double* th0, const MHOut& out, cudaStream_t st) {
+    int use_smem;
+    const size_t smem = pq_pick_smem(p, &use_smem);
+    if (p->d.n_total > PQ_THREAD_SHAPE_MAX_N) {
+        auto kern = k_mh<MODEL, KT, true>;
+        PQ_CUDA_OK(pq_allow_smem((const void*)kern, smem));
+        const long long blocks = (M.n_chains + 7) / 8;
+        kern<<<(unsigned)blocks, 256, smem, st>>>(p->d, M, th0, out, use_smem);
+    } else {
+        auto kern = k_mh<MODEL, KT, false>;
+        PQ_CUDA_OK(pq_allow_smem((const void*)kern, smem));
+        const long long blocks = (M.n_chains + 127) / 128;
+        kern<<<(unsigned)blocks, 128, smem, st>>>(p->d, M, th0, out, use_smem);
+    }
+    PQ_CUDA_OK(cudaGetLastError());
+    return PEUQSE_OK;
+}
+}  // namespace
+
+extern "C" int peuqse_mh_run(const peuqse_problem* p, const peuqse_mh_spec* s, const double* d_theta0, double* d_samples,
+                             double* d_logp, double* d_logprior, double* d_loglik, double* d_deltas, double* d_us,
+                             double* d_stats, void* stream) {
+    if (!p || !s || !d_theta0 || !d_stats) return pq_set_error(PEUQSE_ERR_INVALID, "null argument");
+    if (s->k != p->d.k) return pq_set_error(PEUQSE_ERR_INVALID, "mh k != problem k");
+    if (s->n_chains < 1 || s->n_steps < 1 || s->thin < 1) return pq_set_error(PEUQSE_ERR_INVALID, "bad mh sizes");
+    if (s->k > 14) return pq_set_error(PEUQSE_ERR_INVALID, "mh supports k <= 14 (7 Philox blocks of normals per step)");
+    if ((unsigned long long)(s->first_step + s->n_steps) * 8ULL > 0xffffffffULL)
+        return pq_set_error(PEUQSE_ERR_INVALID, "first_step + n_steps exceeds the 2^29 steps a Philox stream addresses");
+    if (p->d.model_id == PEUQSE_MODEL_EXTERNAL) return pq_set_error(PEUQSE_ERR_INVALID, "mh needs a built-in model");
+    if (p->d.any_full) return pq_set_error(PEUQSE_ERR_INVALID, "mh does not support full-covariance responses");
+    DevMH M;
+    M.n_chains = s->n_chains; M.n_steps = s->n_steps; M.burn_in = s->burn_in; M.first_step = s->first_step;
+    M.chain_offset = s->chain_offset; M.seed = s->seed; M.modulate = s->modulate; M.k = s->k; M.thin = s->thin; M.pad = 0;
+    M.chol_diag = 1;
+    for (int i = 0; i < PQ_MAXK * PQ_MAXK; ++i) M.chol[i] = 0.0;
+    for (int d = 0; d < s->k; ++d)
+        for (int e = 0; e < s->k; ++e) {
+            const double v = s->step_chol[d * s->k + e];
+            M.chol[d * s->k + e] = v;
+            if (d != e && v != 0.0) M.chol_diag = 0;
+        }
+    MHOut out{d_samples, d_logp, d_logprior, d_loglik, d_deltas, d_us, d_stats};
+    cudaStream_t st = (cudaStream_t)stream;
+    const int kb = pq_k_bucket(p->d.k);
+    switch (p->d.model_id) {
+        case PEUQSE_MODEL_QUADRATIC: return launch_mh<PEUQSE_MODEL_QUADRATIC, 2>(p, M, d_theta0, out, st);
+        case PEUQSE_MODEL_TPD2SITE: return launch_mh<PEUQSE_MODEL_TPD2SITE, 6>(p, M, d_theta0, out, st);
+        case PEUQSE_MODEL_LINEAR:
+#define MH_L(KT, ...) return launch_mh<PEUQSE_MODEL_LINEAR, KT>(p, M, d_theta0, out, st)
+            PQ_DISPATCH_K(kb, MH_L, 0)
+#undef MH_L
+            break;
+        default: break;
+    }
+    return pq_set_error(PEUQSE_ERR_INVALID, "unknown model");
+}

@@ -1,0 +1,164 @@
+// Problem handle: validates the host descriptor and uploads the constants once (replaces the per-call
+// re-derivation in the reference: scipy's _PSD eigendecomposition on every logpdf call, IP.py:2773, 2960).
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "common.cuh"
+#include "eval.cuh"
+
+static thread_local std::string g_err;
+
+int pq_set_error(int code, const char* msg) {
+    g_err = msg;
+    return code;
+}
+int pq_set_cuda_error(cudaError_t e, const char* what, int line) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s [line %d]", (int)e, cudaGetErrorString(e), what, line);
+    g_err = buf;
+    return PEUQSE_ERR_CUDA;
+}
+
+extern "C" const char* peuqse_last_error(void) { return g_err.c_str(); }
+extern "C" int peuqse_version(void) { return 100; }
+
+extern "C" int peuqse_device_info(int32_t* out3) {
+    int dev = 0;
+    PQ_CUDA_OK(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    PQ_CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+    out3[0] = prop.multiProcessorCount;
+    out3[1] = (int32_t)prop.sharedMemPerBlockOptin;
+    out3[2] = prop.major * 10 + prop.minor;
+    return PEUQSE_OK;
+}
+
+size_t pq_obs_smem_bytes(const DevProblem& d) { return pq_obs_doubles(d) * sizeof(double); }
+
+namespace {
+struct BlobBuilder {
+    std::vector<unsigned char> host;
+    size_t add(const void* src, size_t bytes) {
+        size_t off = (host.size() + 255) & ~(size_t)255;   // 256 B alignment for vector loads / TMA
+        host.resize(off + bytes);
+        if (bytes) memcpy(host.data() + off, src, bytes);
+        return off;
+    }
+};
+}  // namespace
+
+extern "C" int peuqse_problem_create(const peuqse_problem_desc* h, peuqse_problem** out) {
+    if (!h || !out) return pq_set_error(PEUQSE_ERR_INVALID, "null argument");
+    if (h->k < 1 || h->k > PQ_MAXK) return pq_set_error(PEUQSE_ERR_INVALID, "k must be in [1, PEUQSE_MAX_K]");
+    if (h->n_resp < 1 || h->n_resp > PQ_MAXR) return pq_set_error(PEUQSE_ERR_INVALID, "n_resp must be in [1, PEUQSE_MAX_RESP]");
+    if (h->kp < 0 || h->kp > h->k) return pq_set_error(PEUQSE_ERR_INVALID, "kp out of range");
+    if (h->prior_mode != PEUQSE_PRIOR_NONE && h->kp == 0) return pq_set_error(PEUQSE_ERR_INVALID, "prior_mode needs kp > 0");
+    if (h->model_id < PEUQSE_MODEL_EXTERNAL || h->model_id > PEUQSE_MODEL_LINEAR)
+        return pq_set_error(PEUQSE_ERR_INVALID, "unknown model_id");
+
+    peuqse_problem* p = new peuqse_problem();
+    memset(p, 0, sizeof *p);
+    DevProblem& d = p->d;
+    d.k = h->k;
+    d.kp = h->kp;
+    d.scaling_on = h->scaling_on;
+    d.prior_mode = h->prior_mode;
+    d.has_lb = h->has_lb;
+    d.has_ub = h->has_ub;
+    d.prior_c = h->prior_c;
+    for (int i = 0; i < PQ_MAXK; ++i) {
+        d.lb[i] = -INFINITY; d.ub[i] = INFINITY; d.scale[i] = 1.0; d.mus[i] = 0.0; d.gidx[i] = i; d.pw[i] = 0.0;
+    }
+    for (int i = 0; i < h->k; ++i) {
+        if (h->has_lb) d.lb[i] = h->lb[i];
+        if (h->has_ub) d.ub[i] = h->ub[i];
+        if (h->scaling_on) d.scale[i] = h->scale[i];
+        d.mus[i] = h->mu_scaled[i];
+    }
+    d.prior_identity = 1;
+    for (int j = 0; j < h->kp; ++j) {
+        d.gidx[j] = h->prior_gidx[j];
+        if (d.gidx[j] < 0 || d.gidx[j] >= h->k) { delete p; return pq_set_error(PEUQSE_ERR_INVALID, "prior_gidx out of range"); }
+        if (d.gidx[j] != j) d.prior_identity = 0;
+        if (h->prior_mode == PEUQSE_PRIOR_DIAG) d.pw[j] = h->prior_w[j];
+    }
+    if (h->prior_mode == PEUQSE_PRIOR_DENSE && !d.prior_identity) {
+        delete p;
+        return pq_set_error(PEUQSE_ERR_INVALID, "dense prior needs all parameters Gaussian in natural order (IP.py:151-152)");
+    }
+    d.n_resp = h->n_resp;
+    d.n_total = h->n_total;
+    d.model_id = h->model_id;
+    d.n_mconst = h->n_model_const;
+    int off = 0;
+    for (int r = 0; r < h->n_resp; ++r) {
+        d.resp_n[r] = h->resp_n[r];
+        d.resp_mode[r] = h->resp_mode[r];
+        d.resp_off[r] = off;
+        d.resp_c[r] = h->resp_c[r];
+        if (h->resp_mode[r] == PEUQSE_RESP_PER_VALUE) d.any_per_value = 1;
+        if (h->resp_mode[r] == PEUQSE_RESP_MVN_FULL) d.any_full = 1;
+        off += h->resp_n[r];
+    }
+    if (off != h->n_total) { delete p; return pq_set_error(PEUQSE_ERR_INVALID, "n_total != sum(resp_n)"); }
+    // model constant sizes
+    {
+        long need = 0;
+        if (h->model_id == PEUQSE_MODEL_QUADRATIC) need = h->n_total;
+        if (h->model_id == PEUQSE_MODEL_TPD2SITE) need = 3L * h->n_total;
+        if (h->model_id == PEUQSE_MODEL_LINEAR) need = (long)h->n_total * h->k;
+        if (need != h->n_model_const) { delete p; return pq_set_error(PEUQSE_ERR_INVALID, "n_model_const does not match the model"); }
+        if (h->model_id == PEUQSE_MODEL_QUADRATIC && h->k != 2) { delete p; return pq_set_error(PEUQSE_ERR_INVALID, "quadratic model has k = 2"); }
+        if (h->model_id == PEUQSE_MODEL_TPD2SITE && h->k != 6) { delete p; return pq_set_error(PEUQSE_ERR_INVALID, "tpd2site model has k = 6"); }
+    }
+
+    BlobBuilder bb;
+    const size_t nt = (size_t)h->n_total;
+    std::vector<double> zeros(nt, 0.0);
+    std::vector<int32_t> ident(nt);
+    for (size_t i = 0; i < nt; ++i) ident[i] = (int32_t)i;
+    const size_t o_y = bb.add(h->y, nt * 8);
+    const size_t o_w = bb.add(h->w ? h->w : zeros.data(), nt * 8);
+    const size_t o_c = bb.add(h->cval ? h->cval : zeros.data(), nt * 8);
+    const size_t o_s = bb.add(h->src ? (const void*)h->src : (const void*)ident.data(), nt * 4);
+    const size_t o_m = bb.add(h->model_const, (size_t)h->n_model_const * 8);
+    size_t o_pU = 0;
+    if (h->prior_mode == PEUQSE_PRIOR_DENSE) o_pU = bb.add(h->prior_U, (size_t)h->kp * h->kp * 8);
+    size_t o_U[PQ_MAXR] = {0};
+    for (int r = 0; r < h->n_resp; ++r)
+        if (h->resp_mode[r] == PEUQSE_RESP_MVN_FULL) {
+            if (!h->resp_U || !h->resp_U[r]) { delete p; return pq_set_error(PEUQSE_ERR_INVALID, "MVN_FULL response without resp_U"); }
+            o_U[r] = bb.add(h->resp_U[r], (size_t)h->resp_n[r] * h->resp_n[r] * 8);
+        }
+    cudaError_t e = cudaMalloc(&p->blob, bb.host.size() ? bb.host.size() : 256);
+    if (e != cudaSuccess) { delete p; return pq_set_cuda_error(e, "cudaMalloc(problem blob)", __LINE__); }
+    p->blob_bytes = bb.host.size();
+    e = cudaMemcpy(p->blob, bb.host.data(), bb.host.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(p->blob); delete p; return pq_set_cuda_error(e, "cudaMemcpy(problem blob)", __LINE__); }
+    unsigned char* base = (unsigned char*)p->blob;
+    d.y = (const double*)(base + o_y);
+    d.w = (const double*)(base + o_w);
+    d.cval = (const double*)(base + o_c);
+    d.src = (const int*)(base + o_s);
+    d.mconst = (const double*)(base + o_m);
+    d.pU = h->prior_mode == PEUQSE_PRIOR_DENSE ? (const double*)(base + o_pU) : nullptr;
+    for (int r = 0; r < h->n_resp; ++r)
+        d.U[r] = (h->resp_mode[r] == PEUQSE_RESP_MVN_FULL) ? (const double*)(base + o_U[r]) : nullptr;
+
+    cudaGetDevice(&p->device);
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, p->device);
+    p->sm_count = prop.multiProcessorCount;
+    p->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    p->obs_smem_bytes = pq_obs_smem_bytes(d);
+    *out = p;
+    return PEUQSE_OK;
+}
+
+extern "C" int peuqse_problem_destroy(peuqse_problem* p) {
+    if (!p) return PEUQSE_OK;
+    if (p->blob) cudaFree(p->blob);
+    delete p;
+    return PEUQSE_OK;
+}

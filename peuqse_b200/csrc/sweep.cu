@@ -1,0 +1,590 @@
+// Multistart sweeps (kernels K1 + K6 of SURVEY section 2): grid / uniform point generation fused with
+// simulate -> prior -> likelihood and the reductions the reference does afterwards on the host.
+// Replaces doMultiStart / doListOfPermutationsSearch's Python loop (IP.py:844-956), the list built by
+// CombinationGeneratorModule.combinationGenerator (CombinationGeneratorModule.py:40-81),
+// convertPermutationsToSamples (IP.py:3463-3491) and the moment part of calculatePostBurnInStatistics
+// (IP.py:1923-1931).
+#include "common.cuh"
+#include "eval.cuh"
+#include "launch.cuh"
+#include "philox.cuh"
+
+#define PQ_SWEEP_MAX_BLOCKS 2048
+#define PQ_SWEEP_TICKET_BYTES 256
+#define PQ_ACC_MAX PEUQSE_ACC_DOUBLES(PQ_MAXK)
+
+struct FastDiv {            // unsigned 64-bit division by an invariant (Granlund & Montgomery 1994, fig. 4.1)
+    unsigned long long m;
+    int sh1, sh2;
+};
+
+struct DevSweep {
+    int kind, k;
+    double center[PQ_MAXK], interval[PQ_MAXK], stdp[PQ_MAXK];
+    unsigned long long r2[PQ_MAXK];       // 2*radius
+    unsigned long long mprod[PQ_MAXK + 1];  // prod_{d<p}(2 r_d + 1)
+    FastDiv div[PQ_MAXK];
+    double spread;
+    unsigned long long seed;
+};
+
+static FastDiv make_fastdiv(unsigned long long d) {
+    FastDiv f;
+    if (d == 0) d = 1;
+    int l = 0;
+    while (l < 64 && (((unsigned __int128)1) << l) < d) ++l;
+    const unsigned __int128 two64 = ((unsigned __int128)1) << 64;
+    const unsigned __int128 num = two64 * ((((unsigned __int128)1) << l) - d);
+    f.m = (unsigned long long)(num / d + 1);
+    f.sh1 = l < 1 ? l : 1;
+    f.sh2 = l > 1 ? l - 1 : 0;
+    return f;
+}
+
+__device__ __forceinline__ unsigned long long fastdiv(unsigned long long n, const FastDiv& f) {
+    const unsigned long long t = __umul64hi(f.m, n);
+    return (t + ((n - t) >> f.sh1)) >> f.sh2;
+}
+
+static int build_sweep(const peuqse_sweep_spec* s, DevSweep* d, long long* total) {
+    if (!s || s->k < 1 || s->k > PQ_MAXK) return pq_set_error(PEUQSE_ERR_INVALID, "bad sweep spec");
+    d->kind = s->kind;
+    d->k = s->k;
+    d->spread = s->spread;
+    d->seed = s->seed;
+    unsigned __int128 m = 1;
+    d->mprod[0] = 1;
+    for (int p = 0; p < PQ_MAXK; ++p) {
+        const bool on = p < s->k;
+        d->center[p] = on ? s->center[p] : 0.0;
+        d->interval[p] = on ? s->interval[p] : 0.0;
+        d->stdp[p] = on ? s->std_prior[p] : 0.0;
+        const long long r = on ? s->radii[p] : 0;
+        if (r < 0) return pq_set_error(PEUQSE_ERR_INVALID, "negative grid radius");
+        d->r2[p] = 2ULL * (unsigned long long)r;
+        d->div[p] = make_fastdiv(d->r2[p]);
+        m *= (unsigned __int128)(d->r2[p] + 1);
+        if (m >> 62) return pq_set_error(PEUQSE_ERR_INVALID, "grid has more than 2^62 points");
+        d->mprod[p + 1] = (unsigned long long)m;
+    }
+    if (total) *total = (s->kind == 0) ? (long long)d->mprod[s->k] : (long long)0x3fffffffffffffffLL;
+    return PEUQSE_OK;
+}
+
+// element g of combinationGenerator's list: from the last axis down; point value c -/+ (h*i)
+// (CombinationGeneratorModule.py:59, 71: one multiply, one add)
+template <int KT>
+__device__ __forceinline__ void grid_point(const DevSweep& S, unsigned long long g, double (&th)[KT]) {
+#pragma unroll
+    for (int p = KT - 1; p >= 0; --p) {
+        th[p] = 0.0;
+        if (p < S.k) {
+            const unsigned long long M = S.mprod[p];
+            if (g < M) {
+                th[p] = S.center[p];
+            } else {
+                const unsigned long long gp = g - M;
+                const unsigned long long b = fastdiv(gp, S.div[p]);
+                const unsigned long long j = gp - b * S.r2[p];
+                const double step = S.interval[p] * (double)((j >> 1) + 1ULL);
+                th[p] = (j & 1ULL) ? (S.center[p] + step) : (S.center[p] - step);
+                g = b;
+            }
+        }
+    }
+}
+
+// generateInitialPoints('uniform') (IP.py:706, 749): ((spread*(-2+4u))*std) + center, u = Philox(seed, g)
+template <int KT>
+__device__ __forceinline__ void uniform_point(const DevSweep& S, unsigned long long g, double (&th)[KT]) {
+#pragma unroll
+    for (int b = 0; b < (KT + 1) / 2; ++b) {
+        if (2 * b < S.k) {
+            const Philox4 r = philox_block(S.seed, PQ_STREAM_UNIFORM_SWEEP, g, (uint32_t)b);
+            const double ua = philox_u53(r.x, r.y), ub = philox_u53(r.z, r.w);
+            th[2 * b] = (S.spread * (-2.0 + 4.0 * ua)) * S.stdp[2 * b] + S.center[2 * b];
+            if (2 * b + 1 < KT) {
+                th[2 * b + 1] = 0.0;
+                if (2 * b + 1 < S.k) th[2 * b + 1] = (S.spread * (-2.0 + 4.0 * ub)) * S.stdp[2 * b + 1] + S.center[2 * b + 1];
+            }
+        } else {
+            th[2 * b] = 0.0;
+            if (2 * b + 1 < KT) th[2 * b + 1] = 0.0;
+        }
+    }
+}
+
+template <int KT>
+__device__ __forceinline__ void sweep_point(const DevSweep& S, unsigned long long g, double (&th)[KT]) {
+    if (S.kind == 0) grid_point<KT>(S, g, th);
+    else uniform_point<KT>(S, g, th);
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass 1: logP of every point (+ optional store) and the first strict maximum
+// ---------------------------------------------------------------------------------------------
+template <int MODEL, int KT>
+__global__ void __launch_bounds__(256) k_sweep_pass1(const __grid_constant__ DevProblem P, const __grid_constant__ DevSweep S,
+                                                     long long first, long long count, double* __restrict__ logp_out,
+                                                     peuqse_best* __restrict__ best_out, Best* __restrict__ partial,
+                                                     unsigned int* __restrict__ ticket, int use_smem) {
+    extern __shared__ double smem[];
+    __shared__ Best s_best[8];
+    __shared__ bool s_last;
+    const ObsView O = stage_obs(P, smem, use_smem);
+    Best best = best_none();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        const long long g = first + i;
+        double th[KT];
+        sweep_point<KT>(S, (unsigned long long)g, th);
+        const double lp = eval_prior<KT>(P, th);
+        double v = lp;
+        if (!pq_is_neg_inf(lp)) v = eval_loglik_thread<MODEL, KT>(P, O, th, nullptr) + lp;   // IP.py:1649-1653
+        if (logp_out) __stcs(logp_out + i, v);
+        if (v > best.v) { best.v = v; best.i = g; }            // strict '>', increasing g: first maximum
+    }
+    best = warp_best(best);
+    if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        Best b = (threadIdx.x < (blockDim.x >> 5)) ? s_best[threadIdx.x] : best_none();
+        b = warp_best(b);
+        if (threadIdx.x == 0) {
+            partial[blockIdx.x] = b;
+            __threadfence();
+            const unsigned int t = atomicAdd(ticket, 1u);
+            s_last = (t == gridDim.x - 1);
+        }
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x < 32) {
+        __threadfence();
+        Best b = best_none();
+        for (int j = threadIdx.x; j < (int)gridDim.x; j += 32) {
+            Best o;
+            o.v = __ldcg(&partial[j].v);
+            o.i = __ldcg(&partial[j].i);
+            b = best_merge(b, o);
+        }
+        b = warp_best(b);
+        if (threadIdx.x == 0) {
+            best_out->logp = b.v;
+            best_out->index = (b.i == 0x7fffffffffffffffLL) ? -1 : b.i;
+            *ticket = 0;
+        }
+    }
+}
+
+template <int KT>
+__global__ void __launch_bounds__(256) k_sweep_points(const __grid_constant__ DevSweep S, long long first, long long count,
+                                                      double* __restrict__ theta) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        double th[KT];
+        sweep_point<KT>(S, (unsigned long long)(first + i), th);
+#pragma unroll
+        for (int d = 0; d < KT; ++d)
+            if (d < S.k) theta[i * S.k + d] = th[d];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass 2: weights + moments (+ compaction of the retained points)
+// ---------------------------------------------------------------------------------------------
+template <int KT>
+struct Pass2Acc {
+    double w, wexp, nk;
+    double s1[KT];
+    double s2[KT * (KT + 1) / 2];
+    double mn[KT], mx[KT];
+};
+
+__device__ __forceinline__ double block_sum(double v, double* s_red) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x < 32) {
+        t = (threadIdx.x < (blockDim.x >> 5)) ? s_red[threadIdx.x] : 0.0;
+        t = warp_sum(t);
+    }
+    return t;   // valid in warp 0
+}
+__device__ __forceinline__ double block_min(double v, double* s_red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = pq_pos_inf();
+    if (threadIdx.x < 32) {
+        t = (threadIdx.x < (blockDim.x >> 5)) ? s_red[threadIdx.x] : pq_pos_inf();
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t = fmin(t, __shfl_xor_sync(0xffffffffu, t, o));
+    }
+    return t;
+}
+
+template <int MODEL, int KT>
+__global__ void __launch_bounds__(256) k_sweep_pass2(const __grid_constant__ DevProblem P, const __grid_constant__ DevSweep S,
+                                                     long long first, long long count, const double* __restrict__ logp_in,
+                                                     double thr, double* __restrict__ partial, double* __restrict__ acc_out,
+                                                     unsigned int* __restrict__ ticket, long long* __restrict__ keep_idx,
+                                                     double* __restrict__ keep_logp, long long keep_cap,
+                                                     unsigned long long* __restrict__ keep_count, int use_smem) {
+    extern __shared__ double smem[];
+    __shared__ double s_red[8];
+    __shared__ bool s_last;
+    const ObsView O = stage_obs(P, smem, use_smem);
+    Pass2Acc<KT> A;
+    A.w = A.wexp = A.nk = 0.0;
+#pragma unroll
+    for (int d = 0; d < KT; ++d) { A.s1[d] = 0.0; A.mn[d] = pq_pos_inf(); A.mx[d] = pq_neg_inf(); }
+#pragma unroll
+    for (int e = 0; e < KT * (KT + 1) / 2; ++e) A.s2[e] = 0.0;
+
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        const long long g = first + i;
+        double th[KT];
+        double v;
+        if (logp_in) {
+            v = __ldcs(logp_in + i);
+            if (!(v > thr)) continue;                          // IP.py:3481
+            sweep_point<KT>(S, (unsigned long long)g, th);
+        } else {
+            sweep_point<KT>(S, (unsigned long long)g, th);
+            const double lp = eval_prior<KT>(P, th);
+            v = lp;
+            if (!pq_is_neg_inf(lp)) v = eval_loglik_thread<MODEL, KT>(P, O, th, nullptr) + lp;
+            if (!(v > thr)) continue;
+        }
+        const double reps = exp(v - thr);                       // IP.py:3485
+        const double w = trunc(reps);                           // int(...), IP.py:3486
+        A.w += w;
+        A.wexp = fma(w, exp(v), A.wexp);
+        A.nk += 1.0;
+        int e = 0;
+#pragma unroll
+        for (int d = 0; d < KT; ++d) {
+            if (d < S.k) {
+                const double dd = th[d] - S.center[d];
+                const double wd = w * dd;
+                A.s1[d] += wd;
+#pragma unroll
+                for (int d2 = d; d2 < KT; ++d2) {
+                    if (d2 < S.k) A.s2[e] = fma(wd, th[d2] - S.center[d2], A.s2[e]);
+                    ++e;
+                }
+                A.mn[d] = fmin(A.mn[d], th[d]);
+                A.mx[d] = fmax(A.mx[d], th[d]);
+            } else {
+                e += KT - d;
+            }
+        }
+        if (keep_idx) {
+            const unsigned long long slot = atomicAdd(keep_count, 1ULL);
+            if ((long long)slot < keep_cap) {
+                keep_idx[slot] = g;
+                keep_logp[slot] = v;
+            }
+        }
+    }
+    // block reduction -> partial[blockIdx][...] laid out like d_acc
+    const int k = S.k;
+    double* mine = partial + (size_t)blockIdx.x * PQ_ACC_MAX;
+    double t;
+    t = block_sum(A.w, s_red);    if (threadIdx.x == 0) mine[PEUQSE_ACC_W] = t;
+    t = block_sum(A.wexp, s_red); if (threadIdx.x == 0) mine[PEUQSE_ACC_WEXP] = t;
+    t = block_sum(A.nk, s_red);   if (threadIdx.x == 0) mine[PEUQSE_ACC_NKEPT] = t;
+    {
+        int e = 0;
+#pragma unroll
+        for (int d = 0; d < KT; ++d) {
+            if (d < k) {
+                t = block_sum(A.s1[d], s_red);
+                if (threadIdx.x == 0) mine[PEUQSE_ACC_S1 + d] = t;
+                t = block_min(A.mn[d], s_red);
+                if (threadIdx.x == 0) mine[PEUQSE_ACC_MIN(k) + d] = t;
+                t = -block_min(-A.mx[d], s_red);
+                if (threadIdx.x == 0) mine[PEUQSE_ACC_MAX(k) + d] = t;
+            }
+#pragma unroll
+            for (int d2 = d; d2 < KT; ++d2) {
+                if (d < k && d2 < k) {
+                    t = block_sum(A.s2[e], s_red);
+                    if (threadIdx.x == 0) {
+                        mine[PEUQSE_ACC_S2(k) + d * k + d2] = t;
+                        mine[PEUQSE_ACC_S2(k) + d2 * k + d] = t;
+                    }
+                }
+                ++e;
+            }
+        }
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int tk = atomicAdd(ticket, 1u);
+        s_last = (tk == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        const int nacc = PEUQSE_ACC_DOUBLES(k);
+        const int mn0 = PEUQSE_ACC_MIN(k), mx0 = PEUQSE_ACC_MAX(k);
+        for (int a = threadIdx.x; a < nacc; a += blockDim.x) {
+            double r = acc_out[a];
+            for (int b = 0; b < (int)gridDim.x; ++b) {           // fixed block order: deterministic
+                const double x = __ldcg(partial + (size_t)b * PQ_ACC_MAX + a);
+                if (a >= mx0) r = fmax(r, x);
+                else if (a >= mn0) r = fmin(r, x);
+                else r += x;
+            }
+            acc_out[a] = r;
+        }
+        if (threadIdx.x == 0) *ticket = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass 3: weighted marginal histograms (np.histogram semantics on given edges)
+// ---------------------------------------------------------------------------------------------
+template <int MODEL, int KT>
+__global__ void __launch_bounds__(256) k_sweep_hist(const __grid_constant__ DevProblem P, const __grid_constant__ DevSweep S,
+                                                    long long first, long long count, const double* __restrict__ logp_in,
+                                                    double thr, const double* __restrict__ edges, int nbins,
+                                                    unsigned long long* __restrict__ hist, int use_smem) {
+    extern __shared__ double smem[];
+    const ObsView O = stage_obs(P, smem, use_smem);
+    // block-private histogram after the staged constants
+    unsigned long long* sh = (unsigned long long*)(smem + (use_smem ? pq_obs_doubles(P) : 0));
+    const int k = S.k;
+    for (int a = threadIdx.x; a < k * nbins; a += blockDim.x) sh[a] = 0ULL;
+    __syncthreads();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+        const long long g = first + i;
+        double th[KT];
+        double v;
+        if (logp_in) {
+            v = __ldcs(logp_in + i);
+            if (!(v > thr)) continue;
+            sweep_point<KT>(S, (unsigned long long)g, th);
+        } else {
+            sweep_point<KT>(S, (unsigned long long)g, th);
+            const double lp = eval_prior<KT>(P, th);
+            v = lp;
+            if (!pq_is_neg_inf(lp)) v = eval_loglik_thread<MODEL, KT>(P, O, th, nullptr) + lp;
+            if (!(v > thr)) continue;
+        }
+        const unsigned long long w = (unsigned long long)trunc(exp(v - thr));
+#pragma unroll
+        for (int d = 0; d < KT; ++d) {
+            if (d < k) {
+                const double* ed = edges + d * (nbins + 1);
+                const double lo = ed[0], hi = ed[nbins];
+                const double x = th[d];
+                if (x >= lo && x <= hi) {
+                    // numpy/lib/_histograms_impl.py: index from the normalised position, then corrected
+                    // against the actual edges; the last bin is closed on the right
+                    int b = (int)(((x - lo) / (hi - lo)) * (double)nbins);
+                    if (b >= nbins) b = nbins - 1;
+                    if (b < 0) b = 0;
+                    if (x < ed[b]) --b;
+                    else if (b != nbins - 1 && x >= ed[b + 1]) ++b;
+                    atomicAdd(sh + d * nbins + b, w);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int a = threadIdx.x; a < k * nbins; a += blockDim.x)
+        if (sh[a]) atomicAdd(hist + a, sh[a]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+inline int sweep_grid(const peuqse_problem* p, long long count) {
+    const long long blocks = (count + 255) / 256;
+    return (int)std::max<long long>(1, std::min<long long>(blocks, std::min<long long>((long long)p->sm_count * 8, PQ_SWEEP_MAX_BLOCKS)));
+}
+
+template <int MODEL, int KT>
+int launch_pass1(const peuqse_problem* p, const DevSweep& S, long long first, long long count, double* logp,
+                 peuqse_best* best, void* work, cudaStream_t st) {
+    int use_smem;
+    const size_t smem = pq_pick_smem(p, &use_smem);
+    auto kern = k_sweep_pass1<MODEL, KT>;
+    PQ_CUDA_OK(pq_allow_smem((const void*)kern, smem));
+    unsigned int* ticket = (unsigned int*)work;
+    Best* partial = (Best*)((char*)work + PQ_SWEEP_TICKET_BYTES);
+    kern<<<sweep_grid(p, count), 256, smem, st>>>(p->d, S, first, count, logp, best, partial, ticket, use_smem);
+    PQ_CUDA_OK(cudaGetLastError());
+    return PEUQSE_OK;
+}
+
+template <int MODEL, int KT>
+int launch_pass2(const peuqse_problem* p, const DevSweep& S, long long first, long long count, const double* logp,
+                 double thr, double* acc, long long* kidx, double* klogp, long long kcap, long long* kcount, void* work,
+                 cudaStream_t st) {
+    int use_smem;
+    const size_t smem = pq_pick_smem(p, &use_smem);
+    auto kern = k_sweep_pass2<MODEL, KT>;
+    PQ_CUDA_OK(pq_allow_smem((const void*)kern, smem));
+    unsigned int* ticket = (unsigned int*)work;
+    double* partial = (double*)((char*)work + PQ_SWEEP_TICKET_BYTES);
+    kern<<<sweep_grid(p, count), 256, smem, st>>>(p->d, S, first, count, logp, thr, partial, acc, ticket, kidx, klogp, kcap,
+                                                  (unsigned long long*)kcount, use_smem);
+    PQ_CUDA_OK(cudaGetLastError());
+    return PEUQSE_OK;
+}
+
+template <int MODEL, int KT>
+int launch_hist(const peuqse_problem* p, const DevSweep& S, long long first, long long count, const double* logp, double thr,
+                const double* edges, int nbins, unsigned long long* hist, cudaStream_t st) {
+    int use_smem;
+    size_t smem = pq_pick_smem(p, &use_smem);
+    smem += (size_t)S.k * nbins * sizeof(unsigned long long);
+    auto kern = k_sweep_hist<MODEL, KT>;
+    PQ_CUDA_OK(pq_allow_smem((const void*)kern, smem));
+    kern<<<sweep_grid(p, count), 256, smem, st>>>(p->d, S, first, count, logp, thr, edges, nbins, hist, use_smem);
+    PQ_CUDA_OK(cudaGetLastError());
+    return PEUQSE_OK;
+}
+
+}  // namespace
+
+extern "C" int64_t peuqse_sweep_work_bytes(void) {
+    return (int64_t)PQ_SWEEP_TICKET_BYTES + (int64_t)PQ_SWEEP_MAX_BLOCKS * PQ_ACC_MAX * (int64_t)sizeof(double);
+}
+
+#define PQ_SWEEP_DISPATCH(CALL_Q, CALL_T, CALL_L, CALL_E)                                         \
+    switch (p->d.model_id) {                                                                       \
+        case PEUQSE_MODEL_QUADRATIC: return CALL_Q;                                                \
+        case PEUQSE_MODEL_TPD2SITE: return CALL_T;                                                 \
+        case PEUQSE_MODEL_LINEAR: {                                                                \
+            const int kb = pq_k_bucket(p->d.k);                                                    \
+            PQ_DISPATCH_K(kb, CALL_L, 0)                                                           \
+        } break;                                                                                   \
+        case PEUQSE_MODEL_EXTERNAL: {                                                              \
+            const int kb = pq_k_bucket(p->d.k);                                                    \
+            PQ_DISPATCH_K(kb, CALL_E, 0)                                                           \
+        } break;                                                                                   \
+        default: break;                                                                            \
+    }
+
+static int check_sweep_args(const peuqse_problem* p, const peuqse_sweep_spec* spec, long long first, long long count) {
+    if (!p || !spec) return pq_set_error(PEUQSE_ERR_INVALID, "null argument");
+    if (spec->k != p->d.k) return pq_set_error(PEUQSE_ERR_INVALID, "sweep k != problem k");
+    if (first < 0 || count < 0) return pq_set_error(PEUQSE_ERR_INVALID, "negative range");
+    if (p->d.any_full) return pq_set_error(PEUQSE_ERR_INVALID, "sweeps do not support full-covariance responses; use logp_batch on sweep_points");
+    return PEUQSE_OK;
+}
+
+extern "C" int peuqse_sweep_pass1(const peuqse_problem* p, const peuqse_sweep_spec* spec, int64_t first, int64_t count,
+                                  double* d_logp, peuqse_best* d_best, void* d_work, void* stream) {
+    int rc = check_sweep_args(p, spec, first, count);
+    if (rc) return rc;
+    if (!d_best || !d_work) return pq_set_error(PEUQSE_ERR_INVALID, "d_best and d_work are required");
+    if (p->d.model_id == PEUQSE_MODEL_EXTERNAL) return pq_set_error(PEUQSE_ERR_INVALID, "pass 1 needs a built-in model");
+    DevSweep S;
+    long long total;
+    rc = build_sweep(spec, &S, &total);
+    if (rc) return rc;
+    if (first + count > total) return pq_set_error(PEUQSE_ERR_INVALID, "range exceeds the number of sweep points");
+    cudaStream_t st = (cudaStream_t)stream;
+    PQ_CUDA_OK(cudaMemsetAsync(d_work, 0, PQ_SWEEP_TICKET_BYTES, st));
+#define P1_L(KT, ...) return launch_pass1<PEUQSE_MODEL_LINEAR, KT>(p, S, first, count, d_logp, d_best, d_work, st)
+#define P1_E(KT, ...) return pq_set_error(PEUQSE_ERR_INVALID, "pass 1 needs a built-in model")
+    PQ_SWEEP_DISPATCH((launch_pass1<PEUQSE_MODEL_QUADRATIC, 2>(p, S, first, count, d_logp, d_best, d_work, st)),
+                      (launch_pass1<PEUQSE_MODEL_TPD2SITE, 6>(p, S, first, count, d_logp, d_best, d_work, st)), P1_L, P1_E)
+#undef P1_L
+#undef P1_E
+    return pq_set_error(PEUQSE_ERR_INVALID, "unknown model");
+}
+
+extern "C" int peuqse_sweep_points(const peuqse_sweep_spec* spec, int64_t first, int64_t count, double* d_theta, void* stream) {
+    DevSweep S;
+    long long total;
+    int rc = build_sweep(spec, &S, &total);
+    if (rc) return rc;
+    if (first < 0 || count < 0 || first + count > total) return pq_set_error(PEUQSE_ERR_INVALID, "bad range");
+    if (count == 0) return PEUQSE_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = (int)std::min<long long>((count + 255) / 256, 148 * 8);
+    const int kb = pq_k_bucket(spec->k);
+#define PTS(KT, ...) k_sweep_points<KT><<<grid, 256, 0, st>>>(S, first, count, d_theta)
+    PQ_DISPATCH_K(kb, PTS, 0)
+#undef PTS
+    PQ_CUDA_OK(cudaGetLastError());
+    return PEUQSE_OK;
+}
+
+extern "C" int peuqse_sweep_pass2(const peuqse_problem* p, const peuqse_sweep_spec* spec, int64_t first, int64_t count,
+                                  const double* d_logp, double threshold, double* d_acc, int64_t* d_keep_index,
+                                  double* d_keep_logp, int64_t keep_capacity, int64_t* d_keep_count, void* d_work,
+                                  void* stream) {
+    int rc = check_sweep_args(p, spec, first, count);
+    if (rc) return rc;
+    if (!d_acc || !d_work) return pq_set_error(PEUQSE_ERR_INVALID, "d_acc and d_work are required");
+    if (d_keep_index && (!d_keep_logp || !d_keep_count)) return pq_set_error(PEUQSE_ERR_INVALID, "incomplete keep buffers");
+    if (p->d.model_id == PEUQSE_MODEL_EXTERNAL && !d_logp) return pq_set_error(PEUQSE_ERR_INVALID, "external model needs d_logp");
+    DevSweep S;
+    long long total;
+    rc = build_sweep(spec, &S, &total);
+    if (rc) return rc;
+    if (first + count > total) return pq_set_error(PEUQSE_ERR_INVALID, "range exceeds the number of sweep points");
+    cudaStream_t st = (cudaStream_t)stream;
+    PQ_CUDA_OK(cudaMemsetAsync(d_work, 0, PQ_SWEEP_TICKET_BYTES, st));
+#define P2_ARGS p, S, first, count, d_logp, threshold, d_acc, (long long*)d_keep_index, d_keep_logp, keep_capacity, (long long*)d_keep_count, d_work, st
+#define P2_L(KT, ...) return launch_pass2<PEUQSE_MODEL_LINEAR, KT>(P2_ARGS)
+#define P2_E(KT, ...) return launch_pass2<PEUQSE_MODEL_EXTERNAL, KT>(P2_ARGS)
+    PQ_SWEEP_DISPATCH((launch_pass2<PEUQSE_MODEL_QUADRATIC, 2>(P2_ARGS)), (launch_pass2<PEUQSE_MODEL_TPD2SITE, 6>(P2_ARGS)), P2_L, P2_E)
+#undef P2_L
+#undef P2_E
+    return pq_set_error(PEUQSE_ERR_INVALID, "unknown model");
+}
+
+extern "C" int peuqse_sweep_hist(const peuqse_problem* p, const peuqse_sweep_spec* spec, int64_t first, int64_t count,
+                                 const double* d_logp, double threshold, const double* d_edges, int32_t nbins,
+                                 uint64_t* d_hist, void* stream) {
+    int rc = check_sweep_args(p, spec, first, count);
+    if (rc) return rc;
+    if (!d_edges || !d_hist || nbins < 1 || nbins > 4096) return pq_set_error(PEUQSE_ERR_INVALID, "bad histogram arguments");
+    if (p->d.model_id == PEUQSE_MODEL_EXTERNAL && !d_logp) return pq_set_error(PEUQSE_ERR_INVALID, "external model needs d_logp");
+    DevSweep S;
+    long long total;
+    rc = build_sweep(spec, &S, &total);
+    if (rc) return rc;
+    if (first + count > total) return pq_set_error(PEUQSE_ERR_INVALID, "range exceeds the number of sweep points");
+    cudaStream_t st = (cudaStream_t)stream;
+#define P3_ARGS p, S, first, count, d_logp, threshold, d_edges, nbins, (unsigned long long*)d_hist, st
+#define P3_L(KT, ...) return launch_hist<PEUQSE_MODEL_LINEAR, KT>(P3_ARGS)
+#define P3_E(KT, ...) return launch_hist<PEUQSE_MODEL_EXTERNAL, KT>(P3_ARGS)
+    PQ_SWEEP_DISPATCH((launch_hist<PEUQSE_MODEL_QUADRATIC, 2>(P3_ARGS)), (launch_hist<PEUQSE_MODEL_TPD2SITE, 6>(P3_ARGS)), P3_L, P3_E)
+#undef P3_L
+#undef P3_E
+    return pq_set_error(PEUQSE_ERR_INVALID, "unknown model");
+}
+
+// raw Philox blocks (tests): d_out[count][4]
+__global__ void k_philox_blocks(unsigned long long seed, uint32_t stream_id, long long first, long long count,
+                                uint32_t block, uint32_t* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const Philox4 r = philox_block(seed, stream_id, (unsigned long long)(first + i), block);
+    out[4 * i + 0] = r.x; out[4 * i + 1] = r.y; out[4 * i + 2] = r.z; out[4 * i + 3] = r.w;
+}
+
+extern "C" int peuqse_philox_blocks(uint64_t seed, uint32_t rng_stream, int64_t first, int64_t count, uint32_t block,
+                                    uint32_t* d_out, void* stream) {
+    if (count <= 0) return PEUQSE_OK;
+    k_philox_blocks<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(seed, rng_stream, first, count, block, d_out);
+    PQ_CUDA_OK(cudaGetLastError());
+    return PEUQSE_OK;
+}

@@ -1,0 +1,102 @@
+"""Multi-GPU plumbing: one process per GPU (torch.distributed, NCCL over NVLink), contiguous index ranges or
+chain blocks per rank, and the three tiny collectives the sweeps / chains need.
+
+Replaces PEUQSE/parallel_processing.py + the pickle-file rendezvous of consolidate_parallel_sampling_data
+(PEUQSE/InverseProblem.py:1130-1155, 1209-1319): "keep only the best" for multistart becomes an all-gather
+of (maxLogP, first index) with a lowest-index tie-break (preserving the strict '>' of IP.py:933), and the
+statistics become one all-reduce(sum) of the moment accumulators plus min/max.  No data-path collective:
+points and chains are independent, so nothing is exchanged while kernels run.
+"""
+import numpy as np
+import torch
+
+try:
+    import torch.distributed as dist
+except Exception:  # pragma: no cover
+    dist = None
+
+
+def world():
+    if dist is not None and dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_range(total, rank=None, size=None):
+    """Contiguous global-index range [first, first+count) owned by `rank`."""
+    if rank is None:
+        rank, size = world()
+    first = (total * rank) // size
+    last = (total * (rank + 1)) // size
+    return first, last - first
+
+
+def _comm_device():
+    if dist.get_backend() == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
+def allreduce_np(a, op="sum"):
+    """All-reduce a small float64 numpy array; identity when not distributed."""
+    rank, size = world()
+    a = np.asarray(a, dtype=np.float64)
+    if size == 1:
+        return a
+    t = torch.from_numpy(a.copy()).to(_comm_device())
+    dist.all_reduce(t, op={"sum": dist.ReduceOp.SUM, "min": dist.ReduceOp.MIN, "max": dist.ReduceOp.MAX}[op])
+    return t.cpu().numpy()
+
+
+def allreduce_int_np(a):
+    rank, size = world()
+    a = np.asarray(a, dtype=np.int64)
+    if size == 1:
+        return a
+    t = torch.from_numpy(a.copy()).to(_comm_device())
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.cpu().numpy()
+
+
+def merge_best(pairs):
+    """pairs: iterable of (logp, index) with index -1 for 'none'.  Highest logp, lowest index among equals,
+    NaN / -inf never selected: the result the reference's sequential loop (IP.py:824, 933-938) would give."""
+    best_v, best_i = float("-inf"), -1
+    for v, i in pairs:
+        if i < 0 or not (v > float("-inf")):
+            continue
+        if v > best_v or (v == best_v and i < best_i):
+            best_v, best_i = float(v), int(i)
+    return best_v, best_i
+
+
+def allgather_best(logp, index):
+    rank, size = world()
+    if size == 1:
+        return merge_best([(logp, index)])
+    dev = _comm_device()
+    mine_v = torch.tensor([float(logp)], dtype=torch.float64, device=dev)
+    mine_i = torch.tensor([int(index)], dtype=torch.int64, device=dev)
+    vs = [torch.empty_like(mine_v) for _ in range(size)]
+    is_ = [torch.empty_like(mine_i) for _ in range(size)]
+    dist.all_gather(vs, mine_v)
+    dist.all_gather(is_, mine_i)
+    return merge_best([(float(v.item()), int(i.item())) for v, i in zip(vs, is_)])
+
+
+def allgather_rows(t):
+    """Concatenate a per-rank [n_r, ...] tensor along dim 0 over ranks (sample gather)."""
+    rank, size = world()
+    if size == 1:
+        return t
+    dev = _comm_device()
+    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=dev)
+    ns = [torch.empty_like(n) for _ in range(size)]
+    dist.all_gather(ns, n)
+    ns = [int(x.item()) for x in ns]
+    m = max(ns)
+    pad = torch.zeros((m,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+    pad[: t.shape[0]] = t.to(dev)
+    out = [torch.empty_like(pad) for _ in range(size)]
+    dist.all_gather(out, pad)
+    return torch.cat([o[:c] for o, c in zip(out, ns)], dim=0).to(t.device)

@@ -1,0 +1,486 @@
+"""parameter_estimation: the reference's user-facing class (PEUQSE/InverseProblem.py:25, "IP.py") with the
+log-posterior hot path and its three data-parallel drivers running as sm_100a CUDA kernels.
+
+Same names, argument meanings and return conventions as the reference for the accelerated path:
+getLogP / getLogPrior / getLogLikelihood (IP.py:1647, 2756, 2850), doMultiStart (1077),
+doMetropolisHastings (2563), doEnsembleSliceSampling (2362).  Everything outside that path (plots, file
+export, optimisers, design of experiments, MPI) is out of scope and raises NotImplementedError.
+"""
+import ctypes as C
+import sys
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import distributed as D
+from .models import BuiltinModel, TorchSimulator
+from .problem import DeviceProblem, build_host_problem
+from .sweep import Sweep, grid_size, make_spec
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        raise _lib.PeuqseError("peuqse_b200 needs a CUDA device: there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+class parameter_estimation:
+    software_name = "peuqse_b200"
+
+    def __init__(self, UserInput=None):
+        self.UserInput = UI = UserInput
+        pes = UI.parameter_estimation_settings
+        for key, default in (('mcmc_nchains', 1), ('mcmc_store_samples', 'auto'), ('mcmc_thin', 1),
+                             ('multistart_store_logP', 'auto'), ('multistart_random_seed', None),
+                             ('multistart_histogram_bins', 10)):
+            pes.setdefault(key, default)
+        if UI.model.get('custom_logLikelihood') is not None or UI.model.get('custom_logPrior') is not None:
+            raise NotImplementedError("custom_logLikelihood / custom_logPrior are Python callbacks per point; "
+                                      "not part of the accelerated path")
+        if len(UI.model.get('reducedParameterSpace', [])) or len(UI.responses.get('reducedResponseSpace', [])):
+            raise NotImplementedError("reduced parameter/response spaces are out of scope (DESIGN.md)")
+        if UI.responses.get('data_overcategory', '') != '':
+            raise NotImplementedError("response transforms (data_overcategory) are out of scope (DESIGN.md)")
+        self.parameterBoundsOn = bool(len(UI.model['InputParameterPriorValues_upperBounds']) +
+                                      len(UI.model['InputParameterPriorValues_lowerBounds']))          # IP.py:49
+        UI.InputParameterPriorValues_lowerBounds = UI.model['InputParameterPriorValues_lowerBounds']
+        UI.InputParameterPriorValues_upperBounds = UI.model['InputParameterPriorValues_upperBounds']
+        if len(UI.model['parameterNamesAndMathTypeExpressionsDict']) == 0:                             # IP.py:68-71
+            for i in range(len(UI.model['InputParameterPriorValues'])):
+                UI.model['parameterNamesAndMathTypeExpressionsDict'][str(i)] = 'ParInd_' + str(i)
+        UI.parameterNamesList = list(UI.model['parameterNamesAndMathTypeExpressionsDict'])
+        UI.user_requested_convergence_diagnostics = False
+
+        obs_unc = UI.responses['responses_observed_uncertainties']
+        observed = UI.responses['responses_observed']
+        if isinstance(obs_unc, (list, tuple, np.ndarray)) and len(obs_unc) == 0:
+            # blank list: 5 % of the value with an orthogonal 2 % of the maximum (IP.py:223-229)
+            from .problem import nest_responses
+            obs_n = nest_responses(observed)
+            obs_unc = [((np.abs(o) * 0.05) ** 2 + (np.max(np.abs(o)) * 0.02) ** 2) ** 0.5 for o in obs_n]
+            if len(obs_n) == 1:
+                obs_unc = obs_unc[0]
+        sim_unc = UI.model.get('responses_simulation_uncertainties')
+        if callable(sim_unc):
+            raise NotImplementedError("responses_simulation_uncertainties as a function of the parameters is a per-point "
+                                      "Python callback; not part of the accelerated path")
+        H = build_host_problem(UI.model['InputParameterPriorValues'], UI.model['InputParametersPriorValuesUncertainties'],
+                               observed, obs_unc,
+                               lower_bounds=UI.model['InputParameterPriorValues_lowerBounds'],
+                               upper_bounds=UI.model['InputParameterPriorValues_upperBounds'],
+                               scaling_type=pes['scaling_uncertainties_type'],
+                               simulation_uncertainties=sim_unc,
+                               max_covmat_size=UI.responses['responses_observed_max_covmat_size'])
+        self.host_problem = H
+        # reference-named derived fields, written back into UserInput as the reference does (IP.py:146-350)
+        UI.mu_prior, UI.std_prior, UI.var_prior, UI.covmat_prior = H.mu_prior, H.std_prior, H.var_prior, H.covmat_prior
+        UI.mu_prior_scaled, UI.var_prior_scaled, UI.covmat_prior_scaled = H.mu_prior_scaled, H.var_prior_scaled, H.covmat_prior_scaled
+        if H.scaling is not None:
+            UI.scaling_uncertainties = H.scaling
+        if H.uniform_idx is not None:
+            UI.InputParametersPriorValuesUniformDistributionsIndices = H.uniform_idx
+        UI.responses_observed = H.responses_observed
+        UI.responses_observed_transformed = H.responses_observed
+        UI.num_response_dimensions = len(H.responses_observed)
+        UI.num_data_points = int(sum(len(r) for r in H.responses_observed))
+        self.observed_responses_covmat_transformed = H.responses_cov
+        seed = pes.get('mcmc_random_seed')
+        if type(seed) == type(1):                                                                     # IP.py:191-193
+            np.random.seed(seed)
+        self.samples_of_prior = np.random.multivariate_normal(H.mu_prior, H.covmat_prior, pes['mcmc_length'])  # IP.py:194
+        self.Q_mu = H.mu_prior * 0                                                                    # IP.py:349
+        self.Q_covmat = H.covmat_prior                                                                # IP.py:350
+        guess = UI.model.get('InputParameterInitialGuess', [])
+        if isinstance(guess, str):
+            raise NotImplementedError("pickled initial guesses are file I/O; out of scope (DESIGN.md)")
+        if guess is None or len(guess) == 0:
+            guess = np.array(UI.model['InputParameterPriorValues'], dtype='float')                    # IP.py:383-384
+        UI.InputParameterInitialGuess = np.array(guess, dtype='float').reshape(-1)
+
+        sim = UI.model['simulateByInputParametersOnlyFunction']
+        if sim is None:
+            raise ValueError("UserInput.model['simulateByInputParametersOnlyFunction'] must be provided")
+        if UI.model.get('simulationOutputProcessingFunction') is not None and isinstance(sim, BuiltinModel):
+            raise NotImplementedError("simulationOutputProcessingFunction cannot follow a built-in CUDA model; fold it into a TorchSimulator")
+        if not isinstance(sim, (BuiltinModel, TorchSimulator)):
+            sim = TorchSimulator(sim)      # a bare callable is taken as a vectorised torch simulator (no CPU path)
+        self.simulator = sim
+        _dev()
+        self.device_problem = DeviceProblem(H, sim)
+        if isinstance(sim, BuiltinModel):
+            sim._owner = self
+        self._L = _lib.load()
+        self.k = H.k
+        self.prepareResponsesForSplitLikelihood = False   # the reference's fall-back mode is not replicated
+        self.gpu_launches = 0
+
+    # ------------------------------------------------------------------------------------------
+    # batched evaluation (device tensors in, device tensors out) -- the engine under everything else
+    # ------------------------------------------------------------------------------------------
+    def _as_theta(self, thetas):
+        t = torch.as_tensor(np.asarray(thetas, dtype=float) if not torch.is_tensor(thetas) else thetas,
+                            dtype=torch.float64)
+        if t.ndim == 1:
+            t = t.reshape(1, -1)
+        if t.shape[1] != self.k:
+            raise ValueError(f"expected {self.k} parameters per point, got {t.shape[1]}")
+        return t.to(_dev()).contiguous()
+
+    def simulate_batch(self, thetas):
+        """sim[B, n_total] (natural order) on the device."""
+        th = self._as_theta(thetas)
+        B = th.shape[0]
+        if isinstance(self.simulator, BuiltinModel):
+            out = torch.empty((B, self.host_problem.n_total), dtype=torch.float64, device=th.device)
+            _lib.check(self._L.peuqse_simulate_batch(self.device_problem.handle, _lib.ptr(th), B, _lib.ptr(out),
+                                                     _lib.current_stream()))
+            self.gpu_launches += 1
+            return out
+        out = self.simulator(th)
+        post = self.UserInput.model.get('simulationOutputProcessingFunction')
+        if post is not None:
+            out = post(out)
+        out = torch.as_tensor(out, dtype=torch.float64, device=th.device).reshape(B, -1).contiguous()
+        if out.shape[1] != self.host_problem.n_total:
+            raise ValueError(f"simulator returned {out.shape[1]} values per point, expected {self.host_problem.n_total}")
+        return out
+
+    def getLogP_batch(self, thetas, return_parts=False):
+        """logP[B] (and logPrior[B], logLikelihood[B]) as CUDA tensors for thetas[B,k]."""
+        th = self._as_theta(thetas)
+        B = th.shape[0]
+        logp = torch.empty(B, dtype=torch.float64, device=th.device)
+        lp = torch.empty(B, dtype=torch.float64, device=th.device) if return_parts else None
+        ll = torch.empty(B, dtype=torch.float64, device=th.device) if return_parts else None
+        h = self.device_problem.handle
+        if isinstance(self.simulator, BuiltinModel):
+            _lib.check(self._L.peuqse_logp_batch(h, _lib.ptr(th), B, _lib.ptr(logp), _lib.ptr(lp), _lib.ptr(ll),
+                                                 _lib.current_stream()))
+        else:
+            sim = self.simulate_batch(th)
+            _lib.check(self._L.peuqse_logp_from_sim(h, _lib.ptr(th), _lib.ptr(sim), B, _lib.ptr(logp), _lib.ptr(lp),
+                                                    _lib.ptr(ll), _lib.current_stream()))
+        self.gpu_launches += 1
+        return (logp, lp, ll) if return_parts else logp
+
+    # ------------------------------------------------------------------------------------------
+    # single-point API with the reference's signatures
+    # ------------------------------------------------------------------------------------------
+    def getLogP(self, proposal_sample):                                    # IP.py:1647
+        return float(self.getLogP_batch(proposal_sample)[0].item())
+
+    def getNegLogP(self, proposal_sample):                                 # IP.py:1656
+        return -1 * self.getLogP(proposal_sample)
+
+    def getLogPrior(self, discreteParameterVector):                        # IP.py:2756
+        return float(self.getLogP_batch(discreteParameterVector, return_parts=True)[1][0].item())
+
+    def getSimulatedResponses(self, discreteParameterVector):              # IP.py:2822
+        sim = self.simulate_batch(discreteParameterVector)[0].cpu().numpy()
+        out, off = [], 0
+        for r in self.host_problem.responses_observed:
+            out.append(sim[off:off + len(r)])
+            off += len(r)
+        self.lastSimulatedResponses = out
+        return out
+
+    def getLogLikelihood(self, discreteParameterVector):                   # IP.py:2850 -> (logLikelihood, simulatedResponses)
+        _, _, ll = self.getLogP_batch(discreteParameterVector, return_parts=True)
+        ll = float(ll[0].item())
+        if ll == float('-inf'):
+            return ll, None                                                # IP.py:2865, 2882
+        return ll, self.getSimulatedResponses(discreteParameterVector)
+
+    # ------------------------------------------------------------------------------------------
+    # multistart
+    # ------------------------------------------------------------------------------------------
+    def getGridPermutations(self, gridCenterVector, gridsearchSamplingInterval, gridsearchSamplingRadii):
+        """Resolves the defaults like IP.py:755-770; returns (center, interval, radii, numPermutations)."""
+        k = len(gridCenterVector)
+        radii = np.ones(k, dtype='int') if len(gridsearchSamplingRadii) == 0 else np.array(gridsearchSamplingRadii, dtype='int')
+        if len(gridsearchSamplingInterval) == 0:
+            interval = np.asarray(self.UserInput.std_prior, dtype=float)    # IP.py:767
+            if interval.ndim != 1:
+                raise ValueError("the default grid interval needs 1-D prior uncertainties (SURVEY Q15)")
+        else:
+            interval = np.array(gridsearchSamplingInterval, dtype='float')
+        return np.asarray(gridCenterVector, dtype=float), interval, radii, grid_size(radii)
+
+    def generateInitialPoints(self, numStartPoints=0, initialPointsDistributionType='uniform',
+                              relativeInitialDistributionSpread=1.0, numParameters=0, centerPoint=None,
+                              gridsearchSamplingInterval=[], gridsearchSamplingRadii=[], seed=None):
+        """IP.py:684-750.  'grid' and 'uniform' are generated on the device (index-addressed: grid decode /
+        Philox); the quasi-random and Gaussian variants are drawn on the host exactly like the reference."""
+        if str(centerPoint).lower() == 'none':
+            centerPoint = np.array(self.UserInput.InputParameterInitialGuess) * 1.0
+        centerPoint = np.asarray(centerPoint, dtype=float)
+        kind = initialPointsDistributionType.lower()
+        if kind not in ['grid', 'uniform', 'identical', 'gaussian', 'astroidal', 'sobol', 'shell']:
+            kind = 'sobol'                                                                             # IP.py:693-695
+        k = len(centerPoint) if numParameters == 0 else numParameters
+        if kind == 'grid':
+            c, h, r, n = self.getGridPermutations(centerPoint, gridsearchSamplingInterval, gridsearchSamplingRadii)
+            spec = make_spec("grid", k, c, interval=h, radii=r)
+            return self._points_from_spec(spec, 0, n)
+        if numStartPoints == 0:
+            numStartPoints = getattr(self, 'mcmc_nwalkers', 0) or 3 * k
+        std = np.asarray(self.UserInput.std_prior, dtype=float)
+        if kind == 'uniform':
+            if seed is None:
+                seed = self._sweep_seed()
+            spec = make_spec("uniform", k, centerPoint, spread=relativeInitialDistributionSpread, std_prior=std, seed=seed)
+            return self._points_from_spec(spec, 0, numStartPoints)
+        if kind == 'identical':
+            first = np.zeros((numStartPoints, k))
+        elif kind == 'gaussian':
+            first = np.random.randn(numStartPoints, k)                                                  # IP.py:710
+        else:
+            from warnings import catch_warnings, simplefilter
+            from scipy.stats import qmc
+            with catch_warnings():
+                simplefilter("ignore")
+                sob = qmc.Sobol(d=k, scramble=True).random(numStartPoints)                              # IP.py:718-721, 741-744
+            if kind == 'sobol':
+                first = -2 + 4 * sob                                                                    # IP.py:746
+            else:
+                first = -1 + 2 * sob
+                neg = np.ones((numStartPoints, k), dtype=int)
+                neg[first < 0] = -1
+                first = np.abs(first)
+                first = first ** k if kind == 'astroidal' else first ** (1 / k)                         # IP.py:729-732
+                first = neg * first
+                first *= 2
+        return relativeInitialDistributionSpread * first * std + centerPoint                           # IP.py:749
+
+    def _points_from_spec(self, spec, first, count):
+        th = torch.empty((count, spec.k), dtype=torch.float64, device=_dev())
+        _lib.check(self._L.peuqse_sweep_points(C.byref(spec), int(first), int(count), _lib.ptr(th), _lib.current_stream()))
+        self.gpu_launches += 1
+        return th.cpu().numpy()
+
+    def _sweep_seed(self):
+        pes = self.UserInput.parameter_estimation_settings
+        s = pes.get('multistart_random_seed')
+        if s is None:
+            s = pes.get('mcmc_random_seed')
+        return 0 if s is None else int(s)
+
+    def doMultiStart(self, searchType='UserChoice', numStartPoints='UserChoice', relativeInitialDistributionSpread='UserChoice',
+                     exportLog='UserChoice', initialPointsDistributionType='UserChoice', passThroughArgs='UserChoice',
+                     calculatePostBurnInStatistics='UserChoice', keep_cumulative_post_burn_in_data='UserChoice',
+                     walkerInitialDistribution='UserChoice', centerPoint=None, gridsearchSamplingInterval='UserChoice',
+                     gridsearchSamplingRadii='UserChoice'):
+        """IP.py:1077-1117 for searchType 'getLogP'.  Returns bestResultSoFar = [map_parameter_set, None x 6]."""
+        pes = self.UserInput.parameter_estimation_settings
+        if str(searchType) == 'UserChoice': searchType = pes['multistart_searchType']
+        if str(initialPointsDistributionType) == 'UserChoice': initialPointsDistributionType = pes['multistart_initialPointsDistributionType']
+        if str(numStartPoints) == 'UserChoice': numStartPoints = pes['multistart_numStartPoints']
+        if str(relativeInitialDistributionSpread) == 'UserChoice': relativeInitialDistributionSpread = pes['multistart_relativeInitialDistributionSpread']
+        if str(gridsearchSamplingInterval) == 'UserChoice': gridsearchSamplingInterval = pes['multistart_gridsearchSamplingInterval']
+        if str(gridsearchSamplingRadii) == 'UserChoice': gridsearchSamplingRadii = pes['multistart_gridsearchSamplingRadii']
+        if str(calculatePostBurnInStatistics) == 'UserChoice': calculatePostBurnInStatistics = pes['multistart_calculatePostBurnInStatistics']
+        if numStartPoints == 0: numStartPoints = len(self.UserInput.InputParameterInitialGuess) * 3     # IP.py:1101-1102
+        if relativeInitialDistributionSpread == 0: relativeInitialDistributionSpread = 0.866           # IP.py:1103-1104
+        if searchType in ('doGetLogP', 'doSinglePoint'): searchType = 'getLogP'                        # IP.py:1105-1106
+        if searchType != 'getLogP':
+            raise NotImplementedError(f"multistart searchType '{searchType}' (an optimiser or a whole MCMC run per start point) "
+                                      "is outside the accelerated path; use 'getLogP'")
+        if str(centerPoint).lower() == 'none':
+            centerPoint = np.array(self.UserInput.InputParameterInitialGuess) * 1.0
+        centerPoint = np.asarray(centerPoint, dtype=float)
+        kind = initialPointsDistributionType.lower()
+        toSamples = bool(pes['multistart_permutationsToSamples']) and kind in ('grid', 'uniform', 'sobol', 'astroidal', 'shell')
+        coef = pes['multistart_permutationsToSamples_threshold_filter_coefficient']
+        coef = 2.0 if str(coef).lower() == 'auto' else float(coef)                                      # IP.py:1011-1014
+        nbins = int(pes.get('multistart_histogram_bins', 10))
+        k = self.k
+        if kind == 'grid':
+            c, h, r, n = self.getGridPermutations(centerPoint, gridsearchSamplingInterval, gridsearchSamplingRadii)
+            spec = make_spec("grid", k, c, interval=h, radii=r)
+        elif kind == 'uniform':
+            n = int(numStartPoints)
+            spec = make_spec("uniform", k, centerPoint, spread=relativeInitialDistributionSpread,
+                             std_prior=np.asarray(self.UserInput.std_prior, dtype=float), seed=self._sweep_seed())
+        else:
+            pts = self.generateInitialPoints(numStartPoints=numStartPoints, initialPointsDistributionType=kind,
+                                             relativeInitialDistributionSpread=relativeInitialDistributionSpread,
+                                             centerPoint=centerPoint)
+            return self.doListOfPermutationsSearch(pts, searchType='getLogP', permutationsToSamples=toSamples,
+                                                   calculatePostBurnInStatistics=calculatePostBurnInStatistics, centerPoint=centerPoint)
+        if not isinstance(self.simulator, BuiltinModel) or self.host_problem.resp_mode.max() == _lib.RESP_MVN_FULL:
+            # torch-callable simulators / full covariance: decode points in chunks and use the batched path
+            return self._multistart_external(spec, n, toSamples and calculatePostBurnInStatistics, coef, nbins, centerPoint)
+        store = pes.get('multistart_store_logP', 'auto')
+        store = (n <= 2 ** 31) if store == 'auto' else bool(store)
+        sw = Sweep(self.device_problem, spec, n, store_logp=store)
+        res = sw.run(coef=coef, nbins=nbins, statistics=bool(toSamples and calculatePostBurnInStatistics))
+        self.gpu_launches += sw.launches
+        self._sweep = sw
+        return self._adopt_sweep_result(res, centerPoint)
+
+    def _adopt_sweep_result(self, res, centerPoint):
+        self.sweep_result = res
+        self.highest_logP = res.map_logP                                                               # IP.py:935
+        self.map_logP = res.map_logP                                                                   # IP.py:973
+        self.map_parameter_set = res.map_parameter_set
+        self.map_index = res.map_index
+        self.UserInput.InputParameterInitialGuess = centerPoint                                        # IP.py:971
+        if getattr(res, 'statistics', False):
+            self.mu_AP_parameter_set = res.mu_AP_parameter_set
+            self.stdap_parameter_set = res.stdap_parameter_set
+            self.evidence = res.evidence
+            self.info_gain = None      # the reference's log-ratio branch has no priors vector here
+            self.marginal_histograms = (res.histogram_counts, res.histogram_edges)
+        return [self.map_parameter_set, None, None, None, None, None, None]                            # IP.py:862, 1074
+
+    def doGridSearch(self, searchType='getLogP', gridSamplingAbsoluteIntervalSize=[], gridSamplingNumOfIntervals=[], **kw):
+        """Deprecated alias kept by the reference (IP.py:1120-1128)."""
+        return self.doMultiStart(searchType=searchType, initialPointsDistributionType='grid',
+                                 gridsearchSamplingInterval=gridSamplingAbsoluteIntervalSize,
+                                 gridsearchSamplingRadii=gridSamplingNumOfIntervals)
+
+    # lazily materialised big arrays of the reference's object state --------------------------------
+    @property
+    def permutations_MAP_logP_and_parameters_values(self):
+        """[N, 1+k] = hstack((logP, theta)) of every point, in list order (IP.py:947, 1004).  Materialised on
+        demand: 8*(1+k)*N bytes cross PCIe."""
+        if hasattr(self, '_perm_array'):
+            return self._perm_array
+        sw = self._sweep
+        if D.world()[1] != 1:
+            raise NotImplementedError("gather of all sweep points across ranks is not provided; use rank-local ranges")
+        if sw.logp is None:
+            raise _lib.PeuqseError("logP was not stored for this sweep (multistart_store_logP)")
+        th = sw.points(sw.first, sw.count)
+        return torch.cat([sw.logp.reshape(-1, 1), th], dim=1).cpu().numpy()
+
+    @property
+    def listOfPermutations(self):
+        if hasattr(self, '_list_of_permutations'):
+            return self._list_of_permutations
+        sw = self._sweep
+        return sw.points(0, sw.total).cpu().numpy()
+
+    def doListOfPermutationsSearch(self, listOfPermutations, numPermutations=None, searchType='getLogP', exportLog=True,
+                                   walkerInitialDistribution='UserChoice', passThroughArgs={}, calculatePostBurnInStatistics=True,
+                                   keep_cumulative_post_burn_in_data=False, centerPoint=None, permutationsToSamples=False):
+        """IP.py:772-1074 for an explicit list of points and searchType 'getLogP': one batched evaluation."""
+        if searchType in ('doGetLogP', 'doSinglePoint'): searchType = 'getLogP'
+        if searchType != 'getLogP':
+            raise NotImplementedError("only searchType 'getLogP' is accelerated")
+        pes = self.UserInput.parameter_estimation_settings
+        pts = np.asarray([np.asarray(p, dtype=float) for p in listOfPermutations], dtype=float)
+        self._list_of_permutations = pts
+        if str(centerPoint).lower() == 'none':
+            centerPoint = np.array(self.UserInput.InputParameterInitialGuess) * 1.0
+        logp = self.getLogP_batch(pts).cpu().numpy()
+        self._perm_array = np.hstack([logp.reshape(-1, 1), pts])
+        res = self._reduce_list(logp, pts, permutationsToSamples and calculatePostBurnInStatistics,
+                                pes['multistart_permutationsToSamples_threshold_filter_coefficient'],
+                                int(pes.get('multistart_histogram_bins', 10)))
+        return self._adopt_sweep_result(res, centerPoint)
+
+    def _reduce_list(self, logp, pts, statistics, coef, nbins):
+        """Small explicit lists: the reductions on the host in numpy (same formulas as the kernels)."""
+        from .sweep import SweepResult
+        coef = 2.0 if str(coef).lower() == 'auto' else float(coef)
+        R = SweepResult()
+        lp = np.where(np.isnan(logp), -np.inf, logp)
+        R.total = len(lp)
+        if len(lp) == 0 or not np.any(lp > -np.inf):
+            R.map_logP, R.map_index, R.map_parameter_set, R.statistics = float('-inf'), -1, np.full(self.k, np.nan), False
+            return R
+        i = int(np.argmax(lp))                                           # first maximum == strict '>' loop (IP.py:933)
+        R.map_logP, R.map_index, R.map_parameter_set = float(lp[i]), i, pts[i].copy()
+        R.statistics = bool(statistics)
+        if not statistics:
+            return R
+        thr = R.map_logP + np.log(10 ** (-1 * coef))
+        with np.errstate(over='ignore', invalid='ignore'):
+            w = np.where(lp > thr, np.trunc(np.exp(lp - thr)), 0.0)
+        keep = w > 0
+        W = w.sum()
+        R.threshold, R.sum_weights, R.n_retained = float(thr), W, int(keep.sum())
+        R.mu_AP_parameter_set = (w[:, None] * pts).sum(axis=0) / W
+        dlt = pts - R.mu_AP_parameter_set
+        R.posterior_covariance = (w[:, None, None] * dlt[:, :, None] * dlt[:, None, :]).sum(axis=0) / W
+        R.stdap_parameter_set = np.sqrt(np.diag(R.posterior_covariance))
+        R.evidence = ((w * np.exp(lp)).sum() / W) / np.sqrt((w[:, None] * pts ** 2).sum())
+        R.retained_min, R.retained_max = pts[keep].min(axis=0), pts[keep].max(axis=0)
+        hs, es = [], []
+        for d in range(self.k):
+            h, e = np.histogram(pts[keep, d], bins=nbins, weights=w[keep])
+            hs.append(h.astype(np.int64)); es.append(e)
+        R.histogram_counts, R.histogram_edges = np.array(hs), np.array(es)
+        return R
+
+    def _multistart_external(self, spec, n, statistics, coef, nbins, centerPoint, chunk=1 << 22):
+        """Sweep with a torch-callable simulator or full-covariance responses: points are decoded on the device
+        in chunks, simulated by the callable, evaluated by logp_from_sim; logP stays in HBM for passes 2-3."""
+        if D.world()[1] != 1:
+            raise NotImplementedError("external-simulator sweeps are single-GPU for now")
+        sw = Sweep(self.device_problem, spec, n, store_logp=True)
+        for first in range(0, n, chunk):
+            cnt = min(chunk, n - first)
+            th = sw.points(first, cnt)
+            sw.logp[first:first + cnt] = self.getLogP_batch(th)
+        lp = torch.where(torch.isnan(sw.logp), torch.full_like(sw.logp, float('-inf')), sw.logp)
+        from .sweep import SweepResult
+        R = SweepResult()
+        R.total = n
+        mx = float(lp.max().item()) if n else float('-inf')
+        if not (mx > float('-inf')):
+            R.map_logP, R.map_index, R.map_parameter_set, R.statistics = float('-inf'), -1, np.full(self.k, np.nan), False
+            self._sweep = sw
+            return self._adopt_sweep_result(R, centerPoint)
+        idx = int(torch.nonzero(lp == mx)[0].item())                      # first maximum
+        pts_logp = lp.cpu().numpy()
+        pts = sw.points(0, n).cpu().numpy()
+        self._sweep = sw
+        self._list_of_permutations = pts
+        self._perm_array = np.hstack([sw.logp.cpu().numpy().reshape(-1, 1), pts])
+        assert idx == int(np.argmax(pts_logp))
+        res = self._reduce_list(sw.logp.cpu().numpy(), pts, statistics, coef, nbins)
+        return self._adopt_sweep_result(res, centerPoint)
+
+    def expandedPostBurnInSamples(self, max_rows=50_000_000):
+        """post_burn_in_samples of a permutationsToSamples run: every retained point repeated
+        int(exp(logP - threshold)) times in list order (IP.py:3480-3491).  Built on demand."""
+        res = self.sweep_result
+        arr = self.permutations_MAP_logP_and_parameters_values
+        with np.errstate(over='ignore', invalid='ignore'):
+            w = np.where(arr[:, 0] > res.threshold, np.trunc(np.exp(arr[:, 0] - res.threshold)), 0).astype(np.int64)
+        if w.sum() > max_rows:
+            raise MemoryError(f"{int(w.sum())} expanded rows requested; use the weighted statistics instead")
+        exp = np.repeat(arr, w, axis=0)
+        self.post_burn_in_samples = exp[:, 1:]
+        self.post_burn_in_log_posteriors_un_normed_vec = exp[:, 0:1]
+        return self.post_burn_in_samples
+
+    # ------------------------------------------------------------------------------------------
+    # Metropolis-Hastings
+    # ------------------------------------------------------------------------------------------
+    def doMetropolisHastings(self, calculatePostBurnInStatistics=True, mcmc_exportLog='UserChoice', continueSampling='auto'):
+        from .mcmc import run_metropolis_hastings
+        return run_metropolis_hastings(self, calculatePostBurnInStatistics, continueSampling)
+
+    def doEnsembleSliceSampling(self, mcmc_nwalkers_direct_input=None, walkerInitialDistribution='UserChoice',
+                                walkerInitialDistributionSpread='UserChoice', movesType='UserChoice',
+                                calculatePostBurnInStatistics=True, mcmc_exportLog='UserChoice', continueSampling='auto'):
+        from .mcmc import run_ensemble_slice_sampling
+        return run_ensemble_slice_sampling(self, mcmc_nwalkers_direct_input, walkerInitialDistribution,
+                                           walkerInitialDistributionSpread, movesType, calculatePostBurnInStatistics,
+                                           continueSampling)
+
+    def calculatePostBurnInStatistics(self, calculate_post_burn_in_log_priors_vec=False):
+        from .mcmc import post_burn_in_statistics
+        return post_burn_in_statistics(self, calculate_post_burn_in_log_priors_vec)
+
+    # out of scope ------------------------------------------------------------------------------
+    def _out_of_scope(self, *a, **k):
+        raise NotImplementedError("outside the accelerated hot path (see DESIGN.md, 'Out of scope')")
+
+    createAllPlots = makeHistogramsForEachParameter = makeSamplingScatterMatrixPlot = createSimulatedResponsesPlots = _out_of_scope
+    doOptimizeNegLogP = doOptimizeLogP = doOptimizeSSR = doEnsembleModifiedMHSampling = _out_of_scope
+    doeGetInfoGainMatrix = doeParameterModulationPermutationsScanner = save_to_dill = load_from_dill = _out_of_scope

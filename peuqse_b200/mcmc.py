@@ -1,0 +1,348 @@
+"""Host drivers of the persistent MCMC kernels and the post-burn-in statistics.
+
+doMetropolisHastings (PEUQSE/InverseProblem.py:2563-2754, "IP.py"), doEnsembleSliceSampling (IP.py:2362-2547,
+engine = zeus) and calculatePostBurnInStatistics (IP.py:1861-1937).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import distributed as D
+
+
+def _dev():
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def step_cholesky(Q_covmat, step):
+    """Lower Cholesky factor of the proposal covariance Q_covmat*step (IP.py:2630: proposals are
+    theta + N(Q_mu=0, Q_covmat*mcmc_relative_step_length))."""
+    Q = np.asarray(Q_covmat, dtype=float) * step
+    if np.count_nonzero(Q - np.diag(np.diagonal(Q))) == 0:
+        return np.diag(np.sqrt(np.diagonal(Q)))
+    return np.linalg.cholesky(Q)
+
+
+def mh_launch(pe, theta0, n_steps, burn_in, seed, step_chol, first_step=0, chain_offset=0, modulate=0.0, thin=1,
+              store_samples=True, store_parts=True, export_draws=False):
+    """One call of peuqse_mh_run for C chains starting at theta0[C,k].  Returns a dict of device tensors."""
+    L = _lib.load()
+    dev = _dev()
+    th0 = torch.as_tensor(np.asarray(theta0, dtype=float), dtype=torch.float64).reshape(-1, pe.k).to(dev).contiguous()
+    Cn, k = th0.shape
+    spec = _lib.MHSpec()
+    spec.n_chains, spec.n_steps, spec.burn_in, spec.first_step = Cn, int(n_steps), int(burn_in), int(first_step)
+    spec.chain_offset, spec.seed, spec.modulate, spec.k, spec.thin = int(chain_offset), int(seed) & (2 ** 64 - 1), float(modulate), k, int(thin)
+    flat = np.asarray(step_chol, dtype=float).reshape(-1)
+    for i, v in enumerate(flat):
+        spec.step_chol[i] = float(v)
+    R = (int(n_steps) + thin - 1) // thin
+    lay = _lib.mh_stat_layout(k)
+    out = {}
+    out['samples'] = torch.empty((R, Cn, k), dtype=torch.float64, device=dev) if store_samples else None
+    out['logp'] = torch.empty((R, Cn), dtype=torch.float64, device=dev) if store_samples else None
+    out['logprior'] = torch.empty((R, Cn), dtype=torch.float64, device=dev) if (store_samples and store_parts) else None
+    out['loglik'] = torch.empty((R, Cn), dtype=torch.float64, device=dev) if (store_samples and store_parts) else None
+    out['deltas'] = torch.empty((max(n_steps - 1, 0), Cn, k), dtype=torch.float64, device=dev) if export_draws else None
+    out['us'] = torch.empty((max(n_steps - 1, 0), Cn), dtype=torch.float64, device=dev) if export_draws else None
+    out['stats'] = torch.empty((Cn, lay['SIZE']), dtype=torch.float64, device=dev)
+    _lib.check(L.peuqse_mh_run(pe.device_problem.handle, C.byref(spec), _lib.ptr(th0), _lib.ptr(out['samples']),
+                               _lib.ptr(out['logp']), _lib.ptr(out['logprior']), _lib.ptr(out['loglik']),
+                               _lib.ptr(out['deltas']), _lib.ptr(out['us']), _lib.ptr(out['stats']), _lib.current_stream()))
+    pe.gpu_launches += 1
+    out['theta0'] = th0
+    return out
+
+
+def chain_moments(stats, theta0, k, n_rows):
+    """Pooled mean / covariance / MAP over chains from the per-chain statistics blocks (host, tiny)."""
+    lay = _lib.mh_stat_layout(k)
+    st = stats.cpu().numpy()
+    th0 = theta0.cpu().numpy()
+    Cn = st.shape[0]
+    S1 = st[:, lay['S1']:lay['S1'] + k]
+    S2 = st[:, lay['S2']:lay['S2'] + k * k].reshape(Cn, k, k)
+    ref = th0[0]
+    sh = th0 - ref                                                     # shift of each chain's origin
+    # sums about the common origin `ref`
+    T1 = (S1 + n_rows * sh).sum(axis=0)
+    T2 = (S2 + S1[:, :, None] * sh[:, None, :] + sh[:, :, None] * S1[:, None, :] + n_rows * sh[:, :, None] * sh[:, None, :]).sum(axis=0)
+    N = float(n_rows) * Cn
+    tot = np.array([N])
+    T1, T2, tot = D.allreduce_np(T1), D.allreduce_np(T2.reshape(-1)).reshape(k, k), D.allreduce_np(tot)
+    N = tot[0]
+    m1 = T1 / N
+    cov = T2 / N - np.outer(m1, m1)
+    i = int(np.argmax(st[:, lay['MAPLOGP']]))
+    return dict(mean=ref + m1, cov=cov, std=np.sqrt(np.maximum(np.diag(cov), 0)), n=N,
+                map_logP=float(st[i, lay['MAPLOGP']]), map_theta=st[i, lay['MAPTHETA']:lay['MAPTHETA'] + k].copy(),
+                map_chain=i, accept_rate=st[:, lay['NACC']], sumexp=float(st[:, lay['SUMEXP']].sum()))
+
+
+def run_metropolis_hastings(pe, calculatePostBurnInStatistics=True, continueSampling='auto'):
+    UI = pe.UserInput
+    pes = UI.parameter_estimation_settings
+    if hasattr(UI, 'last_MCMC_run_type') and UI.last_MCMC_run_type != 'MH':                       # IP.py:2565-2569
+        print("ERROR: Two different algorithms of MCMC runs were attempted with the same UserInput."); raise SystemExit
+    if pes['mcmc_mode'] != 'unbiased':
+        raise NotImplementedError("mcmc_mode 'MAP_finding' (polyfit-driven step adaptation, IP.py:2631-2713) is outside the accelerated path")
+    if continueSampling == 'auto':                                                                   # IP.py:2572-2578
+        if ('mcmc_continueSampling' not in pes) or pes['mcmc_continueSampling'] == 'auto':
+            continueSampling = hasattr(pe, 'mcmc_last_point_sampled')
+        else:
+            continueSampling = pes['mcmc_continueSampling']
+    Lm = int(pes['mcmc_length'])
+    burn = int(Lm * 0.1) if str(pes['mcmc_burn_in']).lower() == 'auto' else int(pes['mcmc_burn_in'])  # IP.py:2599-2600
+    Cn = int(pes.get('mcmc_nchains', 1))
+    first_step = 0
+    if continueSampling:
+        burn = 0                                                                                     # IP.py:2601-2602
+        start = np.asarray(pe.mcmc_last_point_sampled, dtype=float).reshape(-1, pe.k)
+        pe.last_post_burn_in_log_posteriors_un_normed_vec = np.array(pe.post_burn_in_log_posteriors_un_normed_vec)
+        pe.last_post_burn_in_samples = np.array(pe.post_burn_in_samples)
+        first_step = getattr(pe, '_mh_steps_done', 0)
+    else:
+        start = np.tile(np.asarray(UI.InputParameterInitialGuess, dtype=float), (Cn, 1))              # IP.py:2610
+    seed = pes.get('mcmc_random_seed')
+    seed = int(np.random.SeedSequence().entropy % (2 ** 63)) if not isinstance(seed, int) else seed
+    rank, size = D.world()
+    c0, cn = D.shard_range(Cn, rank, size)
+    chol = step_cholesky(pe.Q_covmat, pes['mcmc_relative_step_length'])
+    store = pes.get('mcmc_store_samples', 'auto')
+    thin = int(pes.get('mcmc_thin', 1))
+    if store == 'auto':
+        store = (Lm // thin) * cn * (pe.k + 3) * 8 <= 64 * 2 ** 30
+    out = mh_launch(pe, start[c0:c0 + cn], Lm, burn, seed, chol, first_step=first_step, chain_offset=c0,
+                    modulate=float(pes['mcmc_modulate_accept_probability']), thin=thin, store_samples=bool(store))
+    pe._mh_steps_done = first_step + Lm
+    pe._mh_out = out
+    UI.last_MCMC_run_type = 'MH'                                                                     # IP.py:2729
+    n_rows = Lm - burn
+    mom = chain_moments(out['stats'], out['theta0'], pe.k, n_rows)
+    pe.mcmc_acceptance_rate = float(np.mean(mom['accept_rate'])) / max(Lm - 1, 1)
+    pe.mcmc_chain_moments = mom
+    lay = _lib.mh_stat_layout(pe.k)
+    last = out['stats'][:, lay['LAST']:lay['LAST'] + pe.k].cpu().numpy()
+    pe.mcmc_last_point_sampled = last[0] if Cn == 1 else last                                        # IP.py:2725
+    if not store:
+        # statistics from the in-kernel accumulators only (no tail filter: it needs every row)
+        pe.map_logP, pe.map_parameter_set = mom['map_logP'], mom['map_theta']
+        pe.mu_AP_parameter_set, pe.stdap_parameter_set = mom['mean'], mom['std']
+        pe.evidence, pe.info_gain = None, None
+        pe.post_burn_in_samples = None
+        return [pe.map_parameter_set, pe.mu_AP_parameter_set, pe.stdap_parameter_set, pe.evidence, pe.info_gain, None, None]
+    b = burn // thin
+    S = out['samples']                                                                                # [R, C, k]
+    pe.discrete_chains_post_burn_in_samples = D.allgather_rows(S[b:].permute(1, 0, 2).contiguous()).permute(1, 0, 2).cpu().numpy()
+    # chain-major stacking = consolidate_parallel_sampling_data('equal'): vstack of every chain's rows (IP.py:1282-1319)
+    flat = lambda t: D.allgather_rows(t.permute(1, 0, *range(2, t.ndim)).contiguous()).reshape(-1, *t.shape[2:]).cpu().numpy()
+    pe.post_burn_in_samples = flat(S[b:])                                                             # IP.py:2718
+    pe.post_burn_in_log_posteriors_un_normed_vec = flat(out['logp'][b:]).reshape(-1, 1)               # IP.py:2724
+    pe.post_burn_in_log_likelihoods_vec = flat(out['loglik'][b:]).reshape(-1, 1)                      # IP.py:2726
+    pe.post_burn_in_log_priors_vec = flat(out['logprior'][b:]).reshape(-1, 1)                         # IP.py:2727
+    if not continueSampling:
+        pe.during_burn_in_samples = flat(S[:b])                                                       # IP.py:2716
+        pe.during_burn_in_log_posteriors_un_normed_vec = flat(out['logp'][:b]).reshape(-1, 1)
+    else:
+        pe.post_burn_in_samples = np.vstack((pe.last_post_burn_in_samples, pe.post_burn_in_samples))  # IP.py:2731-2733
+        pe.post_burn_in_log_posteriors_un_normed_vec = np.vstack((pe.last_post_burn_in_log_posteriors_un_normed_vec,
+                                                                  pe.post_burn_in_log_posteriors_un_normed_vec))
+    if calculatePostBurnInStatistics:
+        post_burn_in_statistics(pe, calculate_post_burn_in_log_priors_vec=bool(continueSampling))
+        return [pe.map_parameter_set, pe.mu_AP_parameter_set, pe.stdap_parameter_set, pe.evidence, pe.info_gain,
+                pe.post_burn_in_samples, pe.post_burn_in_log_posteriors_un_normed_vec]               # IP.py:2749
+    lp = pe.post_burn_in_log_posteriors_un_normed_vec
+    pe.map_logP = max(lp)                                                                             # IP.py:2751-2754
+    pe.map_index = list(lp).index(pe.map_logP)
+    pe.map_parameter_set = pe.post_burn_in_samples[pe.map_index]
+    return pe.map_logP
+
+
+def array_threshold_filter(merged, key, threshold, remove='below'):
+    """arrayThresholdFilter (IP.py:3635-3664): drop the rows whose key is beyond the threshold."""
+    key = np.asarray(key).reshape(-1)
+    bad = key > threshold if remove == 'above' else key < threshold
+    return merged[~bad]
+
+
+def post_burn_in_statistics(pe, calculate_post_burn_in_log_priors_vec=False):
+    """calculatePostBurnInStatistics (IP.py:1861-1937) on the host arrays, including the default tail filter
+    (Q9: log(-logP) > mean + 2 sigma removed) and the KL-divergence information gain (IP.py:1770-1794)."""
+    pes = pe.UserInput.parameter_estimation_settings
+    if not hasattr(pe, 'post_burn_in_log_priors_vec') or pe.post_burn_in_log_priors_vec is None:
+        calculate_post_burn_in_log_priors_vec = True
+    if calculate_post_burn_in_log_priors_vec:                                                         # IP.py:1865-1869
+        _, lp, _ = pe.getLogP_batch(pe.post_burn_in_samples, return_parts=True)
+        pe.post_burn_in_log_priors_vec = lp.cpu().numpy().reshape(-1, 1)
+    if bool(pes['mcmc_threshold_filter_samples']):
+        coef = pes['mcmc_threshold_filter_coefficient']
+        coef = 2.0 if (isinstance(coef, str) and coef.lower() == 'auto') else coef
+        logp = pe.post_burn_in_log_posteriors_un_normed_vec
+        merged = np.hstack((logp, pe.post_burn_in_log_priors_vec, pe.post_burn_in_samples))
+        with np.errstate(invalid='ignore', divide='ignore'):
+            logNeg = np.log(-1 * logp)                                                                # IP.py:1894
+        bench = pes['mcmc_threshold_filter_benchmark']
+        if bench == 'mu_AP':
+            thr = pe.getLogP(np.mean(pe.post_burn_in_samples, axis=0)) - coef                         # IP.py:1899-1906
+            merged = array_threshold_filter(merged, logp, thr, 'below')
+        elif bench == 'MAP':
+            merged = array_threshold_filter(merged, logp, np.max(logp) - coef, 'below')               # IP.py:1909-1912
+        else:
+            thr = np.mean(logNeg) + coef * np.std(logNeg)                                             # IP.py:1915
+            merged = array_threshold_filter(merged, logNeg, thr, 'above')
+        pe.post_burn_in_log_posteriors_un_normed_vec = np.atleast_2d(merged[:, 0]).transpose()
+        pe.post_burn_in_log_priors_vec = np.atleast_2d(merged[:, 1]).transpose()
+        pe.post_burn_in_samples = merged[:, 2:]
+    S = pe.post_burn_in_samples
+    lp = pe.post_burn_in_log_posteriors_un_normed_vec
+    pe.mu_AP_parameter_set = np.mean(S, axis=0)                                                       # IP.py:1923
+    pe.stdap_parameter_set = np.std(S, axis=0)                                                        # IP.py:1924
+    map_logP = max(lp)                                                                                # IP.py:1925
+    pe.map_logP = map_logP
+    pe.map_index = list(lp).index(map_logP)
+    pe.map_parameter_set = S[pe.map_index]
+    pe.evidence = np.mean(np.exp(lp)) / np.linalg.norm(S)                                             # IP.py:1931
+    pe.info_gain = calculate_info_gain(pe)
+    return [pe.map_parameter_set, pe.mu_AP_parameter_set, pe.stdap_parameter_set, pe.evidence, pe.info_gain, S, lp]
+
+
+def calculate_info_gain(pe):
+    """calculateInfoGain (IP.py:1770-1847): KL divergence from 100-bin histograms over the joint range of the
+    prior samples and the posterior samples (what plt.hist([a, b], bins=100, density=True) computes), or the
+    log-ratio form."""
+    pes = pe.UserInput.parameter_estimation_settings
+    S = pe.post_burn_in_samples
+    if pes['mcmc_info_gain_returned'] == 'KL_divergence':
+        total = 0
+        each = []
+        for d in range(S.shape[1]):
+            a, b = pe.samples_of_prior[:, d].flatten(), S[:, d].flatten()
+            lo, hi = min(a.min(), b.min()), max(a.max(), b.max())
+            d0, _ = np.histogram(a, bins=100, range=(lo, hi), density=True)
+            d1, _ = np.histogram(b, bins=100, range=(lo, hi), density=True)
+            with np.errstate(divide='ignore', invalid='ignore'):
+                cur = d1 * np.log(d1 / d0)
+            cur = np.sum(cur[np.isfinite(cur)])
+            each.append(cur)
+            total = total + cur
+        pe.info_gain_KL_each_parameter = pe.info_gain_each_parameter = each
+        pe.info_gain_KL = total
+        return total
+    if pes['mcmc_info_gain_cutoff'] != 0:
+        raise NotImplementedError("mcmc_info_gain_cutoff != 0 is not supported")
+    post = pe.post_burn_in_log_posteriors_un_normed_vec - np.log(pe.evidence)                        # IP.py:1799
+    ratios = post - pe.post_burn_in_log_priors_vec
+    ratios[np.isinf(ratios)] = 0
+    ratios = np.nan_to_num(ratios)
+    pe.info_gain_log_ratio = np.mean(ratios)
+    return pe.info_gain_log_ratio
+
+
+# ----------------------------------------------------------------------------------------------
+# ensemble slice sampling
+# ----------------------------------------------------------------------------------------------
+def ess_launch(pe, start, n_iters, seed, mu0=1.0, tune=True, max_rounds=10000, first_iter=0, store_chain=True):
+    L = _lib.load()
+    dev = _dev()
+    X = torch.as_tensor(np.asarray(start, dtype=float), dtype=torch.float64).reshape(-1, pe.k).to(dev).contiguous()
+    W, k = X.shape
+    Z = pe.getLogP_batch(X).contiguous()
+    if not bool(torch.isfinite(Z).all().item()):
+        raise ValueError("Invalid walker initial positions! Initialise walkers from positions of finite log probability.")
+    spec = _lib.ESSSpec()
+    spec.n_walkers, spec.n_iters, spec.first_iter, spec.seed = W, int(n_iters), int(first_iter), int(seed) & (2 ** 64 - 1)
+    spec.mu0, spec.tune, spec.max_rounds, spec.k = float(mu0), int(bool(tune)), int(max_rounds), k
+    chain = torch.empty((n_iters, W, k), dtype=torch.float64, device=dev) if store_chain else None
+    chain_lp = torch.empty((n_iters, W), dtype=torch.float64, device=dev) if store_chain else None
+    info = torch.zeros(8, dtype=torch.float64, device=dev)
+    work = torch.empty(int(L.peuqse_ess_work_bytes(W, k)), dtype=torch.uint8, device=dev)
+    _lib.check(L.peuqse_ess_run(pe.device_problem.handle, C.byref(spec), _lib.ptr(X), _lib.ptr(Z), _lib.ptr(chain),
+                                _lib.ptr(chain_lp), _lib.ptr(info), _lib.ptr(work), _lib.current_stream()))
+    pe.gpu_launches += 2 * int(n_iters) + 1
+    return dict(X=X, Z=Z, chain=chain, chain_logp=chain_lp, info=info)
+
+
+def run_ensemble_slice_sampling(pe, mcmc_nwalkers_direct_input=None, walkerInitialDistribution='UserChoice',
+                                walkerInitialDistributionSpread='UserChoice', movesType='UserChoice',
+                                calculatePostBurnInStatistics=True, continueSampling='auto'):
+    UI = pe.UserInput
+    pes = UI.parameter_estimation_settings
+    if walkerInitialDistribution == 'UserChoice': walkerInitialDistribution = pes['mcmc_walkerInitialDistribution']
+    if walkerInitialDistribution.lower() == 'auto': walkerInitialDistribution = 'sobol'              # IP.py:2369-2370
+    if str(walkerInitialDistributionSpread) == 'UserChoice': walkerInitialDistributionSpread = pes['mcmc_walkerInitialDistributionSpread']
+    if str(walkerInitialDistributionSpread).lower() == 'auto': walkerInitialDistributionSpread = 0.866   # IP.py:2373-2374
+    if hasattr(UI, 'last_MCMC_run_type') and UI.last_MCMC_run_type != 'ESS':
+        print("ERROR: Two different algorithms of MCMC runs were attempted with the same UserInput."); raise SystemExit
+    if movesType == 'UserChoice': movesType = pes['mcmc_movesType']
+    if movesType.lower() not in ('auto', 'differential'):
+        raise NotImplementedError("only the differential move (zeus default, IP.py:2439-2440) is implemented")
+    if continueSampling == 'auto':
+        if ('mcmc_continueSampling' not in pes) or pes['mcmc_continueSampling'] == 'auto':
+            continueSampling = hasattr(pe, 'mcmc_last_point_sampled')
+        else:
+            continueSampling = pes['mcmc_continueSampling']
+    k = pe.k
+    seed = pes.get('mcmc_random_seed')
+    if isinstance(seed, int):
+        np.random.seed(seed)                                                                         # IP.py:2413-2415
+    else:
+        seed = int(np.random.SeedSequence().entropy % (2 ** 63))
+    if mcmc_nwalkers_direct_input is None:                                                           # IP.py:2416-2425
+        nw = pes.get('mcmc_nwalkers', 'auto')
+        nw = k * 4 if (isinstance(nw, str) and nw.lower() == 'auto') else int(nw)
+    else:
+        nw = int(mcmc_nwalkers_direct_input)
+    if nw % 2 != 0:
+        nw += 1                                                                                      # IP.py:2426-2428
+    pe.mcmc_nwalkers = nw
+    requested = int(pes['mcmc_length'])
+    nsteps = max(1, int(requested / nw))                                                             # IP.py:2430-2432
+    burn = int(requested * 0.1) if str(pes['mcmc_burn_in']).lower() == 'auto' else int(pes['mcmc_burn_in'])
+    maxiter = int(pes.get('mcmc_maxiter', 1E6))
+    first_iter = 0
+    if continueSampling:
+        burn = 0
+        start = np.asarray(pe.mcmc_last_point_sampled, dtype=float)
+        pe.last_post_burn_in_log_posteriors_un_normed_vec = np.array(pe.post_burn_in_log_posteriors_un_normed_vec)
+        pe.last_post_burn_in_samples = np.array(pe.post_burn_in_samples)
+        first_iter = getattr(pe, '_ess_iters_done', 0)
+    out = None
+    for trial in range(1000):                                                                        # IP.py:2496-2510
+        if not continueSampling:
+            start = pe.generateInitialPoints(initialPointsDistributionType=walkerInitialDistribution, numStartPoints=nw,
+                                             relativeInitialDistributionSpread=walkerInitialDistributionSpread)
+        try:
+            out = ess_launch(pe, start, nsteps, seed + trial, max_rounds=min(maxiter, 2 ** 30), first_iter=first_iter)
+            break
+        except ValueError as e:
+            if "finite" in str(e) and not continueSampling:
+                print("One of the starting points has a non-finite probability. Picking new starting points.")
+                continue
+            raise
+    pe._ess_iters_done = first_iter + nsteps
+    pe._ess_out = out
+    disc = int(burn / nw)                                                                            # IP.py:2512
+    chain = out['chain'][disc:]
+    chain_lp = out['chain_logp'][disc:]
+    pe.discrete_chains_post_burn_in_samples = chain.cpu().numpy()                                    # get_chain(discard), IP.py:2514
+    pe.post_burn_in_samples = chain.reshape(-1, k).cpu().numpy()                                     # samples.flatten(discard), IP.py:2513
+    pe.post_burn_in_log_posteriors_un_normed_vec = chain_lp.reshape(-1, 1).cpu().numpy()             # IP.py:2517
+    pe.mcmc_last_point_sampled = pe.discrete_chains_post_burn_in_samples[-1]                          # IP.py:2518
+    info = out['info'].cpu().numpy()
+    pe.ess_info = dict(n_logp_evaluations=int(info[0]), mu=float(info[1]), n_expansions=int(info[2]), n_contractions=int(info[3]))
+    UI.last_MCMC_run_type = 'ESS'
+    if continueSampling:
+        pe.post_burn_in_samples = np.vstack((pe.last_post_burn_in_samples, pe.post_burn_in_samples))
+        pe.post_burn_in_log_posteriors_un_normed_vec = np.vstack((pe.last_post_burn_in_log_posteriors_un_normed_vec,
+                                                                  pe.post_burn_in_log_posteriors_un_normed_vec))
+    if calculatePostBurnInStatistics:
+        post_burn_in_statistics(pe, calculate_post_burn_in_log_priors_vec=True)                       # IP.py:2533
+        return [pe.map_parameter_set, pe.mu_AP_parameter_set, pe.stdap_parameter_set, pe.evidence, pe.info_gain,
+                pe.post_burn_in_samples, pe.post_burn_in_log_posteriors_un_normed_vec]
+    lp = pe.post_burn_in_log_posteriors_un_normed_vec
+    pe.map_logP = max(lp)
+    pe.map_index = list(lp).index(pe.map_logP)
+    pe.map_parameter_set = pe.post_burn_in_samples[pe.map_index]
+    return pe.map_logP

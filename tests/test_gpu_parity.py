@@ -1,0 +1,328 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI by the Python
+boundary class, against (a) fixtures produced by the unmodified reference and (b) the numpy oracle on the
+same seeded inputs.  Tolerances: bit-exact wherever the reference's summation order is reproduced (diagonal
+covariances, n <= 128, thread shape); 1e-12 relative (north-star budget) where a parallel reduction or a
+dense BLAS order is involved."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+X00 = [600, 1100, 1400]
+Y00 = [360500, 580500, 1620500]
+S00 = [200000, 300000, 200000]
+
+
+@pytest.fixture(scope="module")
+def env():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import peuqse_b200 as PEUQSE
+    from oracle import peuqse_oracle as orc
+    from oracle import philox_np
+    return PEUQSE, orc, philox_np, torch
+
+
+def make_pe(PEUQSE, model, observed, unc, mu, punc, settings=None, **modelkw):
+    UI = PEUQSE.UserInput.fresh()
+    UI.responses['responses_observed'] = observed
+    UI.responses['responses_observed_uncertainties'] = unc
+    UI.model['InputParameterPriorValues'] = mu
+    UI.model['InputParametersPriorValuesUncertainties'] = punc
+    UI.model['simulateByInputParametersOnlyFunction'] = model
+    for k, v in modelkw.items():
+        UI.model[k] = v
+    for k, v in (settings or {}).items():
+        if k in UI.responses:
+            UI.responses[k] = v
+        else:
+            UI.parameter_estimation_settings[k] = v
+    return PEUQSE.parameter_estimation(UI)
+
+
+def parts(PE, th):
+    lp, pr, ll = PE.getLogP_batch(th, return_parts=True)
+    return lp.cpu().numpy(), pr.cpu().numpy(), ll.cpu().numpy()
+
+
+def test_philox_blocks(env):
+    PEUQSE, orc, philox_np, torch = env
+    from peuqse_b200 import _lib
+    L = _lib.load()
+    for seed, stream, first, block in [(0, 1, 0, 0), (12345678901234567, 2, 2 ** 33 + 5, 7), (7, 3, 10, 4000000000)]:
+        out = torch.empty((1000, 4), dtype=torch.int32, device="cuda")
+        _lib.check(L.peuqse_philox_blocks(seed, stream, first, 1000, block, _lib.ptr(out), _lib.current_stream()))
+        got = out.cpu().numpy().view(np.uint32)
+        want = philox_np.raw_block(seed, stream, np.uint64(first) + np.arange(1000, dtype=np.uint64), block)
+        assert np.array_equal(got, want)
+
+
+def test_example00_points_bit_exact(env, golden):
+    PEUQSE, orc, _, _ = env
+    g = golden("example00")
+    PE = make_pe(PEUQSE, PEUQSE.QuadraticModel(X00), Y00, S00, [200, 500], [100, 200])
+    lp, pr, ll = parts(PE, g['ex00_thetas'])
+    vals = g['ex00_logP_prior_lik']            # produced by the reference's getLogP/getLogPrior/getLogLikelihood
+    assert np.array_equal(lp, vals[:, 0])
+    assert np.array_equal(pr, vals[:, 1])
+    assert np.array_equal(ll, vals[:, 2])
+    # the reference repo's own stored rows
+    rows = g['ex00_csv_rows']
+    assert np.array_equal(PE.getLogP_batch(rows[:, 1:]).cpu().numpy(), rows[:, 0])
+    # single-point API
+    assert PE.getLogP([200, 500]) == -42.81726459961094
+    assert PE.getLogPrior([200, 500]) == -1.8378770664093453
+    ll1, sim = PE.getLogLikelihood([200, 500])
+    assert ll1 == -40.97938753320159 and np.array_equal(sim[0], (np.array(X00) - 200.) ** 2 + 500)
+
+
+def test_priors_bounds_scaling(env, golden):
+    PEUQSE, orc, _, _ = env
+    g = golden("priors")
+    Q = PEUQSE.QuadraticModel
+
+    def chk(PE, tag, exact=True):
+        lp, pr, ll = parts(PE, g[f'{tag}_thetas'])
+        v = g[f'{tag}_vals']
+        if exact:
+            assert np.array_equal(lp, v[:, 0]) and np.array_equal(pr, v[:, 1]) and np.array_equal(ll, v[:, 2]), tag
+        else:
+            assert np.array_equal(np.isfinite(lp), np.isfinite(v[:, 0]))
+            f = np.isfinite(v[:, 0])
+            np.testing.assert_allclose(lp[f], v[f, 0], rtol=1e-13)
+            np.testing.assert_allclose(pr, v[:, 1], rtol=1e-13)
+            assert np.array_equal(ll, v[:, 2])
+    chk(make_pe(PEUQSE, Q(X00), Y00, S00, [200, 500], [100, -1], InputParameterPriorValues_upperBounds=[None, 900],
+                InputParameterPriorValues_lowerBounds=[None, 100]), 'unif')
+    chk(make_pe(PEUQSE, Q(X00), Y00, S00, [200, 500], [-1, -1], InputParameterPriorValues_upperBounds=[400, 900],
+                InputParameterPriorValues_lowerBounds=[0, 100]), 'unif2')
+    chk(make_pe(PEUQSE, Q(X00), Y00, S00, [200, 500], [100, 200], InputParameterPriorValues_upperBounds=[300, None],
+                InputParameterPriorValues_lowerBounds=[100, 0]), 'bnd')
+    chk(make_pe(PEUQSE, Q(X00), Y00, S00, [1.0, 2.0], [[1, .3], [.3, 4]]), 'covp', exact=False)
+    for tag, sc in [("off", "off"), ("mu", "mu"), ("fix", 3.0)]:
+        chk(make_pe(PEUQSE, Q(X00), Y00, S00, [200, 500], [100, 200], settings={'scaling_uncertainties_type': sc}),
+            f'scal_{tag}', exact=False)
+    chk(make_pe(PEUQSE, Q(X00), Y00, S00, [200, 500], [100, 200], responses_simulation_uncertainties=[1e5, 5e4, 2e5]), 'simunc')
+
+
+@pytest.mark.parametrize("n", [1024, 96])
+def test_tpd_points(env, golden, n):
+    PEUQSE, orc, _, _ = env
+    g = golden("tpd")
+    PE = make_pe(PEUQSE, PEUQSE.Tpd2SiteModel.linear_ramp(n), list(g[f'tpd{n}_y']), list(np.full(n, float(g[f'tpd{n}_sigma']))),
+                 [41.5, 41.5, 13.0, 13.0, 0.1, 0.1], [20, 20, 13, 13, 0.1, 0.1])
+    lp, pr, ll = parts(PE, g[f'tpd{n}_thetas'])
+    v = g[f'tpd{n}_vals']
+    assert np.array_equal(pr, v[:, 1])
+    np.testing.assert_allclose(ll, v[:, 2], rtol=1e-12)      # north-star tolerance (exp ulp + reduction order)
+    np.testing.assert_allclose(lp, v[:, 0], rtol=1e-12)
+    assert np.max(np.abs(lp - v[:, 0]) / np.abs(v[:, 0])) < 2e-14   # what is actually achieved
+
+
+def test_multiresponse_builtin_and_external(env, golden):
+    PEUQSE, orc, _, torch = env
+    g = golden("multiresponse")
+    for tag, n, full in [("mr_diag", 7, False), ("mr_diag40", 40, False), ("mr_full5", 5, True), ("mr_full50", 50, True)]:
+        Phi, y, unc = g[f'{tag}_Phi'], g[f'{tag}_y'], g[f'{tag}_unc']
+        obs = [list(y[:n]), list(y[n:])]
+        u = [unc[0], unc[1]] if full else [list(unc[0]), list(unc[1])]
+        th, v = g[f'{tag}_thetas'], g[f'{tag}_vals']
+        Phi_t = torch.from_numpy(Phi).cuda()
+        for model in (PEUQSE.LinearModel(Phi), PEUQSE.TorchSimulator(lambda t, P=Phi_t: t @ P.T)):
+            PE = make_pe(PEUQSE, model, obs, u, [0., 0., 0.], [2., 2., 3.])
+            lp, pr, ll = parts(PE, th)
+            np.testing.assert_allclose(pr, v[:, 1], rtol=1e-13)
+            np.testing.assert_allclose(ll, v[:, 2], rtol=1e-12)
+            np.testing.assert_allclose(lp, v[:, 0], rtol=1e-12)
+        if not full:
+            # built-in linear model + diagonal responses: same order as the oracle -> bit exact
+            P = orc.build_problem([0., 0., 0.], [2., 2., 3.], [y[:n], y[n:]], [unc[0], unc[1]])
+            _, bt = orc.sim_linear(Phi)
+            want = orc.log_p_batch(P, th, lambda t: [bt(t)[:, :n], bt(t)[:, n:]])
+            PE = make_pe(PEUQSE, PEUQSE.LinearModel(Phi), obs, u, [0., 0., 0.], [2., 2., 3.])
+            lp, pr, ll = parts(PE, th)
+            assert np.array_equal(lp, want[0]) and np.array_equal(ll, want[2]), tag
+
+
+def test_nan_and_failure_conventions(env):
+    PEUQSE, orc, _, torch = env
+    # simulator returning NaN for some rows -> logLik = -inf, never an exception (IP.py:2880-2882)
+    def sim(t):
+        out = (torch.tensor(X00, dtype=torch.float64, device=t.device)[None, :] - t[:, 0:1]) ** 2 + t[:, 1:2]
+        out[t[:, 0] > 250] = float('nan')
+        return out
+    PE = make_pe(PEUQSE, sim, Y00, S00, [200, 500], [100, 200])
+    lp, pr, ll = parts(PE, np.array([[200., 500.], [300., 500.]]))
+    assert lp[0] == -42.81726459961094 and lp[1] == -np.inf and ll[1] == -np.inf and np.isfinite(pr[1])
+    assert PE.getLogLikelihood([300., 500.]) == (float('-inf'), None)
+    # empty batch
+    assert PE.getLogP_batch(np.zeros((0, 2))).shape[0] == 0
+
+
+def test_grid_multistart_example00(env, golden):
+    PEUQSE, orc, _, _ = env
+    g = golden("example00")
+    PE = make_pe(PEUQSE, PEUQSE.QuadraticModel(X00), Y00, S00, [200, 500], [100, 200],
+                 settings={'multistart_initialPointsDistributionType': 'grid', 'multistart_gridsearchSamplingInterval': [5, 5],
+                           'multistart_gridsearchSamplingRadii': [50, 50]})
+    best = PE.doMultiStart()
+    arr = g['ex00_grid_logP_theta']                     # the reference's permutations_MAP_logP_and_parameters_values
+    assert np.array_equal(PE.permutations_MAP_logP_and_parameters_values, arr)
+    assert np.array_equal(PE.listOfPermutations, arr[:, 1:])
+    assert PE.map_index == 13
+    assert PE.map_logP == float(g['ex00_grid_map_logP']) == PE.highest_logP
+    assert np.array_equal(PE.map_parameter_set, g['ex00_grid_map_theta']) and np.array_equal(best[0], g['ex00_grid_map_theta'])
+    assert PE.sweep_result.sum_weights == int(g['ex00_grid_nrows_expanded']) == 225166
+    np.testing.assert_allclose(PE.mu_AP_parameter_set, g['ex00_grid_mu_AP'], rtol=1e-12)
+    np.testing.assert_allclose(PE.stdap_parameter_set, g['ex00_grid_stdap'], rtol=1e-10)
+    np.testing.assert_allclose(PE.evidence, float(g['ex00_grid_evidence']), rtol=1e-11)
+    # expanded samples == the reference's post_burn_in_samples row multiplicities
+    S = PE.expandedPostBurnInSamples()
+    assert S.shape == (225166, 2)
+    P = orc.build_problem([200, 500], [100, 200], Y00, S00)
+    st = orc.weighted_statistics(arr[:, 0], arr[:, 1:], g['ex00_grid_multiplicity'])
+    assert np.array_equal(PE.marginal_histograms[0], st['hist'].astype(np.int64))
+    np.testing.assert_allclose(PE.marginal_histograms[1], st['edges'], rtol=0, atol=0)
+
+
+def test_grid_order_and_shapes(env, golden):
+    PEUQSE, orc, _, _ = env
+    g = golden("example00")
+    PE = make_pe(PEUQSE, PEUQSE.QuadraticModel(X00), Y00, S00, [200, 500], [100, 200])
+    for name in ("g3", "g3d"):
+        c, h, r = g[f'grid_{name}_center'], g[f'grid_{name}_interval'], g[f'grid_{name}_radii']
+        if len(c) != 2:
+            from peuqse_b200.sweep import make_spec
+            spec = make_spec("grid", len(c), c, interval=h, radii=r)
+            pts = PE._points_from_spec(spec, 0, len(g[f'grid_{name}_list']))
+        else:
+            pts = PE.generateInitialPoints(initialPointsDistributionType='grid', centerPoint=c, gridsearchSamplingInterval=list(h),
+                                           gridsearchSamplingRadii=list(r))
+        assert np.array_equal(pts, g[f'grid_{name}_list'])
+    # default grid: radii 1, interval = prior sigma (IP.py:758-767)
+    PE.UserInput.parameter_estimation_settings['multistart_initialPointsDistributionType'] = 'grid'
+    PE.doMultiStart()
+    assert PE.sweep_result.total == 9
+    assert np.array_equal(PE.listOfPermutations, g['grid_g3_list'])
+    # big random window of a 5-axis grid against the closed-form oracle decode
+    from peuqse_b200.sweep import make_spec
+    c, h, r = [1., -2., 3., 0.5, 10.], [0.1, 0.2, 0.3, 0.05, 1.5], [7, 0, 13, 1, 40]
+    spec = make_spec("grid", 5, c, interval=h, radii=r)
+    N = orc.grid_size(r)
+    first = N - 200000
+    pts = PE._points_from_spec(spec, first, 200000)
+    assert np.array_equal(pts, orc.grid_decode(c, h, r, np.arange(first, N)))
+    assert np.array_equal(PE._points_from_spec(spec, 0, 5000), orc.grid_decode(c, h, r, np.arange(5000)))
+
+
+def test_uniform_multistart_c5(env, golden):
+    PEUQSE, orc, philox_np, _ = env
+    g = golden("uniform_multistart")
+    k, n, N = 10, 64, 400
+    Phi = orc.cos_basis(n, k)
+    PE = make_pe(PEUQSE, PEUQSE.LinearModel(Phi), list(g['c5_y']), list(np.full(n, 0.1)), [0.0] * k, [1.0] * k,
+                 settings={'multistart_initialPointsDistributionType': 'uniform', 'multistart_numStartPoints': N,
+                           'multistart_random_seed': 0})
+    PE.doMultiStart()
+    arr = g['c5_logP_theta']                       # reference fed the same Philox uniforms
+    got = PE.permutations_MAP_logP_and_parameters_values
+    assert np.array_equal(got[:, 1:], arr[:, 1:])  # points bit-exact
+    np.testing.assert_allclose(got[:, 0], arr[:, 0], rtol=1e-13)
+    assert np.array_equal(PE.map_parameter_set, g['c5_map_theta'])
+    np.testing.assert_allclose(PE.map_logP, float(g['c5_map_logP']), rtol=1e-13)
+    np.testing.assert_allclose(PE.mu_AP_parameter_set, g['c5_mu_AP'], rtol=1e-11, atol=1e-13)
+    np.testing.assert_allclose(PE.stdap_parameter_set, g['c5_stdap'], rtol=1e-9, atol=1e-13)
+    # built-in linear model follows the oracle's accumulation order -> bit-exact against the oracle
+    P = orc.build_problem([0.0] * k, [1.0] * k, g['c5_y'], np.full(n, 0.1))
+    _, bt = orc.sim_linear(Phi)
+    assert np.array_equal(got[:, 0], orc.log_p_batch(P, got[:, 1:], bt)[0])
+
+
+def test_mh_example00_step_for_step(env, golden):
+    PEUQSE, orc, philox_np, _ = env
+    g = golden("mh_example00")
+    L = 1500
+    PE = make_pe(PEUQSE, PEUQSE.QuadraticModel(X00), Y00, S00, [200, 500], [100, 200],
+                 settings={'mcmc_length': L, 'mcmc_burn_in': 100, 'mcmc_relative_step_length': 0.1, 'mcmc_random_seed': 0,
+                           'mcmc_threshold_filter_samples': False, 'mcmc_info_gain_returned': 'log_ratio'})
+    from peuqse_b200.mcmc import mh_launch, step_cholesky
+    out = mh_launch(PE, [[200., 500.]], L, 100, 0, step_cholesky(PE.Q_covmat, 0.1), export_draws=True)
+    deltas, us = out['deltas'].cpu().numpy()[:, 0], out['us'].cpu().numpy()[:, 0]
+    # the device draws are the numpy-Philox draws the reference was fed when the fixture was made
+    assert np.array_equal(us, g['mh00_us'])
+    np.testing.assert_allclose(deltas, g['mh00_deltas'], rtol=1e-13, atol=1e-11)
+    # replay the device's own draws through the oracle: step-for-step identical trajectory
+    P = orc.build_problem([200, 500], [100, 200], Y00, S00)
+    _, bt = orc.sim_quadratic(X00)
+    ref = orc.mh_chains_batch(P, np.array([[200., 500.]]), deltas[:, None, :], us[:, None], bt)
+    assert np.array_equal(out['samples'].cpu().numpy(), ref['samples'])
+    assert np.array_equal(out['logp'].cpu().numpy(), ref['logP'])
+    assert np.array_equal(out['logprior'].cpu().numpy()[1:], ref['log_priors'][1:])
+    assert np.array_equal(out['loglik'].cpu().numpy()[1:], ref['log_likelihoods'][1:])
+    same_draws = np.array_equal(deltas, g['mh00_deltas'])
+    # through the reference-named API
+    res = PE.doMetropolisHastings()
+    if same_draws:       # identical draws -> identical to the reference run stored in the fixture
+        assert np.array_equal(PE.post_burn_in_samples, g['mh00_post_samples'])
+        assert np.array_equal(PE.post_burn_in_log_posteriors_un_normed_vec, g['mh00_post_logP'])
+        assert np.array_equal(PE.post_burn_in_log_priors_vec, g['mh00_post_log_priors'])
+        assert np.array_equal(PE.during_burn_in_samples, g['mh00_burn_samples'])
+        assert np.array_equal(PE.mu_AP_parameter_set, g['mh00_mu_AP']) and np.array_equal(PE.stdap_parameter_set, g['mh00_stdap'])
+        assert float(PE.map_logP) == float(g['mh00_map_logP']) and float(PE.evidence) == float(g['mh00_evidence'])
+    else:
+        acc_ref = np.mean(np.any(np.diff(g['mh00_post_samples'], axis=0) != 0, axis=1))
+        acc_got = np.mean(np.any(np.diff(PE.post_burn_in_samples, axis=0) != 0, axis=1))
+        assert abs(acc_ref - acc_got) < 0.05
+    assert PE.post_burn_in_samples.shape == (1400, 2) and len(res) == 7
+    # in-kernel statistics == numpy statistics of the stored rows
+    mom = PE.mcmc_chain_moments
+    np.testing.assert_allclose(mom['mean'], np.mean(PE.post_burn_in_samples, axis=0), rtol=1e-12)
+    np.testing.assert_allclose(mom['std'], np.std(PE.post_burn_in_samples, axis=0), rtol=1e-10)
+    assert mom['map_logP'] == float(PE.map_logP)
+
+
+def test_mh_tpd_step_for_step(env, golden):
+    PEUQSE, orc, _, _ = env
+    g = golden("tpd")
+    n, L = 1024, 120
+    sd = np.array([20, 20, 13, 13, 0.1, 0.1])
+    PE = make_pe(PEUQSE, PEUQSE.Tpd2SiteModel.linear_ramp(n), list(g['tpd1024_y']), list(np.full(n, float(g['tpd1024_sigma']))),
+                 [41.5, 41.5, 13.0, 13.0, 0.1, 0.1], list(sd))
+    from peuqse_b200.mcmc import mh_launch, step_cholesky
+    truth = np.array([[41.5, 45, 13, 13, 0.1, 0.1]])
+    out = mh_launch(PE, truth, L, 0, 0, step_cholesky(PE.Q_covmat, 1e-5), export_draws=True)
+    deltas, us = out['deltas'].cpu().numpy(), out['us'].cpu().numpy()
+    assert np.array_equal(us[:, 0], g['tpdmh_us'])
+    np.testing.assert_allclose(deltas[:, 0], g['tpdmh_deltas'], rtol=1e-12, atol=1e-15)
+    kBT, c1, c2 = orc.tpd2site_constants(n)
+    _, bt = orc.sim_tpd2site(kBT, c1, c2)
+    P = orc.build_problem([41.5, 41.5, 13.0, 13.0, 0.1, 0.1], sd, g['tpd1024_y'], np.full(n, float(g['tpd1024_sigma'])))
+    ref = orc.mh_chains_batch(P, truth, deltas, us, bt)
+    # accept/reject sequence step for step, states identical (they are sums of the same doubles)
+    assert np.array_equal(out['samples'].cpu().numpy(), ref['samples'])
+    np.testing.assert_allclose(out['logp'].cpu().numpy(), ref['logP'], rtol=1e-12)
+    assert 0.05 < ref['accepted'][1:].mean() < 0.95
+
+
+def test_mh_many_chains_statistics(env):
+    """4096 Example00 chains: pooled posterior mean/std against the grid-quadrature posterior (MC error)."""
+    PEUQSE, orc, _, _ = env
+    PE = make_pe(PEUQSE, PEUQSE.QuadraticModel(X00), Y00, S00, [200, 500], [100, 200],
+                 settings={'mcmc_length': 2000, 'mcmc_burn_in': 500, 'mcmc_relative_step_length': 0.5, 'mcmc_random_seed': 3,
+                           'mcmc_nchains': 4096, 'mcmc_threshold_filter_samples': False, 'mcmc_info_gain_returned': 'log_ratio'})
+    PE.doMetropolisHastings()
+    assert PE.post_burn_in_samples.shape == (4096 * 1500, 2)
+    # quadrature reference
+    a = np.linspace(-300, 700, 801)
+    b = np.linspace(-700, 1700, 801)
+    A, B = np.meshgrid(a, b, indexing='ij')
+    P = orc.build_problem([200, 500], [100, 200], Y00, S00)
+    _, bt = orc.sim_quadratic(X00)
+    lp = orc.log_p_batch(P, np.stack([A.ravel(), B.ravel()], axis=1), bt)[0]
+    w = np.exp(lp - lp.max())
+    mean = np.array([(w * A.ravel()).sum(), (w * B.ravel()).sum()]) / w.sum()
+    std = np.sqrt(np.array([(w * (A.ravel() - mean[0]) ** 2).sum(), (w * (B.ravel() - mean[1]) ** 2).sum()]) / w.sum())
+    np.testing.assert_allclose(PE.mcmc_chain_moments['mean'], mean, atol=0.02 * std.max())
+    np.testing.assert_allclose(PE.mcmc_chain_moments['std'], std, rtol=0.02)
+    np.testing.assert_allclose(np.mean(PE.post_burn_in_samples, axis=0), PE.mcmc_chain_moments['mean'], rtol=1e-10)
