@@ -167,34 +167,40 @@ int peuqse_sweep_points(const peuqse_sweep_spec* spec, int64_t first, int64_t co
 
 /*
  * Pass 2: convertPermutationsToSamples + calculatePostBurnInStatistics as weighted reductions
- * (IP.py:3463-3491, 1923-1931).  weight_g = (int)exp(logP_g - threshold) for logP_g > threshold.
- * d_logp: pass-1 logP (nullable: recompute).  d_acc: PEUQSE_ACC_DOUBLES(k) doubles, see layout below;
- * sums are ACCUMULATED into d_acc (zero it first; min/max slots start at +/-inf).
- * d_keep_index/d_keep_logp (nullable, capacity keep_capacity): compacted list of retained points,
- * unordered; d_keep_count: one int64 (running count; may exceed the capacity, extra rows are dropped).
+ * (IP.py:3463-3491, 1923-1931).  threshold = d_best->logp + log_rel_threshold, with
+ * log_rel_threshold = log(10^-coef) (IP.py:1016, 3477); weight_g = (int)exp(logP_g - threshold) for
+ * logP_g > threshold.  d_best: DEVICE struct written by pass 1 (or merged over ranks by the caller), so a
+ * whole multistart needs no host round trip between passes.  Moments are taken about the MAP point
+ * theta(d_best->index) (no cancellation in the variance).  d_logp: pass-1 logP (nullable: recompute).
+ * d_acc: PEUQSE_ACC_DOUBLES(k) doubles, layout below; sums are ACCUMULATED into d_acc (zero it first; the
+ * min/max slots start at +/-inf).  d_keep_index/d_keep_logp (nullable, capacity keep_capacity): compacted
+ * list of retained points, unordered; d_keep_count: one int64 (running count; rows beyond the capacity
+ * are dropped).  Does nothing when d_best->index < 0.
  */
 #define PEUQSE_ACC_W 0                                  /* sum w                                   */
 #define PEUQSE_ACC_WEXP 1                               /* sum w*exp(logP)                         */
 #define PEUQSE_ACC_NKEPT 2                              /* number of retained points               */
-#define PEUQSE_ACC_S1 3                                 /* [k]   sum w*(th-center)                 */
-#define PEUQSE_ACC_S2(k) (3 + (k))                      /* [k*k] sum w*(th-center)(th-center)^T    */
+#define PEUQSE_ACC_S1 3                                 /* [k]   sum w*(th-shift)                  */
+#define PEUQSE_ACC_S2(k) (3 + (k))                      /* [k*k] sum w*(th-shift)(th-shift)^T      */
 #define PEUQSE_ACC_MIN(k) (3 + (k) + (k) * (k))         /* [k]   min retained theta                */
 #define PEUQSE_ACC_MAX(k) (3 + 2 * (k) + (k) * (k))     /* [k]   max retained theta                */
 #define PEUQSE_ACC_DOUBLES(k) (3 + 3 * (k) + (k) * (k))
 int peuqse_sweep_pass2(const peuqse_problem* p, const peuqse_sweep_spec* spec, int64_t first, int64_t count,
-                       const double* d_logp, double threshold, double* d_acc,
+                       const double* d_logp, const peuqse_best* d_best, double log_rel_threshold, double* d_acc,
                        int64_t* d_keep_index, double* d_keep_logp, int64_t keep_capacity, int64_t* d_keep_count,
                        void* d_work, void* stream);
+
+/* bin edges np.linspace(min_d, max_d, nbins+1) from the pass-2 accumulator: d_edges[k][nbins+1] */
+int peuqse_sweep_edges(const double* d_acc, int32_t k, int32_t nbins, double* d_edges, void* stream);
 
 /*
  * Pass 3: weighted marginal histograms of the retained points (plotting_functions.py:135 -> ax.hist ->
  * np.histogram with equal bins over [min, max] of the retained values, last bin closed).
- * d_edges[k][nbins+1]: bin edges (np.linspace(lo_d, hi_d, nbins+1)); d_hist[k][nbins]: integer weight
- * sums, accumulated (zero it first).
+ * d_edges[k][nbins+1]: bin edges; d_hist[k][nbins]: integer weight sums, accumulated (zero it first).
  */
 int peuqse_sweep_hist(const peuqse_problem* p, const peuqse_sweep_spec* spec, int64_t first, int64_t count,
-                      const double* d_logp, double threshold, const double* d_edges, int32_t nbins,
-                      uint64_t* d_hist, void* stream);
+                      const double* d_logp, const peuqse_best* d_best, double log_rel_threshold,
+                      const double* d_edges, int32_t nbins, uint64_t* d_hist, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Metropolis-Hastings: doMetropolisHastings (IP.py:2563-2754), C independent chains

@@ -230,7 +230,8 @@ __device__ __forceinline__ double block_min(double v, double* s_red) {
 template <int MODEL, int KT>
 __global__ void __launch_bounds__(256) k_sweep_pass2(const __grid_constant__ DevProblem P, const __grid_constant__ DevSweep S,
                                                      long long first, long long count, const double* __restrict__ logp_in,
-                                                     double thr, double* __restrict__ partial, double* __restrict__ acc_out,
+                                                     const peuqse_best* __restrict__ best_in, double log_rel,
+                                                     double* __restrict__ partial, double* __restrict__ acc_out,
                                                      unsigned int* __restrict__ ticket, long long* __restrict__ keep_idx,
                                                      double* __restrict__ keep_logp, long long keep_cap,
                                                      unsigned long long* __restrict__ keep_count, int use_smem) {
@@ -238,6 +239,11 @@ __global__ void __launch_bounds__(256) k_sweep_pass2(const __grid_constant__ Dev
     __shared__ double s_red[8];
     __shared__ bool s_last;
     const ObsView O = stage_obs(P, smem, use_smem);
+    const long long best_index = best_in->index;
+    if (best_index < 0) return;                                // no finite point: nothing is retained
+    const double thr = best_in->logp + log_rel;               // maxLogP + np.log(relativeFilteringThreshold), IP.py:3477
+    double shift[KT];                                          // moments about the MAP point (no cancellation)
+    sweep_point<KT>(S, (unsigned long long)best_index, shift);
     Pass2Acc<KT> A;
     A.w = A.wexp = A.nk = 0.0;
 #pragma unroll
@@ -270,12 +276,12 @@ __global__ void __launch_bounds__(256) k_sweep_pass2(const __grid_constant__ Dev
 #pragma unroll
         for (int d = 0; d < KT; ++d) {
             if (d < S.k) {
-                const double dd = th[d] - S.center[d];
+                const double dd = th[d] - shift[d];
                 const double wd = w * dd;
                 A.s1[d] += wd;
 #pragma unroll
                 for (int d2 = d; d2 < KT; ++d2) {
-                    if (d2 < S.k) A.s2[e] = fma(wd, th[d2] - S.center[d2], A.s2[e]);
+                    if (d2 < S.k) A.s2[e] = fma(wd, th[d2] - shift[d2], A.s2[e]);
                     ++e;
                 }
                 A.mn[d] = fmin(A.mn[d], th[d]);
@@ -354,13 +360,16 @@ __global__ void __launch_bounds__(256) k_sweep_pass2(const __grid_constant__ Dev
 template <int MODEL, int KT>
 __global__ void __launch_bounds__(256) k_sweep_hist(const __grid_constant__ DevProblem P, const __grid_constant__ DevSweep S,
                                                     long long first, long long count, const double* __restrict__ logp_in,
-                                                    double thr, const double* __restrict__ edges, int nbins,
+                                                    const peuqse_best* __restrict__ best_in, double log_rel,
+                                                    const double* __restrict__ edges, int nbins,
                                                     unsigned long long* __restrict__ hist, int use_smem) {
     extern __shared__ double smem[];
     const ObsView O = stage_obs(P, smem, use_smem);
     // block-private histogram after the staged constants
     unsigned long long* sh = (unsigned long long*)(smem + (use_smem ? pq_obs_doubles(P) : 0));
     const int k = S.k;
+    if (best_in->index < 0) return;
+    const double thr = best_in->logp + log_rel;
     for (int a = threadIdx.x; a < k * nbins; a += blockDim.x) sh[a] = 0ULL;
     __syncthreads();
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -430,7 +439,7 @@ int launch_pass1(const peuqse_problem* p, const DevSweep& S, long long first, lo
 
 template <int MODEL, int KT>
 int launch_pass2(const peuqse_problem* p, const DevSweep& S, long long first, long long count, const double* logp,
-                 double thr, double* acc, long long* kidx, double* klogp, long long kcap, long long* kcount, void* work,
+                 const peuqse_best* best, double log_rel, double* acc, long long* kidx, double* klogp, long long kcap, long long* kcount, void* work,
                  cudaStream_t st) {
     int use_smem;
     const size_t smem = pq_pick_smem(p, &use_smem);
@@ -438,21 +447,21 @@ int launch_pass2(const peuqse_problem* p, const DevSweep& S, long long first, lo
     PQ_CUDA_OK(pq_allow_smem((const void*)kern, smem));
     unsigned int* ticket = (unsigned int*)work;
     double* partial = (double*)((char*)work + PQ_SWEEP_TICKET_BYTES);
-    kern<<<sweep_grid(p, count), 256, smem, st>>>(p->d, S, first, count, logp, thr, partial, acc, ticket, kidx, klogp, kcap,
+    kern<<<sweep_grid(p, count), 256, smem, st>>>(p->d, S, first, count, logp, best, log_rel, partial, acc, ticket, kidx, klogp, kcap,
                                                   (unsigned long long*)kcount, use_smem);
     PQ_CUDA_OK(cudaGetLastError());
     return PEUQSE_OK;
 }
 
 template <int MODEL, int KT>
-int launch_hist(const peuqse_problem* p, const DevSweep& S, long long first, long long count, const double* logp, double thr,
-                const double* edges, int nbins, unsigned long long* hist, cudaStream_t st) {
+int launch_hist(const peuqse_problem* p, const DevSweep& S, long long first, long long count, const double* logp,
+                const peuqse_best* best, double log_rel, const double* edges, int nbins, unsigned long long* hist, cudaStream_t st) {
     int use_smem;
     size_t smem = pq_pick_smem(p, &use_smem);
     smem += (size_t)S.k * nbins * sizeof(unsigned long long);
     auto kern = k_sweep_hist<MODEL, KT>;
     PQ_CUDA_OK(pq_allow_smem((const void*)kern, smem));
-    kern<<<sweep_grid(p, count), 256, smem, st>>>(p->d, S, first, count, logp, thr, edges, nbins, hist, use_smem);
+    kern<<<sweep_grid(p, count), 256, smem, st>>>(p->d, S, first, count, logp, best, log_rel, edges, nbins, hist, use_smem);
     PQ_CUDA_OK(cudaGetLastError());
     return PEUQSE_OK;
 }
@@ -526,12 +535,13 @@ extern "C" int peuqse_sweep_points(const peuqse_sweep_spec* spec, int64_t first,
 }
 
 extern "C" int peuqse_sweep_pass2(const peuqse_problem* p, const peuqse_sweep_spec* spec, int64_t first, int64_t count,
-                                  const double* d_logp, double threshold, double* d_acc, int64_t* d_keep_index,
+                                  const double* d_logp, const peuqse_best* d_best, double log_rel_threshold, double* d_acc,
+                                  int64_t* d_keep_index,
                                   double* d_keep_logp, int64_t keep_capacity, int64_t* d_keep_count, void* d_work,
                                   void* stream) {
     int rc = check_sweep_args(p, spec, first, count);
     if (rc) return rc;
-    if (!d_acc || !d_work) return pq_set_error(PEUQSE_ERR_INVALID, "d_acc and d_work are required");
+    if (!d_acc || !d_work || !d_best) return pq_set_error(PEUQSE_ERR_INVALID, "d_acc, d_best and d_work are required");
     if (d_keep_index && (!d_keep_logp || !d_keep_count)) return pq_set_error(PEUQSE_ERR_INVALID, "incomplete keep buffers");
     if (p->d.model_id == PEUQSE_MODEL_EXTERNAL && !d_logp) return pq_set_error(PEUQSE_ERR_INVALID, "external model needs d_logp");
     DevSweep S;
@@ -541,7 +551,7 @@ extern "C" int peuqse_sweep_pass2(const peuqse_problem* p, const peuqse_sweep_sp
     if (first + count > total) return pq_set_error(PEUQSE_ERR_INVALID, "range exceeds the number of sweep points");
     cudaStream_t st = (cudaStream_t)stream;
     PQ_CUDA_OK(cudaMemsetAsync(d_work, 0, PQ_SWEEP_TICKET_BYTES, st));
-#define P2_ARGS p, S, first, count, d_logp, threshold, d_acc, (long long*)d_keep_index, d_keep_logp, keep_capacity, (long long*)d_keep_count, d_work, st
+#define P2_ARGS p, S, first, count, d_logp, d_best, log_rel_threshold, d_acc, (long long*)d_keep_index, d_keep_logp, keep_capacity, (long long*)d_keep_count, d_work, st
 #define P2_L(KT, ...) return launch_pass2<PEUQSE_MODEL_LINEAR, KT>(P2_ARGS)
 #define P2_E(KT, ...) return launch_pass2<PEUQSE_MODEL_EXTERNAL, KT>(P2_ARGS)
     PQ_SWEEP_DISPATCH((launch_pass2<PEUQSE_MODEL_QUADRATIC, 2>(P2_ARGS)), (launch_pass2<PEUQSE_MODEL_TPD2SITE, 6>(P2_ARGS)), P2_L, P2_E)
@@ -551,11 +561,11 @@ extern "C" int peuqse_sweep_pass2(const peuqse_problem* p, const peuqse_sweep_sp
 }
 
 extern "C" int peuqse_sweep_hist(const peuqse_problem* p, const peuqse_sweep_spec* spec, int64_t first, int64_t count,
-                                 const double* d_logp, double threshold, const double* d_edges, int32_t nbins,
-                                 uint64_t* d_hist, void* stream) {
+                                 const double* d_logp, const peuqse_best* d_best, double log_rel_threshold,
+                                 const double* d_edges, int32_t nbins, uint64_t* d_hist, void* stream) {
     int rc = check_sweep_args(p, spec, first, count);
     if (rc) return rc;
-    if (!d_edges || !d_hist || nbins < 1 || nbins > 4096) return pq_set_error(PEUQSE_ERR_INVALID, "bad histogram arguments");
+    if (!d_edges || !d_hist || !d_best || nbins < 1 || nbins > 4096) return pq_set_error(PEUQSE_ERR_INVALID, "bad histogram arguments");
     if (p->d.model_id == PEUQSE_MODEL_EXTERNAL && !d_logp) return pq_set_error(PEUQSE_ERR_INVALID, "external model needs d_logp");
     DevSweep S;
     long long total;
@@ -563,13 +573,33 @@ extern "C" int peuqse_sweep_hist(const peuqse_problem* p, const peuqse_sweep_spe
     if (rc) return rc;
     if (first + count > total) return pq_set_error(PEUQSE_ERR_INVALID, "range exceeds the number of sweep points");
     cudaStream_t st = (cudaStream_t)stream;
-#define P3_ARGS p, S, first, count, d_logp, threshold, d_edges, nbins, (unsigned long long*)d_hist, st
+#define P3_ARGS p, S, first, count, d_logp, d_best, log_rel_threshold, d_edges, nbins, (unsigned long long*)d_hist, st
 #define P3_L(KT, ...) return launch_hist<PEUQSE_MODEL_LINEAR, KT>(P3_ARGS)
 #define P3_E(KT, ...) return launch_hist<PEUQSE_MODEL_EXTERNAL, KT>(P3_ARGS)
     PQ_SWEEP_DISPATCH((launch_hist<PEUQSE_MODEL_QUADRATIC, 2>(P3_ARGS)), (launch_hist<PEUQSE_MODEL_TPD2SITE, 6>(P3_ARGS)), P3_L, P3_E)
 #undef P3_L
 #undef P3_E
     return pq_set_error(PEUQSE_ERR_INVALID, "unknown model");
+}
+
+// np.linspace(min_d, max_d, nbins+1) from the pass-2 accumulator (np.histogram's edges for range=None):
+// y = arange(0, num)*step + start with step = (stop-start)/div, last element := stop (numpy/_core/function_base.py)
+__global__ void k_sweep_edges(const double* __restrict__ acc, int k, int nbins, double* __restrict__ edges) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= k * (nbins + 1)) return;
+    const int d = t / (nbins + 1), i = t - d * (nbins + 1);
+    double lo = acc[PEUQSE_ACC_MIN(k) + d], hi = acc[PEUQSE_ACC_MAX(k) + d];
+    if (!(hi > lo)) { lo = lo - 0.5; hi = hi + 0.5; }          // np.histogram widens an empty range by +-0.5
+    const double step = (hi - lo) / (double)nbins;
+    edges[t] = (i == nbins) ? hi : ((double)i * step + lo);
+}
+
+extern "C" int peuqse_sweep_edges(const double* d_acc, int32_t k, int32_t nbins, double* d_edges, void* stream) {
+    if (!d_acc || !d_edges || k < 1 || k > PQ_MAXK || nbins < 1) return pq_set_error(PEUQSE_ERR_INVALID, "bad edges arguments");
+    const int n = k * (nbins + 1);
+    k_sweep_edges<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_acc, k, nbins, d_edges);
+    PQ_CUDA_OK(cudaGetLastError());
+    return PEUQSE_OK;
 }
 
 // raw Philox blocks (tests): d_out[count][4]

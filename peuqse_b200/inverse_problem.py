@@ -141,7 +141,8 @@ class parameter_estimation:
         post = self.UserInput.model.get('simulationOutputProcessingFunction')
         if post is not None:
             out = post(out)
-        out = torch.as_tensor(out, dtype=torch.float64, device=th.device).reshape(B, -1).contiguous()
+        out = torch.as_tensor(out, dtype=torch.float64, device=th.device)
+        out = out.reshape(B, out.numel() // B if B else self.host_problem.n_total).contiguous()
         if out.shape[1] != self.host_problem.n_total:
             raise ValueError(f"simulator returned {out.shape[1]} values per point, expected {self.host_problem.n_total}")
         return out
@@ -150,6 +151,9 @@ class parameter_estimation:
         """logP[B] (and logPrior[B], logLikelihood[B]) as CUDA tensors for thetas[B,k]."""
         th = self._as_theta(thetas)
         B = th.shape[0]
+        if B == 0:
+            e = torch.empty(0, dtype=torch.float64, device=th.device)
+            return (e, e.clone(), e.clone()) if return_parts else e
         logp = torch.empty(B, dtype=torch.float64, device=th.device)
         lp = torch.empty(B, dtype=torch.float64, device=th.device) if return_parts else None
         ll = torch.empty(B, dtype=torch.float64, device=th.device) if return_parts else None
@@ -313,8 +317,8 @@ class parameter_estimation:
             return self._multistart_external(spec, n, toSamples and calculatePostBurnInStatistics, coef, nbins, centerPoint)
         store = pes.get('multistart_store_logP', 'auto')
         store = (n <= 2 ** 31) if store == 'auto' else bool(store)
-        sw = Sweep(self.device_problem, spec, n, store_logp=store)
-        res = sw.run(coef=coef, nbins=nbins, statistics=bool(toSamples and calculatePostBurnInStatistics))
+        sw = Sweep(self.device_problem, spec, n, store_logp=store, nbins=nbins)
+        res = sw.run(coef=coef, statistics=bool(toSamples and calculatePostBurnInStatistics))
         self.gpu_launches += sw.launches
         self._sweep = sw
         return self._adopt_sweep_result(res, centerPoint)

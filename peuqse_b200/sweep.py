@@ -1,11 +1,13 @@
-"""Host driver of the multistart sweeps: three kernel passes + two tiny collectives.
+"""Host driver of the multistart sweeps: three kernel passes + (multi-GPU only) three tiny collectives.
 
 pass 1  logP of every point of this rank's index range (optionally kept in HBM) + first strict maximum
         -> all-gather (max, index)            [doListOfPermutationsSearch loop, IP.py:844-956]
-pass 2  weights int(exp(logP - thr)), shifted moments, min/max of the retained points
+pass 2  weights int(exp(logP - thr)), moments about the MAP point, min/max of the retained points
         -> all-reduce                         [convertPermutationsToSamples + calculatePostBurnInStatistics,
                                                IP.py:3463-3491, 1923-1931]
 pass 3  weighted marginal histograms          [plotting_functions.py:135]
+The best point, the threshold and the bin edges stay on the device between passes, so a whole multistart
+is one stream-ordered sequence with a single device->host read of the packed result at the end.
 """
 import ctypes as C
 
@@ -42,37 +44,58 @@ class SweepResult:
 
 
 class Sweep:
-    def __init__(self, dp, spec, total, store_logp=True):
+    def __init__(self, dp, spec, total, store_logp=True, nbins=10):
         self.dp = dp
         self.spec = spec
-        self.k = spec.k
+        self.k = k = spec.k
         self.total = int(total)
+        self.nbins = int(nbins)
         self.L = _lib.load()
         self.first, self.count = D.shard_range(self.total)
         dev = torch.device("cuda", torch.cuda.current_device())
         self.dev = dev
         self.work = torch.empty(int(self.L.peuqse_sweep_work_bytes()), dtype=torch.uint8, device=dev)
-        self.best = torch.zeros(2, dtype=torch.float64, device=dev)      # peuqse_best {double, int64}
         self.logp = torch.empty(self.count, dtype=torch.float64, device=dev) if store_logp else None
-        self.acc = torch.zeros(_lib.acc_layout(self.k)["SIZE"], dtype=torch.float64, device=dev)
+        # packed result: [best(2) | acc | hist (int64 bits) | edges]
+        self.lay = lay = _lib.acc_layout(k)
+        nacc = lay["SIZE"]
+        self.res = torch.zeros(2 + nacc + k * nbins + k * (nbins + 1), dtype=torch.float64, device=dev)
+        self.best = self.res[0:2]                                        # peuqse_best {double logp, int64 index}
+        self.acc = self.res[2:2 + nacc]
+        self.hist = self.res[2 + nacc:2 + nacc + k * nbins].view(torch.int64)
+        self.edges = self.res[2 + nacc + k * nbins:]
+        self.acc_init = torch.zeros(nacc, dtype=torch.float64, device=dev)
+        self.acc_init[lay["MIN"]:lay["MIN"] + k] = float("inf")
+        self.acc_init[lay["MAX"]:lay["MAX"] + k] = float("-inf")
         self.launches = 0
+        self.world = D.world()[1]
 
-    # -- individual passes (device-resident in/out; used directly by bench.py for the kernel-only timing)
+    # -- individual passes: device-resident in and out (bench.py times these for the kernel-only number)
     def pass1(self):
         _lib.check(self.L.peuqse_sweep_pass1(self.dp.handle, C.byref(self.spec), self.first, self.count,
                                              _lib.ptr(self.logp), _lib.ptr(self.best), _lib.ptr(self.work),
                                              _lib.current_stream()))
         self.launches += 1
+        if self.world > 1:
+            self._merge_best()
 
-    def read_best(self):
-        b = self.best.cpu()
-        return float(b[0].item()), int(b.view(torch.int64)[1].item())
+    def _merge_best(self):
+        """all-gather of the 16-byte (maxLogP, index) records; highest value, lowest index among equals."""
+        import torch.distributed as dist
+        g = torch.empty((self.world, 2), dtype=torch.float64, device=self.dev)
+        dist.all_gather_into_tensor(g, self.best.reshape(1, 2).contiguous())
+        vals = g[:, 0]
+        idx = g[:, 1].contiguous().view(torch.int64)
+        valid = idx >= 0
+        m = torch.where(valid, vals, torch.full_like(vals, float("-inf"))).max()
+        cand = torch.where(valid & (vals == m), idx, torch.full_like(idx, torch.iinfo(torch.int64).max))
+        bi = cand.min()
+        none = bi == torch.iinfo(torch.int64).max
+        self.best[0] = m
+        self.best[1:2].view(torch.int64)[0] = torch.where(none, torch.full_like(bi, -1), bi)
 
-    def pass2(self, thr, keep=None):
-        lay = _lib.acc_layout(self.k)
-        self.acc.zero_()
-        self.acc[lay["MIN"]:lay["MIN"] + self.k] = float("inf")
-        self.acc[lay["MAX"]:lay["MAX"] + self.k] = float("-inf")
+    def pass2(self, log_rel, keep=None):
+        self.acc.copy_(self.acc_init)
         kidx = klogp = kcount = None
         cap = 0
         if keep is not None:
@@ -80,34 +103,64 @@ class Sweep:
             cap = kidx.numel()
             kcount.zero_()
         _lib.check(self.L.peuqse_sweep_pass2(self.dp.handle, C.byref(self.spec), self.first, self.count,
-                                             _lib.ptr(self.logp), float(thr), _lib.ptr(self.acc), _lib.ptr(kidx),
-                                             _lib.ptr(klogp), cap, _lib.ptr(kcount), _lib.ptr(self.work),
+                                             _lib.ptr(self.logp), _lib.ptr(self.best), float(log_rel), _lib.ptr(self.acc),
+                                             _lib.ptr(kidx), _lib.ptr(klogp), cap, _lib.ptr(kcount), _lib.ptr(self.work),
                                              _lib.current_stream()))
         self.launches += 1
+        if self.world > 1:
+            import torch.distributed as dist
+            lay, k = self.lay, self.k
+            dist.all_reduce(self.acc[:lay["MIN"]], op=dist.ReduceOp.SUM)
+            dist.all_reduce(self.acc[lay["MIN"]:lay["MIN"] + k], op=dist.ReduceOp.MIN)
+            dist.all_reduce(self.acc[lay["MAX"]:lay["MAX"] + k], op=dist.ReduceOp.MAX)
 
-    def pass3(self, thr, edges_dev, hist_dev, nbins):
-        hist_dev.zero_()
+    def pass3(self, log_rel):
+        self.hist.zero_()
+        _lib.check(self.L.peuqse_sweep_edges(_lib.ptr(self.acc), self.k, self.nbins, _lib.ptr(self.edges),
+                                             _lib.current_stream()))
         _lib.check(self.L.peuqse_sweep_hist(self.dp.handle, C.byref(self.spec), self.first, self.count,
-                                            _lib.ptr(self.logp), float(thr), _lib.ptr(edges_dev), int(nbins),
-                                            _lib.ptr(hist_dev), _lib.current_stream()))
-        self.launches += 1
+                                            _lib.ptr(self.logp), _lib.ptr(self.best), float(log_rel), _lib.ptr(self.edges),
+                                            self.nbins, _lib.ptr(self.hist), _lib.current_stream()))
+        self.launches += 2
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.hist, op=dist.ReduceOp.SUM)
+
+    def step(self, log_rel, statistics=True):
+        """One whole multistart on the device (no host synchronisation)."""
+        self.pass1()
+        if statistics:
+            self.pass2(log_rel)
+            self.pass3(log_rel)
 
     def points(self, first, count):
         th = torch.empty((count, self.k), dtype=torch.float64, device=self.dev)
         if count:
             _lib.check(self.L.peuqse_sweep_points(C.byref(self.spec), int(first), int(count), _lib.ptr(th),
                                                   _lib.current_stream()))
+            self.launches += 1
         return th
 
-    # -- the whole doMultiStart('getLogP') computation
-    def run(self, coef=2.0, nbins=10, statistics=True):
-        k = self.k
+    def result_bytes(self):
+        return self.res.numel() * 8
+
+    # -- the whole doMultiStart('getLogP') computation, host-facing
+    def run(self, coef=2.0, statistics=True):
+        k, nbins, lay = self.k, self.nbins, self.lay
+        log_rel = float(np.log(10 ** (-1 * coef)))                       # IP.py:1016, 3477
+        self.step(log_rel, statistics)
+        res = self.res.cpu()                                              # the single device->host read
+        R = self.unpack(res.numpy(), coef, statistics)
+        return R
+
+    def unpack(self, res, coef, statistics=True):
+        k, nbins, lay = self.k, self.nbins, self.lay
         R = SweepResult()
-        self.pass1()
-        lv, li = self.read_best()                                        # D2H: 16 bytes
-        R.map_logP, R.map_index = D.allgather_best(lv, li)
         R.total = self.total
+        R.map_logP = float(res[0])
+        R.map_index = int(res[1:2].view(np.int64)[0])
         if R.map_index < 0:
+            R.map_logP = float("-inf")
             R.map_parameter_set = np.full(k, np.nan)
             R.statistics = False
             return R
@@ -115,34 +168,24 @@ class Sweep:
         R.statistics = bool(statistics)
         if not statistics:
             return R
-        thr = R.map_logP + np.log(10 ** (-1 * coef))                     # IP.py:1016, 3477
-        R.threshold = float(thr)
-        self.pass2(thr)
-        lay = _lib.acc_layout(k)
-        acc = self.acc.cpu().numpy()                                      # D2H: (3+3k+k^2)*8 bytes
-        sums = D.allreduce_np(acc[:lay["MIN"]], "sum")
-        mn = D.allreduce_np(acc[lay["MIN"]:lay["MIN"] + k], "min")
-        mx = D.allreduce_np(acc[lay["MAX"]:lay["MAX"] + k], "max")
-        W = sums[lay["W"]]
-        c = np.array([self.spec.center[d] for d in range(k)])
-        S1 = sums[lay["S1"]:lay["S1"] + k]
-        S2 = sums[lay["S2"]:lay["S2"] + k * k].reshape(k, k)
+        R.threshold = R.map_logP + np.log(10 ** (-1 * coef))
+        acc = res[2:2 + lay["SIZE"]]
+        W = acc[lay["W"]]
+        c = R.map_parameter_set                                           # moments were taken about the MAP point
+        S1 = acc[lay["S1"]:lay["S1"] + k]
+        S2 = acc[lay["S2"]:lay["S2"] + k * k].reshape(k, k)
         R.sum_weights = W
-        R.n_retained = int(round(sums[lay["NKEPT"]]))
+        R.n_retained = int(round(acc[lay["NKEPT"]]))
         m1 = S1 / W
-        R.mu_AP_parameter_set = c + m1                                   # np.mean of the expanded rows, IP.py:1923
+        R.mu_AP_parameter_set = c + m1                                    # np.mean of the expanded rows, IP.py:1923
         cov = S2 / W - np.outer(m1, m1)
         R.posterior_covariance = cov
-        R.stdap_parameter_set = np.sqrt(np.maximum(np.diag(cov), 0.0))   # np.std (ddof 0), IP.py:1924
-        sumsq = np.diag(S2) + 2.0 * c * S1 + c * c * W                   # sum w*theta_d^2
-        R.evidence = (sums[lay["WEXP"]] / W) / np.sqrt(np.sum(sumsq))    # IP.py:1931
-        R.retained_min, R.retained_max = mn, mx
-        # histograms: np.histogram(bins=nbins) of every retained column (plotting_functions.py:135)
-        edges = np.stack([np.linspace(mn[d], mx[d], nbins + 1) if mx[d] > mn[d]
-                          else np.linspace(mn[d] - 0.5, mx[d] + 0.5, nbins + 1) for d in range(k)])
-        ed = torch.from_numpy(edges).to(self.dev)
-        hist = torch.zeros((k, nbins), dtype=torch.int64, device=self.dev)
-        self.pass3(thr, ed, hist, nbins)
-        R.histogram_counts = D.allreduce_int_np(hist.cpu().numpy())
-        R.histogram_edges = edges
+        R.stdap_parameter_set = np.sqrt(np.maximum(np.diag(cov), 0.0))    # np.std (ddof 0), IP.py:1924
+        sumsq = np.diag(S2) + 2.0 * c * S1 + c * c * W                    # sum w*theta_d^2
+        R.evidence = (acc[lay["WEXP"]] / W) / np.sqrt(np.sum(sumsq))      # IP.py:1931
+        R.retained_min = acc[lay["MIN"]:lay["MIN"] + k].copy()
+        R.retained_max = acc[lay["MAX"]:lay["MAX"] + k].copy()
+        o = 2 + lay["SIZE"]
+        R.histogram_counts = res[o:o + k * nbins].view(np.int64).reshape(k, nbins).copy()
+        R.histogram_edges = res[o + k * nbins:].reshape(k, nbins + 1).copy()
         return R

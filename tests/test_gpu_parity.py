@@ -210,8 +210,8 @@ def test_grid_order_and_shapes(env, golden):
     c, h, r = [1., -2., 3., 0.5, 10.], [0.1, 0.2, 0.3, 0.05, 1.5], [7, 0, 13, 1, 40]
     spec = make_spec("grid", 5, c, interval=h, radii=r)
     N = orc.grid_size(r)
-    first = N - 200000
-    pts = PE._points_from_spec(spec, first, 200000)
+    first = N - 60000
+    pts = PE._points_from_spec(spec, first, 60000)
     assert np.array_equal(pts, orc.grid_decode(c, h, r, np.arange(first, N)))
     assert np.array_equal(PE._points_from_spec(spec, 0, 5000), orc.grid_decode(c, h, r, np.arange(5000)))
 
