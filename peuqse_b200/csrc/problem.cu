@@ -146,6 +146,24 @@ extern "C" int peuqse_problem_create(const peuqse_problem_desc* h, peuqse_proble
     for (int r = 0; r < h->n_resp; ++r)
         d.U[r] = (h->resp_mode[r] == PEUQSE_RESP_MVN_FULL) ? (const double*)(base + o_U[r]) : nullptr;
 
+    // fast view
+    d.fast_n = 0;
+    for (int i = 0; i < PQ_MAXK; ++i) { d.gauss[i] = 0; d.pwn[i] = 0.0; }
+    for (int j = 0; j < h->kp && h->prior_mode == PEUQSE_PRIOR_DIAG; ++j) { d.gauss[d.gidx[j]] = 1; d.pwn[d.gidx[j]] = d.pw[j]; }
+    for (int i = 0; i < PQ_FAST_N; ++i) { d.fy[i] = 0.0; d.fw[i] = 0.0; }
+    for (int i = 0; i < PQ_FAST_N * PQ_MAXK; ++i) d.fmc[i] = 0.0;
+    if (h->n_resp == 1 && h->resp_mode[0] == PEUQSE_RESP_MVN_DIAG && h->n_total <= PQ_FAST_N &&
+        h->prior_mode != PEUQSE_PRIOR_DENSE &&
+        (h->model_id == PEUQSE_MODEL_QUADRATIC || h->model_id == PEUQSE_MODEL_LINEAR)) {
+        d.fast_n = h->n_total;
+        for (int j = 0; j < h->n_total; ++j) {
+            d.fy[j] = h->y[j];
+            d.fw[j] = h->w[j];
+            if (h->model_id == PEUQSE_MODEL_QUADRATIC) d.fmc[j] = h->model_const[j];
+            else for (int q = 0; q < h->k; ++q) d.fmc[j * PQ_MAXK + q] = h->model_const[(size_t)j * h->k + q];
+        }
+    }
+
     cudaGetDevice(&p->device);
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, p->device);

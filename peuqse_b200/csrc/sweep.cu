@@ -7,117 +7,22 @@
 #include "common.cuh"
 #include "eval.cuh"
 #include "launch.cuh"
-#include "philox.cuh"
 
-#define PQ_SWEEP_MAX_BLOCKS 2048
-#define PQ_SWEEP_TICKET_BYTES 256
-#define PQ_ACC_MAX PEUQSE_ACC_DOUBLES(PQ_MAXK)
+#include "sweep_common.cuh"
 
-struct FastDiv {            // unsigned 64-bit division by an invariant (Granlund & Montgomery 1994, fig. 4.1)
-    unsigned long long m;
-    int sh1, sh2;
-};
+// specialised grid kernels (sweep_grid.cu)
+int pq_grid_pass1(const peuqse_problem* p, const DevSweep& S, long long first, long long count, double* logp,
+                  peuqse_best* best, void* work, cudaStream_t st, bool* handled, long long* slab_count);
+int pq_grid_pass2(const peuqse_problem* p, const DevSweep& S, long long first, long long count, const double* logp,
+                  const peuqse_best* best, double log_rel, double* acc, long long* kidx, double* klogp, long long kcap,
+                  long long* kcount, void* work, cudaStream_t st, bool* handled, long long* slab_count);
+int pq_grid_hist(const peuqse_problem* p, const DevSweep& S, long long first, long long count, const double* logp,
+                 const peuqse_best* best, double log_rel, const double* edges, int nbins, unsigned long long* hist,
+                 cudaStream_t st, bool* handled, long long* slab_count);
 
-struct DevSweep {
-    int kind, k;
-    double center[PQ_MAXK], interval[PQ_MAXK], stdp[PQ_MAXK];
-    unsigned long long r2[PQ_MAXK];       // 2*radius
-    unsigned long long mprod[PQ_MAXK + 1];  // prod_{d<p}(2 r_d + 1)
-    FastDiv div[PQ_MAXK];
-    double spread;
-    unsigned long long seed;
-};
-
-static FastDiv make_fastdiv(unsigned long long d) {
-    FastDiv f;
-    if (d == 0) d = 1;
-    int l = 0;
-    while (l < 64 && (((unsigned __int128)1) << l) < d) ++l;
-    const unsigned __int128 two64 = ((unsigned __int128)1) << 64;
-    const unsigned __int128 num = two64 * ((((unsigned __int128)1) << l) - d);
-    f.m = (unsigned long long)(num / d + 1);
-    f.sh1 = l < 1 ? l : 1;
-    f.sh2 = l > 1 ? l - 1 : 0;
-    return f;
-}
-
-__device__ __forceinline__ unsigned long long fastdiv(unsigned long long n, const FastDiv& f) {
-    const unsigned long long t = __umul64hi(f.m, n);
-    return (t + ((n - t) >> f.sh1)) >> f.sh2;
-}
-
-static int build_sweep(const peuqse_sweep_spec* s, DevSweep* d, long long* total) {
-    if (!s || s->k < 1 || s->k > PQ_MAXK) return pq_set_error(PEUQSE_ERR_INVALID, "bad sweep spec");
-    d->kind = s->kind;
-    d->k = s->k;
-    d->spread = s->spread;
-    d->seed = s->seed;
-    unsigned __int128 m = 1;
-    d->mprod[0] = 1;
-    for (int p = 0; p < PQ_MAXK; ++p) {
-        const bool on = p < s->k;
-        d->center[p] = on ? s->center[p] : 0.0;
-        d->interval[p] = on ? s->interval[p] : 0.0;
-        d->stdp[p] = on ? s->std_prior[p] : 0.0;
-        const long long r = on ? s->radii[p] : 0;
-        if (r < 0) return pq_set_error(PEUQSE_ERR_INVALID, "negative grid radius");
-        d->r2[p] = 2ULL * (unsigned long long)r;
-        d->div[p] = make_fastdiv(d->r2[p]);
-        m *= (unsigned __int128)(d->r2[p] + 1);
-        if (m >> 62) return pq_set_error(PEUQSE_ERR_INVALID, "grid has more than 2^62 points");
-        d->mprod[p + 1] = (unsigned long long)m;
-    }
-    if (total) *total = (s->kind == 0) ? (long long)d->mprod[s->k] : (long long)0x3fffffffffffffffLL;
-    return PEUQSE_OK;
-}
-
-// element g of combinationGenerator's list: from the last axis down; point value c -/+ (h*i)
-// (CombinationGeneratorModule.py:59, 71: one multiply, one add)
-template <int KT>
-__device__ __forceinline__ void grid_point(const DevSweep& S, unsigned long long g, double (&th)[KT]) {
-#pragma unroll
-    for (int p = KT - 1; p >= 0; --p) {
-        th[p] = 0.0;
-        if (p < S.k) {
-            const unsigned long long M = S.mprod[p];
-            if (g < M) {
-                th[p] = S.center[p];
-            } else {
-                const unsigned long long gp = g - M;
-                const unsigned long long b = fastdiv(gp, S.div[p]);
-                const unsigned long long j = gp - b * S.r2[p];
-                const double step = S.interval[p] * (double)((j >> 1) + 1ULL);
-                th[p] = (j & 1ULL) ? (S.center[p] + step) : (S.center[p] - step);
-                g = b;
-            }
-        }
-    }
-}
-
-// generateInitialPoints('uniform') (IP.py:706, 749): ((spread*(-2+4u))*std) + center, u = Philox(seed, g)
-template <int KT>
-__device__ __forceinline__ void uniform_point(const DevSweep& S, unsigned long long g, double (&th)[KT]) {
-#pragma unroll
-    for (int b = 0; b < (KT + 1) / 2; ++b) {
-        if (2 * b < S.k) {
-            const Philox4 r = philox_block(S.seed, PQ_STREAM_UNIFORM_SWEEP, g, (uint32_t)b);
-            const double ua = philox_u53(r.x, r.y), ub = philox_u53(r.z, r.w);
-            th[2 * b] = (S.spread * (-2.0 + 4.0 * ua)) * S.stdp[2 * b] + S.center[2 * b];
-            if (2 * b + 1 < KT) {
-                th[2 * b + 1] = 0.0;
-                if (2 * b + 1 < S.k) th[2 * b + 1] = (S.spread * (-2.0 + 4.0 * ub)) * S.stdp[2 * b + 1] + S.center[2 * b + 1];
-            }
-        } else {
-            th[2 * b] = 0.0;
-            if (2 * b + 1 < KT) th[2 * b + 1] = 0.0;
-        }
-    }
-}
-
-template <int KT>
-__device__ __forceinline__ void sweep_point(const DevSweep& S, unsigned long long g, double (&th)[KT]) {
-    if (S.kind == 0) grid_point<KT>(S, g, th);
-    else uniform_point<KT>(S, g, th);
+__global__ void k_best_init(peuqse_best* b) {
+    b->logp = pq_neg_inf();
+    b->index = -1;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -169,6 +74,10 @@ __global__ void __launch_bounds__(256) k_sweep_pass1(const __grid_constant__ Dev
         }
         b = warp_best(b);
         if (threadIdx.x == 0) {
+            Best cur;
+            cur.v = best_out->logp;
+            cur.i = best_out->index < 0 ? 0x7fffffffffffffffLL : best_out->index;
+            b = best_merge(cur, b);
             best_out->logp = b.v;
             best_out->index = (b.i == 0x7fffffffffffffffLL) ? -1 : b.i;
             *ticket = 0;
@@ -508,6 +417,18 @@ extern "C" int peuqse_sweep_pass1(const peuqse_problem* p, const peuqse_sweep_sp
     if (first + count > total) return pq_set_error(PEUQSE_ERR_INVALID, "range exceeds the number of sweep points");
     cudaStream_t st = (cudaStream_t)stream;
     PQ_CUDA_OK(cudaMemsetAsync(d_work, 0, PQ_SWEEP_TICKET_BYTES, st));
+    k_best_init<<<1, 1, 0, st>>>(d_best);
+    {
+        bool handled = false;
+        long long slab = 0;
+        rc = pq_grid_pass1(p, S, first, count, d_logp, d_best, d_work, st, &handled, &slab);
+        if (rc) return rc;
+        if (handled) {
+            if (slab <= 0) return PEUQSE_OK;
+            count = slab;             // the generic kernel finishes the slab where the last axis sits at its centre
+        }
+    }
+    if (count == 0) return PEUQSE_OK;
 #define P1_L(KT, ...) return launch_pass1<PEUQSE_MODEL_LINEAR, KT>(p, S, first, count, d_logp, d_best, d_work, st)
 #define P1_E(KT, ...) return pq_set_error(PEUQSE_ERR_INVALID, "pass 1 needs a built-in model")
     PQ_SWEEP_DISPATCH((launch_pass1<PEUQSE_MODEL_QUADRATIC, 2>(p, S, first, count, d_logp, d_best, d_work, st)),
@@ -551,6 +472,18 @@ extern "C" int peuqse_sweep_pass2(const peuqse_problem* p, const peuqse_sweep_sp
     if (first + count > total) return pq_set_error(PEUQSE_ERR_INVALID, "range exceeds the number of sweep points");
     cudaStream_t st = (cudaStream_t)stream;
     PQ_CUDA_OK(cudaMemsetAsync(d_work, 0, PQ_SWEEP_TICKET_BYTES, st));
+    {
+        bool handled = false;
+        long long slab = 0;
+        rc = pq_grid_pass2(p, S, first, count, d_logp, d_best, log_rel_threshold, d_acc, (long long*)d_keep_index, d_keep_logp,
+                           keep_capacity, (long long*)d_keep_count, d_work, st, &handled, &slab);
+        if (rc) return rc;
+        if (handled) {
+            if (slab <= 0) return PEUQSE_OK;
+            count = slab;
+        }
+    }
+    if (count == 0) return PEUQSE_OK;
 #define P2_ARGS p, S, first, count, d_logp, d_best, log_rel_threshold, d_acc, (long long*)d_keep_index, d_keep_logp, keep_capacity, (long long*)d_keep_count, d_work, st
 #define P2_L(KT, ...) return launch_pass2<PEUQSE_MODEL_LINEAR, KT>(P2_ARGS)
 #define P2_E(KT, ...) return launch_pass2<PEUQSE_MODEL_EXTERNAL, KT>(P2_ARGS)
@@ -573,6 +506,18 @@ extern "C" int peuqse_sweep_hist(const peuqse_problem* p, const peuqse_sweep_spe
     if (rc) return rc;
     if (first + count > total) return pq_set_error(PEUQSE_ERR_INVALID, "range exceeds the number of sweep points");
     cudaStream_t st = (cudaStream_t)stream;
+    {
+        bool handled = false;
+        long long slab = 0;
+        rc = pq_grid_hist(p, S, first, count, d_logp, d_best, log_rel_threshold, d_edges, nbins, (unsigned long long*)d_hist, st,
+                          &handled, &slab);
+        if (rc) return rc;
+        if (handled) {
+            if (slab <= 0) return PEUQSE_OK;
+            count = slab;
+        }
+    }
+    if (count == 0) return PEUQSE_OK;
 #define P3_ARGS p, S, first, count, d_logp, d_best, log_rel_threshold, d_edges, nbins, (unsigned long long*)d_hist, st
 #define P3_L(KT, ...) return launch_hist<PEUQSE_MODEL_LINEAR, KT>(P3_ARGS)
 #define P3_E(KT, ...) return launch_hist<PEUQSE_MODEL_EXTERNAL, KT>(P3_ARGS)

@@ -326,3 +326,82 @@ def test_mh_many_chains_statistics(env):
     np.testing.assert_allclose(PE.mcmc_chain_moments['mean'], mean, atol=0.02 * std.max())
     np.testing.assert_allclose(PE.mcmc_chain_moments['std'], std, rtol=0.02)
     np.testing.assert_allclose(np.mean(PE.post_burn_in_samples, axis=0), PE.mcmc_chain_moments['mean'], rtol=1e-10)
+
+
+def _oracle_grid_stats(orc, P, bt, c, h, r, coef=2.0, nbins=10):
+    N = orc.grid_size(r)
+    th = orc.grid_decode(c, h, r, np.arange(N))
+    lp = orc.log_p_batch(P, th, bt)[0]
+    idx, best = orc.first_max_np(lp)
+    w, thr = orc.permutation_weights(lp, best, coef)
+    return th, lp, idx, best, w, orc.weighted_statistics(lp, th, w, nbins)
+
+
+@pytest.mark.parametrize("radii", [[20, 300], [3, 1200], [150, 128]])
+def test_grid_specialised_kernels_example00(env, radii):
+    """Long last axis -> the specialised row/column-hoisted grid kernels (sweep_grid.cu); bit-exact logP,
+    exact MAP index / weights / histograms, moments to rounding."""
+    PEUQSE, orc, _, torch = env
+    c, h = [200., 500.], [2.5, 0.4]
+    PE = make_pe(PEUQSE, PEUQSE.QuadraticModel(X00), Y00, S00, [200, 500], [100, 200],
+                 settings={'multistart_initialPointsDistributionType': 'grid', 'multistart_gridsearchSamplingInterval': h,
+                           'multistart_gridsearchSamplingRadii': radii})
+    PE.doMultiStart()
+    P = orc.build_problem([200, 500], [100, 200], Y00, S00)
+    _, bt = orc.sim_quadratic(X00)
+    th, lp, idx, best, w, st = _oracle_grid_stats(orc, P, bt, c, h, radii)
+    got = PE.permutations_MAP_logP_and_parameters_values
+    assert np.array_equal(got[:, 1:], th)
+    assert np.array_equal(got[:, 0], lp)
+    assert PE.map_index == idx and PE.map_logP == best
+    assert PE.sweep_result.sum_weights == w.sum() and PE.sweep_result.n_retained == int((w > 0).sum())
+    np.testing.assert_allclose(PE.mu_AP_parameter_set, st['mu_AP'], rtol=1e-12)
+    np.testing.assert_allclose(PE.stdap_parameter_set, st['stdap'], rtol=1e-10)
+    np.testing.assert_allclose(PE.evidence, st['evidence'], rtol=1e-11)
+    assert np.array_equal(PE.marginal_histograms[0], st['hist'].astype(np.int64))
+    np.testing.assert_allclose(PE.marginal_histograms[1], st['edges'], rtol=1e-15)
+    # sharded exactly like ranks would: three index ranges, merged with the rule of distributed.merge_best
+    from peuqse_b200.sweep import Sweep, make_spec
+    from peuqse_b200 import distributed as D
+    spec = make_spec("grid", 2, c, interval=h, radii=radii)
+    N = orc.grid_size(radii)
+    bests, accs, hists = [], [], []
+    log_rel = float(np.log(10 ** -2.0))
+    for rnk in range(3):
+        sw = Sweep(PE.device_problem, spec, N)
+        sw.first, sw.count = D.shard_range(N, rnk, 3)
+        sw.logp = torch.empty(sw.count, dtype=torch.float64, device="cuda")
+        sw.pass1()
+        b = sw.best.cpu()
+        bests.append((float(b[0]), int(b.view(torch.int64)[1])))
+        assert np.array_equal(sw.logp.cpu().numpy(), lp[sw.first:sw.first + sw.count])
+    gb = D.merge_best(bests)
+    assert gb == (best, idx)
+
+
+def test_grid_specialised_linear_k3(env):
+    PEUQSE, orc, _, _ = env
+    rng = np.random.default_rng(11)
+    k, n = 3, 5
+    Phi = rng.standard_normal((n, k))
+    truth = np.array([0.3, -0.2, 0.5])
+    sig = 0.2 + 0.1 * rng.random(n)
+    y = Phi @ truth + sig * rng.standard_normal(n)
+    c, h, r = [0.0, 0.1, -0.1], [0.05, 0.07, 0.004], [6, 5, 400]
+    PE = make_pe(PEUQSE, PEUQSE.LinearModel(Phi), list(y), list(sig), [0.0] * k, [1.0, 2.0, 0.5],
+                 settings={'multistart_initialPointsDistributionType': 'grid', 'multistart_gridsearchSamplingInterval': h,
+                           'multistart_gridsearchSamplingRadii': r},
+                 InputParameterInitialGuess=c, InputParameterPriorValues_upperBounds=[None, 0.4, None],
+                 InputParameterPriorValues_lowerBounds=[-0.2, None, None])
+    PE.doMultiStart()
+    P = orc.build_problem([0.0] * k, [1.0, 2.0, 0.5], y, sig, upper_bounds=[None, 0.4, None], lower_bounds=[-0.2, None, None])
+    _, bt = orc.sim_linear(Phi)
+    th, lp, idx, best, w, st = _oracle_grid_stats(orc, P, bt, c, h, r)
+    got = PE.permutations_MAP_logP_and_parameters_values
+    assert np.array_equal(got[:, 1:], th)
+    assert np.array_equal(got[:, 0], lp)
+    assert np.isneginf(lp).any() and PE.map_index == idx and PE.map_logP == best
+    assert PE.sweep_result.sum_weights == w.sum()
+    np.testing.assert_allclose(PE.mu_AP_parameter_set, st['mu_AP'], rtol=1e-11)
+    np.testing.assert_allclose(PE.stdap_parameter_set, st['stdap'], rtol=1e-9)
+    assert np.array_equal(PE.marginal_histograms[0], st['hist'].astype(np.int64))
