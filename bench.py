@@ -300,7 +300,7 @@ def run_ours(args):
     dt = float(te.item())
     e2e_value = total * Ke / dt
     h2d = 3 * ctypes.sizeof(_lib.SweepSpec) + 4 * 8      # sweep spec re-sent as kernel parameters by each pass + scalars
-    d2h = sw.result_bytes() + 2 * 8                      # packed (best, moments, histogram, edges) + the MAP point
+    d2h = sw.result_bytes()                              # packed (best, moments, histogram, edges, MAP point)
     assert PE.map_index >= 0 and np.isfinite(PE.map_logP)
 
     if rank != 0:
@@ -310,7 +310,7 @@ def run_ours(args):
     pk, pk_kind = peaks()
     algo_bytes = 8.0 * sw.count                         # one fp64 logP written per evaluated point
     achieved = algo_bytes / (pass1_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_sweep_pass1<QUADRATIC,2>", "achieved": achieved, "peak": pk["hbm_gbs"],
+    roofline = {"bound": "hbm", "kernel": "k_grid_pass1<QUADRATIC,k=2,n=3>", "achieved": achieved, "peak": pk["hbm_gbs"],
                 "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "peak_source": pk_kind, "traffic": TRAFFIC_PASS1,
                 "launch_ms": pass1_ms, "share_of_step": pass1_ms * K / ms_total,
                 "fp64_note": "32 fp64 flop/eval algorithmic (SURVEY 8d): %.2f TFLOP/s" % (32.0 * sw.count / (pass1_ms * 1e-3) / 1e12)}

@@ -156,11 +156,17 @@ typedef struct peuqse_best {
  * Pass 1: evaluate points first..first+count-1 of the sweep, keep the first strict maximum.
  * d_logp (nullable): logP of every point, d_logp[i] for global index first+i (the first column of
  * permutations_MAP_logP_and_parameters_values, IP.py:947).  d_best: one peuqse_best.
- * d_work: scratch of peuqse_sweep_work_bytes() bytes.
+ * d_work: scratch of peuqse_sweep_work_bytes(p, spec, first, count) bytes, ZERO-INITIALISED before its first use
+ * (calls leave it ready for the next call) and shared by passes 1-3 of the same range: pass 1 leaves per-tile
+ * maxima in it that let passes 2-3 skip tiles without retained points.  (p = spec = NULL gives the base size,
+ * enough for any range when logP is not stored.)
  */
-int64_t peuqse_sweep_work_bytes(void);
+int64_t peuqse_sweep_work_bytes(const peuqse_problem* p, const peuqse_sweep_spec* spec, int64_t first, int64_t count);
 int peuqse_sweep_pass1(const peuqse_problem* p, const peuqse_sweep_spec* spec, int64_t first, int64_t count,
                        double* d_logp, peuqse_best* d_best, void* d_work, void* stream);
+
+/* theta[k] of the point d_best->index (NaN when index < 0), decoded on the device */
+int peuqse_sweep_best_point(const peuqse_sweep_spec* spec, const peuqse_best* d_best, double* d_theta, void* stream);
 
 /* decode points of a sweep without evaluating them: d_theta[count][k] (listOfPermutations, IP.py:776) */
 int peuqse_sweep_points(const peuqse_sweep_spec* spec, int64_t first, int64_t count, double* d_theta, void* stream);
@@ -191,7 +197,8 @@ int peuqse_sweep_pass2(const peuqse_problem* p, const peuqse_sweep_spec* spec, i
                        void* d_work, void* stream);
 
 /* bin edges np.linspace(min_d, max_d, nbins+1) from the pass-2 accumulator: d_edges[k][nbins+1] */
-int peuqse_sweep_edges(const double* d_acc, int32_t k, int32_t nbins, double* d_edges, void* stream);
+int peuqse_sweep_edges(const double* d_acc, int32_t k, int32_t nbins, double* d_edges, uint64_t* d_hist_to_zero /*nullable*/,
+                       void* stream);
 
 /*
  * Pass 3: weighted marginal histograms of the retained points (plotting_functions.py:135 -> ax.hist ->
@@ -200,7 +207,7 @@ int peuqse_sweep_edges(const double* d_acc, int32_t k, int32_t nbins, double* d_
  */
 int peuqse_sweep_hist(const peuqse_problem* p, const peuqse_sweep_spec* spec, int64_t first, int64_t count,
                       const double* d_logp, const peuqse_best* d_best, double log_rel_threshold,
-                      const double* d_edges, int32_t nbins, uint64_t* d_hist, void* stream);
+                      const double* d_edges, int32_t nbins, uint64_t* d_hist, void* d_work, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Metropolis-Hastings: doMetropolisHastings (IP.py:2563-2754), C independent chains

@@ -11,14 +11,20 @@
 #include "sweep_common.cuh"
 
 // specialised grid kernels (sweep_grid.cu)
-int pq_grid_pass1(const peuqse_problem* p, const DevSweep& S, long long first, long long count, double* logp,
-                  peuqse_best* best, void* work, cudaStream_t st, bool* handled, long long* slab_count);
+long long pq_grid_aux_bytes(const peuqse_problem* p, const DevSweep& S, long long first, long long count);
+int pq_grid_pass1(const peuqse_problem* p, const DevSweep& S, long long first, long long count, double* logp, double* tilemax,
+                  peuqse_best* best, void* work, cudaStream_t st, bool* handled);
 int pq_grid_pass2(const peuqse_problem* p, const DevSweep& S, long long first, long long count, const double* logp,
-                  const peuqse_best* best, double log_rel, double* acc, long long* kidx, double* klogp, long long kcap,
-                  long long* kcount, void* work, cudaStream_t st, bool* handled, long long* slab_count);
+                  const double* tilemax, const peuqse_best* best, double log_rel, double* acc, long long* kidx, double* klogp,
+                  long long kcap, long long* kcount, void* work, cudaStream_t st, bool* handled);
 int pq_grid_hist(const peuqse_problem* p, const DevSweep& S, long long first, long long count, const double* logp,
-                 const peuqse_best* best, double log_rel, const double* edges, int nbins, unsigned long long* hist,
-                 cudaStream_t st, bool* handled, long long* slab_count);
+                 const double* tilemax, const peuqse_best* best, double log_rel, const double* edges, int nbins,
+                 unsigned long long* hist, cudaStream_t st, bool* handled);
+
+#define PQ_SWEEP_BASE_BYTES ((long long)PQ_SWEEP_TICKET_BYTES + (long long)PQ_SWEEP_MAX_BLOCKS * PQ_ACC_MAX * (long long)sizeof(double))
+static inline double* tilemax_ptr(const peuqse_problem* p, const DevSweep& S, long long first, long long count, void* d_work) {
+    return pq_grid_aux_bytes(p, S, first, count) > 0 ? (double*)((char*)d_work + PQ_SWEEP_BASE_BYTES) : nullptr;
+}
 
 __global__ void k_best_init(peuqse_best* b) {
     b->logp = pq_neg_inf();
@@ -377,8 +383,14 @@ int launch_hist(const peuqse_problem* p, const DevSweep& S, long long first, lon
 
 }  // namespace
 
-extern "C" int64_t peuqse_sweep_work_bytes(void) {
-    return (int64_t)PQ_SWEEP_TICKET_BYTES + (int64_t)PQ_SWEEP_MAX_BLOCKS * PQ_ACC_MAX * (int64_t)sizeof(double);
+extern "C" int64_t peuqse_sweep_work_bytes(const peuqse_problem* p, const peuqse_sweep_spec* spec, int64_t first, int64_t count) {
+    long long aux = 0;
+    if (p && spec) {
+        DevSweep S;
+        long long total;
+        if (build_sweep(spec, &S, &total) == PEUQSE_OK) aux = pq_grid_aux_bytes(p, S, first, count);
+    }
+    return PQ_SWEEP_BASE_BYTES + aux;
 }
 
 #define PQ_SWEEP_DISPATCH(CALL_Q, CALL_T, CALL_L, CALL_E)                                         \
@@ -416,18 +428,13 @@ extern "C" int peuqse_sweep_pass1(const peuqse_problem* p, const peuqse_sweep_sp
     if (rc) return rc;
     if (first + count > total) return pq_set_error(PEUQSE_ERR_INVALID, "range exceeds the number of sweep points");
     cudaStream_t st = (cudaStream_t)stream;
-    PQ_CUDA_OK(cudaMemsetAsync(d_work, 0, PQ_SWEEP_TICKET_BYTES, st));
-    k_best_init<<<1, 1, 0, st>>>(d_best);
     {
         bool handled = false;
-        long long slab = 0;
-        rc = pq_grid_pass1(p, S, first, count, d_logp, d_best, d_work, st, &handled, &slab);
-        if (rc) return rc;
-        if (handled) {
-            if (slab <= 0) return PEUQSE_OK;
-            count = slab;             // the generic kernel finishes the slab where the last axis sits at its centre
-        }
+        rc = pq_grid_pass1(p, S, first, count, d_logp, tilemax_ptr(p, S, first, count, d_work), d_best, d_work, st, &handled);
+        if (rc || handled) return rc;
     }
+    PQ_CUDA_OK(cudaMemsetAsync(d_work, 0, PQ_SWEEP_TICKET_BYTES, st));
+    k_best_init<<<1, 1, 0, st>>>(d_best);
     if (count == 0) return PEUQSE_OK;
 #define P1_L(KT, ...) return launch_pass1<PEUQSE_MODEL_LINEAR, KT>(p, S, first, count, d_logp, d_best, d_work, st)
 #define P1_E(KT, ...) return pq_set_error(PEUQSE_ERR_INVALID, "pass 1 needs a built-in model")
@@ -471,18 +478,13 @@ extern "C" int peuqse_sweep_pass2(const peuqse_problem* p, const peuqse_sweep_sp
     if (rc) return rc;
     if (first + count > total) return pq_set_error(PEUQSE_ERR_INVALID, "range exceeds the number of sweep points");
     cudaStream_t st = (cudaStream_t)stream;
-    PQ_CUDA_OK(cudaMemsetAsync(d_work, 0, PQ_SWEEP_TICKET_BYTES, st));
     {
         bool handled = false;
-        long long slab = 0;
-        rc = pq_grid_pass2(p, S, first, count, d_logp, d_best, log_rel_threshold, d_acc, (long long*)d_keep_index, d_keep_logp,
-                           keep_capacity, (long long*)d_keep_count, d_work, st, &handled, &slab);
-        if (rc) return rc;
-        if (handled) {
-            if (slab <= 0) return PEUQSE_OK;
-            count = slab;
-        }
+        rc = pq_grid_pass2(p, S, first, count, d_logp, tilemax_ptr(p, S, first, count, d_work), d_best, log_rel_threshold, d_acc,
+                           (long long*)d_keep_index, d_keep_logp, keep_capacity, (long long*)d_keep_count, d_work, st, &handled);
+        if (rc || handled) return rc;
     }
+    PQ_CUDA_OK(cudaMemsetAsync(d_work, 0, PQ_SWEEP_TICKET_BYTES, st));
     if (count == 0) return PEUQSE_OK;
 #define P2_ARGS p, S, first, count, d_logp, d_best, log_rel_threshold, d_acc, (long long*)d_keep_index, d_keep_logp, keep_capacity, (long long*)d_keep_count, d_work, st
 #define P2_L(KT, ...) return launch_pass2<PEUQSE_MODEL_LINEAR, KT>(P2_ARGS)
@@ -495,7 +497,7 @@ extern "C" int peuqse_sweep_pass2(const peuqse_problem* p, const peuqse_sweep_sp
 
 extern "C" int peuqse_sweep_hist(const peuqse_problem* p, const peuqse_sweep_spec* spec, int64_t first, int64_t count,
                                  const double* d_logp, const peuqse_best* d_best, double log_rel_threshold,
-                                 const double* d_edges, int32_t nbins, uint64_t* d_hist, void* stream) {
+                                 const double* d_edges, int32_t nbins, uint64_t* d_hist, void* d_work, void* stream) {
     int rc = check_sweep_args(p, spec, first, count);
     if (rc) return rc;
     if (!d_edges || !d_hist || !d_best || nbins < 1 || nbins > 4096) return pq_set_error(PEUQSE_ERR_INVALID, "bad histogram arguments");
@@ -508,14 +510,9 @@ extern "C" int peuqse_sweep_hist(const peuqse_problem* p, const peuqse_sweep_spe
     cudaStream_t st = (cudaStream_t)stream;
     {
         bool handled = false;
-        long long slab = 0;
-        rc = pq_grid_hist(p, S, first, count, d_logp, d_best, log_rel_threshold, d_edges, nbins, (unsigned long long*)d_hist, st,
-                          &handled, &slab);
-        if (rc) return rc;
-        if (handled) {
-            if (slab <= 0) return PEUQSE_OK;
-            count = slab;
-        }
+        rc = pq_grid_hist(p, S, first, count, d_logp, d_work ? tilemax_ptr(p, S, first, count, d_work) : nullptr, d_best,
+                          log_rel_threshold, d_edges, nbins, (unsigned long long*)d_hist, st, &handled);
+        if (rc || handled) return rc;
     }
     if (count == 0) return PEUQSE_OK;
 #define P3_ARGS p, S, first, count, d_logp, d_best, log_rel_threshold, d_edges, nbins, (unsigned long long*)d_hist, st
@@ -529,8 +526,10 @@ extern "C" int peuqse_sweep_hist(const peuqse_problem* p, const peuqse_sweep_spe
 
 // np.linspace(min_d, max_d, nbins+1) from the pass-2 accumulator (np.histogram's edges for range=None):
 // y = arange(0, num)*step + start with step = (stop-start)/div, last element := stop (numpy/_core/function_base.py)
-__global__ void k_sweep_edges(const double* __restrict__ acc, int k, int nbins, double* __restrict__ edges) {
+__global__ void k_sweep_edges(const double* __restrict__ acc, int k, int nbins, double* __restrict__ edges,
+                              unsigned long long* __restrict__ hist_to_zero) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (hist_to_zero && t < k * nbins) hist_to_zero[t] = 0ULL;
     if (t >= k * (nbins + 1)) return;
     const int d = t / (nbins + 1), i = t - d * (nbins + 1);
     double lo = acc[PEUQSE_ACC_MIN(k) + d], hi = acc[PEUQSE_ACC_MAX(k) + d];
@@ -539,10 +538,37 @@ __global__ void k_sweep_edges(const double* __restrict__ acc, int k, int nbins, 
     edges[t] = (i == nbins) ? hi : ((double)i * step + lo);
 }
 
-extern "C" int peuqse_sweep_edges(const double* d_acc, int32_t k, int32_t nbins, double* d_edges, void* stream) {
+extern "C" int peuqse_sweep_edges(const double* d_acc, int32_t k, int32_t nbins, double* d_edges, uint64_t* d_hist_to_zero,
+                                  void* stream) {
     if (!d_acc || !d_edges || k < 1 || k > PQ_MAXK || nbins < 1) return pq_set_error(PEUQSE_ERR_INVALID, "bad edges arguments");
     const int n = k * (nbins + 1);
-    k_sweep_edges<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_acc, k, nbins, d_edges);
+    k_sweep_edges<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_acc, k, nbins, d_edges, (unsigned long long*)d_hist_to_zero);
+    PQ_CUDA_OK(cudaGetLastError());
+    return PEUQSE_OK;
+}
+
+// theta of the best point, decoded on the device (keeps the whole multistart free of host round trips)
+template <int KT>
+__global__ void k_best_point(const __grid_constant__ DevSweep S, const peuqse_best* __restrict__ best, double* __restrict__ theta) {
+    double th[KT];
+    const long long g = best->index;
+    if (g >= 0) sweep_point<KT>(S, (unsigned long long)g, th);
+#pragma unroll
+    for (int d = 0; d < KT; ++d)
+        if (d < S.k) theta[d] = g >= 0 ? th[d] : __longlong_as_double(0x7ff8000000000000LL);
+}
+
+extern "C" int peuqse_sweep_best_point(const peuqse_sweep_spec* spec, const peuqse_best* d_best, double* d_theta, void* stream) {
+    DevSweep S;
+    long long total;
+    int rc = build_sweep(spec, &S, &total);
+    if (rc) return rc;
+    if (!d_best || !d_theta) return pq_set_error(PEUQSE_ERR_INVALID, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int kb = pq_k_bucket(spec->k);
+#define BPT(KT, ...) k_best_point<KT><<<1, 1, 0, st>>>(S, d_best, d_theta)
+    PQ_DISPATCH_K(kb, BPT, 0)
+#undef BPT
     PQ_CUDA_OK(cudaGetLastError());
     return PEUQSE_OK;
 }

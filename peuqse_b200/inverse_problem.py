@@ -317,7 +317,13 @@ class parameter_estimation:
             return self._multistart_external(spec, n, toSamples and calculatePostBurnInStatistics, coef, nbins, centerPoint)
         store = pes.get('multistart_store_logP', 'auto')
         store = (n <= 2 ** 31) if store == 'auto' else bool(store)
-        sw = Sweep(self.device_problem, spec, n, store_logp=store, nbins=nbins)
+        key = (bytes(spec), n, store, nbins, D.world())
+        if getattr(self, '_sweep_key', None) == key:
+            sw = self._sweep                    # same sweep again: reuse the device buffers
+            sw.launches = 0
+        else:
+            sw = Sweep(self.device_problem, spec, n, store_logp=store, nbins=nbins)
+            self._sweep_key = key
         res = sw.run(coef=coef, statistics=bool(toSamples and calculatePostBurnInStatistics))
         self.gpu_launches += sw.launches
         self._sweep = sw

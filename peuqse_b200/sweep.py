@@ -44,26 +44,29 @@ class SweepResult:
 
 
 class Sweep:
-    def __init__(self, dp, spec, total, store_logp=True, nbins=10):
+    def __init__(self, dp, spec, total, store_logp=True, nbins=10, shard=None):
         self.dp = dp
         self.spec = spec
         self.k = k = spec.k
         self.total = int(total)
         self.nbins = int(nbins)
         self.L = _lib.load()
-        self.first, self.count = D.shard_range(self.total)
+        self.first, self.count = D.shard_range(self.total) if shard is None else D.shard_range(self.total, *shard)
         dev = torch.device("cuda", torch.cuda.current_device())
         self.dev = dev
-        self.work = torch.empty(int(self.L.peuqse_sweep_work_bytes()), dtype=torch.uint8, device=dev)
+        self.work = torch.zeros(int(self.L.peuqse_sweep_work_bytes(dp.handle if store_logp else None,
+                                                                    C.byref(spec) if store_logp else None,
+                                                                    self.first, self.count)), dtype=torch.uint8, device=dev)
         self.logp = torch.empty(self.count, dtype=torch.float64, device=dev) if store_logp else None
         # packed result: [best(2) | acc | hist (int64 bits) | edges]
         self.lay = lay = _lib.acc_layout(k)
         nacc = lay["SIZE"]
-        self.res = torch.zeros(2 + nacc + k * nbins + k * (nbins + 1), dtype=torch.float64, device=dev)
+        self.res = torch.zeros(2 + nacc + k * nbins + k * (nbins + 1) + k, dtype=torch.float64, device=dev)
         self.best = self.res[0:2]                                        # peuqse_best {double logp, int64 index}
         self.acc = self.res[2:2 + nacc]
         self.hist = self.res[2 + nacc:2 + nacc + k * nbins].view(torch.int64)
-        self.edges = self.res[2 + nacc + k * nbins:]
+        self.edges = self.res[2 + nacc + k * nbins:2 + nacc + k * nbins + k * (nbins + 1)]
+        self.map_theta = self.res[2 + nacc + k * nbins + k * (nbins + 1):]
         self.acc_init = torch.zeros(nacc, dtype=torch.float64, device=dev)
         self.acc_init[lay["MIN"]:lay["MIN"] + k] = float("inf")
         self.acc_init[lay["MAX"]:lay["MAX"] + k] = float("-inf")
@@ -78,6 +81,9 @@ class Sweep:
         self.launches += 1
         if self.world > 1:
             self._merge_best()
+        _lib.check(self.L.peuqse_sweep_best_point(C.byref(self.spec), _lib.ptr(self.best), _lib.ptr(self.map_theta),
+                                                  _lib.current_stream()))
+        self.launches += 1
 
     def _merge_best(self):
         """all-gather of the 16-byte (maxLogP, index) records; highest value, lowest index among equals."""
@@ -115,12 +121,11 @@ class Sweep:
             dist.all_reduce(self.acc[lay["MAX"]:lay["MAX"] + k], op=dist.ReduceOp.MAX)
 
     def pass3(self, log_rel):
-        self.hist.zero_()
         _lib.check(self.L.peuqse_sweep_edges(_lib.ptr(self.acc), self.k, self.nbins, _lib.ptr(self.edges),
-                                             _lib.current_stream()))
+                                             _lib.ptr(self.hist), _lib.current_stream()))
         _lib.check(self.L.peuqse_sweep_hist(self.dp.handle, C.byref(self.spec), self.first, self.count,
                                             _lib.ptr(self.logp), _lib.ptr(self.best), float(log_rel), _lib.ptr(self.edges),
-                                            self.nbins, _lib.ptr(self.hist), _lib.current_stream()))
+                                            self.nbins, _lib.ptr(self.hist), _lib.ptr(self.work), _lib.current_stream()))
         self.launches += 2
         if self.world > 1:
             import torch.distributed as dist
@@ -164,7 +169,7 @@ class Sweep:
             R.map_parameter_set = np.full(k, np.nan)
             R.statistics = False
             return R
-        R.map_parameter_set = self.points(R.map_index, 1).cpu().numpy()[0]
+        R.map_parameter_set = res[res.shape[0] - k:].copy()
         R.statistics = bool(statistics)
         if not statistics:
             return R
@@ -187,5 +192,5 @@ class Sweep:
         R.retained_max = acc[lay["MAX"]:lay["MAX"] + k].copy()
         o = 2 + lay["SIZE"]
         R.histogram_counts = res[o:o + k * nbins].view(np.int64).reshape(k, nbins).copy()
-        R.histogram_edges = res[o + k * nbins:].reshape(k, nbins + 1).copy()
+        R.histogram_edges = res[o + k * nbins:o + k * nbins + k * (nbins + 1)].reshape(k, nbins + 1).copy()
         return R

@@ -368,9 +368,7 @@ def test_grid_specialised_kernels_example00(env, radii):
     bests, accs, hists = [], [], []
     log_rel = float(np.log(10 ** -2.0))
     for rnk in range(3):
-        sw = Sweep(PE.device_problem, spec, N)
-        sw.first, sw.count = D.shard_range(N, rnk, 3)
-        sw.logp = torch.empty(sw.count, dtype=torch.float64, device="cuda")
+        sw = Sweep(PE.device_problem, spec, N, shard=(rnk, 3))
         sw.pass1()
         b = sw.best.cpu()
         bests.append((float(b[0]), int(b.view(torch.int64)[1])))
