@@ -204,10 +204,14 @@ int peuqse_sweep_edges(const double* d_acc, int32_t k, int32_t nbins, double* d_
  * Pass 3: weighted marginal histograms of the retained points (plotting_functions.py:135 -> ax.hist ->
  * np.histogram with equal bins over [min, max] of the retained values, last bin closed).
  * d_edges[k][nbins+1]: bin edges; d_hist[k][nbins]: integer weight sums, accumulated (zero it first).
+ * reuse_pass2_sums != 0: peuqse_sweep_pass2 with the same (p, spec, first, count, d_logp, d_best, threshold, d_work) was
+ * the previous sweep call on d_work; the per-row / per-column weight sums it left there are binned instead of
+ * reading logP again.  d_work may be NULL (then logP is always re-read).
  */
 int peuqse_sweep_hist(const peuqse_problem* p, const peuqse_sweep_spec* spec, int64_t first, int64_t count,
                       const double* d_logp, const peuqse_best* d_best, double log_rel_threshold,
-                      const double* d_edges, int32_t nbins, uint64_t* d_hist, void* d_work, void* stream);
+                      const double* d_edges, int32_t nbins, uint64_t* d_hist, void* d_work, int32_t reuse_pass2_sums,
+                      void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Metropolis-Hastings: doMetropolisHastings (IP.py:2563-2754), C independent chains

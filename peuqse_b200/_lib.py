@@ -116,7 +116,7 @@ def load():
     L.peuqse_sweep_best_point.argtypes = [C.POINTER(SweepSpec), vp, vp, vp]
     L.peuqse_sweep_pass2.argtypes = [vp, C.POINTER(SweepSpec), i64, i64, vp, vp, dbl, vp, vp, vp, i64, vp, vp, vp]
     L.peuqse_sweep_edges.argtypes = [vp, i32, i32, vp, vp, vp]
-    L.peuqse_sweep_hist.argtypes = [vp, C.POINTER(SweepSpec), i64, i64, vp, vp, dbl, vp, i32, vp, vp, vp]
+    L.peuqse_sweep_hist.argtypes = [vp, C.POINTER(SweepSpec), i64, i64, vp, vp, dbl, vp, i32, vp, vp, i32, vp]
     L.peuqse_mh_run.argtypes = [vp, C.POINTER(MHSpec), vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.peuqse_philox_blocks.argtypes = [u64, u32, i64, i64, u32, vp, vp]
     L.peuqse_ess_work_bytes.restype = i64

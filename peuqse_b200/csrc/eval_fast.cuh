@@ -30,6 +30,62 @@ struct FastSim<PEUQSE_MODEL_LINEAR, KT> {
     }
 };
 
+// Row/column split of the built-in models for grid sweeps: everything that depends only on the lower axes of a
+// grid row is computed once per row (row_pre), the last-axis part per point (at_last).  Same operation order as at().
+template <int MODEL, int KT>
+struct FastSplit;
+
+template <int KT>
+struct FastSplit<PEUQSE_MODEL_QUADRATIC, KT> {           // (x_j - a)^2 + b, a = th[0] (row), b = th[1] (last axis)
+    template <int J>
+    __device__ __forceinline__ static double row_pre(const DevProblem& P, const double (&th)[KT]) {
+        const double d = P.fmc[J] - th[0];
+        return d * d;
+    }
+    template <int J>
+    __device__ __forceinline__ static double at_last(const DevProblem& P, double pre, double thL) { return pre + thL; }
+};
+
+template <int KT>
+struct FastSplit<PEUQSE_MODEL_LINEAR, KT> {              // ((Phi_j0 th_0 + Phi_j1 th_1) + ...) + Phi_jL th_L
+    template <int J>
+    __device__ __forceinline__ static double row_pre(const DevProblem& P, const double (&th)[KT]) {
+        if (KT == 1) return 0.0;
+        double acc = P.fmc[J * PQ_MAXK] * th[0];
+#pragma unroll
+        for (int d = 1; d < KT - 1; ++d) acc = acc + P.fmc[J * PQ_MAXK + d] * th[d];
+        return acc;
+    }
+    template <int J>
+    __device__ __forceinline__ static double at_last(const DevProblem& P, double pre, double thL) {
+        const double t = P.fmc[J * PQ_MAXK + (KT - 1)] * thL;
+        return (KT == 1) ? t : (pre + t);
+    }
+};
+
+template <int MODEL, int KT, int NT, int J>
+struct FastRowPre {
+    __device__ __forceinline__ static void fill(const DevProblem& P, const double (&th)[KT], double* pre) {
+        pre[J] = FastSplit<MODEL, KT>::template row_pre<J>(P, th);
+        if constexpr (J + 1 < NT) FastRowPre<MODEL, KT, NT, J + 1>::fill(P, th, pre);
+    }
+};
+
+template <int MODEL, int KT, int NT, bool EXACT, int J>
+struct FastQLast {
+    __device__ __forceinline__ static void fill(const DevProblem& P, const double (&pre)[NT], double thL, double (&q)[NT]) {
+        if (EXACT || J < P.fast_n) {
+            const double s = FastSplit<MODEL, KT>::template at_last<J>(P, pre[J], thL);
+            const double d = P.fy[J] - s;                       // x - mean (IP.py:2960)
+            const double t = d * P.fw[J];
+            q[J] = t * t;
+        } else {
+            q[J] = 0.0;
+        }
+        if constexpr (J + 1 < NT) FastQLast<MODEL, KT, NT, EXACT, J + 1>::fill(P, pre, thL, q);
+    }
+};
+
 template <int MODEL, int KT, int NT, bool EXACT, int J>
 struct FastQ {
     __device__ __forceinline__ static void fill(const DevProblem& P, const double (&th)[KT], double (&q)[NT]) {

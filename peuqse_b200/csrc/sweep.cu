@@ -12,18 +12,18 @@
 
 // specialised grid kernels (sweep_grid.cu)
 long long pq_grid_aux_bytes(const peuqse_problem* p, const DevSweep& S, long long first, long long count);
-int pq_grid_pass1(const peuqse_problem* p, const DevSweep& S, long long first, long long count, double* logp, double* tilemax,
+int pq_grid_pass1(const peuqse_problem* p, const DevSweep& S, long long first, long long count, double* logp, void* aux_base,
                   peuqse_best* best, void* work, cudaStream_t st, bool* handled);
 int pq_grid_pass2(const peuqse_problem* p, const DevSweep& S, long long first, long long count, const double* logp,
-                  const double* tilemax, const peuqse_best* best, double log_rel, double* acc, long long* kidx, double* klogp,
+                  void* aux_base, const peuqse_best* best, double log_rel, double* acc, long long* kidx, double* klogp,
                   long long kcap, long long* kcount, void* work, cudaStream_t st, bool* handled);
 int pq_grid_hist(const peuqse_problem* p, const DevSweep& S, long long first, long long count, const double* logp,
-                 const double* tilemax, const peuqse_best* best, double log_rel, const double* edges, int nbins,
-                 unsigned long long* hist, cudaStream_t st, bool* handled);
+                 void* aux_base, const peuqse_best* best, double log_rel, const double* edges, int nbins,
+                 unsigned long long* hist, cudaStream_t st, bool* handled, bool use_fused_sums);
 
 #define PQ_SWEEP_BASE_BYTES ((long long)PQ_SWEEP_TICKET_BYTES + (long long)PQ_SWEEP_MAX_BLOCKS * PQ_ACC_MAX * (long long)sizeof(double))
-static inline double* tilemax_ptr(const peuqse_problem* p, const DevSweep& S, long long first, long long count, void* d_work) {
-    return pq_grid_aux_bytes(p, S, first, count) > 0 ? (double*)((char*)d_work + PQ_SWEEP_BASE_BYTES) : nullptr;
+static inline void* aux_ptr(const peuqse_problem* p, const DevSweep& S, long long first, long long count, void* d_work) {
+    return (d_work && pq_grid_aux_bytes(p, S, first, count) > 0) ? (void*)((char*)d_work + PQ_SWEEP_BASE_BYTES) : nullptr;
 }
 
 __global__ void k_best_init(peuqse_best* b) {
@@ -430,7 +430,7 @@ extern "C" int peuqse_sweep_pass1(const peuqse_problem* p, const peuqse_sweep_sp
     cudaStream_t st = (cudaStream_t)stream;
     {
         bool handled = false;
-        rc = pq_grid_pass1(p, S, first, count, d_logp, tilemax_ptr(p, S, first, count, d_work), d_best, d_work, st, &handled);
+        rc = pq_grid_pass1(p, S, first, count, d_logp, aux_ptr(p, S, first, count, d_work), d_best, d_work, st, &handled);
         if (rc || handled) return rc;
     }
     PQ_CUDA_OK(cudaMemsetAsync(d_work, 0, PQ_SWEEP_TICKET_BYTES, st));
@@ -480,7 +480,7 @@ extern "C" int peuqse_sweep_pass2(const peuqse_problem* p, const peuqse_sweep_sp
     cudaStream_t st = (cudaStream_t)stream;
     {
         bool handled = false;
-        rc = pq_grid_pass2(p, S, first, count, d_logp, tilemax_ptr(p, S, first, count, d_work), d_best, log_rel_threshold, d_acc,
+        rc = pq_grid_pass2(p, S, first, count, d_logp, aux_ptr(p, S, first, count, d_work), d_best, log_rel_threshold, d_acc,
                            (long long*)d_keep_index, d_keep_logp, keep_capacity, (long long*)d_keep_count, d_work, st, &handled);
         if (rc || handled) return rc;
     }
@@ -497,7 +497,8 @@ extern "C" int peuqse_sweep_pass2(const peuqse_problem* p, const peuqse_sweep_sp
 
 extern "C" int peuqse_sweep_hist(const peuqse_problem* p, const peuqse_sweep_spec* spec, int64_t first, int64_t count,
                                  const double* d_logp, const peuqse_best* d_best, double log_rel_threshold,
-                                 const double* d_edges, int32_t nbins, uint64_t* d_hist, void* d_work, void* stream) {
+                                 const double* d_edges, int32_t nbins, uint64_t* d_hist, void* d_work,
+                                 int32_t reuse_pass2_sums, void* stream) {
     int rc = check_sweep_args(p, spec, first, count);
     if (rc) return rc;
     if (!d_edges || !d_hist || !d_best || nbins < 1 || nbins > 4096) return pq_set_error(PEUQSE_ERR_INVALID, "bad histogram arguments");
@@ -510,8 +511,8 @@ extern "C" int peuqse_sweep_hist(const peuqse_problem* p, const peuqse_sweep_spe
     cudaStream_t st = (cudaStream_t)stream;
     {
         bool handled = false;
-        rc = pq_grid_hist(p, S, first, count, d_logp, d_work ? tilemax_ptr(p, S, first, count, d_work) : nullptr, d_best,
-                          log_rel_threshold, d_edges, nbins, (unsigned long long*)d_hist, st, &handled);
+        rc = pq_grid_hist(p, S, first, count, d_logp, aux_ptr(p, S, first, count, d_work), d_best, log_rel_threshold, d_edges,
+                          nbins, (unsigned long long*)d_hist, st, &handled, reuse_pass2_sums != 0);
         if (rc || handled) return rc;
     }
     if (count == 0) return PEUQSE_OK;

@@ -1,16 +1,19 @@
 // Specialised grid-sweep kernels (the C2 hot path): the bulk of combinationGenerator's list
 // (CombinationGeneratorModule.py:40-81) is, for the last axis L with radius r, the set
 //     g = M_L + b*2r + j,   b = index of a lower-axes combination (a "row"),  j in [0, 2r)
-// so consecutive g walk along the last axis.  A CTA owns a fixed chunk of j's and strides over rows:
+// so consecutive g walk along the last axis.
+// pass 1: a CTA owns a fixed chunk of j's and strides over rows.
 //   - every thread keeps its last-axis values theta_L(j) and their prior terms (incl. the fp64 division of
-//     IP.py:2767) in registers for the whole kernel,
-//   - the lower-axis point, its prior terms and every model sub-expression that depends on it are
-//     block-uniform per row and are computed once per row (the 8 unrolled, branch-free evaluations share them),
-//   - per point only the last-axis part of the model, the residuals and the two reductions remain;
-//     stores / loads of logP are fully coalesced along the row,
-//   - pass 1 also records the maximum of every warp tile (8 x 32 points); passes 2 and 3 skip tiles whose
-//     maximum is below the retention threshold, so they read only the retained region of the logP array.
-// The slab g < M_L (last axis at its centre, a lower-dimensional grid) is handled per point at the end.
+//     IP.py:2767) in registers for the whole kernel;
+//   - everything that depends only on a row (lower-axis decode, its prior terms, the model's row part, e.g.
+//     (x_j - a)^2) is computed ONCE per row per CTA into a shared-memory record and broadcast-read;
+//   - per point remain the last-axis part of the model, residuals and the two reductions (~20 fp64 ops);
+//     logP stores are coalesced; the maximum of each warp tile (8 x 32 points) is kept as a rounded-up float.
+// pass 2: tiles are visited in flat order with a stride coprime to the number of chunks (even load for a compact
+//   retained region); tiles whose maximum is below the threshold are skipped without touching logP; besides the
+//   moments it accumulates per-row and per-column weight sums, from which a tiny kernel bins the marginal
+//   histograms (pass 3) without reading logP again.
+// The slab g < M_L (last axis at its centre, a lower-dimensional grid) is handled per point.
 // Same arithmetic and summation order as the generic kernels (sweep.cu / eval.cuh): logP is bit-identical.
 #include "common.cuh"
 #include "eval.cuh"
@@ -31,6 +34,14 @@ struct GridTiling {
     int nchunks, nrg;      // chunks along j, row groups
 };
 
+// auxiliary arrays inside d_work (after the base area)
+struct GridAux {
+    unsigned int* tilemax;   // [ntiles * GR_WARPS] order-preserving keys of float upper bounds
+    double* colsum;          // [r2]   sum of weights per last-axis position
+    double* rowsum;          // [rows] sum of weights per row
+    int* valid;              // rowsum/colsum hold the sums of the last pass 2
+};
+
 __device__ __forceinline__ double last_axis_value(const DevSweep& S, int L, long long j) {
     const double step = S.interval[L] * (double)((j >> 1) + 1LL);          // (BaseFactor*i), CombinationGeneratorModule.py:59,71
     return (j & 1LL) ? (S.center[L] + step) : (S.center[L] - step);
@@ -41,8 +52,14 @@ __device__ __forceinline__ bool pq_isnan_bits(double x) {                   // i
     return hi > 0x7ff00000u || (hi == 0x7ff00000u && __double2loint(x) != 0);
 }
 
-__device__ __forceinline__ size_t tile_index(const GridTiling& T, long long b, int chunk, int warp) {
-    return ((size_t)(b - T.b_lo) * T.nchunks + chunk) * GR_WARPS + warp;
+// float upper bound of a double as an order-preserving unsigned key (larger value <=> larger key)
+__device__ __forceinline__ unsigned int up_key(double v) {
+    const unsigned int u = __float_as_uint(__double2float_ru(v));
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ double key_value(unsigned int k) {
+    const unsigned int u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    return (double)__uint_as_float(u);
 }
 
 // block-level merge of per-thread bests into *best_out
@@ -80,7 +97,7 @@ __device__ __forceinline__ void block_store_best(Best best, Best* s_best, bool* 
     }
 }
 
-// logLikelihood with the NaN test on the integer pipe
+// logLikelihood of a full point with the NaN test on the integer pipe (slab points)
 template <int MODEL, int KT, int NT, bool EXACT>
 __device__ __forceinline__ double grid_loglik(const DevProblem& P, const double (&th)[KT]) {
     double q[NT];
@@ -93,14 +110,24 @@ __device__ __forceinline__ double grid_loglik(const DevProblem& P, const double 
 // ---------------------------------------------------------------------------------------------
 // pass 1
 //   SIMPLE: every parameter has a Gaussian prior term, whitening in natural order, k < 8 -> the prior sum is
-//   ((q_0 + q_1) + ...) + q_L with the lower-axis partial sum hoisted per row.
+//   ((q_0 + q_1) + ...) + q_L with the lower-axis partial sum taken from the row record.
+//   row record (doubles): [0] ok flag, [1] plow, [2 .. 2+KT-2] qn of the lower axes, then pre[NT]
 // ---------------------------------------------------------------------------------------------
+template <int KT, int NT>
+struct RowRec {
+    static constexpr int QN = 2;
+    static constexpr int PRE = 2 + (KT - 1);
+    static constexpr int N = ((2 + (KT - 1) + NT) + 1) & ~1;       // even: 16-byte aligned records
+};
+
 template <int MODEL, int KT, int NT, bool EXACT, bool SIMPLE, bool STORE>
-__global__ void __launch_bounds__(GR_THREADS) k_grid_pass1(const __grid_constant__ DevProblem P, const __grid_constant__ DevSweep S,
+__global__ void __launch_bounds__(GR_THREADS, 3) k_grid_pass1(const __grid_constant__ DevProblem P, const __grid_constant__ DevSweep S,
                                                            const __grid_constant__ GridTiling T, long long first, long long count,
-                                                           double* __restrict__ logp_out, double* __restrict__ tilemax,
+                                                           double* __restrict__ logp_out, unsigned int* __restrict__ tilemax,
                                                            peuqse_best* __restrict__ best_out, Best* __restrict__ partial,
                                                            unsigned int* __restrict__ ticket) {
+    using R = RowRec<KT, NT>;
+    __shared__ __align__(16) double s_rec[GR_THREADS * R::N];
     __shared__ Best s_best[GR_WARPS];
     __shared__ bool s_last;
     constexpr int L = KT - 1;
@@ -108,6 +135,7 @@ __global__ void __launch_bounds__(GR_THREADS) k_grid_pass1(const __grid_constant
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long j0 = (long long)chunk * GR_CH + threadIdx.x;
     const long long last = first + count;
+    const bool full_chunk = (long long)(chunk + 1) * GR_CH <= T.r2;     // every j of this chunk exists (block-uniform)
     double thL[GR_JPT], qL[GR_JPT];
     bool okL[GR_JPT], jv[GR_JPT];
 #pragma unroll
@@ -118,51 +146,85 @@ __global__ void __launch_bounds__(GR_THREADS) k_grid_pass1(const __grid_constant
         jv[m] = j < T.r2;
     }
     Best best = best_none();
-    for (long long b = T.b_lo + rg; b < T.b_hi; b += T.nrg) {
-        double th[KT], qn[KT];
-        grid_point<KT>(S, (unsigned long long)b, th, L);          // lower axes of this row (block-uniform)
-        bool ok_low = true;
-        double plow = 0.0;
+    const long long nrows_blk = (T.b_hi - T.b_lo - rg + T.nrg - 1) / T.nrg;     // rows b_lo+rg, +nrg, ...
+    for (long long t0 = 0; t0 < nrows_blk; t0 += GR_THREADS) {
+        __syncthreads();
+        if (t0 + threadIdx.x < nrows_blk) {                          // stage: one row record per thread
+            const long long b = T.b_lo + rg + (t0 + threadIdx.x) * T.nrg;
+            double th[KT];
+            grid_point<KT>(S, (unsigned long long)b, th, L);          // lower axes of this row
+            double* rec = s_rec + threadIdx.x * R::N;
+            bool ok_low = true;
+            double plow = 0.0;
 #pragma unroll
-        for (int d = 0; d < KT; ++d) {
-            qn[d] = 0.0;
-            if (d < L) {
+            for (int d = 0; d < L; ++d) {
                 bool okd;
-                prior_axis(P, d, th[d], okd, qn[d]);
+                double q;
+                prior_axis(P, d, th[d], okd, q);
                 ok_low = ok_low && okd;
-                plow = (d == 0) ? qn[0] : (plow + qn[d]);         // numpy order for < 8 terms: sequential from the first
+                plow = (d == 0) ? q : (plow + q);                     // numpy order for < 8 terms: sequential from the first
+                rec[R::QN + d] = q;
             }
+            rec[0] = ok_low ? 1.0 : 0.0;
+            rec[1] = plow;
+            FastRowPre<MODEL, KT, NT, 0>::fill(P, th, rec + R::PRE);
         }
-        const long long gbase = T.ML + b * T.r2 + j0;
-        const bool inside = (T.ML + b * T.r2 >= first) && (T.ML + (b + 1) * T.r2 <= last);   // whole row in range
-        double rowmax = pq_neg_inf();
-        int rowm = 0;
+        __syncthreads();
+        const int nr = (int)((nrows_blk - t0 < GR_THREADS) ? (nrows_blk - t0) : GR_THREADS);
+        for (int tt = 0; tt < nr; ++tt) {
+            const double* rec = s_rec + tt * R::N;                    // broadcast reads
+            const long long b = T.b_lo + rg + (t0 + tt) * T.nrg;
+            const bool ok_low = rec[0] != 0.0;
+            const double plow = rec[1];
+            double pre[NT], qn[KT];
 #pragma unroll
-        for (int m = 0; m < GR_JPT; ++m) {
-            th[L] = thL[m];
-            double lp;
-            if (SIMPLE) {
-                const double maha = (KT == 1) ? qL[m] : (plow + qL[m]);
-                lp = -0.5 * (P.prior_c + maha);                      // _multivariate.py:591
-            } else {
-                qn[L] = qL[m];
-                lp = prior_combine<KT>(P, true, qn);
-            }
-            const double ll = grid_loglik<MODEL, KT, NT, EXACT>(P, th);
-            const double v = (ok_low && okL[m]) ? (ll + lp) : pq_neg_inf();   // IP.py:1649-1653
-            const long long g = gbase + m * GR_THREADS;
-            const bool valid = jv[m] && (inside || (g >= first && g < last));
-            if (valid) {
-                if (STORE) __stcs(logp_out + (g - first), v);
-                if (v > rowmax) { rowmax = v; rowm = m; }          // strict '>', increasing g within the row
-            }
-        }
-        if (rowmax > best.v) { best.v = rowmax; best.i = gbase + rowm * GR_THREADS; }   // rows in increasing g
-        if (STORE) {
-            double wm = rowmax;
+            for (int j = 0; j < NT; ++j) pre[j] = rec[R::PRE + j];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) wm = fmax(wm, __shfl_xor_sync(0xffffffffu, wm, o));
-            if (lane == 0) tilemax[tile_index(T, b, chunk, warp)] = wm;
+            for (int d = 0; d < KT; ++d) qn[d] = (d < L) ? rec[R::QN + (d < L ? d : 0)] : 0.0;
+            const long long row0 = T.ML + b * T.r2;
+            const long long gbase = row0 + j0;
+            const bool inside = (row0 >= first) && (row0 + T.r2 <= last);   // whole row in range (block-uniform)
+            double v[GR_JPT];
+#pragma unroll
+            for (int m = 0; m < GR_JPT; ++m) {                        // branch-free evaluation of the thread's 8 points
+                double lp;
+                if (SIMPLE) {
+                    const double maha = (KT == 1) ? qL[m] : (plow + qL[m]);
+                    lp = -0.5 * (P.prior_c + maha);                    // _multivariate.py:591
+                } else {
+                    qn[L] = qL[m];
+                    lp = prior_combine<KT>(P, true, qn);
+                }
+                double q[NT];
+                FastQLast<MODEL, KT, NT, EXACT, 0>::fill(P, pre, thL[m], q);
+                const double maha_l = ordered_sum_static<NT>(EXACT ? NT : P.fast_n, q);
+                double ll = -0.5 * (P.resp_c[0] + maha_l);
+                if (pq_isnan_bits(ll)) ll = pq_neg_inf();              // IP.py:2880-2882
+                v[m] = (ok_low && okL[m]) ? (ll + lp) : pq_neg_inf();  // IP.py:1649-1653
+            }
+            double rowmax = pq_neg_inf();
+            int rowm = 0;
+            if (inside && full_chunk) {
+#pragma unroll
+                for (int m = 0; m < GR_JPT; ++m) {
+                    if (STORE) __stcs(logp_out + (gbase + m * GR_THREADS - first), v[m]);
+                    if (v[m] > rowmax) { rowmax = v[m]; rowm = m; }    // strict '>', increasing g within the row
+                }
+            } else {                                                  // ragged chunk or first / last row of a rank's range
+#pragma unroll
+                for (int m = 0; m < GR_JPT; ++m) {
+                    const long long g = gbase + m * GR_THREADS;
+                    if (jv[m] && g >= first && g < last) {
+                        if (STORE) __stcs(logp_out + (g - first), v[m]);
+                        if (v[m] > rowmax) { rowmax = v[m]; rowm = m; }
+                    }
+                }
+            }
+            if (rowmax > best.v) { best.v = rowmax; best.i = gbase + rowm * GR_THREADS; }   // rows in increasing g
+            if (STORE) {
+                const unsigned int key = __reduce_max_sync(0xffffffffu, up_key(rowmax));
+                if (lane == 0) tilemax[((size_t)(b - T.b_lo) * T.nchunks + chunk) * GR_WARPS + warp] = key;
+            }
         }
     }
     // slab: last axis at its centre (indices below M_L), per-point decode
@@ -187,7 +249,7 @@ __global__ void __launch_bounds__(GR_THREADS) k_grid_pass1(const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------------------
-// pass 2 (logP read back from HBM, only tiles that hold retained points)
+// pass 2 (logP read back from HBM, only tiles that hold retained points) + histogram weight sums
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double blk_sum(double v, double* s_red) {
     v = warp_sum(v);
@@ -218,19 +280,21 @@ __device__ __forceinline__ double blk_min(double v, double* s_red) {
 
 template <int KT>
 struct GridAcc {
-    double w, wexp, nk;
+    double w, wr, nk;           // sum w, sum w*exp(logP - thr), retained points
     double s1[KT], s2[KT * (KT + 1) / 2], mn[KT], mx[KT];
     __device__ __forceinline__ void init() {
-        w = wexp = nk = 0.0;
+        w = wr = nk = 0.0;
 #pragma unroll
         for (int d = 0; d < KT; ++d) { s1[d] = 0.0; mn[d] = pq_pos_inf(); mx[d] = pq_neg_inf(); }
 #pragma unroll
         for (int e = 0; e < KT * (KT + 1) / 2; ++e) s2[e] = 0.0;
     }
-    __device__ __forceinline__ void add(double v, double thr, const double (&th)[KT], const double (&shift)[KT]) {
-        const double wt = trunc(exp(v - thr));                      // int(np.exp(...)), IP.py:3485-3486
+    // generic (slab) path
+    __device__ __forceinline__ double add(double v, double thr, const double (&th)[KT], const double (&shift)[KT]) {
+        const double reps = exp(v - thr);                           // np.exp(...), IP.py:3485
+        const double wt = trunc(reps);                              // int(...), IP.py:3486
         w += wt;
-        wexp = fma(wt, exp(v), wexp);
+        wr = fma(wt, reps, wr);                                     // sum w*exp(logP) = exp(thr) * sum w*reps
         nk += 1.0;
         int e = 0;
 #pragma unroll
@@ -242,18 +306,25 @@ struct GridAcc {
             mn[d] = fmin(mn[d], th[d]);
             mx[d] = fmax(mx[d], th[d]);
         }
+        return wt;
     }
 };
 
-template <int KT>
-__global__ void __launch_bounds__(GR_THREADS) k_grid_pass2(const __grid_constant__ DevSweep S, const __grid_constant__ GridTiling T,
-                                                           long long first, long long count, const double* __restrict__ logp_in,
-                                                           const double* __restrict__ tilemax,
-                                                           const peuqse_best* __restrict__ best_in, double log_rel,
-                                                           double* __restrict__ partial, double* __restrict__ acc_out,
-                                                           unsigned int* __restrict__ ticket, long long* __restrict__ keep_idx,
-                                                           double* __restrict__ keep_logp, long long keep_cap,
-                                                           unsigned long long* __restrict__ keep_count) {
+// index of (d, d2>=d) in the packed upper triangle
+__host__ __device__ constexpr int tri_index(int KT, int d, int d2) { return d * KT - d * (d - 1) / 2 + (d2 - d); }
+
+template <int KT, bool FUSE>
+__global__ void __launch_bounds__(GR_THREADS, FUSE ? 2 : 3) k_grid_pass2(const __grid_constant__ DevSweep S,
+                                                                         const __grid_constant__ GridTiling T, long long first,
+                                                                         long long count, const double* __restrict__ logp_in,
+                                                                         const GridAux aux,
+                                                                         const peuqse_best* __restrict__ best_in, double log_rel,
+                                                                         double* __restrict__ partial, double* __restrict__ acc_out,
+                                                                         unsigned int* __restrict__ ticket,
+                                                                         long long* __restrict__ keep_idx,
+                                                                         double* __restrict__ keep_logp, long long keep_cap,
+                                                                         unsigned long long* __restrict__ keep_count) {
+    extern __shared__ double s_col[];                               // FUSE: column sums of this CTA, nchunks*GR_CH doubles
     __shared__ double s_red[GR_WARPS];
     __shared__ bool s_last;
     constexpr int L = KT - 1;
@@ -262,38 +333,81 @@ __global__ void __launch_bounds__(GR_THREADS) k_grid_pass2(const __grid_constant
     const double thr = none ? pq_pos_inf() : best_in->logp + log_rel;   // IP.py:3477
     double shift[KT];
     grid_point<KT>(S, (unsigned long long)(none ? 0 : best_index), shift, KT);   // moments about the MAP point
-    const int chunk = blockIdx.x % T.nchunks, rg = blockIdx.x / T.nchunks;
-    const int warp = threadIdx.x >> 5;
-    const long long j0 = (long long)chunk * GR_CH + threadIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long last = first + count;
-    double thL[GR_JPT];
-#pragma unroll
-    for (int m = 0; m < GR_JPT; ++m) thL[m] = last_axis_value(S, L, j0 + m * GR_THREADS);
+    const long long ntiles = (T.b_hi - T.b_lo) * T.nchunks;
+    if (FUSE) {
+        for (int a = threadIdx.x; a < T.nchunks * GR_CH; a += blockDim.x) s_col[a] = 0.0;
+        __syncthreads();
+    }
     GridAcc<KT> A;
     A.init();
-    for (long long b = T.b_lo + rg; b < T.b_hi && !none; b += T.nrg) {
-        if (!(__ldg(tilemax + tile_index(T, b, chunk, warp)) > thr)) continue;     // nothing retained in this warp tile
-        const long long gbase = T.ML + b * T.r2 + j0;
-        double v[GR_JPT];
+    long long t = blockIdx.x;
+    unsigned int tk = (t < ntiles && !none) ? __ldg(aux.tilemax + (size_t)t * GR_WARPS + warp) : 0u;
+    for (; t < ntiles && !none; t += gridDim.x) {
+        const long long tn = t + gridDim.x;
+        const unsigned int tk_next = (tn < ntiles) ? __ldg(aux.tilemax + (size_t)tn * GR_WARPS + warp) : 0u;   // prefetch
+        if (key_value(tk) > thr) {                                   // something may be retained in this warp tile
+            const long long row = t / T.nchunks;
+            const long long b = T.b_lo + row;
+            const int chunk = (int)(t - row * T.nchunks);
+            const int jt = chunk * GR_CH + threadIdx.x;
+            const long long gbase = T.ML + b * T.r2 + jt;
+            double v[GR_JPT];
 #pragma unroll
-        for (int m = 0; m < GR_JPT; ++m) {                          // all loads of the row first (memory-level parallelism)
-            const long long g = gbase + m * GR_THREADS;
-            v[m] = pq_neg_inf();
-            if (j0 + m * GR_THREADS < T.r2 && g >= first && g < last) v[m] = __ldcs(logp_in + (g - first));
-        }
-        double th[KT];
-        grid_point<KT>(S, (unsigned long long)b, th, L);
+            for (int m = 0; m < GR_JPT; ++m) {                      // all loads first (memory-level parallelism)
+                const long long g = gbase + m * GR_THREADS;
+                v[m] = pq_neg_inf();
+                if (jt + m * GR_THREADS < T.r2 && g >= first && g < last) v[m] = __ldcs(logp_in + (g - first));
+            }
+            double roww = 0.0, rowwL = 0.0;                          // sum_m w, sum_m w*(theta_L - shift_L)
 #pragma unroll
-        for (int m = 0; m < GR_JPT; ++m) {
-            if (v[m] > thr) {                                       // IP.py:3481
-                th[L] = thL[m];
-                A.add(v[m], thr, th, shift);
-                if (keep_idx) {
-                    const unsigned long long slot = atomicAdd(keep_count, 1ULL);
-                    if ((long long)slot < keep_cap) { keep_idx[slot] = gbase + m * GR_THREADS; keep_logp[slot] = v[m]; }
+            for (int m = 0; m < GR_JPT; ++m) {
+                if (v[m] > thr) {                                   // IP.py:3481
+                    const double reps = exp(v[m] - thr);            // IP.py:3485
+                    const double wt = trunc(reps);                  // IP.py:3486
+                    const double thl = last_axis_value(S, L, jt + m * GR_THREADS);
+                    const double dl = thl - shift[L];
+                    const double wdl = wt * dl;
+                    A.wr = fma(wt, reps, A.wr);
+                    A.nk += 1.0;
+                    roww += wt;
+                    rowwL += wdl;
+                    A.s2[tri_index(KT, L, L)] = fma(wdl, dl, A.s2[tri_index(KT, L, L)]);
+                    A.mn[L] = fmin(A.mn[L], thl);
+                    A.mx[L] = fmax(A.mx[L], thl);
+                    if (FUSE) s_col[jt + m * GR_THREADS] += wt;      // position j of a row always belongs to this thread
+                    if (keep_idx) {
+                        const unsigned long long slot = atomicAdd(keep_count, 1ULL);
+                        if ((long long)slot < keep_cap) { keep_idx[slot] = gbase + m * GR_THREADS; keep_logp[slot] = v[m]; }
+                    }
                 }
             }
+            if (roww > 0.0) {                                        // row part of the moments, once per row
+                A.w += roww;
+                A.s1[L] += rowwL;
+                if (KT > 1) {
+                    double th[KT];
+                    grid_point<KT>(S, (unsigned long long)b, th, L);
+#pragma unroll
+                    for (int d = 0; d < L; ++d) {
+                        const double dd = th[d] - shift[d];
+                        const double wd = roww * dd;
+                        A.s1[d] += wd;
+#pragma unroll
+                        for (int d2 = d; d2 < L; ++d2) A.s2[tri_index(KT, d, d2)] = fma(wd, th[d2] - shift[d2], A.s2[tri_index(KT, d, d2)]);
+                        A.s2[tri_index(KT, d, L)] = fma(dd, rowwL, A.s2[tri_index(KT, d, L)]);
+                        A.mn[d] = fmin(A.mn[d], th[d]);
+                        A.mx[d] = fmax(A.mx[d], th[d]);
+                    }
+                }
+            }
+            if (FUSE && KT > 1) {
+                const double rw = warp_sum(roww);                    // integers < 2^53: exact in fp64
+                if (lane == 0 && rw > 0.0) atomicAdd(aux.rowsum + row, rw);
+            }
         }
+        tk = tk_next;
     }
     for (long long g = T.slab_first + (long long)blockIdx.x * GR_THREADS + threadIdx.x; g < T.slab_first + T.slab_count && !none;
          g += (long long)gridDim.x * GR_THREADS) {
@@ -308,53 +422,61 @@ __global__ void __launch_bounds__(GR_THREADS) k_grid_pass2(const __grid_constant
             }
         }
     }
+    if (FUSE) {
+        __syncthreads();
+        for (long long j = threadIdx.x; j < T.r2; j += blockDim.x) {
+            const double cw = s_col[j];
+            if (cw > 0.0) atomicAdd(aux.colsum + j, cw);
+        }
+    }
     double* mine = partial + (size_t)blockIdx.x * PQ_ACC_MAX;
-    double t;
-    t = blk_sum(A.w, s_red);    if (threadIdx.x == 0) mine[PEUQSE_ACC_W] = t;
-    t = blk_sum(A.wexp, s_red); if (threadIdx.x == 0) mine[PEUQSE_ACC_WEXP] = t;
-    t = blk_sum(A.nk, s_red);   if (threadIdx.x == 0) mine[PEUQSE_ACC_NKEPT] = t;
+    double r;
+    r = blk_sum(A.w, s_red);  if (threadIdx.x == 0) mine[PEUQSE_ACC_W] = r;
+    r = blk_sum(A.wr, s_red); if (threadIdx.x == 0) mine[PEUQSE_ACC_WEXP] = none ? 0.0 : r * exp(thr);
+    r = blk_sum(A.nk, s_red); if (threadIdx.x == 0) mine[PEUQSE_ACC_NKEPT] = r;
     {
         int e = 0;
 #pragma unroll
         for (int d = 0; d < KT; ++d) {
-            t = blk_sum(A.s1[d], s_red);   if (threadIdx.x == 0) mine[PEUQSE_ACC_S1 + d] = t;
-            t = blk_min(A.mn[d], s_red);   if (threadIdx.x == 0) mine[PEUQSE_ACC_MIN(KT) + d] = t;
-            t = -blk_min(-A.mx[d], s_red); if (threadIdx.x == 0) mine[PEUQSE_ACC_MAX(KT) + d] = t;
+            r = blk_sum(A.s1[d], s_red);   if (threadIdx.x == 0) mine[PEUQSE_ACC_S1 + d] = r;
+            r = blk_min(A.mn[d], s_red);   if (threadIdx.x == 0) mine[PEUQSE_ACC_MIN(KT) + d] = r;
+            r = -blk_min(-A.mx[d], s_red); if (threadIdx.x == 0) mine[PEUQSE_ACC_MAX(KT) + d] = r;
 #pragma unroll
             for (int d2 = d; d2 < KT; ++d2) {
-                t = blk_sum(A.s2[e], s_red);
-                if (threadIdx.x == 0) { mine[PEUQSE_ACC_S2(KT) + d * KT + d2] = t; mine[PEUQSE_ACC_S2(KT) + d2 * KT + d] = t; }
+                r = blk_sum(A.s2[e], s_red);
+                if (threadIdx.x == 0) { mine[PEUQSE_ACC_S2(KT) + d * KT + d2] = r; mine[PEUQSE_ACC_S2(KT) + d2 * KT + d] = r; }
                 ++e;
             }
         }
     }
     if (threadIdx.x == 0) {
         __threadfence();
-        const unsigned int tk = atomicAdd(ticket, 1u);
-        s_last = (tk == gridDim.x - 1);
+        const unsigned int tkt = atomicAdd(ticket, 1u);
+        s_last = (tkt == gridDim.x - 1);
     }
     __syncthreads();
     if (s_last) {
         __threadfence();
         constexpr int nacc = PEUQSE_ACC_DOUBLES(KT), mn0 = PEUQSE_ACC_MIN(KT), mx0 = PEUQSE_ACC_MAX(KT);
         for (int a = threadIdx.x; a < nacc; a += blockDim.x) {
-            double r = acc_out[a];
-            for (int b = 0; b < (int)gridDim.x; ++b) {             // fixed block order: deterministic
-                const double x = __ldcg(partial + (size_t)b * PQ_ACC_MAX + a);
-                if (a >= mx0) r = fmax(r, x);
-                else if (a >= mn0) r = fmin(r, x);
-                else r += x;
+            double rr = acc_out[a];
+            for (int bb = 0; bb < (int)gridDim.x; ++bb) {          // fixed block order: deterministic
+                const double x = __ldcg(partial + (size_t)bb * PQ_ACC_MAX + a);
+                if (a >= mx0) rr = fmax(rr, x);
+                else if (a >= mn0) rr = fmin(rr, x);
+                else rr += x;
             }
-            acc_out[a] = r;
+            acc_out[a] = rr;
         }
-        if (threadIdx.x == 0) *ticket = 0;
+        if (threadIdx.x == 0) {
+            *ticket = 0;
+            if (FUSE) *aux.valid = 1;
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// pass 3: marginal histograms without per-point atomics
-//   lower axes: the bin is uniform per row -> one shared-memory atomic per warp per row;
-//   last axis:  every thread owns fixed j's -> private column sums in registers, binned once at the end.
+// pass 3
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int hist_bin(const double* __restrict__ ed, int nbins, double x) {
     const double lo = ed[0], hi = ed[nbins];
@@ -367,47 +489,103 @@ __device__ __forceinline__ int hist_bin(const double* __restrict__ ed, int nbins
     return b;
 }
 
+// (a) bins the row / column weight sums left by the fused pass 2 (and clears them); reads only the slab of logP
 template <int KT>
-__global__ void __launch_bounds__(GR_THREADS) k_grid_hist(const __grid_constant__ DevSweep S, const __grid_constant__ GridTiling T,
-                                                          long long first, long long count, const double* __restrict__ logp_in,
-                                                          const double* __restrict__ tilemax,
-                                                          const peuqse_best* __restrict__ best_in, double log_rel,
-                                                          const double* __restrict__ edges, int nbins,
-                                                          unsigned long long* __restrict__ hist) {
+__global__ void __launch_bounds__(GR_THREADS) k_grid_bin(const __grid_constant__ DevSweep S, const __grid_constant__ GridTiling T,
+                                                         long long first, const double* __restrict__ logp_in, const GridAux aux,
+                                                         const peuqse_best* __restrict__ best_in, double log_rel,
+                                                         const double* __restrict__ edges, int nbins,
+                                                         unsigned long long* __restrict__ hist) {
     extern __shared__ unsigned long long sh[];                      // [KT][nbins]
     constexpr int L = KT - 1;
     if (best_in->index < 0) return;
     const double thr = best_in->logp + log_rel;
     for (int a = threadIdx.x; a < KT * nbins; a += blockDim.x) sh[a] = 0ULL;
     __syncthreads();
-    const int chunk = blockIdx.x % T.nchunks, rg = blockIdx.x / T.nchunks;
-    const int warp = threadIdx.x >> 5;
-    const long long j0 = (long long)chunk * GR_CH + threadIdx.x;
-    const long long last = first + count;
-    double colw[GR_JPT];
+    const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long j = t0; j < T.r2; j += stride) {
+        const double cw = aux.colsum[j];
+        if (cw > 0.0) {
+            const int bin = hist_bin(edges + L * (nbins + 1), nbins, last_axis_value(S, L, j));
+            if (bin >= 0) atomicAdd(sh + L * nbins + bin, (unsigned long long)cw);
+        }
+    }
+    if (KT > 1) {
+        for (long long row = t0; row < T.b_hi - T.b_lo; row += stride) {
+            const double rw = aux.rowsum[row];
+            if (rw > 0.0) {
+                double th[KT];
+                grid_point<KT>(S, (unsigned long long)(T.b_lo + row), th, L);
 #pragma unroll
-    for (int m = 0; m < GR_JPT; ++m) colw[m] = 0.0;
-    for (long long b = T.b_lo + rg; b < T.b_hi; b += T.nrg) {
-        if (!(__ldg(tilemax + tile_index(T, b, chunk, warp)) > thr)) continue;
-        const long long gbase = T.ML + b * T.r2 + j0;
+                for (int d = 0; d < L; ++d) {
+                    const int bin = hist_bin(edges + d * (nbins + 1), nbins, th[d]);
+                    if (bin >= 0) atomicAdd(sh + d * nbins + bin, (unsigned long long)rw);
+                }
+            }
+        }
+    }
+    for (long long g = T.slab_first + t0; g < T.slab_first + T.slab_count; g += stride) {
+        const double v = __ldcs(logp_in + (g - first));
+        if (v > thr) {
+            const unsigned long long w = (unsigned long long)trunc(exp(v - thr));
+            double th[KT];
+            grid_point<KT>(S, (unsigned long long)g, th, KT);
+#pragma unroll
+            for (int d = 0; d < KT; ++d) {
+                const int bin = hist_bin(edges + d * (nbins + 1), nbins, th[d]);
+                if (bin >= 0) atomicAdd(sh + d * nbins + bin, w);
+            }
+        }
+    }
+    __syncthreads();
+    for (int a = threadIdx.x; a < KT * nbins; a += blockDim.x)
+        if (sh[a]) atomicAdd(hist + a, sh[a]);
+}
+
+// (b) stand-alone version (no fused sums available): reads the retained tiles of logP again
+template <int KT>
+__global__ void __launch_bounds__(GR_THREADS) k_grid_hist(const __grid_constant__ DevSweep S, const __grid_constant__ GridTiling T,
+                                                          long long first, long long count, const double* __restrict__ logp_in,
+                                                          const GridAux aux, const peuqse_best* __restrict__ best_in,
+                                                          double log_rel, const double* __restrict__ edges, int nbins,
+                                                          unsigned long long* __restrict__ hist) {
+    extern __shared__ unsigned long long sh[];                      // [KT][nbins] bins, then colsum[nchunks*GR_CH] doubles
+    constexpr int L = KT - 1;
+    if (best_in->index < 0) return;
+    const double thr = best_in->logp + log_rel;
+    double* colsum = (double*)(sh + KT * nbins);
+    const int ncol = T.nchunks * GR_CH;
+    for (int a = threadIdx.x; a < KT * nbins; a += blockDim.x) sh[a] = 0ULL;
+    for (int a = threadIdx.x; a < ncol; a += blockDim.x) colsum[a] = 0.0;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5;
+    const long long last = first + count;
+    const long long ntiles = (T.b_hi - T.b_lo) * T.nchunks;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        if (!(key_value(__ldg(aux.tilemax + (size_t)t * GR_WARPS + warp)) > thr)) continue;
+        const long long row = t / T.nchunks;
+        const long long b = T.b_lo + row;
+        const int chunk = (int)(t - row * T.nchunks);
+        const int jt = chunk * GR_CH + threadIdx.x;
+        const long long gbase = T.ML + b * T.r2 + jt;
         double v[GR_JPT];
 #pragma unroll
         for (int m = 0; m < GR_JPT; ++m) {
             const long long g = gbase + m * GR_THREADS;
             v[m] = pq_neg_inf();
-            if (j0 + m * GR_THREADS < T.r2 && g >= first && g < last) v[m] = __ldcs(logp_in + (g - first));
+            if (jt + m * GR_THREADS < T.r2 && g >= first && g < last) v[m] = __ldcs(logp_in + (g - first));
         }
         double roww = 0.0;
 #pragma unroll
         for (int m = 0; m < GR_JPT; ++m) {
             if (v[m] > thr) {
                 const double w = trunc(exp(v[m] - thr));
-                colw[m] += w;
+                colsum[jt + m * GR_THREADS] += w;
                 roww += w;
             }
         }
         if (KT > 1) {
-            roww = warp_sum(roww);                                   // integers < 2^53: exact in fp64
+            roww = warp_sum(roww);
             if ((threadIdx.x & 31) == 0 && roww > 0.0) {
                 double th[KT];
                 grid_point<KT>(S, (unsigned long long)b, th, L);
@@ -419,11 +597,12 @@ __global__ void __launch_bounds__(GR_THREADS) k_grid_hist(const __grid_constant_
             }
         }
     }
-#pragma unroll
-    for (int m = 0; m < GR_JPT; ++m) {
-        if (colw[m] > 0.0) {
-            const int bin = hist_bin(edges + L * (nbins + 1), nbins, last_axis_value(S, L, j0 + m * GR_THREADS));
-            if (bin >= 0) atomicAdd(sh + L * nbins + bin, (unsigned long long)colw[m]);
+    __syncthreads();
+    for (long long j = threadIdx.x; j < T.r2; j += blockDim.x) {
+        const double cw = colsum[j];
+        if (cw > 0.0) {
+            const int bin = hist_bin(edges + L * (nbins + 1), nbins, last_axis_value(S, L, j));
+            if (bin >= 0) atomicAdd(sh + L * nbins + bin, (unsigned long long)cw);
         }
     }
     for (long long g = T.slab_first + (long long)blockIdx.x * GR_THREADS + threadIdx.x; g < T.slab_first + T.slab_count;
@@ -485,6 +664,18 @@ static int resident_blocks(const peuqse_problem* p, K kern, size_t smem) {
     return per_sm * p->sm_count;
 }
 
+static int gcd_int(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
+// number of CTAs for the flat tile loops: at most one resident wave, coprime to nchunks, not more than the tiles
+static int flat_grid(const GridTiling& T, int resident) {
+    long long ntiles = (T.b_hi - T.b_lo) * T.nchunks;
+    long long g = resident;
+    if (g > ntiles) g = ntiles;
+    if (g > PQ_SWEEP_MAX_BLOCKS) g = PQ_SWEEP_MAX_BLOCKS;
+    if (g < 1) g = 1;
+    while (g > 1 && gcd_int((int)g, T.nchunks) != 1) --g;
+    return (int)g;
+}
+
 static bool fast_model_ok(const peuqse_problem* p) {
     const DevProblem& d = p->d;
     if (d.fast_n <= 0) return false;
@@ -495,16 +686,35 @@ static bool fast_model_ok(const peuqse_problem* p) {
 
 static bool grid_k_ok(int k) { return k == 1 || k == 2 || k == 3 || k == 4 || k == 6; }
 
-// bytes of the tile-maximum array for this range (0 when the specialised kernels do not apply)
-long long pq_grid_aux_bytes(const peuqse_problem* p, const DevSweep& S, long long first, long long count) {
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// layout of the auxiliary arrays for this range; returns their total size (0 when the specialised kernels do not apply)
+static long long grid_aux_layout(const peuqse_problem* p, const DevSweep& S, long long first, long long count, char* base,
+                                 GridAux* aux) {
     GridTiling T;
     if (!p || !fast_model_ok(p) || !grid_k_ok(S.k) || !grid_tiling(p, S, first, count, 1, &T)) return 0;
-    return (long long)((T.b_hi - T.b_lo) * T.nchunks * GR_WARPS + 1) * (long long)sizeof(double);
+    const size_t rows = (size_t)(T.b_hi - T.b_lo);
+    size_t off = 0;
+    const size_t o_tile = off; off = align_up(off + (rows * T.nchunks * GR_WARPS + 1) * sizeof(unsigned int), 256);
+    const size_t o_col = off;  off = align_up(off + (size_t)(T.r2 + 1) * sizeof(double), 256);
+    const size_t o_row = off;  off = align_up(off + (rows + 1) * sizeof(double), 256);
+    const size_t o_val = off;  off += 256;
+    if (aux && base) {
+        aux->tilemax = (unsigned int*)(base + o_tile);
+        aux->colsum = (double*)(base + o_col);
+        aux->rowsum = (double*)(base + o_row);
+        aux->valid = (int*)(base + o_val);
+    }
+    return (long long)off;
+}
+
+long long pq_grid_aux_bytes(const peuqse_problem* p, const DevSweep& S, long long first, long long count) {
+    return grid_aux_layout(p, S, first, count, nullptr, nullptr);
 }
 
 template <int MODEL, int KT, int NT, bool EXACT>
 static int launch_grid_pass1(const peuqse_problem* p, const DevSweep& S, long long first, long long count, double* logp,
-                             double* tilemax, peuqse_best* best, void* work, cudaStream_t st) {
+                             unsigned int* tilemax, peuqse_best* best, void* work, cudaStream_t st) {
     const DevProblem& d = p->d;
     const bool simple = d.prior_mode == PEUQSE_PRIOR_DIAG && d.prior_identity && d.kp == d.k && KT < 8;
     unsigned int* ticket = (unsigned int*)work;
@@ -527,45 +737,67 @@ static int launch_grid_pass1(const peuqse_problem* p, const DevSweep& S, long lo
 }
 
 // *handled = true when the specialised kernel covered the whole range [first, first+count)
-int pq_grid_pass1(const peuqse_problem* p, const DevSweep& S, long long first, long long count, double* logp, double* tilemax,
+int pq_grid_pass1(const peuqse_problem* p, const DevSweep& S, long long first, long long count, double* logp, void* aux_base,
                   peuqse_best* best, void* work, cudaStream_t st, bool* handled) {
     *handled = false;
-    GridTiling T;
-    if (!fast_model_ok(p) || !grid_tiling(p, S, first, count, 1, &T)) return PEUQSE_OK;
-    if (logp && !tilemax) return PEUQSE_OK;            // storing logP without the tile maxima: generic path
+    GridAux aux = {nullptr, nullptr, nullptr, nullptr};
+    if (!fast_model_ok(p) || grid_aux_layout(p, S, first, count, (char*)aux_base, &aux) == 0) return PEUQSE_OK;
+    if (logp && !aux_base) return PEUQSE_OK;           // storing logP without room for the tile maxima: generic path
     *handled = true;
     const int n = p->d.fast_n;
     if (p->d.model_id == PEUQSE_MODEL_QUADRATIC) {
         switch (n) {
-#define GQ(N) case N: return launch_grid_pass1<PEUQSE_MODEL_QUADRATIC, 2, N, true>(p, S, first, count, logp, tilemax, best, work, st);
+#define GQ(N) case N: return launch_grid_pass1<PEUQSE_MODEL_QUADRATIC, 2, N, true>(p, S, first, count, logp, aux.tilemax, best, work, st);
             GQ(1) GQ(2) GQ(3) GQ(4) GQ(5) GQ(6) GQ(7) GQ(8)
 #undef GQ
         }
     } else {
-#define GL(K)                                                                                                                    \
-    case K:                                                                                                                      \
-        return n <= 4 ? launch_grid_pass1<PEUQSE_MODEL_LINEAR, K, 4, false>(p, S, first, count, logp, tilemax, best, work, st)    \
-                      : launch_grid_pass1<PEUQSE_MODEL_LINEAR, K, 8, false>(p, S, first, count, logp, tilemax, best, work, st);
+#define GL(K)                                                                                                                       \
+    case K:                                                                                                                         \
+        return n <= 4 ? launch_grid_pass1<PEUQSE_MODEL_LINEAR, K, 4, false>(p, S, first, count, logp, aux.tilemax, best, work, st)    \
+                      : launch_grid_pass1<PEUQSE_MODEL_LINEAR, K, 8, false>(p, S, first, count, logp, aux.tilemax, best, work, st);
         switch (p->d.k) { GL(2) GL(3) GL(4) GL(6) }
 #undef GL
     }
     return pq_set_error(PEUQSE_ERR_INVALID, "grid fast path dispatch");
 }
 
+// whether pass 2 of this range runs fused (leaves row/column weight sums for the binning kernel)
+bool pq_grid_pass2_fuses(const peuqse_problem* p, const DevSweep& S, long long first, long long count) {
+    GridTiling T;
+    if (grid_aux_layout(p, S, first, count, nullptr, nullptr) == 0) return false;
+    grid_tiling(p, S, first, count, 1, &T);
+    return (size_t)T.nchunks * GR_CH * sizeof(double) + 1024 <= (size_t)p->max_smem_optin;
+}
+
 int pq_grid_pass2(const peuqse_problem* p, const DevSweep& S, long long first, long long count, const double* logp,
-                  const double* tilemax, const peuqse_best* best, double log_rel, double* acc, long long* kidx, double* klogp,
+                  void* aux_base, const peuqse_best* best, double log_rel, double* acc, long long* kidx, double* klogp,
                   long long kcap, long long* kcount, void* work, cudaStream_t st, bool* handled) {
     *handled = false;
+    GridAux aux = {nullptr, nullptr, nullptr, nullptr};
     GridTiling T;
-    if (!logp || !tilemax || !fast_model_ok(p) || !grid_k_ok(S.k) || !grid_tiling(p, S, first, count, 1, &T)) return PEUQSE_OK;
+    if (!logp || !aux_base || grid_aux_layout(p, S, first, count, (char*)aux_base, &aux) == 0) return PEUQSE_OK;
+    grid_tiling(p, S, first, count, 1, &T);
     *handled = true;
     unsigned int* ticket = (unsigned int*)work;
     double* partial = (double*)((char*)work + PQ_SWEEP_TICKET_BYTES);
+    const size_t smem = (size_t)T.nchunks * GR_CH * sizeof(double);
+    const bool fuse = pq_grid_pass2_fuses(p, S, first, count);
 #define G2(K)                                                                                                                    \
     case K: {                                                                                                                    \
-        grid_tiling(p, S, first, count, resident_blocks(p, k_grid_pass2<K>, 0), &T);                                             \
-        k_grid_pass2<K><<<T.nchunks * T.nrg, GR_THREADS, 0, st>>>(S, T, first, count, logp, tilemax, best, log_rel, partial, acc, \
-                                                                  ticket, kidx, klogp, kcap, (unsigned long long*)kcount);        \
+        if (fuse) {                                                                                                              \
+            cudaError_t e = cudaMemsetAsync(aux.colsum, 0, (size_t)((char*)aux.valid - (char*)aux.colsum), st);                   \
+            if (e != cudaSuccess) return pq_set_cuda_error(e, "cudaMemsetAsync", __LINE__);                                       \
+            e = pq_allow_smem((const void*)k_grid_pass2<K, true>, smem);                                                          \
+            if (e != cudaSuccess) return pq_set_cuda_error(e, "cudaFuncSetAttribute", __LINE__);                                  \
+            const int g = flat_grid(T, resident_blocks(p, k_grid_pass2<K, true>, smem));                                         \
+            k_grid_pass2<K, true><<<g, GR_THREADS, smem, st>>>(S, T, first, count, logp, aux, best, log_rel, partial, acc, ticket, \
+                                                               kidx, klogp, kcap, (unsigned long long*)kcount);                   \
+        } else {                                                                                                                 \
+            const int g = flat_grid(T, resident_blocks(p, k_grid_pass2<K, false>, 0));                                           \
+            k_grid_pass2<K, false><<<g, GR_THREADS, 0, st>>>(S, T, first, count, logp, aux, best, log_rel, partial, acc, ticket,   \
+                                                             kidx, klogp, kcap, (unsigned long long*)kcount);                     \
+        }                                                                                                                        \
     } break;
     switch (S.k) { G2(1) G2(2) G2(3) G2(4) G2(6) }
 #undef G2
@@ -573,19 +805,33 @@ int pq_grid_pass2(const peuqse_problem* p, const DevSweep& S, long long first, l
     return PEUQSE_OK;
 }
 
+// use_fused_sums: the caller ran pass 2 of the same range immediately before (row / column sums are in d_work)
 int pq_grid_hist(const peuqse_problem* p, const DevSweep& S, long long first, long long count, const double* logp,
-                 const double* tilemax, const peuqse_best* best, double log_rel, const double* edges, int nbins,
-                 unsigned long long* hist, cudaStream_t st, bool* handled) {
+                 void* aux_base, const peuqse_best* best, double log_rel, const double* edges, int nbins,
+                 unsigned long long* hist, cudaStream_t st, bool* handled, bool use_fused_sums) {
     *handled = false;
+    GridAux aux = {nullptr, nullptr, nullptr, nullptr};
     GridTiling T;
-    if (!logp || !tilemax || !fast_model_ok(p) || !grid_k_ok(S.k) || !grid_tiling(p, S, first, count, 1, &T)) return PEUQSE_OK;
+    if (!logp || !aux_base || grid_aux_layout(p, S, first, count, (char*)aux_base, &aux) == 0) return PEUQSE_OK;
+    grid_tiling(p, S, first, count, 1, &T);
+    const size_t smem_bins = (size_t)S.k * nbins * sizeof(unsigned long long);
+    if (use_fused_sums && pq_grid_pass2_fuses(p, S, first, count)) {
+        *handled = true;
+#define GB(K) case K: k_grid_bin<K><<<32, GR_THREADS, smem_bins, st>>>(S, T, first, logp, aux, best, log_rel, edges, nbins, hist); break;
+        switch (S.k) { GB(1) GB(2) GB(3) GB(4) GB(6) }
+#undef GB
+        PQ_CUDA_OK(cudaGetLastError());
+        return PEUQSE_OK;
+    }
+    const size_t smem = smem_bins + (size_t)T.nchunks * GR_CH * sizeof(double);
+    if (smem > (size_t)p->max_smem_optin) return PEUQSE_OK;                           // last axis too long: generic kernel
     *handled = true;
-    const size_t smem = (size_t)S.k * nbins * sizeof(unsigned long long);
 #define G3(K)                                                                                                                    \
     case K: {                                                                                                                    \
-        grid_tiling(p, S, first, count, resident_blocks(p, k_grid_hist<K>, smem), &T);                                           \
-        k_grid_hist<K><<<T.nchunks * T.nrg, GR_THREADS, smem, st>>>(S, T, first, count, logp, tilemax, best, log_rel, edges,      \
-                                                                    nbins, hist);                                                 \
+        cudaError_t e = pq_allow_smem((const void*)k_grid_hist<K>, smem);                                                        \
+        if (e != cudaSuccess) return pq_set_cuda_error(e, "cudaFuncSetAttribute", __LINE__);                                      \
+        const int g = flat_grid(T, resident_blocks(p, k_grid_hist<K>, smem));                                                     \
+        k_grid_hist<K><<<g, GR_THREADS, smem, st>>>(S, T, first, count, logp, aux, best, log_rel, edges, nbins, hist);             \
     } break;
     switch (S.k) { G3(1) G3(2) G3(3) G3(4) G3(6) }
 #undef G3

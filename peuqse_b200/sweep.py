@@ -120,12 +120,13 @@ class Sweep:
             dist.all_reduce(self.acc[lay["MIN"]:lay["MIN"] + k], op=dist.ReduceOp.MIN)
             dist.all_reduce(self.acc[lay["MAX"]:lay["MAX"] + k], op=dist.ReduceOp.MAX)
 
-    def pass3(self, log_rel):
+    def pass3(self, log_rel, reuse_pass2_sums=True):
         _lib.check(self.L.peuqse_sweep_edges(_lib.ptr(self.acc), self.k, self.nbins, _lib.ptr(self.edges),
                                              _lib.ptr(self.hist), _lib.current_stream()))
         _lib.check(self.L.peuqse_sweep_hist(self.dp.handle, C.byref(self.spec), self.first, self.count,
                                             _lib.ptr(self.logp), _lib.ptr(self.best), float(log_rel), _lib.ptr(self.edges),
-                                            self.nbins, _lib.ptr(self.hist), _lib.ptr(self.work), _lib.current_stream()))
+                                            self.nbins, _lib.ptr(self.hist), _lib.ptr(self.work), 1 if reuse_pass2_sums else 0,
+                                            _lib.current_stream()))
         self.launches += 2
         if self.world > 1:
             import torch.distributed as dist
