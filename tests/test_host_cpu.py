@@ -1,0 +1,202 @@
+"""CPU-only tests: host-side normalisation, the C-ABI library (load + exported symbols, no compute calls),
+the UserInput mirror, and the multi-rank reduction logic over gloo with world_size 2."""
+import ctypes
+import os
+import re
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+X00 = [600, 1100, 1400]
+Y00 = [360500, 580500, 1620500]
+S00 = [200000, 300000, 200000]
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from peuqse_b200 import _lib
+    L = _lib.load()
+    hdr = open(os.path.join(REPO, "include", "peuqse_b200.h")).read()
+    declared = set(re.findall(r"\b(peuqse_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"peuqse_problem_desc", "peuqse_sweep_spec", "peuqse_best", "peuqse_mh_spec", "peuqse_ess_spec"}
+    assert len(declared) >= 18
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/peuqse_b200.h but not exported"
+    assert set(_lib.EXPORTS) == declared
+    assert L.peuqse_version() >= 100
+
+
+def test_ctypes_struct_layouts_match_header_sizes():
+    from peuqse_b200 import _lib
+    # sizes implied by the header (LP64): checked so that a field added on one side only is caught
+    assert ctypes.sizeof(_lib.Best) == 16
+    assert ctypes.sizeof(_lib.SweepSpec) == 8 + 16 * 8 * 3 + 8 + 16 * 8 + 8
+    assert ctypes.sizeof(_lib.MHSpec) == 7 * 8 + 8 + 256 * 8
+    assert ctypes.sizeof(_lib.ESSSpec) == 5 * 8 + 4 * 4
+    assert ctypes.sizeof(_lib.ProblemDesc) == 16 + 32 + 8 + 24 + 8 + 8 + 24 + 32 + 8 + 8 + 8
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import peuqse_b200 as PEUQSE
+    UI = PEUQSE.UserInput.fresh()
+    UI.responses['responses_observed'] = Y00
+    UI.responses['responses_observed_uncertainties'] = S00
+    UI.model['InputParameterPriorValues'] = [200, 500]
+    UI.model['InputParametersPriorValuesUncertainties'] = [100, 200]
+    UI.model['simulateByInputParametersOnlyFunction'] = PEUQSE.QuadraticModel(X00)
+    with pytest.raises(PEUQSE.PeuqseError):
+        PEUQSE.parameter_estimation(UI)
+
+
+def test_product_does_not_import_the_oracle():
+    for root, _, files in os.walk(os.path.join(REPO, "peuqse_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(root, f)).read()
+                assert "oracle" not in src.replace("peuqse_oracle", "oracle") or "import oracle" not in src
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+
+
+def test_host_normalisation_matches_oracle_constants():
+    """problem.py (product) and oracle.build_problem restate IP.py:146-350 independently: same constants."""
+    from peuqse_b200 import _lib
+    from peuqse_b200.problem import build_host_problem
+    from oracle import peuqse_oracle as orc
+    cases = [
+        dict(mu=[200, 500], unc=[100, 200]),
+        dict(mu=[200, 500], unc=[100, -1], ub=[None, 900], lb=[None, 100]),
+        dict(mu=[1.0, 2.0], unc=[[1, .3], [.3, 4]]),
+        dict(mu=[200, 500], unc=[100, 200], scaling="off"),
+        dict(mu=[200, 500], unc=[100, 200], scaling=3.0),
+        dict(mu=[200, 500], unc=[100, 200], simunc=[1e5, 5e4, 2e5]),
+    ]
+    for c in cases:
+        H = build_host_problem(c['mu'], c['unc'], Y00, S00, lower_bounds=c.get('lb', ()), upper_bounds=c.get('ub', ()),
+                               scaling_type=c.get('scaling', 'std'), simulation_uncertainties=c.get('simunc'))
+        P = orc.build_problem(c['mu'], c['unc'], Y00, S00, lower_bounds=c.get('lb', ()), upper_bounds=c.get('ub', ()),
+                              scaling_type=c.get('scaling', 'std'), simulation_uncertainties=c.get('simunc'))
+        assert np.array_equal(H.mu_prior_scaled, P.mu_prior_scaled)
+        assert np.array_equal(H.covmat_prior_scaled, P.covmat_prior_scaled)
+        if P.prior_wh is not None:
+            assert H.prior_c == P.prior_wh.rank * orc.LOG2PI + P.prior_wh.log_pdet
+            if P.prior_wh.is_perm:
+                assert H.prior_mode == _lib.PRIOR_DIAG and np.array_equal(H.prior_w, P.prior_wh.w)
+                assert np.array_equal(H.prior_gidx, P.gauss_idx[P.prior_wh.perm])
+            else:
+                assert H.prior_mode == _lib.PRIOR_DENSE and np.array_equal(H.prior_U, P.prior_wh.U)
+        blk = P.responses[0]
+        assert H.resp_mode[0] == _lib.RESP_MVN_DIAG
+        assert np.array_equal(H.w, blk.wh.w) and np.array_equal(H.y, blk.y[blk.wh.perm])
+        assert H.resp_c[0] == blk.wh.rank * orc.LOG2PI + blk.wh.log_pdet
+    # per-value path and full covariance
+    n = 150
+    y = np.linspace(1, 2, n)
+    H = build_host_problem([0.0], [1.0], y, np.full(n, 0.1))
+    P = orc.build_problem([0.0], [1.0], y, np.full(n, 0.1))
+    assert H.resp_mode[0] == _lib.RESP_PER_VALUE
+    assert np.array_equal(H.w, P.responses[0].w_val) and np.array_equal(H.cval, P.responses[0].c_val)
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((6, 6))
+    cov = A @ A.T + np.eye(6)
+    H = build_host_problem([0.0], [1.0], [y[:6], y[6:12]], [cov, cov])
+    assert list(H.resp_mode) == [_lib.RESP_MVN_FULL] * 2 and H.resp_U[0].shape == (6, 6)
+    with pytest.raises(NotImplementedError):
+        build_host_problem([0.0], [1.0], y[:6], cov)        # single-response full covariance: dead code in the reference
+
+
+def test_userinput_mirror_has_reference_keys():
+    import peuqse_b200.UserInput as UI
+    for d, keys in [('responses', ['responses_abscissa', 'responses_observed', 'responses_observed_uncertainties',
+                                   'responses_observed_max_covmat_size']),
+                    ('model', ['InputParameterPriorValues', 'InputParametersPriorValuesUncertainties', 'InputParameterInitialGuess',
+                               'simulateByInputParametersOnlyFunction', 'InputParameterPriorValues_upperBounds',
+                               'InputParameterPriorValues_lowerBounds', 'responses_simulation_uncertainties']),
+                    ('parameter_estimation_settings',
+                     ['scaling_uncertainties_type', 'mcmc_random_seed', 'mcmc_length', 'mcmc_burn_in', 'mcmc_relative_step_length',
+                      'mcmc_modulate_accept_probability', 'mcmc_nwalkers', 'mcmc_maxiter', 'mcmc_threshold_filter_samples',
+                      'multistart_searchType', 'multistart_numStartPoints', 'multistart_initialPointsDistributionType',
+                      'multistart_relativeInitialDistributionSpread', 'multistart_gridsearchSamplingInterval',
+                      'multistart_gridsearchSamplingRadii', 'multistart_permutationsToSamples',
+                      'multistart_permutationsToSamples_threshold_filter_coefficient'])]:
+        for k in keys:
+            assert k in getattr(UI, d), (d, k)
+    a, b = UI.fresh(), UI.fresh()
+    a.model['InputParameterPriorValues'] = [1]
+    assert b.model['InputParameterPriorValues'] == []
+    assert UI.parameter_estimation_settings['multistart_relativeInitialDistributionSpread'] == 0.866
+    assert UI.responses['responses_observed_max_covmat_size'] == 100
+
+
+def test_merge_best_rule():
+    from peuqse_b200.distributed import merge_best, shard_range
+    assert merge_best([(-3.0, 10), (-1.0, 50), (-1.0, 20), (float('nan'), 1), (float('-inf'), 0), (-2.0, -1)]) == (-1.0, 20)
+    assert merge_best([(float('-inf'), -1), (float('nan'), 3)]) == (float('-inf'), -1)
+    cover = []
+    for r in range(7):
+        f, c = shard_range(100020001, r, 7)
+        cover.append((f, c))
+    assert cover[0][0] == 0 and sum(c for _, c in cover) == 100020001
+    assert all(cover[i][0] + cover[i][1] == cover[i + 1][0] for i in range(6))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _rank_main(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, REPO)
+    from peuqse_b200 import distributed as D
+    from oracle import peuqse_oracle as orc
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # every rank evaluates its contiguous shard of the Example00 grid with the oracle (the GPU kernels' stand-in on CPU)
+        c, h, r = [200., 500.], [5., 5.], [50, 50]
+        N = orc.grid_size(r)
+        first, count = D.shard_range(N)
+        P = orc.build_problem([200, 500], [100, 200], Y00, S00)
+        _, bt = orc.sim_quadratic(X00)
+        th = orc.grid_decode(c, h, r, np.arange(first, first + count))
+        lp = orc.log_p_batch(P, th, bt)[0]
+        i, v = orc.first_max_np(lp)
+        best_v, best_i = D.allgather_best(v, first + i if i >= 0 else -1)
+        w, thr = orc.permutation_weights(lp, best_v)
+        shift = orc.grid_decode(c, h, r, np.array([best_i]))[0]
+        sums = np.concatenate([[w.sum()], (w[:, None] * (th - shift)).sum(axis=0)])
+        sums = D.allreduce_np(sums, "sum")
+        kept = w > 0
+        mn = D.allreduce_np(th[kept].min(axis=0) if kept.any() else np.full(2, np.inf), "min")
+        mx = D.allreduce_np(th[kept].max(axis=0) if kept.any() else np.full(2, -np.inf), "max")
+        cnt = D.allreduce_int_np(np.array([int(kept.sum())]))
+        rows = D.allgather_rows(torch.from_numpy(th[:3 + rank]))
+        if rank == 0:
+            np.savez(out, best_v=best_v, best_i=best_i, W=sums[0], mu=shift + sums[1:] / sums[0], mn=mn, mx=mx, cnt=cnt,
+                     nrows=rows.shape[0])
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_reductions_match_single_process(tmp_path, golden):
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "r.npz")
+    port = _free_port()
+    mp.spawn(_rank_main, args=(2, port, out), nprocs=2, join=True)
+    res = np.load(out)
+    g = golden("example00")
+    assert int(res['best_i']) == 13 and float(res['best_v']) == float(g['ex00_grid_map_logP'])
+    assert int(res['W']) == int(g['ex00_grid_nrows_expanded'])
+    np.testing.assert_allclose(res['mu'], g['ex00_grid_mu_AP'], rtol=1e-12)
+    assert int(res['cnt'][0]) == int((g['ex00_grid_multiplicity'] > 0).sum())
+    assert int(res['nrows']) == 3 + 4
