@@ -71,7 +71,7 @@ def mh_stat_layout(k):
 
 
 EXPORTS = [
-    "peuqse_last_error", "peuqse_version", "peuqse_device_info", "peuqse_problem_create", "peuqse_problem_destroy",
+    "peuqse_last_error", "peuqse_version", "peuqse_device_info", "peuqse_bench_fp64", "peuqse_problem_create", "peuqse_problem_destroy",
     "peuqse_logp_batch", "peuqse_logp_from_sim", "peuqse_simulate_batch", "peuqse_sweep_work_bytes",
     "peuqse_sweep_pass1", "peuqse_sweep_best_point", "peuqse_sweep_points", "peuqse_sweep_pass2", "peuqse_sweep_edges", "peuqse_sweep_hist",
     "peuqse_mh_run",
@@ -104,6 +104,7 @@ def load():
     L.peuqse_last_error.argtypes = []
     L.peuqse_version.restype = C.c_int
     L.peuqse_device_info.argtypes = [c_int32_p]
+    L.peuqse_bench_fp64.argtypes = [i32, c_double_p, vp, vp]
     L.peuqse_problem_create.argtypes = [C.POINTER(ProblemDesc), C.POINTER(vp)]
     L.peuqse_problem_destroy.argtypes = [vp]
     L.peuqse_logp_batch.argtypes = [vp, vp, i64, vp, vp, vp, vp]

@@ -180,3 +180,54 @@ extern "C" int peuqse_problem_destroy(peuqse_problem* p) {
     delete p;
     return PEUQSE_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// fp64 pipe microbenchmark (roofline denominator for the compute-bound kernels): every thread runs `iters`
+// rounds of 8 independent chains; mode 0 = DFMA, mode 1 = DADD + DMUL pairs (what -fmad=false parity code issues)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_bench_fp64(int iters, int mode, double seed, double* __restrict__ out) {
+    double a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = seed + threadIdx.x * 1e-9 + j;
+    const double m = 1.0000000001, c = 1e-12;
+    if (mode == 0) {
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = fma(a[j], m, c);
+        }
+    } else {
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = __dadd_rn(__dmul_rn(a[j], m), c);
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += a[j];
+    if (s == 123.456) out[0] = s;    // keep the chains alive
+}
+
+// returns through *instr_per_s the measured fp64 instruction rate (instructions, not flops) of the whole device
+extern "C" int peuqse_bench_fp64(int32_t mode, double* instr_per_s, double* d_scratch, void* stream) {
+    int dev = 0;
+    PQ_CUDA_OK(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    PQ_CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int blocks = prop.multiProcessorCount * 8, iters = 20000;
+    cudaEvent_t e0, e1;
+    PQ_CUDA_OK(cudaEventCreate(&e0));
+    PQ_CUDA_OK(cudaEventCreate(&e1));
+    k_bench_fp64<<<blocks, 256, 0, st>>>(200, mode, 1.0, d_scratch);
+    PQ_CUDA_OK(cudaEventRecord(e0, st));
+    k_bench_fp64<<<blocks, 256, 0, st>>>(iters, mode, 1.0, d_scratch);
+    PQ_CUDA_OK(cudaEventRecord(e1, st));
+    PQ_CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    PQ_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    const double n = (double)blocks * 256.0 * iters * 8.0 * (mode == 0 ? 1.0 : 2.0);
+    *instr_per_s = n / (ms * 1e-3);
+    return PEUQSE_OK;
+}

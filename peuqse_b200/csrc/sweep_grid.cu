@@ -25,6 +25,9 @@
 #define GR_WARPS (GR_THREADS / 32)
 #define GR_JPT 8
 #define GR_CH (GR_THREADS * GR_JPT)
+#define GR_MSTRIDE 32   // a thread's 8 points are 32 apart: a warp covers 256 CONTIGUOUS positions of a row (compact tiles)
+// position of the thread's first point inside its chunk
+#define GR_JL0 ((int)(threadIdx.x >> 5) * (32 * GR_JPT) + (int)(threadIdx.x & 31))
 
 struct GridTiling {
     long long ML;          // first global index of the bulk of the last axis = prod_{d<L}(2 r_d + 1)
@@ -39,6 +42,7 @@ struct GridAux {
     unsigned int* tilemax;   // [ntiles * GR_WARPS] order-preserving keys of float upper bounds
     double* colsum;          // [r2]   sum of weights per last-axis position
     double* rowsum;          // [rows] sum of weights per row
+    double* rowsumL;         // [rows] sum of weights * (theta_L - shift_L) per row
     int* valid;              // rowsum/colsum hold the sums of the last pass 2
 };
 
@@ -120,7 +124,7 @@ struct RowRec {
     static constexpr int N = ((2 + (KT - 1) + NT) + 1) & ~1;       // even: 16-byte aligned records
 };
 
-template <int MODEL, int KT, int NT, bool EXACT, bool SIMPLE, bool STORE>
+template <int MODEL, int KT, int NT, bool EXACT, bool SIMPLE, bool STORE, bool BOUNDS>
 __global__ void __launch_bounds__(GR_THREADS, 3) k_grid_pass1(const __grid_constant__ DevProblem P, const __grid_constant__ DevSweep S,
                                                            const __grid_constant__ GridTiling T, long long first, long long count,
                                                            double* __restrict__ logp_out, unsigned int* __restrict__ tilemax,
@@ -133,14 +137,14 @@ __global__ void __launch_bounds__(GR_THREADS, 3) k_grid_pass1(const __grid_const
     constexpr int L = KT - 1;
     const int chunk = blockIdx.x % T.nchunks, rg = blockIdx.x / T.nchunks;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long j0 = (long long)chunk * GR_CH + threadIdx.x;
+    const long long j0 = (long long)chunk * GR_CH + GR_JL0;
     const long long last = first + count;
     const bool full_chunk = (long long)(chunk + 1) * GR_CH <= T.r2;     // every j of this chunk exists (block-uniform)
     double thL[GR_JPT], qL[GR_JPT];
     bool okL[GR_JPT], jv[GR_JPT];
 #pragma unroll
     for (int m = 0; m < GR_JPT; ++m) {
-        const long long j = j0 + m * GR_THREADS;
+        const long long j = j0 + m * GR_MSTRIDE;
         thL[m] = last_axis_value(S, L, j);
         prior_axis(P, L, thL[m], okL[m], qL[m]);
         jv[m] = j < T.r2;
@@ -198,29 +202,39 @@ __global__ void __launch_bounds__(GR_THREADS, 3) k_grid_pass1(const __grid_const
                 double q[NT];
                 FastQLast<MODEL, KT, NT, EXACT, 0>::fill(P, pre, thL[m], q);
                 const double maha_l = ordered_sum_static<NT>(EXACT ? NT : P.fast_n, q);
-                double ll = -0.5 * (P.resp_c[0] + maha_l);
-                if (pq_isnan_bits(ll)) ll = pq_neg_inf();              // IP.py:2880-2882
-                v[m] = (ok_low && okL[m]) ? (ll + lp) : pq_neg_inf();  // IP.py:1649-1653
+                const double ll = -0.5 * (P.resp_c[0] + maha_l);
+                v[m] = ll + lp;                                        // IP.py:1653
+                if (BOUNDS) v[m] = (ok_low && okL[m]) ? v[m] : pq_neg_inf();   // IP.py:1649-1650
+            }
+            {   // a NaN simulated value must give -inf (IP.py:2880-2882): one exponent test for the 8 points, fix-up is rare
+                unsigned int emax = 0u;
+#pragma unroll
+                for (int m = 0; m < GR_JPT; ++m) emax = max(emax, (unsigned int)__double2hiint(v[m]) & 0x7fffffffu);
+                if (emax >= 0x7ff00000u) {
+#pragma unroll
+                    for (int m = 0; m < GR_JPT; ++m)
+                        if (pq_isnan_bits(v[m])) v[m] = pq_neg_inf();
+                }
             }
             double rowmax = pq_neg_inf();
             int rowm = 0;
             if (inside && full_chunk) {
 #pragma unroll
                 for (int m = 0; m < GR_JPT; ++m) {
-                    if (STORE) __stcs(logp_out + (gbase + m * GR_THREADS - first), v[m]);
+                    if (STORE) __stcs(logp_out + (gbase + m * GR_MSTRIDE - first), v[m]);
                     if (v[m] > rowmax) { rowmax = v[m]; rowm = m; }    // strict '>', increasing g within the row
                 }
             } else {                                                  // ragged chunk or first / last row of a rank's range
 #pragma unroll
                 for (int m = 0; m < GR_JPT; ++m) {
-                    const long long g = gbase + m * GR_THREADS;
+                    const long long g = gbase + m * GR_MSTRIDE;
                     if (jv[m] && g >= first && g < last) {
                         if (STORE) __stcs(logp_out + (g - first), v[m]);
                         if (v[m] > rowmax) { rowmax = v[m]; rowm = m; }
                     }
                 }
             }
-            if (rowmax > best.v) { best.v = rowmax; best.i = gbase + rowm * GR_THREADS; }   // rows in increasing g
+            if (rowmax > best.v) { best.v = rowmax; best.i = gbase + rowm * GR_MSTRIDE; }   // rows in increasing g
             if (STORE) {
                 const unsigned int key = __reduce_max_sync(0xffffffffu, up_key(rowmax));
                 if (lane == 0) tilemax[((size_t)(b - T.b_lo) * T.nchunks + chunk) * GR_WARPS + warp] = key;
@@ -351,14 +365,14 @@ __global__ void __launch_bounds__(GR_THREADS, FUSE ? 2 : 3) k_grid_pass2(const _
             const long long row = t / T.nchunks;
             const long long b = T.b_lo + row;
             const int chunk = (int)(t - row * T.nchunks);
-            const int jt = chunk * GR_CH + threadIdx.x;
+            const int jt = chunk * GR_CH + GR_JL0;
             const long long gbase = T.ML + b * T.r2 + jt;
             double v[GR_JPT];
 #pragma unroll
             for (int m = 0; m < GR_JPT; ++m) {                      // all loads first (memory-level parallelism)
-                const long long g = gbase + m * GR_THREADS;
+                const long long g = gbase + m * GR_MSTRIDE;
                 v[m] = pq_neg_inf();
-                if (jt + m * GR_THREADS < T.r2 && g >= first && g < last) v[m] = __ldcs(logp_in + (g - first));
+                if (jt + m * GR_MSTRIDE < T.r2 && g >= first && g < last) v[m] = __ldcs(logp_in + (g - first));
             }
             double roww = 0.0, rowwL = 0.0;                          // sum_m w, sum_m w*(theta_L - shift_L)
 #pragma unroll
@@ -366,7 +380,7 @@ __global__ void __launch_bounds__(GR_THREADS, FUSE ? 2 : 3) k_grid_pass2(const _
                 if (v[m] > thr) {                                   // IP.py:3481
                     const double reps = exp(v[m] - thr);            // IP.py:3485
                     const double wt = trunc(reps);                  // IP.py:3486
-                    const double thl = last_axis_value(S, L, jt + m * GR_THREADS);
+                    const double thl = last_axis_value(S, L, jt + m * GR_MSTRIDE);
                     const double dl = thl - shift[L];
                     const double wdl = wt * dl;
                     A.wr = fma(wt, reps, A.wr);
@@ -376,10 +390,10 @@ __global__ void __launch_bounds__(GR_THREADS, FUSE ? 2 : 3) k_grid_pass2(const _
                     A.s2[tri_index(KT, L, L)] = fma(wdl, dl, A.s2[tri_index(KT, L, L)]);
                     A.mn[L] = fmin(A.mn[L], thl);
                     A.mx[L] = fmax(A.mx[L], thl);
-                    if (FUSE) s_col[jt + m * GR_THREADS] += wt;      // position j of a row always belongs to this thread
+                    if (FUSE) s_col[jt + m * GR_MSTRIDE] += wt;      // position j of a row always belongs to this thread
                     if (keep_idx) {
                         const unsigned long long slot = atomicAdd(keep_count, 1ULL);
-                        if ((long long)slot < keep_cap) { keep_idx[slot] = gbase + m * GR_THREADS; keep_logp[slot] = v[m]; }
+                        if ((long long)slot < keep_cap) { keep_idx[slot] = gbase + m * GR_MSTRIDE; keep_logp[slot] = v[m]; }
                     }
                 }
             }
@@ -476,6 +490,569 @@ __global__ void __launch_bounds__(GR_THREADS, FUSE ? 2 : 3) k_grid_pass2(const _
 }
 
 // ---------------------------------------------------------------------------------------------
+// pass 2, TMA version: the retained tiles of logP are streamed through a shared-memory ring by bulk async copies
+// (cp.async.bulk global->shared, completion on an mbarrier), so that HBM latency is hidden by the copy engine
+// instead of by occupancy.  Per CTA: (1) the keys of its tiles are scanned once and the tiles with retained points
+// are listed in shared memory, (2) one elected thread keeps P2_STAGES-1 copies in flight, (3) all warps consume a
+// stage (a warp whose own tile maximum is below the threshold skips the arithmetic).
+// ---------------------------------------------------------------------------------------------
+#define P2_STAGES 4
+#define P2_KLIST 1024
+#define P2_STAGE_DOUBLES (GR_CH + 2)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+struct TileSpan {          // element range of one (row, chunk) tile inside logp_in, and the 16-byte aligned copy range
+    long long start;       // element index of j = chunk*GR_CH (may lie outside [0,count) for a rank's first/last row)
+    long long lo, hi;      // valid elements [lo, hi)
+    long long a0, a1;      // copied elements [a0, a1), both even; elements in [a1, hi) are loaded directly
+    int len;               // number of j's in this chunk
+};
+__device__ __forceinline__ TileSpan tile_span(const GridTiling& T, long long first, long long count, long long t) {
+    TileSpan s;
+    const long long row = t / T.nchunks;
+    const int chunk = (int)(t - row * T.nchunks);
+    s.start = T.ML + (T.b_lo + row) * T.r2 + (long long)chunk * GR_CH - first;
+    const long long rem = T.r2 - (long long)chunk * GR_CH;
+    s.len = (int)(rem < GR_CH ? rem : GR_CH);
+    s.lo = s.start > 0 ? s.start : 0;
+    s.hi = s.start + s.len < count ? s.start + s.len : count;
+    if (s.hi < s.lo) s.hi = s.lo;
+    s.a0 = s.lo & ~1LL;
+    s.a1 = (s.hi + 1) & ~1LL;
+    if (s.a1 > count) s.a1 = s.hi & ~1LL;          // never read past the caller's buffer
+    if (s.a1 < s.a0) s.a1 = s.a0;
+    return s;
+}
+
+template <int KT, bool FUSE>
+__global__ void __launch_bounds__(GR_THREADS) k_grid_pass2_tma(const __grid_constant__ DevSweep S,
+                                                               const __grid_constant__ GridTiling T, long long first,
+                                                               long long count, const double* __restrict__ logp_in,
+                                                               const GridAux aux, const peuqse_best* __restrict__ best_in,
+                                                               double log_rel, double* __restrict__ partial,
+                                                               double* __restrict__ acc_out, unsigned int* __restrict__ ticket) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    double* s_buf = (double*)s_raw;                                              // [P2_STAGES][P2_STAGE_DOUBLES]
+    int* s_klist = (int*)(s_buf + P2_STAGES * P2_STAGE_DOUBLES);                 // [P2_KLIST] local tile slot | warp mask << 24
+    unsigned int* s_col = (unsigned int*)(s_klist + P2_KLIST);                   // FUSE: [nchunks*GR_CH] column weight sums
+    __shared__ __align__(8) unsigned long long s_full[P2_STAGES];
+    __shared__ int s_nk;
+    __shared__ double s_red[GR_WARPS];
+    __shared__ bool s_last;
+    constexpr int L = KT - 1;
+    const long long best_index = best_in->index;
+    const bool none = best_index < 0;
+    const double thr = none ? pq_pos_inf() : best_in->logp + log_rel;   // IP.py:3477
+    double shift[KT];
+    grid_point<KT>(S, (unsigned long long)(none ? 0 : best_index), shift, KT);   // moments about the MAP point
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long ntiles = (T.b_hi - T.b_lo) * T.nchunks;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < P2_STAGES; ++s) mbar_init(&s_full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (FUSE)
+        for (int a = threadIdx.x; a < T.nchunks * GR_CH; a += blockDim.x) s_col[a] = 0u;
+    __syncthreads();
+    GridAcc<KT> A;
+    A.init();
+    const long long nt_blk = none ? 0 : (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;   // tiles blockIdx.x + i*gridDim.x
+    unsigned int it = 0;                                             // stages consumed so far (ring position / phase)
+    for (long long base = 0; base < nt_blk; base += P2_KLIST) {
+        // (1) list the tiles of this batch that hold retained points
+        if (threadIdx.x == 0) s_nk = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < P2_KLIST && base + i < nt_blk; i += blockDim.x) {
+            const long long t = blockIdx.x + (base + i) * gridDim.x;
+            const uint4 k0 = __ldg((const uint4*)(aux.tilemax + (size_t)t * GR_WARPS));
+            const uint4 k1 = __ldg((const uint4*)(aux.tilemax + (size_t)t * GR_WARPS) + 1);
+            const unsigned int ks[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+            int mask = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w)
+                if (key_value(ks[w]) > thr) mask |= 1 << w;
+            if (mask) s_klist[atomicAdd(&s_nk, 1)] = i | (mask << 24);
+        }
+        __syncthreads();
+        const int nk = s_nk;
+        // (2) prologue: P2_STAGES-1 copies in flight
+        if (threadIdx.x == 0) {
+            for (int q = 0; q < P2_STAGES - 1 && q < nk; ++q) {
+                const long long t = blockIdx.x + (base + (s_klist[q] & 0xffffff)) * gridDim.x;
+                const TileSpan sp = tile_span(T, first, count, t);
+                const int st = (it + q) % P2_STAGES;
+                const uint32_t bytes = (uint32_t)((sp.a1 - sp.a0) * 8);
+                mbar_arrive_expect_tx(&s_full[st], bytes);
+                if (bytes) tma_load_1d(s_buf + st * P2_STAGE_DOUBLES, logp_in + sp.a0, bytes, &s_full[st]);
+            }
+        }
+        // (3) consume
+        for (int q = 0; q < nk; ++q, ++it) {
+            const int st = it % P2_STAGES;
+            if (threadIdx.x == 0 && q + P2_STAGES - 1 < nk) {        // refill the stage freed at the end of the previous iteration
+                const int qn = q + P2_STAGES - 1;
+                const long long t = blockIdx.x + (base + (s_klist[qn] & 0xffffff)) * gridDim.x;
+                const TileSpan sp = tile_span(T, first, count, t);
+                const int stn = (it + P2_STAGES - 1) % P2_STAGES;
+                const uint32_t bytes = (uint32_t)((sp.a1 - sp.a0) * 8);
+                mbar_arrive_expect_tx(&s_full[stn], bytes);
+                if (bytes) tma_load_1d(s_buf + stn * P2_STAGE_DOUBLES, logp_in + sp.a0, bytes, &s_full[stn]);
+            }
+            const int ent = s_klist[q];
+            const long long t = blockIdx.x + (base + (ent & 0xffffff)) * gridDim.x;
+            const bool mine = (ent >> (24 + warp)) & 1;              // this warp's tile maximum is above the threshold
+            while (!mbar_try_wait(&s_full[st], (it / P2_STAGES) & 1)) {}
+            if (mine) {
+                const TileSpan sp = tile_span(T, first, count, t);
+                const long long row = t / T.nchunks;
+                const int chunk = (int)(t - row * T.nchunks);
+                const int jt = chunk * GR_CH + GR_JL0;
+                const double* buf = s_buf + st * P2_STAGE_DOUBLES;
+                double v[GR_JPT];
+#pragma unroll
+                for (int m = 0; m < GR_JPT; ++m) {
+                    const long long e = sp.start + GR_JL0 + m * GR_MSTRIDE;
+                    v[m] = pq_neg_inf();
+                    if (GR_JL0 + m * GR_MSTRIDE < sp.len && e >= sp.lo && e < sp.hi)
+                        v[m] = (e < sp.a1) ? buf[e - sp.a0] : __ldcs(logp_in + e);
+                }
+                double roww = 0.0, rowwL = 0.0;                      // sum_m w, sum_m w*(theta_L - shift_L)
+#pragma unroll
+                for (int m = 0; m < GR_JPT; ++m) {
+                    if (v[m] > thr) {                               // IP.py:3481
+                        const double reps = exp(v[m] - thr);        // IP.py:3485
+                        const double wt = trunc(reps);              // IP.py:3486
+                        const double thl = last_axis_value(S, L, jt + m * GR_MSTRIDE);
+                        const double dl = thl - shift[L];
+                        const double wdl = wt * dl;
+                        A.wr = fma(wt, reps, A.wr);
+                        A.nk += 1.0;
+                        roww += wt;
+                        rowwL += wdl;
+                        A.s2[tri_index(KT, L, L)] = fma(wdl, dl, A.s2[tri_index(KT, L, L)]);
+                        A.mn[L] = fmin(A.mn[L], thl);
+                        A.mx[L] = fmax(A.mx[L], thl);
+                        if (FUSE) s_col[jt + m * GR_MSTRIDE] += (unsigned int)wt;   // j always belongs to this thread
+                    }
+                }
+                if (roww > 0.0) {                                    // row part of the moments, once per row
+                    A.w += roww;
+                    A.s1[L] += rowwL;
+                    if (KT > 1) {
+                        double th[KT];
+                        grid_point<KT>(S, (unsigned long long)(T.b_lo + row), th, L);
+#pragma unroll
+                        for (int d = 0; d < L; ++d) {
+                            const double dd = th[d] - shift[d];
+                            const double wd = roww * dd;
+                            A.s1[d] += wd;
+#pragma unroll
+                            for (int d2 = d; d2 < L; ++d2) A.s2[tri_index(KT, d, d2)] = fma(wd, th[d2] - shift[d2], A.s2[tri_index(KT, d, d2)]);
+                            A.s2[tri_index(KT, d, L)] = fma(dd, rowwL, A.s2[tri_index(KT, d, L)]);
+                            A.mn[d] = fmin(A.mn[d], th[d]);
+                            A.mx[d] = fmax(A.mx[d], th[d]);
+                        }
+                    }
+                }
+                if (FUSE && KT > 1) {
+                    const double rw = warp_sum(roww);                // integers < 2^53: exact in fp64
+                    if (lane == 0 && rw > 0.0) atomicAdd(aux.rowsum + row, rw);
+                }
+            }
+            __syncthreads();                                         // stage st may be refilled from now on
+        }
+    }
+    for (long long g = T.slab_first + (long long)blockIdx.x * GR_THREADS + threadIdx.x; g < T.slab_first + T.slab_count && !none;
+         g += (long long)gridDim.x * GR_THREADS) {
+        const double v = __ldcs(logp_in + (g - first));
+        if (v > thr) {
+            double th[KT];
+            grid_point<KT>(S, (unsigned long long)g, th, KT);
+            A.add(v, thr, th, shift);
+        }
+    }
+    if (FUSE) {
+        __syncthreads();
+        for (long long j = threadIdx.x; j < T.r2; j += blockDim.x) {
+            const unsigned int cw = s_col[j];
+            if (cw) atomicAdd(aux.colsum + j, (double)cw);
+        }
+    }
+    double* mine_p = partial + (size_t)blockIdx.x * PQ_ACC_MAX;
+    double r;
+    r = blk_sum(A.w, s_red);  if (threadIdx.x == 0) mine_p[PEUQSE_ACC_W] = r;
+    r = blk_sum(A.wr, s_red); if (threadIdx.x == 0) mine_p[PEUQSE_ACC_WEXP] = none ? 0.0 : r * exp(thr);
+    r = blk_sum(A.nk, s_red); if (threadIdx.x == 0) mine_p[PEUQSE_ACC_NKEPT] = r;
+    {
+        int e = 0;
+#pragma unroll
+        for (int d = 0; d < KT; ++d) {
+            r = blk_sum(A.s1[d], s_red);   if (threadIdx.x == 0) mine_p[PEUQSE_ACC_S1 + d] = r;
+            r = blk_min(A.mn[d], s_red);   if (threadIdx.x == 0) mine_p[PEUQSE_ACC_MIN(KT) + d] = r;
+            r = -blk_min(-A.mx[d], s_red); if (threadIdx.x == 0) mine_p[PEUQSE_ACC_MAX(KT) + d] = r;
+#pragma unroll
+            for (int d2 = d; d2 < KT; ++d2) {
+                r = blk_sum(A.s2[e], s_red);
+                if (threadIdx.x == 0) { mine_p[PEUQSE_ACC_S2(KT) + d * KT + d2] = r; mine_p[PEUQSE_ACC_S2(KT) + d2 * KT + d] = r; }
+                ++e;
+            }
+        }
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int tkt = atomicAdd(ticket, 1u);
+        s_last = (tkt == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        constexpr int nacc = PEUQSE_ACC_DOUBLES(KT), mn0 = PEUQSE_ACC_MIN(KT), mx0 = PEUQSE_ACC_MAX(KT);
+        for (int a = threadIdx.x; a < nacc; a += blockDim.x) {
+            double rr = acc_out[a];
+            for (int bb = 0; bb < (int)gridDim.x; ++bb) {          // fixed block order: deterministic
+                const double x = __ldcg(partial + (size_t)bb * PQ_ACC_MAX + a);
+                if (a >= mx0) rr = fmax(rr, x);
+                else if (a >= mn0) rr = fmin(rr, x);
+                else rr += x;
+            }
+            acc_out[a] = rr;
+        }
+        if (threadIdx.x == 0) *ticket = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass 2, TMA version 2 (the one the C2 step uses): per retained point only exp, trunc and four accumulations remain;
+// everything separable comes from the per-column sums (shared memory -> global) and per-row sums (global atomics):
+//     W = sum_j colsum_j,  S1_L = sum_j colsum_j dL_j,  S2_LL = sum_j colsum_j dL_j^2,  min/max_L = support of colsum,
+//     S1_d = sum_b rowsum_b dd_b,  S2_dd' = sum_b rowsum_b dd_b dd'_b,  S2_dL = sum_b dd_b rowsumL_b   (d, d' < L)
+// which the single-CTA k_grid_finish evaluates (it also handles the slab).
+// ---------------------------------------------------------------------------------------------
+// exp(x) for 0 <= x < 700: the usual reduction x = n ln2 + r, |r| <= ln2/2, degree-13 Taylor polynomial in Horner form,
+// scaling through the exponent field; <= 1 ulp like libdevice's exp but without its range / denormal handling.
+__device__ __forceinline__ double pq_exp_pos(double x) {
+    const double t = fma(x, 1.4426950408889634, 6755399441055744.0);
+    const int n = __double2loint(t);
+    const double fn = t - 6755399441055744.0;
+    double r = fma(fn, -6.93147180369123816490e-01, x);
+    r = fma(fn, -1.90821492927058770002e-10, r);
+    double p = 1.6059043836821613e-10;                    // 1/13!
+    p = fma(p, r, 2.08767569878681e-09);                  // 1/12!
+    p = fma(p, r, 2.505210838544172e-08);                 // 1/11!
+    p = fma(p, r, 2.755731922398589e-07);                 // 1/10!
+    p = fma(p, r, 2.7557319223985893e-06);                // 1/9!
+    p = fma(p, r, 2.48015873015873e-05);                  // 1/8!
+    p = fma(p, r, 1.984126984126984e-04);                 // 1/7!
+    p = fma(p, r, 1.388888888888889e-03);                 // 1/6!
+    p = fma(p, r, 8.333333333333333e-03);                 // 1/5!
+    p = fma(p, r, 4.1666666666666664e-02);                // 1/4!
+    p = fma(p, r, 1.6666666666666666e-01);                // 1/3!
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+}
+
+struct KTile {            // one retained tile of a CTA's batch
+    int row;              // row - b_lo
+    short chunk;
+    unsigned short mask;  // warps whose tile maximum is above the threshold
+};
+
+__device__ __forceinline__ TileSpan tile_span_rc(const GridTiling& T, long long first, long long count, int row, int chunk) {
+    TileSpan s;
+    s.start = T.ML + (T.b_lo + row) * T.r2 + (long long)chunk * GR_CH - first;
+    const long long rem = T.r2 - (long long)chunk * GR_CH;
+    s.len = (int)(rem < GR_CH ? rem : GR_CH);
+    s.lo = s.start > 0 ? s.start : 0;
+    s.hi = s.start + s.len < count ? s.start + s.len : count;
+    if (s.hi < s.lo) s.hi = s.lo;
+    s.a0 = s.lo & ~1LL;
+    s.a1 = (s.hi + 1) & ~1LL;
+    if (s.a1 > count) s.a1 = s.hi & ~1LL;          // never read past the caller's buffer
+    if (s.a1 < s.a0) s.a1 = s.a0;
+    return s;
+}
+
+template <int KT>
+__global__ void __launch_bounds__(GR_THREADS) k_grid_pass2_tma2(const __grid_constant__ DevSweep S,
+                                                                const __grid_constant__ GridTiling T, long long first,
+                                                                long long count, const double* __restrict__ logp_in,
+                                                                const GridAux aux, const peuqse_best* __restrict__ best_in,
+                                                                double log_rel, double* __restrict__ partial,
+                                                                double* __restrict__ acc_out, unsigned int* __restrict__ ticket) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    double* s_buf = (double*)s_raw;                                              // [P2_STAGES][P2_STAGE_DOUBLES]
+    KTile* s_klist = (KTile*)(s_buf + P2_STAGES * P2_STAGE_DOUBLES);             // [P2_KLIST]
+    unsigned int* s_col = (unsigned int*)(s_klist + P2_KLIST);                   // [nchunks*GR_CH] column weight sums
+    __shared__ __align__(8) unsigned long long s_full[P2_STAGES];
+    __shared__ int s_nk;
+    __shared__ double s_red[GR_WARPS];
+    __shared__ bool s_last;
+    constexpr int L = KT - 1;
+    const long long best_index = best_in->index;
+    const bool none = best_index < 0;
+    const double thr = none ? pq_pos_inf() : best_in->logp + log_rel;   // IP.py:3477
+    double shift[KT];
+    grid_point<KT>(S, (unsigned long long)(none ? 0 : best_index), shift, KT);   // moments about the MAP point
+    const double shiftL = shift[L], cL = S.center[L], hL = S.interval[L];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long ntiles = (T.b_hi - T.b_lo) * T.nchunks;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < P2_STAGES; ++s) mbar_init(&s_full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int a = threadIdx.x; a < T.nchunks * GR_CH; a += blockDim.x) s_col[a] = 0u;
+    __syncthreads();
+    double a_wr = 0.0, a_nk = 0.0;
+    const long long nt_blk = none ? 0 : (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;   // tiles blockIdx.x + i*gridDim.x
+    unsigned int it = 0;                                             // stages consumed so far (ring position / phase)
+    for (long long base = 0; base < nt_blk; base += P2_KLIST) {
+        // (1) list the tiles of this batch that hold retained points (row / chunk resolved here, once per tile)
+        if (threadIdx.x == 0) s_nk = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < P2_KLIST && base + i < nt_blk; i += blockDim.x) {
+            const long long t = blockIdx.x + (base + i) * gridDim.x;
+            const uint4 k0 = __ldg((const uint4*)(aux.tilemax + (size_t)t * GR_WARPS));
+            const uint4 k1 = __ldg((const uint4*)(aux.tilemax + (size_t)t * GR_WARPS) + 1);
+            const unsigned int ks[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+            int mask = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w)
+                if (key_value(ks[w]) > thr) mask |= 1 << w;
+            if (mask) {
+                const long long row = t / T.nchunks;
+                KTile kt;
+                kt.row = (int)row;
+                kt.chunk = (short)(t - row * T.nchunks);
+                kt.mask = (unsigned short)mask;
+                s_klist[atomicAdd(&s_nk, 1)] = kt;
+            }
+        }
+        __syncthreads();
+        const int nk = s_nk;
+        // (2) prologue: P2_STAGES-1 copies in flight
+        if (threadIdx.x == 0) {
+            for (int q = 0; q < P2_STAGES - 1 && q < nk; ++q) {
+                const TileSpan sp = tile_span_rc(T, first, count, s_klist[q].row, s_klist[q].chunk);
+                const int st = (it + q) % P2_STAGES;
+                const uint32_t bytes = (uint32_t)((sp.a1 - sp.a0) * 8);
+                mbar_arrive_expect_tx(&s_full[st], bytes);
+                if (bytes) tma_load_1d(s_buf + st * P2_STAGE_DOUBLES, logp_in + sp.a0, bytes, &s_full[st]);
+            }
+        }
+        // (3) consume
+        for (int q = 0; q < nk; ++q, ++it) {
+            const int st = it % P2_STAGES;
+            if (threadIdx.x == 0 && q + P2_STAGES - 1 < nk) {        // refill the stage freed at the end of the previous iteration
+                const int qn = q + P2_STAGES - 1;
+                const TileSpan sp = tile_span_rc(T, first, count, s_klist[qn].row, s_klist[qn].chunk);
+                const int stn = (it + P2_STAGES - 1) % P2_STAGES;
+                const uint32_t bytes = (uint32_t)((sp.a1 - sp.a0) * 8);
+                mbar_arrive_expect_tx(&s_full[stn], bytes);
+                if (bytes) tma_load_1d(s_buf + stn * P2_STAGE_DOUBLES, logp_in + sp.a0, bytes, &s_full[stn]);
+            }
+            const KTile kt = s_klist[q];
+            const bool mine = (kt.mask >> warp) & 1;                 // this warp's tile maximum is above the threshold
+            while (!mbar_try_wait(&s_full[st], (it / P2_STAGES) & 1)) {}
+            if (mine) {
+                const TileSpan sp = tile_span_rc(T, first, count, kt.row, kt.chunk);
+                const int jt = kt.chunk * GR_CH + GR_JL0;
+                const double* buf = s_buf + st * P2_STAGE_DOUBLES;
+                double roww = 0.0, rowwL = 0.0;                      // sum_m w, sum_m w*(theta_L - shift_L)
+#pragma unroll
+                for (int m = 0; m < GR_JPT; ++m) {
+                    const long long e = sp.start + GR_JL0 + m * GR_MSTRIDE;
+                    double v = pq_neg_inf();
+                    if (GR_JL0 + m * GR_MSTRIDE < sp.len && e >= sp.lo && e < sp.hi)
+                        v = (e < sp.a1) ? buf[e - sp.a0] : __ldcs(logp_in + e);
+                    if (v > thr) {                                  // IP.py:3481
+                        const double reps = pq_exp_pos(v - thr);    // IP.py:3485
+                        const double wt = trunc(reps);              // IP.py:3486
+                        const int j = jt + m * GR_MSTRIDE;
+                        const double step = hL * (double)((j >> 1) + 1);
+                        const double dl = ((j & 1) ? (cL + step) : (cL - step)) - shiftL;
+                        a_wr = fma(wt, reps, a_wr);
+                        a_nk += 1.0;
+                        roww += wt;
+                        rowwL = fma(wt, dl, rowwL);
+                        s_col[j] += (unsigned int)wt;                // j always belongs to this thread
+                    }
+                }
+                const double rw = warp_sum(roww);                    // integers < 2^53: exact in fp64
+                if (rw > 0.0) {
+                    const double rwl = warp_sum(rowwL);
+                    if (lane == 0) {
+                        atomicAdd(aux.rowsum + kt.row, rw);
+                        atomicAdd(aux.rowsumL + kt.row, rwl);
+                    }
+                }
+            }
+            __syncthreads();                                         // stage st may be refilled from now on
+        }
+    }
+    for (long long j = threadIdx.x; j < T.r2; j += blockDim.x) {
+        const unsigned int cw = s_col[j];
+        if (cw) atomicAdd(aux.colsum + j, (double)cw);
+    }
+    double* mine_p = partial + (size_t)blockIdx.x * PQ_ACC_MAX;
+    double r;
+    r = blk_sum(a_wr, s_red); if (threadIdx.x == 0) mine_p[0] = none ? 0.0 : r * exp(thr);
+    r = blk_sum(a_nk, s_red); if (threadIdx.x == 0) mine_p[1] = r;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int tkt = atomicAdd(ticket, 1u);
+        s_last = (tkt == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {                                                    // fixed assignment + fixed tree: deterministic
+        __threadfence();
+        double r0 = 0.0, r1 = 0.0;
+        for (int bb = threadIdx.x; bb < (int)gridDim.x; bb += blockDim.x) {
+            r0 += __ldcg(partial + (size_t)bb * PQ_ACC_MAX);
+            r1 += __ldcg(partial + (size_t)bb * PQ_ACC_MAX + 1);
+        }
+        r0 = blk_sum(r0, s_red);
+        r1 = blk_sum(r1, s_red);
+        if (threadIdx.x == 0) {
+            acc_out[PEUQSE_ACC_WEXP] += r0;
+            acc_out[PEUQSE_ACC_NKEPT] += r1;
+            *ticket = 0;
+        }
+    }
+}
+
+// separable moments and min/max from the row / column sums + the slab, accumulated into acc_out (a few CTAs; partials
+// are combined by the last CTA in fixed order, so the result is deterministic)
+template <int KT>
+__global__ void __launch_bounds__(GR_THREADS) k_grid_finish(const __grid_constant__ DevSweep S, const __grid_constant__ GridTiling T,
+                                                            long long first, const double* __restrict__ logp_in, const GridAux aux,
+                                                            const peuqse_best* __restrict__ best_in, double log_rel,
+                                                            double* __restrict__ partial, double* __restrict__ acc_out,
+                                                            unsigned int* __restrict__ ticket) {
+    __shared__ double s_red[GR_WARPS];
+    __shared__ bool s_last;
+    constexpr int L = KT - 1;
+    const long long best_index = best_in->index;
+    if (best_index < 0) return;
+    const double thr = best_in->logp + log_rel;
+    double shift[KT];
+    grid_point<KT>(S, (unsigned long long)best_index, shift, KT);
+    GridAcc<KT> A;
+    A.init();
+    const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long j = t0; j < T.r2; j += stride) {
+        const double cw = aux.colsum[j];
+        if (cw > 0.0) {
+            const double thl = last_axis_value(S, L, j);
+            const double dl = thl - shift[L];
+            const double wd = cw * dl;
+            A.w += cw;
+            A.s1[L] += wd;
+            A.s2[tri_index(KT, L, L)] = fma(wd, dl, A.s2[tri_index(KT, L, L)]);
+            A.mn[L] = fmin(A.mn[L], thl);
+            A.mx[L] = fmax(A.mx[L], thl);
+        }
+    }
+    if (KT > 1) {
+        for (long long row = t0; row < T.b_hi - T.b_lo; row += stride) {
+            const double rw = aux.rowsum[row];
+            if (rw > 0.0) {
+                const double rwl = aux.rowsumL[row];
+                double th[KT];
+                grid_point<KT>(S, (unsigned long long)(T.b_lo + row), th, L);
+#pragma unroll
+                for (int d = 0; d < L; ++d) {
+                    const double dd = th[d] - shift[d];
+                    const double wd = rw * dd;
+                    A.s1[d] += wd;
+#pragma unroll
+                    for (int d2 = d; d2 < L; ++d2) A.s2[tri_index(KT, d, d2)] = fma(wd, th[d2] - shift[d2], A.s2[tri_index(KT, d, d2)]);
+                    A.s2[tri_index(KT, d, L)] = fma(dd, rwl, A.s2[tri_index(KT, d, L)]);
+                    A.mn[d] = fmin(A.mn[d], th[d]);
+                    A.mx[d] = fmax(A.mx[d], th[d]);
+                }
+            }
+        }
+    }
+    for (long long g = T.slab_first + t0; g < T.slab_first + T.slab_count; g += stride) {
+        const double v = __ldcs(logp_in + (g - first));
+        if (v > thr) {
+            double th[KT];
+            grid_point<KT>(S, (unsigned long long)g, th, KT);
+            A.add(v, thr, th, shift);
+        }
+    }
+    double* mine = partial + (size_t)blockIdx.x * PQ_ACC_MAX;
+    double r;
+    r = blk_sum(A.w, s_red);  if (threadIdx.x == 0) mine[PEUQSE_ACC_W] = r;
+    r = blk_sum(A.wr, s_red); if (threadIdx.x == 0) mine[PEUQSE_ACC_WEXP] = r * exp(thr);
+    r = blk_sum(A.nk, s_red); if (threadIdx.x == 0) mine[PEUQSE_ACC_NKEPT] = r;
+    {
+        int e = 0;
+#pragma unroll
+        for (int d = 0; d < KT; ++d) {
+            r = blk_sum(A.s1[d], s_red);   if (threadIdx.x == 0) mine[PEUQSE_ACC_S1 + d] = r;
+            r = blk_min(A.mn[d], s_red);   if (threadIdx.x == 0) mine[PEUQSE_ACC_MIN(KT) + d] = r;
+            r = -blk_min(-A.mx[d], s_red); if (threadIdx.x == 0) mine[PEUQSE_ACC_MAX(KT) + d] = r;
+#pragma unroll
+            for (int d2 = d; d2 < KT; ++d2) {
+                r = blk_sum(A.s2[e], s_red);
+                if (threadIdx.x == 0) { mine[PEUQSE_ACC_S2(KT) + d * KT + d2] = r; mine[PEUQSE_ACC_S2(KT) + d2 * KT + d] = r; }
+                ++e;
+            }
+        }
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int tkt = atomicAdd(ticket, 1u);
+        s_last = (tkt == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        constexpr int nacc = PEUQSE_ACC_DOUBLES(KT), mn0 = PEUQSE_ACC_MIN(KT), mx0 = PEUQSE_ACC_MAX(KT);
+        for (int a = threadIdx.x; a < nacc; a += blockDim.x) {
+            double x[16];
+#pragma unroll
+            for (int bb = 0; bb < 16; ++bb) x[bb] = (bb < (int)gridDim.x) ? __ldcg(partial + (size_t)bb * PQ_ACC_MAX + a) : 0.0;
+            double rr = acc_out[a];
+#pragma unroll
+            for (int bb = 0; bb < 16; ++bb) {
+                if (bb < (int)gridDim.x) {
+                    if (a >= mx0) rr = fmax(rr, x[bb]);
+                    else if (a >= mn0) rr = fmin(rr, x[bb]);
+                    else rr += x[bb];
+                }
+            }
+            acc_out[a] = rr;
+        }
+        if (threadIdx.x == 0) *ticket = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // pass 3
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ int hist_bin(const double* __restrict__ ed, int nbins, double x) {
@@ -487,6 +1064,22 @@ __device__ __forceinline__ int hist_bin(const double* __restrict__ ed, int nbins
     if (x < ed[b]) --b;
     else if (b != nbins - 1 && x >= ed[b + 1]) ++b;
     return b;
+}
+
+// adds w to bins[bin] (bin < 0: nothing); lanes of a warp that hit the same bin are summed first, so that the 64-bit
+// shared-memory atomic (a CAS loop) sees one update per distinct bin per warp instead of 32 colliding ones.
+// Must be called by all 32 lanes.
+__device__ __forceinline__ void warp_bin_add(unsigned long long* bins, int bin, double w) {
+    unsigned int todo = __ballot_sync(0xffffffffu, bin >= 0 && w > 0.0);
+    const int lane = threadIdx.x & 31;
+    while (todo) {
+        const int leader = __ffs(todo) - 1;
+        const int b0 = __shfl_sync(0xffffffffu, bin, leader);
+        const bool mine = (bin == b0) && ((todo >> lane) & 1u);
+        const double sum = warp_sum(mine ? w : 0.0);                 // integer-valued doubles: exact
+        if (lane == leader) atomicAdd(bins + b0, (unsigned long long)sum);
+        todo &= ~__ballot_sync(0xffffffffu, mine);
+    }
 }
 
 // (a) bins the row / column weight sums left by the fused pass 2 (and clears them); reads only the slab of logP
@@ -503,38 +1096,37 @@ __global__ void __launch_bounds__(GR_THREADS) k_grid_bin(const __grid_constant__
     for (int a = threadIdx.x; a < KT * nbins; a += blockDim.x) sh[a] = 0ULL;
     __syncthreads();
     const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    for (long long j = t0; j < T.r2; j += stride) {
-        const double cw = aux.colsum[j];
-        if (cw > 0.0) {
-            const int bin = hist_bin(edges + L * (nbins + 1), nbins, last_axis_value(S, L, j));
-            if (bin >= 0) atomicAdd(sh + L * nbins + bin, (unsigned long long)cw);
-        }
+    // every loop runs the same number of iterations in all lanes of a warp (warp_bin_add is a warp collective)
+    for (long long j0 = (long long)blockIdx.x * blockDim.x; j0 < T.r2; j0 += stride) {
+        const long long j = j0 + threadIdx.x;
+        const double cw = (j < T.r2) ? aux.colsum[j] : 0.0;
+        const int bin = (cw > 0.0) ? hist_bin(edges + L * (nbins + 1), nbins, last_axis_value(S, L, j)) : -1;
+        warp_bin_add(sh + L * nbins, bin, cw);
     }
     if (KT > 1) {
-        for (long long row = t0; row < T.b_hi - T.b_lo; row += stride) {
-            const double rw = aux.rowsum[row];
-            if (rw > 0.0) {
-                double th[KT];
-                grid_point<KT>(S, (unsigned long long)(T.b_lo + row), th, L);
+        const long long rows = T.b_hi - T.b_lo;
+        for (long long r0 = (long long)blockIdx.x * blockDim.x; r0 < rows; r0 += stride) {
+            const long long row = r0 + threadIdx.x;
+            const double rw = (row < rows) ? aux.rowsum[row] : 0.0;
+            double th[KT];
+            if (rw > 0.0) grid_point<KT>(S, (unsigned long long)(T.b_lo + row), th, L);
 #pragma unroll
-                for (int d = 0; d < L; ++d) {
-                    const int bin = hist_bin(edges + d * (nbins + 1), nbins, th[d]);
-                    if (bin >= 0) atomicAdd(sh + d * nbins + bin, (unsigned long long)rw);
-                }
+            for (int d = 0; d < L; ++d) {
+                const int bin = (rw > 0.0) ? hist_bin(edges + d * (nbins + 1), nbins, th[d]) : -1;
+                warp_bin_add(sh + d * nbins, bin, rw);
             }
         }
     }
-    for (long long g = T.slab_first + t0; g < T.slab_first + T.slab_count; g += stride) {
-        const double v = __ldcs(logp_in + (g - first));
-        if (v > thr) {
-            const unsigned long long w = (unsigned long long)trunc(exp(v - thr));
-            double th[KT];
-            grid_point<KT>(S, (unsigned long long)g, th, KT);
+    for (long long g0 = T.slab_first + (long long)blockIdx.x * blockDim.x; g0 < T.slab_first + T.slab_count; g0 += stride) {
+        const long long g = g0 + threadIdx.x;
+        const double v = (g < T.slab_first + T.slab_count) ? __ldcs(logp_in + (g - first)) : pq_neg_inf();
+        const double w = (v > thr) ? trunc(exp(v - thr)) : 0.0;
+        double th[KT];
+        if (w > 0.0) grid_point<KT>(S, (unsigned long long)g, th, KT);
 #pragma unroll
-            for (int d = 0; d < KT; ++d) {
-                const int bin = hist_bin(edges + d * (nbins + 1), nbins, th[d]);
-                if (bin >= 0) atomicAdd(sh + d * nbins + bin, w);
-            }
+        for (int d = 0; d < KT; ++d) {
+            const int bin = (w > 0.0) ? hist_bin(edges + d * (nbins + 1), nbins, th[d]) : -1;
+            warp_bin_add(sh + d * nbins, bin, w);
         }
     }
     __syncthreads();
@@ -566,21 +1158,21 @@ __global__ void __launch_bounds__(GR_THREADS) k_grid_hist(const __grid_constant_
         const long long row = t / T.nchunks;
         const long long b = T.b_lo + row;
         const int chunk = (int)(t - row * T.nchunks);
-        const int jt = chunk * GR_CH + threadIdx.x;
+        const int jt = chunk * GR_CH + GR_JL0;
         const long long gbase = T.ML + b * T.r2 + jt;
         double v[GR_JPT];
 #pragma unroll
         for (int m = 0; m < GR_JPT; ++m) {
-            const long long g = gbase + m * GR_THREADS;
+            const long long g = gbase + m * GR_MSTRIDE;
             v[m] = pq_neg_inf();
-            if (jt + m * GR_THREADS < T.r2 && g >= first && g < last) v[m] = __ldcs(logp_in + (g - first));
+            if (jt + m * GR_MSTRIDE < T.r2 && g >= first && g < last) v[m] = __ldcs(logp_in + (g - first));
         }
         double roww = 0.0;
 #pragma unroll
         for (int m = 0; m < GR_JPT; ++m) {
             if (v[m] > thr) {
                 const double w = trunc(exp(v[m] - thr));
-                colsum[jt + m * GR_THREADS] += w;
+                colsum[jt + m * GR_MSTRIDE] += w;
                 roww += w;
             }
         }
@@ -698,11 +1290,13 @@ static long long grid_aux_layout(const peuqse_problem* p, const DevSweep& S, lon
     const size_t o_tile = off; off = align_up(off + (rows * T.nchunks * GR_WARPS + 1) * sizeof(unsigned int), 256);
     const size_t o_col = off;  off = align_up(off + (size_t)(T.r2 + 1) * sizeof(double), 256);
     const size_t o_row = off;  off = align_up(off + (rows + 1) * sizeof(double), 256);
+    const size_t o_rowL = off; off = align_up(off + (rows + 1) * sizeof(double), 256);
     const size_t o_val = off;  off += 256;
     if (aux && base) {
         aux->tilemax = (unsigned int*)(base + o_tile);
         aux->colsum = (double*)(base + o_col);
         aux->rowsum = (double*)(base + o_row);
+        aux->rowsumL = (double*)(base + o_rowL);
         aux->valid = (int*)(base + o_val);
     }
     return (long long)off;
@@ -721,17 +1315,21 @@ static int launch_grid_pass1(const peuqse_problem* p, const DevSweep& S, long lo
     Best* partial = (Best*)((char*)work + PQ_SWEEP_TICKET_BYTES);
     GridTiling T;
 #define GP1_LAUNCH(SIMPLE, STORE)                                                                                            \
+    if (bounds) GP1_LAUNCH2(SIMPLE, STORE, true) else GP1_LAUNCH2(SIMPLE, STORE, false)
+#define GP1_LAUNCH2(SIMPLE, STORE, BOUNDS)                                                                                   \
     {                                                                                                                         \
-        auto kern = k_grid_pass1<MODEL, KT, NT, EXACT, SIMPLE, STORE>;                                                        \
+        auto kern = k_grid_pass1<MODEL, KT, NT, EXACT, SIMPLE, STORE, BOUNDS>;                                                \
         grid_tiling(p, S, first, count, resident_blocks(p, kern, 0), &T);                                                     \
         kern<<<T.nchunks * T.nrg, GR_THREADS, 0, st>>>(p->d, S, T, first, count, logp, tilemax, best, partial, ticket);        \
     }
     const bool store = logp != nullptr && tilemax != nullptr;
+    const bool bounds = d.has_lb || d.has_ub;
     if (simple && store) GP1_LAUNCH(true, true)
     else if (simple) GP1_LAUNCH(true, false)
     else if (store) GP1_LAUNCH(false, true)
     else GP1_LAUNCH(false, false)
 #undef GP1_LAUNCH
+#undef GP1_LAUNCH2
     PQ_CUDA_OK(cudaGetLastError());
     return PEUQSE_OK;
 }
@@ -740,7 +1338,7 @@ static int launch_grid_pass1(const peuqse_problem* p, const DevSweep& S, long lo
 int pq_grid_pass1(const peuqse_problem* p, const DevSweep& S, long long first, long long count, double* logp, void* aux_base,
                   peuqse_best* best, void* work, cudaStream_t st, bool* handled) {
     *handled = false;
-    GridAux aux = {nullptr, nullptr, nullptr, nullptr};
+    GridAux aux = {nullptr, nullptr, nullptr, nullptr, nullptr};
     if (!fast_model_ok(p) || grid_aux_layout(p, S, first, count, (char*)aux_base, &aux) == 0) return PEUQSE_OK;
     if (logp && !aux_base) return PEUQSE_OK;           // storing logP without room for the tile maxima: generic path
     *handled = true;
@@ -774,7 +1372,7 @@ int pq_grid_pass2(const peuqse_problem* p, const DevSweep& S, long long first, l
                   void* aux_base, const peuqse_best* best, double log_rel, double* acc, long long* kidx, double* klogp,
                   long long kcap, long long* kcount, void* work, cudaStream_t st, bool* handled) {
     *handled = false;
-    GridAux aux = {nullptr, nullptr, nullptr, nullptr};
+    GridAux aux = {nullptr, nullptr, nullptr, nullptr, nullptr};
     GridTiling T;
     if (!logp || !aux_base || grid_aux_layout(p, S, first, count, (char*)aux_base, &aux) == 0) return PEUQSE_OK;
     grid_tiling(p, S, first, count, 1, &T);
@@ -783,12 +1381,35 @@ int pq_grid_pass2(const peuqse_problem* p, const DevSweep& S, long long first, l
     double* partial = (double*)((char*)work + PQ_SWEEP_TICKET_BYTES);
     const size_t smem = (size_t)T.nchunks * GR_CH * sizeof(double);
     const bool fuse = pq_grid_pass2_fuses(p, S, first, count);
+    const size_t smem_tma = (size_t)P2_STAGES * P2_STAGE_DOUBLES * sizeof(double) + P2_KLIST * sizeof(int) +
+                            (fuse ? (size_t)T.nchunks * GR_CH * sizeof(unsigned int) : 0);
+    const bool use_tma = (((uintptr_t)logp) & 15) == 0 && kidx == nullptr && smem_tma + 1024 <= (size_t)p->max_smem_optin;
+#define G2T(K, F)                                                                                                                \
+    {                                                                                                                            \
+        cudaError_t e = pq_allow_smem((const void*)k_grid_pass2_tma<K, F>, smem_tma);                                            \
+        if (e != cudaSuccess) return pq_set_cuda_error(e, "cudaFuncSetAttribute", __LINE__);                                      \
+        const int g = flat_grid(T, resident_blocks(p, k_grid_pass2_tma<K, F>, smem_tma));                                        \
+        k_grid_pass2_tma<K, F><<<g, GR_THREADS, smem_tma, st>>>(S, T, first, count, logp, aux, best, log_rel, partial, acc,       \
+                                                                 ticket);                                                         \
+    }
 #define G2(K)                                                                                                                    \
     case K: {                                                                                                                    \
         if (fuse) {                                                                                                              \
             cudaError_t e = cudaMemsetAsync(aux.colsum, 0, (size_t)((char*)aux.valid - (char*)aux.colsum), st);                   \
             if (e != cudaSuccess) return pq_set_cuda_error(e, "cudaMemsetAsync", __LINE__);                                       \
-            e = pq_allow_smem((const void*)k_grid_pass2<K, true>, smem);                                                          \
+        }                                                                                                                        \
+        if (use_tma && fuse) {                                                                                                   \
+            const size_t sm2 = (size_t)P2_STAGES * P2_STAGE_DOUBLES * sizeof(double) + P2_KLIST * sizeof(KTile) +                 \
+                               (size_t)T.nchunks * GR_CH * sizeof(unsigned int);                                                   \
+            cudaError_t e = pq_allow_smem((const void*)k_grid_pass2_tma2<K>, sm2);                                                \
+            if (e != cudaSuccess) return pq_set_cuda_error(e, "cudaFuncSetAttribute", __LINE__);                                  \
+            const int g = flat_grid(T, resident_blocks(p, k_grid_pass2_tma2<K>, sm2));                                            \
+            k_grid_pass2_tma2<K><<<g, GR_THREADS, sm2, st>>>(S, T, first, count, logp, aux, best, log_rel, partial, acc, ticket);  \
+            k_grid_finish<K><<<16, GR_THREADS, 0, st>>>(S, T, first, logp, aux, best, log_rel, partial, acc, ticket);             \
+        } else if (use_tma) {                                                                                                    \
+            G2T(K, false)                                                                                                        \
+        } else if (fuse) {                                                                                                       \
+            cudaError_t e = pq_allow_smem((const void*)k_grid_pass2<K, true>, smem);                                             \
             if (e != cudaSuccess) return pq_set_cuda_error(e, "cudaFuncSetAttribute", __LINE__);                                  \
             const int g = flat_grid(T, resident_blocks(p, k_grid_pass2<K, true>, smem));                                         \
             k_grid_pass2<K, true><<<g, GR_THREADS, smem, st>>>(S, T, first, count, logp, aux, best, log_rel, partial, acc, ticket, \
@@ -800,6 +1421,7 @@ int pq_grid_pass2(const peuqse_problem* p, const DevSweep& S, long long first, l
         }                                                                                                                        \
     } break;
     switch (S.k) { G2(1) G2(2) G2(3) G2(4) G2(6) }
+#undef G2T
 #undef G2
     PQ_CUDA_OK(cudaGetLastError());
     return PEUQSE_OK;
@@ -810,14 +1432,14 @@ int pq_grid_hist(const peuqse_problem* p, const DevSweep& S, long long first, lo
                  void* aux_base, const peuqse_best* best, double log_rel, const double* edges, int nbins,
                  unsigned long long* hist, cudaStream_t st, bool* handled, bool use_fused_sums) {
     *handled = false;
-    GridAux aux = {nullptr, nullptr, nullptr, nullptr};
+    GridAux aux = {nullptr, nullptr, nullptr, nullptr, nullptr};
     GridTiling T;
     if (!logp || !aux_base || grid_aux_layout(p, S, first, count, (char*)aux_base, &aux) == 0) return PEUQSE_OK;
     grid_tiling(p, S, first, count, 1, &T);
     const size_t smem_bins = (size_t)S.k * nbins * sizeof(unsigned long long);
     if (use_fused_sums && pq_grid_pass2_fuses(p, S, first, count)) {
         *handled = true;
-#define GB(K) case K: k_grid_bin<K><<<32, GR_THREADS, smem_bins, st>>>(S, T, first, logp, aux, best, log_rel, edges, nbins, hist); break;
+#define GB(K) case K: k_grid_bin<K><<<40, GR_THREADS, smem_bins, st>>>(S, T, first, logp, aux, best, log_rel, edges, nbins, hist); break;
         switch (S.k) { GB(1) GB(2) GB(3) GB(4) GB(6) }
 #undef GB
         PQ_CUDA_OK(cudaGetLastError());

@@ -375,6 +375,41 @@ def test_grid_specialised_kernels_example00(env, radii):
         assert np.array_equal(sw.logp.cpu().numpy(), lp[sw.first:sw.first + sw.count])
     gb = D.merge_best(bests)
     assert gb == (best, idx)
+    # passes 2 and 3 per shard with the merged best record, reduced like the collectives would
+    from peuqse_b200 import _lib
+    lay = _lib.acc_layout(2)
+    tot = None
+    hist = np.zeros((2, 10), dtype=np.int64)
+    sws = []
+    for rnk in range(3):
+        sw = Sweep(PE.device_problem, spec, N, shard=(rnk, 3))
+        sw.pass1()
+        sw.best[0] = gb[0]
+        sw.best[1:2].view(torch.int64)[0] = gb[1]
+        sw.pass2(log_rel)
+        a = sw.acc.cpu().numpy()
+        if tot is None:
+            tot = a.copy()
+        else:
+            tot[:lay['MIN']] += a[:lay['MIN']]
+            tot[lay['MIN']:lay['MIN'] + 2] = np.minimum(tot[lay['MIN']:lay['MIN'] + 2], a[lay['MIN']:lay['MIN'] + 2])
+            tot[lay['MAX']:lay['MAX'] + 2] = np.maximum(tot[lay['MAX']:lay['MAX'] + 2], a[lay['MAX']:lay['MAX'] + 2])
+        sws.append(sw)
+    assert tot[lay['W']] == w.sum() and tot[lay['NKEPT']] == int((w > 0).sum())
+    np.testing.assert_allclose(th[idx] + tot[lay['S1']:lay['S1'] + 2] / tot[lay['W']], st['mu_AP'], rtol=1e-12)
+    for sw in sws:                         # every rank bins with the globally reduced min/max
+        sw.acc.copy_(torch.from_numpy(tot).cuda())
+        sw.pass3(log_rel, reuse_pass2_sums=True)
+        hist += sw.hist.cpu().numpy().reshape(2, 10)
+    assert np.array_equal(hist, st['hist'].astype(np.int64))
+    # stand-alone histogram pass (no fused sums) gives the same counts
+    sw = sws[0]
+    sw.pass3(log_rel, reuse_pass2_sums=False)
+    h0 = sw.hist.cpu().numpy().reshape(2, 10).copy()
+    sw.pass2(log_rel)
+    sw.acc.copy_(torch.from_numpy(tot).cuda())
+    sw.pass3(log_rel, reuse_pass2_sums=True)
+    assert np.array_equal(h0, sw.hist.cpu().numpy().reshape(2, 10))
 
 
 def test_grid_specialised_linear_k3(env):
