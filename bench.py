@@ -335,7 +335,7 @@ def run_ours(args):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one pass-1 launch from the committed ncu --set full capture
 # (profiles/); None until a capture exists.
-TRAFFIC_PASS1 = None
+TRAFFIC_PASS1 = 743.6e6   # 0.65 MB read + 742.95 MB written (profiles/r1_ncu_full_pass1_pass2_final_raw.csv); algorithmic 800.2 MB
 
 
 def main():

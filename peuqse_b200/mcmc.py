@@ -244,6 +244,12 @@ def calculate_info_gain(pe):
 # ensemble slice sampling
 # ----------------------------------------------------------------------------------------------
 def ess_launch(pe, start, n_iters, seed, mu0=1.0, tune=True, max_rounds=10000, first_iter=0, store_chain=True):
+    """Ensemble slice sampling of `n_iters` ensemble iterations from walkers start[W,k].
+    Built-in model + diagonal responses: the per-walker CUDA kernels (peuqse_ess_run).  Torch-callable simulators or
+    full-covariance responses: the round-synchronous driver below (every round is one batched log-posterior launch)."""
+    from .models import BuiltinModel
+    if not isinstance(pe.simulator, BuiltinModel) or int(pe.host_problem.resp_mode.max()) == _lib.RESP_MVN_FULL:
+        return ess_batched(pe, start, n_iters, seed, mu0=mu0, tune=tune, max_rounds=max_rounds, store_chain=store_chain)
     L = _lib.load()
     dev = _dev()
     X = torch.as_tensor(np.asarray(start, dtype=float), dtype=torch.float64).reshape(-1, pe.k).to(dev).contiguous()
@@ -257,10 +263,102 @@ def ess_launch(pe, start, n_iters, seed, mu0=1.0, tune=True, max_rounds=10000, f
     chain = torch.empty((n_iters, W, k), dtype=torch.float64, device=dev) if store_chain else None
     chain_lp = torch.empty((n_iters, W), dtype=torch.float64, device=dev) if store_chain else None
     info = torch.zeros(8, dtype=torch.float64, device=dev)
-    work = torch.empty(int(L.peuqse_ess_work_bytes(W, k)), dtype=torch.uint8, device=dev)
+    work = torch.zeros(int(L.peuqse_ess_work_bytes(W, k)), dtype=torch.uint8, device=dev)
     _lib.check(L.peuqse_ess_run(pe.device_problem.handle, C.byref(spec), _lib.ptr(X), _lib.ptr(Z), _lib.ptr(chain),
                                 _lib.ptr(chain_lp), _lib.ptr(info), _lib.ptr(work), _lib.current_stream()))
-    pe.gpu_launches += 2 * int(n_iters) + 1
+    pe.gpu_launches += 5 * int(n_iters) + 3
+    if int(info[4].item()) != 0:
+        raise RuntimeError("Number of expansions / contractions exceeded maximum limit! Increase mcmc_maxiter.")
+    return dict(X=X, Z=Z, chain=chain, chain_logp=chain_lp, info=info)
+
+
+def ess_batched(pe, start, n_iters, seed, mu0=1.0, tune=True, max_rounds=10000, store_chain=True, maxsteps=10000,
+                tolerance=0.05, patience=5):
+    """Round-synchronous ensemble slice sampling (same algorithm as csrc/ess.cu) for simulators / likelihoods that must
+    be evaluated in batches: every stepping-out or shrink round gathers the still-active walkers and evaluates their
+    log-posteriors with ONE batched launch (pe.getLogP_batch -> full-covariance contraction for C4)."""
+    dev = _dev()
+    g = torch.Generator(device=dev)
+    g.manual_seed(int(seed) & (2 ** 63 - 1))
+    X = torch.as_tensor(np.asarray(start, dtype=float), dtype=torch.float64).reshape(-1, pe.k).to(dev).contiguous()
+    W, k = X.shape
+    H = W // 2
+    Z = pe.getLogP_batch(X).clone()
+    if not bool(torch.isfinite(Z).all().item()):
+        raise ValueError("Invalid walker initial positions! Initialise walkers from positions of finite log probability.")
+    chain = torch.empty((n_iters, W, k), dtype=torch.float64, device=dev) if store_chain else None
+    chain_lp = torch.empty((n_iters, W), dtype=torch.float64, device=dev) if store_chain else None
+    mu, ncount, neval, tot_exp, tot_con = float(mu0), 0, W, 0, 0
+    rnd = lambda n: torch.rand(n, dtype=torch.float64, device=dev, generator=g)
+    for it in range(n_iters):
+        perm = torch.randperm(W, device=dev, generator=g)
+        nexp = ncon = 0
+        for half in (0, 1):
+            act, comp = perm[half * H:(half + 1) * H], perm[(1 - half) * H:(2 - half) * H]
+            i1 = torch.clamp((rnd(H) * H).long(), max=H - 1)
+            i2 = torch.clamp((rnd(H) * (H - 1)).long(), max=H - 2)
+            i2 = i2 + (i2 >= i1).long()
+            dirs = 2.0 * mu * (X[comp[i1]] - X[comp[i2]])
+            X0 = X[act]
+            Z0 = Z[act] + torch.log1p(-rnd(H))                    # logP - Exp(1)
+            Lb = -rnd(H)
+            Rb = Lb + 1.0
+            J = torch.floor(maxsteps * rnd(H))
+            K = (maxsteps - 1.0) - J
+            for side in (0, 1):                                   # stepping out: left, then right
+                B, cnt = (Lb, J) if side == 0 else (Rb, K)
+                mask = cnt >= 1
+                rounds = 0
+                while bool(mask.any().item()):
+                    idx = mask.nonzero(as_tuple=True)[0]
+                    z = pe.getLogP_batch(X0[idx] + B[idx, None] * dirs[idx])
+                    neval += idx.numel()
+                    grow = Z0[idx] < z
+                    gi = idx[grow]
+                    B[gi] += (-1.0 if side == 0 else 1.0)
+                    cnt[gi] -= 1.0
+                    nexp += int(grow.sum().item())
+                    mask[idx[~grow]] = False
+                    mask &= cnt >= 1
+                    rounds += 1
+                    if rounds > max_rounds:
+                        raise RuntimeError("Number of expansions exceeded maximum limit! Increase mcmc_maxiter.")
+            mask = torch.ones(H, dtype=torch.bool, device=dev)
+            Xn, Zn = X0.clone(), Z[act].clone()
+            rounds = 0
+            while bool(mask.any().item()):                        # shrinking
+                idx = mask.nonzero(as_tuple=True)[0]
+                wd = Lb[idx] + rnd(idx.numel()) * (Rb[idx] - Lb[idx])
+                cand = X0[idx] + wd[:, None] * dirs[idx]
+                z = pe.getLogP_batch(cand)
+                neval += idx.numel()
+                ok = Z0[idx] < z
+                Xn[idx[ok]] = cand[ok]
+                Zn[idx[ok]] = z[ok]
+                mask[idx[ok]] = False
+                rej, wr = idx[~ok], wd[~ok]
+                Lb[rej[wr < 0]] = wr[wr < 0]
+                Rb[rej[wr > 0]] = wr[wr > 0]
+                ncon += int((~ok).sum().item())
+                rounds += 1
+                if rounds > max_rounds:
+                    raise RuntimeError("Number of contractions exceeded maximum limit! Increase mcmc_maxiter.")
+            X[act] = Xn
+            Z[act] = Zn
+        tot_exp += nexp
+        tot_con += ncon
+        if tune:
+            ne = max(1, nexp)
+            frac = ne / (ne + ncon)
+            mu *= 2.0 * frac
+            if abs(frac - 0.5) < tolerance:
+                ncount += 1
+            if ncount > patience:
+                tune = False
+        if store_chain:
+            chain[it] = X
+            chain_lp[it] = Z
+    info = torch.tensor([neval, mu, tot_exp, tot_con, 0, 0, 0, 0], dtype=torch.float64, device=dev)
     return dict(X=X, Z=Z, chain=chain, chain_logp=chain_lp, info=info)
 
 

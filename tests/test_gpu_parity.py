@@ -438,3 +438,91 @@ def test_grid_specialised_linear_k3(env):
     np.testing.assert_allclose(PE.mu_AP_parameter_set, st['mu_AP'], rtol=1e-11)
     np.testing.assert_allclose(PE.stdap_parameter_set, st['stdap'], rtol=1e-9)
     assert np.array_equal(PE.marginal_histograms[0], st['hist'].astype(np.int64))
+
+
+def _linear_gaussian_case(orc, k=4, n=30, sig=0.3, seed=3):
+    rng = np.random.default_rng(seed)
+    Phi = orc.cos_basis(n, k)
+    truth = rng.standard_normal(k)
+    y = Phi @ truth + sig * rng.standard_normal(n)
+    mean, cov = orc.linear_gaussian_posterior(Phi, Phi / sig ** 2, y, 4.0)
+    return Phi, y, mean, cov
+
+
+def test_ess_kernel_linear_gaussian(env):
+    """Ensemble slice sampling kernels (parity unpinned: zeus is not available) against the closed-form posterior of
+    a linear-Gaussian problem, within Monte-Carlo error."""
+    PEUQSE, orc, _, torch = env
+    k, n, sig = 4, 30, 0.3
+    Phi, y, mean, cov = _linear_gaussian_case(orc, k, n, sig)
+    PE = make_pe(PEUQSE, PEUQSE.LinearModel(Phi), list(y), list(np.full(n, sig)), [0.0] * k, [2.0] * k,
+                 settings={'mcmc_length': 64 * 1500, 'mcmc_nwalkers': 64, 'mcmc_burn_in': 64 * 300, 'mcmc_random_seed': 11,
+                           'mcmc_threshold_filter_samples': False, 'mcmc_info_gain_returned': 'log_ratio'})
+    res = PE.doEnsembleSliceSampling()
+    S = PE.post_burn_in_samples
+    assert S.shape == (64 * 1200, k) and len(res) == 7
+    assert PE.discrete_chains_post_burn_in_samples.shape == (1200, 64, k)
+    ess_n = len(S) / 10.0                                   # generous autocorrelation allowance
+    se = np.sqrt(np.diag(cov) / ess_n)
+    assert np.all(np.abs(S.mean(axis=0) - mean) < 5 * se), (S.mean(axis=0), mean, se)
+    d = np.sqrt(np.diag(cov))
+    np.testing.assert_allclose(np.cov(S.T) / np.outer(d, d), cov / np.outer(d, d), atol=0.08)
+    # stored logP of the chain is the logP of the stored positions
+    lp = PE.getLogP_batch(S[:500]).cpu().numpy()
+    np.testing.assert_allclose(lp, PE.post_burn_in_log_posteriors_un_normed_vec[:500, 0], rtol=1e-13)
+    assert PE.ess_info['n_logp_evaluations'] > 64 * 1500 and 0.05 < PE.ess_info['mu'] < 50
+    # same seed -> same chain (counter-based RNG), different seed -> different chain
+    from peuqse_b200.mcmc import ess_launch
+    start = PE.discrete_chains_post_burn_in_samples[-1]
+    a = ess_launch(PE, start, 20, 5)['chain'].cpu().numpy()
+    b = ess_launch(PE, start, 20, 5)['chain'].cpu().numpy()
+    c = ess_launch(PE, start, 20, 6)['chain'].cpu().numpy()
+    assert np.array_equal(a, b) and not np.array_equal(a, c)
+
+
+def test_ess_batched_full_covariance(env):
+    """Round-synchronous ESS driver + full-covariance contraction (the C4 path at a small size): two responses with
+    dense covariance, posterior mean/cov against the closed form."""
+    PEUQSE, orc, _, torch = env
+    rng = np.random.default_rng(21)
+    k, n = 3, 24
+    Phi = orc.cos_basis(2 * n, k)
+    x = np.linspace(0, 1, n)
+    Sig = 0.1 ** 2 * np.exp(-(x[:, None] - x[None, :]) ** 2 / (2 * 0.05 ** 2)) + 0.05 ** 2 * np.eye(n)
+    truth = rng.standard_normal(k)
+    Lc = np.linalg.cholesky(Sig)
+    y = Phi @ truth + np.concatenate([Lc @ rng.standard_normal(n), Lc @ rng.standard_normal(n)])
+    Sinv = np.linalg.inv(Sig)
+    big = np.block([[Sinv, np.zeros((n, n))], [np.zeros((n, n)), Sinv]])
+    mean, cov = orc.linear_gaussian_posterior(Phi, big @ Phi, y, 4.0)
+    PE = make_pe(PEUQSE, PEUQSE.LinearModel(Phi), [list(y[:n]), list(y[n:])], [Sig, Sig], [0.0] * k, [2.0] * k,
+                 settings={'mcmc_length': 32 * 700, 'mcmc_nwalkers': 32, 'mcmc_burn_in': 32 * 200, 'mcmc_random_seed': 4,
+                           'mcmc_threshold_filter_samples': False, 'mcmc_info_gain_returned': 'log_ratio'})
+    # per-point parity of the full-covariance likelihood against scipy's logpdf (what IP.py:2960 computes)
+    from scipy.stats import multivariate_normal as mvn
+    th = truth + 0.1 * rng.standard_normal((20, k))
+    want = np.array([mvn.logpdf(x=y[:n], mean=(Phi @ t)[:n], cov=Sig) + mvn.logpdf(x=y[n:], mean=(Phi @ t)[n:], cov=Sig) for t in th])
+    _, _, ll = parts(PE, th)
+    np.testing.assert_allclose(ll, want, rtol=1e-12)
+    PE.doEnsembleSliceSampling()
+    S = PE.post_burn_in_samples
+    se = np.sqrt(np.diag(cov) / (len(S) / 10.0))
+    assert np.all(np.abs(S.mean(axis=0) - mean) < 5 * se)
+    d = np.sqrt(np.diag(cov))
+    np.testing.assert_allclose(np.cov(S.T) / np.outer(d, d), cov / np.outer(d, d), atol=0.12)
+
+
+def test_ess_warp_shape_tpd(env, golden):
+    PEUQSE, orc, _, _ = env
+    g = golden("tpd")
+    n = 1024
+    PE = make_pe(PEUQSE, PEUQSE.Tpd2SiteModel.linear_ramp(n), list(g['tpd1024_y']), list(np.full(n, float(g['tpd1024_sigma']))),
+                 [41.5, 41.5, 13.0, 13.0, 0.1, 0.1], [20, 20, 13, 13, 0.1, 0.1])
+    from peuqse_b200.mcmc import ess_launch
+    truth = np.array([41.5, 45, 13, 13, 0.1, 0.1])
+    start = truth + 1e-3 * np.array([20, 20, 13, 13, 0.1, 0.1]) * np.random.default_rng(2).standard_normal((24, 6))
+    out = ess_launch(PE, start, 30, 9)
+    Z = out['chain_logp'].cpu().numpy()
+    assert np.all(np.isfinite(Z)) and Z[-1].mean() > Z[0].mean() - 5
+    lp = PE.getLogP_batch(out['chain'][-1]).cpu().numpy()
+    np.testing.assert_allclose(lp, Z[-1], rtol=1e-12)
