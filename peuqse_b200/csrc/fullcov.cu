@@ -56,6 +56,109 @@ __global__ void __launch_bounds__(QF_THREADS) k_quadform(const double* __restric
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// v1: tensor-core contraction.  T[B,n] = Rsd[B,n] @ U[n,n] with DMMA (mma.sync.m8n8k4 f64 -- there is no tcgen05 kind
+// for fp64), fused with the row-wise sum of squares so that T is never written: every CTA owns a 64 x 64 tile of T,
+// loops over K in steps of 16 with register-prefetched, double-buffered shared-memory tiles (the residual y - sim
+// is formed while staging A), squares its accumulators and writes one partial row sum per (column tile, row).
+// A second tiny kernel adds the partials in fixed order: ll_b += -0.5*(c + sum).
+// ---------------------------------------------------------------------------------------------------
+#define QD_BM 64
+#define QD_BN 64
+#define QD_BK 16
+#define QD_LDA (QD_BK + 4)     // padded leading dimensions: operand fragment loads hit every bank exactly twice
+#define QD_LDB (QD_BN + 8)
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256) k_quadform_dmma(const double* __restrict__ sim, int ld_sim, int off,
+                                                      const int* __restrict__ src, const double* __restrict__ y,
+                                                      const double* __restrict__ U, int n, long long B,
+                                                      double* __restrict__ partial /* [gridDim.x][B] */) {
+    __shared__ double As[2][QD_BM][QD_LDA];
+    __shared__ double Bs[2][QD_BK][QD_LDB];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 2, wn = warp & 3;                   // 2 x 4 warps: each owns 32 x 16 of the 64 x 64 tile
+    const long long bm = (long long)blockIdx.y * QD_BM;
+    const int bn = blockIdx.x * QD_BN;
+    // staging assignments: A tile 64 x 16 (thread -> row ar, 4 consecutive k), B tile 16 x 64 (thread -> row br, 4 consecutive cols)
+    const int ar = tid >> 2, ak = (tid & 3) * 4;
+    const int br = tid >> 4, bc = (tid & 15) * 4;
+    const long long arow = bm + ar;
+    double ra[4], rb[4];
+    auto load_tiles = [&](int k0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int kk = k0 + ak + q;
+            ra[q] = (arow < B && kk < n) ? (y[off + kk] - sim[arow * ld_sim + src[off + kk]]) : 0.0;   // x - mean (IP.py:2960)
+            const int kb = k0 + br, cc = bn + bc + q;
+            rb[q] = (kb < n && cc < n) ? __ldg(U + (size_t)kb * n + cc) : 0.0;
+        }
+    };
+    auto store_tiles = [&](int st) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            As[st][ar][ak + q] = ra[q];
+            Bs[st][br][bc + q] = rb[q];
+        }
+    };
+    double acc[4][2][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const int nk = (n + QD_BK - 1) / QD_BK;
+    load_tiles(0);
+    store_tiles(0);
+    __syncthreads();
+    for (int kt = 0; kt < nk; ++kt) {
+        const int st = kt & 1;
+        if (kt + 1 < nk) load_tiles((kt + 1) * QD_BK);           // global loads of the next tile fly during the MMAs
+#pragma unroll
+        for (int ks = 0; ks < QD_BK; ks += 4) {
+            double af[4], bf[2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) af[i] = As[st][wm * 32 + i * 8 + (lane >> 2)][ks + (lane & 3)];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) bf[j] = Bs[st][ks + (lane & 3)][wn * 16 + j * 8 + (lane >> 2)];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+        if (kt + 1 < nk) store_tiles(st ^ 1);
+        __syncthreads();
+    }
+    // row-wise sum of squares of this CTA's 64 columns -> partial[blockIdx.x][row]
+    __shared__ double s_row[4][QD_BM];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) s = fma(acc[i][j][0], acc[i][j][0], fma(acc[i][j][1], acc[i][j][1], s));
+        s += __shfl_xor_sync(0xffffffffu, s, 1);                   // the 4 lanes of a row group hold different columns
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if ((lane & 3) == 0) s_row[wn][wm * 32 + i * 8 + (lane >> 2)] = s;
+    }
+    __syncthreads();
+    if (tid < QD_BM) {
+        const long long row = bm + tid;
+        if (row < B) partial[(size_t)blockIdx.x * B + row] = ((s_row[0][tid] + s_row[1][tid]) + s_row[2][tid]) + s_row[3][tid];
+    }
+}
+
+__global__ void k_quadform_reduce(const double* __restrict__ partial, int ntn, long long B, double c, double* __restrict__ ll) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double m = 0.0;
+    for (int t = 0; t < ntn; ++t) m += partial[(size_t)t * B + b];     // fixed order
+    ll[b] = ll[b] + (-0.5 * (c + m));
+}
+
 __global__ void k_fullcov_finish(long long B, const double* __restrict__ lp, double* __restrict__ ll,
                                  double* __restrict__ logp) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -83,15 +186,16 @@ int pq_fullcov_logp(const peuqse_problem* p, const double* d_theta, const double
         for (int r = 0; r < p->d.n_resp && rc == PEUQSE_OK; ++r) {
             if (p->d.resp_mode[r] != PEUQSE_RESP_MVN_FULL) continue;
             const int n = p->d.resp_n[r];
-            const size_t smem = (size_t)QF_ROWS * n * sizeof(double);
-            if (smem > (size_t)p->max_smem_optin) { rc = pq_set_error(PEUQSE_ERR_INVALID, "full-covariance response too long for the v0 contraction"); break; }
-            cudaError_t e = pq_allow_smem((const void*)k_quadform, smem);
-            if (e != cudaSuccess) { rc = pq_set_cuda_error(e, "cudaFuncSetAttribute", __LINE__); break; }
-            const unsigned blocks = (unsigned)((B + QF_ROWS - 1) / QF_ROWS);
-            k_quadform<<<blocks, QF_THREADS, smem, st>>>(d_sim, p->d.n_total, p->d.resp_off[r], p->d.src, p->d.y, p->d.U[r], n,
-                                                       p->d.resp_c[r], B, ll);
+            const int ntn = (n + QD_BN - 1) / QD_BN;
+            double* part = nullptr;
+            cudaError_t e = cudaMallocAsync((void**)&part, (size_t)ntn * B * sizeof(double), st);
+            if (e != cudaSuccess) { rc = pq_set_cuda_error(e, "cudaMallocAsync(quadform partials)", __LINE__); break; }
+            const dim3 grid((unsigned)ntn, (unsigned)((B + QD_BM - 1) / QD_BM));
+            k_quadform_dmma<<<grid, 256, 0, st>>>(d_sim, p->d.n_total, p->d.resp_off[r], p->d.src, p->d.y, p->d.U[r], n, B, part);
+            k_quadform_reduce<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(part, ntn, B, p->d.resp_c[r], ll);
             e = cudaGetLastError();
-            if (e != cudaSuccess) rc = pq_set_cuda_error(e, "k_quadform", __LINE__);
+            cudaFreeAsync(part, st);
+            if (e != cudaSuccess) rc = pq_set_cuda_error(e, "k_quadform_dmma", __LINE__);
         }
         if (rc == PEUQSE_OK) {
             k_fullcov_finish<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(B, lp, ll, d_logp);

@@ -16,6 +16,7 @@ def ev_time(fn, n=3, warm=1):
 
 def make(model, obs, unc, mu, sd, **pes):
     UI = PEUQSE.UserInput.fresh()
+    UI.responses['responses_observed_max_covmat_size'] = 5000
     UI.responses['responses_observed'] = obs; UI.responses['responses_observed_uncertainties'] = unc
     UI.model['InputParameterPriorValues'] = mu; UI.model['InputParametersPriorValuesUncertainties'] = sd
     UI.model['simulateByInputParametersOnlyFunction'] = model
@@ -24,7 +25,7 @@ def make(model, obs, unc, mu, sd, **pes):
     return PEUQSE.parameter_estimation(UI)
 
 out = {}
-which = sys.argv[1:] or ["c1", "c3", "c5"]
+which = sys.argv[1:] or ["c1", "c3", "c5", "c4"]
 if "c1" in which:
     PE = make(PEUQSE.QuadraticModel([600, 1100, 1400]), [360500, 580500, 1620500], [200000, 300000, 200000], [200, 500], [100, 200])
     C, Lm = 65536, 2000
@@ -68,4 +69,22 @@ if "c5" in which:
     ms = ev_time(sw.pass1, n=2)
     out["c5_pass1_evals_per_s"] = N / (ms * 1e-3)
     out["c5_pass1_ms_for_2^27"] = ms
+if "c4" in which:
+    from oracle import peuqse_oracle as orc
+    k, n = 12, 4096
+    x = np.linspace(0, 1, n)
+    Phi = orc.cos_basis(2 * n, k)
+    Sig = 0.1 ** 2 * np.exp(-(x[:, None] - x[None, :]) ** 2 / (2 * 0.02 ** 2)) + 0.05 ** 2 * np.eye(n)
+    truth = np.random.default_rng(1).standard_normal(k)
+    y = Phi @ truth + 0.1 * np.random.default_rng(2).standard_normal(2 * n)
+    t0 = time.time()
+    PE = make(PEUQSE.LinearModel(Phi), [list(y[:n]), list(y[n:])], [Sig, Sig], [0.0] * k, [2.0] * k)
+    PE.UserInput  # noqa
+    out["c4_host_setup_s"] = time.time() - t0
+    B = 1024
+    th = torch.from_numpy(truth + 0.05 * np.random.default_rng(3).standard_normal((B, k))).cuda()
+    ms = ev_time(lambda: PE.getLogP_batch(th), n=5)
+    out["c4_logp_batch_ms_B1024_two_4096_responses"] = ms
+    out["c4_evals_per_s"] = B / (ms * 1e-3)
+    out["c4_dmma_tflops_executed"] = 2 * (2.0 * B * n * n) / (ms * 1e-3) / 1e12
 print(json.dumps(out, indent=1))

@@ -526,3 +526,42 @@ def test_ess_warp_shape_tpd(env, golden):
     assert np.all(np.isfinite(Z)) and Z[-1].mean() > Z[0].mean() - 5
     lp = PE.getLogP_batch(out['chain'][-1]).cpu().numpy()
     np.testing.assert_allclose(lp, Z[-1], rtol=1e-12)
+
+
+def test_fullcov_dmma_contraction(env):
+    """DMMA quadratic form at sizes that are not multiples of the tile (n_r = 520, B = 130), two responses with dense
+    covariances (the reference's working full-covariance route), against scipy's logpdf per point and the
+    oracle batch; also through a torch-callable simulator."""
+    PEUQSE, orc, _, torch = env
+    from scipy.stats import multivariate_normal as mvn
+    rng = np.random.default_rng(31)
+    k, n = 5, 520
+    x = np.linspace(0, 1, n)
+    Phi = orc.cos_basis(2 * n, k)
+    covs = []
+    for ell in (0.02, 0.05):
+        covs.append(0.1 ** 2 * np.exp(-(x[:, None] - x[None, :]) ** 2 / (2 * ell ** 2)) + 0.05 ** 2 * np.eye(n))
+    truth = rng.standard_normal(k)
+    y = Phi @ truth + 0.1 * rng.standard_normal(2 * n)
+    B = 130
+    th = truth + 0.05 * rng.standard_normal((B, k))
+    P = orc.build_problem([0.0] * k, [2.0] * k, [y[:n], y[n:]], covs, max_covmat_size=600)
+    _, bt = orc.sim_linear(Phi)
+    want = orc.log_p_batch(P, th, lambda t: [bt(t)[:, :n], bt(t)[:, n:]])
+    Phi_t = torch.from_numpy(Phi).cuda()
+    for model in (PEUQSE.LinearModel(Phi), PEUQSE.TorchSimulator(lambda t, Pm=Phi_t: t @ Pm.T)):
+        PE = make_pe(PEUQSE, model, [list(y[:n]), list(y[n:])], covs, [0.0] * k, [2.0] * k,
+                     settings={'responses_observed_max_covmat_size': 600})
+        lp, pr, ll = parts(PE, th)
+        np.testing.assert_allclose(ll, want[2], rtol=1e-12)
+        np.testing.assert_allclose(lp, want[0], rtol=1e-12)
+        assert np.array_equal(pr, want[1])
+    for i in (0, 7, 129):
+        s = Phi @ th[i]
+        ref = mvn.logpdf(x=y[:n], mean=s[:n], cov=covs[0]) + mvn.logpdf(x=y[n:], mean=s[n:], cov=covs[1])
+        np.testing.assert_allclose(ll[i], ref, rtol=1e-12)
+    # NaN parameter: logLik = -inf (NaN simulated values, IP.py:2880-2882); logP = -inf + NaN prior = NaN as in the reference
+    bad = th.copy()
+    bad[3, 0] = np.nan
+    lpb, _, llb = parts(PE, bad)
+    assert llb[3] == float('-inf') and np.isnan(lpb[3]) and np.array_equal(np.delete(lpb, 3), np.delete(lp, 3))
