@@ -217,6 +217,14 @@ int peuqse_sweep_hist(const peuqse_problem* p, const peuqse_sweep_spec* spec, in
                       const double* d_edges, int32_t nbins, uint64_t* d_hist, void* d_work, int32_t reuse_pass2_sums,
                       void* stream);
 
+/*
+ * Multi-GPU merges (replace consolidate_parallel_sampling_data's "keep the best" / stacking, IP.py:1209-1319):
+ * d_all holds the all-gathered per-rank records; the merged record is what a single process would have produced
+ * (highest logP, lowest index among equals; sums added in rank order, min/max slots reduced accordingly).
+ */
+int peuqse_merge_best(const peuqse_best* d_all /*[n]*/, int32_t n, peuqse_best* d_out, void* stream);
+int peuqse_merge_acc(const double* d_all /*[n][PEUQSE_ACC_DOUBLES(k)]*/, int32_t n, int32_t k, double* d_out, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Metropolis-Hastings: doMetropolisHastings (IP.py:2563-2754), C independent chains
  * (mcmc_parallel_sampling, IP.py:1282-1319) advanced by one persistent kernel.

@@ -574,6 +574,53 @@ extern "C" int peuqse_sweep_best_point(const peuqse_sweep_spec* spec, const peuq
     return PEUQSE_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// multi-GPU merges: the all-gathered per-rank records are combined by one tiny kernel each
+// ---------------------------------------------------------------------------------------------
+__global__ void k_merge_best(const peuqse_best* __restrict__ all, int n, peuqse_best* __restrict__ out) {
+    Best b = best_none();
+    for (int r = threadIdx.x; r < n; r += 32) {
+        Best o;
+        o.v = all[r].logp;
+        o.i = all[r].index < 0 ? 0x7fffffffffffffffLL : all[r].index;
+        if (all[r].index < 0) o.v = pq_neg_inf();
+        b = best_merge(b, o);
+    }
+    b = warp_best(b);
+    if (threadIdx.x == 0) {
+        out->logp = b.v;
+        out->index = (b.i == 0x7fffffffffffffffLL) ? -1 : b.i;
+    }
+}
+
+__global__ void k_merge_acc(const double* __restrict__ all, int n, int k, double* __restrict__ out) {
+    const int nacc = PEUQSE_ACC_DOUBLES(k), mn0 = PEUQSE_ACC_MIN(k), mx0 = PEUQSE_ACC_MAX(k);
+    for (int a = threadIdx.x; a < nacc; a += blockDim.x) {
+        double r = all[a];
+        for (int q = 1; q < n; ++q) {                      // fixed rank order: identical result on every rank
+            const double x = all[(size_t)q * nacc + a];
+            if (a >= mx0) r = fmax(r, x);
+            else if (a >= mn0) r = fmin(r, x);
+            else r += x;
+        }
+        out[a] = r;
+    }
+}
+
+extern "C" int peuqse_merge_best(const peuqse_best* d_all, int32_t n, peuqse_best* d_out, void* stream) {
+    if (!d_all || !d_out || n < 1) return pq_set_error(PEUQSE_ERR_INVALID, "bad merge_best arguments");
+    k_merge_best<<<1, 32, 0, (cudaStream_t)stream>>>(d_all, n, d_out);
+    PQ_CUDA_OK(cudaGetLastError());
+    return PEUQSE_OK;
+}
+
+extern "C" int peuqse_merge_acc(const double* d_all, int32_t n, int32_t k, double* d_out, void* stream) {
+    if (!d_all || !d_out || n < 1 || k < 1 || k > PQ_MAXK) return pq_set_error(PEUQSE_ERR_INVALID, "bad merge_acc arguments");
+    k_merge_acc<<<1, 128, 0, (cudaStream_t)stream>>>(d_all, n, k, d_out);
+    PQ_CUDA_OK(cudaGetLastError());
+    return PEUQSE_OK;
+}
+
 // raw Philox blocks (tests): d_out[count][4]
 __global__ void k_philox_blocks(unsigned long long seed, uint32_t stream_id, long long first, long long count,
                                 uint32_t block, uint32_t* __restrict__ out) {

@@ -86,19 +86,14 @@ class Sweep:
         self.launches += 1
 
     def _merge_best(self):
-        """all-gather of the 16-byte (maxLogP, index) records; highest value, lowest index among equals."""
+        """all-gather of the 16-byte (maxLogP, index) records + one merge kernel (highest value, lowest index among equals)."""
         import torch.distributed as dist
-        g = torch.empty((self.world, 2), dtype=torch.float64, device=self.dev)
-        dist.all_gather_into_tensor(g, self.best.reshape(1, 2).contiguous())
-        vals = g[:, 0]
-        idx = g[:, 1].contiguous().view(torch.int64)
-        valid = idx >= 0
-        m = torch.where(valid, vals, torch.full_like(vals, float("-inf"))).max()
-        cand = torch.where(valid & (vals == m), idx, torch.full_like(idx, torch.iinfo(torch.int64).max))
-        bi = cand.min()
-        none = bi == torch.iinfo(torch.int64).max
-        self.best[0] = m
-        self.best[1:2].view(torch.int64)[0] = torch.where(none, torch.full_like(bi, -1), bi)
+        if not hasattr(self, "_g_best"):
+            self._g_best = torch.empty((self.world, 2), dtype=torch.float64, device=self.dev)
+            self._g_acc = torch.empty((self.world, self.lay["SIZE"]), dtype=torch.float64, device=self.dev)
+        dist.all_gather_into_tensor(self._g_best, self.best.reshape(1, 2))
+        _lib.check(self.L.peuqse_merge_best(_lib.ptr(self._g_best), self.world, _lib.ptr(self.best), _lib.current_stream()))
+        self.launches += 1
 
     def pass2(self, log_rel, keep=None):
         self.acc.copy_(self.acc_init)
@@ -112,13 +107,13 @@ class Sweep:
                                              _lib.ptr(self.logp), _lib.ptr(self.best), float(log_rel), _lib.ptr(self.acc),
                                              _lib.ptr(kidx), _lib.ptr(klogp), cap, _lib.ptr(kcount), _lib.ptr(self.work),
                                              _lib.current_stream()))
-        self.launches += 1
-        if self.world > 1:
+        self.launches += 2                                  # main kernel + finish kernel
+        if self.world > 1:                                  # one all-gather + one merge kernel (sum / min / max by slot)
             import torch.distributed as dist
-            lay, k = self.lay, self.k
-            dist.all_reduce(self.acc[:lay["MIN"]], op=dist.ReduceOp.SUM)
-            dist.all_reduce(self.acc[lay["MIN"]:lay["MIN"] + k], op=dist.ReduceOp.MIN)
-            dist.all_reduce(self.acc[lay["MAX"]:lay["MAX"] + k], op=dist.ReduceOp.MAX)
+            dist.all_gather_into_tensor(self._g_acc, self.acc.reshape(1, -1))
+            _lib.check(self.L.peuqse_merge_acc(_lib.ptr(self._g_acc), self.world, self.k, _lib.ptr(self.acc),
+                                               _lib.current_stream()))
+            self.launches += 1
 
     def pass3(self, log_rel, reuse_pass2_sums=True):
         _lib.check(self.L.peuqse_sweep_edges(_lib.ptr(self.acc), self.k, self.nbins, _lib.ptr(self.edges),

@@ -1,0 +1,66 @@
+"""Run under torchrun with N >= 2 GPUs: the sharded multistart / MH paths must reproduce the single-GPU results.
+(Launched by tests/test_multi_gpu.py; not collected by pytest itself.)"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import peuqse_b200 as PEUQSE
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "example00.npz"))
+X00, Y00, S00 = [600, 1100, 1400], [360500, 580500, 1620500], [200000, 300000, 200000]
+
+
+def make(settings):
+    UI = PEUQSE.UserInput.fresh()
+    UI.responses['responses_observed'] = Y00
+    UI.responses['responses_observed_uncertainties'] = S00
+    UI.model['InputParameterPriorValues'] = [200, 500]
+    UI.model['InputParametersPriorValuesUncertainties'] = [100, 200]
+    UI.model['simulateByInputParametersOnlyFunction'] = PEUQSE.QuadraticModel(X00)
+    UI.parameter_estimation_settings.update(settings)
+    return PEUQSE.parameter_estimation(UI)
+
+
+# 1. reference grid (generic kernels: short last axis), sharded over the ranks
+PE = make({'multistart_initialPointsDistributionType': 'grid', 'multistart_gridsearchSamplingInterval': [5, 5],
+           'multistart_gridsearchSamplingRadii': [50, 50]})
+PE.doMultiStart()
+assert PE.map_index == 13 and PE.map_logP == float(g['ex00_grid_map_logP'])
+assert PE.sweep_result.sum_weights == int(g['ex00_grid_nrows_expanded'])
+np.testing.assert_allclose(PE.mu_AP_parameter_set, g['ex00_grid_mu_AP'], rtol=1e-12)
+np.testing.assert_allclose(PE.stdap_parameter_set, g['ex00_grid_stdap'], rtol=1e-10)
+# 2. long last axis (specialised + TMA kernels), compared with a one-rank run of the same sweep on every rank
+settings = {'multistart_initialPointsDistributionType': 'grid', 'multistart_gridsearchSamplingInterval': [2.5, 0.4],
+            'multistart_gridsearchSamplingRadii': [37, 2900]}
+PE = make(settings)
+PE.doMultiStart()
+from peuqse_b200.sweep import Sweep, make_spec
+spec = make_spec("grid", 2, [200., 500.], interval=[2.5, 0.4], radii=[37, 2900])
+N = 75 * 5801
+one = Sweep(PE.device_problem, spec, N, shard=(0, 1))
+one.world = 1
+R1 = one.unpack(one_res := (one.step(float(np.log(1e-2))), one.res.cpu().numpy())[1], 2.0)
+assert PE.map_index == R1.map_index and PE.map_logP == R1.map_logP
+assert PE.sweep_result.sum_weights == R1.sum_weights and PE.sweep_result.n_retained == R1.n_retained
+np.testing.assert_allclose(PE.mu_AP_parameter_set, R1.mu_AP_parameter_set, rtol=1e-13)
+np.testing.assert_allclose(PE.stdap_parameter_set, R1.stdap_parameter_set, rtol=1e-11)
+assert np.array_equal(PE.marginal_histograms[0], R1.histogram_counts)
+# 3. MH chains sharded by global chain index: same pooled moments as one rank running all chains
+PE = make({'mcmc_length': 400, 'mcmc_burn_in': 100, 'mcmc_nchains': 64, 'mcmc_random_seed': 5, 'mcmc_relative_step_length': 0.5,
+           'mcmc_threshold_filter_samples': False, 'mcmc_info_gain_returned': 'log_ratio'})
+PE.doMetropolisHastings()
+from peuqse_b200.mcmc import mh_launch, step_cholesky, chain_moments
+all_ = mh_launch(PE, np.tile([200., 500.], (64, 1)), 400, 100, 5, step_cholesky(PE.Q_covmat, 0.5))
+S = all_['samples'][100:].permute(1, 0, 2).reshape(-1, 2).cpu().numpy()
+assert PE.post_burn_in_samples.shape == S.shape and np.array_equal(PE.post_burn_in_samples, S)
+dist.barrier()
+if rank == 0:
+    print("MGPU_OK", world)
+dist.destroy_process_group()

@@ -565,3 +565,95 @@ def test_fullcov_dmma_contraction(env):
     bad[3, 0] = np.nan
     lpb, _, llb = parts(PE, bad)
     assert llb[3] == float('-inf') and np.isnan(lpb[3]) and np.array_equal(np.delete(lpb, 3), np.delete(lp, 3))
+
+
+def test_c2_full_size_properties(env):
+    """BASELINE config C2 at full size (100 020 001 grid points): size-independent properties + spot checks."""
+    PEUQSE, orc, _, torch = env
+    c, h, r = [200., 500.], [0.08, 0.16], [5000, 5000]
+    PE = make_pe(PEUQSE, PEUQSE.QuadraticModel(X00), Y00, S00, [200, 500], [100, 200],
+                 settings={'multistart_initialPointsDistributionType': 'grid', 'multistart_gridsearchSamplingInterval': h,
+                           'multistart_gridsearchSamplingRadii': r})
+    PE.doMultiStart()
+    N = orc.grid_size(r)
+    assert N == 100020001 and PE.sweep_result.total == N
+    P = orc.build_problem([200, 500], [100, 200], Y00, S00)
+    _, bt = orc.sim_quadratic(X00)
+    sw = PE._sweep
+    # (i) the MAP point: decoded parameters and logP are the oracle's, bit for bit
+    th_map = orc.grid_decode(c, h, r, np.array([PE.map_index]))[0]
+    assert np.array_equal(th_map, PE.map_parameter_set)
+    assert orc.log_p_batch(P, th_map[None, :], bt)[0][0] == PE.map_logP
+    # (ii) 200 000 random indices (plus both ends) of the stored logP are bit-exact
+    rng = np.random.default_rng(0)
+    idx = np.unique(np.concatenate([rng.integers(0, N, 200000), [0, 1, 10000, 10001, 10002, N - 1]]))
+    got = sw.logp[torch.from_numpy(idx).cuda()].cpu().numpy()
+    assert np.array_equal(got, orc.log_p_batch(P, orc.grid_decode(c, h, r, idx), bt)[0])
+    # (iii) the maximum of the stored array is the reported MAP, at its first occurrence
+    m = sw.logp.max()
+    assert float(m.item()) == PE.map_logP
+    assert int(torch.nonzero(sw.logp == m)[0].item()) == PE.map_index
+    # (iv) weights: retained count and weight sum recomputed from the stored logP
+    thr = PE.sweep_result.threshold
+    kept = sw.logp > thr
+    assert int(kept.sum().item()) == PE.sweep_result.n_retained
+    wsum = float(torch.floor(torch.exp(sw.logp[kept] - thr)).sum().item())
+    assert abs(wsum - PE.sweep_result.sum_weights) <= 4          # two exp implementations may differ on a few exact-integer edges
+    # (v) every marginal histogram holds all the weight; edges span the retained range
+    H, E = PE.marginal_histograms
+    assert np.all(H.sum(axis=1) == int(PE.sweep_result.sum_weights))
+    assert np.array_equal(E[:, 0], PE.sweep_result.retained_min) and np.array_equal(E[:, -1], PE.sweep_result.retained_max)
+    # (vi) moments against a float64 torch reduction over the stored array (independent code path)
+    ii = torch.nonzero(kept)[:, 0]
+    th = sw.points(0, N)[ii]
+    w = torch.floor(torch.exp(sw.logp[ii] - thr))
+    mu = (w[:, None] * th).sum(0) / w.sum()
+    sd = torch.sqrt((w[:, None] * (th - mu) ** 2).sum(0) / w.sum())
+    np.testing.assert_allclose(PE.mu_AP_parameter_set, mu.cpu().numpy(), rtol=1e-9)
+    np.testing.assert_allclose(PE.stdap_parameter_set, sd.cpu().numpy(), rtol=1e-8)
+    # (vii) two-rank style sharding at full size gives the same best record
+    from peuqse_b200.sweep import Sweep, make_spec
+    from peuqse_b200 import distributed as D
+    spec = make_spec("grid", 2, c, interval=h, radii=r)
+    bests = []
+    for rnk in range(2):
+        s2 = Sweep(PE.device_problem, spec, N, store_logp=False, shard=(rnk, 2))
+        s2.pass1()
+        b = s2.best.cpu()
+        bests.append((float(b[0]), int(b.view(torch.int64)[1])))
+        del s2
+    assert D.merge_best(bests) == (PE.map_logP, PE.map_index)
+
+
+def test_c5_uniform_sweep_properties(env):
+    """Uniform (Philox) sweep of the C5-shaped problem at 2^24 points: index-addressed draws make any sharding give the
+    same points and the same best; spot-checked against the oracle."""
+    PEUQSE, orc, philox_np, torch = env
+    k, n, N = 10, 64, 1 << 24
+    Phi = orc.cos_basis(n, k)
+    truth = np.random.default_rng(5).standard_normal(k) * 0.5
+    y = Phi @ truth + 0.1 * np.random.default_rng(6).standard_normal(n)
+    PE = make_pe(PEUQSE, PEUQSE.LinearModel(Phi), list(y), list(np.full(n, 0.1)), [0.0] * k, [1.0] * k,
+                 settings={'multistart_initialPointsDistributionType': 'uniform', 'multistart_numStartPoints': N,
+                           'multistart_random_seed': 7})
+    PE.doMultiStart()
+    sw = PE._sweep
+    P = orc.build_problem([0.0] * k, [1.0] * k, y, np.full(n, 0.1))
+    _, bt = orc.sim_linear(Phi)
+    idx = np.array([0, 1, 2, 12345, 99999, N // 2, N - 2, N - 1, PE.map_index])
+    u = np.vstack([philox_np.sweep_uniforms(7, int(i), 1, k) for i in idx])
+    th = orc.uniform_points(u, 0.866, np.ones(k), np.zeros(k))
+    got_th = np.vstack([sw.points(int(i), 1).cpu().numpy() for i in idx])
+    assert np.array_equal(got_th, th)
+    assert np.array_equal(sw.logp[torch.from_numpy(idx).cuda()].cpu().numpy(), orc.log_p_batch(P, th, bt)[0])
+    assert float(sw.logp.max().item()) == PE.map_logP and np.array_equal(PE.map_parameter_set, th[-1])
+    from peuqse_b200.sweep import Sweep
+    from peuqse_b200 import distributed as D
+    bests = []
+    for rnk in range(3):
+        s2 = Sweep(PE.device_problem, sw.spec, N, store_logp=False, shard=(rnk, 3))
+        s2.pass1()
+        b = s2.best.cpu()
+        bests.append((float(b[0]), int(b.view(torch.int64)[1])))
+    assert D.merge_best(bests) == (PE.map_logP, PE.map_index)
+    assert PE.sweep_result.sum_weights >= 100 - 1
