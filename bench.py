@@ -7,7 +7,7 @@ weighted moments + marginal histograms.  One "step" = one complete multistart ov
   pass 1 (logP of every point materialised in HBM + first strict maximum), pass 2 (weights + moments),
   edges + pass 3 (marginal histograms).
 Metric: fp64 log-posterior evals/s = grid points / step time (pass-1 evaluations only are counted).
-With N GPUs the grid's second axis is widened so that every rank owns ~1e8 points (weak scaling); the three
+With N GPUs the grid's first axis is widened so that every rank owns ~1e8 points (weak scaling); the three
 tiny collectives (all-gather of the best point, all-reduce of moments / histograms) are inside the step.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
@@ -39,8 +39,8 @@ UNIT = "evals/s"
 
 def grid_for(n_gpus):
     """radii so that the grid has ~n_gpus * 100 020 001 points (exactly that at n_gpus = 1)."""
-    r1 = (10001 * n_gpus - 1) // 2
-    radii = [5000, r1]
+    r0 = (10001 * n_gpus - 1) // 2          # more rows of the same width: every rank sees the tiling of the 1-GPU run
+    radii = [r0, 5000]
     total = (2 * radii[0] + 1) * (2 * radii[1] + 1)
     return radii, total
 

@@ -218,6 +218,18 @@ int peuqse_sweep_hist(const peuqse_problem* p, const peuqse_sweep_spec* spec, in
                       void* stream);
 
 /*
+ * Multi-GPU communicator: NCCL calls issued by the library on the caller's stream (one rank per GPU, one process per
+ * rank).  Rank 0 obtains a 128-byte id with peuqse_comm_unique_id and distributes it by any means (e.g. a
+ * torch.distributed broadcast); every rank then calls peuqse_comm_create with its CUDA device current.
+ */
+typedef struct peuqse_comm peuqse_comm;
+int peuqse_comm_unique_id(void* out128);
+int peuqse_comm_create(const void* id128, int32_t rank, int32_t world, peuqse_comm** out);
+int peuqse_comm_destroy(peuqse_comm* c);
+int peuqse_comm_allgather(peuqse_comm* c, const void* d_send, void* d_recv /*[world][bytes]*/, int64_t bytes, void* stream);
+int peuqse_comm_allreduce_sum_i64(peuqse_comm* c, void* d_buf, int64_t count, void* stream);
+
+/*
  * Multi-GPU merges (replace consolidate_parallel_sampling_data's "keep the best" / stacking, IP.py:1209-1319):
  * d_all holds the all-gathered per-rank records; the merged record is what a single process would have produced
  * (highest logP, lowest index among equals; sums added in rank order, min/max slots reduced accordingly).

@@ -100,3 +100,30 @@ def allgather_rows(t):
     out = [torch.empty_like(pad) for _ in range(size)]
     dist.all_gather(out, pad)
     return torch.cat([o[:c] for o, c in zip(out, ns)], dim=0).to(t.device)
+
+
+_native_comm = None
+
+
+def native_comm():
+    """The library's own NCCL communicator (collectives enqueued on the compute stream by libpeuqse_b200, without the
+    per-call stream hand-over of torch.distributed).  Created on first use from the torch.distributed NCCL group: rank 0
+    makes the 128-byte id, a broadcast distributes it.  None when not running multi-GPU on NCCL."""
+    global _native_comm
+    rank, size = world()
+    if size == 1 or dist.get_backend() != "nccl":
+        return None
+    if _native_comm is None:
+        import ctypes as C
+        from . import _lib
+        L = _lib.load()
+        buf = (C.c_ubyte * 128)()
+        if rank == 0:
+            _lib.check(L.peuqse_comm_unique_id(buf))
+        t = torch.tensor(list(buf), dtype=torch.uint8, device=_comm_device())
+        dist.broadcast(t, 0)
+        idb = (C.c_ubyte * 128)(*t.cpu().tolist())
+        h = C.c_void_p()
+        _lib.check(L.peuqse_comm_create(idb, rank, size, C.byref(h)))
+        _native_comm = h
+    return _native_comm

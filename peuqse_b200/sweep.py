@@ -72,6 +72,7 @@ class Sweep:
         self.acc_init[lay["MAX"]:lay["MAX"] + k] = float("-inf")
         self.launches = 0
         self.world = D.world()[1]
+        self.comm = D.native_comm() if self.world > 1 else None
 
     # -- individual passes: device-resident in and out (bench.py times these for the kernel-only number)
     def pass1(self):
@@ -91,7 +92,10 @@ class Sweep:
         if not hasattr(self, "_g_best"):
             self._g_best = torch.empty((self.world, 2), dtype=torch.float64, device=self.dev)
             self._g_acc = torch.empty((self.world, self.lay["SIZE"]), dtype=torch.float64, device=self.dev)
-        dist.all_gather_into_tensor(self._g_best, self.best.reshape(1, 2))
+        if self.comm is not None:
+            _lib.check(self.L.peuqse_comm_allgather(self.comm, _lib.ptr(self.best), _lib.ptr(self._g_best), 16, _lib.current_stream()))
+        else:
+            dist.all_gather_into_tensor(self._g_best, self.best.reshape(1, 2))
         _lib.check(self.L.peuqse_merge_best(_lib.ptr(self._g_best), self.world, _lib.ptr(self.best), _lib.current_stream()))
         self.launches += 1
 
@@ -110,7 +114,11 @@ class Sweep:
         self.launches += 2                                  # main kernel + finish kernel
         if self.world > 1:                                  # one all-gather + one merge kernel (sum / min / max by slot)
             import torch.distributed as dist
-            dist.all_gather_into_tensor(self._g_acc, self.acc.reshape(1, -1))
+            if self.comm is not None:
+                _lib.check(self.L.peuqse_comm_allgather(self.comm, _lib.ptr(self.acc), _lib.ptr(self._g_acc),
+                                                        self.lay["SIZE"] * 8, _lib.current_stream()))
+            else:
+                dist.all_gather_into_tensor(self._g_acc, self.acc.reshape(1, -1))
             _lib.check(self.L.peuqse_merge_acc(_lib.ptr(self._g_acc), self.world, self.k, _lib.ptr(self.acc),
                                                _lib.current_stream()))
             self.launches += 1
@@ -124,8 +132,12 @@ class Sweep:
                                             _lib.current_stream()))
         self.launches += 2
         if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.hist, op=dist.ReduceOp.SUM)
+            if self.comm is not None:
+                _lib.check(self.L.peuqse_comm_allreduce_sum_i64(self.comm, _lib.ptr(self.hist), self.hist.numel(),
+                                                                _lib.current_stream()))
+            else:
+                import torch.distributed as dist
+                dist.all_reduce(self.hist, op=dist.ReduceOp.SUM)
 
     def step(self, log_rel, statistics=True):
         """One whole multistart on the device (no host synchronisation)."""
