@@ -71,6 +71,7 @@ class Sweep:
         self.acc_init[lay["MIN"]:lay["MIN"] + k] = float("inf")
         self.acc_init[lay["MAX"]:lay["MAX"] + k] = float("-inf")
         self.launches = 0
+        self.use_graph = True
         self.world = D.world()[1]
         self.comm = D.native_comm() if self.world > 1 else None
 
@@ -161,7 +162,25 @@ class Sweep:
     def run(self, coef=2.0, statistics=True):
         k, nbins, lay = self.k, self.nbins, self.lay
         log_rel = float(np.log(10 ** (-1 * coef)))                       # IP.py:1016, 3477
-        self.step(log_rel, statistics)
+        key = (log_rel, bool(statistics))
+        if getattr(self, "_graph_key", None) == key and self._graph is not None:
+            self._graph.replay()                                          # the same sweep again: one graph launch
+        else:
+            self.step(log_rel, statistics)
+            self._graph, self._graph_key = None, None
+            if self.world == 1 and self.use_graph:                        # capture the launch sequence for the next call
+                try:
+                    cur = torch.cuda.current_stream()
+                    side = torch.cuda.Stream()
+                    side.wait_stream(cur)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.stream(side):
+                        with torch.cuda.graph(g, stream=side):
+                            self.step(log_rel, statistics)
+                    cur.wait_stream(side)
+                    self._graph, self._graph_key = g, key
+                except Exception:
+                    self._graph, self._graph_key = None, None
         res = self.res.cpu()                                              # the single device->host read
         R = self.unpack(res.numpy(), coef, statistics)
         return R
