@@ -119,36 +119,16 @@ __device__ __forceinline__ void draws_thread(const DevMH& M, unsigned long long 
     u = philox_u53(r.x, r.y);
 }
 
-// warp version: lane b < 7 makes normal pair b, lane 7 the uniform; everything is then broadcast
-template <int KT>
-__device__ __forceinline__ void draws_warp(const DevMH& M, unsigned long long chain, unsigned long long step, int lane,
-                                           double (&z)[KT], double& u) {
-    double a = 0.0, b2 = 0.0;
-    if (lane < 7) {
-        if (2 * lane < M.k) philox_normal_pair(philox_block(M.seed, PQ_STREAM_MH, chain, (uint32_t)(8ULL * step + lane)), a, b2);
-    } else if (lane == 7) {
-        const Philox4 r = philox_block(M.seed, PQ_STREAM_MH, chain, (uint32_t)(8ULL * step + 7ULL));
-        a = philox_u53(r.x, r.y);
-    }
-#pragma unroll
-    for (int j = 0; j < (KT + 1) / 2; ++j) {
-        z[2 * j] = __shfl_sync(0xffffffffu, a, j);
-        const double zb = __shfl_sync(0xffffffffu, b2, j);
-        if (2 * j + 1 < KT) z[2 * j + 1] = zb;
-    }
-    u = __shfl_sync(0xffffffffu, a, 7);
-}
-
-template <int MODEL, int KT, bool WARP>
-__global__ void __launch_bounds__(WARP ? 256 : 128) k_mh(const __grid_constant__ DevProblem P, const __grid_constant__ DevMH M,
-                                                         const double* __restrict__ theta0, const MHOut out, int use_smem) {
+// ---------------------------------------------------------------------------------------------
+// thread shape: one chain per thread (n_total <= PQ_THREAD_SHAPE_MAX_N)
+// ---------------------------------------------------------------------------------------------
+template <int MODEL, int KT>
+__global__ void __launch_bounds__(128) k_mh(const __grid_constant__ DevProblem P, const __grid_constant__ DevMH M,
+                                            const double* __restrict__ theta0, const MHOut out, int use_smem) {
     extern __shared__ double smem[];
     const ObsView O = stage_obs(P, smem, use_smem);
-    const int lane = threadIdx.x & 31;
-    const long long c = WARP ? ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5))
-                             : ((long long)blockIdx.x * blockDim.x + threadIdx.x);
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= M.n_chains) return;
-    const bool writer = WARP ? (lane == 0) : true;
     const int k = P.k;
     const long long C = M.n_chains;
     const unsigned long long gchain = (unsigned long long)(M.chain_offset + c);
@@ -157,35 +137,31 @@ __global__ void __launch_bounds__(WARP ? 256 : 128) k_mh(const __grid_constant__
 #pragma unroll
     for (int d = 0; d < KT; ++d) { th[d] = (d < k) ? theta0[c * k + d] : 0.0; th0[d] = th[d]; }
     double cur_lp = eval_prior<KT>(P, th);
-    double cur_ll = WARP ? eval_loglik_warp<MODEL, KT>(P, O, th, nullptr, lane) : eval_loglik_thread<MODEL, KT>(P, O, th, nullptr);
+    double cur_ll = eval_loglik_thread<MODEL, KT>(P, O, th, nullptr);
     double cur_sum = cur_ll + cur_lp;                            // what the accept test uses (IP.py:2641)
     ChainStats<KT> st;
     st.init();
     // row 0: samples[0] = start, logP[0] = getLogP(start); log_priors[0] = log_likelihoods[0] = 0 (IP.py:2610-2625)
     {
         const double lp0 = combine_logp(cur_lp, cur_ll);
-        if (writer) {
-            if (out.samples) {
+        if (out.samples) {
 #pragma unroll
-                for (int d = 0; d < KT; ++d) if (d < k) out.samples[c * k + d] = th[d];
-            }
-            if (out.logp) out.logp[c] = lp0;
-            if (out.lprior) out.lprior[c] = 0.0;
-            if (out.llik) out.llik[c] = 0.0;
+            for (int d = 0; d < KT; ++d) if (d < k) out.samples[c * k + d] = th[d];
         }
+        if (out.logp) out.logp[c] = lp0;
+        if (out.lprior) out.lprior[c] = 0.0;
+        if (out.llik) out.llik[c] = 0.0;
         if (M.burn_in <= 0) st.add_row(k, 0, th, th0, lp0);
     }
     for (long long i = 1; i < M.n_steps; ++i) {
         double z[KT], delta[KT], prop[KT], u;
         const unsigned long long step = (unsigned long long)(M.first_step + i);
-        if (WARP) draws_warp<KT>(M, gchain, step, lane, z, u);
-        else draws_thread<KT>(M, gchain, step, z, u);
+        draws_thread<KT>(M, gchain, step, z, u);
         make_delta<KT>(M, z, delta);
 #pragma unroll
         for (int d = 0; d < KT; ++d) prop[d] = th[d] + delta[d];  // IP.py:2630
         const double lp_p = eval_prior<KT>(P, prop);
-        const double ll_p = WARP ? eval_loglik_warp<MODEL, KT>(P, O, prop, nullptr, lane)
-                                 : eval_loglik_thread<MODEL, KT>(P, O, prop, nullptr);   // evaluated even if lp_p == -inf (IP.py:2637)
+        const double ll_p = eval_loglik_thread<MODEL, KT>(P, O, prop, nullptr);   // evaluated even if lp_p == -inf (IP.py:2637)
         const double sum_p = ll_p + lp_p;
         double la = sum_p - cur_sum;                              // IP.py:2641
         if (M.modulate != 0.0) la = (1.0 / M.modulate) * la;      // IP.py:2649
@@ -196,12 +172,176 @@ __global__ void __launch_bounds__(WARP ? 256 : 128) k_mh(const __grid_constant__
             cur_lp = lp_p; cur_ll = ll_p; cur_sum = sum_p;
             st.nacc += 1.0;
         }
-        if (writer) {
+        if (out.deltas) {
+#pragma unroll
+            for (int d = 0; d < KT; ++d) if (d < k) out.deltas[((i - 1) * C + c) * k + d] = delta[d];
+        }
+        if (out.us) out.us[(i - 1) * C + c] = u;
+        if (i % M.thin == 0) {
+            const long long row = i / M.thin;
+            if (out.samples) {
+#pragma unroll
+                for (int d = 0; d < KT; ++d) if (d < k) out.samples[(row * C + c) * k + d] = th[d];
+            }
+            if (out.logp) out.logp[row * C + c] = cur_sum;      // IP.py:2661, 2673
+            if (out.lprior) out.lprior[row * C + c] = cur_lp;
+            if (out.llik) out.llik[row * C + c] = cur_ll;
+        }
+        if (i >= M.burn_in) st.add_row(k, i, th, th0, cur_sum);
+    }
+    st.store(k, out.stats + c * PEUQSE_MH_STAT_DOUBLES(k), th, cur_sum);
+}
+
+// ---------------------------------------------------------------------------------------------
+// warp shape: one chain per warp (n_total > PQ_THREAD_SHAPE_MAX_N); lanes stride over the observations.
+// What is per chain rather than per observation is spread over the lanes instead of being repeated in all 32:
+//   * the running moments: accumulator slot s (the KT(KT+1)/2 second moments in the order ChainStats
+//     enumerates them, then the KT first moments) lives in lane s % 32, so the chain state costs ~20
+//     registers instead of ~120 and four CTAs of four chains fit an SM;
+//   * the draws: one Philox + Box-Muller (+ log u) pass fills the 8 blocks of FOUR consecutive steps
+//     (lane = 8*substep + block) and the per-step values are broadcast reads of a 512-byte shared-memory row.
+// The arithmetic on every value is that of the thread shape, so both shapes walk the same trajectory.
+// ---------------------------------------------------------------------------------------------
+#define MHW_WARPS 4
+template <int KT>
+struct MhwLayout {
+    static constexpr int NPAIR = KT * (KT + 1) / 2;
+    static constexpr int NSLOT = NPAIR + KT;
+    static constexpr int NACC = (NSLOT + 31) / 32;
+    static constexpr int KPAD = (KT + 1) & ~1;
+    static constexpr int WDOUBLES = 2 * KPAD + 64;       // cur[KPAD] | th0[KPAD] | draws[32][2]
+};
+
+template <int MODEL, int KT>
+__global__ void __launch_bounds__(32 * MHW_WARPS, 4) k_mh_warp(const __grid_constant__ DevProblem P,
+                                                               const __grid_constant__ DevMH M,
+                                                               const double* __restrict__ theta0, const MHOut out,
+                                                               int use_smem) {
+    using L = MhwLayout<KT>;
+    extern __shared__ double smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* cur = smem + warp * L::WDOUBLES;
+    double* th0s = cur + L::KPAD;
+    double2* dr = reinterpret_cast<double2*>(th0s + L::KPAD);
+    const ObsView O = stage_obs(P, smem + MHW_WARPS * L::WDOUBLES, use_smem);
+    const long long c = (long long)blockIdx.x * MHW_WARPS + warp;
+    if (c >= M.n_chains) return;
+    const int k = P.k;
+    const long long C = M.n_chains;
+    const unsigned long long gchain = (unsigned long long)(M.chain_offset + c);
+
+    double th[KT];
+#pragma unroll
+    for (int d = 0; d < KT; ++d) th[d] = (d < k) ? theta0[c * k + d] : 0.0;
+    if (lane == 0) {
+#pragma unroll
+        for (int d = 0; d < KT; ++d) { cur[d] = th[d]; th0s[d] = th[d]; }
+    }
+    __syncwarp();
+    // accumulator slots of this lane
+    int sa[L::NACC], sb[L::NACC];
+    double acc[L::NACC], va[L::NACC], vb[L::NACC];
+#pragma unroll
+    for (int q = 0; q < L::NACC; ++q) {
+        const int s = lane + 32 * q;
+        int a = -1, b = -1;
+        if (s < L::NPAIR) {
+            int e = 0;
+            for (int d = 0; d < KT; ++d)
+                for (int d2 = d; d2 < KT; ++d2) { if (e == s) { a = d; b = d2; } ++e; }
+            if (a >= k || b >= k) a = -1;
+        } else if (s < L::NSLOT) {
+            a = s - L::NPAIR; b = -1;
+            if (a >= k) a = -1;
+        }
+        sa[q] = a; sb[q] = b; acc[q] = 0.0; va[q] = 0.0; vb[q] = (a >= 0 && b < 0) ? 1.0 : 0.0;
+    }
+    double nacc = 0.0, maplogp = pq_neg_inf(), maprow = -1.0, sumexp = 0.0, mapth = 0.0;
+
+    double cur_lp = eval_prior<KT>(P, th);
+    double cur_ll = eval_loglik_warp<MODEL, KT>(P, O, th, nullptr, lane);
+    double cur_sum = cur_ll + cur_lp;
+    auto add_row = [&](long long row, double lp) {
+        if (lp > maplogp) {                                       // first maximum (IP.py:1925-1927)
+            maplogp = lp; maprow = (double)row;
+            if (lane < KT) mapth = cur[lane];
+        }
+        sumexp += exp(lp);
+#pragma unroll
+        for (int q = 0; q < L::NACC; ++q) acc[q] = fma(va[q], vb[q], acc[q]);   // first moments: fma(dd, 1, s1) == s1 + dd
+    };
+    {
+        const double lp0 = combine_logp(cur_lp, cur_ll);
+        if (lane == 0) {
+            if (out.samples) {
+#pragma unroll
+                for (int d = 0; d < KT; ++d) if (d < k) out.samples[c * k + d] = th[d];
+            }
+            if (out.logp) out.logp[c] = lp0;
+            if (out.lprior) out.lprior[c] = 0.0;
+            if (out.llik) out.llik[c] = 0.0;
+        }
+        if (M.burn_in <= 0) add_row(0, lp0);
+    }
+    const int sub = lane >> 3, blk = lane & 7;
+    for (long long i = 1; i < M.n_steps; ++i) {
+        const int g = (int)((i - 1) & 3);
+        if (g == 0) {
+            const unsigned long long step = (unsigned long long)(M.first_step + i + sub);
+            const Philox4 r = philox_block(M.seed, PQ_STREAM_MH, gchain, (uint32_t)(8ULL * step + (unsigned)blk));
+            double a = 0.0, b2 = 0.0;
+            if (blk < 7) {
+                if (2 * blk < k) philox_normal_pair(r, a, b2);
+            } else {
+                a = philox_u53(r.x, r.y);
+                b2 = log(a);
+            }
+            __syncwarp();
+            dr[lane] = make_double2(a, b2);
+            __syncwarp();
+        }
+        double z[KT], delta[KT], prop[KT];
+#pragma unroll
+        for (int j = 0; j < (KT + 1) / 2; ++j) {
+            const double2 zz = dr[g * 8 + (j < 7 ? j : 0)];
+            z[2 * j] = zz.x;
+            if (2 * j + 1 < KT) z[2 * j + 1] = zz.y;
+        }
+        const double2 uu = dr[g * 8 + 7];                         // (u, log u)
+        make_delta<KT>(M, z, delta);
+#pragma unroll
+        for (int d = 0; d < KT; ++d) prop[d] = th[d] + delta[d];  // IP.py:2630
+        const double lp_p = eval_prior<KT>(P, prop);
+        const double ll_p = eval_loglik_warp<MODEL, KT>(P, O, prop, nullptr, lane);
+        const double sum_p = ll_p + lp_p;
+        double la = sum_p - cur_sum;                              // IP.py:2641
+        if (M.modulate != 0.0) la = (1.0 / M.modulate) * la;      // IP.py:2649
+        const bool accept = la > uu.y;                            // IP.py:2651-2652; NaN -> reject
+        if (accept) {                                             // the same in every lane
+#pragma unroll
+            for (int d = 0; d < KT; ++d) th[d] = prop[d];
+            cur_lp = lp_p; cur_ll = ll_p; cur_sum = sum_p;
+            nacc += 1.0;
+            __syncwarp();
+            if (lane == 0) {
+#pragma unroll
+                for (int d = 0; d < KT; ++d) cur[d] = th[d];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < L::NACC; ++q) {
+                if (sa[q] >= 0) {
+                    va[q] = cur[sa[q]] - th0s[sa[q]];
+                    if (sb[q] >= 0) vb[q] = cur[sb[q]] - th0s[sb[q]];
+                }
+            }
+        }
+        if (lane == 0) {
             if (out.deltas) {
 #pragma unroll
                 for (int d = 0; d < KT; ++d) if (d < k) out.deltas[((i - 1) * C + c) * k + d] = delta[d];
             }
-            if (out.us) out.us[(i - 1) * C + c] = u;
+            if (out.us) out.us[(i - 1) * C + c] = uu.x;
             if (i % M.thin == 0) {
                 const long long row = i / M.thin;
                 if (out.samples) {
@@ -213,9 +353,31 @@ __global__ void __launch_bounds__(WARP ? 256 : 128) k_mh(const __grid_constant__
                 if (out.llik) out.llik[row * C + c] = cur_ll;
             }
         }
-        if (i >= M.burn_in) st.add_row(k, i, th, th0, cur_sum);
+        if (i >= M.burn_in) add_row(i, cur_sum);
     }
-    if (writer) st.store(k, out.stats + c * PEUQSE_MH_STAT_DOUBLES(k), th, cur_sum);
+    double* so = out.stats + c * PEUQSE_MH_STAT_DOUBLES(k);
+    if (lane == 0) {
+        so[PEUQSE_MH_STAT_NACC] = nacc;
+        so[PEUQSE_MH_STAT_MAPLOGP] = maplogp;
+        so[PEUQSE_MH_STAT_MAPROW] = maprow;
+        so[PEUQSE_MH_STAT_LASTLOGP] = cur_sum;
+        so[PEUQSE_MH_STAT_SUMEXP] = sumexp;
+    }
+    if (lane < k) {
+        so[PEUQSE_MH_STAT_MAPTHETA + lane] = mapth;
+        so[PEUQSE_MH_STAT_LAST(k) + lane] = cur[lane];
+    }
+#pragma unroll
+    for (int q = 0; q < L::NACC; ++q) {
+        if (sa[q] >= 0) {
+            if (sb[q] >= 0) {
+                so[PEUQSE_MH_STAT_S2(k) + sa[q] * k + sb[q]] = acc[q];
+                so[PEUQSE_MH_STAT_S2(k) + sb[q] * k + sa[q]] = acc[q];
+            } else {
+                so[PEUQSE_MH_STAT_S1(k) + sa[q]] = acc[q];
+            }
+        }
+    }
 }
 
 namespace {
@@ -224,12 +386,13 @@ int launch_mh(const peuqse_problem* p, const DevMH& M, const double* th0, const 
     int use_smem;
     const size_t smem = pq_pick_smem(p, &use_smem);
     if (p->d.n_total > PQ_THREAD_SHAPE_MAX_N) {
-        auto kern = k_mh<MODEL, KT, true>;
-        PQ_CUDA_OK(pq_allow_smem((const void*)kern, smem));
-        const long long blocks = (M.n_chains + 7) / 8;
-        kern<<<(unsigned)blocks, 256, smem, st>>>(p->d, M, th0, out, use_smem);
+        auto kern = k_mh_warp<MODEL, KT>;
+        const size_t wsmem = smem + (size_t)MHW_WARPS * MhwLayout<KT>::WDOUBLES * sizeof(double);
+        PQ_CUDA_OK(pq_allow_smem((const void*)kern, wsmem));
+        const long long blocks = (M.n_chains + MHW_WARPS - 1) / MHW_WARPS;
+        kern<<<(unsigned)blocks, 32 * MHW_WARPS, wsmem, st>>>(p->d, M, th0, out, use_smem);
     } else {
-        auto kern = k_mh<MODEL, KT, false>;
+        auto kern = k_mh<MODEL, KT>;
         PQ_CUDA_OK(pq_allow_smem((const void*)kern, smem));
         const long long blocks = (M.n_chains + 127) / 128;
         kern<<<(unsigned)blocks, 128, smem, st>>>(p->d, M, th0, out, use_smem);

@@ -90,7 +90,7 @@ extern "C" int peuqse_problem_create(const peuqse_problem_desc* h, peuqse_proble
     d.n_resp = h->n_resp;
     d.n_total = h->n_total;
     d.model_id = h->model_id;
-    d.n_mconst = h->n_model_const;
+    d.n_mconst = h->n_model_const;                       // tpd2site: + n reciprocals appended below
     int off = 0;
     for (int r = 0; r < h->n_resp; ++r) {
         d.resp_n[r] = h->resp_n[r];
@@ -122,7 +122,17 @@ extern "C" int peuqse_problem_create(const peuqse_problem_desc* h, peuqse_proble
     const size_t o_w = bb.add(h->w ? h->w : zeros.data(), nt * 8);
     const size_t o_c = bb.add(h->cval ? h->cval : zeros.data(), nt * 8);
     const size_t o_s = bb.add(h->src ? (const void*)h->src : (const void*)ident.data(), nt * 4);
-    const size_t o_m = bb.add(h->model_const, (size_t)h->n_model_const * 8);
+    size_t o_m;
+    if (h->model_id == PEUQSE_MODEL_TPD2SITE) {
+        // kBT, cov1, cov2 as given, then the correctly rounded reciprocals 1/kBT that eval.cuh's pq_div_by needs
+        std::vector<double> mc(4 * nt);
+        for (size_t i = 0; i < 3 * nt; ++i) mc[i] = h->model_const[i];
+        for (size_t i = 0; i < nt; ++i) mc[3 * nt + i] = 1.0 / h->model_const[i];
+        o_m = bb.add(mc.data(), mc.size() * 8);
+        d.n_mconst = (int)(4 * nt);
+    } else {
+        o_m = bb.add(h->model_const, (size_t)h->n_model_const * 8);
+    }
     size_t o_pU = 0;
     if (h->prior_mode == PEUQSE_PRIOR_DENSE) o_pU = bb.add(h->prior_U, (size_t)h->kp * h->kp * 8);
     size_t o_U[PQ_MAXR] = {0};
