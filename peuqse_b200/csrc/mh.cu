@@ -212,7 +212,7 @@ struct MhwLayout {
     static constexpr int WDOUBLES = 2 * KPAD + 64;       // cur[KPAD] | th0[KPAD] | draws[32][2]
 };
 
-template <int MODEL, int KT>
+template <int MODEL, int KT, int U, int SMEM>
 __global__ void __launch_bounds__(32 * MHW_WARPS, 4) k_mh_warp(const __grid_constant__ DevProblem P,
                                                                const __grid_constant__ DevMH M,
                                                                const double* __restrict__ theta0, const MHOut out,
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(32 * MHW_WARPS, 4) k_mh_warp(const __grid_cons
     double* cur = smem + warp * L::WDOUBLES;
     double* th0s = cur + L::KPAD;
     double2* dr = reinterpret_cast<double2*>(th0s + L::KPAD);
-    const ObsView O = stage_obs(P, smem + MHW_WARPS * L::WDOUBLES, use_smem);
+    const ObsView O = stage_obs<SMEM>(P, smem + MHW_WARPS * L::WDOUBLES, use_smem);
     const long long c = (long long)blockIdx.x * MHW_WARPS + warp;
     if (c >= M.n_chains) return;
     const int k = P.k;
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(32 * MHW_WARPS, 4) k_mh_warp(const __grid_cons
     double nacc = 0.0, maplogp = pq_neg_inf(), maprow = -1.0, sumexp = 0.0, mapth = 0.0;
 
     double cur_lp = eval_prior<KT>(P, th);
-    double cur_ll = eval_loglik_warp<MODEL, KT>(P, O, th, nullptr, lane);
+    double cur_ll = eval_loglik_warp<MODEL, KT, U>(P, O, th, nullptr, lane);
     double cur_sum = cur_ll + cur_lp;
     auto add_row = [&](long long row, double lp) {
         if (lp > maplogp) {                                       // first maximum (IP.py:1925-1927)
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(32 * MHW_WARPS, 4) k_mh_warp(const __grid_cons
 #pragma unroll
         for (int d = 0; d < KT; ++d) prop[d] = th[d] + delta[d];  // IP.py:2630
         const double lp_p = eval_prior<KT>(P, prop);
-        const double ll_p = eval_loglik_warp<MODEL, KT>(P, O, prop, nullptr, lane);
+        const double ll_p = eval_loglik_warp<MODEL, KT, U>(P, O, prop, nullptr, lane);
         const double sum_p = ll_p + lp_p;
         double la = sum_p - cur_sum;                              // IP.py:2641
         if (M.modulate != 0.0) la = (1.0 / M.modulate) * la;      // IP.py:2649
@@ -386,7 +386,8 @@ int launch_mh(const peuqse_problem* p, const DevMH& M, const double* th0, const 
     int use_smem;
     const size_t smem = pq_pick_smem(p, &use_smem);
     if (p->d.n_total > PQ_THREAD_SHAPE_MAX_N) {
-        auto kern = k_mh_warp<MODEL, KT>;
+        void (*kern)(const DevProblem, const DevMH, const double*, const MHOut, int) = k_mh_warp<MODEL, KT, 2, -1>;
+        if (use_smem) kern = k_mh_warp<MODEL, KT, 2, 1>;
         const size_t wsmem = smem + (size_t)MHW_WARPS * MhwLayout<KT>::WDOUBLES * sizeof(double);
         PQ_CUDA_OK(pq_allow_smem((const void*)kern, wsmem));
         const long long blocks = (M.n_chains + MHW_WARPS - 1) / MHW_WARPS;

@@ -156,6 +156,7 @@ extern "C" int peuqse_problem_create(const peuqse_problem_desc* h, peuqse_proble
     for (int r = 0; r < h->n_resp; ++r)
         d.U[r] = (h->resp_mode[r] == PEUQSE_RESP_MVN_FULL) ? (const double*)(base + o_U[r]) : nullptr;
 
+    pq_fill_mathc(d);
     // fast view
     d.fast_n = 0;
     for (int i = 0; i < PQ_MAXK; ++i) { d.gauss[i] = 0; d.pwn[i] = 0.0; }
@@ -218,6 +219,46 @@ __global__ void __launch_bounds__(256) k_bench_fp64(int iters, int mode, double 
 }
 
 // returns through *instr_per_s the measured fp64 instruction rate (instructions, not flops) of the whole device
+// latency probe: NCH dependent DFMA chains per thread, one warp per scheduler (128-thread CTA per SM)
+template <int NCH>
+__global__ void __launch_bounds__(128) k_bench_fp64_lat(int iters, double seed, double* __restrict__ out) {
+    double a[NCH];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) a[j] = seed + threadIdx.x * 1e-9 + j;
+    const double m = 1.0000000001, c = 1e-12;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+#pragma unroll
+            for (int j = 0; j < NCH; ++j) a[j] = fma(a[j], m, c);
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) s += a[j];
+    if (s == 123.456) out[0] = s;
+}
+
+// operand-pattern probe: Horner steps p = fma(r, p, c_i) with r, p and twelve c_i all in distinct registers (what an
+// exp/log polynomial issues), 4 chains per thread, full occupancy -- against mode 0 whose multiplier and addend are
+// two fixed registers
+__global__ void __launch_bounds__(256) k_bench_fp64_horner(int iters, const double* __restrict__ coef, double* __restrict__ out) {
+    double c[12], r[4], p[4];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) c[i] = coef[i];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { r[j] = coef[12 + j] + threadIdx.x * 1e-12; p[j] = c[0]; }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) p[j] = fma(r[j], p[j], c[i]);
+        }
+    }
+    const double s = (p[0] + p[1]) + (p[2] + p[3]);
+    if (s == 123.456) out[0] = s;
+}
+
 extern "C" int peuqse_bench_fp64(int32_t mode, double* instr_per_s, double* d_scratch, void* stream) {
     int dev = 0;
     PQ_CUDA_OK(cudaGetDevice(&dev));
@@ -228,6 +269,42 @@ extern "C" int peuqse_bench_fp64(int32_t mode, double* instr_per_s, double* d_sc
     cudaEvent_t e0, e1;
     PQ_CUDA_OK(cudaEventCreate(&e0));
     PQ_CUDA_OK(cudaEventCreate(&e1));
+    if (mode == 2) {    // Horner operand pattern; d_scratch holds 16 doubles: 12 coefficients + 4 arguments
+        const int nb = prop.multiProcessorCount * 8, it = 4000;
+        k_bench_fp64_horner<<<nb, 256, 0, st>>>(50, d_scratch, d_scratch + 16);
+        PQ_CUDA_OK(cudaEventRecord(e0, st));
+        k_bench_fp64_horner<<<nb, 256, 0, st>>>(it, d_scratch, d_scratch + 16);
+        PQ_CUDA_OK(cudaEventRecord(e1, st));
+        PQ_CUDA_OK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        PQ_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        *instr_per_s = (double)nb * 256.0 * it * 48.0 / (ms * 1e-3);
+        return PEUQSE_OK;
+    }
+    if (mode >= 10) {   // 10 + log2(chains): dependent-chain probe, one warp per scheduler; result = DFMA/s of the device
+        const int lg = mode - 10, nch = 1 << lg, it = 20000;
+        const int nb = prop.multiProcessorCount;
+        auto run = [&](int n_it) {
+            if (lg == 0) k_bench_fp64_lat<1><<<nb, 128, 0, st>>>(n_it, 1.0, d_scratch);
+            else if (lg == 1) k_bench_fp64_lat<2><<<nb, 128, 0, st>>>(n_it, 1.0, d_scratch);
+            else if (lg == 2) k_bench_fp64_lat<4><<<nb, 128, 0, st>>>(n_it, 1.0, d_scratch);
+            else if (lg == 3) k_bench_fp64_lat<8><<<nb, 128, 0, st>>>(n_it, 1.0, d_scratch);
+            else k_bench_fp64_lat<16><<<nb, 128, 0, st>>>(n_it, 1.0, d_scratch);
+        };
+        run(100);
+        PQ_CUDA_OK(cudaEventRecord(e0, st));
+        run(it);
+        PQ_CUDA_OK(cudaEventRecord(e1, st));
+        PQ_CUDA_OK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        PQ_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        *instr_per_s = (double)nb * 128.0 * it * 8.0 * nch / (ms * 1e-3);
+        return PEUQSE_OK;
+    }
     k_bench_fp64<<<blocks, 256, 0, st>>>(200, mode, 1.0, d_scratch);
     PQ_CUDA_OK(cudaEventRecord(e0, st));
     k_bench_fp64<<<blocks, 256, 0, st>>>(iters, mode, 1.0, d_scratch);
