@@ -31,29 +31,75 @@ __global__ void k_best_init(peuqse_best* b) {
     b->index = -1;
 }
 
+// shortlist helpers (sweep_common.cuh): monotone double <-> key, append
+__device__ __forceinline__ unsigned long long short_double_to_key(double v) {
+    const long long b = __double_as_longlong(v);
+    return b < 0 ? ~(unsigned long long)b : ((unsigned long long)b | 0x8000000000000000ULL);
+}
+__device__ __forceinline__ double short_key_to_double(unsigned long long key) {
+    return __longlong_as_double((long long)((key & 0x8000000000000000ULL) ? (key & 0x7fffffffffffffffULL) : ~key));
+}
+__device__ __forceinline__ void short_push(ShortHdr* sh, long long* c_idx, double* c_logp, long long g, double v) {
+    const unsigned long long slot = atomicAdd(&sh->count, 1ULL);
+    if (slot < (unsigned long long)PQ_SHORT_CAP) {
+        c_idx[slot] = g;
+        c_logp[slot] = v;
+    }
+}
+__device__ __forceinline__ bool short_usable(const ShortHdr* sh, int margin_ok) {
+    return sh && margin_ok && sh->valid == 1u && sh->count <= (unsigned long long)PQ_SHORT_CAP;
+}
+
 // ---------------------------------------------------------------------------------------------
 // pass 1: logP of every point (+ optional store) and the first strict maximum
 // ---------------------------------------------------------------------------------------------
-template <int MODEL, int KT>
-__global__ void __launch_bounds__(256) k_sweep_pass1(const __grid_constant__ DevProblem P, const __grid_constant__ DevSweep S,
+#define P1_THREADS 128
+template <int MODEL, int KT, int SMEM>
+__global__ void __launch_bounds__(P1_THREADS, 3) k_sweep_pass1(const __grid_constant__ DevProblem P, const __grid_constant__ DevSweep S,
                                                      long long first, long long count, double* __restrict__ logp_out,
                                                      peuqse_best* __restrict__ best_out, Best* __restrict__ partial,
-                                                     unsigned int* __restrict__ ticket, int use_smem) {
-    extern __shared__ double smem[];
+                                                     unsigned int* __restrict__ ticket, int use_smem,
+                                                     ShortHdr* __restrict__ sh, long long* __restrict__ c_idx,
+                                                     double* __restrict__ c_logp) {
+    extern __shared__ __align__(16) double smem[];
     __shared__ Best s_best[8];
     __shared__ bool s_last;
-    const ObsView O = stage_obs(P, smem, use_smem);
+    const ObsView O = stage_obs<SMEM>(P, smem, use_smem);
     Best best = best_none();
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+    // two points per trip (i and i + stride) share every load of the per-observation constants
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += 2 * stride) {
         const long long g = first + i;
-        double th[KT];
-        sweep_point<KT>(S, (unsigned long long)g, th);
-        const double lp = eval_prior<KT>(P, th);
-        double v = lp;
-        if (!pq_is_neg_inf(lp)) v = eval_loglik_thread<MODEL, KT>(P, O, th, nullptr) + lp;   // IP.py:1649-1653
-        if (logp_out) __stcs(logp_out + i, v);
-        if (v > best.v) { best.v = v; best.i = g; }            // strict '>', increasing g: first maximum
+        const bool two = i + stride < count;
+        double gm = pq_neg_inf();                               // best logP published so far (shortlist mode)
+        if (sh) {
+            const unsigned long long key = *(volatile unsigned long long*)&sh->gmax_key;
+            if (key) gm = short_key_to_double(key);
+        }
+        double tha[KT], thb[KT];
+        sweep_point<KT>(S, (unsigned long long)g, tha);
+        sweep_point<KT>(S, (unsigned long long)(two ? g + stride : g), thb);
+        const double lpa = eval_prior<KT>(P, tha), lpb = eval_prior<KT>(P, thb);
+        double va = lpa, vb = lpb;
+        if (!(pq_is_neg_inf(lpa) && pq_is_neg_inf(lpb))) {
+            double lla, llb;
+            eval_loglik_thread2<MODEL, KT>(P, O, tha, thb, lla, llb);
+            if (!pq_is_neg_inf(lpa)) va = lla + lpa;            // IP.py:1649-1653
+            if (!pq_is_neg_inf(lpb)) vb = llb + lpb;
+        }
+        if (logp_out) __stcs(logp_out + i, va);
+        if (va > best.v) { best.v = va; best.i = g; }          // strict '>', increasing g: first maximum
+        if (two) {
+            if (logp_out) __stcs(logp_out + i + stride, vb);
+            if (vb > best.v) { best.v = vb; best.i = g + stride; }
+        }
+        if (sh) {
+            const double lim = gm - PQ_SHORT_MARGIN;
+            if (va > lim) short_push(sh, c_idx, c_logp, g, va);
+            if (two && vb > lim) short_push(sh, c_idx, c_logp, g + stride, vb);
+            if (va > gm) { atomicMax(&sh->gmax_key, short_double_to_key(va)); gm = va; }
+            if (two && vb > gm) atomicMax(&sh->gmax_key, short_double_to_key(vb));
+        }
     }
     best = warp_best(best);
     if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = best;
@@ -87,6 +133,7 @@ __global__ void __launch_bounds__(256) k_sweep_pass1(const __grid_constant__ Dev
             best_out->logp = b.v;
             best_out->index = (b.i == 0x7fffffffffffffffLL) ? -1 : b.i;
             *ticket = 0;
+            if (sh) sh->valid = 1u;
         }
     }
 }
@@ -142,6 +189,35 @@ __device__ __forceinline__ double block_min(double v, double* s_red) {
     return t;
 }
 
+// one retained point into the running sums (convertPermutationsToSamples' replication as a weight, IP.py:3485-3486)
+template <int KT>
+__device__ __forceinline__ void pass2_accumulate(Pass2Acc<KT>& A, const DevSweep& S, const double (&th)[KT],
+                                                 const double (&shift)[KT], double v, double thr) {
+    const double reps = exp(v - thr);                           // IP.py:3485
+    const double w = trunc(reps);                               // int(...), IP.py:3486
+    A.w += w;
+    A.wexp = fma(w, exp(v), A.wexp);
+    A.nk += 1.0;
+    int e = 0;
+#pragma unroll
+    for (int d = 0; d < KT; ++d) {
+        if (d < S.k) {
+            const double dd = th[d] - shift[d];
+            const double wd = w * dd;
+            A.s1[d] += wd;
+#pragma unroll
+            for (int d2 = d; d2 < KT; ++d2) {
+                if (d2 < S.k) A.s2[e] = fma(wd, th[d2] - shift[d2], A.s2[e]);
+                ++e;
+            }
+            A.mn[d] = fmin(A.mn[d], th[d]);
+            A.mx[d] = fmax(A.mx[d], th[d]);
+        } else {
+            e += KT - d;
+        }
+    }
+}
+
 template <int MODEL, int KT>
 __global__ void __launch_bounds__(256) k_sweep_pass2(const __grid_constant__ DevProblem P, const __grid_constant__ DevSweep S,
                                                      long long first, long long count, const double* __restrict__ logp_in,
@@ -149,10 +225,12 @@ __global__ void __launch_bounds__(256) k_sweep_pass2(const __grid_constant__ Dev
                                                      double* __restrict__ partial, double* __restrict__ acc_out,
                                                      unsigned int* __restrict__ ticket, long long* __restrict__ keep_idx,
                                                      double* __restrict__ keep_logp, long long keep_cap,
-                                                     unsigned long long* __restrict__ keep_count, int use_smem) {
+                                                     unsigned long long* __restrict__ keep_count, int use_smem,
+                                                     const ShortHdr* __restrict__ sh) {
     extern __shared__ double smem[];
     __shared__ double s_red[8];
     __shared__ bool s_last;
+    if (sh && !sh->full_pass2) return;                         // k_short_pass2 already produced the statistics
     const ObsView O = stage_obs(P, smem, use_smem);
     const long long best_index = best_in->index;
     if (best_index < 0) return;                                // no finite point: nothing is retained
@@ -182,29 +260,7 @@ __global__ void __launch_bounds__(256) k_sweep_pass2(const __grid_constant__ Dev
             if (!pq_is_neg_inf(lp)) v = eval_loglik_thread<MODEL, KT>(P, O, th, nullptr) + lp;
             if (!(v > thr)) continue;
         }
-        const double reps = exp(v - thr);                       // IP.py:3485
-        const double w = trunc(reps);                           // int(...), IP.py:3486
-        A.w += w;
-        A.wexp = fma(w, exp(v), A.wexp);
-        A.nk += 1.0;
-        int e = 0;
-#pragma unroll
-        for (int d = 0; d < KT; ++d) {
-            if (d < S.k) {
-                const double dd = th[d] - shift[d];
-                const double wd = w * dd;
-                A.s1[d] += wd;
-#pragma unroll
-                for (int d2 = d; d2 < KT; ++d2) {
-                    if (d2 < S.k) A.s2[e] = fma(wd, th[d2] - shift[d2], A.s2[e]);
-                    ++e;
-                }
-                A.mn[d] = fmin(A.mn[d], th[d]);
-                A.mx[d] = fmax(A.mx[d], th[d]);
-            } else {
-                e += KT - d;
-            }
-        }
+        pass2_accumulate<KT>(A, S, th, shift, v, thr);
         if (keep_idx) {
             const unsigned long long slot = atomicAdd(keep_count, 1ULL);
             if ((long long)slot < keep_cap) {
@@ -270,6 +326,153 @@ __global__ void __launch_bounds__(256) k_sweep_pass2(const __grid_constant__ Dev
 }
 
 // ---------------------------------------------------------------------------------------------
+// pass 2 from the shortlist (logP not stored): one CTA filters the candidates against the final threshold, orders
+// the retained ones by global index (bitonic sort in shared memory, so the floating-point sums do not depend on
+// the order in which pass 1's threads appended them) and accumulates them.  When the list is unusable or more than
+// PQ_SHORT_RCAP points are retained it raises full_pass2 and the recomputing kernel that follows does the work.
+// ---------------------------------------------------------------------------------------------
+template <int KT>
+__global__ void __launch_bounds__(256) k_short_pass2(const __grid_constant__ DevSweep S, ShortHdr* __restrict__ sh,
+                                                     const long long* __restrict__ c_idx, const double* __restrict__ c_logp,
+                                                     const peuqse_best* __restrict__ best_in, double log_rel, int margin_ok,
+                                                     double* __restrict__ acc_out, long long* __restrict__ keep_idx,
+                                                     double* __restrict__ keep_logp, long long keep_cap,
+                                                     unsigned long long* __restrict__ keep_count) {
+    __shared__ long long s_idx[PQ_SHORT_RCAP];
+    __shared__ double s_lp[PQ_SHORT_RCAP];
+    __shared__ double s_red[8];
+    __shared__ unsigned int s_n;
+    if (!short_usable(sh, margin_ok)) {
+        if (threadIdx.x == 0) sh->full_pass2 = 1u;
+        return;
+    }
+    if (best_in->index < 0) {                                  // no finite point: nothing is retained
+        if (threadIdx.x == 0) sh->full_pass2 = 0u;
+        return;
+    }
+    const double thr = best_in->logp + log_rel;
+    if (threadIdx.x == 0) s_n = 0u;
+    __syncthreads();
+    const unsigned int nc = (unsigned int)sh->count;
+    for (unsigned int c = threadIdx.x; c < nc; c += blockDim.x) {
+        const double v = c_logp[c];
+        if (v > thr) {
+            const unsigned int slot = atomicAdd(&s_n, 1u);
+            if (slot < PQ_SHORT_RCAP) { s_idx[slot] = c_idx[c]; s_lp[slot] = v; }
+        }
+    }
+    __syncthreads();
+    const unsigned int nr = s_n;
+    if (nr > PQ_SHORT_RCAP) {
+        if (threadIdx.x == 0) sh->full_pass2 = 1u;
+        return;
+    }
+    unsigned int np2 = 1;
+    while (np2 < nr) np2 <<= 1;
+    for (unsigned int c = nr + threadIdx.x; c < np2; c += blockDim.x) { s_idx[c] = 0x7fffffffffffffffLL; s_lp[c] = 0.0; }
+    __syncthreads();
+    for (unsigned int kk = 2; kk <= np2; kk <<= 1) {
+        for (unsigned int j = kk >> 1; j > 0; j >>= 1) {
+            for (unsigned int t = threadIdx.x; t < np2; t += blockDim.x) {
+                const unsigned int x = t ^ j;
+                if (x > t) {
+                    const bool up = (t & kk) == 0;
+                    const long long a = s_idx[t], b = s_idx[x];
+                    if ((a > b) == up) {
+                        s_idx[t] = b; s_idx[x] = a;
+                        const double la = s_lp[t]; s_lp[t] = s_lp[x]; s_lp[x] = la;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    double shift[KT];
+    sweep_point<KT>(S, (unsigned long long)best_in->index, shift);
+    Pass2Acc<KT> A;
+    A.w = A.wexp = A.nk = 0.0;
+#pragma unroll
+    for (int d = 0; d < KT; ++d) { A.s1[d] = 0.0; A.mn[d] = pq_pos_inf(); A.mx[d] = pq_neg_inf(); }
+#pragma unroll
+    for (int e = 0; e < KT * (KT + 1) / 2; ++e) A.s2[e] = 0.0;
+    for (unsigned int c = threadIdx.x; c < nr; c += blockDim.x) {
+        double th[KT];
+        sweep_point<KT>(S, (unsigned long long)s_idx[c], th);
+        pass2_accumulate<KT>(A, S, th, shift, s_lp[c], thr);
+        if (keep_idx && (long long)c < keep_cap) { keep_idx[c] = s_idx[c]; keep_logp[c] = s_lp[c]; }
+    }
+    if (keep_idx && threadIdx.x == 0) *keep_count += nr;
+    const int k = S.k;
+    double t;
+    t = block_sum(A.w, s_red);    if (threadIdx.x == 0) acc_out[PEUQSE_ACC_W] += t;
+    t = block_sum(A.wexp, s_red); if (threadIdx.x == 0) acc_out[PEUQSE_ACC_WEXP] += t;
+    t = block_sum(A.nk, s_red);   if (threadIdx.x == 0) acc_out[PEUQSE_ACC_NKEPT] += t;
+    int e = 0;
+#pragma unroll
+    for (int d = 0; d < KT; ++d) {
+        if (d < k) {
+            t = block_sum(A.s1[d], s_red);
+            if (threadIdx.x == 0) acc_out[PEUQSE_ACC_S1 + d] += t;
+            t = block_min(A.mn[d], s_red);
+            if (threadIdx.x == 0) acc_out[PEUQSE_ACC_MIN(k) + d] = fmin(acc_out[PEUQSE_ACC_MIN(k) + d], t);
+            t = -block_min(-A.mx[d], s_red);
+            if (threadIdx.x == 0) acc_out[PEUQSE_ACC_MAX(k) + d] = fmax(acc_out[PEUQSE_ACC_MAX(k) + d], t);
+        }
+#pragma unroll
+        for (int d2 = d; d2 < KT; ++d2) {
+            if (d < k && d2 < k) {
+                t = block_sum(A.s2[e], s_red);
+                if (threadIdx.x == 0) {
+                    acc_out[PEUQSE_ACC_S2(k) + d * k + d2] += t;
+                    if (d2 != d) acc_out[PEUQSE_ACC_S2(k) + d2 * k + d] += t;
+                }
+            }
+            ++e;
+        }
+    }
+    if (threadIdx.x == 0) sh->full_pass2 = 0u;
+}
+
+// np.histogram bin of x on the given edges (numpy/lib/_histograms_impl.py: index from the normalised position,
+// corrected against the actual edges; the last bin is closed on the right); -1 when x is outside [lo, hi]
+__device__ __forceinline__ int hist_bin(const double* __restrict__ ed, int nbins, double x) {
+    const double lo = ed[0], hi = ed[nbins];
+    if (!(x >= lo && x <= hi)) return -1;
+    int b = (int)(((x - lo) / (hi - lo)) * (double)nbins);
+    if (b >= nbins) b = nbins - 1;
+    if (b < 0) b = 0;
+    if (x < ed[b]) --b;
+    else if (b != nbins - 1 && x >= ed[b + 1]) ++b;
+    return b;
+}
+
+// pass 3 from the shortlist: integer weight sums, so the order of the candidates does not matter
+template <int KT>
+__global__ void __launch_bounds__(256) k_short_hist(const __grid_constant__ DevSweep S, const ShortHdr* __restrict__ sh,
+                                                    const long long* __restrict__ c_idx, const double* __restrict__ c_logp,
+                                                    const peuqse_best* __restrict__ best_in, double log_rel, int margin_ok,
+                                                    const double* __restrict__ edges, int nbins,
+                                                    unsigned long long* __restrict__ hist) {
+    if (!short_usable(sh, margin_ok) || best_in->index < 0) return;
+    const double thr = best_in->logp + log_rel;
+    const unsigned int nc = (unsigned int)sh->count;
+    for (unsigned int c = blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += gridDim.x * blockDim.x) {
+        const double v = c_logp[c];
+        if (!(v > thr)) continue;
+        double th[KT];
+        sweep_point<KT>(S, (unsigned long long)c_idx[c], th);
+        const unsigned long long w = (unsigned long long)trunc(exp(v - thr));
+#pragma unroll
+        for (int d = 0; d < KT; ++d) {
+            if (d < S.k) {
+                const int b = hist_bin(edges + d * (nbins + 1), nbins, th[d]);
+                if (b >= 0) atomicAdd(hist + d * nbins + b, w);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // pass 3: weighted marginal histograms (np.histogram semantics on given edges)
 // ---------------------------------------------------------------------------------------------
 template <int MODEL, int KT>
@@ -277,8 +480,10 @@ __global__ void __launch_bounds__(256) k_sweep_hist(const __grid_constant__ DevP
                                                     long long first, long long count, const double* __restrict__ logp_in,
                                                     const peuqse_best* __restrict__ best_in, double log_rel,
                                                     const double* __restrict__ edges, int nbins,
-                                                    unsigned long long* __restrict__ hist, int use_smem) {
+                                                    unsigned long long* __restrict__ hist, int use_smem,
+                                                    const ShortHdr* __restrict__ shl, int margin_ok) {
     extern __shared__ double smem[];
+    if (short_usable(shl, margin_ok)) return;                  // k_short_hist binned the retained points already
     const ObsView O = stage_obs(P, smem, use_smem);
     // block-private histogram after the staged constants
     unsigned long long* sh = (unsigned long long*)(smem + (use_smem ? pq_obs_doubles(P) : 0));
@@ -307,19 +512,8 @@ __global__ void __launch_bounds__(256) k_sweep_hist(const __grid_constant__ DevP
 #pragma unroll
         for (int d = 0; d < KT; ++d) {
             if (d < k) {
-                const double* ed = edges + d * (nbins + 1);
-                const double lo = ed[0], hi = ed[nbins];
-                const double x = th[d];
-                if (x >= lo && x <= hi) {
-                    // numpy/lib/_histograms_impl.py: index from the normalised position, then corrected
-                    // against the actual edges; the last bin is closed on the right
-                    int b = (int)(((x - lo) / (hi - lo)) * (double)nbins);
-                    if (b >= nbins) b = nbins - 1;
-                    if (b < 0) b = 0;
-                    if (x < ed[b]) --b;
-                    else if (b != nbins - 1 && x >= ed[b + 1]) ++b;
-                    atomicAdd(sh + d * nbins + b, w);
-                }
+                const int b = hist_bin(edges + d * (nbins + 1), nbins, th[d]);
+                if (b >= 0) atomicAdd(sh + d * nbins + b, w);
             }
         }
     }
@@ -338,16 +532,34 @@ inline int sweep_grid(const peuqse_problem* p, long long count) {
     return (int)std::max<long long>(1, std::min<long long>(blocks, std::min<long long>((long long)p->sm_count * 8, PQ_SWEEP_MAX_BLOCKS)));
 }
 
+// linear model with k == KT (even): the instantiation that reads whole rows as double2 (eval.cuh)
+template <int MODEL, int KT>
+struct FullRows {
+    static constexpr int value = (MODEL == PEUQSE_MODEL_LINEAR && KT % 2 == 0) ? PQ_MODEL_LINEAR_FULL : MODEL;
+};
+
 template <int MODEL, int KT>
 int launch_pass1(const peuqse_problem* p, const DevSweep& S, long long first, long long count, double* logp,
                  peuqse_best* best, void* work, cudaStream_t st) {
     int use_smem;
     const size_t smem = pq_pick_smem(p, &use_smem);
-    auto kern = k_sweep_pass1<MODEL, KT>;
+    constexpr int MF = FullRows<MODEL, KT>::value;
+    const bool full = MF != MODEL && p->d.k == KT;
+    void (*kern)(const DevProblem, const DevSweep, long long, long long, double*, peuqse_best*, Best*, unsigned int*, int,
+                 ShortHdr*, long long*, double*) =
+        full ? (use_smem ? k_sweep_pass1<MF, KT, 1> : k_sweep_pass1<MF, KT, -1>)
+             : (use_smem ? k_sweep_pass1<MODEL, KT, 1> : k_sweep_pass1<MODEL, KT, -1>);
     PQ_CUDA_OK(pq_allow_smem((const void*)kern, smem));
     unsigned int* ticket = (unsigned int*)work;
     Best* partial = (Best*)((char*)work + PQ_SWEEP_TICKET_BYTES);
-    kern<<<sweep_grid(p, count), 256, smem, st>>>(p->d, S, first, count, logp, best, partial, ticket, use_smem);
+    // 128-thread CTAs, three per SM (168 registers for the two points a thread carries); 12 CTAs queued per SM
+    const long long want = (count + 2 * P1_THREADS - 1) / (2 * P1_THREADS);
+    const int grid = (int)std::max<long long>(1, std::min<long long>(want, std::min<long long>((long long)p->sm_count * 12, PQ_SWEEP_MAX_BLOCKS)));
+    // logP not kept: shortlist mode (sweep_common.cuh)
+    ShortHdr* sh = logp ? nullptr : (ShortHdr*)((char*)work + PQ_SHORT_HDR_OFFSET);
+    long long* c_idx = (long long*)((char*)work + PQ_SWEEP_BASE_BYTES);
+    double* c_logp = (double*)(c_idx + PQ_SHORT_CAP);
+    kern<<<grid, P1_THREADS, smem, st>>>(p->d, S, first, count, logp, best, partial, ticket, use_smem, sh, c_idx, c_logp);
     PQ_CUDA_OK(cudaGetLastError());
     return PEUQSE_OK;
 }
@@ -362,21 +574,40 @@ int launch_pass2(const peuqse_problem* p, const DevSweep& S, long long first, lo
     PQ_CUDA_OK(pq_allow_smem((const void*)kern, smem));
     unsigned int* ticket = (unsigned int*)work;
     double* partial = (double*)((char*)work + PQ_SWEEP_TICKET_BYTES);
+    ShortHdr* sh = nullptr;
+    if (!logp) {                                                // statistics from pass 1's shortlist when it is usable
+        sh = (ShortHdr*)((char*)work + PQ_SHORT_HDR_OFFSET);
+        const long long* c_idx = (const long long*)((char*)work + PQ_SWEEP_BASE_BYTES);
+        const double* c_logp = (const double*)(c_idx + PQ_SHORT_CAP);
+        k_short_pass2<KT><<<1, 256, 0, st>>>(S, sh, c_idx, c_logp, best, log_rel, (-log_rel <= PQ_SHORT_MARGIN) ? 1 : 0, acc, kidx, klogp,
+                                             kcap, (unsigned long long*)kcount);
+        PQ_CUDA_OK(cudaGetLastError());
+    }
     kern<<<sweep_grid(p, count), 256, smem, st>>>(p->d, S, first, count, logp, best, log_rel, partial, acc, ticket, kidx, klogp, kcap,
-                                                  (unsigned long long*)kcount, use_smem);
+                                                  (unsigned long long*)kcount, use_smem, sh);
     PQ_CUDA_OK(cudaGetLastError());
     return PEUQSE_OK;
 }
 
 template <int MODEL, int KT>
 int launch_hist(const peuqse_problem* p, const DevSweep& S, long long first, long long count, const double* logp,
-                const peuqse_best* best, double log_rel, const double* edges, int nbins, unsigned long long* hist, cudaStream_t st) {
+                const peuqse_best* best, double log_rel, const double* edges, int nbins, unsigned long long* hist, void* work,
+                cudaStream_t st) {
     int use_smem;
     size_t smem = pq_pick_smem(p, &use_smem);
     smem += (size_t)S.k * nbins * sizeof(unsigned long long);
     auto kern = k_sweep_hist<MODEL, KT>;
     PQ_CUDA_OK(pq_allow_smem((const void*)kern, smem));
-    kern<<<sweep_grid(p, count), 256, smem, st>>>(p->d, S, first, count, logp, best, log_rel, edges, nbins, hist, use_smem);
+    const ShortHdr* sh = nullptr;
+    const int margin_ok = (-log_rel <= PQ_SHORT_MARGIN) ? 1 : 0;
+    if (!logp && work) {
+        sh = (const ShortHdr*)((char*)work + PQ_SHORT_HDR_OFFSET);
+        const long long* c_idx = (const long long*)((char*)work + PQ_SWEEP_BASE_BYTES);
+        const double* c_logp = (const double*)(c_idx + PQ_SHORT_CAP);
+        k_short_hist<KT><<<64, 256, 0, st>>>(S, sh, c_idx, c_logp, best, log_rel, margin_ok, edges, nbins, hist);
+        PQ_CUDA_OK(cudaGetLastError());
+    }
+    kern<<<sweep_grid(p, count), 256, smem, st>>>(p->d, S, first, count, logp, best, log_rel, edges, nbins, hist, use_smem, sh, margin_ok);
     PQ_CUDA_OK(cudaGetLastError());
     return PEUQSE_OK;
 }
@@ -390,7 +621,8 @@ extern "C" int64_t peuqse_sweep_work_bytes(const peuqse_problem* p, const peuqse
         long long total;
         if (build_sweep(spec, &S, &total) == PEUQSE_OK) aux = pq_grid_aux_bytes(p, S, first, count);
     }
-    return PQ_SWEEP_BASE_BYTES + aux;
+    const long long shortlist = PQ_SHORT_CAP * 16LL;          // (index, logP) entries of the no-store mode
+    return PQ_SWEEP_BASE_BYTES + std::max(aux, shortlist);
 }
 
 #define PQ_SWEEP_DISPATCH(CALL_Q, CALL_T, CALL_L, CALL_E)                                         \
@@ -484,7 +716,7 @@ extern "C" int peuqse_sweep_pass2(const peuqse_problem* p, const peuqse_sweep_sp
                            (long long*)d_keep_index, d_keep_logp, keep_capacity, (long long*)d_keep_count, d_work, st, &handled);
         if (rc || handled) return rc;
     }
-    PQ_CUDA_OK(cudaMemsetAsync(d_work, 0, PQ_SWEEP_TICKET_BYTES, st));
+    PQ_CUDA_OK(cudaMemsetAsync(d_work, 0, PQ_SHORT_HDR_OFFSET, st));   // the ticket; pass 1's shortlist header stays
     if (count == 0) return PEUQSE_OK;
 #define P2_ARGS p, S, first, count, d_logp, d_best, log_rel_threshold, d_acc, (long long*)d_keep_index, d_keep_logp, keep_capacity, (long long*)d_keep_count, d_work, st
 #define P2_L(KT, ...) return launch_pass2<PEUQSE_MODEL_LINEAR, KT>(P2_ARGS)
@@ -516,7 +748,7 @@ extern "C" int peuqse_sweep_hist(const peuqse_problem* p, const peuqse_sweep_spe
         if (rc || handled) return rc;
     }
     if (count == 0) return PEUQSE_OK;
-#define P3_ARGS p, S, first, count, d_logp, d_best, log_rel_threshold, d_edges, nbins, (unsigned long long*)d_hist, st
+#define P3_ARGS p, S, first, count, d_logp, d_best, log_rel_threshold, d_edges, nbins, (unsigned long long*)d_hist, d_work, st
 #define P3_L(KT, ...) return launch_hist<PEUQSE_MODEL_LINEAR, KT>(P3_ARGS)
 #define P3_E(KT, ...) return launch_hist<PEUQSE_MODEL_EXTERNAL, KT>(P3_ARGS)
     PQ_SWEEP_DISPATCH((launch_hist<PEUQSE_MODEL_QUADRATIC, 2>(P3_ARGS)), (launch_hist<PEUQSE_MODEL_TPD2SITE, 6>(P3_ARGS)), P3_L, P3_E)

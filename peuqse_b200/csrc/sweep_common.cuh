@@ -7,6 +7,25 @@
 #define PQ_SWEEP_TICKET_BYTES 256
 #define PQ_ACC_MAX PEUQSE_ACC_DOUBLES(PQ_MAXK)
 
+// Shortlist of a sweep whose logP is not kept in HBM (sweep.cu): while pass 1 runs, every point whose logP is within
+// PQ_SHORT_MARGIN of the best value seen so far (a lower bound of the final maximum, shared through one 64-bit
+// atomicMax key) is appended as (index, logP).  The final threshold max + log(10^-coef) is >= best-so-far - margin
+// whenever -log_rel <= margin, so the list is a superset of the retained points and passes 2-3 read it instead of
+// evaluating every point again.  Header at d_work + PQ_SHORT_HDR_OFFSET (inside the 256-byte ticket area, never
+// overlapping the grid kernels' aux data); entries at d_work + PQ_SWEEP_BASE_BYTES (that region is only used by
+// the grid kernels when logP IS stored).
+#define PQ_SHORT_HDR_OFFSET 64
+#define PQ_SHORT_VALID_WORD ((PQ_SHORT_HDR_OFFSET + 16) / 4)
+#define PQ_SHORT_CAP (1LL << 20)
+#define PQ_SHORT_RCAP 2048
+#define PQ_SHORT_MARGIN 50.0
+struct ShortHdr {
+    unsigned long long gmax_key;   // order-preserving key of the best logP published so far (0 = none)
+    unsigned long long count;      // entries appended; > PQ_SHORT_CAP means overflow (list unusable)
+    unsigned int valid;            // pass 1 finished in shortlist mode on this work buffer
+    unsigned int full_pass2;       // set by k_short_pass2: the statistics must be recomputed from all points
+};
+
 struct FastDiv {            // unsigned 64-bit division by an invariant (Granlund & Montgomery 1994, fig. 4.1)
     unsigned long long m;
     int sh1, sh2;

@@ -97,6 +97,7 @@ __device__ __forceinline__ void block_store_best(Best best, Best* s_best, bool* 
             best_out->logp = b.v;
             best_out->index = (b.i == 0x7fffffffffffffffLL) ? -1 : b.i;
             *ticket = 0;
+            ticket[PQ_SHORT_VALID_WORD] = 0u;                  // this pass 1 leaves no shortlist (sweep_common.cuh)
         }
     }
 }

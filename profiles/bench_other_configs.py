@@ -69,6 +69,12 @@ if "c5" in which:
     ms = ev_time(sw.pass1, n=2)
     out["c5_pass1_evals_per_s"] = N / (ms * 1e-3)
     out["c5_pass1_ms_for_2^27"] = ms
+    lr = float(np.log(10 ** -2.0))
+    ms = ev_time(lambda: sw.step(lr, True), n=2)
+    out["c5_whole_sweep_ms_for_2^27"] = ms
+    out["c5_whole_sweep_evals_per_s"] = N / (ms * 1e-3)
+    R = sw.unpack(sw.res.cpu().numpy(), 2.0)
+    out["c5_n_retained"] = R.n_retained
 if "c4" in which:
     from oracle import peuqse_oracle as orc
     k, n = 12, 4096

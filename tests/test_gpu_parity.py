@@ -279,7 +279,7 @@ def test_mh_example00_step_for_step(env, golden):
     mom = PE.mcmc_chain_moments
     np.testing.assert_allclose(mom['mean'], np.mean(PE.post_burn_in_samples, axis=0), rtol=1e-12)
     np.testing.assert_allclose(mom['std'], np.std(PE.post_burn_in_samples, axis=0), rtol=1e-10)
-    assert mom['map_logP'] == float(PE.map_logP)
+    assert mom['map_logP'] == float(np.ravel(PE.map_logP)[0])
 
 
 def test_mh_tpd_step_for_step(env, golden):
@@ -657,3 +657,54 @@ def test_c5_uniform_sweep_properties(env):
         bests.append((float(b[0]), int(b.view(torch.int64)[1])))
     assert D.merge_best(bests) == (PE.map_logP, PE.map_index)
     assert PE.sweep_result.sum_weights >= 100 - 1
+
+
+@pytest.mark.parametrize("case", ["sparse", "dense"])
+def test_uniform_sweep_without_stored_logp(env, case):
+    """multistart_store_logP=False: pass 1 keeps a shortlist of near-maximal points and passes 2-3 read it ("sparse":
+    10-D, a handful of retained points); when more than the shortlist's sort capacity are retained ("dense": 2-D, broad
+    posterior) the recomputing kernels take over.  Either way the results must be those of the stored-logP sweep."""
+    PEUQSE, orc, philox_np, torch = env
+    from peuqse_b200.sweep import Sweep
+    if case == "sparse":
+        k, n, N = 10, 64, 1 << 22
+        Phi = orc.cos_basis(n, k)
+        truth = np.random.default_rng(5).standard_normal(k) * 0.5
+        y = Phi @ truth + 0.1 * np.random.default_rng(6).standard_normal(n)
+        PE = make_pe(PEUQSE, PEUQSE.LinearModel(Phi), list(y), list(np.full(n, 0.1)), [0.0] * k, [1.0] * k,
+                     settings={'multistart_initialPointsDistributionType': 'uniform', 'multistart_numStartPoints': N,
+                               'multistart_random_seed': 3})
+    else:
+        k, N = 2, 1 << 20
+        PE = make_pe(PEUQSE, PEUQSE.QuadraticModel(X00), Y00, S00, [200, 500], [100, 200],
+                     settings={'multistart_initialPointsDistributionType': 'uniform', 'multistart_numStartPoints': N,
+                               'multistart_random_seed': 3})
+    PE.doMultiStart()
+    A = PE.sweep_result
+    spec = PE._sweep.spec
+    for shard in (None, (1, 3)):
+        ref = Sweep(PE.device_problem, spec, N, store_logp=True, shard=shard)
+        new = Sweep(PE.device_problem, spec, N, store_logp=False, shard=shard)
+        ref.use_graph = new.use_graph = False
+        Rr, Rn = ref.run(2.0), new.run(2.0)
+        assert (Rn.map_logP, Rn.map_index) == (Rr.map_logP, Rr.map_index)
+        assert Rn.n_retained == Rr.n_retained and Rn.sum_weights == Rr.sum_weights
+        assert (Rn.n_retained > 2048) == (case == "dense")
+        assert np.array_equal(Rn.histogram_counts, Rr.histogram_counts)
+        assert np.array_equal(Rn.histogram_edges, Rr.histogram_edges)
+        np.testing.assert_allclose(Rn.mu_AP_parameter_set, Rr.mu_AP_parameter_set, rtol=1e-13)
+        np.testing.assert_allclose(Rn.stdap_parameter_set, Rr.stdap_parameter_set, rtol=1e-10)
+        np.testing.assert_allclose(Rn.evidence, Rr.evidence, rtol=1e-12)
+        if shard is None:
+            assert (Rn.map_logP, Rn.map_index) == (A.map_logP, A.map_index)
+        # a second run on the same work buffer (header and list are rebuilt by pass 1)
+        Rn2 = new.run(2.0)
+        assert Rn2.n_retained == Rr.n_retained and np.array_equal(Rn2.histogram_counts, Rr.histogram_counts)
+        np.testing.assert_array_equal(Rn2.mu_AP_parameter_set, Rn.mu_AP_parameter_set)
+    # a threshold wider than the shortlist margin (coef 25 -> 57.6 nats) must fall back to recomputation
+    ref = Sweep(PE.device_problem, spec, N, store_logp=True)
+    new = Sweep(PE.device_problem, spec, N, store_logp=False)
+    ref.use_graph = new.use_graph = False
+    Rr, Rn = ref.run(25.0), new.run(25.0)
+    assert Rn.n_retained == Rr.n_retained
+    np.testing.assert_allclose(Rn.mu_AP_parameter_set, Rr.mu_AP_parameter_set, rtol=1e-12)
