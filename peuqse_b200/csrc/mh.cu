@@ -40,13 +40,15 @@ struct ChainStats {
 #pragma unroll
         for (int e = 0; e < KT * (KT + 1) / 2; ++e) s2[e] = 0.0;
     }
-    __device__ __forceinline__ void add_row(int k, long long row, const double (&th)[KT], const double (&th0)[KT], double lp) {
+    // explp = exp(lp), computed by the caller when lp last changed (an unchanged chain state repeats the same value)
+    __device__ __forceinline__ void add_row(int k, long long row, const double (&th)[KT], const double (&th0)[KT], double lp,
+                                            double explp) {
         if (lp > maplogp) {                                    // first maximum (list.index of max, IP.py:1925-1927)
             maplogp = lp; maprow = (double)row;
 #pragma unroll
             for (int d = 0; d < KT; ++d) maptheta[d] = th[d];
         }
-        sumexp += exp(lp);
+        sumexp += explp;
         int e = 0;
 #pragma unroll
         for (int d = 0; d < KT; ++d) {
@@ -151,8 +153,11 @@ __global__ void __launch_bounds__(128) k_mh(const __grid_constant__ DevProblem P
         if (out.logp) out.logp[c] = lp0;
         if (out.lprior) out.lprior[c] = 0.0;
         if (out.llik) out.llik[c] = 0.0;
-        if (M.burn_in <= 0) st.add_row(k, 0, th, th0, lp0);
+        if (M.burn_in <= 0) st.add_row(k, 0, th, th0, lp0, exp(lp0));
     }
+    double cur_exp = exp(cur_sum);                               // exp(logP) of the current state, for the evidence sum
+    long long next_row = 1;                                      // rows are written every thin-th step
+    int until_row = M.thin;
     for (long long i = 1; i < M.n_steps; ++i) {
         double z[KT], delta[KT], prop[KT], u;
         const unsigned long long step = (unsigned long long)(M.first_step + i);
@@ -170,6 +175,7 @@ __global__ void __launch_bounds__(128) k_mh(const __grid_constant__ DevProblem P
 #pragma unroll
             for (int d = 0; d < KT; ++d) th[d] = prop[d];
             cur_lp = lp_p; cur_ll = ll_p; cur_sum = sum_p;
+            cur_exp = exp(cur_sum);
             st.nacc += 1.0;
         }
         if (out.deltas) {
@@ -177,8 +183,9 @@ __global__ void __launch_bounds__(128) k_mh(const __grid_constant__ DevProblem P
             for (int d = 0; d < KT; ++d) if (d < k) out.deltas[((i - 1) * C + c) * k + d] = delta[d];
         }
         if (out.us) out.us[(i - 1) * C + c] = u;
-        if (i % M.thin == 0) {
-            const long long row = i / M.thin;
+        if (--until_row == 0) {
+            until_row = M.thin;
+            const long long row = next_row++;
             if (out.samples) {
 #pragma unroll
                 for (int d = 0; d < KT; ++d) if (d < k) out.samples[(row * C + c) * k + d] = th[d];
@@ -187,7 +194,7 @@ __global__ void __launch_bounds__(128) k_mh(const __grid_constant__ DevProblem P
             if (out.lprior) out.lprior[row * C + c] = cur_lp;
             if (out.llik) out.llik[row * C + c] = cur_ll;
         }
-        if (i >= M.burn_in) st.add_row(k, i, th, th0, cur_sum);
+        if (i >= M.burn_in) st.add_row(k, i, th, th0, cur_sum, cur_exp);
     }
     st.store(k, out.stats + c * PEUQSE_MH_STAT_DOUBLES(k), th, cur_sum);
 }
@@ -203,6 +210,7 @@ __global__ void __launch_bounds__(128) k_mh(const __grid_constant__ DevProblem P
 // The arithmetic on every value is that of the thread shape, so both shapes walk the same trajectory.
 // ---------------------------------------------------------------------------------------------
 #define MHW_WARPS 4
+#define MH_FEW_CHAINS 8192   // below this the thread shape cannot fill the fp64 pipe (one warp step ~4000 cycles)
 template <int KT>
 struct MhwLayout {
     static constexpr int NPAIR = KT * (KT + 1) / 2;
@@ -212,7 +220,11 @@ struct MhwLayout {
     static constexpr int WDOUBLES = 2 * KPAD + 64;       // cur[KPAD] | th0[KPAD] | draws[32][2]
 };
 
-template <int MODEL, int KT, int U, int SMEM>
+// TEVAL: every lane evaluates the whole likelihood in the thread shape's order (few observations, few chains):
+// the values are bit-identical to k_mh's, and what the warp buys is latency -- draws for four steps per pass and
+// lane-spread moments cut a chain step from ~4000 to a few hundred cycles when there are too few chains to fill
+// the machine with one thread each.
+template <int MODEL, int KT, int U, int SMEM, bool TEVAL = false>
 __global__ void __launch_bounds__(32 * MHW_WARPS, 4) k_mh_warp(const __grid_constant__ DevProblem P,
                                                                const __grid_constant__ DevMH M,
                                                                const double* __restrict__ theta0, const MHOut out,
@@ -259,14 +271,14 @@ __global__ void __launch_bounds__(32 * MHW_WARPS, 4) k_mh_warp(const __grid_cons
     double nacc = 0.0, maplogp = pq_neg_inf(), maprow = -1.0, sumexp = 0.0, mapth = 0.0;
 
     double cur_lp = eval_prior<KT>(P, th);
-    double cur_ll = eval_loglik_warp<MODEL, KT, U>(P, O, th, nullptr, lane);
+    double cur_ll = TEVAL ? eval_loglik_thread<MODEL, KT>(P, O, th, nullptr) : eval_loglik_warp<MODEL, KT, U>(P, O, th, nullptr, lane);
     double cur_sum = cur_ll + cur_lp;
-    auto add_row = [&](long long row, double lp) {
+    auto add_row = [&](long long row, double lp, double explp) {
         if (lp > maplogp) {                                       // first maximum (IP.py:1925-1927)
             maplogp = lp; maprow = (double)row;
             if (lane < KT) mapth = cur[lane];
         }
-        sumexp += exp(lp);
+        sumexp += explp;
 #pragma unroll
         for (int q = 0; q < L::NACC; ++q) acc[q] = fma(va[q], vb[q], acc[q]);   // first moments: fma(dd, 1, s1) == s1 + dd
     };
@@ -281,8 +293,11 @@ __global__ void __launch_bounds__(32 * MHW_WARPS, 4) k_mh_warp(const __grid_cons
             if (out.lprior) out.lprior[c] = 0.0;
             if (out.llik) out.llik[c] = 0.0;
         }
-        if (M.burn_in <= 0) add_row(0, lp0);
+        if (M.burn_in <= 0) add_row(0, lp0, exp(lp0));
     }
+    double cur_exp = exp(cur_sum);
+    long long next_row = 1;
+    int until_row = M.thin;
     const int sub = lane >> 3, blk = lane & 7;
     for (long long i = 1; i < M.n_steps; ++i) {
         const int g = (int)((i - 1) & 3);
@@ -312,7 +327,8 @@ __global__ void __launch_bounds__(32 * MHW_WARPS, 4) k_mh_warp(const __grid_cons
 #pragma unroll
         for (int d = 0; d < KT; ++d) prop[d] = th[d] + delta[d];  // IP.py:2630
         const double lp_p = eval_prior<KT>(P, prop);
-        const double ll_p = eval_loglik_warp<MODEL, KT, U>(P, O, prop, nullptr, lane);
+        const double ll_p = TEVAL ? eval_loglik_thread<MODEL, KT>(P, O, prop, nullptr)
+                                  : eval_loglik_warp<MODEL, KT, U>(P, O, prop, nullptr, lane);
         const double sum_p = ll_p + lp_p;
         double la = sum_p - cur_sum;                              // IP.py:2641
         if (M.modulate != 0.0) la = (1.0 / M.modulate) * la;      // IP.py:2649
@@ -321,6 +337,7 @@ __global__ void __launch_bounds__(32 * MHW_WARPS, 4) k_mh_warp(const __grid_cons
 #pragma unroll
             for (int d = 0; d < KT; ++d) th[d] = prop[d];
             cur_lp = lp_p; cur_ll = ll_p; cur_sum = sum_p;
+            cur_exp = exp(cur_sum);
             nacc += 1.0;
             __syncwarp();
             if (lane == 0) {
@@ -342,8 +359,11 @@ __global__ void __launch_bounds__(32 * MHW_WARPS, 4) k_mh_warp(const __grid_cons
                 for (int d = 0; d < KT; ++d) if (d < k) out.deltas[((i - 1) * C + c) * k + d] = delta[d];
             }
             if (out.us) out.us[(i - 1) * C + c] = uu.x;
-            if (i % M.thin == 0) {
-                const long long row = i / M.thin;
+        }
+        if (--until_row == 0) {
+            until_row = M.thin;
+            const long long row = next_row++;
+            if (lane == 0) {
                 if (out.samples) {
 #pragma unroll
                     for (int d = 0; d < KT; ++d) if (d < k) out.samples[(row * C + c) * k + d] = th[d];
@@ -353,7 +373,7 @@ __global__ void __launch_bounds__(32 * MHW_WARPS, 4) k_mh_warp(const __grid_cons
                 if (out.llik) out.llik[row * C + c] = cur_ll;
             }
         }
-        if (i >= M.burn_in) add_row(i, cur_sum);
+        if (i >= M.burn_in) add_row(i, cur_sum, cur_exp);
     }
     double* so = out.stats + c * PEUQSE_MH_STAT_DOUBLES(k);
     if (lane == 0) {
@@ -385,9 +405,12 @@ template <int MODEL, int KT>
 int launch_mh(const peuqse_problem* p, const DevMH& M, const double* th0, const MHOut& out, cudaStream_t st) {
     int use_smem;
     const size_t smem = pq_pick_smem(p, &use_smem);
-    if (p->d.n_total > PQ_THREAD_SHAPE_MAX_N) {
+    // few chains with few observations: one warp per chain, thread-order evaluation (latency); many: one thread per chain
+    const bool few = M.n_chains <= MH_FEW_CHAINS;
+    if (p->d.n_total > PQ_THREAD_SHAPE_MAX_N || few) {
         void (*kern)(const DevProblem, const DevMH, const double*, const MHOut, int) = k_mh_warp<MODEL, KT, 2, -1>;
-        if (use_smem) kern = k_mh_warp<MODEL, KT, 2, 1>;
+        if (p->d.n_total <= PQ_THREAD_SHAPE_MAX_N) kern = k_mh_warp<MODEL, KT, 2, -1, true>;
+        else if (use_smem) kern = k_mh_warp<MODEL, KT, 2, 1>;
         const size_t wsmem = smem + (size_t)MHW_WARPS * MhwLayout<KT>::WDOUBLES * sizeof(double);
         PQ_CUDA_OK(pq_allow_smem((const void*)kern, wsmem));
         const long long blocks = (M.n_chains + MHW_WARPS - 1) / MHW_WARPS;

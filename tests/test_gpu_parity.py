@@ -708,3 +708,31 @@ def test_uniform_sweep_without_stored_logp(env, case):
     Rr, Rn = ref.run(25.0), new.run(25.0)
     assert Rn.n_retained == Rr.n_retained
     np.testing.assert_allclose(Rn.mu_AP_parameter_set, Rr.mu_AP_parameter_set, rtol=1e-12)
+
+
+def test_mh_kernel_shapes_agree(env):
+    """The two Metropolis-Hastings kernel shapes for small n -- one warp per chain with thread-order evaluation
+    (<= 8192 chains) and one thread per chain (more) -- must produce the same chains bit for bit: draws are
+    addressed by (seed, chain, step) and every value goes through the same operations in the same order."""
+    PEUQSE, orc, _, torch = env
+    from peuqse_b200.mcmc import mh_launch, step_cholesky
+    PE = make_pe(PEUQSE, PEUQSE.QuadraticModel(X00), Y00, S00, [200, 500], [100, 200])
+    rng = np.random.default_rng(11)
+    th0 = np.array([200.0, 500.0]) + rng.standard_normal((8200, 2)) * [30.0, 60.0]
+    L = step_cholesky(PE.Q_covmat, 0.3)
+    few = mh_launch(PE, th0[:300], 400, 100, 5, L, thin=3, export_draws=True)
+    many = mh_launch(PE, th0, 400, 100, 5, L, thin=3, export_draws=True)
+    for key in ('samples', 'logp', 'logprior', 'loglik', 'deltas', 'us'):
+        a, b = few[key].cpu().numpy(), many[key].cpu().numpy()[:, :300]
+        assert np.array_equal(a, b), key
+    assert np.array_equal(few['stats'].cpu().numpy(), many['stats'].cpu().numpy()[:300])
+    # k = 10 linear model: more than 32 moment slots per chain (two per lane)
+    k, n = 10, 64
+    Phi = orc.cos_basis(n, k)
+    y = Phi @ (0.5 * rng.standard_normal(k)) + 0.1 * rng.standard_normal(n)
+    PE = make_pe(PEUQSE, PEUQSE.LinearModel(Phi), list(y), list(np.full(n, 0.1)), [0.0] * k, [1.0] * k)
+    th0 = 0.1 * rng.standard_normal((8200, k))
+    L = step_cholesky(PE.Q_covmat, 1e-3)
+    few = mh_launch(PE, th0[:200], 150, 30, 9, L, store_samples=False)
+    many = mh_launch(PE, th0, 150, 30, 9, L, store_samples=False)
+    assert np.array_equal(few['stats'].cpu().numpy(), many['stats'].cpu().numpy()[:200])
