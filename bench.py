@@ -231,7 +231,8 @@ def run_ours(args):
     PE = PEUQSE.parameter_estimation(UI)
 
     spec = make_spec("grid", 2, [float(MU[0]), float(MU[1])], interval=INTERVAL, radii=radii)
-    sw = Sweep(PE.device_problem, spec, total, store_logp=True, nbins=10)
+    pieces = int(os.environ.get('PEUQSE_BENCH_PIECES', '1'))
+    sw = Sweep(PE.device_problem, spec, total, store_logp=True, nbins=10, pieces=pieces)
     log_rel = float(np.log(10 ** -2.0))
 
     def barrier():
@@ -320,7 +321,9 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": workload_name(n_gpus), "points_per_gpu": sw.count,
                        "l2": "inputs larger than L2: the 800 MB logP buffer is rewritten and re-read every step",
-                       "parallelism": f"index-range sharding x{n_gpus}, 3 tiny NCCL collectives per step" if n_gpus > 1 else "single GPU"},
+                       "parallelism": (f"index-range sharding x{n_gpus}, 3 tiny exchanges per step ("
+                                       + ("push-wait-merge kernels over NVLink peer memory" if getattr(sw, "peer", None) is not None
+                                          else "NCCL") + ")") if n_gpus > 1 else "single GPU"},
             "roofline": roofline, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "PE_object.doMultiStart()", "steps": Ke, "ms_per_step": 1e3 * dt / Ke},

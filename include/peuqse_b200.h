@@ -230,6 +230,26 @@ int peuqse_comm_allgather(peuqse_comm* c, const void* d_send, void* d_recv /*[wo
 int peuqse_comm_allreduce_sum_i64(peuqse_comm* c, void* d_buf, int64_t count, void* stream);
 
 /*
+ * Peer-memory exchange (ranks on one NVLink/NVSwitch node, world <= 16): the sweep's three tiny collectives as ONE
+ * kernel each -- push this rank's payload into every peer's mailbox with remote stores, raise a sequence flag, wait for
+ * the peers' flags, merge -- instead of an NCCL collective plus a merge kernel.  replaces: the pickle-file gather +
+ * "keep only the best" / concatenate of consolidate_parallel_sampling_data (IP.py:1209-1319).
+ * Setup: every rank calls peuqse_peer_alloc (a zeroed mailbox in its device memory + its 64-byte CUDA IPC handle),
+ * the handles are all-gathered by any means, then peuqse_peer_create maps the peers' mailboxes.  Every rank must issue
+ * the same exchanges in the same order.  A peer that does not arrive within 5 s poisons the result (NaN / index -1)
+ * instead of hanging the device.  The exchange calls are not capturable in a CUDA graph (the sequence number is an
+ * argument).
+ */
+typedef struct peuqse_peer peuqse_peer;
+int peuqse_peer_alloc(void** d_local, void* handle64);
+int peuqse_peer_create(void* d_local, const void* handles /*[world][64]*/, int32_t rank, int32_t world, peuqse_peer** out);
+int peuqse_peer_destroy(peuqse_peer* p);    /* also frees the local mailbox */
+int64_t peuqse_peer_max_bytes(void);        /* largest payload of one exchange */
+int peuqse_peer_merge_best(peuqse_peer* p, peuqse_best* d_best /*in: local, out: merged*/, void* stream);
+int peuqse_peer_merge_acc(peuqse_peer* p, double* d_acc /*PEUQSE_ACC_DOUBLES(k), in/out*/, int32_t k, void* stream);
+int peuqse_peer_sum_i64(peuqse_peer* p, void* d_buf /*count int64, in/out*/, int64_t count, void* stream);
+
+/*
  * Multi-GPU merges (replace consolidate_parallel_sampling_data's "keep the best" / stacking, IP.py:1209-1319):
  * d_all holds the all-gathered per-rank records; the merged record is what a single process would have produced
  * (highest logP, lowest index among equals; sums added in rank order, min/max slots reduced accordingly).

@@ -96,6 +96,7 @@ parameter_estimation_settings = {
     'mcmc_store_samples': 'auto',      # 'auto': keep every row while it fits comfortably in device memory
     'mcmc_thin': 1,
     'multistart_store_logP': 'auto',   # materialise logP of every sweep point in HBM ('auto': when <= 2^31 points)
+    'multistart_shard_pieces': 'auto', # multi-GPU: index-range pieces per rank, dealt round-robin ('auto': 1 = one contiguous range; more balances pass 2-3 of centre-heavy grids at the cost of extra launches)
     'multistart_random_seed': None,    # Philox seed of the uniform sweep (None -> mcmc_random_seed or 0)
     'multistart_histogram_bins': 10,
 }

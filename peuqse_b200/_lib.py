@@ -75,7 +75,8 @@ EXPORTS = [
     "peuqse_logp_batch", "peuqse_logp_from_sim", "peuqse_simulate_batch", "peuqse_sweep_work_bytes",
     "peuqse_sweep_pass1", "peuqse_sweep_best_point", "peuqse_sweep_points", "peuqse_sweep_pass2", "peuqse_sweep_edges", "peuqse_sweep_hist",
     "peuqse_comm_unique_id", "peuqse_comm_create", "peuqse_comm_destroy", "peuqse_comm_allgather",
-    "peuqse_comm_allreduce_sum_i64", "peuqse_merge_best", "peuqse_merge_acc", "peuqse_mh_run",
+    "peuqse_comm_allreduce_sum_i64", "peuqse_peer_alloc", "peuqse_peer_create", "peuqse_peer_destroy",
+    "peuqse_peer_max_bytes", "peuqse_peer_merge_best", "peuqse_peer_merge_acc", "peuqse_peer_sum_i64", "peuqse_merge_best", "peuqse_merge_acc", "peuqse_mh_run",
     "peuqse_philox_blocks", "peuqse_ess_work_bytes", "peuqse_ess_run",
 ]
 
@@ -124,6 +125,14 @@ def load():
     L.peuqse_comm_destroy.argtypes = [vp]
     L.peuqse_comm_allgather.argtypes = [vp, vp, vp, i64, vp]
     L.peuqse_comm_allreduce_sum_i64.argtypes = [vp, vp, i64, vp]
+    L.peuqse_peer_alloc.argtypes = [C.POINTER(vp), vp]
+    L.peuqse_peer_create.argtypes = [vp, vp, i32, i32, C.POINTER(vp)]
+    L.peuqse_peer_destroy.argtypes = [vp]
+    L.peuqse_peer_max_bytes.argtypes = []
+    L.peuqse_peer_max_bytes.restype = i64
+    L.peuqse_peer_merge_best.argtypes = [vp, vp, vp]
+    L.peuqse_peer_merge_acc.argtypes = [vp, vp, i32, vp]
+    L.peuqse_peer_sum_i64.argtypes = [vp, vp, i64, vp]
     L.peuqse_merge_best.argtypes = [vp, i32, vp, vp]
     L.peuqse_merge_acc.argtypes = [vp, i32, i32, vp, vp]
     L.peuqse_mh_run.argtypes = [vp, C.POINTER(MHSpec), vp, vp, vp, vp, vp, vp, vp, vp, vp]

@@ -1,0 +1,193 @@
+// Peer-memory exchange for the three tiny collectives of a sharded multistart (best record, moment accumulator,
+// histogram): ONE kernel per exchange pushes this rank's payload straight into every peer's mailbox over
+// NVLink/NVSwitch (plain remote stores into memory mapped with CUDA IPC), raises a per-sender sequence flag, waits
+// for the peers' flags and merges the gathered payloads -- instead of an NCCL collective followed by a merge kernel.
+// Replaces the pickle-file rendezvous of consolidate_parallel_sampling_data (IP.py:1130-1155, 1209-1319).
+//
+// Mailbox of a rank (device memory it owns, zero-initialised):
+//   data [2 slots][PQ_PEER_MAX_WORLD senders][PQ_PEER_PAYLOAD bytes]
+//   flag [2 slots][PQ_PEER_MAX_WORLD senders]  (uint64 sequence number of the payload in that cell)
+// Exchange number q (1, 2, ... identical on all ranks: every rank issues the same exchanges in the same order) uses
+// slot q & 1.  A rank starts exchange q+2 only after its wait in q+1 saw every peer's flag q+1, i.e. after every peer
+// finished reading slot q & 1 in exchange q (a rank reads before it pushes the next exchange), so two slots suffice.
+// The wait is bounded (PQ_PEER_TIMEOUT_NS): a dead peer poisons the result instead of hanging the GPU.
+#include <cstring>
+#include "common.cuh"
+
+#define PQ_PEER_MAX_WORLD 16
+#define PQ_PEER_PAYLOAD 8192
+#define PQ_PEER_DATA_BYTES (2LL * PQ_PEER_MAX_WORLD * PQ_PEER_PAYLOAD)
+#define PQ_PEER_FLAG_BYTES (2LL * PQ_PEER_MAX_WORLD * 8)
+#define PQ_PEER_BYTES (PQ_PEER_DATA_BYTES + PQ_PEER_FLAG_BYTES + 64)
+#define PQ_PEER_TIMEOUT_NS 5000000000ULL
+
+struct PeerView {
+    int rank, world;
+    unsigned char* box[PQ_PEER_MAX_WORLD];    // box[r]: rank r's mailbox as mapped into this process (box[rank] is local)
+};
+
+struct peuqse_peer {
+    PeerView v;
+    unsigned long long seq;
+    void* local;
+    bool opened[PQ_PEER_MAX_WORLD];
+};
+
+__device__ __forceinline__ unsigned long long* peer_data(unsigned char* box, int slot, int sender) {
+    return reinterpret_cast<unsigned long long*>(box + ((size_t)slot * PQ_PEER_MAX_WORLD + sender) * PQ_PEER_PAYLOAD);
+}
+__device__ __forceinline__ unsigned long long* peer_flag(unsigned char* box, int slot, int sender) {
+    return reinterpret_cast<unsigned long long*>(box + PQ_PEER_DATA_BYTES) + slot * PQ_PEER_MAX_WORLD + sender;
+}
+__device__ __forceinline__ unsigned long long peer_now() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+enum { PEER_OP_BEST = 0, PEER_OP_ACC = 1, PEER_OP_SUM_I64 = 2 };
+
+// io: this rank's payload (n8 8-byte words) in, the merged result out
+template <int OP>
+__global__ void __launch_bounds__(256) k_peer_exchange(const __grid_constant__ PeerView V, unsigned long long* __restrict__ io,
+                                                       int n8, unsigned long long seq, int k) {
+    __shared__ int s_ok;
+    const int slot = (int)(seq & 1ULL), me = V.rank, W = V.world;
+    if (threadIdx.x == 0) s_ok = 1;
+    // push my payload into every mailbox (my own included)
+    for (int idx = threadIdx.x; idx < W * n8; idx += blockDim.x) {
+        const int r = idx / n8, w = idx - r * n8;
+        *(volatile unsigned long long*)(peer_data(V.box[r], slot, me) + w) = io[w];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < W) {
+        *(volatile unsigned long long*)peer_flag(V.box[threadIdx.x], slot, me) = seq;
+        // wait for sender threadIdx.x's payload in my mailbox
+        volatile unsigned long long* f = peer_flag(V.box[me], slot, threadIdx.x);
+        const unsigned long long t0 = peer_now();
+        while (*f < seq) {
+            if (peer_now() - t0 > PQ_PEER_TIMEOUT_NS) { s_ok = 0; break; }
+        }
+    }
+    __syncthreads();
+    __threadfence_system();
+    unsigned char* mine = V.box[me];
+    if (!s_ok) {                                               // a peer never arrived: poison the result
+        for (int w = threadIdx.x; w < n8; w += blockDim.x) io[w] = 0xFFF8000000000000ULL;
+        if (OP == PEER_OP_BEST && threadIdx.x == 0) io[1] = (unsigned long long)(-1LL);
+        return;
+    }
+    if (OP == PEER_OP_BEST) {                                  // highest logP, lowest index among equals (IP.py:933)
+        if (threadIdx.x < 32) {
+            Best b = best_none();
+            for (int r = threadIdx.x; r < W; r += 32) {
+                volatile unsigned long long* d = peer_data(mine, slot, r);
+                Best o;
+                o.v = __longlong_as_double((long long)d[0]);
+                o.i = (long long)d[1];
+                if (o.i < 0) { o.i = 0x7fffffffffffffffLL; o.v = pq_neg_inf(); }
+                b = best_merge(b, o);
+            }
+            b = warp_best(b);
+            if (threadIdx.x == 0) {
+                io[0] = (unsigned long long)__double_as_longlong(b.v);
+                io[1] = (unsigned long long)((b.i == 0x7fffffffffffffffLL) ? -1LL : b.i);
+            }
+        }
+    } else if (OP == PEER_OP_ACC) {                            // sums / minima / maxima by slot, fixed rank order
+        const int mn0 = PEUQSE_ACC_MIN(k), mx0 = PEUQSE_ACC_MAX(k);
+        for (int a = threadIdx.x; a < n8; a += blockDim.x) {
+            double r = __longlong_as_double((long long)*(volatile unsigned long long*)(peer_data(mine, slot, 0) + a));
+            for (int q = 1; q < W; ++q) {
+                const double x = __longlong_as_double((long long)*(volatile unsigned long long*)(peer_data(mine, slot, q) + a));
+                if (a >= mx0) r = fmax(r, x);
+                else if (a >= mn0) r = fmin(r, x);
+                else r += x;
+            }
+            io[a] = (unsigned long long)__double_as_longlong(r);
+        }
+    } else {                                                   // integer sums (histograms)
+        for (int a = threadIdx.x; a < n8; a += blockDim.x) {
+            unsigned long long r = 0ULL;
+            for (int q = 0; q < W; ++q) r += *(volatile unsigned long long*)(peer_data(mine, slot, q) + a);
+            io[a] = r;
+        }
+    }
+}
+
+extern "C" int peuqse_peer_alloc(void** d_local, void* handle64) {
+    if (!d_local || !handle64) return pq_set_error(PEUQSE_ERR_INVALID, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    void* p = nullptr;
+    PQ_CUDA_OK(cudaMalloc(&p, PQ_PEER_BYTES));
+    PQ_CUDA_OK(cudaMemset(p, 0, PQ_PEER_BYTES));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return pq_set_cuda_error(e, "cudaIpcGetMemHandle", __LINE__); }
+    memcpy(handle64, &h, 64);
+    *d_local = p;
+    return PEUQSE_OK;
+}
+
+extern "C" int peuqse_peer_create(void* d_local, const void* handles, int32_t rank, int32_t world, peuqse_peer** out) {
+    if (!d_local || !handles || !out || world < 1 || world > PQ_PEER_MAX_WORLD || rank < 0 || rank >= world)
+        return pq_set_error(PEUQSE_ERR_INVALID, "bad peer arguments");
+    peuqse_peer* p = new peuqse_peer();
+    p->v.rank = rank;
+    p->v.world = world;
+    p->seq = 0;
+    p->local = d_local;
+    for (int r = 0; r < PQ_PEER_MAX_WORLD; ++r) { p->v.box[r] = nullptr; p->opened[r] = false; }
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) { p->v.box[r] = (unsigned char*)d_local; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char*)handles + (size_t)r * 64, 64);
+        void* q = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            for (int s = 0; s < r; ++s) if (p->opened[s]) cudaIpcCloseMemHandle(p->v.box[s]);
+            delete p;
+            return pq_set_cuda_error(e, "cudaIpcOpenMemHandle", __LINE__);
+        }
+        p->v.box[r] = (unsigned char*)q;
+        p->opened[r] = true;
+    }
+    *out = p;
+    return PEUQSE_OK;
+}
+
+extern "C" int peuqse_peer_destroy(peuqse_peer* p) {
+    if (!p) return PEUQSE_OK;
+    for (int r = 0; r < p->v.world; ++r) if (p->opened[r]) cudaIpcCloseMemHandle(p->v.box[r]);
+    if (p->local) cudaFree(p->local);
+    delete p;
+    return PEUQSE_OK;
+}
+
+extern "C" int64_t peuqse_peer_max_bytes(void) { return PQ_PEER_PAYLOAD; }
+
+// d_best: this rank's record in, the merged record out (every rank ends with the same record)
+extern "C" int peuqse_peer_merge_best(peuqse_peer* p, peuqse_best* d_best, void* stream) {
+    if (!p || !d_best) return pq_set_error(PEUQSE_ERR_INVALID, "bad peer_merge_best arguments");
+    k_peer_exchange<PEER_OP_BEST><<<1, 256, 0, (cudaStream_t)stream>>>(p->v, (unsigned long long*)d_best, 2, ++p->seq, 0);
+    PQ_CUDA_OK(cudaGetLastError());
+    return PEUQSE_OK;
+}
+
+// d_acc: PEUQSE_ACC_DOUBLES(k) doubles, combined over ranks like peuqse_merge_acc
+extern "C" int peuqse_peer_merge_acc(peuqse_peer* p, double* d_acc, int32_t k, void* stream) {
+    if (!p || !d_acc || k < 1 || k > PQ_MAXK) return pq_set_error(PEUQSE_ERR_INVALID, "bad peer_merge_acc arguments");
+    k_peer_exchange<PEER_OP_ACC><<<1, 256, 0, (cudaStream_t)stream>>>(p->v, (unsigned long long*)d_acc, PEUQSE_ACC_DOUBLES(k), ++p->seq, k);
+    PQ_CUDA_OK(cudaGetLastError());
+    return PEUQSE_OK;
+}
+
+// in-place sum over ranks of count int64 counters (count*8 <= peuqse_peer_max_bytes())
+extern "C" int peuqse_peer_sum_i64(peuqse_peer* p, void* d_buf, int64_t count, void* stream) {
+    if (!p || !d_buf || count < 0 || count * 8 > PQ_PEER_PAYLOAD) return pq_set_error(PEUQSE_ERR_INVALID, "bad peer_sum_i64 arguments");
+    if (count == 0) return PEUQSE_OK;
+    k_peer_exchange<PEER_OP_SUM_I64><<<1, 256, 0, (cudaStream_t)stream>>>(p->v, (unsigned long long*)d_buf, (int)count, ++p->seq, 0);
+    PQ_CUDA_OK(cudaGetLastError());
+    return PEUQSE_OK;
+}

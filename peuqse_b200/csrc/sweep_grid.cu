@@ -1415,6 +1415,8 @@ int pq_grid_pass2(const peuqse_problem* p, const DevSweep& S, long long first, l
             const int g = flat_grid(T, resident_blocks(p, k_grid_pass2<K, true>, smem));                                         \
             k_grid_pass2<K, true><<<g, GR_THREADS, smem, st>>>(S, T, first, count, logp, aux, best, log_rel, partial, acc, ticket, \
                                                                kidx, klogp, kcap, (unsigned long long*)kcount);                   \
+            e = cudaGetLastError();                                                                                              \
+            if (e != cudaSuccess) return pq_set_cuda_error(e, "k_grid_pass2<fused> launch", (int)smem);                          \
         } else {                                                                                                                 \
             const int g = flat_grid(T, resident_blocks(p, k_grid_pass2<K, false>, 0));                                           \
             k_grid_pass2<K, false><<<g, GR_THREADS, 0, st>>>(S, T, first, count, logp, aux, best, log_rel, partial, acc, ticket,   \

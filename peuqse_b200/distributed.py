@@ -127,3 +127,49 @@ def native_comm():
         _lib.check(L.peuqse_comm_create(idb, rank, size, C.byref(h)))
         _native_comm = h
     return _native_comm
+
+
+_native_peer = None
+_native_peer_failed = False
+
+
+def native_peer():
+    """The library's peer-memory exchange (csrc/peer.cu): every rank owns a small mailbox in its device memory, maps the
+    peers' mailboxes through CUDA IPC and the sweep's collectives become one push-wait-merge kernel each.  Needs all
+    ranks on one node (NVLink/NVSwitch) and world <= 16; returns None otherwise, or when IPC is not available (the NCCL
+    communicator is used then).  PEUQSE_B200_NO_PEER=1 disables it."""
+    global _native_peer, _native_peer_failed
+    import os
+    rank, size = world()
+    if size == 1 or size > 16 or dist.get_backend() != "nccl" or _native_peer_failed or os.environ.get("PEUQSE_B200_NO_PEER") == "1":
+        return None
+    if _native_peer is None:
+        import ctypes as C
+        from . import _lib
+        L = _lib.load()
+        local = C.c_void_p()
+        hbuf = (C.c_ubyte * 64)()
+        ok = L.peuqse_peer_alloc(C.byref(local), hbuf) == 0
+        # every rank must take the same branch: agree on success before mapping
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=_comm_device())
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        mine = torch.tensor(list(hbuf), dtype=torch.uint8, device=_comm_device())
+        allh = torch.empty((size, 64), dtype=torch.uint8, device=_comm_device())
+        dist.all_gather_into_tensor(allh, mine.reshape(1, 64))
+        h = C.c_void_p()
+        if int(flag.item()) == 1:
+            raw = bytes(allh.cpu().numpy().tobytes())
+            ok = L.peuqse_peer_create(local, raw, rank, size, C.byref(h)) == 0
+        else:
+            ok = False
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=_comm_device())
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) != 1:
+            if ok:
+                L.peuqse_peer_destroy(h)
+            _native_peer_failed = True
+            return None
+        torch.cuda.synchronize()
+        dist.barrier()                       # every mailbox is mapped and zeroed before the first exchange
+        _native_peer = h
+    return _native_peer

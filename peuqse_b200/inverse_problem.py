@@ -32,7 +32,7 @@ class parameter_estimation:
         self.UserInput = UI = UserInput
         pes = UI.parameter_estimation_settings
         for key, default in (('mcmc_nchains', 1), ('mcmc_store_samples', 'auto'), ('mcmc_thin', 1),
-                             ('multistart_store_logP', 'auto'), ('multistart_random_seed', None),
+                             ('multistart_store_logP', 'auto'), ('multistart_random_seed', None), ('multistart_shard_pieces', 'auto'),
                              ('multistart_histogram_bins', 10)):
             pes.setdefault(key, default)
         if UI.model.get('custom_logLikelihood') is not None or UI.model.get('custom_logPrior') is not None:
@@ -317,12 +317,14 @@ class parameter_estimation:
             return self._multistart_external(spec, n, toSamples and calculatePostBurnInStatistics, coef, nbins, centerPoint)
         store = pes.get('multistart_store_logP', 'auto')
         store = (n <= 2 ** 31) if store == 'auto' else bool(store)
-        key = (bytes(spec), n, store, nbins, D.world())
+        pieces = pes.get('multistart_shard_pieces', 'auto')            # multi-GPU: pieces per rank, dealt round-robin
+        pieces = 1 if pieces == 'auto' else int(pieces)
+        key = (bytes(spec), n, store, nbins, D.world(), pieces)
         if getattr(self, '_sweep_key', None) == key:
             sw = self._sweep                    # same sweep again: reuse the device buffers
             sw.launches = 0
         else:
-            sw = Sweep(self.device_problem, spec, n, store_logp=store, nbins=nbins)
+            sw = Sweep(self.device_problem, spec, n, store_logp=store, nbins=nbins, pieces=pieces)
             self._sweep_key = key
         res = sw.run(coef=coef, statistics=bool(toSamples and calculatePostBurnInStatistics))
         self.gpu_launches += sw.launches

@@ -43,21 +43,46 @@ class SweepResult:
     pass
 
 
+def interleaved_ranges(total, rank, size, pieces):
+    """Index ranges of one rank when [0, total) is cut into size*pieces contiguous pieces dealt round-robin.
+    combinationGenerator lists a grid from the centre outwards, so the retained (near-MAP) points of a grid sweep sit in
+    a prefix of the index space: one contiguous range per rank would leave all of pass 2-3 to rank 0."""
+    P = size * pieces
+    out = []
+    for j in range(rank, P, size):
+        a, b = (total * j) // P, (total * (j + 1)) // P
+        if b > a:
+            out.append((a, b - a))
+    return out or [(0, 0)]
+
+
 class Sweep:
-    def __init__(self, dp, spec, total, store_logp=True, nbins=10, shard=None):
+    def __init__(self, dp, spec, total, store_logp=True, nbins=10, shard=None, pieces=None):
         self.dp = dp
         self.spec = spec
         self.k = k = spec.k
         self.total = int(total)
         self.nbins = int(nbins)
         self.L = _lib.load()
-        self.first, self.count = D.shard_range(self.total) if shard is None else D.shard_range(self.total, *shard)
+        rank, size = D.world()
+        if shard is not None:
+            self.ranges = [D.shard_range(self.total, *shard)]
+        elif size > 1 and (pieces or 1) > 1:
+            self.ranges = interleaved_ranges(self.total, rank, size, int(pieces))
+        else:
+            self.ranges = [D.shard_range(self.total)]
+        self.first = self.ranges[0][0]
+        self.count = sum(c for _, c in self.ranges)
         dev = torch.device("cuda", torch.cuda.current_device())
         self.dev = dev
-        self.work = torch.zeros(int(self.L.peuqse_sweep_work_bytes(dp.handle if store_logp else None,
-                                                                    C.byref(spec) if store_logp else None,
-                                                                    self.first, self.count)), dtype=torch.uint8, device=dev)
+        self.works = [torch.zeros(int(self.L.peuqse_sweep_work_bytes(dp.handle if store_logp else None,
+                                                                     C.byref(spec) if store_logp else None, f, c)),
+                                  dtype=torch.uint8, device=dev) for f, c in self.ranges]
+        self.work = self.works[0]
         self.logp = torch.empty(self.count, dtype=torch.float64, device=dev) if store_logp else None
+        offs = np.cumsum([0] + [c for _, c in self.ranges])
+        self.logps = [self.logp[offs[i]:offs[i + 1]] if store_logp else None for i in range(len(self.ranges))]
+        self.bests = torch.zeros((len(self.ranges), 2), dtype=torch.float64, device=dev) if len(self.ranges) > 1 else None
         # packed result: [best(2) | acc | hist (int64 bits) | edges]
         self.lay = lay = _lib.acc_layout(k)
         nacc = lay["SIZE"]
@@ -73,14 +98,21 @@ class Sweep:
         self.launches = 0
         self.use_graph = True
         self.world = D.world()[1]
-        self.comm = D.native_comm() if self.world > 1 else None
+        self.peer = D.native_peer() if self.world > 1 else None      # push-wait-merge kernels over peer memory
+        self.comm = D.native_comm() if (self.world > 1 and self.peer is None) else None
+        self.peer_max = int(self.L.peuqse_peer_max_bytes())
 
     # -- individual passes: device-resident in and out (bench.py times these for the kernel-only number)
     def pass1(self):
-        _lib.check(self.L.peuqse_sweep_pass1(self.dp.handle, C.byref(self.spec), self.first, self.count,
-                                             _lib.ptr(self.logp), _lib.ptr(self.best), _lib.ptr(self.work),
-                                             _lib.current_stream()))
-        self.launches += 1
+        multi = len(self.ranges) > 1
+        for i, (f, c) in enumerate(self.ranges):
+            _lib.check(self.L.peuqse_sweep_pass1(self.dp.handle, C.byref(self.spec), f, c, _lib.ptr(self.logps[i]),
+                                                 _lib.ptr(self.bests[i]) if multi else _lib.ptr(self.best),
+                                                 _lib.ptr(self.works[i]), _lib.current_stream()))
+            self.launches += 1
+        if multi:                                           # this rank's pieces -> one record
+            _lib.check(self.L.peuqse_merge_best(_lib.ptr(self.bests), len(self.ranges), _lib.ptr(self.best), _lib.current_stream()))
+            self.launches += 1
         if self.world > 1:
             self._merge_best()
         _lib.check(self.L.peuqse_sweep_best_point(C.byref(self.spec), _lib.ptr(self.best), _lib.ptr(self.map_theta),
@@ -90,6 +122,10 @@ class Sweep:
     def _merge_best(self):
         """all-gather of the 16-byte (maxLogP, index) records + one merge kernel (highest value, lowest index among equals)."""
         import torch.distributed as dist
+        if self.peer is not None:
+            _lib.check(self.L.peuqse_peer_merge_best(self.peer, _lib.ptr(self.best), _lib.current_stream()))
+            self.launches += 1
+            return
         if not hasattr(self, "_g_best"):
             self._g_best = torch.empty((self.world, 2), dtype=torch.float64, device=self.dev)
             self._g_acc = torch.empty((self.world, self.lay["SIZE"]), dtype=torch.float64, device=self.dev)
@@ -108,13 +144,19 @@ class Sweep:
             kidx, klogp, kcount = keep
             cap = kidx.numel()
             kcount.zero_()
-        _lib.check(self.L.peuqse_sweep_pass2(self.dp.handle, C.byref(self.spec), self.first, self.count,
-                                             _lib.ptr(self.logp), _lib.ptr(self.best), float(log_rel), _lib.ptr(self.acc),
-                                             _lib.ptr(kidx), _lib.ptr(klogp), cap, _lib.ptr(kcount), _lib.ptr(self.work),
-                                             _lib.current_stream()))
-        self.launches += 2                                  # main kernel + finish kernel
-        if self.world > 1:                                  # one all-gather + one merge kernel (sum / min / max by slot)
+        for i, (f, c) in enumerate(self.ranges):            # sums accumulate into self.acc over the pieces
+            _lib.check(self.L.peuqse_sweep_pass2(self.dp.handle, C.byref(self.spec), f, c,
+                                                 _lib.ptr(self.logps[i]), _lib.ptr(self.best), float(log_rel), _lib.ptr(self.acc),
+                                                 _lib.ptr(kidx), _lib.ptr(klogp), cap, _lib.ptr(kcount), _lib.ptr(self.works[i]),
+                                                 _lib.current_stream()))
+            self.launches += 2                              # main kernel + finish kernel
+        if self.world > 1 and self.peer is not None:
+            _lib.check(self.L.peuqse_peer_merge_acc(self.peer, _lib.ptr(self.acc), self.k, _lib.current_stream()))
+            self.launches += 1
+        elif self.world > 1:                                # one all-gather + one merge kernel (sum / min / max by slot)
             import torch.distributed as dist
+            if not hasattr(self, "_g_acc"):
+                self._g_acc = torch.empty((self.world, self.lay["SIZE"]), dtype=torch.float64, device=self.dev)
             if self.comm is not None:
                 _lib.check(self.L.peuqse_comm_allgather(self.comm, _lib.ptr(self.acc), _lib.ptr(self._g_acc),
                                                         self.lay["SIZE"] * 8, _lib.current_stream()))
@@ -127,12 +169,19 @@ class Sweep:
     def pass3(self, log_rel, reuse_pass2_sums=True):
         _lib.check(self.L.peuqse_sweep_edges(_lib.ptr(self.acc), self.k, self.nbins, _lib.ptr(self.edges),
                                              _lib.ptr(self.hist), _lib.current_stream()))
-        _lib.check(self.L.peuqse_sweep_hist(self.dp.handle, C.byref(self.spec), self.first, self.count,
-                                            _lib.ptr(self.logp), _lib.ptr(self.best), float(log_rel), _lib.ptr(self.edges),
-                                            self.nbins, _lib.ptr(self.hist), _lib.ptr(self.work), 1 if reuse_pass2_sums else 0,
-                                            _lib.current_stream()))
-        self.launches += 2
-        if self.world > 1:
+        self.launches += 1
+        for i, (f, c) in enumerate(self.ranges):
+            _lib.check(self.L.peuqse_sweep_hist(self.dp.handle, C.byref(self.spec), f, c,
+                                                _lib.ptr(self.logps[i]), _lib.ptr(self.best), float(log_rel), _lib.ptr(self.edges),
+                                                self.nbins, _lib.ptr(self.hist), _lib.ptr(self.works[i]), 1 if reuse_pass2_sums else 0,
+                                                _lib.current_stream()))
+            self.launches += 1
+        if self.world > 1 and self.peer is not None and self.hist.numel() * 8 <= self.peer_max:
+            _lib.check(self.L.peuqse_peer_sum_i64(self.peer, _lib.ptr(self.hist), self.hist.numel(), _lib.current_stream()))
+            self.launches += 1
+        elif self.world > 1:
+            if self.comm is None and self.peer is not None:
+                self.comm = D.native_comm()
             if self.comm is not None:
                 _lib.check(self.L.peuqse_comm_allreduce_sum_i64(self.comm, _lib.ptr(self.hist), self.hist.numel(),
                                                                 _lib.current_stream()))

@@ -52,6 +52,21 @@ assert PE.sweep_result.sum_weights == R1.sum_weights and PE.sweep_result.n_retai
 np.testing.assert_allclose(PE.mu_AP_parameter_set, R1.mu_AP_parameter_set, rtol=1e-13)
 np.testing.assert_allclose(PE.stdap_parameter_set, R1.stdap_parameter_set, rtol=1e-11)
 assert np.array_equal(PE.marginal_histograms[0], R1.histogram_counts)
+# 2b. the same sweep with each rank's share dealt as 3 interleaved pieces (multistart_shard_pieces)
+try:
+    multi = Sweep(PE.device_problem, spec, N, pieces=3)
+    assert len(multi.ranges) == 3
+    Rm = multi.run(2.0)
+    assert (Rm.map_index, Rm.map_logP) == (R1.map_index, R1.map_logP)
+    assert Rm.sum_weights == R1.sum_weights and Rm.n_retained == R1.n_retained
+    assert np.array_equal(Rm.histogram_counts, R1.histogram_counts)
+    np.testing.assert_allclose(Rm.mu_AP_parameter_set, R1.mu_AP_parameter_set, rtol=1e-12)
+    np.testing.assert_allclose(Rm.stdap_parameter_set, R1.stdap_parameter_set, rtol=1e-10)
+except Exception:
+    import traceback
+    traceback.print_exc()
+    sys.stdout.flush(); sys.stderr.flush()
+    raise
 # 3. MH chains sharded by global chain index: same pooled moments as one rank running all chains
 PE = make({'mcmc_length': 400, 'mcmc_burn_in': 100, 'mcmc_nchains': 64, 'mcmc_random_seed': 5, 'mcmc_relative_step_length': 0.5,
            'mcmc_threshold_filter_samples': False, 'mcmc_info_gain_returned': 'log_ratio'})

@@ -736,3 +736,27 @@ def test_mh_kernel_shapes_agree(env):
     few = mh_launch(PE, th0[:200], 150, 30, 9, L, store_samples=False)
     many = mh_launch(PE, th0, 150, 30, 9, L, store_samples=False)
     assert np.array_equal(few['stats'].cpu().numpy(), many['stats'].cpu().numpy()[:200])
+
+
+def test_grid_sweep_with_unaligned_logp_buffer(env):
+    """d_logp only 8-byte aligned: pass 2 cannot use the bulk-copy (TMA) kernel and takes the plain fused one (48 KB of
+    dynamic shared memory next to its static arrays); results must be those of the aligned run."""
+    PEUQSE, orc, _, torch = env
+    from peuqse_b200.sweep import Sweep, make_spec
+    PE = make_pe(PEUQSE, PEUQSE.QuadraticModel(X00), Y00, S00, [200, 500], [100, 200])
+    spec = make_spec("grid", 2, [200., 500.], interval=[2.5, 0.4], radii=[37, 2900])
+    N = 75 * 5801
+    ref = Sweep(PE.device_problem, spec, N)
+    ref.use_graph = False
+    Rr = ref.run(2.0)
+    sw = Sweep(PE.device_problem, spec, N)
+    sw.use_graph = False
+    big = torch.empty(N + 1, dtype=torch.float64, device='cuda')
+    sw.logp = big[1:]
+    sw.logps = [sw.logp]
+    R = sw.run(2.0)
+    assert (R.map_index, R.map_logP, R.sum_weights, R.n_retained) == (Rr.map_index, Rr.map_logP, Rr.sum_weights, Rr.n_retained)
+    assert np.array_equal(R.histogram_counts, Rr.histogram_counts)
+    assert torch.equal(sw.logp, ref.logp)
+    np.testing.assert_allclose(R.mu_AP_parameter_set, Rr.mu_AP_parameter_set, rtol=1e-13)
+    np.testing.assert_allclose(R.stdap_parameter_set, Rr.stdap_parameter_set, rtol=1e-11)
