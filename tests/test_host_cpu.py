@@ -143,6 +143,14 @@ def test_merge_best_rule():
         cover.append((f, c))
     assert cover[0][0] == 0 and sum(c for _, c in cover) == 100020001
     assert all(cover[i][0] + cover[i][1] == cover[i + 1][0] for i in range(6))
+    # interleaved pieces (multistart_shard_pieces): every index exactly once, piece j of rank r is global piece r + j*size
+    from peuqse_b200.sweep import interleaved_ranges
+    for total, size, pieces in ((100020001, 8, 8), (10, 4, 5), (7, 3, 1)):
+        allr = sorted(x for r in range(size) for x in interleaved_ranges(total, r, size, pieces) if x[1] > 0)
+        assert allr[0][0] == 0 and sum(c for _, c in allr) == total
+        assert all(allr[i][0] + allr[i][1] == allr[i + 1][0] for i in range(len(allr) - 1))
+    a = interleaved_ranges(1000, 1, 4, 2)
+    assert a == [(125, 125), (625, 125)]
 
 
 def _free_port():
