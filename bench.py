@@ -99,7 +99,7 @@ def cpu_baseline_single_core(radii, budget_s=12.0):
                       f"scipy.stats.multivariate_normal.logpdf as the reference does (oracle/peuqse_oracle.py log_p_point), {dt:.1f} s"}
 
 
-def run_reference_arm(args):
+def run_reference_arm(args, emit=print):
     """--impl reference: the reference's own CPU algorithm for this path (oracle port; the reference is Python and
     its tree is not on the GPU box), on all host cores as independent workers each owning a slice of the grid
     (what the reference's mpiexec mode amounts to, IP.py:845-857)."""
@@ -140,7 +140,7 @@ def run_reference_arm(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(json.dumps(line))
     return 0
 
 
@@ -196,7 +196,7 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
-def run_ours(args):
+def run_ours(args, emit=print):
     import torch
     import peuqse_b200 as PEUQSE
     from peuqse_b200 import _lib
@@ -330,7 +330,7 @@ def run_ours(args):
             "gpu_launches": launches}
     if cpu is not None:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line))
+    emit(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
     return 0
@@ -348,9 +348,21 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference_arm(args)
-    return run_ours(args)
+    # The contract is ONE JSON line on stdout: libraries that print banners there (NCCL prints its version on the first
+    # communicator) are sent to stderr by pointing fd 1 at fd 2 for the duration of the run; the line goes to the real stdout.
+    sys.stdout.flush()
+    real_out = os.dup(1)
+    os.dup2(2, 1)
+    lines = []
+    try:
+        rc = run_reference_arm(args, lines.append) if args.impl == "reference" else run_ours(args, lines.append)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_out, 1)
+        os.close(real_out)
+    for ln in lines:
+        print(ln, flush=True)
+    return rc
 
 
 if __name__ == "__main__":

@@ -25,6 +25,9 @@
 #define GR_WARPS (GR_THREADS / 32)
 #define GR_JPT 8
 #define GR_CH (GR_THREADS * GR_JPT)
+#define GR_RB 4         // rows per work unit of pass 1
+#define PQ_GRID_CTR_WORD 24   // unit counters of pass 1: ticket words 24..63 (bytes 96..255 of the ticket area, after ShortHdr)
+#define PQ_GRID_MAX_CTR 32
 #define GR_MSTRIDE 32   // a thread's 8 points are 32 apart: a warp covers 256 CONTIGUOUS positions of a row (compact tiles)
 // position of the thread's first point inside its chunk
 #define GR_JL0 ((int)(threadIdx.x >> 5) * (32 * GR_JPT) + (int)(threadIdx.x & 31))
@@ -35,6 +38,7 @@ struct GridTiling {
     long long b_lo, b_hi;  // rows intersecting [first, first+count)
     long long slab_first, slab_count;   // part of [first, first+count) below ML
     int nchunks, nrg;      // chunks along j, row groups
+    int dyn;               // pass 1 hands out its work units through atomic counters (nchunks <= PQ_GRID_MAX_CTR)
 };
 
 // auxiliary arrays inside d_work (after the base area)
@@ -68,7 +72,7 @@ __device__ __forceinline__ double key_value(unsigned int k) {
 
 // block-level merge of per-thread bests into *best_out
 __device__ __forceinline__ void block_store_best(Best best, Best* s_best, bool* s_last, Best* partial, unsigned int* ticket,
-                                                 peuqse_best* best_out) {
+                                                 peuqse_best* best_out, int nctr) {
     best = warp_best(best);
     if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = best;
     __syncthreads();
@@ -99,6 +103,7 @@ __device__ __forceinline__ void block_store_best(Best best, Best* s_best, bool* 
             *ticket = 0;
             ticket[PQ_SHORT_VALID_WORD] = 0u;                  // this pass 1 leaves no shortlist (sweep_common.cuh)
         }
+        if ((int)threadIdx.x < nctr) ticket[PQ_GRID_CTR_WORD + threadIdx.x] = 0u;    // unit counters ready for the next launch
     }
 }
 
@@ -125,6 +130,26 @@ struct RowRec {
     static constexpr int N = ((2 + (KT - 1) + NT) + 1) & ~1;       // even: 16-byte aligned records
 };
 
+// order-preserving key of the high word of a double (larger value <=> larger key; NaNs excluded by the callers)
+__device__ __forceinline__ unsigned int hi_okey(unsigned int h) { return (h & 0x80000000u) ? ~h : (h | 0x80000000u); }
+// upper bound of every double whose high-word key is k
+__device__ __forceinline__ double hi_okey_upper(unsigned int k) {
+    if (k & 0x80000000u) {                                       // non-negative: largest low word
+        const unsigned int h = k & 0x7fffffffu;
+        return (h >= 0x7ff00000u) ? pq_pos_inf() : __hiloint2double((int)h, (int)0xffffffffu);
+    }
+    return __hiloint2double((int)~k, 0);                          // negative: smallest magnitude
+}
+
+// Work distribution: a "unit" is GR_RB consecutive rows of one chunk of columns.  T.dyn: units are handed out by one
+// atomic counter per chunk (ticket words PQ_GRID_CTR_WORD ...): a CTA starts on chunk blockIdx % nchunks, keeps its
+// per-column registers while that chunk has units and then moves on to the next chunk, so SMs that were given fewer
+// CTAs (or faster ones) absorb the difference.  Otherwise (more chunks than counters) unit u of a chunk goes to row
+// group u % nrg.  Row records of the NEXT unit are staged by warp 0 after its share of the current unit (the atomic is
+// issued before, its result consumed after), double-buffered: one __syncthreads per unit.
+// Maximum tracking: the eight values of a thread are compared on the integer pipe through their high words (for negative
+// finite doubles a larger high word is a smaller value); the exact fp64 scan runs only when a row could hold a new
+// thread-best (high word <= that of the thread's best), a NaN / -inf, or a non-negative value.
 template <int MODEL, int KT, int NT, bool EXACT, bool SIMPLE, bool STORE, bool BOUNDS>
 __global__ void __launch_bounds__(GR_THREADS, 3) k_grid_pass1(const __grid_constant__ DevProblem P, const __grid_constant__ DevSweep S,
                                                            const __grid_constant__ GridTiling T, long long first, long long count,
@@ -132,114 +157,183 @@ __global__ void __launch_bounds__(GR_THREADS, 3) k_grid_pass1(const __grid_const
                                                            peuqse_best* __restrict__ best_out, Best* __restrict__ partial,
                                                            unsigned int* __restrict__ ticket) {
     using R = RowRec<KT, NT>;
-    __shared__ __align__(16) double s_rec[GR_THREADS * R::N];
+    __shared__ __align__(16) double s_rec[2][GR_RB * R::N];
+    __shared__ long long s_unit[2];
     __shared__ Best s_best[GR_WARPS];
     __shared__ bool s_last;
     constexpr int L = KT - 1;
-    const int chunk = blockIdx.x % T.nchunks, rg = blockIdx.x / T.nchunks;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long j0 = (long long)chunk * GR_CH + GR_JL0;
     const long long last = first + count;
-    const bool full_chunk = (long long)(chunk + 1) * GR_CH <= T.r2;     // every j of this chunk exists (block-uniform)
-    double thL[GR_JPT], qL[GR_JPT];
-    bool okL[GR_JPT], jv[GR_JPT];
-#pragma unroll
-    for (int m = 0; m < GR_JPT; ++m) {
-        const long long j = j0 + m * GR_MSTRIDE;
-        thL[m] = last_axis_value(S, L, j);
-        prior_axis(P, L, thL[m], okL[m], qL[m]);
-        jv[m] = j < T.r2;
-    }
+    const long long nrows = T.b_hi - T.b_lo;
+    const long long nunits = (nrows + GR_RB - 1) / GR_RB;
+    unsigned int* ctr = ticket + PQ_GRID_CTR_WORD;
     Best best = best_none();
-    const long long nrows_blk = (T.b_hi - T.b_lo - rg + T.nrg - 1) / T.nrg;     // rows b_lo+rg, +nrg, ...
-    for (long long t0 = 0; t0 < nrows_blk; t0 += GR_THREADS) {
-        __syncthreads();
-        if (t0 + threadIdx.x < nrows_blk) {                          // stage: one row record per thread
-            const long long b = T.b_lo + rg + (t0 + threadIdx.x) * T.nrg;
-            double th[KT];
-            grid_point<KT>(S, (unsigned long long)b, th, L);          // lower axes of this row
-            double* rec = s_rec + threadIdx.x * R::N;
-            bool ok_low = true;
-            double plow = 0.0;
-#pragma unroll
-            for (int d = 0; d < L; ++d) {
-                bool okd;
-                double q;
-                prior_axis(P, d, th[d], okd, q);
-                ok_low = ok_low && okd;
-                plow = (d == 0) ? q : (plow + q);                     // numpy order for < 8 terms: sequential from the first
-                rec[R::QN + d] = q;
-            }
-            rec[0] = ok_low ? 1.0 : 0.0;
-            rec[1] = plow;
-            FastRowPre<MODEL, KT, NT, 0>::fill(P, th, rec + R::PRE);
+    unsigned int lim = 0xffefffffu;            // exact scan when a row's smallest high word is <= lim (see above)
+    int chunk = blockIdx.x % T.nchunks;
+    long long static_next = blockIdx.x / T.nchunks;               // !T.dyn: units rg, rg + nrg, ...
+    const int attempts = (nrows > 0) ? (T.dyn ? T.nchunks : 1) : 0;
+    for (int attempt = 0; attempt < attempts; ++attempt, chunk = (chunk + 1 == T.nchunks) ? 0 : chunk + 1) {
+        __syncthreads();                                          // s_unit / s_rec of the previous chunk are no longer read
+        if (threadIdx.x == 0) {
+            long long u0;
+            if (T.dyn) u0 = (long long)atomicAdd(ctr + chunk, 1u);
+            else { u0 = static_next; static_next += T.nrg; }
+            s_unit[0] = u0;
         }
         __syncthreads();
-        const int nr = (int)((nrows_blk - t0 < GR_THREADS) ? (nrows_blk - t0) : GR_THREADS);
-        for (int tt = 0; tt < nr; ++tt) {
-            const double* rec = s_rec + tt * R::N;                    // broadcast reads
-            const long long b = T.b_lo + rg + (t0 + tt) * T.nrg;
-            const bool ok_low = rec[0] != 0.0;
-            const double plow = rec[1];
-            double pre[NT], qn[KT];
+        if (s_unit[0] >= nunits) continue;                        // this chunk is finished (block-uniform)
+        const long long j0 = (long long)chunk * GR_CH + GR_JL0;
+        const bool warp_full = (long long)chunk * GR_CH + (long long)(warp + 1) * (32 * GR_JPT) <= T.r2;   // all 256 columns exist
+        double thL[GR_JPT], qL[GR_JPT];
+        bool okL[GR_JPT], jv[GR_JPT];
 #pragma unroll
-            for (int j = 0; j < NT; ++j) pre[j] = rec[R::PRE + j];
+        for (int m = 0; m < GR_JPT; ++m) {
+            const long long j = j0 + m * GR_MSTRIDE;
+            thL[m] = last_axis_value(S, L, j);
+            prior_axis(P, L, thL[m], okL[m], qL[m]);
+            jv[m] = j < T.r2;
+        }
+        // row records of unit `u` into buffer `buf` (lanes < GR_RB of warp 0)
+        auto stage = [&](long long u, int buf) {
+            if (lane == 0) s_unit[buf] = u;
+            const long long b = T.b_lo + u * GR_RB + lane;
+            if (lane < GR_RB && u < nunits && b < T.b_hi) {
+                double th[KT];
+                grid_point<KT>(S, (unsigned long long)b, th, L);      // lower axes of this row
+                double* rec = s_rec[buf] + lane * R::N;
+                bool ok_low = true;
+                double plow = 0.0;
 #pragma unroll
-            for (int d = 0; d < KT; ++d) qn[d] = (d < L) ? rec[R::QN + (d < L ? d : 0)] : 0.0;
-            const long long row0 = T.ML + b * T.r2;
-            const long long gbase = row0 + j0;
-            const bool inside = (row0 >= first) && (row0 + T.r2 <= last);   // whole row in range (block-uniform)
-            double v[GR_JPT];
-#pragma unroll
-            for (int m = 0; m < GR_JPT; ++m) {                        // branch-free evaluation of the thread's 8 points
-                double lp;
-                if (SIMPLE) {
-                    const double maha = (KT == 1) ? qL[m] : (plow + qL[m]);
-                    lp = -0.5 * (P.prior_c + maha);                    // _multivariate.py:591
-                } else {
-                    qn[L] = qL[m];
-                    lp = prior_combine<KT>(P, true, qn);
+                for (int d = 0; d < L; ++d) {
+                    bool okd;
+                    double q;
+                    prior_axis(P, d, th[d], okd, q);
+                    ok_low = ok_low && okd;
+                    plow = (d == 0) ? q : (plow + q);                 // numpy order for < 8 terms: sequential from the first
+                    rec[R::QN + d] = q;
                 }
-                double q[NT];
-                FastQLast<MODEL, KT, NT, EXACT, 0>::fill(P, pre, thL[m], q);
-                const double maha_l = ordered_sum_static<NT>(EXACT ? NT : P.fast_n, q);
-                const double ll = -0.5 * (P.resp_c[0] + maha_l);
-                v[m] = ll + lp;                                        // IP.py:1653
-                if (BOUNDS) v[m] = (ok_low && okL[m]) ? v[m] : pq_neg_inf();   // IP.py:1649-1650
+                rec[0] = ok_low ? 1.0 : 0.0;
+                rec[1] = plow;
+                FastRowPre<MODEL, KT, NT, 0>::fill(P, th, rec + R::PRE);
             }
-            {   // a NaN simulated value must give -inf (IP.py:2880-2882): one exponent test for the 8 points, fix-up is rare
-                unsigned int emax = 0u;
-#pragma unroll
-                for (int m = 0; m < GR_JPT; ++m) emax = max(emax, (unsigned int)__double2hiint(v[m]) & 0x7fffffffu);
-                if (emax >= 0x7ff00000u) {
-#pragma unroll
-                    for (int m = 0; m < GR_JPT; ++m)
-                        if (pq_isnan_bits(v[m])) v[m] = pq_neg_inf();
-                }
+        };
+        if (warp == 0) stage(s_unit[0], 0);
+        __syncthreads();
+        int cur = 0;
+        while (true) {
+            const long long u = s_unit[cur];
+            if (u >= nunits) break;
+            long long un = 0;
+            if (threadIdx.x == 0) {                                // next unit: issued now, consumed after this unit's rows
+                if (T.dyn) un = (long long)atomicAdd(ctr + chunk, 1u);
+                else { un = static_next; static_next += T.nrg; }
             }
-            double rowmax = pq_neg_inf();
-            int rowm = 0;
-            if (inside && full_chunk) {
+            const long long bu = T.b_lo + u * GR_RB;
+            const int nr = (int)((T.b_hi - bu < GR_RB) ? (T.b_hi - bu) : GR_RB);
+            long long row0 = T.ML + bu * T.r2;
+            const bool unit_inside = (row0 >= first) && (row0 + (long long)nr * T.r2 <= last);   // block-uniform
+            size_t tix = ((size_t)(bu - T.b_lo) * T.nchunks + chunk) * GR_WARPS + warp;
+            for (int tt = 0; tt < nr; ++tt, row0 += T.r2, tix += (size_t)T.nchunks * GR_WARPS) {
+                const double* rec = s_rec[cur] + tt * R::N;           // broadcast reads
+                const bool ok_low = rec[0] != 0.0;
+                const double plow = rec[1];
+                double pre[NT], qn[KT];
 #pragma unroll
-                for (int m = 0; m < GR_JPT; ++m) {
-                    if (STORE) __stcs(logp_out + (gbase + m * GR_MSTRIDE - first), v[m]);
-                    if (v[m] > rowmax) { rowmax = v[m]; rowm = m; }    // strict '>', increasing g within the row
-                }
-            } else {                                                  // ragged chunk or first / last row of a rank's range
+                for (int j = 0; j < NT; ++j) pre[j] = rec[R::PRE + j];
 #pragma unroll
-                for (int m = 0; m < GR_JPT; ++m) {
-                    const long long g = gbase + m * GR_MSTRIDE;
-                    if (jv[m] && g >= first && g < last) {
-                        if (STORE) __stcs(logp_out + (g - first), v[m]);
-                        if (v[m] > rowmax) { rowmax = v[m]; rowm = m; }
+                for (int d = 0; d < KT; ++d) qn[d] = (d < L) ? rec[R::QN + (d < L ? d : 0)] : 0.0;
+                const long long gbase = row0 + j0;
+                double v[GR_JPT];
+#pragma unroll
+                for (int m = 0; m < GR_JPT; ++m) {                    // branch-free evaluation of the thread's 8 points
+                    double lp;
+                    if (SIMPLE) {
+                        const double maha = (KT == 1) ? qL[m] : (plow + qL[m]);
+                        lp = -0.5 * (P.prior_c + maha);                // _multivariate.py:591
+                    } else {
+                        qn[L] = qL[m];
+                        lp = prior_combine<KT>(P, true, qn);
                     }
+                    double q[NT];
+                    FastQLast<MODEL, KT, NT, EXACT, 0>::fill(P, pre, thL[m], q);
+                    const double maha_l = ordered_sum_static<NT>(EXACT ? NT : P.fast_n, q);
+                    const double ll = -0.5 * (P.resp_c[0] + maha_l);
+                    v[m] = ll + lp;                                    // IP.py:1653
+                    if (BOUNDS) v[m] = (ok_low && okL[m]) ? v[m] : pq_neg_inf();   // IP.py:1649-1650
+                }
+                unsigned int okey;
+                if (unit_inside && warp_full) {                       // every point of the warp's 256-column segment exists
+                    unsigned int mn = (unsigned int)__double2hiint(v[0]), mx = mn;
+#pragma unroll
+                    for (int m = 1; m < GR_JPT; ++m) {
+                        const unsigned int h = (unsigned int)__double2hiint(v[m]);
+                        mn = min(mn, h);
+                        mx = max(mx, h);
+                    }
+                    bool exact = false;
+                    if (mx >= 0xfff00000u || mn < 0x80000000u) {      // a NaN / -inf or a non-negative value: rare
+#pragma unroll
+                        for (int m = 0; m < GR_JPT; ++m)
+                            if (pq_isnan_bits(v[m])) v[m] = pq_neg_inf();     // NaN simulated value -> -inf (IP.py:2880-2882)
+                        exact = true;
+                    }
+                    if (STORE) {
+#pragma unroll
+                        for (int m = 0; m < GR_JPT; ++m) __stcs(logp_out + (gbase + m * GR_MSTRIDE - first), v[m]);
+                    }
+                    if (exact || mn <= lim) {                         // the row may hold this thread's new best
+                        double rowmax = v[0];
+                        int rowm = 0;
+#pragma unroll
+                        for (int m = 1; m < GR_JPT; ++m)
+                            if (v[m] > rowmax) { rowmax = v[m]; rowm = m; }    // strict '>', increasing g within the row
+                        const long long g = gbase + rowm * GR_MSTRIDE;
+                        if (rowmax > best.v || (rowmax == best.v && g < best.i && rowmax > pq_neg_inf())) {
+                            best.v = rowmax;
+                            best.i = g;
+                            const unsigned int hb = (unsigned int)__double2hiint(rowmax);
+                            lim = (hb & 0x80000000u) ? min(hb, 0xffefffffu) : 0x7fffffffu;
+                        }
+                        okey = hi_okey((unsigned int)__double2hiint(rowmax));
+                    } else {
+                        okey = ~mn;                                   // all negative finite: key of the smallest high word
+                    }
+                } else {                                              // ragged chunk or first / last rows of a rank's range
+                    unsigned int emax = 0u;
+#pragma unroll
+                    for (int m = 0; m < GR_JPT; ++m) emax = max(emax, (unsigned int)__double2hiint(v[m]) & 0x7fffffffu);
+                    if (emax >= 0x7ff00000u) {
+#pragma unroll
+                        for (int m = 0; m < GR_JPT; ++m)
+                            if (pq_isnan_bits(v[m])) v[m] = pq_neg_inf();
+                    }
+                    double rowmax = pq_neg_inf();
+                    int rowm = 0;
+#pragma unroll
+                    for (int m = 0; m < GR_JPT; ++m) {
+                        const long long g = gbase + m * GR_MSTRIDE;
+                        if (jv[m] && g >= first && g < last) {
+                            if (STORE) __stcs(logp_out + (g - first), v[m]);
+                            if (v[m] > rowmax) { rowmax = v[m]; rowm = m; }
+                        }
+                    }
+                    const long long g = gbase + rowm * GR_MSTRIDE;
+                    if (rowmax > best.v || (rowmax == best.v && g < best.i && rowmax > pq_neg_inf())) {
+                        best.v = rowmax;
+                        best.i = g;
+                        const unsigned int hb = (unsigned int)__double2hiint(rowmax);
+                        lim = (hb & 0x80000000u) ? min(hb, 0xffefffffu) : 0x7fffffffu;
+                    }
+                    okey = hi_okey((unsigned int)__double2hiint(rowmax));
+                }
+                if (STORE) {
+                    const unsigned int wk = __reduce_max_sync(0xffffffffu, okey);
+                    if (lane == 0) tilemax[tix] = up_key(hi_okey_upper(wk));
                 }
             }
-            if (rowmax > best.v) { best.v = rowmax; best.i = gbase + rowm * GR_MSTRIDE; }   // rows in increasing g
-            if (STORE) {
-                const unsigned int key = __reduce_max_sync(0xffffffffu, up_key(rowmax));
-                if (lane == 0) tilemax[((size_t)(b - T.b_lo) * T.nchunks + chunk) * GR_WARPS + warp] = key;
-            }
+            if (warp == 0) stage(__shfl_sync(0xffffffffu, un, 0), cur ^ 1);
+            __syncthreads();
+            cur ^= 1;
         }
     }
     // slab: last axis at its centre (indices below M_L), per-point decode
@@ -258,9 +352,9 @@ __global__ void __launch_bounds__(GR_THREADS, 3) k_grid_pass1(const __grid_const
         const double ll = grid_loglik<MODEL, KT, NT, EXACT>(P, th);
         const double v = ok ? (ll + lp) : pq_neg_inf();
         if (STORE) __stcs(logp_out + (g - first), v);
-        if (v > best.v || (v == best.v && g < best.i)) { best.v = v; best.i = g; }
+        if (v > best.v || (v == best.v && g < best.i && v > pq_neg_inf())) { best.v = v; best.i = g; }
     }
-    block_store_best(best, s_best, &s_last, partial, ticket, best_out);
+    block_store_best(best, s_best, &s_last, partial, ticket, best_out, T.dyn ? T.nchunks : 0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1237,15 +1331,18 @@ static bool grid_tiling(const peuqse_problem* p, const DevSweep& S, long long fi
     if (end <= g0) {
         T->b_lo = T->b_hi = 0;
         T->nrg = 1;
+        T->dyn = 0;
         return true;
     }
     T->b_lo = (g0 - ML) / r2;
     T->b_hi = (end - ML + r2 - 1) / r2;
     const long long rows = T->b_hi - T->b_lo;
+    const long long units = (rows + GR_RB - 1) / GR_RB;  // pass-1 work units per chunk
     long long nrg = resident_blocks / T->nchunks;       // one resident wave: no tail
-    if (nrg > rows) nrg = rows;
+    if (nrg > units) nrg = units;
     if (nrg < 1) nrg = 1;
     if (nrg * T->nchunks > PQ_SWEEP_MAX_BLOCKS) nrg = PQ_SWEEP_MAX_BLOCKS / T->nchunks;
+    T->dyn = T->nchunks <= PQ_GRID_MAX_CTR ? 1 : 0;
     T->nrg = (int)nrg;
     return true;
 }
@@ -1320,8 +1417,16 @@ static int launch_grid_pass1(const peuqse_problem* p, const DevSweep& S, long lo
 #define GP1_LAUNCH2(SIMPLE, STORE, BOUNDS)                                                                                   \
     {                                                                                                                         \
         auto kern = k_grid_pass1<MODEL, KT, NT, EXACT, SIMPLE, STORE, BOUNDS>;                                                \
-        grid_tiling(p, S, first, count, resident_blocks(p, kern, 0), &T);                                                     \
-        kern<<<T.nchunks * T.nrg, GR_THREADS, 0, st>>>(p->d, S, T, first, count, logp, tilemax, best, partial, ticket);        \
+        const int resident = resident_blocks(p, kern, 0);                                                                    \
+        grid_tiling(p, S, first, count, resident, &T);                                                                        \
+        long long nblk = (long long)T.nchunks * T.nrg;                                                                        \
+        if (T.dyn) {                        /* any grid works: fill the GPU exactly, but not more CTAs than units */          \
+            const long long units = ((T.b_hi - T.b_lo + GR_RB - 1) / GR_RB) * T.nchunks;                                      \
+            nblk = resident < PQ_SWEEP_MAX_BLOCKS ? resident : PQ_SWEEP_MAX_BLOCKS;                                            \
+            if (nblk > units) nblk = units;                                                                                   \
+            if (nblk < 1) nblk = 1;                                                                                           \
+        }                                                                                                                     \
+        kern<<<(int)nblk, GR_THREADS, 0, st>>>(p->d, S, T, first, count, logp, tilemax, best, partial, ticket);                \
     }
     const bool store = logp != nullptr && tilemax != nullptr;
     const bool bounds = d.has_lb || d.has_ub;
@@ -1347,9 +1452,14 @@ int pq_grid_pass1(const peuqse_problem* p, const DevSweep& S, long long first, l
     if (p->d.model_id == PEUQSE_MODEL_QUADRATIC) {
         switch (n) {
 #define GQ(N) case N: return launch_grid_pass1<PEUQSE_MODEL_QUADRATIC, 2, N, true>(p, S, first, count, logp, aux.tilemax, best, work, st);
+#ifdef PQ_GRID_MINIMAL                      /* development builds: only the C2 instantiation */
+            GQ(3)
+#else
             GQ(1) GQ(2) GQ(3) GQ(4) GQ(5) GQ(6) GQ(7) GQ(8)
+#endif
 #undef GQ
         }
+#ifndef PQ_GRID_MINIMAL
     } else {
 #define GL(K)                                                                                                                       \
     case K:                                                                                                                         \
@@ -1357,6 +1467,7 @@ int pq_grid_pass1(const peuqse_problem* p, const DevSweep& S, long long first, l
                       : launch_grid_pass1<PEUQSE_MODEL_LINEAR, K, 8, false>(p, S, first, count, logp, aux.tilemax, best, work, st);
         switch (p->d.k) { GL(2) GL(3) GL(4) GL(6) }
 #undef GL
+#endif
     }
     return pq_set_error(PEUQSE_ERR_INVALID, "grid fast path dispatch");
 }
