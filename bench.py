@@ -193,6 +193,123 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+
+# ------------------------------------------------------------------------------------------------
+# second half of BASELINE.json's metric: MH chain-steps/s on configs[2] ("C3": 4096 chains, 6-parameter
+# TPD-style kinetics, 1024 observations, diagonal uncertainties).  Reported inside the same JSON line.
+# ------------------------------------------------------------------------------------------------
+C3 = {"n": 1024, "chains": 4096, "truth": [41.5, 45.0, 13.0, 13.0, 0.1, 0.1], "mu": [41.5, 41.5, 13.0, 13.0, 0.1, 0.1],
+      "sd": [20.0, 20.0, 13.0, 13.0, 0.1, 0.1], "step": 2.5e-6, "seed": 0}
+# per chain-step: n x (21 flop + 2 exp) + prior 24 + proposal ~ 21.5 kflop + 2048 exp; one software exp is ~30
+# fp64 instructions, an algorithmic flop at most one: ~97 k fp64 instructions per chain-step
+C3_FP64_INSTR_PER_STEP = 97.0e3
+C3_FLOP_PER_STEP = 23.6e3       # SURVEY 8d algorithmic figure (one exp counted as one flop)
+FP64_INSTR_PEAK = 1.80e13     # measured DFMA / DMUL+DADD issue rate of one B200 (profiles/microbench.py), instructions/s
+
+
+def c3_problem(PEUQSE, steps, chains):
+    """The C3 problem built through the public API; the synthetic observations come from the product's own simulator."""
+    import torch
+    model = PEUQSE.Tpd2SiteModel.linear_ramp(C3["n"])
+
+    def make(y, sig):
+        UI = PEUQSE.UserInput.fresh()
+        UI.responses['responses_observed_max_covmat_size'] = 5000
+        UI.responses['responses_observed'] = list(y)
+        UI.responses['responses_observed_uncertainties'] = list(sig)
+        UI.model['InputParameterPriorValues'] = C3["mu"]
+        UI.model['InputParametersPriorValuesUncertainties'] = C3["sd"]
+        UI.model['simulateByInputParametersOnlyFunction'] = PEUQSE.Tpd2SiteModel.linear_ramp(C3["n"])
+        pes = UI.parameter_estimation_settings
+        pes.update({'mcmc_length': steps, 'mcmc_burn_in': steps // 10, 'mcmc_nchains': chains, 'mcmc_random_seed': C3["seed"],
+                    'mcmc_relative_step_length': C3["step"], 'mcmc_store_samples': False,
+                    'mcmc_threshold_filter_samples': False})
+        UI.model['InputParameterInitialGuess'] = C3["truth"]
+        return PEUQSE.parameter_estimation(UI)
+    n = C3["n"]
+    probe = make(np.ones(n), np.ones(n))
+    sim_t = probe.simulate_batch(np.asarray(C3["truth"]))[0].cpu().numpy()
+    sig = 0.02 * float(np.max(sim_t))
+    y = sim_t + sig * np.random.default_rng(0).standard_normal(n)
+    return make(y, np.full(n, sig)), y, sig
+
+
+def mh_secondary(PEUQSE, torch, dist, rank, world, steps):
+    """chain-steps/s: device-timed peuqse_mh_run over this rank's chains (moments in-kernel, samples not stored) and
+    end to end through PE_object.doMetropolisHastings() (host start points in, pooled host statistics out)."""
+    from peuqse_b200.mcmc import mh_launch, step_cholesky
+    from peuqse_b200 import distributed as D
+    chains = C3["chains"] * world                                   # weak scaling: 4096 chains per GPU
+    PE, y, sig = c3_problem(PEUQSE, steps, chains)
+    c0, cn = D.shard_range(chains, rank, world)
+    th0 = np.tile(np.asarray(C3["truth"]), (cn, 1))
+    chol = step_cholesky(PE.Q_covmat, C3["step"])
+    run = lambda: mh_launch(PE, th0, steps, steps // 10, C3["seed"], chol, chain_offset=c0, store_samples=False)
+    run(); run(); run()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    reps = 3
+    a.record()
+    for _ in range(reps):
+        out = run()
+    b.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(b) / reps], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    acc = float(out['stats'][:, 0].mean().item()) / max(steps - 1, 1)
+    PE.doMetropolisHastings()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    PE.doMetropolisHastings()
+    torch.cuda.synchronize()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    value = chains * (steps - 1) / (ms * 1e-3)
+    per_gpu = value / world
+    sec = {"metric": "mh_chain_steps_per_s", "value": value, "unit": "chain-steps/s", "ms_per_run": ms,
+           "config": {"workload": f"{chains} Metropolis-Hastings chains x {steps} steps, 6-parameter two-site TPD kinetics, "
+                                  f"{C3['n']} observations, diagonal uncertainties, relative step {C3['step']}, in-kernel moments "
+                                  "(samples not stored)", "chains_per_gpu": cn, "acceptance_rate": acc},
+           "roofline": {"bound": "fp64", "kernel": "k_mh_warp<TPD2SITE,k=6>", "achieved": per_gpu * C3_FLOP_PER_STEP / 1e12,
+                        "peak": 2.0 * FP64_INSTR_PEAK / 1e12, "unit": "TFLOP/s", "frac": per_gpu * C3_FLOP_PER_STEP / (2.0 * FP64_INSTR_PEAK),
+                        "peak_source": "2 flop x measured fp64 issue rate 1.80e13 instr/s (profiles/microbench.py; MEASURED_PEAKS.json "
+                                       "has no fp64 figure; nominal 37 TFLOP/s)",
+                        "note": "SURVEY 8d counts one exp as one flop (23.6 kflop per chain-step); executed work is ~97 k fp64 "
+                                "instructions per chain-step (2048 software exps), i.e. %.2f of the fp64 issue rate; %.3g exp/s"
+                                % (per_gpu * C3_FP64_INSTR_PER_STEP / FP64_INSTR_PEAK, per_gpu * 2.0 * C3["n"]),
+                        "traffic": None},
+           "e2e": {"value": chains * (steps - 1) / float(te.item()), "unit": "chain-steps/s", "api": "PE_object.doMetropolisHastings()",
+                   "h2d_bytes_per_step": int(th0.nbytes), "d2h_bytes_per_step": int(out['stats'].numel() * 8)}}
+    if world == 1 and rank == 0:
+        sec["cpu_baseline"] = mh_cpu_baseline(y, sig)
+    return sec
+
+
+def mh_cpu_baseline(y, sig, budget_s=8.0):
+    """One chain of the oracle port of doMetropolisHastings (IP.py:2626-2675: per step one getLogP through scipy logpdf,
+    n > 100 => one scalar logpdf per observation) on one host core."""
+    from oracle import peuqse_oracle as orc
+    n = C3["n"]
+    kBT, c1, c2 = orc.tpd2site_constants(n)
+    sim = orc.sim_tpd2site(kBT, c1, c2)[0]
+    P = orc.build_problem(C3["mu"], C3["sd"], list(y), list(np.full(n, sig)))
+    rng = np.random.default_rng(1)
+    sd = np.sqrt(C3["step"]) * np.asarray(C3["sd"])
+    nst, done, t0 = 6, 0, time.perf_counter()
+    while time.perf_counter() - t0 < budget_s:
+        orc.mh_chain_point(P, np.asarray(C3["truth"]), rng.standard_normal((nst, 6)) * sd, rng.uniform(size=nst), sim)
+        done += nst
+    dt = time.perf_counter() - t0
+    return {"value": done / dt, "unit": "chain-steps/s", "cores": 1, "kind": "port",
+            "sample": f"{done} steps of one chain, point at a time (oracle.mh_chain_point), {dt:.1f} s"}
+
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
@@ -304,6 +421,9 @@ def run_ours(args, emit=print):
     d2h = sw.result_bytes()                              # packed (best, moments, histogram, edges, MAP point)
     assert PE.map_index >= 0 and np.isfinite(PE.map_logP)
 
+    secondary = None
+    if not args.no_mh:
+        secondary = mh_secondary(PEUQSE, torch, dist, rank, world, args.mh_steps)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -330,6 +450,8 @@ def run_ours(args, emit=print):
             "gpu_launches": launches}
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if secondary is not None:
+        line["secondary"] = secondary
     emit(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -347,6 +469,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mh-steps", type=int, default=20000, help="steps per chain of the secondary (C3 Metropolis-Hastings) measurement")
+    ap.add_argument("--no-mh", action="store_true", help="skip the secondary measurement")
     args = ap.parse_args()
     # The contract is ONE JSON line on stdout: libraries that print banners there (NCCL prints its version on the first
     # communicator) are sent to stderr by pointing fd 1 at fd 2 for the duration of the run; the line goes to the real stdout.

@@ -25,7 +25,7 @@
 #define GR_WARPS (GR_THREADS / 32)
 #define GR_JPT 8
 #define GR_CH (GR_THREADS * GR_JPT)
-#define GR_RB 4         // rows per work unit of pass 1
+#define GR_RB 8         // rows per work unit of pass 1
 #define PQ_GRID_CTR_WORD 24   // unit counters of pass 1: ticket words 24..63 (bytes 96..255 of the ticket area, after ShortHdr)
 #define PQ_GRID_MAX_CTR 32
 #define GR_MSTRIDE 32   // a thread's 8 points are 32 apart: a warp covers 256 CONTIGUOUS positions of a row (compact tiles)
@@ -60,14 +60,16 @@ __device__ __forceinline__ bool pq_isnan_bits(double x) {                   // i
     return hi > 0x7ff00000u || (hi == 0x7ff00000u && __double2loint(x) != 0);
 }
 
-// float upper bound of a double as an order-preserving unsigned key (larger value <=> larger key)
-__device__ __forceinline__ unsigned int up_key(double v) {
-    const unsigned int u = __float_as_uint(__double2float_ru(v));
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
+// Tile maxima are kept as order-preserving keys of the HIGH WORD of a double (larger value <=> larger key; NaNs are
+// excluded by the callers); key_value() returns an upper bound of every double with that key.  Key 0 decodes to NaN
+// (compares false with everything: "no tile").
+__device__ __forceinline__ unsigned int hi_okey(unsigned int h) { return (h & 0x80000000u) ? ~h : (h | 0x80000000u); }
 __device__ __forceinline__ double key_value(unsigned int k) {
-    const unsigned int u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
-    return (double)__uint_as_float(u);
+    if (k & 0x80000000u) {                                       // non-negative: largest low word
+        const unsigned int h = k & 0x7fffffffu;
+        return (h >= 0x7ff00000u) ? pq_pos_inf() : __hiloint2double((int)h, (int)0xffffffffu);
+    }
+    return __hiloint2double((int)~k, 0);                          // negative: smallest magnitude
 }
 
 // block-level merge of per-thread bests into *best_out
@@ -130,17 +132,6 @@ struct RowRec {
     static constexpr int N = ((2 + (KT - 1) + NT) + 1) & ~1;       // even: 16-byte aligned records
 };
 
-// order-preserving key of the high word of a double (larger value <=> larger key; NaNs excluded by the callers)
-__device__ __forceinline__ unsigned int hi_okey(unsigned int h) { return (h & 0x80000000u) ? ~h : (h | 0x80000000u); }
-// upper bound of every double whose high-word key is k
-__device__ __forceinline__ double hi_okey_upper(unsigned int k) {
-    if (k & 0x80000000u) {                                       // non-negative: largest low word
-        const unsigned int h = k & 0x7fffffffu;
-        return (h >= 0x7ff00000u) ? pq_pos_inf() : __hiloint2double((int)h, (int)0xffffffffu);
-    }
-    return __hiloint2double((int)~k, 0);                          // negative: smallest magnitude
-}
-
 // Work distribution: a "unit" is GR_RB consecutive rows of one chunk of columns.  T.dyn: units are handed out by one
 // atomic counter per chunk (ticket words PQ_GRID_CTR_WORD ...): a CTA starts on chunk blockIdx % nchunks, keeps its
 // per-column registers while that chunk has units and then moves on to the next chunk, so SMs that were given fewer
@@ -169,6 +160,7 @@ __global__ void __launch_bounds__(GR_THREADS, 3) k_grid_pass1(const __grid_const
     unsigned int* ctr = ticket + PQ_GRID_CTR_WORD;
     Best best = best_none();
     unsigned int lim = 0xffefffffu;            // exact scan when a row's smallest high word is <= lim (see above)
+    const int tstride = T.nchunks * GR_WARPS;
     int chunk = blockIdx.x % T.nchunks;
     long long static_next = blockIdx.x / T.nchunks;               // !T.dyn: units rg, rg + nrg, ...
     const int attempts = (nrows > 0) ? (T.dyn ? T.nchunks : 1) : 0;
@@ -232,8 +224,8 @@ __global__ void __launch_bounds__(GR_THREADS, 3) k_grid_pass1(const __grid_const
             const int nr = (int)((T.b_hi - bu < GR_RB) ? (T.b_hi - bu) : GR_RB);
             long long row0 = T.ML + bu * T.r2;
             const bool unit_inside = (row0 >= first) && (row0 + (long long)nr * T.r2 <= last);   // block-uniform
-            size_t tix = ((size_t)(bu - T.b_lo) * T.nchunks + chunk) * GR_WARPS + warp;
-            for (int tt = 0; tt < nr; ++tt, row0 += T.r2, tix += (size_t)T.nchunks * GR_WARPS) {
+            unsigned int* tptr = tilemax + ((size_t)(bu - T.b_lo) * T.nchunks + chunk) * GR_WARPS + warp;
+            for (int tt = 0; tt < nr; ++tt, row0 += T.r2, tptr += tstride) {
                 const double* rec = s_rec[cur] + tt * R::N;           // broadcast reads
                 const bool ok_low = rec[0] != 0.0;
                 const double plow = rec[1];
@@ -328,7 +320,7 @@ __global__ void __launch_bounds__(GR_THREADS, 3) k_grid_pass1(const __grid_const
                 }
                 if (STORE) {
                     const unsigned int wk = __reduce_max_sync(0xffffffffu, okey);
-                    if (lane == 0) tilemax[tix] = up_key(hi_okey_upper(wk));
+                    if (lane == 0) *tptr = wk;
                 }
             }
             if (warp == 0) stage(__shfl_sync(0xffffffffu, un, 0), cur ^ 1);
