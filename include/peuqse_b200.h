@@ -328,6 +328,73 @@ int64_t peuqse_ess_work_bytes(int64_t n_walkers, int32_t k);
 int peuqse_ess_run(const peuqse_problem* p, const peuqse_ess_spec* spec, double* d_x, double* d_logp_x,
                    double* d_chain, double* d_chain_logp, double* d_info, void* d_work, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Post-burn-in statistics of device-resident samples:
+ * calculatePostBurnInStatistics (IP.py:1861-1937) incl. its tail filter (arrayThresholdFilter, IP.py:3635-3664)
+ * and calculateInfoGain (IP.py:1770-1847; log-ratio form and the 100-bin KL-divergence form of
+ * plt.hist([prior, posterior], bins=100, density=True)), as streaming reductions over
+ * d_samples[n][k] (row-major), d_logp[n], d_logprior[n] -- the order the reference stacks the rows in
+ * (chain after chain, IP.py:1282-1319).  mu_AP / stdap / evidence agree with numpy to ~1e-13 relative
+ * (different summation order); the kept-row set, MAP row and histogram counts are exact.
+ * ------------------------------------------------------------------------------------------- */
+enum {
+    PEUQSE_FILTER_NONE = 0,      /* mcmc_threshold_filter_samples = False */
+    PEUQSE_FILTER_AUTO = 1,      /* benchmark 'auto': remove rows with log(-logP) > mean + coef*std (IP.py:1913-1918) */
+    PEUQSE_FILTER_MAP = 2,       /* benchmark 'MAP': remove rows with logP < max(logP) - coef (IP.py:1907-1912) */
+    PEUQSE_FILTER_MU_AP = 3      /* benchmark 'mu_AP': remove rows with logP < getLogP(mean of all samples) - coef (IP.py:1901-1906) */
+};
+
+typedef struct peuqse_stats_spec {
+    int32_t k;
+    int32_t filter;              /* PEUQSE_FILTER_* */
+    double coef;                 /* mcmc_threshold_filter_coefficient ('auto' = 2.0, IP.py:1873-1875) */
+    int32_t kl_bins;             /* bins of the KL-divergence histograms (reference: 100); 0 = skip */
+    int32_t reserved;
+} peuqse_stats_spec;
+
+/* layout of d_out (doubles; index values are int64 bit patterns) */
+#define PEUQSE_STATS_N_TOTAL 0
+#define PEUQSE_STATS_N_KEPT 1
+#define PEUQSE_STATS_CUT 2               /* a row is removed iff logP < cut (-inf: nothing removed) */
+#define PEUQSE_STATS_THRESHOLD 3         /* the reference's filteringThreshold (on log(-logP) for 'auto', on logP otherwise) */
+#define PEUQSE_STATS_MEAN_LOGNEG 4
+#define PEUQSE_STATS_STD_LOGNEG 5
+#define PEUQSE_STATS_MAX_LOGP_ALL 6      /* np.max over the unfiltered rows (NaN if any logP is NaN) */
+#define PEUQSE_STATS_MAP_LOGP 7
+#define PEUQSE_STATS_MAP_INDEX 8         /* int64: row of the first maximum among the KEPT rows (IP.py:1927) */
+#define PEUQSE_STATS_MAP_INDEX_ALL 9     /* int64: the same row in the unfiltered numbering */
+#define PEUQSE_STATS_EVIDENCE 10         /* mean(exp(logP)) / ||samples||_F (IP.py:1931) */
+#define PEUQSE_STATS_INFO_GAIN_LOG_RATIO 11   /* NaN when d_logprior is NULL */
+#define PEUQSE_STATS_INFO_GAIN_KL 12     /* NaN when no prior samples are given */
+#define PEUQSE_STATS_SUM_EXP 13
+#define PEUQSE_STATS_FROB2 14
+#define PEUQSE_STATS_MEAN_ALL 16         /* [16] mean of the unfiltered samples (written by begin for PEUQSE_FILTER_MU_AP) */
+#define PEUQSE_STATS_MU_AP 32            /* [16] */
+#define PEUQSE_STATS_STDAP 48            /* [16] np.std, ddof 0 */
+#define PEUQSE_STATS_MAP_THETA 64        /* [16] */
+#define PEUQSE_STATS_MIN 80              /* [16] of the kept rows */
+#define PEUQSE_STATS_MAX 96              /* [16] */
+#define PEUQSE_STATS_KL_EACH 112         /* [16] info_gain_KL_each_parameter */
+#define PEUQSE_STATS_JOINT_LO 128        /* [16] common histogram range of prior and posterior samples */
+#define PEUQSE_STATS_JOINT_HI 144        /* [16] */
+#define PEUQSE_STATS_DOUBLES 160
+
+int64_t peuqse_stats_work_bytes(void);
+/* unfiltered pass: fills N_TOTAL, MEAN_LOGNEG, STD_LOGNEG ('auto'), MAX_LOGP_ALL, MEAN_ALL ('mu_AP': the caller then
+ * evaluates getLogP at MEAN_ALL, e.g. with peuqse_logp_batch, and hands the device scalar to finish) */
+int peuqse_stats_begin(const peuqse_stats_spec* spec, const double* d_samples, const double* d_logp, int64_t n,
+                       double* d_out /*PEUQSE_STATS_DOUBLES*/, void* d_work, void* stream);
+/* d_logprior nullable (no log-ratio info gain); d_mu_ap_logp: device scalar, PEUQSE_FILTER_MU_AP only;
+ * d_prior_samples[n_prior][k] nullable (samples_of_prior, IP.py:194; no KL info gain without it) */
+int peuqse_stats_finish(const peuqse_stats_spec* spec, const double* d_samples, const double* d_logp, const double* d_logprior,
+                        int64_t n, const double* d_mu_ap_logp, const double* d_prior_samples, int64_t n_prior,
+                        double* d_out, void* d_work, void* stream);
+/* after finish: the kept rows copied in order into d_out_*[N_KEPT] (what the reference leaves in post_burn_in_samples,
+ * post_burn_in_log_posteriors_un_normed_vec, post_burn_in_log_priors_vec, IP.py:1919-1921) */
+int peuqse_stats_compact(const peuqse_stats_spec* spec, const double* d_samples, const double* d_logp, const double* d_logprior,
+                         int64_t n, const double* d_out, double* d_out_samples, double* d_out_logp,
+                         double* d_out_logprior /*nullable*/, void* d_work, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -639,6 +639,73 @@ def post_burn_in_statistics(samples, logp):
                 evidence=evidence)
 
 
+def array_threshold_filter(merged, key, threshold, remove='below'):
+    """arrayThresholdFilter (IP.py:3635-3664): rows whose key is beyond the threshold become NaN rows and are dropped
+    (comparisons with a NaN key or a NaN threshold are False, so such rows stay)."""
+    key = np.asarray(key).reshape(-1)
+    with np.errstate(invalid='ignore'):
+        bad = key > threshold if remove == 'above' else key < threshold
+    marked = merged * 1.0
+    marked[bad] = np.nan
+    return marked[~np.all(np.isnan(marked), axis=1)]
+
+
+def info_gain_kl(prior_samples, post_samples, bins=100):
+    """calculateInfoGain, KL form (IP.py:1772-1791).  plt.hist([a, b], bins=100, density=True) bins both data sets on
+    the common edges np.histogram_bin_edges(concatenate([a, b]), 100) and normalises each separately
+    (matplotlib Axes.hist; matplotlib itself is not installed here, so this restates its documented behaviour:
+    parity unpinned at that one call).  Returns (total, per-parameter list)."""
+    each = []
+    total = 0
+    for d in range(post_samples.shape[1]):
+        a, b = prior_samples[:, d].flatten(), post_samples[:, d].flatten()
+        edges = np.histogram_bin_edges(np.concatenate([a, b]), bins)
+        d0, _ = np.histogram(a, edges, density=True)
+        d1, _ = np.histogram(b, edges, density=True)
+        with np.errstate(divide='ignore', invalid='ignore'):
+            cur = d1 * np.log(d1 / d0)                                    # IP.py:1785
+        cur = np.sum(cur[np.isfinite(cur)])                               # IP.py:1786-1787
+        each.append(cur)
+        total = total + cur
+    return total, each
+
+
+def post_burn_in_statistics_filtered(samples, logp, logprior, benchmark='auto', coef=2.0, filter_samples=True,
+                                     mu_ap_logp_fn=None, prior_samples=None):
+    """calculatePostBurnInStatistics (IP.py:1861-1937) including the tail filter and calculateInfoGain's log-ratio form
+    (IP.py:1793-1803).  logp, logprior: (N,1).  Returns a dict with the filtered arrays and the statistics."""
+    samples = np.asarray(samples, dtype=float)
+    logp = np.asarray(logp, dtype=float).reshape(-1, 1)
+    logprior = np.asarray(logprior, dtype=float).reshape(-1, 1)
+    thr = None
+    if filter_samples:
+        merged = np.hstack((logp, logprior, samples))                    # IP.py:1887
+        with np.errstate(invalid='ignore', divide='ignore'):
+            log_neg = np.log(-1 * logp)                                   # IP.py:1894
+        if benchmark == 'mu_AP':
+            thr = mu_ap_logp_fn(np.mean(samples, axis=0)) - coef          # IP.py:1899-1904
+            merged = array_threshold_filter(merged, logp, thr, 'below')
+        elif benchmark == 'MAP':
+            thr = np.max(logp) - coef                                     # IP.py:1897, 1910
+            merged = array_threshold_filter(merged, logp, thr, 'below')
+        else:
+            thr = np.mean(log_neg) + coef * np.std(log_neg)               # IP.py:1895-1896, 1915
+            merged = array_threshold_filter(merged, log_neg, thr, 'above')
+        logp = np.atleast_2d(merged[:, 0]).transpose()
+        logprior = np.atleast_2d(merged[:, 1]).transpose()
+        samples = merged[:, 2:]
+    st = post_burn_in_statistics(samples, logp)
+    post = logp - np.log(st['evidence'])                                  # IP.py:1799
+    with np.errstate(invalid='ignore'):
+        ratios = post - logprior
+    ratios[np.isinf(ratios)] = 0
+    ratios = np.nan_to_num(ratios)
+    st.update(samples=samples, logP=logp, log_priors=logprior, threshold=thr, info_gain_log_ratio=np.mean(ratios))
+    if prior_samples is not None:
+        st['info_gain_KL'], st['info_gain_KL_each_parameter'] = info_gain_kl(np.asarray(prior_samples, dtype=float), samples)
+    return st
+
+
 # --------------------------------------------------------------------------------------------
 # Ensemble slice sampling -- published algorithm (parity unpinned, see module header)
 # --------------------------------------------------------------------------------------------

@@ -51,6 +51,17 @@ class MHSpec(C.Structure):
     ]
 
 
+class StatsSpec(C.Structure):
+    _fields_ = [("k", C.c_int32), ("filter", C.c_int32), ("coef", C.c_double), ("kl_bins", C.c_int32), ("reserved", C.c_int32)]
+
+
+FILTER_NONE, FILTER_AUTO, FILTER_MAP, FILTER_MU_AP = 0, 1, 2, 3
+# offsets inside the packed statistics result (PEUQSE_STATS_* macros)
+STATS = dict(N_TOTAL=0, N_KEPT=1, CUT=2, THRESHOLD=3, MEAN_LOGNEG=4, STD_LOGNEG=5, MAX_LOGP_ALL=6, MAP_LOGP=7, MAP_INDEX=8,
+             MAP_INDEX_ALL=9, EVIDENCE=10, INFO_GAIN_LOG_RATIO=11, INFO_GAIN_KL=12, SUM_EXP=13, FROB2=14, MEAN_ALL=16, MU_AP=32,
+             STDAP=48, MAP_THETA=64, MIN=80, MAX=96, KL_EACH=112, JOINT_LO=128, JOINT_HI=144, DOUBLES=160)
+
+
 class ESSSpec(C.Structure):
     _fields_ = [
         ("n_walkers", C.c_int64), ("n_iters", C.c_int64), ("first_iter", C.c_int64), ("seed", C.c_uint64),
@@ -78,6 +89,7 @@ EXPORTS = [
     "peuqse_comm_allreduce_sum_i64", "peuqse_peer_alloc", "peuqse_peer_create", "peuqse_peer_destroy",
     "peuqse_peer_max_bytes", "peuqse_peer_merge_best", "peuqse_peer_merge_acc", "peuqse_peer_sum_i64", "peuqse_merge_best", "peuqse_merge_acc", "peuqse_mh_run",
     "peuqse_philox_blocks", "peuqse_ess_work_bytes", "peuqse_ess_run",
+    "peuqse_stats_work_bytes", "peuqse_stats_begin", "peuqse_stats_finish", "peuqse_stats_compact",
 ]
 
 _lib = None
@@ -140,8 +152,14 @@ def load():
     L.peuqse_ess_work_bytes.restype = i64
     L.peuqse_ess_work_bytes.argtypes = [i64, i32]
     L.peuqse_ess_run.argtypes = [vp, C.POINTER(ESSSpec), vp, vp, vp, vp, vp, vp, vp]
+    L.peuqse_stats_work_bytes.restype = i64
+    L.peuqse_stats_work_bytes.argtypes = []
+    L.peuqse_stats_begin.argtypes = [C.POINTER(StatsSpec), vp, vp, i64, vp, vp, vp]
+    L.peuqse_stats_finish.argtypes = [C.POINTER(StatsSpec), vp, vp, vp, i64, vp, vp, i64, vp, vp, vp]
+    L.peuqse_stats_compact.argtypes = [C.POINTER(StatsSpec), vp, vp, vp, i64, vp, vp, vp, vp, vp, vp]
     for name in EXPORTS:
-        if name not in ("peuqse_last_error", "peuqse_version", "peuqse_sweep_work_bytes", "peuqse_ess_work_bytes"):
+        if name not in ("peuqse_last_error", "peuqse_version", "peuqse_sweep_work_bytes", "peuqse_ess_work_bytes",
+                        "peuqse_stats_work_bytes", "peuqse_peer_max_bytes"):
             getattr(L, name).restype = C.c_int
     _lib = L
     return L

@@ -56,6 +56,13 @@ def mh_launch(pe, theta0, n_steps, burn_in, seed, step_chol, first_step=0, chain
     return out
 
 
+class _RowsOnDevice:
+    """Placeholder for an (N,1) array whose rows are still on the device (shape only)."""
+
+    def __init__(self, n):
+        self.shape = (int(n), 1)
+
+
 def chain_moments(stats, theta0, k, n_rows):
     """Pooled mean / covariance / MAP over chains from the per-chain statistics blocks (host, tiny)."""
     lay = _lib.mh_stat_layout(k)
@@ -137,11 +144,23 @@ def run_metropolis_hastings(pe, calculatePostBurnInStatistics=True, continueSamp
     S = out['samples']                                                                                # [R, C, k]
     pe.discrete_chains_post_burn_in_samples = D.allgather_rows(S[b:].permute(1, 0, 2).contiguous()).permute(1, 0, 2).cpu().numpy()
     # chain-major stacking = consolidate_parallel_sampling_data('equal'): vstack of every chain's rows (IP.py:1282-1319)
-    flat = lambda t: D.allgather_rows(t.permute(1, 0, *range(2, t.ndim)).contiguous()).reshape(-1, *t.shape[2:]).cpu().numpy()
-    pe.post_burn_in_samples = flat(S[b:])                                                             # IP.py:2718
-    pe.post_burn_in_log_posteriors_un_normed_vec = flat(out['logp'][b:]).reshape(-1, 1)               # IP.py:2724
+    flat_dev = lambda t: D.allgather_rows(t.permute(1, 0, *range(2, t.ndim)).contiguous()).reshape(-1, *t.shape[2:])
+    flat = lambda t: flat_dev(t).cpu().numpy()
+    d_s, d_lp, d_pr = flat_dev(S[b:]), flat_dev(out['logp'][b:]), flat_dev(out['logprior'][b:])
+    pe._dev_post = dict(samples=d_s, logp=d_lp, logprior=d_pr)              # device copies for the statistics kernels
+    from . import stats as ST
+    filtered = ST.filter_settings(pes)[0] != _lib.FILTER_NONE
+    if calculatePostBurnInStatistics and filtered and not continueSampling:
+        # the tail filter replaces these three arrays (IP.py:1919-1921): only the kept rows are copied to the host
+        pe._host_arrays_pending = True
+        pe.post_burn_in_samples = np.empty((d_s.shape[0], pe.k))[:0]
+        pe.post_burn_in_log_posteriors_un_normed_vec = _RowsOnDevice(d_lp.shape[0])
+        pe.post_burn_in_log_priors_vec = None
+    else:
+        pe.post_burn_in_samples = d_s.cpu().numpy()                                                   # IP.py:2718
+        pe.post_burn_in_log_posteriors_un_normed_vec = d_lp.cpu().numpy().reshape(-1, 1)              # IP.py:2724
+        pe.post_burn_in_log_priors_vec = d_pr.cpu().numpy().reshape(-1, 1)                            # IP.py:2727
     pe.post_burn_in_log_likelihoods_vec = flat(out['loglik'][b:]).reshape(-1, 1)                      # IP.py:2726
-    pe.post_burn_in_log_priors_vec = flat(out['logprior'][b:]).reshape(-1, 1)                         # IP.py:2727
     if not continueSampling:
         pe.during_burn_in_samples = flat(S[:b])                                                       # IP.py:2716
         pe.during_burn_in_log_posteriors_un_normed_vec = flat(out['logp'][:b]).reshape(-1, 1)
@@ -149,6 +168,7 @@ def run_metropolis_hastings(pe, calculatePostBurnInStatistics=True, continueSamp
         pe.post_burn_in_samples = np.vstack((pe.last_post_burn_in_samples, pe.post_burn_in_samples))  # IP.py:2731-2733
         pe.post_burn_in_log_posteriors_un_normed_vec = np.vstack((pe.last_post_burn_in_log_posteriors_un_normed_vec,
                                                                   pe.post_burn_in_log_posteriors_un_normed_vec))
+        pe._dev_post = None                                                  # merged on the host: statistics upload them
     if calculatePostBurnInStatistics:
         post_burn_in_statistics(pe, calculate_post_burn_in_log_priors_vec=bool(continueSampling))
         return [pe.map_parameter_set, pe.mu_AP_parameter_set, pe.stdap_parameter_set, pe.evidence, pe.info_gain,
@@ -160,84 +180,57 @@ def run_metropolis_hastings(pe, calculatePostBurnInStatistics=True, continueSamp
     return pe.map_logP
 
 
-def array_threshold_filter(merged, key, threshold, remove='below'):
-    """arrayThresholdFilter (IP.py:3635-3664): drop the rows whose key is beyond the threshold."""
-    key = np.asarray(key).reshape(-1)
-    bad = key > threshold if remove == 'above' else key < threshold
-    return merged[~bad]
-
-
 def post_burn_in_statistics(pe, calculate_post_burn_in_log_priors_vec=False):
-    """calculatePostBurnInStatistics (IP.py:1861-1937) on the host arrays, including the default tail filter
-    (Q9: log(-logP) > mean + 2 sigma removed) and the KL-divergence information gain (IP.py:1770-1794)."""
+    """calculatePostBurnInStatistics (IP.py:1861-1937) incl. the default tail filter (Q9: rows with
+    log(-logP) > mean + 2 sigma removed) and calculateInfoGain (IP.py:1770-1847), computed by the streaming kernels of
+    csrc/stats.cu on the device copies of the sample arrays (peuqse_b200/stats.py).  The sampler leaves those copies in
+    pe._dev_post; arrays that only exist on the host (continued sampling, ESS, user-edited arrays) are uploaded."""
+    from . import stats as ST
     pes = pe.UserInput.parameter_estimation_settings
-    if not hasattr(pe, 'post_burn_in_log_priors_vec') or pe.post_burn_in_log_priors_vec is None:
-        calculate_post_burn_in_log_priors_vec = True
-    if calculate_post_burn_in_log_priors_vec:                                                         # IP.py:1865-1869
-        _, lp, _ = pe.getLogP_batch(pe.post_burn_in_samples, return_parts=True)
+    dev = getattr(pe, '_dev_post', None)
+    pe._dev_post = None                       # consumed: a later call works from the (possibly edited) host arrays
+    n_rows = int(np.shape(pe.post_burn_in_log_posteriors_un_normed_vec)[0])
+    if dev is None or dev['samples'].shape[0] != n_rows:
+        up = lambda a: torch.as_tensor(np.ascontiguousarray(np.asarray(a, dtype=float)), dtype=torch.float64).to(_dev())
+        dev = dict(samples=up(pe.post_burn_in_samples).reshape(n_rows, pe.k), logp=up(pe.post_burn_in_log_posteriors_un_normed_vec).reshape(-1),
+                   logprior=None)
+        lpv = getattr(pe, 'post_burn_in_log_priors_vec', None)
+        if lpv is not None and not calculate_post_burn_in_log_priors_vec and np.shape(lpv)[0] == n_rows:
+            dev['logprior'] = up(lpv).reshape(-1)
+    if dev.get('logprior') is None or calculate_post_burn_in_log_priors_vec:                          # IP.py:1863-1869
+        _, lp, _ = pe.getLogP_batch(dev['samples'], return_parts=True)
+        dev['logprior'] = lp
         pe.post_burn_in_log_priors_vec = lp.cpu().numpy().reshape(-1, 1)
-    if bool(pes['mcmc_threshold_filter_samples']):
-        coef = pes['mcmc_threshold_filter_coefficient']
-        coef = 2.0 if (isinstance(coef, str) and coef.lower() == 'auto') else coef
-        logp = pe.post_burn_in_log_posteriors_un_normed_vec
-        merged = np.hstack((logp, pe.post_burn_in_log_priors_vec, pe.post_burn_in_samples))
-        with np.errstate(invalid='ignore', divide='ignore'):
-            logNeg = np.log(-1 * logp)                                                                # IP.py:1894
-        bench = pes['mcmc_threshold_filter_benchmark']
-        if bench == 'mu_AP':
-            thr = pe.getLogP(np.mean(pe.post_burn_in_samples, axis=0)) - coef                         # IP.py:1899-1906
-            merged = array_threshold_filter(merged, logp, thr, 'below')
-        elif bench == 'MAP':
-            merged = array_threshold_filter(merged, logp, np.max(logp) - coef, 'below')               # IP.py:1909-1912
-        else:
-            thr = np.mean(logNeg) + coef * np.std(logNeg)                                             # IP.py:1915
-            merged = array_threshold_filter(merged, logNeg, thr, 'above')
-        pe.post_burn_in_log_posteriors_un_normed_vec = np.atleast_2d(merged[:, 0]).transpose()
-        pe.post_burn_in_log_priors_vec = np.atleast_2d(merged[:, 1]).transpose()
-        pe.post_burn_in_samples = merged[:, 2:]
-    S = pe.post_burn_in_samples
-    lp = pe.post_burn_in_log_posteriors_un_normed_vec
-    pe.mu_AP_parameter_set = np.mean(S, axis=0)                                                       # IP.py:1923
-    pe.stdap_parameter_set = np.std(S, axis=0)                                                        # IP.py:1924
-    map_logP = max(lp)                                                                                # IP.py:1925
-    pe.map_logP = map_logP
-    pe.map_index = list(lp).index(map_logP)
-    pe.map_parameter_set = S[pe.map_index]
-    pe.evidence = np.mean(np.exp(lp)) / np.linalg.norm(S)                                             # IP.py:1931
-    pe.info_gain = calculate_info_gain(pe)
-    return [pe.map_parameter_set, pe.mu_AP_parameter_set, pe.stdap_parameter_set, pe.evidence, pe.info_gain, S, lp]
-
-
-def calculate_info_gain(pe):
-    """calculateInfoGain (IP.py:1770-1847): KL divergence from 100-bin histograms over the joint range of the
-    prior samples and the posterior samples (what plt.hist([a, b], bins=100, density=True) computes), or the
-    log-ratio form."""
-    pes = pe.UserInput.parameter_estimation_settings
-    S = pe.post_burn_in_samples
-    if pes['mcmc_info_gain_returned'] == 'KL_divergence':
-        total = 0
-        each = []
-        for d in range(S.shape[1]):
-            a, b = pe.samples_of_prior[:, d].flatten(), S[:, d].flatten()
-            lo, hi = min(a.min(), b.min()), max(a.max(), b.max())
-            d0, _ = np.histogram(a, bins=100, range=(lo, hi), density=True)
-            d1, _ = np.histogram(b, bins=100, range=(lo, hi), density=True)
-            with np.errstate(divide='ignore', invalid='ignore'):
-                cur = d1 * np.log(d1 / d0)
-            cur = np.sum(cur[np.isfinite(cur)])
-            each.append(cur)
-            total = total + cur
-        pe.info_gain_KL_each_parameter = pe.info_gain_each_parameter = each
-        pe.info_gain_KL = total
-        return total
-    if pes['mcmc_info_gain_cutoff'] != 0:
+    mode, coef = ST.filter_settings(pes)
+    want_kl = pes['mcmc_info_gain_returned'] == 'KL_divergence'
+    if not want_kl and pes['mcmc_info_gain_cutoff'] != 0:
         raise NotImplementedError("mcmc_info_gain_cutoff != 0 is not supported")
-    post = pe.post_burn_in_log_posteriors_un_normed_vec - np.log(pe.evidence)                        # IP.py:1799
-    ratios = post - pe.post_burn_in_log_priors_vec
-    ratios[np.isinf(ratios)] = 0
-    ratios = np.nan_to_num(ratios)
-    pe.info_gain_log_ratio = np.mean(ratios)
-    return pe.info_gain_log_ratio
+    R = ST.device_statistics(dev['samples'], dev['logp'], dev['logprior'], mode, coef,
+                             prior_samples=pe.samples_of_prior if want_kl else None, kl_bins=100, logp_fn=pe.getLogP_batch)
+    pe.gpu_launches += R.gpu_launches
+    pe.device_statistics = R
+    if mode != _lib.FILTER_NONE or getattr(pe, '_host_arrays_pending', False):                        # IP.py:1919-1921
+        ks, kl, kp = R.kept_rows()
+        pe.gpu_launches += 1
+        pe.post_burn_in_samples = ks.cpu().numpy()
+        pe.post_burn_in_log_posteriors_un_normed_vec = kl.cpu().numpy()
+        pe.post_burn_in_log_priors_vec = kp.cpu().numpy()
+        pe._host_arrays_pending = False
+    pe.mu_AP_parameter_set = R.mu_AP_parameter_set                                                    # IP.py:1923
+    pe.stdap_parameter_set = R.stdap_parameter_set                                                    # IP.py:1924
+    pe.map_logP = np.array([R.map_logP])                                                              # max() of (N,1) rows, IP.py:1925
+    pe.map_index = R.map_index
+    pe.map_parameter_set = R.map_parameter_set
+    pe.evidence = R.evidence                                                                          # IP.py:1931
+    pe.info_gain_log_ratio = R.info_gain_log_ratio
+    if want_kl:
+        pe.info_gain_KL_each_parameter = pe.info_gain_each_parameter = R.info_gain_KL_each_parameter
+        pe.info_gain_KL = R.info_gain_KL
+        pe.info_gain = R.info_gain_KL
+    else:
+        pe.info_gain = R.info_gain_log_ratio
+    return [pe.map_parameter_set, pe.mu_AP_parameter_set, pe.stdap_parameter_set, pe.evidence, pe.info_gain,
+            pe.post_burn_in_samples, pe.post_burn_in_log_posteriors_un_normed_vec]
 
 
 # ----------------------------------------------------------------------------------------------

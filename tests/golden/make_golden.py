@@ -195,6 +195,55 @@ def case_mh_example00(out):
     out['mh00_evidence'] = np.array(float(PE.evidence))
 
 
+def case_post_burn_in_statistics(out):
+    """calculatePostBurnInStatistics (IP.py:1861-1937) of the UNMODIFIED reference on given sample arrays, for every
+    filter benchmark; the info gain is the log-ratio form (the KL form needs a real matplotlib)."""
+    import contextlib
+    import io
+    import warnings
+    rng = np.random.default_rng(21)
+    N = 3000
+    mu, sd = np.array([200., 500.]), np.array([100., 200.])
+    th = np.vstack([np.array([165., 500.]) + np.array([55., 130.]) * rng.standard_normal((N - 300, 2)),
+                    mu + 6.0 * sd * (rng.random((300, 2)) - 0.5)])          # a posterior-like cloud plus a far tail
+    th = th[rng.permutation(N)]
+    UI = ui_example00()
+    UI.parameter_estimation_settings['mcmc_info_gain_returned'] = 'log_ratio'
+    PE = make_pe(UI)
+    vals = eval_points(PE, th)
+    out['pbs_samples'] = th
+    out['pbs_logP'] = vals[:, 0:1]
+    out['pbs_log_priors'] = vals[:, 1:2]
+    odd = vals[:, 0:1].copy()                                                # logP values the log(-logP) rule cannot handle
+    odd[5], odd[17], odd[123] = 0.5, 0.0, 3.25
+    out['pbs_logP_odd'] = odd
+    cases = [('auto', True, 2.0, 'pbs_logP'), ('auto1', True, 1.0, 'pbs_logP'), ('MAP', True, 2.0, 'pbs_logP'),
+             ('mu_AP', True, 2.0, 'pbs_logP'), ('off', False, 2.0, 'pbs_logP'), ('odd', True, 2.0, 'pbs_logP_odd')]
+    for name, on, coef, key in cases:
+        pes = PE.UserInput.parameter_estimation_settings
+        pes['mcmc_threshold_filter_samples'] = on
+        pes['mcmc_threshold_filter_coefficient'] = coef if name != 'auto' else 'auto'
+        pes['mcmc_threshold_filter_benchmark'] = {'auto1': 'auto', 'off': 'auto', 'odd': 'auto'}.get(name, name)
+        PE.post_burn_in_samples = th.copy()
+        PE.post_burn_in_log_posteriors_un_normed_vec = out[key].copy()
+        PE.post_burn_in_log_priors_vec = vals[:, 1:2].copy()
+        with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            res = PE.calculatePostBurnInStatistics()
+        p = f'pbs_{name}_'
+        out[p + 'map_theta'], out[p + 'mu_AP'], out[p + 'stdap'] = np.array(res[0]), np.array(res[1]), np.array(res[2])
+        out[p + 'evidence'], out[p + 'info_gain'] = np.array(float(res[3])), np.array(float(res[4]))
+        # the filtered arrays are row subsets of the inputs: store the kept row numbers (checked here, bit for bit)
+        kept_s, kept_lp, kept_pr = np.array(res[5]), np.array(res[6]), np.array(PE.post_burn_in_log_priors_vec)
+        lookup = {tuple(r): i for i, r in enumerate(th)}
+        idx = np.array([lookup[tuple(r)] for r in kept_s], dtype=np.int32)
+        assert np.all(np.diff(idx) > 0) and np.array_equal(th[idx], kept_s)
+        assert np.array_equal(out[key][idx], kept_lp, equal_nan=True) and np.array_equal(vals[idx, 1:2], kept_pr)
+        out[p + 'kept_rows'] = idx
+        out[p + 'map_logP'] = np.array(float(PE.map_logP))
+        out[p + 'map_index'] = np.array(int(PE.map_index))
+
+
 def case_priors(out):
     rng = np.random.default_rng(101)
     # uniform prior on parameter 1 (uncertainty -1) with bounds; Gaussian on parameter 0
@@ -391,6 +440,7 @@ if __name__ == "__main__":
         "tpd": [case_tpd],
         "multiresponse": [case_multiresponse],
         "uniform_multistart": [case_uniform_multistart],
+        "post_burn_in_statistics": [case_post_burn_in_statistics],
     }
     only = sys.argv[1:]
     for name, fns in groups.items():

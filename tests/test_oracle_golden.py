@@ -261,3 +261,31 @@ def test_ess_linear_gaussian_statistics():
     assert np.all(np.abs(s.mean(axis=0) - mean) < 5 * se)
     d = np.sqrt(np.diag(cov))
     np.testing.assert_allclose(np.cov(s.T) / np.outer(d, d), cov / np.outer(d, d), atol=0.15)
+
+
+PBS_CASES = [('auto', True, 2.0, 'auto', 'pbs_logP'), ('auto1', True, 1.0, 'auto', 'pbs_logP'), ('MAP', True, 2.0, 'MAP', 'pbs_logP'),
+             ('mu_AP', True, 2.0, 'mu_AP', 'pbs_logP'), ('off', False, 2.0, 'auto', 'pbs_logP'), ('odd', True, 2.0, 'auto', 'pbs_logP_odd')]
+
+
+@pytest.mark.parametrize("case", PBS_CASES, ids=[c[0] for c in PBS_CASES])
+def test_post_burn_in_statistics_with_filter(golden, case):
+    """calculatePostBurnInStatistics of the unmodified reference (every filter benchmark, log-ratio info gain): the
+    oracle restatement keeps exactly the same rows and reproduces the statistics bit for bit (same numpy calls)."""
+    name, on, coef, bench, key = case
+    g = golden("post_burn_in_statistics")
+    P = ex00()
+    sim_point, _ = orc.sim_quadratic(X00)
+    with np.errstate(all='ignore'):
+        st = orc.post_burn_in_statistics_filtered(g['pbs_samples'], g[key], g['pbs_log_priors'], benchmark=bench, coef=coef,
+                                                  filter_samples=on, mu_ap_logp_fn=lambda th: orc.log_p_point(P, th, sim_point))
+    rows = g[f'pbs_{name}_kept_rows']
+    assert np.array_equal(st['samples'], g['pbs_samples'][rows])
+    assert np.array_equal(st['logP'], g[key][rows], equal_nan=True)
+    assert np.array_equal(st['log_priors'], g['pbs_log_priors'][rows])
+    assert np.array_equal(st['mu_AP'], g[f'pbs_{name}_mu_AP']) and np.array_equal(st['stdap'], g[f'pbs_{name}_stdap'])
+    assert float(st['map_logP']) == float(g[f'pbs_{name}_map_logP']) and st['map_index'] == int(g[f'pbs_{name}_map_index'])
+    assert np.array_equal(st['map_parameter_set'], g[f'pbs_{name}_map_theta'])
+    assert st['evidence'] == float(g[f'pbs_{name}_evidence'])
+    assert st['info_gain_log_ratio'] == float(g[f'pbs_{name}_info_gain'])
+    if name == 'odd':
+        assert len(rows) == 3000          # a non-negative logP makes the threshold NaN: nothing is removed (IP.py:1894, 3650)
