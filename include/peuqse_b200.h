@@ -372,7 +372,7 @@ typedef struct peuqse_stats_spec {
 #define PEUQSE_STATS_MU_AP 32            /* [16] */
 #define PEUQSE_STATS_STDAP 48            /* [16] np.std, ddof 0 */
 #define PEUQSE_STATS_MAP_THETA 64        /* [16] */
-#define PEUQSE_STATS_MIN 80              /* [16] of the kept rows */
+#define PEUQSE_STATS_MIN 80              /* [16] of the kept rows (NaN unless prior samples are given: only the KL range needs them) */
 #define PEUQSE_STATS_MAX 96              /* [16] */
 #define PEUQSE_STATS_KL_EACH 112         /* [16] info_gain_KL_each_parameter */
 #define PEUQSE_STATS_JOINT_LO 128        /* [16] common histogram range of prior and posterior samples */

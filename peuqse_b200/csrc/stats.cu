@@ -3,8 +3,8 @@
 // as streaming reductions over samples[N][k], logP[N], logPrior[N] that already live in HBM (the sampler kernels'
 // outputs), so that neither the 8(k+2) N bytes nor a numpy pass over them ever cross to the host.
 //
-//   begin : A1  sum log(-logP), max logP (+ NaN flag), sum theta           (the unfiltered quantities of IP.py:1894-1900)
-//           A2  sum (log(-logP) - mean)^2                                   (np.std is two-pass: mean |x - mean|^2)
+//   begin : A   sum and sum of squares of log(-logP) about a pivot (the first row's value), max logP (+ NaN flag),
+//               sum theta                                                   (the unfiltered quantities of IP.py:1894-1900)
 //   finish: CUT threshold of the chosen benchmark -> one rule for every mode: a row is REMOVED iff logP < cut
 //           B1  over kept rows: n, sum theta, sum theta^2, first maximum of logP, sum exp(logP), min / max theta
 //           MID mu_AP, evidence (IP.py:1931), joint histogram range of prior and posterior samples
@@ -13,7 +13,9 @@
 //           FIN stdap, info gains, packed result
 //   compact (optional): order-preserving copy of the kept rows.
 // All sums are deterministic: every CTA owns a contiguous row range, per-CTA partials are combined in CTA order by the
-// last CTA to finish.  HBM-bound: 16 B/row (begin) + 2 x 8(k+2) B/row (finish) [+ 16(k+2) B/row for compact].
+// last CTA to finish.  HBM-bound: 8 B/row (begin) + 2 x 8(k+2) B/row (finish) [+ 16(k+2) B/row for compact].
+// B1 / B2 stream contiguous 256-row tiles (samples, logP, logPrior) through a 3-stage cp.async.bulk (TMA) ring into
+// shared memory: one elected thread issues the copies, every thread then reads its own row from the staged tile.
 //
 // 'auto' benchmark: the reference removes rows with log(-logP) > mean + coef*std.  log is monotone, so that set is
 // {-logP > x0} with x0 the largest double whose log is <= the threshold; CUT finds x0 by stepping ulps around
@@ -21,6 +23,8 @@
 // with logP >= 0 or NaN are kept, exactly like `filterKey > thresholdValue` on NaN keys (IP.py:3650).
 #include "common.cuh"
 #include "eval.cuh"
+#include "launch.cuh"
+#include "tma.cuh"
 
 #define ST_THREADS 256
 #define ST_MAXG 1024
@@ -42,7 +46,9 @@ struct StatsWork {                          // layout of d_work
     unsigned long long hist_prior[ST_K * ST_MAXBINS];
     double edges[ST_K * (ST_MAXBINS + 1)];
 };
-enum { K_SUMLN = 0, K_NANS = 1, K_MEANLN = 2, K_N = 3, K_LOGEV = 4, K_BEFORE = 5 };
+enum { K_N = 3, K_LOGEV = 4 };
+#define ST_STAGES 3
+#define ST_TILE ST_THREADS                  // rows per staged tile
 
 struct StatsGeom {
     long long n, rows_per_cta;
@@ -156,50 +162,108 @@ __device__ __forceinline__ bool cta_combine(StatsWork* W, double (&v)[NV], int n
 template <int KT, bool VEC2, bool THETA>
 __global__ void __launch_bounds__(ST_THREADS) k_stats_a1(const double* __restrict__ samples, const double* __restrict__ logp,
                                                          StatsGeom G, StatsWork* W, double* __restrict__ out) {
-    double v[2 + KT];
+    // slots: [0] sum (x - p), [1] sum (x - p)^2 with x = log(-logP) and p = x of row 0, [2] NaN logP count, [3..] sum theta
+    double v[3 + KT];
 #pragma unroll
-    for (int a = 0; a < 2 + KT; ++a) v[a] = 0.0;
+    for (int a = 0; a < 3 + KT; ++a) v[a] = 0.0;
     Best best = best_none();
+    const double pivot = log(-1.0 * logp[0]);
+    const bool piv_ok = pivot == pivot && fabs(pivot) < pq_pos_inf();
     const long long r0 = (long long)blockIdx.x * G.rows_per_cta;
     const long long r1 = (r0 + G.rows_per_cta < G.n) ? r0 + G.rows_per_cta : G.n;
     for (long long i = r0 + threadIdx.x; i < r1; i += ST_THREADS) {
         const double lp = __ldcs(logp + i);
-        v[0] += log(-1.0 * lp);                                    // IP.py:1894
-        if (lp != lp) v[1] += 1.0;
+        const double e = log(-1.0 * lp) - (piv_ok ? pivot : 0.0);    // IP.py:1894
+        v[0] += e;
+        v[1] += e * e;
+        if (lp != lp) v[2] += 1.0;
         if (lp > best.v) { best.v = lp; best.i = i; }
         if (THETA) {
             double th[KT];
             load_row<KT, VEC2>(samples, i, G.k, th);
 #pragma unroll
-            for (int d = 0; d < KT; ++d) v[2 + d] += th[d];
+            for (int d = 0; d < KT; ++d) v[3 + d] += th[d];
         }
     }
-    if (cta_combine<2 + KT>(W, v, 2 + KT, 0, best, true)) {
+    if (cta_combine<3 + KT>(W, v, 3 + KT, 0, best, true)) {
         if (threadIdx.x == 0) {
-            W->keep[K_SUMLN] = W->res[0];
-            W->keep[K_NANS] = W->res[1];
             const double n = (double)G.n;
-            W->keep[K_MEANLN] = W->res[0] / n;
+            const double m1 = W->res[0] / n;                           // mean - pivot
+            double var = W->res[1] / n - m1 * m1;                      // mean |x - mean|^2 (np.std, IP.py:1896)
+            if (var < 0.0) var = 0.0;
             out[PEUQSE_STATS_N_TOTAL] = n;
-            out[PEUQSE_STATS_MEAN_LOGNEG] = W->res[0] / n;
-            out[PEUQSE_STATS_MAX_LOGP_ALL] = (W->res[1] > 0.0) ? __longlong_as_double(0x7ff8000000000000LL) : W->bestv;   // np.max propagates NaN
+            out[PEUQSE_STATS_MEAN_LOGNEG] = (piv_ok ? pivot : 0.0) + m1;   // IP.py:1895
+            out[PEUQSE_STATS_STD_LOGNEG] = sqrt(var);
+            out[PEUQSE_STATS_MAX_LOGP_ALL] = (W->res[2] > 0.0) ? __longlong_as_double(0x7ff8000000000000LL) : W->bestv;   // np.max propagates NaN
         }
-        if (THETA && threadIdx.x < G.k) out[PEUQSE_STATS_MEAN_ALL + threadIdx.x] = W->res[2 + threadIdx.x] / (double)G.n;   // IP.py:1899
+        if (THETA && threadIdx.x < G.k) out[PEUQSE_STATS_MEAN_ALL + threadIdx.x] = W->res[3 + threadIdx.x] / (double)G.n;   // IP.py:1899
     }
 }
 
-__global__ void __launch_bounds__(ST_THREADS) k_stats_a2(const double* __restrict__ logp, StatsGeom G, StatsWork* W,
-                                                         double* __restrict__ out) {
-    double v[1] = {0.0};
-    const double mean = W->keep[K_MEANLN];
+// ---------------------------------------------------------------------------------------------
+// tile streaming for B1 / B2: stage buffer = [ST_TILE*k samples][ST_TILE logP][ST_TILE logPrior]
+// ---------------------------------------------------------------------------------------------
+struct TileRing {
+    double* buf;                 // [ST_STAGES][stage_doubles]
+    unsigned long long* full;    // [ST_STAGES]
+    int stage_doubles, k;
+    bool prior;
+    __device__ __forceinline__ void issue(int st, const double* samples, const double* logp, const double* logprior, long long row0) {
+        double* b = buf + (size_t)st * stage_doubles;
+        const uint32_t bs = (uint32_t)(ST_TILE * k * sizeof(double)), bl = (uint32_t)(ST_TILE * sizeof(double));
+        mbar_arrive_expect_tx(&full[st], bs + bl + (prior ? bl : 0u));
+        tma_load_1d(b, samples + row0 * k, bs, &full[st]);
+        tma_load_1d(b + ST_TILE * k, logp + row0, bl, &full[st]);
+        if (prior) tma_load_1d(b + ST_TILE * k + ST_TILE, logprior + row0, bl, &full[st]);
+    }
+};
+
+// Calls f(row, logP, logPrior, theta[KT]) for every row of this CTA's range: full 256-row tiles through the TMA ring
+// (when `tma`), the ragged tail (and everything, without `tma`) with direct loads.
+template <int KT, bool VEC2, class F>
+__device__ __forceinline__ void for_each_row(const double* __restrict__ samples, const double* __restrict__ logp,
+                                             const double* __restrict__ logprior, const StatsGeom& G, bool tma, unsigned char* s_raw,
+                                             F f) {
     const long long r0 = (long long)blockIdx.x * G.rows_per_cta;
     const long long r1 = (r0 + G.rows_per_cta < G.n) ? r0 + G.rows_per_cta : G.n;
-    for (long long i = r0 + threadIdx.x; i < r1; i += ST_THREADS) {
-        const double d = log(-1.0 * __ldcs(logp + i)) - mean;
-        v[0] += d * d;
+    long long done = r0;
+    if (tma) {
+        __shared__ __align__(8) unsigned long long s_full[ST_STAGES];
+        TileRing ring;
+        ring.buf = (double*)s_raw;
+        ring.full = s_full;
+        ring.k = G.k;
+        ring.prior = logprior != nullptr;
+        ring.stage_doubles = ST_TILE * (G.k + 2);
+        const long long ntile = (r1 - r0) / ST_TILE;
+        if (threadIdx.x == 0) {
+            for (int q = 0; q < ST_STAGES; ++q) mbar_init(&s_full[q], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int q = 0; q < ST_STAGES - 1 && q < ntile; ++q) ring.issue(q, samples, logp, logprior, r0 + (long long)q * ST_TILE);
+        for (long long t = 0; t < ntile; ++t) {
+            const int st = (int)(t % ST_STAGES);
+            if (threadIdx.x == 0 && t + ST_STAGES - 1 < ntile)       // the stage consumed in the previous iteration
+                ring.issue((int)((t + ST_STAGES - 1) % ST_STAGES), samples, logp, logprior, r0 + (t + ST_STAGES - 1) * ST_TILE);
+            while (!mbar_try_wait(&s_full[st], (uint32_t)((t / ST_STAGES) & 1))) {}
+            const double* b = ring.buf + (size_t)st * ring.stage_doubles;
+            double th[KT];
+#pragma unroll
+            for (int d = 0; d < KT; ++d) th[d] = (d < G.k) ? b[threadIdx.x * G.k + d] : 0.0;
+            const double lp = b[ST_TILE * G.k + threadIdx.x];
+            const double lpr = ring.prior ? b[ST_TILE * G.k + ST_TILE + threadIdx.x] : 0.0;
+            f(r0 + t * ST_TILE + threadIdx.x, lp, lpr, th);
+            __syncthreads();                                       // stage st may be refilled from now on
+        }
+        done = r0 + ntile * ST_TILE;
     }
-    if (cta_combine<1>(W, v, 1, 0, best_none(), false) && threadIdx.x == 0)
-        out[PEUQSE_STATS_STD_LOGNEG] = sqrt(W->res[0] / (double)G.n);                              // IP.py:1896
+    for (long long i = done + threadIdx.x; i < r1; i += ST_THREADS) {
+        double th[KT];
+        load_row<KT, VEC2>(samples, i, G.k, th);
+        f(i, __ldcs(logp + i), logprior ? __ldcs(logprior + i) : 0.0, th);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -235,10 +299,12 @@ __global__ void k_stats_cut(int filter, double coef, const double* __restrict__ 
     for (int a = 0; a < k * bins; ++a) { W->hist_post[a] = 0ULL; W->hist_prior[a] = 0ULL; }
 }
 
-template <int KT, bool VEC2>
+// RANGE: also the per-parameter minimum / maximum of the kept rows (needed for the KL histograms' range only)
+template <int KT, bool VEC2, bool RANGE>
 __global__ void __launch_bounds__(ST_THREADS) k_stats_b1(const double* __restrict__ samples, const double* __restrict__ logp,
-                                                         StatsGeom G, StatsWork* W, double* __restrict__ out) {
+                                                         StatsGeom G, StatsWork* W, double* __restrict__ out, bool tma) {
     // slots: [0] n_kept, [1] sum exp(logP), [2..2+KT) sum theta, [2+KT..2+2KT) sum theta^2 | min[KT] | max[KT]
+    extern __shared__ __align__(16) unsigned char s_raw[];
     constexpr int NV = 2 + 4 * KT;
     double v[NV];
 #pragma unroll
@@ -247,12 +313,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_stats_b1(const double* __restric
     for (int d = 0; d < KT; ++d) { v[2 + 2 * KT + d] = pq_pos_inf(); v[2 + 3 * KT + d] = pq_neg_inf(); }
     Best best = best_none();
     const double cut = out[PEUQSE_STATS_CUT];
-    const long long r0 = (long long)blockIdx.x * G.rows_per_cta;
-    const long long r1 = (r0 + G.rows_per_cta < G.n) ? r0 + G.rows_per_cta : G.n;
-    for (long long i = r0 + threadIdx.x; i < r1; i += ST_THREADS) {
-        const double lp = __ldcs(logp + i);
-        double th[KT];
-        load_row<KT, VEC2>(samples, i, G.k, th);
+    for_each_row<KT, VEC2>(samples, logp, nullptr, G, tma, s_raw, [&](long long i, double lp, double, const double (&th)[KT]) {
         if (!(lp < cut)) {
             v[0] += 1.0;
             v[1] += exp(lp);                                       // IP.py:1931
@@ -261,11 +322,13 @@ __global__ void __launch_bounds__(ST_THREADS) k_stats_b1(const double* __restric
             for (int d = 0; d < KT; ++d) {
                 v[2 + d] += th[d];
                 v[2 + KT + d] += th[d] * th[d];
-                v[2 + 2 * KT + d] = fmin(v[2 + 2 * KT + d], th[d]);
-                v[2 + 3 * KT + d] = fmax(v[2 + 3 * KT + d], th[d]);
+                if (RANGE) {
+                    v[2 + 2 * KT + d] = fmin(v[2 + 2 * KT + d], th[d]);
+                    v[2 + 3 * KT + d] = fmax(v[2 + 3 * KT + d], th[d]);
+                }
             }
         }
-    }
+    });
     {   // kept rows of this CTA (for compact): block-level count
         __shared__ double s_cnt[ST_THREADS / 32];
         const double c = warp_sum(v[0]);
@@ -282,8 +345,9 @@ __global__ void __launch_bounds__(ST_THREADS) k_stats_b1(const double* __restric
         if (threadIdx.x < G.k) {
             const int d = threadIdx.x;
             out[PEUQSE_STATS_MU_AP + d] = W->res[2 + d] / n;                                         // IP.py:1923
-            out[PEUQSE_STATS_MIN + d] = W->res[2 + 2 * KT + d];
-            out[PEUQSE_STATS_MAX + d] = W->res[2 + 3 * KT + d];
+            const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+            out[PEUQSE_STATS_MIN + d] = RANGE ? W->res[2 + 2 * KT + d] : qnan;
+            out[PEUQSE_STATS_MAX + d] = RANGE ? W->res[2 + 3 * KT + d] : qnan;
         }
         if (threadIdx.x == 0) {
             double f2 = 0.0;
@@ -352,14 +416,16 @@ __device__ __forceinline__ int st_hist_bin(const double* __restrict__ ed, int nb
 template <int KT, bool VEC2>
 __global__ void __launch_bounds__(ST_THREADS) k_stats_b2(const double* __restrict__ samples, const double* __restrict__ logp,
                                                          const double* __restrict__ logprior, StatsGeom G, StatsWork* W,
-                                                         double* __restrict__ out, int bins) {
+                                                         double* __restrict__ out, int bins, int copies, bool tma) {
     // slots: [0] sum log-ratio terms, [1] kept rows before the MAP row, [2..2+KT) sum (theta - mu_AP)^2
-    extern __shared__ __align__(8) unsigned char s_raw[];
-    double* s_edges = (double*)s_raw;                                             // [k][bins+1]
-    unsigned int* s_hist = (unsigned int*)(s_edges + (size_t)G.k * (bins + 1));   // [k][bins]
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    const size_t ring_bytes = tma ? (size_t)ST_STAGES * ST_TILE * (G.k + 2) * sizeof(double) : 0;
+    double* s_edges = (double*)(s_raw + ring_bytes);                              // [k][bins+1]
+    unsigned int* s_hist = (unsigned int*)(s_edges + (size_t)G.k * (bins + 1));   // [k][bins][copies]: lane & (copies-1) picks a
+    const int cmask = copies - 1, csel = (int)(threadIdx.x & 31) & cmask;         // private copy: fewer same-address conflicts
     if (bins > 0) {
         for (int a = threadIdx.x; a < G.k * (bins + 1); a += ST_THREADS) s_edges[a] = W->edges[a];
-        for (int a = threadIdx.x; a < G.k * bins; a += ST_THREADS) s_hist[a] = 0u;
+        for (int a = threadIdx.x; a < G.k * bins * copies; a += ST_THREADS) s_hist[a] = 0u;
         __syncthreads();
     }
     constexpr int NV = 2 + KT;
@@ -371,15 +437,10 @@ __global__ void __launch_bounds__(ST_THREADS) k_stats_b2(const double* __restric
     for (int d = 0; d < KT; ++d) mu[d] = (d < G.k) ? out[PEUQSE_STATS_MU_AP + d] : 0.0;
     const double cut = out[PEUQSE_STATS_CUT], logev = W->keep[K_LOGEV];
     const long long istar = __double_as_longlong(out[PEUQSE_STATS_MAP_INDEX_ALL]);
-    const long long r0 = (long long)blockIdx.x * G.rows_per_cta;
-    const long long r1 = (r0 + G.rows_per_cta < G.n) ? r0 + G.rows_per_cta : G.n;
-    for (long long i = r0 + threadIdx.x; i < r1; i += ST_THREADS) {
-        const double lp = __ldcs(logp + i);
-        double th[KT];
-        load_row<KT, VEC2>(samples, i, G.k, th);
-        const double lpr = logprior ? __ldcs(logprior + i) : 0.0;
+    const bool has_prior = logprior != nullptr;
+    for_each_row<KT, VEC2>(samples, logp, logprior, G, tma, s_raw, [&](long long i, double lp, double lpr, const double (&th)[KT]) {
         if (!(lp < cut)) {
-            if (logprior) {
+            if (has_prior) {
                 const double t = (lp - logev) - lpr;               // IP.py:1799-1800
                 if (t == t && fabs(t) < pq_pos_inf()) v[0] += t;   // inf -> 0, NaN -> 0 (IP.py:1801-1802)
             }
@@ -390,15 +451,18 @@ __global__ void __launch_bounds__(ST_THREADS) k_stats_b2(const double* __restric
                 v[2 + d] += e * e;                                 // np.std: mean(|x - mean|^2)
                 if (bins > 0 && d < G.k) {
                     const int b = st_hist_bin(s_edges + d * (bins + 1), bins, th[d]);
-                    if (b >= 0) atomicAdd(&s_hist[d * bins + b], 1u);
+                    if (b >= 0) atomicAdd(&s_hist[(d * bins + b) * copies + csel], 1u);
                 }
             }
         }
-    }
+    });
     if (bins > 0) {
         __syncthreads();
-        for (int a = threadIdx.x; a < G.k * bins; a += ST_THREADS)
-            if (s_hist[a]) atomicAdd(&W->hist_post[a], (unsigned long long)s_hist[a]);
+        for (int a = threadIdx.x; a < G.k * bins; a += ST_THREADS) {
+            unsigned int c = 0u;
+            for (int q = 0; q < copies; ++q) c += s_hist[a * copies + q];
+            if (c) atomicAdd(&W->hist_post[a], (unsigned long long)c);
+        }
     }
     if (cta_combine<NV>(W, v, NV, 0, best_none(), false)) {
         const double n = W->keep[K_N];
@@ -413,12 +477,19 @@ __global__ void __launch_bounds__(ST_THREADS) k_stats_b2(const double* __restric
 
 __global__ void __launch_bounds__(ST_THREADS) k_stats_prior_hist(const double* __restrict__ prior, long long np, int k, int bins,
                                                                 StatsWork* W) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    unsigned int* s_hist = (unsigned int*)s_raw;                    // [k][bins], flushed once per CTA
+    for (int a = threadIdx.x; a < k * bins; a += ST_THREADS) s_hist[a] = 0u;
+    __syncthreads();
     const long long total = np * k;
     for (long long e = (long long)blockIdx.x * ST_THREADS + threadIdx.x; e < total; e += (long long)gridDim.x * ST_THREADS) {
         const int d = (int)(e % k);
         const int b = st_hist_bin(W->edges + d * (bins + 1), bins, prior[e]);
-        if (b >= 0) atomicAdd(&W->hist_prior[d * bins + b], 1ULL);
+        if (b >= 0) atomicAdd(&s_hist[d * bins + b], 1u);
     }
+    __syncthreads();
+    for (int a = threadIdx.x; a < k * bins; a += ST_THREADS)
+        if (s_hist[a]) atomicAdd(&W->hist_prior[a], (unsigned long long)s_hist[a]);
 }
 
 // MAP row and KL-divergence information gain (IP.py:1772-1791): densities of np.histogram(density=True)
@@ -542,7 +613,6 @@ extern "C" int peuqse_stats_begin(const peuqse_stats_spec* s, const double* d_sa
     }
     PQ_DISPATCH_K(kb, SA1, 0)
 #undef SA1
-    if (s->filter == PEUQSE_FILTER_AUTO) k_stats_a2<<<G.grid, ST_THREADS, 0, st>>>(d_logp, G, W, d_out);
     PQ_CUDA_OK(cudaGetLastError());
     return PEUQSE_OK;
 }
@@ -561,26 +631,46 @@ extern "C" int peuqse_stats_finish(const peuqse_stats_spec* s, const double* d_s
     const bool vec2 = (s->k % 2 == 0) && ((((uintptr_t)d_samples) & 15) == 0);
     const int kb = pq_k_bucket(s->k);
     k_stats_cut<<<1, 32, 0, st>>>(s->filter, s->coef, d_mu_ap_logp, d_out, W, s->k, bins);
-#define SB1(KT, ...)                                                                                          \
-    {                                                                                                         \
-        if (vec2) k_stats_b1<KT, true><<<G.grid, ST_THREADS, 0, st>>>(d_samples, d_logp, G, W, d_out);           \
-        else k_stats_b1<KT, false><<<G.grid, ST_THREADS, 0, st>>>(d_samples, d_logp, G, W, d_out);               \
+    // TMA ring: 16-byte aligned sources (tile starts are multiples of 256 rows) and room for three stages
+    const size_t ring = (size_t)ST_STAGES * ST_TILE * (s->k + 2) * sizeof(double);
+    int dev = 0, max_optin = 48 * 1024;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    int copies = 8;                                     // private histogram copies per lane group, as many as fit
+    auto hist_bytes = [&](int c) { return (size_t)s->k * (bins + 1) * sizeof(double) + (size_t)s->k * bins * c * sizeof(unsigned int); };
+    while (copies > 1 && ring + hist_bytes(copies) + 2048 > (size_t)max_optin / 2) copies >>= 1;
+    const size_t smem_hist = kl ? hist_bytes(copies) : 0;
+    const bool aligned = ((((uintptr_t)d_samples) | ((uintptr_t)d_logp) | ((uintptr_t)d_logprior)) & 15) == 0;
+    const bool tma = aligned && ring + smem_hist + 2048 <= (size_t)max_optin;
+    const size_t smem1 = tma ? ring : 0, smem2 = (tma ? ring : 0) + smem_hist;
+#define SB1L(KT, V, R)                                                                                                         \
+    {                                                                                                                         \
+        cudaError_t e = pq_allow_smem((const void*)k_stats_b1<KT, V, R>, smem1);                                             \
+        if (e != cudaSuccess) return pq_set_cuda_error(e, "cudaFuncSetAttribute", __LINE__);                                  \
+        k_stats_b1<KT, V, R><<<G.grid, ST_THREADS, smem1, st>>>(d_samples, d_logp, G, W, d_out, tma);                          \
+    }
+#define SB1(KT, ...)                                                                                                          \
+    {                                                                                                                         \
+        if (vec2 && kl) SB1L(KT, true, true) else if (vec2) SB1L(KT, true, false) else if (kl) SB1L(KT, false, true) else SB1L(KT, false, false) \
     }
     PQ_DISPATCH_K(kb, SB1, 0)
 #undef SB1
+#undef SB1L
     if (kl) k_stats_edges<<<s->k, ST_THREADS, 0, st>>>(d_prior_samples, n_prior, s->k, bins, d_out, W);
-    const size_t smem = kl ? ((size_t)s->k * (bins + 1) * sizeof(double) + (size_t)s->k * bins * sizeof(unsigned int)) : 0;
-#define SB2(KT, ...)                                                                                                          \
+#define SB2L(KT, V)                                                                                                           \
     {                                                                                                                         \
-        if (vec2) k_stats_b2<KT, true><<<G.grid, ST_THREADS, smem, st>>>(d_samples, d_logp, d_logprior, G, W, d_out, bins);      \
-        else k_stats_b2<KT, false><<<G.grid, ST_THREADS, smem, st>>>(d_samples, d_logp, d_logprior, G, W, d_out, bins);          \
+        cudaError_t e = pq_allow_smem((const void*)k_stats_b2<KT, V>, smem2);                                                \
+        if (e != cudaSuccess) return pq_set_cuda_error(e, "cudaFuncSetAttribute", __LINE__);                                  \
+        k_stats_b2<KT, V><<<G.grid, ST_THREADS, smem2, st>>>(d_samples, d_logp, d_logprior, G, W, d_out, bins, copies, tma);  \
     }
+#define SB2(KT, ...) { if (vec2) SB2L(KT, true) else SB2L(KT, false) }
     PQ_DISPATCH_K(kb, SB2, 0)
 #undef SB2
+#undef SB2L
     if (kl) {
         const long long tot = n_prior * s->k;
-        const int g = (int)std::min<long long>((tot + ST_THREADS - 1) / ST_THREADS, 592);
-        k_stats_prior_hist<<<g, ST_THREADS, 0, st>>>(d_prior_samples, n_prior, s->k, bins, W);
+        const int g = (int)std::min<long long>((tot + 8 * ST_THREADS - 1) / (8 * ST_THREADS), 148);
+        k_stats_prior_hist<<<g, ST_THREADS, (size_t)s->k * bins * sizeof(unsigned int), st>>>(d_prior_samples, n_prior, s->k, bins, W);
     }
     k_stats_final<<<1, ST_THREADS, 0, st>>>(d_samples, s->k, bins, kl, d_out, W);
     PQ_CUDA_OK(cudaGetLastError());
