@@ -224,8 +224,8 @@ struct MhwLayout {
 // the values are bit-identical to k_mh's, and what the warp buys is latency -- draws for four steps per pass and
 // lane-spread moments cut a chain step from ~4000 to a few hundred cycles when there are too few chains to fill
 // the machine with one thread each.
-template <int MODEL, int KT, int U, int SMEM, bool TEVAL = false>
-__global__ void __launch_bounds__(32 * MHW_WARPS, 4) k_mh_warp(const __grid_constant__ DevProblem P,
+template <int MODEL, int KT, int U, int SMEM, bool TEVAL = false, int MINB = 4>
+__global__ void __launch_bounds__(32 * MHW_WARPS, MINB) k_mh_warp(const __grid_constant__ DevProblem P,
                                                                const __grid_constant__ DevMH M,
                                                                const double* __restrict__ theta0, const MHOut out,
                                                                int use_smem) {
@@ -410,7 +410,8 @@ int launch_mh(const peuqse_problem* p, const DevMH& M, const double* th0, const 
     if (p->d.n_total > PQ_THREAD_SHAPE_MAX_N || few) {
         void (*kern)(const DevProblem, const DevMH, const double*, const MHOut, int) = k_mh_warp<MODEL, KT, 2, -1>;
         if (p->d.n_total <= PQ_THREAD_SHAPE_MAX_N) kern = k_mh_warp<MODEL, KT, 2, -1, true>;
-        else if (use_smem) kern = k_mh_warp<MODEL, KT, 2, 1>;
+        // 3 CTAs (12 chains) per SM at 168 registers: the 4-CTA shape spills inside the observation loop and is 8 % slower
+        else if (use_smem) kern = k_mh_warp<MODEL, KT, 2, 1, false, 3>;
         const size_t wsmem = smem + (size_t)MHW_WARPS * MhwLayout<KT>::WDOUBLES * sizeof(double);
         PQ_CUDA_OK(pq_allow_smem((const void*)kern, wsmem));
         const long long blocks = (M.n_chains + MHW_WARPS - 1) / MHW_WARPS;
