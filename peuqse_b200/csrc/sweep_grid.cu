@@ -817,24 +817,22 @@ __global__ void __launch_bounds__(GR_THREADS) k_grid_pass2_tma(const __grid_cons
 // ---------------------------------------------------------------------------------------------
 // exp(x) for 0 <= x < 700: the usual reduction x = n ln2 + r, |r| <= ln2/2, degree-13 Taylor polynomial in Horner form,
 // scaling through the exponent field; <= 1 ulp like libdevice's exp but without its range / denormal handling.
+__constant__ double c_exp_pos[16] = {1.6059043836821613e-10 /* 1/13! */, 2.08767569878681e-09, 2.505210838544172e-08,
+                                     2.755731922398589e-07, 2.7557319223985893e-06, 2.48015873015873e-05,
+                                     1.984126984126984e-04, 1.388888888888889e-03, 8.333333333333333e-03,
+                                     4.1666666666666664e-02, 1.6666666666666666e-01, 0.5,
+                                     1.4426950408889634 /* log2(e) */, -6.93147180369123816490e-01 /* -ln2 hi */,
+                                     -1.90821492927058770002e-10 /* -ln2 lo */, 0.0};
+// (the coefficients sit in the constant bank / uniform registers: as immediates each costs two UMOVs per use)
 __device__ __forceinline__ double pq_exp_pos(double x) {
-    const double t = fma(x, 1.4426950408889634, 6755399441055744.0);
+    const double t = fma(x, c_exp_pos[12], 6755399441055744.0);
     const int n = __double2loint(t);
     const double fn = t - 6755399441055744.0;
-    double r = fma(fn, -6.93147180369123816490e-01, x);
-    r = fma(fn, -1.90821492927058770002e-10, r);
-    double p = 1.6059043836821613e-10;                    // 1/13!
-    p = fma(p, r, 2.08767569878681e-09);                  // 1/12!
-    p = fma(p, r, 2.505210838544172e-08);                 // 1/11!
-    p = fma(p, r, 2.755731922398589e-07);                 // 1/10!
-    p = fma(p, r, 2.7557319223985893e-06);                // 1/9!
-    p = fma(p, r, 2.48015873015873e-05);                  // 1/8!
-    p = fma(p, r, 1.984126984126984e-04);                 // 1/7!
-    p = fma(p, r, 1.388888888888889e-03);                 // 1/6!
-    p = fma(p, r, 8.333333333333333e-03);                 // 1/5!
-    p = fma(p, r, 4.1666666666666664e-02);                // 1/4!
-    p = fma(p, r, 1.6666666666666666e-01);                // 1/3!
-    p = fma(p, r, 0.5);
+    double r = fma(fn, c_exp_pos[13], x);
+    r = fma(fn, c_exp_pos[14], r);
+    double p = c_exp_pos[0];
+#pragma unroll
+    for (int i = 1; i < 12; ++i) p = fma(p, r, c_exp_pos[i]);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
     return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
@@ -947,23 +945,54 @@ __global__ void __launch_bounds__(GR_THREADS) k_grid_pass2_tma2(const __grid_con
                 const int jt = kt.chunk * GR_CH + GR_JL0;
                 const double* buf = s_buf + st * P2_STAGE_DOUBLES;
                 double roww = 0.0, rowwL = 0.0;                      // sum_m w, sum_m w*(theta_L - shift_L)
+                // a complete tile whose copy covers every point (all but the ragged last chunk and a rank's first / last rows)
+                const bool whole = sp.len == GR_CH && sp.lo == sp.start && sp.hi == sp.start + GR_CH && sp.a1 >= sp.hi;
+                if (whole) {
+                    // branch-free: the eight exp chains of a thread interleave in the fp64 pipe (a branch around each one
+                    // serialises them: 13 dependent DFMAs per point); points below the threshold get x = 0 and weight 0,
+                    // which adds exact zeros in the same order, so the sums are bit-identical to the guarded form.
+                    const double* bufw = buf + (sp.start - sp.a0) + GR_JL0;
+                    double x[GR_JPT], reps[GR_JPT];
+                    bool kp[GR_JPT];
 #pragma unroll
-                for (int m = 0; m < GR_JPT; ++m) {
-                    const long long e = sp.start + GR_JL0 + m * GR_MSTRIDE;
-                    double v = pq_neg_inf();
-                    if (GR_JL0 + m * GR_MSTRIDE < sp.len && e >= sp.lo && e < sp.hi)
-                        v = (e < sp.a1) ? buf[e - sp.a0] : __ldcs(logp_in + e);
-                    if (v > thr) {                                  // IP.py:3481
-                        const double reps = pq_exp_pos(v - thr);    // IP.py:3485
-                        const double wt = trunc(reps);              // IP.py:3486
+                    for (int m = 0; m < GR_JPT; ++m) {
+                        const double v = bufw[m * GR_MSTRIDE];
+                        kp[m] = v > thr;                             // IP.py:3481
+                        x[m] = kp[m] ? (v - thr) : 0.0;
+                    }
+#pragma unroll
+                    for (int m = 0; m < GR_JPT; ++m) reps[m] = pq_exp_pos(x[m]);    // IP.py:3485
+#pragma unroll
+                    for (int m = 0; m < GR_JPT; ++m) {
+                        const double wt = kp[m] ? trunc(reps[m]) : 0.0;             // IP.py:3486
                         const int j = jt + m * GR_MSTRIDE;
                         const double step = hL * (double)((j >> 1) + 1);
                         const double dl = ((j & 1) ? (cL + step) : (cL - step)) - shiftL;
-                        a_wr = fma(wt, reps, a_wr);
-                        a_nk += 1.0;
+                        a_wr = fma(wt, reps[m], a_wr);
+                        a_nk += kp[m] ? 1.0 : 0.0;
                         roww += wt;
                         rowwL = fma(wt, dl, rowwL);
                         s_col[j] += (unsigned int)wt;                // j always belongs to this thread
+                    }
+                } else {
+#pragma unroll
+                    for (int m = 0; m < GR_JPT; ++m) {
+                        const long long e = sp.start + GR_JL0 + m * GR_MSTRIDE;
+                        double v = pq_neg_inf();
+                        if (GR_JL0 + m * GR_MSTRIDE < sp.len && e >= sp.lo && e < sp.hi)
+                            v = (e < sp.a1) ? buf[e - sp.a0] : __ldcs(logp_in + e);
+                        if (v > thr) {                                  // IP.py:3481
+                            const double reps = pq_exp_pos(v - thr);    // IP.py:3485
+                            const double wt = trunc(reps);              // IP.py:3486
+                            const int j = jt + m * GR_MSTRIDE;
+                            const double step = hL * (double)((j >> 1) + 1);
+                            const double dl = ((j & 1) ? (cL + step) : (cL - step)) - shiftL;
+                            a_wr = fma(wt, reps, a_wr);
+                            a_nk += 1.0;
+                            roww += wt;
+                            rowwL = fma(wt, dl, rowwL);
+                            s_col[j] += (unsigned int)wt;                // j always belongs to this thread
+                        }
                     }
                 }
                 const double rw = warp_sum(roww);                    // integers < 2^53: exact in fp64
