@@ -41,7 +41,9 @@ enum {
     PEUQSE_MODEL_QUADRATIC = 1,  /* Examples/Example00/simulation_model_00.py:6-10: (x_j - th0)^2 + th1; const = x[n] */
     PEUQSE_MODEL_TPD2SITE = 2,   /* rate law of Examples/Example01/tprmodel.py:20, prescribed coverages;
                                     const = kBT[n], cov1[n], cov2[n]; theta = Ea1,Ea2,logA1,logA2,g1,g2 */
-    PEUQSE_MODEL_LINEAR = 3      /* sim_j = sum_d Phi[j][d]*th_d (d ascending); const = Phi[n][k] row-major */
+    PEUQSE_MODEL_LINEAR = 3,     /* sim_j = sum_d Phi[j][d]*th_d (d ascending); const = Phi[n][k] row-major */
+    PEUQSE_MODEL_LANGMUIR_LOG = 4 /* Examples/Example13doeFunctionExample/simulation_functions_Langmuir_CO_H2O_four_parameters.py:23-52:
+                                    log10(K pA/(1 + K pA)), K = exp(-(th0 - T_j th1)/(kB T_j)); const = T[n], kB*T[n], pA[n] */
 };
 
 /* likelihood evaluation mode of one response dimension (IP.py:2949-2979) */
@@ -394,6 +396,55 @@ int peuqse_stats_finish(const peuqse_stats_spec* spec, const double* d_samples, 
 int peuqse_stats_compact(const peuqse_stats_spec* spec, const double* d_samples, const double* d_logp, const double* d_logprior,
                          int64_t n, const double* d_out, double* d_out_samples, double* d_out_logp,
                          double* d_out_logprior /*nullable*/, void* d_work, void* stream);
+
+/*
+ * Design-of-experiments scenario batches.  replaces: doeGetInfoGainMatrix / doeParameterModulationPermutationsScanner
+ * (IP.py:1363-1572), which run one whole doMetropolisHastings per (parameter modulation, condition) pair on synthetic
+ * observations (populateResponsesWithSyntheticData, IP.py:1326-1354).  A scenario = one row of model constants (the
+ * independent variables the reference's populateIndependentVariablesFunction plugin pushes into the simulator,
+ * UserInput.py model['populateIndependentVariablesFunction'], IP.py:1403) + one row of observed values; prior, observed
+ * covariance and every other constant are the problem's (the reference keeps the first __init__'s covariance, IP.py:342-346).
+ */
+typedef struct peuqse_scenarios peuqse_scenarios;   /* opaque; owns d_model_const[S][..] and d_y[S][n_total] */
+
+/* h_model_const[S][n_model_const]: HOST rows laid out like peuqse_problem_desc.model_const (rows ordered like y) */
+int peuqse_scenarios_create(const peuqse_problem* p, int64_t n_scenarios, const double* h_model_const, peuqse_scenarios** out);
+int peuqse_scenarios_destroy(peuqse_scenarios* sc);
+/* observed values of scenario s := simulation at d_theta_true[s*theta_stride ..+k] under scenario s's constants
+ * (theta_stride 0 = one "true" parameter vector for every scenario); d_y_natural[S][n_total] (nullable) receives them in
+ * the caller's natural order (what the reference leaves in UserInput.responses['responses_observed'], IP.py:1351) */
+int peuqse_scenarios_synthesize(const peuqse_problem* p, peuqse_scenarios* sc, const double* d_theta_true, int64_t theta_stride,
+                                double* d_y_natural, void* stream);
+/* explicit observed values, d_y_natural[S][n_total] in natural order */
+int peuqse_scenarios_set_observed(const peuqse_problem* p, peuqse_scenarios* sc, const double* d_y_natural, void* stream);
+/* getLogP / getLogPrior / getLogLikelihood of d_theta[S][B][k] under each scenario; outputs [S][B], each nullable */
+int peuqse_scenarios_logp(const peuqse_problem* p, const peuqse_scenarios* sc, const double* d_theta, int64_t B,
+                          double* d_logp, double* d_logprior, double* d_loglik, void* stream);
+/* peuqse_mh_run with chain c sampling scenario c / chains_per_scenario; spec->n_chains = S * chains_per_scenario.  Chain j of
+ * every scenario draws from Philox stream chain_offset + j: all scenarios see the same draws, as in the reference, which
+ * reseeds numpy in every __init__ (IP.py:191-193).  Needs n_total <= 128.  Outputs as peuqse_mh_run. */
+int peuqse_mh_run_scenarios(const peuqse_problem* p, const peuqse_scenarios* sc, const peuqse_mh_spec* spec,
+                            int64_t chains_per_scenario, const double* d_theta0, double* d_samples, double* d_logp,
+                            double* d_logprior, double* d_loglik, double* d_deltas, double* d_us, double* d_stats, void* stream);
+
+/* per-scenario calculatePostBurnInStatistics (IP.py:1861-1937; filter NONE / AUTO / MAP) + log-ratio information gain
+ * (IP.py:1793-1803) over the MH outputs d_samples[n_rows][C][k], d_logp / d_logprior[n_rows][C], C = S * chains_per_scenario,
+ * rows [first_row, n_rows) of each chain, a scenario's chains stacked one after the other (IP.py:1282-1319).
+ * d_out[S][PEUQSE_SCEN_STATS_DOUBLES]; d_logprior nullable (no information gain). */
+#define PEUQSE_SCEN_STATS_N_TOTAL 0
+#define PEUQSE_SCEN_STATS_N_KEPT 1
+#define PEUQSE_SCEN_STATS_THRESHOLD 2
+#define PEUQSE_SCEN_STATS_MAP_LOGP 3
+#define PEUQSE_SCEN_STATS_MAP_INDEX 4        /* as a double: row of the first maximum among the kept rows */
+#define PEUQSE_SCEN_STATS_EVIDENCE 5
+#define PEUQSE_SCEN_STATS_INFO_GAIN_LOG_RATIO 6
+#define PEUQSE_SCEN_STATS_MU_AP 8            /* [16] */
+#define PEUQSE_SCEN_STATS_STDAP 24           /* [16] */
+#define PEUQSE_SCEN_STATS_MAP_THETA 40       /* [16] */
+#define PEUQSE_SCEN_STATS_DOUBLES 56
+int peuqse_scenarios_stats(int32_t k, int32_t filter, double coef, int64_t n_scenarios, int64_t chains_per_scenario,
+                           int64_t n_rows, int64_t first_row, const double* d_samples, const double* d_logp,
+                           const double* d_logprior, double* d_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -448,6 +448,28 @@ def sim_linear(Phi):
     return point, batch
 
 
+KB_EV = 8.61733035E-5   # eV/K, Examples/Example13doeFunctionExample/simulation_functions_Langmuir_CO_H2O_four_parameters.py:31
+
+
+def sim_langmuir_log(T, pA, offsets=(0.0, -25.0, 25.0)):
+    """Langmuir_replacement_three_temperatures_log of the reference's design-of-experiments example
+    (Examples/Example13doeFunctionExample/simulation_functions_Langmuir_CO_H2O_four_parameters.py:23-52):
+    for each temperature T_j = T + offsets[j] (the reference's order: middle, low, high)
+        delta_G = dH - T_j*dS;  K = exp(-delta_G/(kB*T_j));  theta_A = (K*pA)/(1 + K*pA);  sim_j = log10(theta_A).
+    theta = (dH, dS).  T and pA are the independent variables the DOE loop modulates."""
+    Tj = np.array([T + o for o in offsets], dtype=float)            # T, T-25, T+25 (T - 25 == T + (-25) in IEEE arithmetic)
+
+    def batch(th):
+        th = np.atleast_2d(np.asarray(th, dtype=float))
+        dG = th[:, 0:1] - Tj[None, :] * th[:, 1:2]
+        K = np.exp(-dG / (KB_EV * Tj[None, :]))
+        return np.log10((K * pA) / (1 + K * pA))
+
+    def point(theta):
+        return batch(np.asarray(theta, dtype=float)[None, :])[0]
+    return point, batch
+
+
 def cos_basis(n, k):
     x = np.linspace(0, 1, n)
     return np.cos(np.pi * np.arange(k)[None, :] * x[:, None])
@@ -704,6 +726,47 @@ def post_burn_in_statistics_filtered(samples, logp, logprior, benchmark='auto', 
     if prior_samples is not None:
         st['info_gain_KL'], st['info_gain_KL_each_parameter'] = info_gain_kl(np.asarray(prior_samples, dtype=float), samples)
     return st
+
+
+# --------------------------------------------------------------------------------------------
+# Design of experiments: information gain over a grid of conditions (IP.py:1326-1354, 1363-1572)
+# --------------------------------------------------------------------------------------------
+def doe_conditions(center, interval, num_intervals, array_format='xyz'):
+    """The conditions visited by doeGetInfoGainMatrix, in its loop order: 'xyz' walks getGridPermutations
+    (IP.py:1382, 755-770: the combination generator's order); 'meshgrid' walks np.linspace axes with the SECOND
+    variable in the outer loop (IP.py:1426-1438)."""
+    center = np.asarray(center, dtype=float)
+    if array_format == 'xyz':
+        return np.array(combination_generator(center, np.asarray(interval, dtype=float), np.asarray(num_intervals, dtype=int)), dtype=float)
+    lo = [center[i] - interval[i] * num_intervals[i] for i in range(2)]
+    hi = [center[i] + interval[i] * num_intervals[i] for i in range(2)]
+    ax = [np.linspace(lo[i], hi[i], num_intervals[i] * 2 + 1) for i in range(2)]
+    return np.array([[v1, v2] for v2 in ax[1] for v1 in ax[0]], dtype=float)
+
+
+def doe_info_gain_matrix(build_problem_for, simulate_for, conditions, theta_true, theta0, deltas, us, burn_in,
+                         filter_kwargs=None, prior_samples=None, info_gain_returned='log_ratio'):
+    """doeGetInfoGainMatrix (IP.py:1363-1472) for one "true" parameter vector: for every condition c the observed
+    responses are replaced by the simulation at theta_true (populateResponsesWithSyntheticData, IP.py:1326-1354; the
+    observed covariance keeps the values of the first __init__ because the synthetic uncertainties are None, IP.py:342-346),
+    one Metropolis-Hastings chain is run and its post-burn-in information gain is appended to the condition values.
+    build_problem_for(y) -> OracleProblem with observed responses y; simulate_for(c) -> (point, batch) simulators under
+    condition c; deltas[L-1,k] / us[L-1]: the draws, the SAME for every condition (the reference reseeds numpy in every
+    __init__, IP.py:191-193).  Returns (matrix[n_cond, n_var+1], list of per-condition statistics dicts)."""
+    rows, stats = [], []
+    fk = dict(filter_samples=False) if filter_kwargs is None else dict(filter_kwargs)
+    for c in np.asarray(conditions, dtype=float):
+        point, batch = simulate_for(c)
+        y = point(np.asarray(theta_true, dtype=float))                                    # IP.py:1332, 1351
+        P = build_problem_for(y)
+        run = mh_chains_batch(P, np.asarray(theta0, dtype=float)[None, :], deltas[:, None, :], us[:, None], batch)
+        b = int(burn_in)
+        st = post_burn_in_statistics_filtered(run['samples'][b:, 0, :], run['logP'][b:, 0], run['log_priors'][b:, 0],
+                                              prior_samples=prior_samples, **fk)
+        ig = st['info_gain_KL'] if info_gain_returned == 'KL_divergence' else st['info_gain_log_ratio']
+        rows.append(np.hstack((c, ig)))                                                   # IP.py:1412-1413
+        stats.append(st)
+    return np.array(rows), stats
 
 
 # --------------------------------------------------------------------------------------------

@@ -11,7 +11,7 @@ libpeuqse_b200.so (hand-written sm_100a CUDA behind the C ABI of include/peuqse_
 """
 from . import UserInput  # noqa: F401
 from .inverse_problem import parameter_estimation  # noqa: F401
-from .models import BuiltinModel, LinearModel, QuadraticModel, TorchSimulator, Tpd2SiteModel  # noqa: F401
+from .models import BuiltinModel, LangmuirLogModel, LinearModel, QuadraticModel, TorchSimulator, Tpd2SiteModel  # noqa: F401
 from ._lib import PeuqseError  # noqa: F401
 
 __version__ = "0.1.0"

@@ -9,7 +9,7 @@ import os
 MAX_K = 16
 MAX_RESP = 8
 
-MODEL_EXTERNAL, MODEL_QUADRATIC, MODEL_TPD2SITE, MODEL_LINEAR = 0, 1, 2, 3
+MODEL_EXTERNAL, MODEL_QUADRATIC, MODEL_TPD2SITE, MODEL_LINEAR, MODEL_LANGMUIR_LOG = 0, 1, 2, 3, 4
 RESP_MVN_DIAG, RESP_PER_VALUE, RESP_MVN_FULL = 0, 1, 2
 PRIOR_NONE, PRIOR_DIAG, PRIOR_DENSE = 0, 1, 2
 
@@ -62,6 +62,11 @@ STATS = dict(N_TOTAL=0, N_KEPT=1, CUT=2, THRESHOLD=3, MEAN_LOGNEG=4, STD_LOGNEG=
              STDAP=48, MAP_THETA=64, MIN=80, MAX=96, KL_EACH=112, JOINT_LO=128, JOINT_HI=144, DOUBLES=160)
 
 
+# offsets inside one scenario's statistics block (PEUQSE_SCEN_STATS_* macros)
+SCEN_STATS = dict(N_TOTAL=0, N_KEPT=1, THRESHOLD=2, MAP_LOGP=3, MAP_INDEX=4, EVIDENCE=5, INFO_GAIN_LOG_RATIO=6, MU_AP=8, STDAP=24,
+                  MAP_THETA=40, DOUBLES=56)
+
+
 class ESSSpec(C.Structure):
     _fields_ = [
         ("n_walkers", C.c_int64), ("n_iters", C.c_int64), ("first_iter", C.c_int64), ("seed", C.c_uint64),
@@ -90,6 +95,8 @@ EXPORTS = [
     "peuqse_peer_max_bytes", "peuqse_peer_merge_best", "peuqse_peer_merge_acc", "peuqse_peer_sum_i64", "peuqse_merge_best", "peuqse_merge_acc", "peuqse_mh_run",
     "peuqse_philox_blocks", "peuqse_ess_work_bytes", "peuqse_ess_run",
     "peuqse_stats_work_bytes", "peuqse_stats_begin", "peuqse_stats_finish", "peuqse_stats_compact",
+    "peuqse_scenarios_create", "peuqse_scenarios_destroy", "peuqse_scenarios_synthesize", "peuqse_scenarios_set_observed",
+    "peuqse_scenarios_logp", "peuqse_mh_run_scenarios", "peuqse_scenarios_stats",
 ]
 
 _lib = None
@@ -157,6 +164,13 @@ def load():
     L.peuqse_stats_begin.argtypes = [C.POINTER(StatsSpec), vp, vp, i64, vp, vp, vp]
     L.peuqse_stats_finish.argtypes = [C.POINTER(StatsSpec), vp, vp, vp, i64, vp, vp, i64, vp, vp, vp]
     L.peuqse_stats_compact.argtypes = [C.POINTER(StatsSpec), vp, vp, vp, i64, vp, vp, vp, vp, vp, vp]
+    L.peuqse_scenarios_create.argtypes = [vp, i64, c_double_p, C.POINTER(vp)]
+    L.peuqse_scenarios_destroy.argtypes = [vp]
+    L.peuqse_scenarios_synthesize.argtypes = [vp, vp, vp, i64, vp, vp]
+    L.peuqse_scenarios_set_observed.argtypes = [vp, vp, vp, vp]
+    L.peuqse_scenarios_logp.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp]
+    L.peuqse_mh_run_scenarios.argtypes = [vp, vp, C.POINTER(MHSpec), i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.peuqse_scenarios_stats.argtypes = [i32, i32, dbl, i64, i64, i64, i64, vp, vp, vp, vp, vp]
     for name in EXPORTS:
         if name not in ("peuqse_last_error", "peuqse_version", "peuqse_sweep_work_bytes", "peuqse_ess_work_bytes",
                         "peuqse_stats_work_bytes", "peuqse_peer_max_bytes"):

@@ -131,6 +131,7 @@ extern "C" int peuqse_simulate_batch(const peuqse_problem* p, const double* d_th
     switch (p->d.model_id) {
         case PEUQSE_MODEL_QUADRATIC: return launch_sim<PEUQSE_MODEL_QUADRATIC, 2>(p, d_theta, B, d_sim, st);
         case PEUQSE_MODEL_TPD2SITE: return launch_sim<PEUQSE_MODEL_TPD2SITE, 6>(p, d_theta, B, d_sim, st);
+        case PEUQSE_MODEL_LANGMUIR_LOG: return launch_sim<PEUQSE_MODEL_LANGMUIR_LOG, 2>(p, d_theta, B, d_sim, st);
         case PEUQSE_MODEL_LINEAR:
 #define PQ_SIM_LIN(KT, ...) return launch_sim<PEUQSE_MODEL_LINEAR, KT>(p, d_theta, B, d_sim, st)
             PQ_DISPATCH_K(kb, PQ_SIM_LIN, 0)
@@ -163,6 +164,8 @@ extern "C" int peuqse_logp_batch(const peuqse_problem* p, const double* d_theta,
             return launch_logp<PEUQSE_MODEL_QUADRATIC, 2>(p, d_theta, nullptr, B, d_logp, d_logprior, d_loglik, st);
         case PEUQSE_MODEL_TPD2SITE:
             return launch_logp<PEUQSE_MODEL_TPD2SITE, 6>(p, d_theta, nullptr, B, d_logp, d_logprior, d_loglik, st);
+        case PEUQSE_MODEL_LANGMUIR_LOG:
+            return launch_logp<PEUQSE_MODEL_LANGMUIR_LOG, 2>(p, d_theta, nullptr, B, d_logp, d_logprior, d_loglik, st);
         case PEUQSE_MODEL_LINEAR:
 #define PQ_LOGP_LIN(KT, ...) return launch_logp<PEUQSE_MODEL_LINEAR, KT>(p, d_theta, nullptr, B, d_logp, d_logprior, d_loglik, st)
             PQ_DISPATCH_K(kb, PQ_LOGP_LIN, 0)

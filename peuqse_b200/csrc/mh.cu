@@ -124,16 +124,26 @@ __device__ __forceinline__ void draws_thread(const DevMH& M, unsigned long long 
 // ---------------------------------------------------------------------------------------------
 // thread shape: one chain per thread (n_total <= PQ_THREAD_SHAPE_MAX_N)
 // ---------------------------------------------------------------------------------------------
-template <int MODEL, int KT>
+// SCEN: chain c samples the posterior of scenario c / SC.per (its own observed values and model constants, read from
+// global memory) and draws from Philox stream chain_offset + c % SC.per, so every scenario sees the same draws -- what the
+// reference's design-of-experiments loop does by reseeding numpy in each __init__ (IP.py:191-193, 1404-1407).
+template <int MODEL, int KT, bool SCEN = false>
 __global__ void __launch_bounds__(128) k_mh(const __grid_constant__ DevProblem P, const __grid_constant__ DevMH M,
-                                            const double* __restrict__ theta0, const MHOut out, int use_smem) {
+                                            const double* __restrict__ theta0, const MHOut out, int use_smem,
+                                            const DevScen SC) {
     extern __shared__ double smem[];
-    const ObsView O = stage_obs(P, smem, use_smem);
+    ObsView O = stage_obs(P, smem, use_smem);
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= M.n_chains) return;
     const int k = P.k;
     const long long C = M.n_chains;
-    const unsigned long long gchain = (unsigned long long)(M.chain_offset + c);
+    unsigned long long gchain = (unsigned long long)(M.chain_offset + c);
+    if constexpr (SCEN) {
+        const long long s = c / SC.per;
+        O.y = SC.y + s * SC.n_total;
+        O.mc = SC.mc + s * SC.n_mconst;
+        gchain = (unsigned long long)(M.chain_offset + (c - s * SC.per));
+    }
 
     double th[KT], th0[KT];
 #pragma unroll
@@ -224,23 +234,29 @@ struct MhwLayout {
 // the values are bit-identical to k_mh's, and what the warp buys is latency -- draws for four steps per pass and
 // lane-spread moments cut a chain step from ~4000 to a few hundred cycles when there are too few chains to fill
 // the machine with one thread each.
-template <int MODEL, int KT, int U, int SMEM, bool TEVAL = false, int MINB = 4>
+template <int MODEL, int KT, int U, int SMEM, bool TEVAL = false, int MINB = 4, bool SCEN = false>
 __global__ void __launch_bounds__(32 * MHW_WARPS, MINB) k_mh_warp(const __grid_constant__ DevProblem P,
                                                                const __grid_constant__ DevMH M,
                                                                const double* __restrict__ theta0, const MHOut out,
-                                                               int use_smem) {
+                                                               int use_smem, const DevScen SC) {
     using L = MhwLayout<KT>;
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* cur = smem + warp * L::WDOUBLES;
     double* th0s = cur + L::KPAD;
     double2* dr = reinterpret_cast<double2*>(th0s + L::KPAD);
-    const ObsView O = stage_obs<SMEM>(P, smem + MHW_WARPS * L::WDOUBLES, use_smem);
+    ObsView O = stage_obs<SMEM>(P, smem + MHW_WARPS * L::WDOUBLES, use_smem);
     const long long c = (long long)blockIdx.x * MHW_WARPS + warp;
     if (c >= M.n_chains) return;
     const int k = P.k;
     const long long C = M.n_chains;
-    const unsigned long long gchain = (unsigned long long)(M.chain_offset + c);
+    unsigned long long gchain = (unsigned long long)(M.chain_offset + c);
+    if constexpr (SCEN) {
+        const long long s = c / SC.per;
+        O.y = SC.y + s * SC.n_total;
+        O.mc = SC.mc + s * SC.n_mconst;
+        gchain = (unsigned long long)(M.chain_offset + (c - s * SC.per));
+    }
 
     double th[KT];
 #pragma unroll
@@ -402,34 +418,52 @@ __global__ void __launch_bounds__(32 * MHW_WARPS, MINB) k_mh_warp(const __grid_c
 
 namespace {
 template <int MODEL, int KT>
-int launch_mh(const peuqse_problem* p, const DevMH& M, const double* th0, const MHOut& out, cudaStream_t st) {
+int launch_mh(const peuqse_problem* p, const DevMH& M, const double* th0, const MHOut& out, cudaStream_t st,
+              const DevScen& SC = pq_no_scen()) {
     int use_smem;
     const size_t smem = pq_pick_smem(p, &use_smem);
     // few chains with few observations: one warp per chain, thread-order evaluation (latency); many: one thread per chain
     const bool few = M.n_chains <= MH_FEW_CHAINS;
+    if (SC.y) {
+        // scenario batch: thread-order evaluation in both shapes (n_total <= PQ_THREAD_SHAPE_MAX_N, checked by the caller)
+        if (few) {
+            auto kern = k_mh_warp<MODEL, KT, 2, -1, true, 4, true>;
+            const size_t wsmem = smem + (size_t)MHW_WARPS * MhwLayout<KT>::WDOUBLES * sizeof(double);
+            PQ_CUDA_OK(pq_allow_smem((const void*)kern, wsmem));
+            const long long blocks = (M.n_chains + MHW_WARPS - 1) / MHW_WARPS;
+            kern<<<(unsigned)blocks, 32 * MHW_WARPS, wsmem, st>>>(p->d, M, th0, out, use_smem, SC);
+        } else {
+            auto kern = k_mh<MODEL, KT, true>;
+            PQ_CUDA_OK(pq_allow_smem((const void*)kern, smem));
+            const long long blocks = (M.n_chains + 127) / 128;
+            kern<<<(unsigned)blocks, 128, smem, st>>>(p->d, M, th0, out, use_smem, SC);
+        }
+        PQ_CUDA_OK(cudaGetLastError());
+        return PEUQSE_OK;
+    }
     if (p->d.n_total > PQ_THREAD_SHAPE_MAX_N || few) {
-        void (*kern)(const DevProblem, const DevMH, const double*, const MHOut, int) = k_mh_warp<MODEL, KT, 2, -1>;
+        void (*kern)(const DevProblem, const DevMH, const double*, const MHOut, int, const DevScen) = k_mh_warp<MODEL, KT, 2, -1>;
         if (p->d.n_total <= PQ_THREAD_SHAPE_MAX_N) kern = k_mh_warp<MODEL, KT, 2, -1, true>;
         // 3 CTAs (12 chains) per SM at 168 registers: the 4-CTA shape spills inside the observation loop and is 8 % slower
         else if (use_smem) kern = k_mh_warp<MODEL, KT, 2, 1, false, 3>;
         const size_t wsmem = smem + (size_t)MHW_WARPS * MhwLayout<KT>::WDOUBLES * sizeof(double);
         PQ_CUDA_OK(pq_allow_smem((const void*)kern, wsmem));
         const long long blocks = (M.n_chains + MHW_WARPS - 1) / MHW_WARPS;
-        kern<<<(unsigned)blocks, 32 * MHW_WARPS, wsmem, st>>>(p->d, M, th0, out, use_smem);
+        kern<<<(unsigned)blocks, 32 * MHW_WARPS, wsmem, st>>>(p->d, M, th0, out, use_smem, SC);
     } else {
         auto kern = k_mh<MODEL, KT>;
         PQ_CUDA_OK(pq_allow_smem((const void*)kern, smem));
         const long long blocks = (M.n_chains + 127) / 128;
-        kern<<<(unsigned)blocks, 128, smem, st>>>(p->d, M, th0, out, use_smem);
+        kern<<<(unsigned)blocks, 128, smem, st>>>(p->d, M, th0, out, use_smem, SC);
     }
     PQ_CUDA_OK(cudaGetLastError());
     return PEUQSE_OK;
 }
 }  // namespace
 
-extern "C" int peuqse_mh_run(const peuqse_problem* p, const peuqse_mh_spec* s, const double* d_theta0, double* d_samples,
-                             double* d_logp, double* d_logprior, double* d_loglik, double* d_deltas, double* d_us,
-                             double* d_stats, void* stream) {
+static int mh_run_impl(const peuqse_problem* p, const peuqse_mh_spec* s, const DevScen& SC, const double* d_theta0,
+                       double* d_samples, double* d_logp, double* d_logprior, double* d_loglik, double* d_deltas, double* d_us,
+                       double* d_stats, void* stream) {
     if (!p || !s || !d_theta0 || !d_stats) return pq_set_error(PEUQSE_ERR_INVALID, "null argument");
     if (s->k != p->d.k) return pq_set_error(PEUQSE_ERR_INVALID, "mh k != problem k");
     if (s->n_chains < 1 || s->n_steps < 1 || s->thin < 1) return pq_set_error(PEUQSE_ERR_INVALID, "bad mh sizes");
@@ -453,14 +487,35 @@ extern "C" int peuqse_mh_run(const peuqse_problem* p, const peuqse_mh_spec* s, c
     cudaStream_t st = (cudaStream_t)stream;
     const int kb = pq_k_bucket(p->d.k);
     switch (p->d.model_id) {
-        case PEUQSE_MODEL_QUADRATIC: return launch_mh<PEUQSE_MODEL_QUADRATIC, 2>(p, M, d_theta0, out, st);
-        case PEUQSE_MODEL_TPD2SITE: return launch_mh<PEUQSE_MODEL_TPD2SITE, 6>(p, M, d_theta0, out, st);
+        case PEUQSE_MODEL_QUADRATIC: return launch_mh<PEUQSE_MODEL_QUADRATIC, 2>(p, M, d_theta0, out, st, SC);
+        case PEUQSE_MODEL_TPD2SITE: return launch_mh<PEUQSE_MODEL_TPD2SITE, 6>(p, M, d_theta0, out, st, SC);
+        case PEUQSE_MODEL_LANGMUIR_LOG: return launch_mh<PEUQSE_MODEL_LANGMUIR_LOG, 2>(p, M, d_theta0, out, st, SC);
         case PEUQSE_MODEL_LINEAR:
-#define MH_L(KT, ...) return launch_mh<PEUQSE_MODEL_LINEAR, KT>(p, M, d_theta0, out, st)
+#define MH_L(KT, ...) return launch_mh<PEUQSE_MODEL_LINEAR, KT>(p, M, d_theta0, out, st, SC)
             PQ_DISPATCH_K(kb, MH_L, 0)
 #undef MH_L
             break;
         default: break;
     }
     return pq_set_error(PEUQSE_ERR_INVALID, "unknown model");
+}
+
+extern "C" int peuqse_mh_run(const peuqse_problem* p, const peuqse_mh_spec* s, const double* d_theta0, double* d_samples,
+                             double* d_logp, double* d_logprior, double* d_loglik, double* d_deltas, double* d_us,
+                             double* d_stats, void* stream) {
+    return mh_run_impl(p, s, pq_no_scen(), d_theta0, d_samples, d_logp, d_logprior, d_loglik, d_deltas, d_us, d_stats, stream);
+}
+
+extern "C" int peuqse_mh_run_scenarios(const peuqse_problem* p, const peuqse_scenarios* sc, const peuqse_mh_spec* s,
+                                       int64_t chains_per_scenario, const double* d_theta0, double* d_samples, double* d_logp,
+                                       double* d_logprior, double* d_loglik, double* d_deltas, double* d_us, double* d_stats,
+                                       void* stream) {
+    if (!p || !sc || !s) return pq_set_error(PEUQSE_ERR_INVALID, "null argument");
+    if (!sc->has_y) return pq_set_error(PEUQSE_ERR_INVALID, "scenarios have no observed values yet (peuqse_scenarios_synthesize / _set_observed)");
+    if (sc->n_total != p->d.n_total || sc->n_mconst != p->d.n_mconst) return pq_set_error(PEUQSE_ERR_INVALID, "scenarios belong to another problem");
+    if (chains_per_scenario < 1 || s->n_chains != sc->S * chains_per_scenario)
+        return pq_set_error(PEUQSE_ERR_INVALID, "n_chains must equal n_scenarios * chains_per_scenario");
+    if (p->d.n_total > PQ_THREAD_SHAPE_MAX_N) return pq_set_error(PEUQSE_ERR_INVALID, "scenario batches support n_total <= 128");
+    DevScen SC{sc->d_y, sc->d_mc, (long long)chains_per_scenario, sc->n_total, sc->n_mconst};
+    return mh_run_impl(p, s, SC, d_theta0, d_samples, d_logp, d_logprior, d_loglik, d_deltas, d_us, d_stats, stream);
 }

@@ -54,7 +54,7 @@ extern "C" int peuqse_problem_create(const peuqse_problem_desc* h, peuqse_proble
     if (h->n_resp < 1 || h->n_resp > PQ_MAXR) return pq_set_error(PEUQSE_ERR_INVALID, "n_resp must be in [1, PEUQSE_MAX_RESP]");
     if (h->kp < 0 || h->kp > h->k) return pq_set_error(PEUQSE_ERR_INVALID, "kp out of range");
     if (h->prior_mode != PEUQSE_PRIOR_NONE && h->kp == 0) return pq_set_error(PEUQSE_ERR_INVALID, "prior_mode needs kp > 0");
-    if (h->model_id < PEUQSE_MODEL_EXTERNAL || h->model_id > PEUQSE_MODEL_LINEAR)
+    if (h->model_id < PEUQSE_MODEL_EXTERNAL || h->model_id > PEUQSE_MODEL_LANGMUIR_LOG)
         return pq_set_error(PEUQSE_ERR_INVALID, "unknown model_id");
 
     peuqse_problem* p = new peuqse_problem();
@@ -107,9 +107,11 @@ extern "C" int peuqse_problem_create(const peuqse_problem_desc* h, peuqse_proble
         long need = 0;
         if (h->model_id == PEUQSE_MODEL_QUADRATIC) need = h->n_total;
         if (h->model_id == PEUQSE_MODEL_TPD2SITE) need = 3L * h->n_total;
+        if (h->model_id == PEUQSE_MODEL_LANGMUIR_LOG) need = 3L * h->n_total;
         if (h->model_id == PEUQSE_MODEL_LINEAR) need = (long)h->n_total * h->k;
         if (need != h->n_model_const) { delete p; return pq_set_error(PEUQSE_ERR_INVALID, "n_model_const does not match the model"); }
         if (h->model_id == PEUQSE_MODEL_QUADRATIC && h->k != 2) { delete p; return pq_set_error(PEUQSE_ERR_INVALID, "quadratic model has k = 2"); }
+        if (h->model_id == PEUQSE_MODEL_LANGMUIR_LOG && h->k != 2) { delete p; return pq_set_error(PEUQSE_ERR_INVALID, "langmuir_log model has k = 2"); }
         if (h->model_id == PEUQSE_MODEL_TPD2SITE && h->k != 6) { delete p; return pq_set_error(PEUQSE_ERR_INVALID, "tpd2site model has k = 6"); }
     }
 

@@ -3,8 +3,9 @@ log-posterior hot path and its three data-parallel drivers running as sm_100a CU
 
 Same names, argument meanings and return conventions as the reference for the accelerated path:
 getLogP / getLogPrior / getLogLikelihood (IP.py:1647, 2756, 2850), doMultiStart (1077),
-doMetropolisHastings (2563), doEnsembleSliceSampling (2362).  Everything outside that path (plots, file
-export, optimisers, design of experiments, MPI) is out of scope and raises NotImplementedError.
+doMetropolisHastings (2563), doEnsembleSliceSampling (2362), doeGetInfoGainMatrix (1363),
+doeParameterModulationPermutationsScanner (1499).  Everything outside that path (plots, file export, optimisers, MPI)
+is out of scope and raises NotImplementedError.
 """
 import ctypes as C
 import sys
@@ -489,10 +490,21 @@ class parameter_estimation:
         from .mcmc import post_burn_in_statistics
         return post_burn_in_statistics(self, calculate_post_burn_in_log_priors_vec)
 
+    # ------------------------------------------------------------------------------------------
+    # design of experiments: every (modulation, condition) pair is one scenario of a device batch
+    # ------------------------------------------------------------------------------------------
+    def doeGetInfoGainMatrix(self, parameterPermutation, searchType='doMetropolisHastings'):     # IP.py:1363
+        from .doe import doe_get_info_gain_matrix
+        return doe_get_info_gain_matrix(self, parameterPermutation, searchType)
+
+    def doeParameterModulationPermutationsScanner(self, searchType='doMetropolisHastings'):       # IP.py:1499
+        from .doe import doe_parameter_modulation_scanner
+        return doe_parameter_modulation_scanner(self, searchType)
+
     # out of scope ------------------------------------------------------------------------------
     def _out_of_scope(self, *a, **k):
         raise NotImplementedError("outside the accelerated hot path (see DESIGN.md, 'Out of scope')")
 
     createAllPlots = makeHistogramsForEachParameter = makeSamplingScatterMatrixPlot = createSimulatedResponsesPlots = _out_of_scope
     doOptimizeNegLogP = doOptimizeLogP = doOptimizeSSR = doEnsembleModifiedMHSampling = _out_of_scope
-    doeGetInfoGainMatrix = doeParameterModulationPermutationsScanner = save_to_dill = load_from_dill = _out_of_scope
+    save_to_dill = load_from_dill = createInfoGainPlots = createInfoGainModulationPlots = _out_of_scope

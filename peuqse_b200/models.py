@@ -25,6 +25,12 @@ class BuiltinModel:
         """Flat float64 constants with per-observation rows permuted by `order` (the kernels' row order)."""
         raise NotImplementedError
 
+    def with_conditions(self, values):
+        """A copy of this model under other independent variables (design of experiments): the batched counterpart of the
+        reference's populateIndependentVariablesFunction plugin, which pushes the values into the simulator's module
+        namespace before every run (PEUQSE/InverseProblem.py:1403)."""
+        raise NotImplementedError(f"{type(self).__name__} has no independent variables to modulate")
+
     def __call__(self, theta):
         """Single-point simulation through the CUDA kernel (keeps the plugin callable like the reference's)."""
         if getattr(self, "_owner", None) is None:
@@ -43,8 +49,39 @@ class QuadraticModel(BuiltinModel):
     def n_total(self):
         return len(self.x)
 
+    def with_conditions(self, values):
+        return QuadraticModel(values)
+
     def constants(self, order):
         return np.ascontiguousarray(self.x[order])
+
+
+class LangmuirLogModel(BuiltinModel):
+    """log10 of a Langmuir coverage at the temperatures T + offsets: the simulator of the reference's design-of-experiments
+    example (Examples/Example13doeFunctionExample/simulation_functions_Langmuir_CO_H2O_four_parameters.py:23-52):
+        delta_G = dH - T_j*dS;  K = exp(-delta_G/(kB*T_j));  theta_A = K*pA/(1 + K*pA);  sim_j = log10(theta_A).
+    theta = (dH, dS); the independent variables are (T, pA)."""
+    model_id = _lib.MODEL_LANGMUIR_LOG
+    n_params = 2
+    KB_EV = 8.61733035E-5       # eV/K, simulation_functions_Langmuir_CO_H2O_four_parameters.py:31
+
+    def __init__(self, T=398.15, pA=0.1, offsets=(0.0, -25.0, 25.0)):
+        self.T, self.pA = float(T), float(pA)
+        self.offsets = tuple(float(o) for o in offsets)
+
+    def n_total(self):
+        return len(self.offsets)
+
+    def with_conditions(self, values):
+        return LangmuirLogModel(values[0], values[1], self.offsets)
+
+    def populateIndependentVariables(self, values):
+        """Usable as UserInput.model['populateIndependentVariablesFunction'] (takes effect at the next parameter_estimation)."""
+        self.T, self.pA = float(values[0]), float(values[1])
+
+    def constants(self, order):
+        Tj = np.array([self.T + o for o in self.offsets])
+        return np.ascontiguousarray(np.concatenate([Tj[order], (self.KB_EV * Tj)[order], np.full(len(Tj), self.pA)]))
 
 
 class Tpd2SiteModel(BuiltinModel):

@@ -1,0 +1,209 @@
+"""GPU parity tests of the design-of-experiments scenario batches (csrc/doe.cu, peuqse_b200/doe.py) against
+(a) tests/golden/doe.npz, produced by the UNMODIFIED reference's doeGetInfoGainMatrix /
+doeParameterModulationPermutationsScanner on the configuration of Examples/Example13doeFunctionExample with injected draws
+(tests/golden/make_golden_doe.py), (b) the numpy oracle replaying the device's own exported draws, and (c) the
+single-problem Metropolis-Hastings path (itself pinned against the reference) scenario by scenario.
+Tolerances: per-point values 1e-12 relative (exp / log10 of the CUDA math library are within 1-2 ulp of numpy's);
+information gains 1e-9 (a mean over post-burn-in rows of differences of log-posteriors)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import peuqse_b200 as PEUQSE
+    from oracle import peuqse_oracle as orc
+    from oracle import philox_np
+    return PEUQSE, orc, philox_np, torch
+
+
+X00 = [600, 1100, 1400]
+Y00 = [360500, 580500, 1620500]
+S00 = [200000, 300000, 200000]
+
+
+def make_pe(PEUQSE, model, observed, unc, mu, punc, settings=None):
+    UI = PEUQSE.UserInput.fresh()
+    UI.responses['responses_observed'] = observed
+    UI.responses['responses_observed_uncertainties'] = unc
+    UI.model['InputParameterPriorValues'] = mu
+    UI.model['InputParametersPriorValuesUncertainties'] = punc
+    UI.model['simulateByInputParametersOnlyFunction'] = model
+    UI.parameter_estimation_settings.update(settings or {})
+    return PEUQSE.parameter_estimation(UI)
+
+
+def doe_pe(PEUQSE, g, fmt='xyz', filtered=False, info='log_ratio', **extra):
+    L, BURN, STEP, DH, DS, DHU, DSU, SIG = g['settings']
+    UI = PEUQSE.UserInput.fresh()
+    model = PEUQSE.LangmuirLogModel(400, 0.1)
+    UI.responses['responses_observed'] = [0.0, 0.0, 0.0]
+    UI.responses['responses_observed_uncertainties'] = [SIG] * 3
+    UI.responses['independent_variables_values'] = [400, 0.1]
+    UI.model['InputParameterPriorValues'] = [DH, DS]
+    UI.model['InputParametersPriorValuesUncertainties'] = [DHU, DSU]
+    UI.model['simulateByInputParametersOnlyFunction'] = model
+    UI.model['populateIndependentVariablesFunction'] = model.populateIndependentVariables
+    pes = UI.parameter_estimation_settings
+    pes.update({'scaling_uncertainties_type': 'std', 'mcmc_mode': 'unbiased', 'mcmc_random_seed': 0, 'mcmc_burn_in': int(BURN),
+                'mcmc_length': int(L), 'mcmc_relative_step_length': float(STEP), 'mcmc_modulate_accept_probability': 0,
+                'mcmc_info_gain_returned': info, 'mcmc_threshold_filter_samples': filtered})
+    pes.update(extra)
+    UI.doe_settings.update({'info_gains_matrices_array_format': fmt, 'independent_variable_grid_center': [500, 0.5],
+                            'independent_variable_grid_interval_size': [100, 0.1], 'independent_variable_grid_num_intervals': [2, 2],
+                            'parameter_modulation_grid_interval_size': [1, 1], 'parameter_modulation_grid_num_intervals': [1, 1]})
+    return PEUQSE.parameter_estimation(UI)
+
+
+def test_langmuir_points_and_scenario_logp(env, golden):
+    PEUQSE, orc, _, torch = env
+    g = golden("doe")
+    L, BURN, STEP, DH, DS, DHU, DSU, SIG = g['settings']
+    PE = doe_pe(PEUQSE, g)
+    rng = np.random.default_rng(5)
+    th = np.array([DH, DS]) + np.array([DHU, DSU]) * rng.standard_normal((500, 2))
+    # single problem under the model's own conditions
+    P = orc.build_problem([DH, DS], [DHU, DSU], [0.0, 0.0, 0.0], [SIG] * 3)
+    _, bt = orc.sim_langmuir_log(400, 0.1)
+    ref = orc.log_p_batch(P, th, bt)
+    got = [t.cpu().numpy() for t in PE.getLogP_batch(th, return_parts=True)]
+    for a, b in zip(got, ref):
+        np.testing.assert_allclose(a, b, rtol=1e-12)
+    np.testing.assert_allclose(PE.simulate_batch(th).cpu().numpy(), bt(th), rtol=1e-13)
+    # scenario batch: synthetic observations and per-scenario log-posteriors
+    from peuqse_b200.doe import ScenarioBatch, conditions_grid
+    conds = conditions_grid(PE, PE.UserInput.doe_settings)
+    assert np.array_equal(conds, orc.doe_conditions([500, 0.5], [100, 0.1], [2, 2], 'xyz'))
+    batch = ScenarioBatch(PE, conds, g['theta_true'])
+    obs = batch.observed.cpu().numpy()
+    lp, pr, ll = (t.cpu().numpy() for t in batch.logp(np.tile(th[:64], (len(conds), 1, 1)), return_parts=True))
+    for s, c in enumerate(conds):
+        pt, bt = orc.sim_langmuir_log(c[0], c[1])
+        np.testing.assert_allclose(obs[s], pt(g['theta_true']), rtol=1e-13)
+        Ps = orc.build_problem([DH, DS], [DHU, DSU], obs[s], [SIG] * 3)
+        r = orc.log_p_batch(Ps, th[:64], bt)
+        np.testing.assert_allclose(lp[s], r[0], rtol=1e-12)
+        np.testing.assert_allclose(pr[s], r[1], rtol=1e-12)
+        np.testing.assert_allclose(ll[s], r[2], rtol=1e-12)
+    assert np.allclose(obs[-1], g['xyz_unfiltered_last_observed'][0], rtol=1e-13)
+
+
+@pytest.mark.parametrize("fmt", ["xyz", "meshgrid"])
+@pytest.mark.parametrize("filtered", [False, True])
+def test_info_gain_matrix_vs_reference_fixture(env, golden, fmt, filtered):
+    PEUQSE, orc, _, _ = env
+    g = golden("doe")
+    L, BURN, STEP, DH, DS, DHU, DSU, SIG = g['settings']
+    PE = doe_pe(PEUQSE, g, fmt, filtered)
+    M = PE.doeGetInfoGainMatrix(g['theta_true'])
+    ref = g[f"{fmt}_{'filtered' if filtered else 'unfiltered'}_info_gain_matrix"]
+    assert M.shape == ref.shape == (25, 3)
+    assert np.array_equal(M[:, :2], ref[:, :2])                      # the conditions, in the reference's loop order
+    np.testing.assert_allclose(M[:, 2], ref[:, 2], rtol=1e-9)        # the reference's information gains
+    assert np.array_equal(PE.info_gain_matrix, M)
+    # the oracle replaying the device's own draws (exported by a second launch of the same batch)
+    from peuqse_b200.mcmc import step_cholesky
+    batch = PE._doe_batch
+    run = batch.run_mh([DH, DS], int(L), int(BURN), 0, step_cholesky(PE.Q_covmat, STEP), export_draws=True)
+    deltas, us = run['deltas'].cpu().numpy(), run['us'].cpu().numpy()
+    assert np.array_equal(us[:, 0], g['us']) and all(np.array_equal(us[:, 0], us[:, s]) for s in range(25))   # common draws
+    np.testing.assert_allclose(deltas[:, 0], g['deltas'], rtol=1e-13, atol=1e-18)
+    assert np.array_equal(run['samples'].cpu().numpy(), PE._doe_run['samples'].cpu().numpy())
+    conds = orc.doe_conditions([500, 0.5], [100, 0.1], [2, 2], fmt)
+    fk = dict(filter_samples=filtered, benchmark='auto', coef=2.0)
+    Mo, st = orc.doe_info_gain_matrix(lambda y: orc.build_problem([DH, DS], [DHU, DSU], y, [SIG] * 3),
+                                      lambda c: orc.sim_langmuir_log(c[0], c[1]), conds, g['theta_true'], [DH, DS],
+                                      deltas[:, 0], us[:, 0], int(BURN), fk)
+    np.testing.assert_allclose(M[:, 2], Mo[:, 2], rtol=1e-9)
+    S = PE.doe_scenario_statistics
+    from peuqse_b200 import _lib
+    for s in range(25):
+        assert int(S[s, _lib.SCEN_STATS['N_KEPT']]) == st[s]['samples'].shape[0]
+        np.testing.assert_allclose(S[s, _lib.SCEN_STATS['MU_AP']:_lib.SCEN_STATS['MU_AP'] + 2], st[s]['mu_AP'], rtol=1e-11)
+        np.testing.assert_allclose(S[s, _lib.SCEN_STATS['STDAP']:_lib.SCEN_STATS['STDAP'] + 2], st[s]['stdap'], rtol=1e-9)
+        np.testing.assert_allclose(S[s, _lib.SCEN_STATS['MAP_LOGP']], st[s]['map_logP'], rtol=1e-12)
+        assert int(S[s, _lib.SCEN_STATS['MAP_INDEX']]) == st[s]['map_index']
+        np.testing.assert_allclose(S[s, _lib.SCEN_STATS['EVIDENCE']], st[s]['evidence'], rtol=1e-11)
+
+
+@pytest.mark.parametrize("fmt", ["xyz", "meshgrid"])
+def test_parameter_modulation_scanner_vs_reference_fixture(env, golden, fmt):
+    PEUQSE, orc, _, _ = env
+    g = golden("doe")
+    PE = doe_pe(PEUQSE, g, fmt, False)
+    A = PE.doeParameterModulationPermutationsScanner()
+    ref = g[f'scanner_{fmt}_info_gains_matrices_array']
+    assert A.shape == ref.shape == (9, 25, 3)
+    assert np.array_equal(A[:, :, :2], ref[:, :, :2])
+    np.testing.assert_allclose(A[:, :, 2], ref[:, :, 2], rtol=1e-9)
+    assert np.array_equal(PE.info_gains_matrices_array, A) and np.array_equal(PE.info_gain_matrix, A[-1])
+    assert PE.numParModulationPermutations == 9
+
+
+def test_map_filter_and_kl_information_gain(env, golden):
+    PEUQSE, orc, _, _ = env
+    g = golden("doe")
+    L, BURN, STEP, DH, DS, DHU, DSU, SIG = g['settings']
+    conds = orc.doe_conditions([500, 0.5], [100, 0.1], [2, 2], 'xyz')
+    build = lambda y: orc.build_problem([DH, DS], [DHU, DSU], y, [SIG] * 3)
+    sim = lambda c: orc.sim_langmuir_log(c[0], c[1])
+    # 'MAP' benchmark through the batched statistics kernel
+    PE = doe_pe(PEUQSE, g, 'xyz', True, mcmc_threshold_filter_benchmark='MAP', mcmc_threshold_filter_coefficient=1.5)
+    M = PE.doeGetInfoGainMatrix(g['theta_true'])
+    Mo, _ = orc.doe_info_gain_matrix(build, sim, conds, g['theta_true'], [DH, DS], g['deltas'], g['us'], int(BURN),
+                                     dict(filter_samples=True, benchmark='MAP', coef=1.5))
+    np.testing.assert_allclose(M[:, 2], Mo[:, 2], rtol=1e-9)
+    # KL-divergence form (per-scenario streaming statistics kernels), 'each' matrices
+    PE = doe_pe(PEUQSE, g, 'xyz', False, info='KL_divergence')
+    PE.UserInput.doe_settings['info_gains_matrices_multiple_parameters'] = 'each'
+    M = PE.doeGetInfoGainMatrix(g['theta_true'])
+    Mo, st = orc.doe_info_gain_matrix(build, sim, conds, g['theta_true'], [DH, DS], g['deltas'], g['us'], int(BURN),
+                                      dict(filter_samples=False), prior_samples=PE.samples_of_prior, info_gain_returned='KL_divergence')
+    np.testing.assert_allclose(M[:, 2], Mo[:, 2], rtol=1e-9)
+    for d in range(2):
+        np.testing.assert_allclose(PE.info_gain_matrices_each_parameter[d][:, 2],
+                                   [s['info_gain_KL_each_parameter'][d] for s in st], rtol=1e-9, atol=1e-12)
+
+
+def test_scenario_chains_equal_single_problem_chains(env):
+    """Thread-shape scenario kernel (more than 8192 chains) and the warp shape (few chains): every scenario's chains are
+    bit-identical to the chains of a stand-alone problem built from that scenario's conditions and observations."""
+    PEUQSE, orc, _, torch = env
+    from peuqse_b200.doe import ScenarioBatch
+    from peuqse_b200.mcmc import mh_launch, step_cholesky
+    rng = np.random.default_rng(11)
+    L, burn, cps = 120, 20, 4
+    for S in (2200, 37):
+        PE = make_pe(PEUQSE, PEUQSE.QuadraticModel(X00), Y00, S00, [200, 500], [100, 200], settings={'mcmc_length': L})
+        conds = np.array(X00, dtype=float) + 50.0 * rng.standard_normal((S, 3))
+        truth = np.array([200., 500.]) + np.array([100., 200.]) * rng.standard_normal((S, 2))
+        batch = ScenarioBatch(PE, conds, truth)
+        chol = step_cholesky(PE.Q_covmat, 0.1)
+        run = batch.run_mh([200., 500.], L, burn, 7, chol, chains_per_scenario=cps)
+        obs = batch.observed.cpu().numpy()
+        stats = batch.statistics(run, burn)
+        for s in rng.choice(S, 5, replace=False):
+            assert np.array_equal(obs[s], (conds[s] - truth[s, 0]) ** 2 + truth[s, 1])
+            PE1 = make_pe(PEUQSE, PEUQSE.QuadraticModel(conds[s]), list(obs[s]), S00, [200, 500], [100, 200], settings={'mcmc_length': L})
+            one = mh_launch(PE1, np.tile([200., 500.], (cps, 1)), L, burn, 7, chol)
+            sl = slice(s * cps, (s + 1) * cps)
+            assert np.array_equal(run['samples'][:, sl].cpu().numpy(), one['samples'].cpu().numpy())
+            assert np.array_equal(run['logp'][:, sl].cpu().numpy(), one['logp'].cpu().numpy())
+            assert np.array_equal(run['logprior'][:, sl].cpu().numpy(), one['logprior'].cpu().numpy())
+            # per-scenario statistics against the oracle on the stacked chains
+            smp = one['samples'][burn:].permute(1, 0, 2).reshape(-1, 2).cpu().numpy()
+            lp = one['logp'][burn:].permute(1, 0).reshape(-1).cpu().numpy()
+            pr = one['logprior'][burn:].permute(1, 0).reshape(-1).cpu().numpy()
+            st = orc.post_burn_in_statistics_filtered(smp, lp, pr, filter_samples=False)
+            from peuqse_b200 import _lib
+            SS = _lib.SCEN_STATS
+            np.testing.assert_allclose(stats[s, SS['MU_AP']:SS['MU_AP'] + 2], st['mu_AP'], rtol=1e-12)
+            np.testing.assert_allclose(stats[s, SS['STDAP']:SS['STDAP'] + 2], st['stdap'], rtol=1e-10)
+            assert int(stats[s, SS['MAP_INDEX']]) == st['map_index'] and stats[s, SS['MAP_LOGP']] == st['map_logP']
+            np.testing.assert_allclose(stats[s, SS['INFO_GAIN_LOG_RATIO']], st['info_gain_log_ratio'], rtol=1e-10)
+            assert np.array_equal(stats[s, SS['MAP_THETA']:SS['MAP_THETA'] + 2], st['map_parameter_set'])

@@ -289,3 +289,21 @@ def test_post_burn_in_statistics_with_filter(golden, case):
     assert st['info_gain_log_ratio'] == float(g[f'pbs_{name}_info_gain'])
     if name == 'odd':
         assert len(rows) == 3000          # a non-negative logP makes the threshold NaN: nothing is removed (IP.py:1894, 3650)
+
+
+@pytest.mark.parametrize("fmt", ["xyz", "meshgrid"])
+def test_doe_info_gain_matrices(golden, fmt):
+    """doeGetInfoGainMatrix / doeParameterModulationPermutationsScanner of the unmodified reference (Example13's
+    configuration, injected draws; tests/golden/make_golden_doe.py) vs the oracle restatement: bit for bit."""
+    g = golden("doe")
+    L, BURN, STEP, DH, DS, DHU, DSU, SIG = g['settings']
+    build = lambda y: orc.build_problem([DH, DS], [DHU, DSU], y, [SIG] * 3)
+    sim = lambda c: orc.sim_langmuir_log(c[0], c[1])
+    conds = orc.doe_conditions([500, 0.5], [100, 0.1], [2, 2], fmt)
+    for filt in (False, True):
+        M, _ = orc.doe_info_gain_matrix(build, sim, conds, g['theta_true'], [DH, DS], g['deltas'], g['us'], int(BURN),
+                                        dict(filter_samples=filt, benchmark='auto', coef=2.0))
+        assert np.array_equal(M, g[f"{fmt}_{'filtered' if filt else 'unfiltered'}_info_gain_matrix"])
+    mods = np.array(orc.combination_generator([DH, DS], np.array([1, 1]) * np.array([DHU, DSU]), [1, 1]), dtype=float)   # IP.py:1506-1509
+    A = np.array([orc.doe_info_gain_matrix(build, sim, conds, m, [DH, DS], g['deltas'], g['us'], int(BURN))[0] for m in mods])
+    assert np.array_equal(A, g[f'scanner_{fmt}_info_gains_matrices_array'])
