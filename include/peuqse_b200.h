@@ -430,7 +430,7 @@ int peuqse_mh_run_scenarios(const peuqse_problem* p, const peuqse_scenarios* sc,
 /* per-scenario calculatePostBurnInStatistics (IP.py:1861-1937; filter NONE / AUTO / MAP) + log-ratio information gain
  * (IP.py:1793-1803) over the MH outputs d_samples[n_rows][C][k], d_logp / d_logprior[n_rows][C], C = S * chains_per_scenario,
  * rows [first_row, n_rows) of each chain, a scenario's chains stacked one after the other (IP.py:1282-1319).
- * d_out[S][PEUQSE_SCEN_STATS_DOUBLES]; d_logprior nullable (no information gain). */
+ * d_out[S][PEUQSE_SCEN_STATS_DOUBLES(k)]; d_logprior nullable (no information gain). */
 #define PEUQSE_SCEN_STATS_N_TOTAL 0
 #define PEUQSE_SCEN_STATS_N_KEPT 1
 #define PEUQSE_SCEN_STATS_THRESHOLD 2
@@ -438,10 +438,10 @@ int peuqse_mh_run_scenarios(const peuqse_problem* p, const peuqse_scenarios* sc,
 #define PEUQSE_SCEN_STATS_MAP_INDEX 4        /* as a double: row of the first maximum among the kept rows */
 #define PEUQSE_SCEN_STATS_EVIDENCE 5
 #define PEUQSE_SCEN_STATS_INFO_GAIN_LOG_RATIO 6
-#define PEUQSE_SCEN_STATS_MU_AP 8            /* [16] */
-#define PEUQSE_SCEN_STATS_STDAP 24           /* [16] */
-#define PEUQSE_SCEN_STATS_MAP_THETA 40       /* [16] */
-#define PEUQSE_SCEN_STATS_DOUBLES 56
+#define PEUQSE_SCEN_STATS_MU_AP 8            /* [k] */
+#define PEUQSE_SCEN_STATS_STDAP(k) (8 + (k))        /* [k] */
+#define PEUQSE_SCEN_STATS_MAP_THETA(k) (8 + 2 * (k)) /* [k] */
+#define PEUQSE_SCEN_STATS_DOUBLES(k) (8 + 3 * (k))   /* doubles per scenario: the whole read-back of a batch is S of these */
 int peuqse_scenarios_stats(int32_t k, int32_t filter, double coef, int64_t n_scenarios, int64_t chains_per_scenario,
                            int64_t n_rows, int64_t first_row, const double* d_samples, const double* d_logp,
                            const double* d_logprior, double* d_out, void* stream);

@@ -63,8 +63,9 @@ STATS = dict(N_TOTAL=0, N_KEPT=1, CUT=2, THRESHOLD=3, MEAN_LOGNEG=4, STD_LOGNEG=
 
 
 # offsets inside one scenario's statistics block (PEUQSE_SCEN_STATS_* macros)
-SCEN_STATS = dict(N_TOTAL=0, N_KEPT=1, THRESHOLD=2, MAP_LOGP=3, MAP_INDEX=4, EVIDENCE=5, INFO_GAIN_LOG_RATIO=6, MU_AP=8, STDAP=24,
-                  MAP_THETA=40, DOUBLES=56)
+def scen_stats_layout(k):
+    return dict(N_TOTAL=0, N_KEPT=1, THRESHOLD=2, MAP_LOGP=3, MAP_INDEX=4, EVIDENCE=5, INFO_GAIN_LOG_RATIO=6, MU_AP=8, STDAP=8 + k,
+                MAP_THETA=8 + 2 * k, DOUBLES=8 + 3 * k)
 
 
 class ESSSpec(C.Structure):

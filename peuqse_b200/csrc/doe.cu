@@ -5,8 +5,8 @@
 // Here the S pairs are ONE batch: scenario s owns a row of model constants (the independent variables the reference
 // pushes into the simulator's namespace) and a row of observed values; the MH kernels of mh.cu walk S x chains chains at
 // once (peuqse_mh_run_scenarios) and k_scen_stats reduces every scenario's post-burn-in rows (calculatePostBurnInStatistics
-// IP.py:1861-1937 with the 'auto' / 'MAP' tail filter, calculateInfoGain's log-ratio form IP.py:1793-1803) with one CTA
-// per scenario, so the host reads back S x 56 doubles for the whole info-gain matrix.
+// IP.py:1861-1937 with the 'auto' / 'MAP' tail filter, calculateInfoGain's log-ratio form IP.py:1793-1803) in one launch,
+// so the host reads back S x (8 + 3k) doubles for the whole info-gain matrix.
 #include <vector>
 #include "common.cuh"
 #include "eval.cuh"
@@ -67,124 +67,243 @@ __global__ void __launch_bounds__(128) k_scen_logp(const __grid_constant__ DevPr
 }
 
 // ---------------------------------------------------------------------------------------------------
-// per-scenario post-burn-in statistics: one CTA per scenario
+// per-scenario post-burn-in statistics
 // ---------------------------------------------------------------------------------------------------
 #define SS_THREADS 256
+#define SS_WARPS (SS_THREADS / 32)
 
-// deterministic block sum: lanes by shuffle butterfly, warps in order by thread 0; result broadcast to every thread
-__device__ __forceinline__ double block_sum(double v, double* red) {
-    v = warp_sum(v);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double t = 0.0;
-#pragma unroll
-    for (int w = 0; w < SS_THREADS / 32; ++w) t += red[w];
-    return t;
-}
-__device__ __forceinline__ Best block_best(Best b, double* redv, long long* redi) {
-    b = warp_best(b);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) { redv[threadIdx.x >> 5] = b.v; redi[threadIdx.x >> 5] = b.i; }
-    __syncthreads();
-    Best t = best_none();
-#pragma unroll
-    for (int w = 0; w < SS_THREADS / 32; ++w) t = best_merge(t, Best{redv[w], redi[w]});
-    return t;
-}
-
-// rows of scenario s in the reference's stacking order (chain after chain, IP.py:1282-1319): i -> (chain, stored row)
+// rows of a scenario in the reference's stacking order (chain after chain, IP.py:1282-1319): i = chain*rows + r
 struct ScenRows {
     long long C, per, rows, first_row;      // chains in the launch, chains per scenario, post-burn-in rows per chain, first such row
-    __device__ __forceinline__ long long at(long long s, long long i) const {
-        const long long ch = i / rows, r = first_row + (i - ch * rows);
-        return r * C + (s * per + ch);
+};
+
+// Two ways of handing a scenario's rows to threads.  The MH kernels store row-major over chains (samples[r][c][k],
+// coalesced for the sampler), so a scenario's rows are C*8 bytes apart.
+//   ColumnTiles: a CTA owns 32 ADJACENT chains (32/per scenarios); lane = chain, the 8 warps take interleaved rows, so every
+//                warp load is one contiguous 256-byte run of a row; per-scenario totals = 8 row slices (shared memory, in
+//                order) then the scenario's `per` adjacent lanes (shuffle butterfly).  Needs per in {1,2,4,8,16,32}.
+//   CtaPerScenario: any `per`; one CTA per scenario with strided reads.
+struct ColumnTiles {
+    const ScenRows& R;
+    double (*red)[32];
+    long long (*redi)[32];
+    int lane, w;
+    long long c, s, ch;
+    bool live;
+    __device__ ColumnTiles(const ScenRows& R_, double (*red_)[32], long long (*redi_)[32]) : R(R_), red(red_), redi(redi_) {
+        lane = threadIdx.x & 31; w = threadIdx.x >> 5;
+        c = (long long)blockIdx.x * 32 + lane;
+        live = c < R.C;
+        s = c / R.per; ch = c - s * R.per;
+    }
+    __device__ __forceinline__ long long begin() const { return live ? w : R.rows; }
+    __device__ __forceinline__ long long end() const { return R.rows; }
+    __device__ __forceinline__ long long step() const { return SS_WARPS; }
+    __device__ __forceinline__ long long index(long long r) const { return ch * R.rows + r; }
+    __device__ __forceinline__ long long mem(long long r) const { return (R.first_row + r) * R.C + c; }
+    __device__ __forceinline__ long long mem_of_index(long long i) const {
+        const long long h = i / R.rows;
+        return (R.first_row + (i - h * R.rows)) * R.C + (s * R.per + h);
+    }
+    __device__ __forceinline__ bool writer() const { return live && w == 0 && ch == 0; }
+    __device__ __forceinline__ double sum(double v) const {
+        __syncthreads();
+        red[w][lane] = v;
+        __syncthreads();
+        double t = 0.0;
+#pragma unroll
+        for (int q = 0; q < SS_WARPS; ++q) t += red[q][lane];
+        for (int o = (int)R.per >> 1; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        return t;
+    }
+    __device__ __forceinline__ Best best(Best b) const {
+        __syncthreads();
+        red[w][lane] = b.v; redi[w][lane] = b.i;
+        __syncthreads();
+        Best t = best_none();
+#pragma unroll
+        for (int q = 0; q < SS_WARPS; ++q) t = best_merge(t, Best{red[q][lane], redi[q][lane]});
+        for (int o = (int)R.per >> 1; o > 0; o >>= 1) {
+            Best y;
+            y.v = __shfl_xor_sync(0xffffffffu, t.v, o);
+            y.i = __shfl_xor_sync(0xffffffffu, t.i, o);
+            t = best_merge(t, y);
+        }
+        return t;
     }
 };
 
-template <int KT>
+struct CtaPerScenario {
+    const ScenRows& R;
+    double (*red)[32];
+    long long (*redi)[32];
+    long long s;
+    __device__ CtaPerScenario(const ScenRows& R_, double (*red_)[32], long long (*redi_)[32]) : R(R_), red(red_), redi(redi_) {
+        s = blockIdx.x;
+    }
+    __device__ __forceinline__ long long begin() const { return threadIdx.x; }
+    __device__ __forceinline__ long long end() const { return R.per * R.rows; }
+    __device__ __forceinline__ long long step() const { return SS_THREADS; }
+    __device__ __forceinline__ long long index(long long i) const { return i; }
+    __device__ __forceinline__ long long mem(long long i) const { return mem_of_index(i); }
+    __device__ __forceinline__ long long mem_of_index(long long i) const {
+        const long long h = i / R.rows;
+        return (R.first_row + (i - h * R.rows)) * R.C + (s * R.per + h);
+    }
+    __device__ __forceinline__ bool writer() const { return threadIdx.x == 0; }
+    __device__ __forceinline__ double sum(double v) const {
+        v = warp_sum(v);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = v;
+        __syncthreads();
+        double t = 0.0;
+#pragma unroll
+        for (int q = 0; q < SS_WARPS; ++q) t += red[0][q];
+        return t;
+    }
+    __device__ __forceinline__ Best best(Best b) const {
+        b = warp_best(b);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = b.v; redi[0][threadIdx.x >> 5] = b.i; }
+        __syncthreads();
+        Best t = best_none();
+#pragma unroll
+        for (int q = 0; q < SS_WARPS; ++q) t = best_merge(t, Best{red[0][q], redi[0][q]});
+        return t;
+    }
+};
+
+// U rows per trip with every load issued before the first use: a thread's rows are independent but each trip ends in
+// transcendental chains (log / exp), so without this a warp has a single 256-byte load in flight and the kernel runs at the
+// memory latency (measured: 1.3 TB/s with one row per trip).
+template <int U, class MAP, class F>
+__device__ __forceinline__ void for_rows_logp(const MAP& T, const double* __restrict__ logp, F f) {
+    const long long b1 = T.end(), bs = T.step();
+    for (long long r = T.begin(); r < b1; r += U * bs) {
+        double lp[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) lp[u] = (r + u * bs < b1) ? logp[T.mem(r + u * bs)] : 0.0;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (r + u * bs < b1) f(r + u * bs, lp[u]);
+    }
+}
+
+template <int KT, int U, class MAP, class F>
+__device__ __forceinline__ void for_rows_all(const MAP& T, int k, const double* __restrict__ samples, const double* __restrict__ logp,
+                                             const double* __restrict__ lprior, F f) {
+    const long long b1 = T.end(), bs = T.step();
+    for (long long r = T.begin(); r < b1; r += U * bs) {
+        double lp[U], pr[U], th[U][KT];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const bool ok = r + u * bs < b1;
+            const long long row = ok ? T.mem(r + u * bs) : 0;
+            lp[u] = ok ? logp[row] : 0.0;
+            pr[u] = (ok && lprior) ? lprior[row] : 0.0;
+#pragma unroll
+            for (int d = 0; d < KT; ++d) th[u][d] = (ok && d < k) ? samples[row * k + d] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (r + u * bs < b1) f(r + u * bs, lp[u], pr[u], th[u]);
+    }
+}
+
+template <int KT, class MAP>
 __global__ void __launch_bounds__(SS_THREADS) k_scen_stats(const double* __restrict__ samples, const double* __restrict__ logp,
                                                            const double* __restrict__ lprior, const ScenRows R, int k, int filter,
                                                            double coef, double* __restrict__ out) {
-    __shared__ double red[SS_THREADS / 32];
-    __shared__ long long redi[SS_THREADS / 32];
-    const long long s = blockIdx.x;
-    const long long n = R.per * R.rows;
-    const int t = threadIdx.x;
-    // ---- threshold of the tail filter (IP.py:1887-1918): a row is removed iff `drop(logP)` ----
-    double thr = 0.0;                        // the reference's filteringThreshold
+    constexpr int U = KT <= 4 ? 4 : (KT <= 8 ? 2 : 1);
+    __shared__ double red[SS_WARPS][32];
+    __shared__ long long redi[SS_WARPS][32];
+    const MAP T(R, red, redi);
+    const double n = (double)(R.per * R.rows);
+    // ---- threshold of the tail filter (IP.py:1887-1918), turned into ONE rule: a row is removed iff logP < cut ----
+    double thr = __longlong_as_double(0x7ff8000000000000LL);     // the reference's filteringThreshold
+    double cut = pq_neg_inf();
     if (filter == PEUQSE_FILTER_AUTO) {
-        double a = 0.0;
-        for (long long i = t; i < n; i += SS_THREADS) a += log(-1.0 * logp[R.at(s, i)]);              // IP.py:1894
-        const double mean = block_sum(a, red) / (double)n;
-        a = 0.0;
-        for (long long i = t; i < n; i += SS_THREADS) { const double d = log(-1.0 * logp[R.at(s, i)]) - mean; a += d * d; }
-        const double sd = sqrt(block_sum(a, red) / (double)n);                                         // np.std, ddof 0
-        thr = mean + coef * sd;                                                                        // IP.py:1895-1896
+        // mean and standard deviation of log(-logP) (IP.py:1894-1896) in one pass about a pivot (the scenario's first row)
+        const double pivot = log(-1.0 * logp[T.mem_of_index(0)]);
+        double a = 0.0, a2 = 0.0;
+        for_rows_logp<8>(T, logp, [&](long long, double lp) { const double d = log(-1.0 * lp) - pivot; a += d; a2 = fma(d, d, a2); });
+        const double m1 = T.sum(a) / n, m2 = T.sum(a2) / n;
+        const double sd = sqrt(fmax(m2 - m1 * m1, 0.0));                                               // np.std, ddof 0
+        thr = (pivot + m1) + coef * sd;
+        // rows with log(-logP) > thr go (IP.py:1915, 3650).  log is monotone: x0 = the largest double with log(x0) <= thr,
+        // removed <=> -logP > x0 <=> logP < -x0.  A NaN threshold (some logP >= 0) removes nothing, NaN rows are kept.
+        double c = 0.0;
+        if (T.writer()) {
+            c = pq_neg_inf();
+            if (thr == thr && thr < pq_pos_inf()) {
+                double x = exp(thr);
+                if (!(x < pq_pos_inf())) x = 1.7976931348623157e308;
+                for (int it = 0; it < 64 && log(x) > thr; ++it) x = __longlong_as_double(__double_as_longlong(x) - 1);
+                for (int it = 0; it < 64; ++it) {
+                    const double xn = __longlong_as_double(__double_as_longlong(x) + 1);
+                    if (!(xn < pq_pos_inf()) || log(xn) > thr) break;
+                    x = xn;
+                }
+                c = -x;
+            }
+        }
+        cut = T.sum(c);                                          // one writer per scenario: broadcast
     } else if (filter == PEUQSE_FILTER_MAP) {
         // np.max propagates NaN: a NaN anywhere makes the threshold NaN and nothing is removed
-        double m = pq_neg_inf(); bool nan = false;
-        for (long long i = t; i < n; i += SS_THREADS) { const double v = logp[R.at(s, i)]; nan = nan || (v != v); m = fmax(m, v); }
-        const Best b = block_best(Best{m, (long long)t}, red, redi);
-        const int anynan = __syncthreads_or(nan ? 1 : 0);
-        thr = anynan ? __longlong_as_double(0x7ff8000000000000LL) : b.v - coef;                        // IP.py:1897, 1910
+        double m = pq_neg_inf(), nan = 0.0;
+        for_rows_logp<8>(T, logp, [&](long long, double v) { if (v != v) nan = 1.0; m = fmax(m, v); });
+        const Best b = T.best(Best{m, 0});
+        if (!(T.sum(nan) > 0.0)) { thr = b.v - coef; cut = thr; }                                      // IP.py:1897, 1910
     }
-    auto dropped = [&](double lp) -> bool {
-        if (filter == PEUQSE_FILTER_AUTO) return log(-1.0 * lp) > thr;                                 // remove 'above', IP.py:1915, 3650
-        if (filter == PEUQSE_FILTER_MAP) return lp < thr;                                              // remove 'below', IP.py:1910
-        return false;
-    };
-    // ---- pass B1 over kept rows: count, sum theta, sum theta^2, first maximum, sum exp(logP) ----
+    // ---- pass B1 over kept rows: count, sum theta, sum theta^2, first maximum, sum exp(logP); branch-free so that the
+    //      U rows' exp chains interleave ----
     double cnt = 0.0, sexp = 0.0, frob = 0.0, s1[KT];
 #pragma unroll
     for (int d = 0; d < KT; ++d) s1[d] = 0.0;
     Best best = best_none();
-    for (long long i = t; i < n; i += SS_THREADS) {
-        const long long row = R.at(s, i);
-        const double lp = logp[row];
-        if (dropped(lp)) continue;
-        cnt += 1.0;
-        sexp += exp(lp);
-        if (lp > best.v) { best.v = lp; best.i = i; }          // i ascending per thread: first maximum
+    for_rows_all<KT, U>(T, k, samples, logp, nullptr, [&](long long r, double lp, double, const double (&th)[KT]) {
+        const bool kept = !(lp < cut);
+        const double e = exp(lp);
+        cnt += kept ? 1.0 : 0.0;
+        sexp += kept ? e : 0.0;
+        if (kept && lp > best.v) { best.v = lp; best.i = T.index(r); }     // indices ascend per thread: first maximum
 #pragma unroll
         for (int d = 0; d < KT; ++d)
-            if (d < k) { const double v = samples[row * k + d]; s1[d] += v; frob = fma(v, v, frob); }
-    }
-    const double nk = block_sum(cnt, red);
-    const double sumexp = block_sum(sexp, red);
-    const double fro2 = block_sum(frob, red);
+            if (d < k) { const double v = kept ? th[d] : 0.0; s1[d] += v; frob = fma(v, v, frob); }
+    });
+    const double nk = T.sum(cnt);
+    const double sumexp = T.sum(sexp);
+    const double fro2 = T.sum(frob);
     double mu[KT];
 #pragma unroll
-    for (int d = 0; d < KT; ++d) mu[d] = block_sum(s1[d], red) / nk;                                   // IP.py:1923
-    best = block_best(best, red, redi);
+    for (int d = 0; d < KT; ++d) mu[d] = T.sum(s1[d]) / nk;                                            // IP.py:1923
+    best = T.best(best);
     const double evidence = (sumexp / nk) / sqrt(fro2);                                                // IP.py:1931
     const double logev = log(evidence);
     // ---- pass B2: sum (theta - mu)^2, log-ratio terms, rank of the MAP row among the kept rows ----
     double s2[KT], ratio = 0.0, before = 0.0;
 #pragma unroll
     for (int d = 0; d < KT; ++d) s2[d] = 0.0;
-    for (long long i = t; i < n; i += SS_THREADS) {
-        const long long row = R.at(s, i);
-        const double lp = logp[row];
-        if (dropped(lp)) continue;
-        if (i < best.i) before += 1.0;
+    for_rows_all<KT, U>(T, k, samples, logp, lprior, [&](long long r, double lp, double pr, const double (&th)[KT]) {
+        const bool kept = !(lp < cut);
+        before += (kept && T.index(r) < best.i) ? 1.0 : 0.0;
 #pragma unroll
         for (int d = 0; d < KT; ++d)
-            if (d < k) { const double dv = samples[row * k + d] - mu[d]; s2[d] = fma(dv, dv, s2[d]); }
+            if (d < k) { const double dv = kept ? th[d] - mu[d] : 0.0; s2[d] = fma(dv, dv, s2[d]); }
         if (lprior) {
-            double r = (lp - logev) - lprior[row];                                                     // IP.py:1799-1800
-            if (isinf(r) || r != r) r = 0.0;                                                           // IP.py:1801-1802
-            ratio += r;
+            double q = (lp - logev) - pr;                                                              // IP.py:1799-1800
+            if (!kept || isinf(q) || q != q) q = 0.0;                                                  // IP.py:1801-1802
+            ratio += q;
         }
-    }
-    const double nbefore = block_sum(before, red);
-    const double ig = block_sum(ratio, red) / nk;                                                      // IP.py:1803
+    });
+    const double nbefore = T.sum(before);
+    const double ig = T.sum(ratio) / nk;                                                               // IP.py:1803
     double sd[KT];
 #pragma unroll
-    for (int d = 0; d < KT; ++d) sd[d] = sqrt(block_sum(s2[d], red) / nk);                             // IP.py:1924
-    if (t == 0) {
-        double* o = out + s * PEUQSE_SCEN_STATS_DOUBLES;
-        o[PEUQSE_SCEN_STATS_N_TOTAL] = (double)n;
+    for (int d = 0; d < KT; ++d) sd[d] = sqrt(T.sum(s2[d]) / nk);                                      // IP.py:1924
+    if (T.writer()) {
+        double* o = out + T.s * PEUQSE_SCEN_STATS_DOUBLES(k);
+        o[PEUQSE_SCEN_STATS_N_TOTAL] = n;
         o[PEUQSE_SCEN_STATS_N_KEPT] = nk;
         o[PEUQSE_SCEN_STATS_THRESHOLD] = thr;
         o[PEUQSE_SCEN_STATS_MAP_LOGP] = best.v;
@@ -192,16 +311,13 @@ __global__ void __launch_bounds__(SS_THREADS) k_scen_stats(const double* __restr
         o[PEUQSE_SCEN_STATS_EVIDENCE] = evidence;
         o[PEUQSE_SCEN_STATS_INFO_GAIN_LOG_RATIO] = lprior ? ig : __longlong_as_double(0x7ff8000000000000LL);
         o[7] = 0.0;
-        const long long maprow = nk > 0.0 ? R.at(s, best.i) : 0;
-        for (int d = 0; d < 16; ++d) {
-            o[PEUQSE_SCEN_STATS_MU_AP + d] = 0.0; o[PEUQSE_SCEN_STATS_STDAP + d] = 0.0; o[PEUQSE_SCEN_STATS_MAP_THETA + d] = 0.0;
-        }
+        const long long maprow = nk > 0.0 ? T.mem_of_index(best.i) : 0;
 #pragma unroll
         for (int d = 0; d < KT; ++d)
             if (d < k) {
                 o[PEUQSE_SCEN_STATS_MU_AP + d] = mu[d];
-                o[PEUQSE_SCEN_STATS_STDAP + d] = sd[d];
-                o[PEUQSE_SCEN_STATS_MAP_THETA + d] = samples[maprow * k + d];
+                o[PEUQSE_SCEN_STATS_STDAP(k) + d] = sd[d];
+                o[PEUQSE_SCEN_STATS_MAP_THETA(k) + d] = samples[maprow * k + d];
             }
     }
 }
@@ -331,7 +447,11 @@ extern "C" int peuqse_scenarios_stats(int32_t k, int32_t filter, double coef, in
     ScenRows R;
     R.C = n_scenarios * chains_per_scenario; R.per = chains_per_scenario; R.rows = n_rows - first_row; R.first_row = first_row;
     cudaStream_t st = (cudaStream_t)stream;
-#define SSTAT(KT, ...) k_scen_stats<KT><<<(unsigned)n_scenarios, SS_THREADS, 0, st>>>(d_samples, d_logp, d_logprior, R, k, filter, coef, d_out)
+    const bool tiles = chains_per_scenario <= 32 && (chains_per_scenario & (chains_per_scenario - 1)) == 0;
+    const unsigned col_grid = (unsigned)((R.C + 31) / 32);
+#define SSTAT(KT, ...)                                                                                                              \
+    if (tiles) k_scen_stats<KT, ColumnTiles><<<col_grid, SS_THREADS, 0, st>>>(d_samples, d_logp, d_logprior, R, k, filter, coef, d_out); \
+    else k_scen_stats<KT, CtaPerScenario><<<(unsigned)n_scenarios, SS_THREADS, 0, st>>>(d_samples, d_logp, d_logprior, R, k, filter, coef, d_out)
     PQ_DISPATCH_K(pq_k_bucket(k), SSTAT, 0)
 #undef SSTAT
     PQ_CUDA_OK(cudaGetLastError());

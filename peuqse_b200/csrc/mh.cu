@@ -5,6 +5,7 @@
 // log_accept = (ll_p + lp_p) - (ll_c + lp_c) (2641), optional 1/N flattening (2644-2649),
 // accept iff log_accept > log(u) (2650-2652).  The reference re-simulates the current point each step
 // (2638-2639); re-evaluating an unchanged point reproduces the same doubles, so the cached value is used.
+#include <cstdlib>
 #include "common.cuh"
 #include "eval.cuh"
 #include "launch.cuh"
@@ -417,13 +418,23 @@ __global__ void __launch_bounds__(32 * MHW_WARPS, MINB) k_mh_warp(const __grid_c
 }
 
 namespace {
+// tuning override for the shape crossover (profiles/mh_variants.py): PEUQSE_MH_FEW_CHAINS=<n>
+long long mh_few_chains() {
+    static long long v = -1;
+    if (v < 0) {
+        const char* e = getenv("PEUQSE_MH_FEW_CHAINS");
+        v = e ? atoll(e) : MH_FEW_CHAINS;
+    }
+    return v;
+}
+
 template <int MODEL, int KT>
 int launch_mh(const peuqse_problem* p, const DevMH& M, const double* th0, const MHOut& out, cudaStream_t st,
               const DevScen& SC = pq_no_scen()) {
     int use_smem;
     const size_t smem = pq_pick_smem(p, &use_smem);
     // few chains with few observations: one warp per chain, thread-order evaluation (latency); many: one thread per chain
-    const bool few = M.n_chains <= MH_FEW_CHAINS;
+    const bool few = M.n_chains <= mh_few_chains();
     if (SC.y) {
         // scenario batch: thread-order evaluation in both shapes (n_total <= PQ_THREAD_SHAPE_MAX_N, checked by the caller)
         if (few) {

@@ -5,7 +5,7 @@ The reference loops `for modulation: for condition: populate independent variabl
 doMetropolisHastings -> info_gain`.  Here every (modulation, condition) pair is one SCENARIO of a single batch
 (csrc/doe.cu): the scenarios' model constants and synthetic observations live in HBM, one launch of the persistent MH
 kernel walks all scenarios' chains, one launch of the per-scenario statistics kernel returns every information gain, and
-the host reads back 56 doubles per scenario.  Scenarios are independent, so with several ranks each GPU takes a contiguous
+the host reads back 8 + 3k doubles per scenario.  Scenarios are independent, so with several ranks each GPU takes a contiguous
 range of them and the matrices are all-gathered (no data-path collective) -- the reference's 'parallel_conditions_exploration'
 / 'parallel_parameter_modulation' MPI modes with their pickle files (IP.py:1384-1397, 1530-1543) collapse into that.
 """
@@ -96,9 +96,9 @@ class ScenarioBatch:
         return out
 
     def statistics(self, run, burn_in, filter_mode=_lib.FILTER_NONE, coef=2.0):
-        """Per-scenario post-burn-in statistics + log-ratio information gain: host array [S, SCEN_STATS['DOUBLES']]."""
+        """Per-scenario post-burn-in statistics + log-ratio information gain: host array [S, 8 + 3k] (_lib.scen_stats_layout)."""
         R = run['samples'].shape[0]
-        out = torch.empty((self.S, _lib.SCEN_STATS['DOUBLES']), dtype=torch.float64, device=_dev())
+        out = torch.empty((self.S, _lib.scen_stats_layout(self.pe.k)['DOUBLES']), dtype=torch.float64, device=_dev())
         _lib.check(self._L.peuqse_scenarios_stats(self.pe.k, int(filter_mode), float(coef), self.S, run['chains_per_scenario'], R,
                                                   int(burn_in), _lib.ptr(run['samples']), _lib.ptr(run['logp']),
                                                   _lib.ptr(run['logprior']), _lib.ptr(out), _lib.current_stream()))
@@ -188,7 +188,7 @@ def run_info_gain_matrices(pe, modulations, searchType='doMetropolisHastings'):
                            modulate=float(pes['mcmc_modulate_accept_probability']))
         if not want_kl:
             stats_rows = batch.statistics(run, burn, mode, coef)
-            gains = stats_rows[:, _lib.SCEN_STATS['INFO_GAIN_LOG_RATIO']].copy()
+            gains = stats_rows[:, _lib.scen_stats_layout(pe.k)['INFO_GAIN_LOG_RATIO']].copy()
         else:
             # the KL form bins prior and posterior samples on scenario-specific joint edges: the streaming statistics
             # kernels (csrc/stats.cu) scenario by scenario, every array staying on the device

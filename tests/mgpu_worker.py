@@ -75,6 +75,26 @@ from peuqse_b200.mcmc import mh_launch, step_cholesky, chain_moments
 all_ = mh_launch(PE, np.tile([200., 500.], (64, 1)), 400, 100, 5, step_cholesky(PE.Q_covmat, 0.5))
 S = all_['samples'][100:].permute(1, 0, 2).reshape(-1, 2).cpu().numpy()
 assert PE.post_burn_in_samples.shape == S.shape and np.array_equal(PE.post_burn_in_samples, S)
+# 4. design of experiments: the 9 x 25 scenarios of the reference's Example13 unit test sharded over the ranks
+gd = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "doe.npz"))
+Ld, Bd, STEP, DH, DS, DHU, DSU, SIG = gd['settings']
+UI = PEUQSE.UserInput.fresh()
+UI.responses['responses_observed'] = [0.0, 0.0, 0.0]
+UI.responses['responses_observed_uncertainties'] = [SIG] * 3
+UI.model['InputParameterPriorValues'] = [DH, DS]
+UI.model['InputParametersPriorValuesUncertainties'] = [DHU, DSU]
+UI.model['simulateByInputParametersOnlyFunction'] = PEUQSE.LangmuirLogModel(400, 0.1)
+UI.parameter_estimation_settings.update({'mcmc_random_seed': 0, 'mcmc_burn_in': int(Bd), 'mcmc_length': int(Ld),
+                                         'mcmc_relative_step_length': float(STEP), 'mcmc_info_gain_returned': 'log_ratio',
+                                         'mcmc_threshold_filter_samples': False})
+UI.doe_settings.update({'info_gains_matrices_array_format': 'xyz', 'independent_variable_grid_center': [500, 0.5],
+                        'independent_variable_grid_interval_size': [100, 0.1], 'independent_variable_grid_num_intervals': [2, 2],
+                        'parameter_modulation_grid_interval_size': [1, 1], 'parameter_modulation_grid_num_intervals': [1, 1]})
+PE = PEUQSE.parameter_estimation(UI)
+A = PE.doeParameterModulationPermutationsScanner()
+ref = gd['scanner_xyz_info_gains_matrices_array']
+assert A.shape == ref.shape and np.array_equal(A[:, :, :2], ref[:, :, :2])
+np.testing.assert_allclose(A[:, :, 2], ref[:, :, 2], rtol=1e-9)
 dist.barrier()
 if rank == 0:
     print("MGPU_OK", world)

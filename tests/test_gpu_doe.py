@@ -122,13 +122,14 @@ def test_info_gain_matrix_vs_reference_fixture(env, golden, fmt, filtered):
     np.testing.assert_allclose(M[:, 2], Mo[:, 2], rtol=1e-9)
     S = PE.doe_scenario_statistics
     from peuqse_b200 import _lib
+    SS = _lib.scen_stats_layout(2)
     for s in range(25):
-        assert int(S[s, _lib.SCEN_STATS['N_KEPT']]) == st[s]['samples'].shape[0]
-        np.testing.assert_allclose(S[s, _lib.SCEN_STATS['MU_AP']:_lib.SCEN_STATS['MU_AP'] + 2], st[s]['mu_AP'], rtol=1e-11)
-        np.testing.assert_allclose(S[s, _lib.SCEN_STATS['STDAP']:_lib.SCEN_STATS['STDAP'] + 2], st[s]['stdap'], rtol=1e-9)
-        np.testing.assert_allclose(S[s, _lib.SCEN_STATS['MAP_LOGP']], st[s]['map_logP'], rtol=1e-12)
-        assert int(S[s, _lib.SCEN_STATS['MAP_INDEX']]) == st[s]['map_index']
-        np.testing.assert_allclose(S[s, _lib.SCEN_STATS['EVIDENCE']], st[s]['evidence'], rtol=1e-11)
+        assert int(S[s, SS['N_KEPT']]) == st[s]['samples'].shape[0]
+        np.testing.assert_allclose(S[s, SS['MU_AP']:SS['MU_AP'] + 2], st[s]['mu_AP'], rtol=1e-11)
+        np.testing.assert_allclose(S[s, SS['STDAP']:SS['STDAP'] + 2], st[s]['stdap'], rtol=1e-9)
+        np.testing.assert_allclose(S[s, SS['MAP_LOGP']], st[s]['map_logP'], rtol=1e-12)
+        assert int(S[s, SS['MAP_INDEX']]) == st[s]['map_index']
+        np.testing.assert_allclose(S[s, SS['EVIDENCE']], st[s]['evidence'], rtol=1e-11)
 
 
 @pytest.mark.parametrize("fmt", ["xyz", "meshgrid"])
@@ -177,8 +178,8 @@ def test_scenario_chains_equal_single_problem_chains(env):
     from peuqse_b200.doe import ScenarioBatch
     from peuqse_b200.mcmc import mh_launch, step_cholesky
     rng = np.random.default_rng(11)
-    L, burn, cps = 120, 20, 4
-    for S in (2200, 37):
+    L, burn = 120, 20
+    for S, cps in ((2200, 4), (37, 3), (40, 1)):          # cps = 3: one CTA per scenario; powers of two: column tiles
         PE = make_pe(PEUQSE, PEUQSE.QuadraticModel(X00), Y00, S00, [200, 500], [100, 200], settings={'mcmc_length': L})
         conds = np.array(X00, dtype=float) + 50.0 * rng.standard_normal((S, 3))
         truth = np.array([200., 500.]) + np.array([100., 200.]) * rng.standard_normal((S, 2))
@@ -201,7 +202,7 @@ def test_scenario_chains_equal_single_problem_chains(env):
             pr = one['logprior'][burn:].permute(1, 0).reshape(-1).cpu().numpy()
             st = orc.post_burn_in_statistics_filtered(smp, lp, pr, filter_samples=False)
             from peuqse_b200 import _lib
-            SS = _lib.SCEN_STATS
+            SS = _lib.scen_stats_layout(2)
             np.testing.assert_allclose(stats[s, SS['MU_AP']:SS['MU_AP'] + 2], st['mu_AP'], rtol=1e-12)
             np.testing.assert_allclose(stats[s, SS['STDAP']:SS['STDAP'] + 2], st['stdap'], rtol=1e-10)
             assert int(stats[s, SS['MAP_INDEX']]) == st['map_index'] and stats[s, SS['MAP_LOGP']] == st['map_logP']
