@@ -53,7 +53,7 @@ parameter_estimation_settings = {
     'scaling_uncertainties_type': "std",
     'undo_scaling_uncertainties_type': False,
     'convergence_diagnostics': False,
-    'mcmc_exportLog': False,
+    'mcmc_exportLog': True,            # as the reference (UserInput.py:62): sampler results are written to logs_and_csvs/ and pickles/
     'mcmc_random_seed': None,
     'mcmc_mode': 'unbiased',
     'mcmc_length': 10000,
@@ -92,6 +92,7 @@ parameter_estimation_settings = {
     'multistart_keep_cumulative_post_burn_in_data': False,
     'multistart_exportLog': False,
     # ---- additions of this engine (absent keys in a reference UserInput mean the defaults below)
+    'export_max_rows': 1_000_000,      # sample / point arrays with more rows than this are not written to file
     'mcmc_nchains': 1,                 # independent MH chains advanced by one kernel (reference: one per MPI rank)
     'mcmc_store_samples': 'auto',      # 'auto': keep every row while it fits comfortably in device memory
     'mcmc_thin': 1,

@@ -345,7 +345,13 @@ class parameter_estimation:
             self.evidence = res.evidence
             self.info_gain = None      # the reference's log-ratio branch has no priors vector here
             self.marginal_histograms = (res.histogram_counts, res.histogram_edges)
-        return [self.map_parameter_set, None, None, None, None, None, None]                            # IP.py:862, 1074
+        best = [self.map_parameter_set, None, None, None, None, None, None]                            # IP.py:862, 1074
+        if bool(self.UserInput.parameter_estimation_settings.get('exportLog', True)) and res.map_index >= 0:
+            from .export import exportMultistart                                                       # IP.py:1037-1072
+            stats = bool(getattr(res, 'statistics', False))
+            exportMultistart(self, centerPoint, [self.map_parameter_set, getattr(self, 'mu_AP_parameter_set', None) if stats else None,
+                                                 getattr(self, 'stdap_parameter_set', None) if stats else None], stats)
+        return best
 
     def doGridSearch(self, searchType='getLogP', gridSamplingAbsoluteIntervalSize=[], gridSamplingNumOfIntervals=[], **kw):
         """Deprecated alias kept by the reference (IP.py:1120-1128)."""
@@ -476,7 +482,7 @@ class parameter_estimation:
     # ------------------------------------------------------------------------------------------
     def doMetropolisHastings(self, calculatePostBurnInStatistics=True, mcmc_exportLog='UserChoice', continueSampling='auto'):
         from .mcmc import run_metropolis_hastings
-        return run_metropolis_hastings(self, calculatePostBurnInStatistics, continueSampling)
+        return run_metropolis_hastings(self, calculatePostBurnInStatistics, continueSampling, mcmc_exportLog)
 
     def doEnsembleSliceSampling(self, mcmc_nwalkers_direct_input=None, walkerInitialDistribution='UserChoice',
                                 walkerInitialDistributionSpread='UserChoice', movesType='UserChoice',
@@ -484,7 +490,7 @@ class parameter_estimation:
         from .mcmc import run_ensemble_slice_sampling
         return run_ensemble_slice_sampling(self, mcmc_nwalkers_direct_input, walkerInitialDistribution,
                                            walkerInitialDistributionSpread, movesType, calculatePostBurnInStatistics,
-                                           continueSampling)
+                                           continueSampling, mcmc_exportLog)
 
     def calculatePostBurnInStatistics(self, calculate_post_burn_in_log_priors_vec=False):
         from .mcmc import post_burn_in_statistics
@@ -500,6 +506,21 @@ class parameter_estimation:
     def doeParameterModulationPermutationsScanner(self, searchType='doMetropolisHastings'):       # IP.py:1499
         from .doe import doe_parameter_modulation_scanner
         return doe_parameter_modulation_scanner(self, searchType)
+
+    # ------------------------------------------------------------------------------------------
+    # on-disk formats
+    # ------------------------------------------------------------------------------------------
+    def exportPostBurnInStatistics(self):                                                          # IP.py:1956
+        from .export import exportPostBurnInStatistics
+        return exportPostBurnInStatistics(self)
+
+    def exportResponses(self, choiceOrResponsesData='', filenameString='', consolidated='auto'):  # IP.py:2044
+        from .export import exportResponses
+        return exportResponses(self, choiceOrResponsesData, filenameString, consolidated)
+
+    def reload_samples(self, sampling_type='', filepath=''):                                       # IP.py:441
+        from .export import reload_samples
+        return reload_samples(self, sampling_type, filepath)
 
     # out of scope ------------------------------------------------------------------------------
     def _out_of_scope(self, *a, **k):

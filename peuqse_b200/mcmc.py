@@ -88,7 +88,7 @@ def chain_moments(stats, theta0, k, n_rows):
                 map_chain=i, accept_rate=st[:, lay['NACC']], sumexp=float(st[:, lay['SUMEXP']].sum()))
 
 
-def run_metropolis_hastings(pe, calculatePostBurnInStatistics=True, continueSampling='auto'):
+def run_metropolis_hastings(pe, calculatePostBurnInStatistics=True, continueSampling='auto', mcmc_exportLog='UserChoice'):
     UI = pe.UserInput
     pes = UI.parameter_estimation_settings
     if hasattr(UI, 'last_MCMC_run_type') and UI.last_MCMC_run_type != 'MH':                       # IP.py:2565-2569
@@ -171,6 +171,7 @@ def run_metropolis_hastings(pe, calculatePostBurnInStatistics=True, continueSamp
         pe._dev_post = None                                                  # merged on the host: statistics upload them
     if calculatePostBurnInStatistics:
         post_burn_in_statistics(pe, calculate_post_burn_in_log_priors_vec=bool(continueSampling))
+        _export_if_requested(pe, mcmc_exportLog)                                                      # IP.py:2743-2746
         return [pe.map_parameter_set, pe.mu_AP_parameter_set, pe.stdap_parameter_set, pe.evidence, pe.info_gain,
                 pe.post_burn_in_samples, pe.post_burn_in_log_posteriors_un_normed_vec]               # IP.py:2749
     lp = pe.post_burn_in_log_posteriors_un_normed_vec
@@ -178,6 +179,14 @@ def run_metropolis_hastings(pe, calculatePostBurnInStatistics=True, continueSamp
     pe.map_index = list(lp).index(pe.map_logP)
     pe.map_parameter_set = pe.post_burn_in_samples[pe.map_index]
     return pe.map_logP
+
+
+def _export_if_requested(pe, mcmc_exportLog):
+    if str(mcmc_exportLog) == 'UserChoice':
+        mcmc_exportLog = bool(pe.UserInput.parameter_estimation_settings['mcmc_exportLog'])
+    if mcmc_exportLog == True:                                                                        # noqa: E712
+        from .export import exportPostBurnInStatistics
+        exportPostBurnInStatistics(pe)
 
 
 def post_burn_in_statistics(pe, calculate_post_burn_in_log_priors_vec=False):
@@ -357,7 +366,7 @@ def ess_batched(pe, start, n_iters, seed, mu0=1.0, tune=True, max_rounds=10000, 
 
 def run_ensemble_slice_sampling(pe, mcmc_nwalkers_direct_input=None, walkerInitialDistribution='UserChoice',
                                 walkerInitialDistributionSpread='UserChoice', movesType='UserChoice',
-                                calculatePostBurnInStatistics=True, continueSampling='auto'):
+                                calculatePostBurnInStatistics=True, continueSampling='auto', mcmc_exportLog='UserChoice'):
     UI = pe.UserInput
     pes = UI.parameter_estimation_settings
     if walkerInitialDistribution == 'UserChoice': walkerInitialDistribution = pes['mcmc_walkerInitialDistribution']
@@ -430,6 +439,7 @@ def run_ensemble_slice_sampling(pe, mcmc_nwalkers_direct_input=None, walkerIniti
                                                                   pe.post_burn_in_log_posteriors_un_normed_vec))
     if calculatePostBurnInStatistics:
         post_burn_in_statistics(pe, calculate_post_burn_in_log_priors_vec=True)                       # IP.py:2533
+        _export_if_requested(pe, mcmc_exportLog)                                                      # IP.py:2536-2539
         return [pe.map_parameter_set, pe.mu_AP_parameter_set, pe.stdap_parameter_set, pe.evidence, pe.info_gain,
                 pe.post_burn_in_samples, pe.post_burn_in_log_posteriors_un_normed_vec]
     lp = pe.post_burn_in_log_posteriors_un_normed_vec

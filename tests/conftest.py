@@ -20,3 +20,9 @@ def golden():
     def load(name):
         return np.load(os.path.join(gdir, name + ".npz"))
     return load
+
+
+@pytest.fixture(autouse=True)
+def _scratch_cwd(tmp_path, monkeypatch):
+    """Samplers and multistarts write logs_and_csvs/ and pickles/ like the reference: keep them out of the repository."""
+    monkeypatch.chdir(tmp_path)

@@ -879,3 +879,55 @@ def test_device_statistics_full_size_properties(env):
     np.testing.assert_allclose(R2.info_gain_log_ratio, R.info_gain_log_ratio, rtol=1e-11)
     np.testing.assert_allclose(R.mu_AP_parameter_set, ks.mean(dim=0).cpu().numpy(), rtol=1e-9, atol=1e-12)
     np.testing.assert_allclose(R.stdap_parameter_set, ks.std(dim=0, unbiased=False).cpu().numpy(), rtol=1e-10)
+
+
+def test_on_disk_formats_round_trip(env, golden):
+    """the samplers / multistart write the reference's files (byte-level format pinned on the CPU in
+    tests/test_host_cpu.py); here the files of real device runs are read back by reload_samples and by the reference's
+    own readers (np.genfromtxt / pickle)."""
+    import os
+    import pickle
+    PEUQSE, orc, _, _ = env
+    PE = make_pe(PEUQSE, PEUQSE.QuadraticModel(X00), Y00, S00, [200, 500], [100, 200],
+                 settings={'mcmc_length': 800, 'mcmc_burn_in': 100, 'mcmc_relative_step_length': 0.1, 'mcmc_random_seed': 0,
+                           'mcmc_info_gain_returned': 'log_ratio', 'responses_abscissa': X00})
+    PE.UserInput.model['exportResponses'] = True
+    res = PE.doMetropolisHastings()
+    files = set(os.listdir('logs_and_csvs')) | set(os.listdir('pickles'))
+    for f in ('mcmc_logP_and_parameter_samples.csv', 'mcmc_log_file.txt', 'mcmc_burn_in_logP_and_parameter_samples.csv',
+              'mcmc_post_burn_in_statistics.pkl', 'mcmc_map_logP.pkl', 'mcmc_map_parameter_set.pkl', 'mcmc_initial_point_parameters.pkl',
+              'mcmc_last_point_sampled.pkl', 'mcmc_logP_and_parameter_samples.pkl', 'ExportedResponsesData__map__ResponsesConsolidated.csv',
+              'ExportedResponsesData__muap__ResponsesConsolidated.csv', 'ExportedResponsesData__prior__ResponsesConsolidated.csv'):
+        assert f in files, f
+    arr = np.genfromtxt('logs_and_csvs/mcmc_logP_and_parameter_samples.csv', delimiter=",")
+    assert np.array_equal(arr[:, 1:], PE.post_burn_in_samples) and np.array_equal(arr[:, 0:1], PE.post_burn_in_log_posteriors_un_normed_vec)
+    st = pickle.load(open('pickles/mcmc_post_burn_in_statistics.pkl', 'rb'))
+    assert np.array_equal(st[0], res[0]) and np.array_equal(st[5], res[5]) and st[4] == res[4]
+    sim = np.genfromtxt('logs_and_csvs/ExportedResponsesData__map__ResponsesConsolidated.csv', delimiter=",", skip_header=1)
+    assert np.array_equal(sim[:, 0], X00) and np.array_equal(sim[:, 1], (np.array(X00) - res[0][0]) ** 2 + res[0][1])
+    # a fresh object rebuilds the statistics from the files (the filter already ran: the kept rows are what was written)
+    PE2 = make_pe(PEUQSE, PEUQSE.QuadraticModel(X00), Y00, S00, [200, 500], [100, 200],
+                  settings={'mcmc_length': 800, 'mcmc_threshold_filter_samples': False, 'mcmc_info_gain_returned': 'log_ratio'})
+    r2 = PE2.reload_samples('mcmc')
+    assert np.array_equal(r2[0], res[0]) and np.array_equal(PE2.post_burn_in_samples, PE.post_burn_in_samples)
+    np.testing.assert_allclose(r2[1], res[1], rtol=1e-13)
+    np.testing.assert_allclose(r2[2], res[2], rtol=1e-12)
+    np.testing.assert_allclose(r2[4], res[4], rtol=1e-12)
+    # multistart: the reference's stored grid (10 201 points)
+    g = golden("example00")
+    PE = make_pe(PEUQSE, PEUQSE.QuadraticModel(X00), Y00, S00, [200, 500], [100, 200],
+                 settings={'multistart_initialPointsDistributionType': 'grid', 'multistart_gridsearchSamplingInterval': [5, 5],
+                           'multistart_gridsearchSamplingRadii': [50, 50], 'responses_abscissa': X00})
+    PE.doMultiStart()
+    arr = np.genfromtxt('logs_and_csvs/multistart_MAP_logP_and_parameters_values.csv', delimiter=",")
+    assert arr.shape == (10201, 3) and np.array_equal(arr, PE.permutations_MAP_logP_and_parameters_values)
+    assert np.array_equal(pickle.load(open('pickles/multistart_MAP_logP_and_parameters_values.pkl', 'rb')), arr)
+    pts = np.genfromtxt('logs_and_csvs/multistart_initial_points_parameters_values.csv', delimiter=",")
+    assert np.array_equal(pts, arr[:, 1:])
+    log = open('logs_and_csvs/multistart_log_file.txt').read()
+    assert "highest_MAP_initial_point_index: 13" in log and "highest_MAP_logP: [-42.63739101]" in log
+    PE3 = make_pe(PEUQSE, PEUQSE.QuadraticModel(X00), Y00, S00, [200, 500], [100, 200], settings={'mcmc_info_gain_returned': 'log_ratio'})
+    r3 = PE3.reload_samples('multistart')
+    assert PE3.post_burn_in_samples.shape[0] == int(g['ex00_grid_nrows_expanded'])
+    np.testing.assert_allclose(r3[1], g['ex00_grid_mu_AP'], rtol=1e-12)
+    np.testing.assert_allclose(r3[2], g['ex00_grid_stdap'], rtol=1e-10)

@@ -208,3 +208,84 @@ def test_two_rank_gloo_reductions_match_single_process(tmp_path, golden):
     np.testing.assert_allclose(res['mu'], g['ex00_grid_mu_AP'], rtol=1e-12)
     assert int(res['cnt'][0]) == int((g['ex00_grid_multiplicity'] > 0).sum())
     assert int(res['nrows']) == 3 + 4
+
+
+def _export_stub(golden):
+    """An object carrying exactly the state the exporters read, filled from the reference run stored in the fixture."""
+    import types
+    from peuqse_b200 import UserInput as UIM
+    g = golden("export_formats")
+    UI = UIM.fresh()
+    UI.responses['responses_abscissa'] = [600, 1100, 1400]
+    UI.std_prior = np.array([100., 200.])
+    UI.mu_prior = np.array([200., 500.])
+    UI.model['exportResponses'] = False
+    pe = types.SimpleNamespace(UserInput=UI)
+    return g, UI, pe
+
+
+def test_export_post_burn_in_statistics_matches_reference_files(golden, tmp_path):
+    """exportPostBurnInStatistics (IP.py:1956-2001): text and CSV files byte for byte, pickles object for object, against
+    the files the unmodified reference wrote from the same state (tests/golden/make_golden_export.py)."""
+    import pickle
+    from peuqse_b200 import export as EX
+    g, UI, pe = _export_stub(golden)
+    for name in ('post_burn_in_samples', 'post_burn_in_log_posteriors_un_normed_vec', 'during_burn_in_samples',
+                 'during_burn_in_log_posteriors_un_normed_vec', 'map_logP', 'map_parameter_set', 'mu_AP_parameter_set',
+                 'stdap_parameter_set', 'mcmc_last_point_sampled'):
+        setattr(pe, name, g['mh_state__' + name])
+    pe.map_index = int(g['mh_state__map_index'])
+    pe.info_gain = float(g['mh_state__info_gain'])
+    pe.evidence = np.float64(g['mh_state__evidence'])
+    UI.InputParameterInitialGuess = g['mh_state__initial_guess']
+    EX.exportPostBurnInStatistics(pe)
+    keys = [k for k in g.files if k.startswith('mh__')]
+    assert len(keys) == 10
+    for key in keys:
+        _, sub, fname = key.split('__', 2)
+        got = open(os.path.join(sub, fname), 'rb').read()
+        ref = bytes(g[key])
+        if fname.endswith('.pkl'):
+            a, b = pickle.loads(got), pickle.loads(ref)
+            if isinstance(b, list):
+                assert len(a) == len(b)
+                for x, y in zip(a, b):
+                    assert np.array_equal(np.asarray(x), np.asarray(y))
+            else:
+                assert np.array_equal(np.asarray(a), np.asarray(b))
+        else:
+            assert got == ref, fname
+    assert sorted(os.listdir('pickles')) == sorted(k.split('__', 2)[2] for k in keys if '__pickles__' in k)
+    # round trip through reload_samples' reader
+    arr = np.genfromtxt(os.path.join('logs_and_csvs', 'mcmc_logP_and_parameter_samples.csv'), delimiter=",")
+    assert np.array_equal(arr[:, 1:], pe.post_burn_in_samples) and np.array_equal(arr[:, 0:1], pe.post_burn_in_log_posteriors_un_normed_vec)
+    assert np.array_equal(EX.unpickleAnObject('pickles/mcmc_last_point_sampled'), pe.mcmc_last_point_sampled)
+
+
+def test_export_multistart_matches_reference_files(golden, tmp_path):
+    import pickle
+    import types
+    from peuqse_b200 import export as EX
+    g, UI, pe = _export_stub(golden)
+    pe.sweep_result = types.SimpleNamespace(total=25)
+    pe.map_logP = float(g['ms_state__map_logP'][0])
+    pe.map_index = 1
+    pe.map_parameter_set = g['ms_state__map_parameter_set']
+    pe.listOfPermutations = g['ms_state__list']
+    pe._perm_array = pe.permutations_MAP_logP_and_parameters_values = g['ms_state__perm_array']
+    pe.getSimulatedResponses = lambda th: g['ms_state__map_sim']
+    EX.exportMultistart(pe, np.array([200., 500.]), [pe.map_parameter_set, None, None], False)
+    keys = [k for k in g.files if k.startswith('ms__')]
+    assert len(keys) == 5
+    for key in keys:
+        _, sub, fname = key.split('__', 2)
+        got = open(os.path.join(sub, fname), 'rb').read()
+        if fname.endswith('.pkl'):
+            assert np.array_equal(pickle.loads(got), pickle.loads(bytes(g[key])))
+        else:
+            assert got == bytes(g[key]), fname
+    # with the weighted statistics of a permutationsToSamples run the two extra lines of IP.py:1050-1051 follow
+    EX.exportMultistart(pe, np.array([200., 500.]), [pe.map_parameter_set, g['ms_state__mu_AP'], g['ms_state__stdap']], True)
+    txt = open('logs_and_csvs/multistart_log_file.txt').read()
+    assert txt.startswith(bytes(g['ms__logs_and_csvs__multistart_log_file.txt']).decode())
+    assert "self.mu_AP_parameter_set : " + str(g['ms_state__mu_AP']) in txt and "self.stdap_parameter_set : " in txt
