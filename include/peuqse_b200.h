@@ -446,6 +446,20 @@ int peuqse_scenarios_stats(int32_t k, int32_t filter, double coef, int64_t n_sce
                            int64_t n_rows, int64_t first_row, const double* d_samples, const double* d_logp,
                            const double* d_logprior, double* d_out, void* stream);
 
+/*
+ * Geweke convergence diagnostic of many chains at once.  replaces: geweke_diagnostic (IP.py:4012-4062) called per window,
+ * chain and parameter by calculateAndPlotConvergenceDiagnostics (IP.py:3960-3975).
+ * d_samples[n_rows][n_cols]: discrete_chains_post_burn_in_samples (nsteps, nchains, k) viewed with n_cols = nchains*k.
+ * positions[n_positions]: strictly increasing row numbers in [0, n_rows] at which prefix sums are recorded (host and
+ * device copies).  d_slices[n_z][2][6]: for z-score i the first and the last slice [a, b) of IP.py:4053-4054, each as the
+ * indices INTO positions[] of the rows a, a+1, a+2, b-2, b-1, b.  d_z[n_z][n_cols].  The spectral variance is
+ * statsmodels' yule_walker(order 2, method 'adjusted', demeaned): sigma^2 / (1 - sum(beta))^2, NaN unless sigma^2 > 0.
+ */
+int64_t peuqse_geweke_work_bytes(int64_t n_rows, int64_t n_cols, int32_t n_positions);
+int peuqse_geweke(const double* d_samples, int64_t n_rows, int64_t n_cols, const int64_t* h_positions,
+                  const int64_t* d_positions, int32_t n_positions, const int32_t* d_slices, int32_t n_z, double* d_z,
+                  void* d_work, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

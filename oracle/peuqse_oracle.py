@@ -770,6 +770,72 @@ def doe_info_gain_matrix(build_problem_for, simulate_for, conditions, theta_true
 
 
 # --------------------------------------------------------------------------------------------
+# Convergence diagnostics: Geweke z-scores (IP.py:3960-3975, 4012-4062)
+# --------------------------------------------------------------------------------------------
+def yule_walker(x, order=2):
+    """statsmodels.regression.linear_model.yule_walker(x, order, method='adjusted', demean=True) -- a third-party
+    dependency (statsmodels, unpinned in the reference's setup.py extras, imported at IP.py:4044) that is not installed
+    here: restated from its published algorithm (parity unpinned at this one call): demean, r_0 = sum x^2 / n,
+    r_k = sum x_t x_{t+k} / (n - k), solve the order x order Toeplitz system, sigma^2 = r_0 - r_{1..}.rho."""
+    x = np.array(x, dtype=np.float64)
+    x -= x.mean()
+    n = x.shape[0]
+    r = np.zeros(order + 1, np.float64)
+    r[0] = (x ** 2).sum() / n
+    for k in range(1, order + 1):
+        r[k] = (x[0:-k] * x[k:]).sum() / (n - k)
+    R = scipy.linalg.toeplitz(r[:-1])
+    rho = np.linalg.solve(R, r[1:])
+    sigmasq = r[0] - (r[1:] * rho).sum()
+    sigma = np.sqrt(sigmasq) if sigmasq > 0 else np.nan
+    return rho, sigma
+
+
+def geweke_slices(n, initial_window=0.1, comparison_window=0.5, intervals=20):
+    """The (start, first slice, last slice) index triples of geweke_diagnostic for a chain of n rows (IP.py:4030-4052)."""
+    last_index = n - 1
+    last_start_index = (1 - comparison_window) * last_index
+    out = []
+    for start in np.linspace(0, last_start_index, num=intervals, endpoint=True, dtype=int):
+        out.append((int(start), (int(start), int(start) + int(initial_window * (last_index - start))),
+                    (int(last_index - comparison_window * (last_index - start)), n)))
+    return out
+
+
+def geweke_diagnostic(x, initial_window=0.1, comparison_window=0.5, intervals=20):
+    """geweke_diagnostic (IP.py:4012-4062): [(start, z)] with z = (mean_first - mean_last) / sqrt(sv_first/n_first + sv_last/n_last),
+    sv = sigma^2 / (1 - sum(beta))^2 of an order-2 Yule-Walker fit (the spectral density at frequency zero)."""
+    x = np.asarray(x, dtype=float)
+    rows = []
+    for start, (a1, b1), (a2, b2) in geweke_slices(len(x), initial_window, comparison_window, intervals):
+        first, last = x[a1:b1], x[a2:b2]
+
+        def spec_var(v):
+            beta, sigma = yule_walker(v, 2)
+            return sigma ** 2 / (1. - np.sum(beta)) ** 2
+        z = first.mean() - last.mean()
+        z /= np.sqrt(spec_var(first) / len(first) + spec_var(last) / len(last))
+        rows.append([start, z])
+    return np.array(rows)
+
+
+def geweke_convergence(chains):
+    """The Geweke half of calculateAndPlotConvergenceDiagnostics (IP.py:3960-4005) for chains[R, C, k]: z[k, C, 20, 20] over
+    the 20 growing windows, and the reference's combined outputs (window indices, final combined values, percent outliers)."""
+    R, C, k = chains.shape
+    windows = np.linspace(0, R, 21).astype(int)[1:]
+    z = np.empty((k, C, len(windows), 20))
+    for d in range(k):
+        for c in range(C):
+            for w, n in enumerate(windows):
+                z[d, c, w] = geweke_diagnostic(chains[:n, c, d])[:, 1]
+    comb = np.mean(np.mean(np.abs(z), axis=0), axis=0)                    # over parameters, then chains
+    final = comb[:, -1]
+    outlier = np.count_nonzero(comb > 1, axis=1) / comb.shape[1]
+    return dict(z=z, window_indices=windows, final_combined_parameter_values=final, final_combined_parameter_percent_outlier=outlier)
+
+
+# --------------------------------------------------------------------------------------------
 # Ensemble slice sampling -- published algorithm (parity unpinned, see module header)
 # --------------------------------------------------------------------------------------------
 def ess_run(logp_batch: Callable, start, nsteps, rng: np.random.Generator, mu0=1.0, maxiter=10000,

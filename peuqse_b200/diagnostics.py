@@ -1,0 +1,113 @@
+"""Convergence diagnostics on device-resident chains: the Geweke half of
+getConvergenceDiagnostics / calculateAndPlotConvergenceDiagnostics (PEUQSE/InverseProblem.py:2121-2161, 3960-4005, "IP.py")
+with geweke_diagnostic (IP.py:4012-4062), for thousands of chains at once (csrc/diag.cu).
+
+The integrated autocorrelation time (IP.py:3916-3948) is zeus.autocorr.AutoCorrTime, a third-party routine that is neither
+vendored by the reference nor installed here; it is not restated (its entries of PE_object.convergence are None).
+The spectral variance inside the Geweke score is statsmodels' yule_walker (order 2, 'adjusted', demeaned), restated from
+its published algorithm (oracle/peuqse_oracle.py:yule_walker): parity pinned for everything but that one call.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def geweke_slices(n, initial_window=0.1, comparison_window=0.5, intervals=20):
+    """[(start, (a1, b1), (a2, b2))] exactly as geweke_diagnostic forms them (IP.py:4030-4054)."""
+    for interval in (initial_window, comparison_window):
+        if interval <= 0 or interval >= 1:
+            raise ValueError("Invalid intervals for Geweke convergence analysis:", (initial_window, comparison_window), "Must be between 0 and 1")
+    if initial_window + comparison_window >= 1:
+        raise ValueError("Invalid intervals for Geweke convergence analysis:", (initial_window, comparison_window),
+                         "first and last intervals should not overlap.")
+    last_index = n - 1
+    last_start_index = (1 - comparison_window) * last_index
+    out = []
+    for start in np.linspace(0, last_start_index, num=intervals, endpoint=True, dtype=int):
+        out.append((int(start), (int(start), int(start) + int(initial_window * (last_index - start))),
+                    (int(last_index - comparison_window * (last_index - start)), n)))
+    return out
+
+
+_TABLES = {}
+
+
+def _slice_tables(R, windows, initial_window, comparison_window, intervals):
+    """Rows at which prefix sums are needed and, per z-score, the indices of its two slices' six rows (cached per shape)."""
+    key = (int(R), tuple(int(w) for w in windows), initial_window, comparison_window, intervals)
+    if key in _TABLES:
+        return _TABLES[key]
+    slices, starts = [], None
+    for n in windows:
+        sl = geweke_slices(int(n), initial_window, comparison_window, intervals)
+        slices.append(sl)
+        starts = np.array([s[0] for s in sl])
+    need = set()
+    for sl in slices:
+        for _, s1, s2 in sl:
+            for a, b in (s1, s2):
+                b = max(b, a)
+                need.update(min(max(p, a), b) for p in (a, a + 1, a + 2, b - 2, b - 1, b))
+    pos = np.array(sorted(need), dtype=np.int64)
+    index = {int(p): i for i, p in enumerate(pos)}
+    table = np.empty((len(windows), intervals, 2, 6), dtype=np.int32)
+    for w, sl in enumerate(slices):
+        for i, (_, s1, s2) in enumerate(sl):
+            for h, (a, b) in enumerate((s1, s2)):
+                b = max(b, a)
+                table[w, i, h] = [index[min(max(p, a), b)] for p in (a, a + 1, a + 2, b - 2, b - 1, b)]
+    _TABLES[key] = (pos, table, starts)
+    return _TABLES[key]
+
+
+def geweke_z_scores(chains, windows=None, initial_window=0.1, comparison_window=0.5, intervals=20):
+    """chains[R, C, k] (CUDA float64 tensor or array) -> (z[k, C, W, intervals] CUDA tensor, windows, start indices of the
+    last window).  windows default to the reference's 20 growing windows np.linspace(0, R, 21).astype(int)[1:]."""
+    L = _lib.load()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    x = chains if torch.is_tensor(chains) else torch.as_tensor(np.ascontiguousarray(np.asarray(chains, dtype=float)))
+    x = x.to(dev, dtype=torch.float64).contiguous()
+    R, C, k = x.shape
+    if windows is None:
+        windows = np.linspace(0, R, 21).astype(int)[1:]                              # IP.py:3963
+    windows = np.asarray(windows, dtype=np.int64)
+    pos, table, starts = _slice_tables(R, windows, initial_window, comparison_window, intervals)
+    nz = len(windows) * intervals
+    d_pos = torch.as_tensor(pos).to(dev)
+    d_tab = torch.as_tensor(table.reshape(-1)).to(dev)
+    z = torch.empty((nz, C * k), dtype=torch.float64, device=dev)
+    work = torch.empty(int(L.peuqse_geweke_work_bytes(R, C * k, len(pos))), dtype=torch.uint8, device=dev)
+    _lib.check(L.peuqse_geweke(_lib.ptr(x), R, C * k, pos.ctypes.data_as(_lib.C.c_void_p), _lib.ptr(d_pos), len(pos), _lib.ptr(d_tab), nz,
+                               _lib.ptr(z), _lib.ptr(work), _lib.current_stream()))
+    return z.reshape(len(windows), intervals, C, k).permute(3, 2, 0, 1), windows, starts
+
+
+def convergence_diagnostics(pe, discrete_chains_post_burn_in_samples=None):
+    """getConvergenceDiagnostics (IP.py:2121-2161): fills PE_object.convergence; returns the reference's output tuple."""
+    x = discrete_chains_post_burn_in_samples
+    if x is None or (not torch.is_tensor(x) and len(x) == 0):
+        out = getattr(pe, '_mh_out', None)
+        if out is not None and out.get('samples') is not None and hasattr(pe, '_mh_burn_rows'):
+            x = out['samples'][pe._mh_burn_rows:]                                  # still on the device
+        else:
+            x = pe.discrete_chains_post_burn_in_samples
+    if not torch.is_tensor(x) and type(x).__module__ != np.__name__:
+        print('The input array needs to a numpy array. If a list was inputted, wrap the variable in np.array(var)'); raise SystemExit
+    if len(x.shape) != 3:
+        print('The input array needs to take the shape (numSamples, numChains, numParameters). The current inputs does not have the appropriate dimensions.')
+        raise SystemExit
+    z, windows, starts = geweke_z_scores(x)
+    pe.gpu_launches += 3
+    a = z.abs()
+    comb = a.mean(dim=0).mean(dim=0)                                                # over parameters, then chains (IP.py:3993-3996)
+    final = comb[:, -1].cpu().numpy()                                               # IP.py:3998
+    nan_safe = torch.where(torch.isnan(comb), torch.zeros_like(comb), comb)
+    outlier = ((nan_safe > 1).sum(dim=1).double() / comb.shape[1]).cpu().numpy()    # IP.py:4000
+    per_param = a.mean(dim=1)                                                       # [k, W, I]: the per-parameter plots' data
+    pe.convergence = {'AutoCorrTime': {'window_indices': None, 'final_parameter_values': None, 'parameter_act_for_each_window': None},
+                      'Geweke': {'window_indices': windows, 'final_combined_parameter_values': final,
+                                 'final_combined_parameter_percent_outlier': outlier,
+                                 'interval_start_indices': starts, 'z_scores_each_parameter': per_param.cpu().numpy()}}
+    pe.geweke_z_scores = z
+    return (None, None, None, windows, final, outlier)

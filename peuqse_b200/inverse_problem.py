@@ -8,6 +8,7 @@ doeParameterModulationPermutationsScanner (1499).  Everything outside that path 
 is out of scope and raises NotImplementedError.
 """
 import ctypes as C
+import os
 import sys
 
 import numpy as np
@@ -51,7 +52,7 @@ class parameter_estimation:
             for i in range(len(UI.model['InputParameterPriorValues'])):
                 UI.model['parameterNamesAndMathTypeExpressionsDict'][str(i)] = 'ParInd_' + str(i)
         UI.parameterNamesList = list(UI.model['parameterNamesAndMathTypeExpressionsDict'])
-        UI.user_requested_convergence_diagnostics = False
+        UI.user_requested_convergence_diagnostics = bool(pes.get('convergence_diagnostics', False))       # IP.py:2741
 
         obs_unc = UI.responses['responses_observed_uncertainties']
         observed = UI.responses['responses_observed']
@@ -94,7 +95,22 @@ class parameter_estimation:
         self.Q_covmat = H.covmat_prior                                                                # IP.py:350
         guess = UI.model.get('InputParameterInitialGuess', [])
         if isinstance(guess, str):
-            raise NotImplementedError("pickled initial guesses are file I/O; out of scope (DESIGN.md)")
+            # a pickle file written by an earlier run, e.g. 'mcmc_last_point_sampled' (IP.py:355-380): looked for in the
+            # working directory, then in the pickles directory; of a (walkers, parameters) array the first walker is taken
+            from .export import unpickleAnObject
+            name = guess.replace('.pkl', '')
+            if os.path.exists(name + '.pkl'):
+                loaded = unpickleAnObject(name)
+            elif os.path.exists(UI.directories['pickles'] + name + '.pkl'):
+                loaded = unpickleAnObject(UI.directories['pickles'] + name)
+            else:
+                print('The pickled object for initial guess points must exist in base directory or pickles directory. The pickled file should have extension of ".pkl"')
+                sys.exit()
+            loaded = np.array(loaded)
+            if loaded.ndim not in (1, 2):
+                print('The shape of the initial guess pickled array should be (num_walkers, num_parameters). The current pickled array does not have this shape and has:', loaded.shape)
+                sys.exit()
+            guess = loaded if loaded.ndim == 1 else loaded[0]
         if guess is None or len(guess) == 0:
             guess = np.array(UI.model['InputParameterPriorValues'], dtype='float')                    # IP.py:383-384
         UI.InputParameterInitialGuess = np.array(guess, dtype='float').reshape(-1)
@@ -506,6 +522,13 @@ class parameter_estimation:
     def doeParameterModulationPermutationsScanner(self, searchType='doMetropolisHastings'):       # IP.py:1499
         from .doe import doe_parameter_modulation_scanner
         return doe_parameter_modulation_scanner(self, searchType)
+
+    # ------------------------------------------------------------------------------------------
+    # convergence diagnostics: Geweke z-scores of every chain, window and parameter on the device
+    # ------------------------------------------------------------------------------------------
+    def getConvergenceDiagnostics(self, discrete_chains_post_burn_in_samples=[], showFigure=None):   # IP.py:2121
+        from .diagnostics import convergence_diagnostics
+        return convergence_diagnostics(self, discrete_chains_post_burn_in_samples)
 
     # ------------------------------------------------------------------------------------------
     # on-disk formats

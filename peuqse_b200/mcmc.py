@@ -171,6 +171,9 @@ def run_metropolis_hastings(pe, calculatePostBurnInStatistics=True, continueSamp
         pe._dev_post = None                                                  # merged on the host: statistics upload them
     if calculatePostBurnInStatistics:
         post_burn_in_statistics(pe, calculate_post_burn_in_log_priors_vec=bool(continueSampling))
+        if UI.user_requested_convergence_diagnostics:                                                 # IP.py:2741-2742
+            pe._mh_burn_rows = b
+            pe.getConvergenceDiagnostics(S[b:] if D.world()[1] == 1 else pe.discrete_chains_post_burn_in_samples)
         _export_if_requested(pe, mcmc_exportLog)                                                      # IP.py:2743-2746
         return [pe.map_parameter_set, pe.mu_AP_parameter_set, pe.stdap_parameter_set, pe.evidence, pe.info_gain,
                 pe.post_burn_in_samples, pe.post_burn_in_log_posteriors_un_normed_vec]               # IP.py:2749

@@ -905,6 +905,9 @@ def test_on_disk_formats_round_trip(env, golden):
     assert np.array_equal(st[0], res[0]) and np.array_equal(st[5], res[5]) and st[4] == res[4]
     sim = np.genfromtxt('logs_and_csvs/ExportedResponsesData__map__ResponsesConsolidated.csv', delimiter=",", skip_header=1)
     assert np.array_equal(sim[:, 0], X00) and np.array_equal(sim[:, 1], (np.array(X00) - res[0][0]) ** 2 + res[0][1])
+    # the last point of this run, by file name, as the start of a new object (IP.py:355-380)
+    PE4 = make_pe(PEUQSE, PEUQSE.QuadraticModel(X00), Y00, S00, [200, 500], [100, 200], InputParameterInitialGuess='mcmc_last_point_sampled.pkl')
+    assert np.array_equal(PE4.UserInput.InputParameterInitialGuess, PE.mcmc_last_point_sampled)
     # a fresh object rebuilds the statistics from the files (the filter already ran: the kept rows are what was written)
     PE2 = make_pe(PEUQSE, PEUQSE.QuadraticModel(X00), Y00, S00, [200, 500], [100, 200],
                   settings={'mcmc_length': 800, 'mcmc_threshold_filter_samples': False, 'mcmc_info_gain_returned': 'log_ratio'})
@@ -931,3 +934,75 @@ def test_on_disk_formats_round_trip(env, golden):
     assert PE3.post_burn_in_samples.shape[0] == int(g['ex00_grid_nrows_expanded'])
     np.testing.assert_allclose(r3[1], g['ex00_grid_mu_AP'], rtol=1e-12)
     np.testing.assert_allclose(r3[2], g['ex00_grid_stdap'], rtol=1e-10)
+
+
+def test_geweke_on_device_vs_reference_fixture_and_oracle(env, golden):
+    """Geweke z-scores from one streaming prefix-sum pass (csrc/diag.cu) against the reference's own
+    outputs (tests/golden/geweke.npz) and the oracle on larger seeded chains.  Tolerance 1e-8 relative: slice statistics are
+    differences of prefix sums instead of numpy's pairwise sums over each slice."""
+    import warnings
+    PEUQSE, orc, _, torch = env
+    from peuqse_b200.diagnostics import geweke_z_scores, convergence_diagnostics
+    g = golden("geweke")
+    x = g['chains_a']
+    z, windows, starts = geweke_z_scores(x)
+    z = z.cpu().numpy()
+    assert np.array_equal(windows, g['a_window_indices']) and z.shape == (3, 3, 20, 20)
+    ref_full = g['single_chain_z']
+    assert np.array_equal(starts, ref_full[:, 0].astype(int))
+    np.testing.assert_allclose(z[0, 0, -1], ref_full[:, 1], rtol=1e-8)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        r = orc.geweke_convergence(x)
+    fin = np.isfinite(r['z'])
+    assert np.array_equal(np.isfinite(z), fin)
+    np.testing.assert_allclose(z[fin], r['z'][fin], rtol=1e-8)
+    import types
+    pe = types.SimpleNamespace(gpu_launches=0)
+    out = convergence_diagnostics(pe, x)
+    np.testing.assert_allclose(out[4], g['a_final_combined'], rtol=1e-8, equal_nan=True)
+    np.testing.assert_allclose(out[5], g['a_percent_outlier'], rtol=1e-15)
+    assert np.array_equal(np.asarray(out[3]), g['a_window_indices'])
+    assert pe.convergence['Geweke']['z_scores_each_parameter'].shape == (3, 20, 20)
+    # many columns and several row segments; values with a large offset (the pivot keeps the prefix sums small)
+    rng = np.random.default_rng(21)
+    R, C, k = 6000, 40, 4
+    e = rng.standard_normal((R, C, k))
+    y = np.empty_like(e)
+    y[0] = e[0]
+    phi = np.array([0.2, 0.8, 0.95, 0.5])
+    for t in range(1, R):
+        y[t] = phi * y[t - 1] + e[t]
+    y = y * np.array([1e-3, 1.0, 50.0, 1e4]) + np.array([7.0, -3e3, 1e5, 1e7])
+    z2 = geweke_z_scores(torch.as_tensor(y).cuda())[0].cpu().numpy()
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        for c, d in ((0, 0), (17, 2), (39, 3), (5, 1)):
+            for w, n in ((19, R), (7, 2400), (1, 600)):
+                ref = orc.geweke_diagnostic(y[:n, c, d])[:, 1]
+                np.testing.assert_allclose(z2[d, c, w], ref, rtol=1e-7, equal_nan=True)
+    # through the sampler: convergence_diagnostics=True fills PE_object.convergence after doMetropolisHastings
+    PE = make_pe(PEUQSE, PEUQSE.QuadraticModel(X00), Y00, S00, [200, 500], [100, 200],
+                 settings={'mcmc_length': 3000, 'mcmc_burn_in': 500, 'mcmc_nchains': 8, 'mcmc_random_seed': 1, 'mcmc_relative_step_length': 0.3,
+                           'mcmc_info_gain_returned': 'log_ratio', 'convergence_diagnostics': True, 'mcmc_exportLog': False})
+    PE.doMetropolisHastings()
+    G = PE.convergence['Geweke']
+    assert np.array_equal(G['window_indices'], np.linspace(0, 2500, 21).astype(int)[1:]) and PE.convergence['AutoCorrTime']['window_indices'] is None
+    zz = PE.geweke_z_scores.cpu().numpy()
+    chains = PE.discrete_chains_post_burn_in_samples
+    assert chains.shape == (2500, 8, 2) and zz.shape == (2, 8, 20, 20)
+    checked = 0
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        for d in range(2):
+            for c in range(8):
+                for w in (6, 13, 19):
+                    try:       # MH chains repeat rows: a short slice of identical values makes the reference's 2x2 solve singular
+                        ref = orc.geweke_diagnostic(chains[:G['window_indices'][w], c, d])[:, 1]
+                    except np.linalg.LinAlgError:
+                        continue
+                    np.testing.assert_allclose(zz[d, c, w], ref, rtol=1e-7, equal_nan=True)
+                    checked += 1
+    assert checked >= 40
+    comb = np.mean(np.mean(np.abs(zz), axis=0), axis=0)
+    np.testing.assert_allclose(G['final_combined_parameter_values'], comb[:, -1], rtol=1e-12, equal_nan=True)

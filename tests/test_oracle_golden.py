@@ -307,3 +307,27 @@ def test_doe_info_gain_matrices(golden, fmt):
     mods = np.array(orc.combination_generator([DH, DS], np.array([1, 1]) * np.array([DHU, DSU]), [1, 1]), dtype=float)   # IP.py:1506-1509
     A = np.array([orc.doe_info_gain_matrix(build, sim, conds, m, [DH, DS], g['deltas'], g['us'], int(BURN))[0] for m in mods])
     assert np.array_equal(A, g[f'scanner_{fmt}_info_gains_matrices_array'])
+
+
+def test_geweke_diagnostic_vs_reference(golden):
+    """geweke_diagnostic and the Geweke half of calculateAndPlotConvergenceDiagnostics of the unmodified reference
+    (tests/golden/make_golden_geweke.py; statsmodels' yule_walker supplied by the oracle's restatement): bit for bit."""
+    import warnings
+    g = golden("geweke")
+    x = g['chains_a']
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        assert np.array_equal(orc.geweke_diagnostic(x[:, 0, 0]), g['single_chain_z'], equal_nan=True)
+        assert np.array_equal(orc.geweke_diagnostic(x[:333, 1, 2]), g['single_chain_z_short'], equal_nan=True)
+        r = orc.geweke_convergence(x)
+    assert np.array_equal(r['window_indices'], g['a_window_indices'])
+    assert np.array_equal(r['final_combined_parameter_values'], g['a_final_combined'], equal_nan=True)
+    assert np.array_equal(r['final_combined_parameter_percent_outlier'], g['a_percent_outlier'])
+    # the closed-form Yule-Walker restatement against a direct least-squares view of the same equations
+    rng = np.random.default_rng(3)
+    v = np.cumsum(rng.standard_normal(400)) * 0.1 + rng.standard_normal(400)
+    rho, sigma = orc.yule_walker(v, 2)
+    d = v - v.mean()
+    r0, r1, r2 = (d * d).sum() / 400, (d[:-1] * d[1:]).sum() / 399, (d[:-2] * d[2:]).sum() / 398
+    np.testing.assert_allclose(np.array([[r0, r1], [r1, r0]]) @ rho, [r1, r2], rtol=1e-12)
+    np.testing.assert_allclose(sigma ** 2, r0 - r1 * rho[0] - r2 * rho[1], rtol=1e-12)
