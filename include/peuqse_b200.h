@@ -422,7 +422,7 @@ int peuqse_scenarios_logp(const peuqse_problem* p, const peuqse_scenarios* sc, c
                           double* d_logp, double* d_logprior, double* d_loglik, void* stream);
 /* peuqse_mh_run with chain c sampling scenario c / chains_per_scenario; spec->n_chains = S * chains_per_scenario.  Chain j of
  * every scenario draws from Philox stream chain_offset + j: all scenarios see the same draws, as in the reference, which
- * reseeds numpy in every __init__ (IP.py:191-193).  Needs n_total <= 128.  Outputs as peuqse_mh_run. */
+ * reseeds numpy in every __init__ (IP.py:191-193).  Outputs as peuqse_mh_run. */
 int peuqse_mh_run_scenarios(const peuqse_problem* p, const peuqse_scenarios* sc, const peuqse_mh_spec* spec,
                             int64_t chains_per_scenario, const double* d_theta0, double* d_samples, double* d_logp,
                             double* d_logprior, double* d_loglik, double* d_deltas, double* d_us, double* d_stats, void* stream);

@@ -66,6 +66,30 @@ __global__ void __launch_bounds__(128) k_scen_logp(const __grid_constant__ DevPr
     if (llik) llik[i] = ll;
 }
 
+// the same for many observations: one warp per (scenario, point), lanes stride over the observations
+template <int MODEL, int KT>
+__global__ void __launch_bounds__(128) k_scen_logp_warp(const __grid_constant__ DevProblem P, const DevScen SC, long long S, long long B,
+                                                        const double* __restrict__ theta, double* __restrict__ logp,
+                                                        double* __restrict__ lprior, double* __restrict__ llik) {
+    const long long i = (long long)blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (i >= S * B) return;
+    const long long s = i / B;
+    ObsView O;
+    O.y = SC.y + s * SC.n_total; O.w = P.w; O.cval = P.cval;
+    O.mc = SC.mc + s * SC.n_mconst;
+    double th[KT];
+#pragma unroll
+    for (int d = 0; d < KT; ++d) th[d] = (d < P.k) ? theta[i * P.k + d] : 0.0;
+    const double lp = eval_prior<KT>(P, th);
+    const double ll = eval_loglik_warp<MODEL, KT>(P, O, th, nullptr, lane);
+    if (lane == 0) {
+        if (logp) logp[i] = combine_logp(lp, ll);
+        if (lprior) lprior[i] = lp;
+        if (llik) llik[i] = ll;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // per-scenario post-burn-in statistics
 // ---------------------------------------------------------------------------------------------------
@@ -423,13 +447,15 @@ extern "C" int peuqse_scenarios_logp(const peuqse_problem* p, const peuqse_scena
     if (rc) return rc;
     if (!sc->has_y) return pq_set_error(PEUQSE_ERR_INVALID, "scenarios have no observed values yet");
     if (!d_theta || B < 0) return pq_set_error(PEUQSE_ERR_INVALID, "bad argument");
-    if (p->d.n_total > PQ_THREAD_SHAPE_MAX_N) return pq_set_error(PEUQSE_ERR_INVALID, "scenario batches support n_total <= 128");
     if (B == 0) return PEUQSE_OK;
     const DevScen SC{sc->d_y, sc->d_mc, (long long)B, sc->n_total, sc->n_mconst};
     const long long total = sc->S * B;
-    const unsigned grid = (unsigned)((total + 127) / 128);
+    const bool warp_shape = p->d.n_total > PQ_THREAD_SHAPE_MAX_N;
+    const unsigned grid = (unsigned)(warp_shape ? (total + 3) / 4 : (total + 127) / 128);
     cudaStream_t st = (cudaStream_t)stream;
-#define SLOGP(MODEL, KT) k_scen_logp<MODEL, KT><<<grid, 128, 0, st>>>(p->d, SC, sc->S, B, d_theta, d_logp, d_logprior, d_loglik)
+#define SLOGP(MODEL, KT)                                                                                                      \
+    if (warp_shape) k_scen_logp_warp<MODEL, KT><<<grid, 128, 0, st>>>(p->d, SC, sc->S, B, d_theta, d_logp, d_logprior, d_loglik); \
+    else k_scen_logp<MODEL, KT><<<grid, 128, 0, st>>>(p->d, SC, sc->S, B, d_theta, d_logp, d_logprior, d_loglik)
     SCEN_MODEL_DISPATCH(SLOGP)
 #undef SLOGP
     PQ_CUDA_OK(cudaGetLastError());

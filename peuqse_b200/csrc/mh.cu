@@ -436,8 +436,15 @@ int launch_mh(const peuqse_problem* p, const DevMH& M, const double* th0, const 
     // few chains with few observations: one warp per chain, thread-order evaluation (latency); many: one thread per chain
     const bool few = M.n_chains <= mh_few_chains();
     if (SC.y) {
-        // scenario batch: thread-order evaluation in both shapes (n_total <= PQ_THREAD_SHAPE_MAX_N, checked by the caller)
-        if (few) {
+        // scenario batch.  Many observations: one warp per chain, lanes stride over the scenario's own rows of constants in
+        // global memory (L1/L2-resident; nothing is staged because every warp of a CTA may belong to another scenario).
+        // Few observations: thread-order evaluation, one warp per chain when there are few chains, else one thread per chain.
+        if (p->d.n_total > PQ_THREAD_SHAPE_MAX_N) {
+            auto kern = k_mh_warp<MODEL, KT, 2, -1, false, 4, true>;
+            const size_t wsmem = (size_t)MHW_WARPS * MhwLayout<KT>::WDOUBLES * sizeof(double);
+            const long long blocks = (M.n_chains + MHW_WARPS - 1) / MHW_WARPS;
+            kern<<<(unsigned)blocks, 32 * MHW_WARPS, wsmem, st>>>(p->d, M, th0, out, 0, SC);
+        } else if (few) {
             auto kern = k_mh_warp<MODEL, KT, 2, -1, true, 4, true>;
             const size_t wsmem = smem + (size_t)MHW_WARPS * MhwLayout<KT>::WDOUBLES * sizeof(double);
             PQ_CUDA_OK(pq_allow_smem((const void*)kern, wsmem));
@@ -526,7 +533,6 @@ extern "C" int peuqse_mh_run_scenarios(const peuqse_problem* p, const peuqse_sce
     if (sc->n_total != p->d.n_total || sc->n_mconst != p->d.n_mconst) return pq_set_error(PEUQSE_ERR_INVALID, "scenarios belong to another problem");
     if (chains_per_scenario < 1 || s->n_chains != sc->S * chains_per_scenario)
         return pq_set_error(PEUQSE_ERR_INVALID, "n_chains must equal n_scenarios * chains_per_scenario");
-    if (p->d.n_total > PQ_THREAD_SHAPE_MAX_N) return pq_set_error(PEUQSE_ERR_INVALID, "scenario batches support n_total <= 128");
     DevScen SC{sc->d_y, sc->d_mc, (long long)chains_per_scenario, sc->n_total, sc->n_mconst};
     return mh_run_impl(p, s, SC, d_theta0, d_samples, d_logp, d_logprior, d_loglik, d_deltas, d_us, d_stats, stream);
 }

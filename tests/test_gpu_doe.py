@@ -34,7 +34,8 @@ def make_pe(PEUQSE, model, observed, unc, mu, punc, settings=None):
     UI.model['InputParameterPriorValues'] = mu
     UI.model['InputParametersPriorValuesUncertainties'] = punc
     UI.model['simulateByInputParametersOnlyFunction'] = model
-    UI.parameter_estimation_settings.update(settings or {})
+    for key, v in (settings or {}).items():
+        (UI.responses if key in UI.responses else UI.parameter_estimation_settings)[key] = v
     return PEUQSE.parameter_estimation(UI)
 
 
@@ -208,3 +209,46 @@ def test_scenario_chains_equal_single_problem_chains(env):
             assert int(stats[s, SS['MAP_INDEX']]) == st['map_index'] and stats[s, SS['MAP_LOGP']] == st['map_logP']
             np.testing.assert_allclose(stats[s, SS['INFO_GAIN_LOG_RATIO']], st['info_gain_log_ratio'], rtol=1e-10)
             assert np.array_equal(stats[s, SS['MAP_THETA']:SS['MAP_THETA'] + 2], st['map_parameter_set'])
+
+
+def test_scenarios_with_many_observations_tpd(env, golden):
+    """Scenario batches of a model with 1024 observations (the warp shape: lanes stride over the scenario's own rows of
+    constants): chains bit-identical to stand-alone runs of the same problem, per-point values against the oracle."""
+    PEUQSE, orc, _, torch = env
+    from peuqse_b200.doe import ScenarioBatch
+    from peuqse_b200.mcmc import mh_launch, step_cholesky
+    n = 1024
+    mu, sd = [41.5, 41.5, 13., 13., 0.1, 0.1], [20., 20., 13., 13., 0.1, 0.1]
+    truth = np.array([41.5, 45., 13., 13., 0.1, 0.1])
+    kBT, c1, c2 = orc.tpd2site_constants(n)
+
+    class RampModel(PEUQSE.Tpd2SiteModel):
+        """Independent variables: heating rate and initial coverage of the prescribed-coverage TPD model."""
+
+        def with_conditions(self, values):
+            return RampModel.linear_ramp(n, beta=values[0], cov0=values[1])
+
+    base = RampModel.linear_ramp(n)
+    pt, _ = orc.sim_tpd2site(kBT, c1, c2)
+    sig = [0.02 * float(np.max(pt(truth)))] * n
+    PE = make_pe(PEUQSE, base, list(pt(truth)), sig, mu, sd, settings={'mcmc_length': 60, 'responses_observed_max_covmat_size': 5000})
+    conds = np.array([[0.5, 0.5], [0.4, 0.6], [0.7, 0.3], [0.55, 0.45], [0.3, 0.5]])
+    batch = ScenarioBatch(PE, conds, truth)
+    obs = batch.observed.cpu().numpy()
+    rng = np.random.default_rng(2)
+    th = truth + 0.01 * np.array(sd) * rng.standard_normal((5, 16, 6))
+    lp, pr, ll = (t.cpu().numpy() for t in batch.logp(th, return_parts=True))
+    chol = step_cholesky(PE.Q_covmat, 2.5e-6)
+    run = batch.run_mh(truth, 60, 10, 5, chol, chains_per_scenario=2)
+    for s, c in enumerate(conds):
+        m = RampModel.linear_ramp(n, beta=c[0], cov0=c[1])
+        pts, bts = orc.sim_tpd2site(m.kBT, m.cov1, m.cov2)
+        np.testing.assert_allclose(obs[s], pts(truth), rtol=1e-12)
+        Ps = orc.build_problem(mu, sd, obs[s], sig, max_covmat_size=5000)
+        r = orc.log_p_batch(Ps, th[s], bts)
+        np.testing.assert_allclose(lp[s], r[0], rtol=1e-12)
+        np.testing.assert_allclose(ll[s], r[2], rtol=1e-12)
+        PE1 = make_pe(PEUQSE, m, list(obs[s]), sig, mu, sd, settings={'mcmc_length': 60, 'responses_observed_max_covmat_size': 5000})
+        one = mh_launch(PE1, np.tile(truth, (2, 1)), 60, 10, 5, chol)
+        assert np.array_equal(run['samples'][:, 2 * s:2 * s + 2].cpu().numpy(), one['samples'].cpu().numpy())
+        assert np.array_equal(run['logp'][:, 2 * s:2 * s + 2].cpu().numpy(), one['logp'].cpu().numpy())
