@@ -103,7 +103,7 @@ def exportPostBurnInStatistics(pe):
         exportResponses(pe)
 
 
-def exportMultistart(pe, centerPoint, bestResultSoFar, permutationsToSamples):
+def exportMultistart(pe, centerPoint, bestResultSoFar, permutationsToSamples, initial_point=None, optimizer=False):
     """The file output at the end of doListOfPermutationsSearch for searchType 'getLogP' (IP.py:1037-1072)."""
     if _rank_suffix() != 0:
         return
@@ -112,15 +112,19 @@ def exportMultistart(pe, centerPoint, bestResultSoFar, permutationsToSamples):
     res = pe.sweep_result
     with open(logs + "multistart_log_file.txt", 'w') as out_file:
         exportResponses(pe, "map")
-        point = tuple(np.float64(v) for v in bestResultSoFar[0])                     # the reference keeps the list's tuple
+        start = bestResultSoFar[0] if initial_point is None else initial_point
+        start = tuple(np.float64(v) for v in start)                                  # the reference keeps the list's tuple
+        best = np.asarray(bestResultSoFar[0]) if optimizer else start                # an optimiser returns an array (IP.py:916)
         out_file.write("centerPoint: " + str(centerPoint) + "\n")
         out_file.write("highest_MAP_logP: " + str(np.array([pe.map_logP])) + "\n")
-        out_file.write("highest_MAP_logP_parameter_set: " + str(point) + "\n")
+        out_file.write("highest_MAP_logP_parameter_set: " + str(best) + "\n")
         out_file.write("highest_MAP_initial_point_index: " + str(pe.map_index) + "\n")
-        out_file.write("highest_MAP_initial_point_parameters: " + str(point) + "\n")
+        out_file.write("highest_MAP_initial_point_parameters: " + str(start) + "\n")
         if permutationsToSamples == True:                                            # noqa: E712
             out_file.write("self.mu_AP_parameter_set : " + str(bestResultSoFar[1]) + "\n")
             out_file.write("self.stdap_parameter_set : " + str(bestResultSoFar[2]) + "\n")
+        if optimizer:                                                                # IP.py:1052-1053
+            out_file.write("\n WARNING: It appears this run used a doOptimize with multi-start. In this case, the MAP_logP and map_parameter_set are the optimum from the run.  However, the mu_AP_parameter_set and stdap_parameter_set are not meaningful, since this was not an even weighted exploration of the posterior. \n")
     from . import distributed as D
     sw = getattr(pe, '_sweep', None)
     have_arrays = hasattr(pe, '_perm_array') or (sw is not None and sw.logp is not None and D.world()[1] == 1)

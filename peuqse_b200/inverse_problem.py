@@ -304,9 +304,10 @@ class parameter_estimation:
         if numStartPoints == 0: numStartPoints = len(self.UserInput.InputParameterInitialGuess) * 3     # IP.py:1101-1102
         if relativeInitialDistributionSpread == 0: relativeInitialDistributionSpread = 0.866           # IP.py:1103-1104
         if searchType in ('doGetLogP', 'doSinglePoint'): searchType = 'getLogP'                        # IP.py:1105-1106
-        if searchType != 'getLogP':
-            raise NotImplementedError(f"multistart searchType '{searchType}' (an optimiser or a whole MCMC run per start point) "
-                                      "is outside the accelerated path; use 'getLogP'")
+        if searchType not in ('getLogP', 'doOptimizeNegLogP', 'doOptimizeLogP'):
+            raise NotImplementedError(f"multistart searchType '{searchType}' (a whole MCMC run or an SSR fit per start point) "
+                                      "is outside the accelerated path; use 'getLogP', 'doOptimizeNegLogP' or 'doOptimizeLogP'")
+        if str(passThroughArgs) == 'UserChoice': passThroughArgs = pes.get('multistart_passThroughArgs', {})
         if str(centerPoint).lower() == 'none':
             centerPoint = np.array(self.UserInput.InputParameterInitialGuess) * 1.0
         centerPoint = np.asarray(centerPoint, dtype=float)
@@ -316,6 +317,11 @@ class parameter_estimation:
         coef = 2.0 if str(coef).lower() == 'auto' else float(coef)                                      # IP.py:1011-1014
         nbins = int(pes.get('multistart_histogram_bins', 10))
         k = self.k
+        if searchType != 'getLogP':
+            pts = self.generateInitialPoints(numStartPoints=numStartPoints, initialPointsDistributionType=kind,
+                                             relativeInitialDistributionSpread=relativeInitialDistributionSpread, centerPoint=centerPoint,
+                                             gridsearchSamplingInterval=gridsearchSamplingInterval, gridsearchSamplingRadii=gridsearchSamplingRadii)
+            return self._multistart_optimize(searchType, pts, passThroughArgs, centerPoint)
         if kind == 'grid':
             c, h, r, n = self.getGridPermutations(centerPoint, gridsearchSamplingInterval, gridsearchSamplingRadii)
             spec = make_spec("grid", k, c, interval=h, radii=r)
@@ -366,8 +372,58 @@ class parameter_estimation:
             from .export import exportMultistart                                                       # IP.py:1037-1072
             stats = bool(getattr(res, 'statistics', False))
             exportMultistart(self, centerPoint, [self.map_parameter_set, getattr(self, 'mu_AP_parameter_set', None) if stats else None,
-                                                 getattr(self, 'stdap_parameter_set', None) if stats else None], stats)
+                                                 getattr(self, 'stdap_parameter_set', None) if stats else None], stats,
+                             initial_point=getattr(res, 'initial_point', None), optimizer=getattr(res, 'optimizer', False))
         return best
+
+    # optimisers: scipy drives, every objective evaluation is one launch of the log-posterior kernel -------------------
+    def doOptimizeNegLogP(self, simulationFunctionAdditionalArgs=(), method=None, optimizationAdditionalArgs={}, printOptimum=True,
+                          verbose=True, maxiter=0):
+        """IP.py:1670-1694: scipy.optimize.minimize(getNegLogP, InputParameterInitialGuess, method).  The optimiser is scipy's own
+        code on the host, as in the reference; with a bit-exact getLogP it walks the reference's iterates."""
+        import scipy.optimize
+        initialGuess = self.UserInput.InputParameterInitialGuess
+        options = {"maxiter": maxiter} if maxiter != 0 else ({"disp": True} if verbose else None)
+        res = scipy.optimize.minimize(self.getNegLogP, initialGuess, method=method, options=options)
+        self.map_parameter_set = res.x
+        negLogP = res.fun
+        self.map_logP = -1.0 * negLogP
+        if printOptimum:
+            print("Final results from doOptimizeNegLogP:", self.map_parameter_set, "final negLogP:", negLogP, "final logP:", self.map_logP)
+        return [self.map_parameter_set, negLogP]
+
+    def doOptimizeLogP(self, simulationFunctionAdditionalArgs=(), method=None, optimizationAdditionalArgs={}, printOptimum=True,
+                       verbose=True, maxiter=0):
+        """IP.py:1661-1666."""
+        self.map_parameter_set, negLogP = self.doOptimizeNegLogP(simulationFunctionAdditionalArgs, method, optimizationAdditionalArgs,
+                                                                 printOptimum, verbose, maxiter)
+        self.map_logP = -1.0 * negLogP
+        return [self.map_parameter_set, self.map_logP]
+
+    find_MAP = doOptimizeLogP                                                                         # IP.py:1668
+
+    def _multistart_optimize(self, searchType, pts, passThroughArgs, centerPoint):
+        """The start-point loop of doListOfPermutationsSearch for an optimiser searchType (IP.py:844-956, 912-921)."""
+        from .sweep import SweepResult
+        pts = np.asarray(pts, dtype=float)
+        self._list_of_permutations = pts
+        highest, R, rows = float('-inf'), SweepResult(), []
+        R.total, R.map_index, R.statistics, R.optimizer = len(pts), -1, False, True
+        for i, p in enumerate(pts):
+            self.UserInput.InputParameterInitialGuess = p                                             # IP.py:858
+            if searchType == 'doOptimizeLogP':
+                x, logp = self.doOptimizeLogP(**passThroughArgs)
+            else:
+                x, neg = self.doOptimizeNegLogP(**passThroughArgs)
+                logp = -1.0 * neg
+            if logp > highest:                                                                        # IP.py:933
+                highest, R.map_index, R.map_parameter_set, R.initial_point = float(logp), i, np.copy(x), p
+            rows.append(np.hstack((logp, x)))                                                         # IP.py:947
+        self._perm_array = np.array(rows)
+        R.map_logP = highest
+        if R.map_index < 0:
+            R.map_parameter_set = np.full(self.k, np.nan)
+        return self._adopt_sweep_result(R, centerPoint)
 
     def doGridSearch(self, searchType='getLogP', gridSamplingAbsoluteIntervalSize=[], gridSamplingNumOfIntervals=[], **kw):
         """Deprecated alias kept by the reference (IP.py:1120-1128)."""
@@ -550,5 +606,5 @@ class parameter_estimation:
         raise NotImplementedError("outside the accelerated hot path (see DESIGN.md, 'Out of scope')")
 
     createAllPlots = makeHistogramsForEachParameter = makeSamplingScatterMatrixPlot = createSimulatedResponsesPlots = _out_of_scope
-    doOptimizeNegLogP = doOptimizeLogP = doOptimizeSSR = doEnsembleModifiedMHSampling = _out_of_scope
+    doOptimizeSSR = doEnsembleModifiedMHSampling = _out_of_scope
     save_to_dill = load_from_dill = createInfoGainPlots = createInfoGainModulationPlots = _out_of_scope

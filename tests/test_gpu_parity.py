@@ -1006,3 +1006,32 @@ def test_geweke_on_device_vs_reference_fixture_and_oracle(env, golden):
     assert checked >= 40
     comb = np.mean(np.mean(np.abs(zz), axis=0), axis=0)
     np.testing.assert_allclose(G['final_combined_parameter_values'], comb[:, -1], rtol=1e-12, equal_nan=True)
+
+
+def test_optimizers_walk_the_reference_iterates(env, golden):
+    """doOptimizeNegLogP / doOptimizeLogP and a multistart of optimiser runs (IP.py:1661-1694, 912-921): scipy's optimiser on
+    the host with every objective value from the log-posterior kernel.  getLogP is bit-exact for Example00, so the optimiser
+    sees the reference's values and must end on the reference's optimum to the last bit (tests/golden/make_golden_optimize.py)."""
+    import contextlib
+    import io
+    PEUQSE, _, _, _ = env
+    g = golden("optimize")
+    for tag, method in (('nm', 'Nelder-Mead'), ('bfgs', None), ('powell', 'Powell')):
+        PE = make_pe(PEUQSE, PEUQSE.QuadraticModel(X00), Y00, S00, [200, 500], [100, 200])
+        with contextlib.redirect_stdout(io.StringIO()):
+            x, f = PE.doOptimizeNegLogP(method=method, printOptimum=False, verbose=False)
+        assert np.array_equal(x, g[f'{tag}_x']) and float(f) == float(g[f'{tag}_negLogP']), tag
+        assert float(PE.map_logP) == -float(g[f'{tag}_negLogP'])
+    PE = make_pe(PEUQSE, PEUQSE.QuadraticModel(X00), Y00, S00, [200, 500], [100, 200])
+    x, lp = PE.find_MAP(method='Nelder-Mead', printOptimum=False, verbose=False, maxiter=30)
+    assert np.array_equal(x, g['nm30_x']) and float(lp) == float(g['nm30_logP'])
+    PE = make_pe(PEUQSE, PEUQSE.QuadraticModel(X00), Y00, S00, [200, 500], [100, 200],
+                 settings={'multistart_initialPointsDistributionType': 'grid', 'multistart_gridsearchSamplingInterval': [50, 100],
+                           'multistart_gridsearchSamplingRadii': [1, 1], 'multistart_searchType': 'doOptimizeNegLogP',
+                           'multistart_passThroughArgs': {'method': 'Nelder-Mead', 'printOptimum': False, 'verbose': False},
+                           'responses_abscissa': X00})
+    best = PE.doMultiStart()
+    assert np.array_equal(best[0], g['ms_best_x']) and float(PE.map_logP) == float(g['ms_map_logP'][0]) and PE.map_index == 6
+    assert np.array_equal(PE.permutations_MAP_logP_and_parameters_values, g['ms_perm_array'])
+    assert np.array_equal(PE.listOfPermutations, g['ms_list'])
+    assert open('logs_and_csvs/multistart_log_file.txt', 'rb').read() == bytes(g['ms_log'])
