@@ -103,7 +103,7 @@ def exportPostBurnInStatistics(pe):
         exportResponses(pe)
 
 
-def exportMultistart(pe, centerPoint, bestResultSoFar, permutationsToSamples, initial_point=None, optimizer=False):
+def exportMultistart(pe, centerPoint, bestResultSoFar, permutationsToSamples, initial_point=None, optimizer=False, mcmc=False):
     """The file output at the end of doListOfPermutationsSearch for searchType 'getLogP' (IP.py:1037-1072)."""
     if _rank_suffix() != 0:
         return
@@ -114,15 +114,16 @@ def exportMultistart(pe, centerPoint, bestResultSoFar, permutationsToSamples, in
         exportResponses(pe, "map")
         start = bestResultSoFar[0] if initial_point is None else initial_point
         start = tuple(np.float64(v) for v in start)                                  # the reference keeps the list's tuple
-        best = np.asarray(bestResultSoFar[0]) if optimizer else start                # an optimiser returns an array (IP.py:916)
+        best = np.asarray(bestResultSoFar[0]) if (optimizer or mcmc) else start      # optimisers and samplers return arrays
         out_file.write("centerPoint: " + str(centerPoint) + "\n")
         out_file.write("highest_MAP_logP: " + str(np.array([pe.map_logP])) + "\n")
         out_file.write("highest_MAP_logP_parameter_set: " + str(best) + "\n")
         out_file.write("highest_MAP_initial_point_index: " + str(pe.map_index) + "\n")
         out_file.write("highest_MAP_initial_point_parameters: " + str(start) + "\n")
         if permutationsToSamples == True:                                            # noqa: E712
-            out_file.write("self.mu_AP_parameter_set : " + str(bestResultSoFar[1]) + "\n")
-            out_file.write("self.stdap_parameter_set : " + str(bestResultSoFar[2]) + "\n")
+            caveat = ' (for the above initial point) ' if mcmc else ''                # IP.py:1046-1049
+            out_file.write("self.mu_AP_parameter_set : " + caveat + str(bestResultSoFar[1]) + "\n")
+            out_file.write("self.stdap_parameter_set : " + caveat + str(bestResultSoFar[2]) + "\n")
         if optimizer:                                                                # IP.py:1052-1053
             out_file.write("\n WARNING: It appears this run used a doOptimize with multi-start. In this case, the MAP_logP and map_parameter_set are the optimum from the run.  However, the mu_AP_parameter_set and stdap_parameter_set are not meaningful, since this was not an even weighted exploration of the posterior. \n")
     from . import distributed as D

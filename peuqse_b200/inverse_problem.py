@@ -304,9 +304,11 @@ class parameter_estimation:
         if numStartPoints == 0: numStartPoints = len(self.UserInput.InputParameterInitialGuess) * 3     # IP.py:1101-1102
         if relativeInitialDistributionSpread == 0: relativeInitialDistributionSpread = 0.866           # IP.py:1103-1104
         if searchType in ('doGetLogP', 'doSinglePoint'): searchType = 'getLogP'                        # IP.py:1105-1106
-        if searchType not in ('getLogP', 'doOptimizeNegLogP', 'doOptimizeLogP'):
-            raise NotImplementedError(f"multistart searchType '{searchType}' (a whole MCMC run or an SSR fit per start point) "
-                                      "is outside the accelerated path; use 'getLogP', 'doOptimizeNegLogP' or 'doOptimizeLogP'")
+        if searchType not in ('getLogP', 'doOptimizeNegLogP', 'doOptimizeLogP', 'doMetropolisHastings'):
+            raise NotImplementedError(f"multistart searchType '{searchType}' (an ensemble sampler or an SSR fit per start point) is outside "
+                                      "the accelerated path; use 'getLogP', 'doMetropolisHastings', 'doOptimizeNegLogP' or 'doOptimizeLogP'")
+        if str(keep_cumulative_post_burn_in_data) == 'UserChoice':
+            keep_cumulative_post_burn_in_data = pes.get('multistart_keep_cumulative_post_burn_in_data', False)
         if str(passThroughArgs) == 'UserChoice': passThroughArgs = pes.get('multistart_passThroughArgs', {})
         if str(centerPoint).lower() == 'none':
             centerPoint = np.array(self.UserInput.InputParameterInitialGuess) * 1.0
@@ -321,6 +323,8 @@ class parameter_estimation:
             pts = self.generateInitialPoints(numStartPoints=numStartPoints, initialPointsDistributionType=kind,
                                              relativeInitialDistributionSpread=relativeInitialDistributionSpread, centerPoint=centerPoint,
                                              gridsearchSamplingInterval=gridsearchSamplingInterval, gridsearchSamplingRadii=gridsearchSamplingRadii)
+            if searchType == 'doMetropolisHastings':
+                return self._multistart_mh(pts, bool(calculatePostBurnInStatistics), bool(keep_cumulative_post_burn_in_data), centerPoint)
             return self._multistart_optimize(searchType, pts, passThroughArgs, centerPoint)
         if kind == 'grid':
             c, h, r, n = self.getGridPermutations(centerPoint, gridsearchSamplingInterval, gridsearchSamplingRadii)
@@ -424,6 +428,81 @@ class parameter_estimation:
         if R.map_index < 0:
             R.map_parameter_set = np.full(self.k, np.nan)
         return self._adopt_sweep_result(R, centerPoint)
+
+    def _multistart_mh(self, pts, calculatePostBurnInStatistics, keep_cumulative, centerPoint):
+        """Multistart with searchType 'doMetropolisHastings' (IP.py:865-879, 975-990): the reference runs one whole chain per
+        start point, one after the other; here the start points are the chains of ONE launch of the persistent MH kernel
+        (chain c starts at point c and draws from Philox stream c), the per-start MAP comes from the kernel's own per-chain
+        statistics, and the best start's rows go through calculatePostBurnInStatistics like the reference's bestResultSoFar."""
+        from .mcmc import mh_launch, step_cholesky, post_burn_in_statistics, _export_if_requested
+        from .sweep import SweepResult
+        UI = self.UserInput
+        pes = UI.parameter_estimation_settings
+        if pes['mcmc_mode'] != 'unbiased':
+            raise NotImplementedError("mcmc_mode 'MAP_finding' is outside the accelerated path")
+        pts = np.asarray(pts, dtype=float).reshape(-1, self.k)
+        self._list_of_permutations = pts
+        Lm = int(pes['mcmc_length'])
+        burn = int(Lm * 0.1) if str(pes['mcmc_burn_in']).lower() == 'auto' else int(pes['mcmc_burn_in'])
+        seed = pes.get('mcmc_random_seed')
+        seed = int(np.random.SeedSequence().entropy % (2 ** 63)) if not isinstance(seed, int) else seed
+        rank, size = D.world()
+        c0, cn = D.shard_range(len(pts), rank, size)
+        from .mcmc import step_cholesky as _chol
+        out = mh_launch(self, pts[c0:c0 + cn], Lm, burn, seed, _chol(self.Q_covmat, pes['mcmc_relative_step_length']), chain_offset=c0,
+                        modulate=float(pes['mcmc_modulate_accept_probability']))
+        lay = _lib.mh_stat_layout(self.k)
+        st = out['stats']
+        rows = torch.cat([st[:, lay['MAPLOGP']:lay['MAPLOGP'] + 1], st[:, lay['MAPTHETA']:lay['MAPTHETA'] + self.k]], dim=1)
+        rows = D.allgather_rows(rows.contiguous()).cpu().numpy()                                   # [starts, 1 + k]: IP.py:947
+        self._perm_array = rows
+        lp = np.where(np.isnan(rows[:, 0]), -np.inf, rows[:, 0])
+        R = SweepResult()
+        R.total, R.statistics, R.optimizer = len(pts), False, False
+        if not np.any(lp > -np.inf):
+            R.map_logP, R.map_index, R.map_parameter_set = float('-inf'), -1, np.full(self.k, np.nan)
+            return self._adopt_sweep_result(R, centerPoint)
+        i = int(np.argmax(lp))                                                                     # first strict maximum, IP.py:933
+        own = c0 <= i < c0 + cn
+        j = i - c0 if own else 0
+        pick = lambda t, lo, hi: D.allgather_rows((t[lo:hi, j] if own else t[0:0, 0]).contiguous())
+        d_s, d_lp, d_pr = pick(out['samples'], burn, Lm), pick(out['logp'], burn, Lm), pick(out['logprior'], burn, Lm)
+        self.discrete_chains_post_burn_in_samples = d_s.cpu().numpy()[:, None, :]
+        self.post_burn_in_samples = d_s.cpu().numpy()
+        self.post_burn_in_log_posteriors_un_normed_vec = d_lp.cpu().numpy().reshape(-1, 1)
+        self.post_burn_in_log_priors_vec = d_pr.cpu().numpy().reshape(-1, 1)
+        self.during_burn_in_samples = pick(out['samples'], 0, burn).cpu().numpy()
+        self.during_burn_in_log_posteriors_un_normed_vec = pick(out['logp'], 0, burn).cpu().numpy().reshape(-1, 1)
+        self.mcmc_last_point_sampled = self.post_burn_in_samples[-1]
+        UI.last_MCMC_run_type = 'MH'
+        if keep_cumulative:                                                                        # IP.py:869-879: every start, stacked
+            flat = lambda t: D.allgather_rows(t[burn:].permute(1, 0, *range(2, t.ndim)).contiguous()).reshape(-1, *t.shape[2:]).cpu().numpy()
+            self.cumulative_post_burn_in_samples = flat(out['samples'])
+            self.cumulative_post_burn_in_log_posteriors_un_normed_vec = flat(out['logp']).reshape(-1, 1)
+            self.cumulative_post_burn_in_log_priors_vec = flat(out['logprior']).reshape(-1, 1)
+        R.map_logP, R.map_index, R.map_parameter_set, R.initial_point = float(rows[i, 0]), i, rows[i, 1:].copy(), pts[i]
+        self.highest_logP = R.map_logP
+        UI.InputParameterInitialGuess = pts[i]            # what the best start's own run recorded (mcmc_log_file.txt, IP.py:1971)
+        best = [R.map_parameter_set, None, None, None, None, self.post_burn_in_samples, self.post_burn_in_log_posteriors_un_normed_vec]
+        if calculatePostBurnInStatistics:
+            from . import stats as ST
+            self._dev_post = dict(samples=d_s, logp=d_lp, logprior=d_pr)
+            post_burn_in_statistics(self)                   # the best start's own doMetropolisHastings (IP.py:866) ...
+            if ST.filter_settings(pes)[0] != _lib.FILTER_NONE:
+                post_burn_in_statistics(self)               # ... and once more on bestResultSoFar's filtered rows (IP.py:979-982)
+            _export_if_requested(self, 'UserChoice')
+            best = [self.map_parameter_set, self.mu_AP_parameter_set, self.stdap_parameter_set, self.evidence, self.info_gain,
+                    self.post_burn_in_samples, self.post_burn_in_log_posteriors_un_normed_vec]
+            R.statistics, R.mcmc = True, True
+        self.sweep_result = R
+        self.map_logP, self.map_index_of_start, self.map_parameter_set = R.map_logP, i, R.map_parameter_set
+        UI.InputParameterInitialGuess = centerPoint                                                # IP.py:971
+        if bool(pes.get('exportLog', True)):
+            from .export import exportMultistart
+            saved, self.map_index = getattr(self, 'map_index', None), i
+            exportMultistart(self, centerPoint, best, R.statistics, initial_point=pts[i], mcmc=True)
+            self.map_index = saved if saved is not None else i
+        return best
 
     def doGridSearch(self, searchType='getLogP', gridSamplingAbsoluteIntervalSize=[], gridSamplingNumOfIntervals=[], **kw):
         """Deprecated alias kept by the reference (IP.py:1120-1128)."""

@@ -1035,3 +1035,44 @@ def test_optimizers_walk_the_reference_iterates(env, golden):
     assert np.array_equal(PE.permutations_MAP_logP_and_parameters_values, g['ms_perm_array'])
     assert np.array_equal(PE.listOfPermutations, g['ms_list'])
     assert open('logs_and_csvs/multistart_log_file.txt', 'rb').read() == bytes(g['ms_log'])
+
+
+def test_multistart_of_metropolis_hastings_runs(env):
+    """doMultiStart(searchType='doMetropolisHastings') (IP.py:865-879, 975-990): every start point is one chain of a single
+    launch.  The oracle replays each chain with the kernel's own draws (step for step), picks the best start with the
+    reference's strict '>' rule and filters its rows twice, as the reference does with bestResultSoFar."""
+    PEUQSE, orc, _, _ = env
+    from peuqse_b200.mcmc import mh_launch, step_cholesky
+    settings = {'mcmc_length': 400, 'mcmc_burn_in': 50, 'mcmc_relative_step_length': 0.1, 'mcmc_random_seed': 3,
+                'mcmc_info_gain_returned': 'log_ratio', 'multistart_searchType': 'doMetropolisHastings',
+                'multistart_initialPointsDistributionType': 'grid', 'multistart_gridsearchSamplingInterval': [60, 120],
+                'multistart_gridsearchSamplingRadii': [1, 1], 'multistart_keep_cumulative_post_burn_in_data': True,
+                'responses_abscissa': X00}
+    PE = make_pe(PEUQSE, PEUQSE.QuadraticModel(X00), Y00, S00, [200, 500], [100, 200], settings=settings)
+    best = PE.doMultiStart()
+    pts = PE.listOfPermutations
+    assert pts.shape == (9, 2) and np.array_equal(pts[0], [200., 500.])
+    raw = mh_launch(PE, pts, 400, 50, 3, step_cholesky(PE.Q_covmat, 0.1), export_draws=True)
+    P = orc.build_problem([200, 500], [100, 200], Y00, S00)
+    _, bt = orc.sim_quadratic(X00)
+    ref = orc.mh_chains_batch(P, pts, raw['deltas'].cpu().numpy(), raw['us'].cpu().numpy(), bt)
+    assert np.array_equal(raw['samples'].cpu().numpy(), ref['samples'])
+    post_lp = ref['logP'][50:]                                                  # [rows, starts]
+    maps = post_lp.max(axis=0)
+    i = int(np.argmax(maps))
+    arr = PE.permutations_MAP_logP_and_parameters_values
+    assert np.array_equal(arr[:, 0], maps)
+    for c in range(9):
+        assert np.array_equal(arr[c, 1:], ref['samples'][50:, c][int(np.argmax(post_lp[:, c]))])
+    with np.errstate(all='ignore'):
+        st = orc.post_burn_in_statistics_filtered(ref['samples'][50:, i], ref['logP'][50:, i], ref['log_priors'][50:, i])
+        st = orc.post_burn_in_statistics_filtered(st['samples'], st['logP'], st['log_priors'])
+    assert np.array_equal(best[5], st['samples']) and np.array_equal(best[0], st['map_parameter_set'])
+    np.testing.assert_allclose(best[1], st['mu_AP'], rtol=1e-12)
+    np.testing.assert_allclose(best[2], st['stdap'], rtol=1e-12)
+    np.testing.assert_allclose(best[4], st['info_gain_log_ratio'], rtol=1e-11)
+    assert PE.cumulative_post_burn_in_samples.shape == (9 * 350, 2)
+    assert np.array_equal(PE.cumulative_post_burn_in_samples[350 * 4:350 * 5], ref['samples'][50:, 4])
+    log = open('logs_and_csvs/multistart_log_file.txt').read()
+    assert f"highest_MAP_initial_point_index: {i}" in log and "(for the above initial point)" in log
+    assert np.array_equal(PE.UserInput.InputParameterInitialGuess, [200., 500.])
