@@ -92,6 +92,7 @@ parameter_estimation_settings = {
     'multistart_keep_cumulative_post_burn_in_data': False,
     'multistart_exportLog': False,
     # ---- additions of this engine (absent keys in a reference UserInput mean the defaults below)
+    'multistart_batched_optimizer': True,   # Nelder-Mead multistarts advance all start points in lock step (peuqse_b200/optimize.py)
     'export_max_rows': 1_000_000,      # sample / point arrays with more rows than this are not written to file
     'mcmc_nchains': 1,                 # independent MH chains advanced by one kernel (reference: one per MPI rank)
     'mcmc_store_samples': 'auto',      # 'auto': keep every row while it fits comfortably in device memory

@@ -413,7 +413,24 @@ class parameter_estimation:
         self._list_of_permutations = pts
         highest, R, rows = float('-inf'), SweepResult(), []
         R.total, R.map_index, R.statistics, R.optimizer = len(pts), -1, False, True
-        for i, p in enumerate(pts):
+        args = dict(passThroughArgs)
+        batched = (str(args.get('method', '')).lower() == 'nelder-mead' and set(args) <= {'method', 'printOptimum', 'verbose', 'maxiter'}
+                   and bool(self.UserInput.parameter_estimation_settings.get('multistart_batched_optimizer', True)) and len(pts) > 0)
+        if batched:
+            # every start point's simplex advances in lock step: one launch of the log-posterior kernel per Nelder-Mead stage
+            from .optimize import nelder_mead_batch
+            res = nelder_mead_batch(lambda q: (-1 * self.getLogP_batch(q)).cpu().numpy(), pts,
+                                    maxiter=(args.get('maxiter', 0) or None))
+            self.multistart_optimizer_info = res
+            for i, p in enumerate(pts):
+                logp = -1.0 * res['fun'][i]
+                if logp > highest:                                                                    # IP.py:933
+                    highest, R.map_index, R.map_parameter_set, R.initial_point = float(logp), i, np.copy(res['x'][i]), p
+                rows.append(np.hstack((logp, res['x'][i])))                                           # IP.py:947
+            pts_loop = []
+        else:
+            pts_loop = pts
+        for i, p in enumerate(pts_loop):
             self.UserInput.InputParameterInitialGuess = p                                             # IP.py:858
             if searchType == 'doOptimizeLogP':
                 x, logp = self.doOptimizeLogP(**passThroughArgs)

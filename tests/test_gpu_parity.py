@@ -1035,6 +1035,18 @@ def test_optimizers_walk_the_reference_iterates(env, golden):
     assert np.array_equal(PE.permutations_MAP_logP_and_parameters_values, g['ms_perm_array'])
     assert np.array_equal(PE.listOfPermutations, g['ms_list'])
     assert open('logs_and_csvs/multistart_log_file.txt', 'rb').read() == bytes(g['ms_log'])
+    assert PE.multistart_optimizer_info['launches'] < 400          # the 9 start points advanced in lock step
+    # 64 uniform start points: lock-step batch == one scipy run per start point (multistart_batched_optimizer False)
+    res = {}
+    for flag in (True, False):
+        PE = make_pe(PEUQSE, PEUQSE.QuadraticModel(X00), Y00, S00, [200, 500], [100, 200],
+                     settings={'multistart_initialPointsDistributionType': 'uniform', 'multistart_numStartPoints': 64,
+                               'multistart_searchType': 'doOptimizeLogP', 'multistart_batched_optimizer': flag, 'exportLog': False,
+                               'multistart_passThroughArgs': {'method': 'Nelder-Mead', 'printOptimum': False, 'verbose': False}})
+        best = PE.doMultiStart()
+        res[flag] = (best[0], PE.map_logP, PE.map_index, PE.permutations_MAP_logP_and_parameters_values)
+    assert np.array_equal(res[True][0], res[False][0]) and res[True][1] == res[False][1] and res[True][2] == res[False][2]
+    assert np.array_equal(res[True][3], res[False][3])
 
 
 def test_multistart_of_metropolis_hastings_runs(env):

@@ -289,3 +289,22 @@ def test_export_multistart_matches_reference_files(golden, tmp_path):
     txt = open('logs_and_csvs/multistart_log_file.txt').read()
     assert txt.startswith(bytes(g['ms__logs_and_csvs__multistart_log_file.txt']).decode())
     assert "self.mu_AP_parameter_set : " + str(g['ms_state__mu_AP']) in txt and "self.stdap_parameter_set : " in txt
+
+
+def test_lockstep_nelder_mead_equals_scipy():
+    """peuqse_b200/optimize.py restates scipy's _minimize_neldermead for many start points at once: same optimum, same
+    function value, same iteration and evaluation counts as a stand-alone scipy run of every start point, including runs cut
+    short by maxiter and by the default evaluation budget."""
+    import scipy.optimize
+    from peuqse_b200.optimize import nelder_mead_batch
+    rng = np.random.default_rng(0)
+
+    def rosen(x):
+        return 100 * (x[1] - x[0] ** 2) ** 2 + (1 - x[0]) ** 2 + (0 if len(x) < 3 else np.sum((x[2:] - 0.3) ** 4))
+    for N, B, kw in ((2, 30, {}), (3, 12, {}), (2, 8, {'maxiter': 17}), (4, 6, {})):
+        X0 = rng.normal(0, 2, (B, N))
+        X0[0, 0] = 0.0                                   # a zero coordinate takes the absolute initial step
+        r = nelder_mead_batch(lambda P: np.array([rosen(p) for p in P]), X0, **kw)
+        for i in range(B):
+            s = scipy.optimize.minimize(rosen, X0[i], method='Nelder-Mead', options=({'maxiter': kw['maxiter']} if kw else None))
+            assert np.array_equal(s.x, r['x'][i]) and s.fun == r['fun'][i] and s.nit == r['nit'][i] and s.nfev == r['nfev'][i]
