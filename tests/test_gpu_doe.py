@@ -252,3 +252,50 @@ def test_scenarios_with_many_observations_tpd(env, golden):
         one = mh_launch(PE1, np.tile(truth, (2, 1)), 60, 10, 5, chol)
         assert np.array_equal(run['samples'][:, 2 * s:2 * s + 2].cpu().numpy(), one['samples'].cpu().numpy())
         assert np.array_equal(run['logp'][:, 2 * s:2 * s + 2].cpu().numpy(), one['logp'].cpu().numpy())
+
+
+def test_scenario_statistics_edge_cases(env):
+    """peuqse_scenarios_stats on hand-made MH-layout arrays: non-negative and NaN logP (the 'auto' threshold becomes NaN and
+    nothing is removed, IP.py:1894-1915 with arrayThresholdFilter's NaN comparisons), -inf log-priors (infinite ratios count
+    as 0, IP.py:1801), identical logP values, two chains per scenario and three (the one-CTA-per-scenario shape)."""
+    PEUQSE, orc, _, torch = env
+    from peuqse_b200 import _lib
+    L = _lib.load()
+    rng = np.random.default_rng(8)
+    for cps in (2, 3):
+        S, R, k, burn = 6, 300, 3, 20
+        C = S * cps
+        smp = rng.normal([1.0, -50.0, 3e3], [0.5, 4.0, 100.0], size=(R, C, k))
+        lp = -0.5 * rng.chisquare(3, size=(R, C)) - 40.0
+        pr = -1.0 - 0.1 * rng.random((R, C))
+        lp[100, 1 * cps] = 0.5                      # scenario 1: a positive logP
+        lp[150, 2 * cps + 1] = np.nan               # scenario 2: a NaN
+        pr[60:70, 3 * cps] = -np.inf                # scenario 3: -inf priors
+        lp[:, 4 * cps:5 * cps] = -41.25             # scenario 4: identical values
+        lp[30, 5 * cps] = -1e4                      # scenario 5: one far outlier (removed by 'auto' and by 'MAP')
+        d_smp, d_lp, d_pr = (torch.as_tensor(a).cuda().contiguous() for a in (smp, lp, pr))     # kept alive across the launches
+        lay = _lib.scen_stats_layout(k)
+        for mode, bench in ((_lib.FILTER_AUTO, 'auto'), (_lib.FILTER_MAP, 'MAP'), (_lib.FILTER_NONE, None)):
+            out = torch.empty((S, lay['DOUBLES']), dtype=torch.float64, device='cuda')
+            _lib.check(L.peuqse_scenarios_stats(k, mode, 2.0, S, cps, R, burn, _lib.ptr(d_smp), _lib.ptr(d_lp), _lib.ptr(d_pr),
+                                                _lib.ptr(out), _lib.current_stream()))
+            got = out.cpu().numpy()
+            for s in range(S):
+                if s == 2 and mode != _lib.FILTER_AUTO:
+                    continue                         # python's max() over a NaN is order dependent: only the 'auto' rule is defined
+                cols = slice(s * cps, (s + 1) * cps)
+                flat = lambda a: np.moveaxis(a[burn:, cols], 1, 0).reshape((R - burn) * cps, *a.shape[2:])
+                with np.errstate(all='ignore'):
+                    st = orc.post_burn_in_statistics_filtered(flat(smp), flat(lp), flat(pr), benchmark=bench or 'auto', coef=2.0,
+                                                              filter_samples=bench is not None)
+                assert int(got[s, lay['N_KEPT']]) == st['samples'].shape[0], (cps, bench, s)
+                np.testing.assert_allclose(got[s, lay['MU_AP']:lay['MU_AP'] + k], st['mu_AP'], rtol=1e-12)
+                if s == 2:
+                    continue
+                np.testing.assert_allclose(got[s, lay['STDAP']:lay['STDAP'] + k], st['stdap'], rtol=1e-10)
+                assert int(got[s, lay['MAP_INDEX']]) == st['map_index'] and got[s, lay['MAP_LOGP']] == st['map_logP']
+                np.testing.assert_allclose(got[s, lay['EVIDENCE']], st['evidence'], rtol=1e-12)
+                np.testing.assert_allclose(got[s, lay['INFO_GAIN_LOG_RATIO']], st['info_gain_log_ratio'], rtol=1e-11)
+            if mode == _lib.FILTER_AUTO:
+                assert int(got[1, lay['N_KEPT']]) == (R - burn) * cps        # NaN threshold: nothing removed
+                assert int(got[5, lay['N_KEPT']]) < (R - burn) * cps         # the far outlier is gone

@@ -1088,3 +1088,28 @@ def test_multistart_of_metropolis_hastings_runs(env):
     log = open('logs_and_csvs/multistart_log_file.txt').read()
     assert f"highest_MAP_initial_point_index: {i}" in log and "(for the above initial point)" in log
     assert np.array_equal(PE.UserInput.InputParameterInitialGuess, [200., 500.])
+
+
+def test_geweke_short_and_single_column_chains(env):
+    """Chains too short for the early windows give NaN scores there (slices of fewer than three rows) and the later windows
+    still agree with the oracle; a single chain with a single parameter; a window list given by the caller."""
+    import warnings
+    PEUQSE, orc, _, torch = env
+    from peuqse_b200.diagnostics import geweke_z_scores
+    rng = np.random.default_rng(4)
+    x = np.cumsum(rng.standard_normal((260, 1, 1)), axis=0) * 0.1 + rng.standard_normal((260, 1, 1))
+    z, windows, _ = geweke_z_scores(x)
+    z = z.cpu().numpy()
+    assert z.shape == (1, 1, 20, 20) and np.array_equal(windows, np.linspace(0, 260, 21).astype(int)[1:])
+    assert np.isnan(z[0, 0, 0]).all()                # 13 rows: every early slice holds a single row
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        for w in (9, 14, 19):
+            np.testing.assert_allclose(z[0, 0, w], orc.geweke_diagnostic(x[:windows[w], 0, 0])[:, 1], rtol=1e-7, equal_nan=True)
+        z2, w2, _ = geweke_z_scores(torch.as_tensor(x).cuda(), windows=[200, 260], initial_window=0.2, comparison_window=0.4, intervals=7)
+        z2 = z2.cpu().numpy()
+        assert z2.shape == (1, 1, 2, 7)
+        np.testing.assert_allclose(z2[0, 0, 0], orc.geweke_diagnostic(x[:200, 0, 0], 0.2, 0.4, 7)[:, 1], rtol=1e-7)
+        np.testing.assert_allclose(z2[0, 0, 1], orc.geweke_diagnostic(x[:260, 0, 0], 0.2, 0.4, 7)[:, 1], rtol=1e-7)
+    with pytest.raises(ValueError):
+        geweke_z_scores(x, initial_window=0.6, comparison_window=0.5)
