@@ -438,6 +438,7 @@ int peuqse_mh_run_scenarios(const peuqse_problem* p, const peuqse_scenarios* sc,
 #define PEUQSE_SCEN_STATS_MAP_INDEX 4        /* as a double: row of the first maximum among the kept rows */
 #define PEUQSE_SCEN_STATS_EVIDENCE 5
 #define PEUQSE_SCEN_STATS_INFO_GAIN_LOG_RATIO 6
+#define PEUQSE_SCEN_STATS_CUT 7              /* a row was removed iff logP < cut (-inf: nothing removed) */
 #define PEUQSE_SCEN_STATS_MU_AP 8            /* [k] */
 #define PEUQSE_SCEN_STATS_STDAP(k) (8 + (k))        /* [k] */
 #define PEUQSE_SCEN_STATS_MAP_THETA(k) (8 + 2 * (k)) /* [k] */
@@ -445,6 +446,13 @@ int peuqse_mh_run_scenarios(const peuqse_problem* p, const peuqse_scenarios* sc,
 int peuqse_scenarios_stats(int32_t k, int32_t filter, double coef, int64_t n_scenarios, int64_t chains_per_scenario,
                            int64_t n_rows, int64_t first_row, const double* d_samples, const double* d_logp,
                            const double* d_logprior, double* d_out, void* stream);
+
+/* per-scenario KL-divergence information gain (calculateInfoGain, IP.py:1772-1791) after peuqse_scenarios_stats: the kept
+ * rows (logP >= d_stats[s][PEUQSE_SCEN_STATS_CUT]) and d_prior_samples[n_prior][k] (samples_of_prior, IP.py:194, shared by all
+ * scenarios) are binned on each scenario's joint edges with np.histogram semantics; d_out[S][1 + k] = total, then each parameter */
+int peuqse_scenarios_kl(int32_t k, int32_t bins, int64_t n_scenarios, int64_t chains_per_scenario, int64_t n_rows,
+                        int64_t first_row, const double* d_samples, const double* d_logp, const double* d_prior_samples,
+                        int64_t n_prior, const double* d_stats, double* d_out, void* stream);
 
 /*
  * Geweke convergence diagnostic of many chains at once.  replaces: geweke_diagnostic (IP.py:4012-4062) called per window,

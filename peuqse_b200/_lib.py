@@ -64,7 +64,7 @@ STATS = dict(N_TOTAL=0, N_KEPT=1, CUT=2, THRESHOLD=3, MEAN_LOGNEG=4, STD_LOGNEG=
 
 # offsets inside one scenario's statistics block (PEUQSE_SCEN_STATS_* macros)
 def scen_stats_layout(k):
-    return dict(N_TOTAL=0, N_KEPT=1, THRESHOLD=2, MAP_LOGP=3, MAP_INDEX=4, EVIDENCE=5, INFO_GAIN_LOG_RATIO=6, MU_AP=8, STDAP=8 + k,
+    return dict(N_TOTAL=0, N_KEPT=1, THRESHOLD=2, MAP_LOGP=3, MAP_INDEX=4, EVIDENCE=5, INFO_GAIN_LOG_RATIO=6, CUT=7, MU_AP=8, STDAP=8 + k,
                 MAP_THETA=8 + 2 * k, DOUBLES=8 + 3 * k)
 
 
@@ -98,7 +98,7 @@ EXPORTS = [
     "peuqse_stats_work_bytes", "peuqse_stats_begin", "peuqse_stats_finish", "peuqse_stats_compact",
     "peuqse_scenarios_create", "peuqse_scenarios_destroy", "peuqse_scenarios_synthesize", "peuqse_scenarios_set_observed",
     "peuqse_scenarios_logp", "peuqse_mh_run_scenarios", "peuqse_scenarios_stats",
-    "peuqse_geweke_work_bytes", "peuqse_geweke",
+    "peuqse_geweke_work_bytes", "peuqse_geweke", "peuqse_scenarios_kl",
 ]
 
 _lib = None
@@ -173,6 +173,7 @@ def load():
     L.peuqse_scenarios_logp.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp]
     L.peuqse_mh_run_scenarios.argtypes = [vp, vp, C.POINTER(MHSpec), i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.peuqse_scenarios_stats.argtypes = [i32, i32, dbl, i64, i64, i64, i64, vp, vp, vp, vp, vp]
+    L.peuqse_scenarios_kl.argtypes = [i32, i32, i64, i64, i64, i64, vp, vp, vp, i64, vp, vp, vp]
     L.peuqse_geweke_work_bytes.restype = i64
     L.peuqse_geweke_work_bytes.argtypes = [i64, i64, i32]
     L.peuqse_geweke.argtypes = [vp, i64, i64, vp, vp, i32, vp, i32, vp, vp, vp]

@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(SS_THREADS) k_scen_stats(const double* __restr
         o[PEUQSE_SCEN_STATS_MAP_INDEX] = nbefore;
         o[PEUQSE_SCEN_STATS_EVIDENCE] = evidence;
         o[PEUQSE_SCEN_STATS_INFO_GAIN_LOG_RATIO] = lprior ? ig : __longlong_as_double(0x7ff8000000000000LL);
-        o[7] = 0.0;
+        o[PEUQSE_SCEN_STATS_CUT] = cut;
         const long long maprow = nk > 0.0 ? T.mem_of_index(best.i) : 0;
 #pragma unroll
         for (int d = 0; d < KT; ++d)
@@ -343,6 +343,110 @@ __global__ void __launch_bounds__(SS_THREADS) k_scen_stats(const double* __restr
                 o[PEUQSE_SCEN_STATS_STDAP(k) + d] = sd[d];
                 o[PEUQSE_SCEN_STATS_MAP_THETA(k) + d] = samples[maprow * k + d];
             }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// per-scenario KL-divergence information gain (calculateInfoGain, IP.py:1772-1791): one CTA per scenario bins the kept
+// posterior rows and the (shared) prior samples on that scenario's joint edges, np.histogram semantics, density=True
+// ---------------------------------------------------------------------------------------------------
+#define SK_MAXBINS 128
+
+// np.histogram bin of x (numpy/lib/_histograms_impl.py), -1 outside [lo, hi]
+__device__ __forceinline__ int sk_hist_bin(const double* __restrict__ ed, int nbins, double x) {
+    const double lo = ed[0], hi = ed[nbins];
+    if (!(x >= lo && x <= hi)) return -1;
+    int b = (int)(((x - lo) / (hi - lo)) * (double)nbins);
+    if (b >= nbins) b = nbins - 1;
+    if (b < 0) b = 0;
+    if (x < ed[b]) --b;
+    else if (b != nbins - 1 && x >= ed[b + 1]) ++b;
+    return b;
+}
+
+__global__ void __launch_bounds__(SS_THREADS) k_scen_kl(const double* __restrict__ samples, const double* __restrict__ logp,
+                                                        const ScenRows R, int k, int bins, const double* __restrict__ prior,
+                                                        long long n_prior, const double* __restrict__ stats, int stats_stride,
+                                                        double* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char sk_raw[];
+    double* s_edges = (double*)sk_raw;                                   // [k][bins + 1]
+    unsigned int* s_h0 = (unsigned int*)(s_edges + (size_t)k * (bins + 1));   // prior counts [k][bins]
+    unsigned int* s_h1 = s_h0 + (size_t)k * bins;                        // posterior counts
+    __shared__ double s_lo[PQ_MAXK][SS_WARPS], s_hi[PQ_MAXK][SS_WARPS];
+    __shared__ double s_each[PQ_MAXK];
+    const long long s = blockIdx.x;
+    const long long n = R.per * R.rows;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const double cut = stats[s * stats_stride + PEUQSE_SCEN_STATS_CUT];
+    auto mem = [&](long long i) {
+        const long long h = i / R.rows;
+        return (R.first_row + (i - h * R.rows)) * R.C + (s * R.per + h);
+    };
+    for (int a = t; a < 2 * k * bins; a += SS_THREADS) s_h0[a] = 0u;
+    // joint range of the kept posterior rows and the prior samples, per parameter
+    for (int d = 0; d < k; ++d) {
+        double lo = pq_pos_inf(), hi = pq_neg_inf();
+        for (long long i = t; i < n; i += SS_THREADS) {
+            const long long row = mem(i);
+            if (logp[row] < cut) continue;
+            const double v = samples[row * k + d];
+            lo = fmin(lo, v); hi = fmax(hi, v);
+        }
+        for (long long i = t; i < n_prior; i += SS_THREADS) {
+            const double v = prior[i * k + d];
+            lo = fmin(lo, v); hi = fmax(hi, v);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+            hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+        }
+        if (lane == 0) { s_lo[d][w] = lo; s_hi[d][w] = hi; }
+    }
+    __syncthreads();
+    for (int d = 0; d < k; ++d) {
+        double lo = s_lo[d][0], hi = s_hi[d][0];
+        for (int q = 1; q < SS_WARPS; ++q) { lo = fmin(lo, s_lo[d][q]); hi = fmax(hi, s_hi[d][q]); }
+        if (!(hi > lo)) { lo = lo - 0.5; hi = hi + 0.5; }               // np.histogram widens an empty range by +-0.5
+        const double step = (hi - lo) / (double)bins;                    // np.linspace(lo, hi, bins + 1)
+        for (int i = t; i <= bins; i += SS_THREADS) s_edges[d * (bins + 1) + i] = (i == bins) ? hi : ((double)i * step + lo);
+    }
+    __syncthreads();
+    for (long long i = t; i < n; i += SS_THREADS) {
+        const long long row = mem(i);
+        if (logp[row] < cut) continue;
+        for (int d = 0; d < k; ++d) {
+            const int b = sk_hist_bin(s_edges + d * (bins + 1), bins, samples[row * k + d]);
+            if (b >= 0) atomicAdd(&s_h1[d * bins + b], 1u);
+        }
+    }
+    for (long long e = t; e < n_prior * k; e += SS_THREADS) {
+        const int d = (int)(e % k);
+        const int b = sk_hist_bin(s_edges + d * (bins + 1), bins, prior[e]);
+        if (b >= 0) atomicAdd(&s_h0[d * bins + b], 1u);
+    }
+    __syncthreads();
+    if (t < k) {
+        const int d = t;
+        const double* ed = s_edges + d * (bins + 1);
+        double n0 = 0.0, n1 = 0.0;
+        for (int b = 0; b < bins; ++b) { n0 += (double)s_h0[d * bins + b]; n1 += (double)s_h1[d * bins + b]; }
+        double acc = 0.0;
+        for (int b = 0; b < bins; ++b) {
+            const double db = ed[b + 1] - ed[b];
+            const double d0 = (double)s_h0[d * bins + b] / db / n0;      // counts / db / counts.sum()
+            const double d1 = (double)s_h1[d * bins + b] / db / n1;
+            const double v = d1 * log(d1 / d0);                          // IP.py:1785
+            if (v == v && fabs(v) < pq_pos_inf()) acc += v;              // np.isfinite filter (IP.py:1786-1787)
+        }
+        s_each[d] = acc;
+        out[s * (1 + k) + 1 + d] = acc;
+    }
+    __syncthreads();
+    if (t == 0) {
+        double tot = 0.0;
+        for (int d = 0; d < k; ++d) tot = tot + s_each[d];               // IP.py:1789
+        out[s * (1 + k)] = tot;
     }
 }
 
@@ -480,6 +584,22 @@ extern "C" int peuqse_scenarios_stats(int32_t k, int32_t filter, double coef, in
     else k_scen_stats<KT, CtaPerScenario><<<(unsigned)n_scenarios, SS_THREADS, 0, st>>>(d_samples, d_logp, d_logprior, R, k, filter, coef, d_out)
     PQ_DISPATCH_K(pq_k_bucket(k), SSTAT, 0)
 #undef SSTAT
+    PQ_CUDA_OK(cudaGetLastError());
+    return PEUQSE_OK;
+}
+
+extern "C" int peuqse_scenarios_kl(int32_t k, int32_t bins, int64_t n_scenarios, int64_t chains_per_scenario, int64_t n_rows,
+                                   int64_t first_row, const double* d_samples, const double* d_logp, const double* d_prior_samples,
+                                   int64_t n_prior, const double* d_stats, double* d_out, void* stream) {
+    if (!d_samples || !d_logp || !d_prior_samples || !d_stats || !d_out) return pq_set_error(PEUQSE_ERR_INVALID, "null argument");
+    if (k < 1 || k > PEUQSE_MAX_K || bins < 1 || bins > SK_MAXBINS || n_scenarios < 1 || chains_per_scenario < 1 || first_row < 0 ||
+        n_rows <= first_row || n_prior < 1)
+        return pq_set_error(PEUQSE_ERR_INVALID, "bad sizes");
+    ScenRows R;
+    R.C = n_scenarios * chains_per_scenario; R.per = chains_per_scenario; R.rows = n_rows - first_row; R.first_row = first_row;
+    const size_t smem = (size_t)k * (bins + 1) * sizeof(double) + 2 * (size_t)k * bins * sizeof(unsigned int);
+    k_scen_kl<<<(unsigned)n_scenarios, SS_THREADS, smem, (cudaStream_t)stream>>>(d_samples, d_logp, R, k, bins, d_prior_samples, n_prior,
+                                                                                d_stats, PEUQSE_SCEN_STATS_DOUBLES(k), d_out);
     PQ_CUDA_OK(cudaGetLastError());
     return PEUQSE_OK;
 }

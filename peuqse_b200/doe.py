@@ -103,6 +103,18 @@ class ScenarioBatch:
                                                   int(burn_in), _lib.ptr(run['samples']), _lib.ptr(run['logp']),
                                                   _lib.ptr(run['logprior']), _lib.ptr(out), _lib.current_stream()))
         self.pe.gpu_launches += 1
+        self._d_stats = out
+        return out.cpu().numpy()
+
+    def kl_information_gain(self, run, burn_in, prior_samples, bins=100):
+        """KL-divergence information gain of every scenario (after statistics()): host array [S, 1 + k] = total, each parameter."""
+        k = self.pe.k
+        pri = torch.as_tensor(np.ascontiguousarray(np.asarray(prior_samples, dtype=float))).to(_dev()).reshape(-1, k).contiguous()
+        out = torch.empty((self.S, 1 + k), dtype=torch.float64, device=_dev())
+        _lib.check(self._L.peuqse_scenarios_kl(k, int(bins), self.S, run['chains_per_scenario'], run['samples'].shape[0], int(burn_in),
+                                               _lib.ptr(run['samples']), _lib.ptr(run['logp']), _lib.ptr(pri), pri.shape[0],
+                                               _lib.ptr(self._d_stats), _lib.ptr(out), _lib.current_stream()))
+        self.pe.gpu_launches += 1
         return out.cpu().numpy()
 
     def close(self):
@@ -186,20 +198,13 @@ def run_info_gain_matrices(pe, modulations, searchType='doMetropolisHastings'):
         batch = ScenarioBatch(pe, all_conds[s0:s0 + sn], all_true[s0:s0 + sn])
         run = batch.run_mh(np.asarray(UI.InputParameterInitialGuess, dtype=float), Lm, burn, seed, chol, chains_per_scenario=cps,
                            modulate=float(pes['mcmc_modulate_accept_probability']))
+        stats_rows = batch.statistics(run, burn, mode, coef)
         if not want_kl:
-            stats_rows = batch.statistics(run, burn, mode, coef)
             gains = stats_rows[:, _lib.scen_stats_layout(pe.k)['INFO_GAIN_LOG_RATIO']].copy()
         else:
-            # the KL form bins prior and posterior samples on scenario-specific joint edges: the streaming statistics
-            # kernels (csrc/stats.cu) scenario by scenario, every array staying on the device
-            for j in range(sn):
-                sl = slice(j * cps, (j + 1) * cps)
-                flat = lambda t: t[burn:, sl].permute(1, 0, *range(2, t.ndim)).reshape(-1, *t.shape[2:]).contiguous()
-                Rs = ST.device_statistics(flat(run['samples']), flat(run['logp']), flat(run['logprior']), mode, coef,
-                                          prior_samples=pe.samples_of_prior, kl_bins=100)
-                pe.gpu_launches += Rs.gpu_launches
-                gains[j] = Rs.info_gain_KL
-                each[j] = Rs.info_gain_KL_each_parameter
+            # the KL form bins prior and posterior samples on scenario-specific joint edges: one CTA per scenario (k_scen_kl)
+            kl = batch.kl_information_gain(run, burn, pe.samples_of_prior, bins=100)
+            gains, each = kl[:, 0].copy(), kl[:, 1:].copy()
         pe.responses_observed_last_scenario = batch.observed[-1].cpu().numpy()
         pe._doe_batch, pe._doe_run = batch, run
     if size > 1:

@@ -72,6 +72,12 @@ st = d_st.cpu().numpy()                                         # the batch's wh
 ev[3].record()
 torch.cuda.synchronize()
 mh_ms, st_ms, d2h_ms = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2]), ev[2].elapsed_time(ev[3])
+batch._d_stats = d_st
+kl = batch.kl_information_gain(run, LEN // 10, PE.samples_of_prior)                   # warm-up
+ka, kb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+ka.record()
+kl = batch.kl_information_gain(run, LEN // 10, PE.samples_of_prior)
+kb.record(); torch.cuda.synchronize()
 rows = S * (LEN - LEN // 10)
 out['large'] = dict(scenarios=S, steps=LEN, mh_ms=mh_ms, stats_ms=st_ms, readback_ms=d2h_ms, readback_bytes=S * lay['DOUBLES'] * 8, chain_steps_per_s=S * LEN / (mh_ms * 1e-3),
                     sample_bytes_written=S * LEN * 5 * 8, mh_write_GBps=S * LEN * 5 * 8 / (mh_ms * 1e-3) / 1e9,
@@ -79,7 +85,8 @@ out['large'] = dict(scenarios=S, steps=LEN, mh_ms=mh_ms, stats_ms=st_ms, readbac
                     stats_algorithmic_GBps=rows * (8 + 24 + 32) / (st_ms * 1e-3) / 1e9,   # logP | logP + theta | logP + theta + logPrior
                     accept_rate=float(run['stats'][:, 0].mean().item()) / (LEN - 1),
                     info_gain_range=[float(st[:, 6].min()), float(st[:, 6].max())],
-                    e2e_chain_steps_per_s=S * LEN / ((mh_ms + st_ms + d2h_ms) * 1e-3))
+                    e2e_chain_steps_per_s=S * LEN / ((mh_ms + st_ms + d2h_ms) * 1e-3),
+                    kl_ms=ka.elapsed_time(kb), kl_range=[float(kl[:, 0].min()), float(kl[:, 0].max())])
 
 from oracle import peuqse_oracle as orc
 from oracle import philox_np
