@@ -106,10 +106,25 @@ def run_metropolis_hastings(pe, calculatePostBurnInStatistics=True, continueSamp
     first_step = 0
     if continueSampling:
         burn = 0                                                                                     # IP.py:2601-2602
+        if hasattr(pe, 'mcmc_last_point_sampled'):
+            pe.last_post_burn_in_log_posteriors_un_normed_vec = np.array(pe.post_burn_in_log_posteriors_un_normed_vec)
+            pe.last_post_burn_in_samples = np.array(pe.post_burn_in_samples)
+            first_step = getattr(pe, '_mh_steps_done', 0)
+        else:
+            # a fresh object continues the run an earlier process exported (IP.py:2583-2596): rows of
+            # pickles/mcmc_logP_and_parameter_samples.pkl, start = its last row, initial guess from its pickle
+            from .export import unpickleAnObject
+            data = np.atleast_2d(np.asarray(unpickleAnObject(UI.directories['pickles'] + "mcmc_logP_and_parameter_samples"), dtype=float))
+            pe.last_post_burn_in_log_posteriors_un_normed_vec = data[:, 0:1].copy()
+            pe.last_post_burn_in_samples = data[:, 1:].copy()
+            pe.mcmc_last_point_sampled = pe.last_post_burn_in_samples[-1]
+            UI.InputParameterInitialGuess = unpickleAnObject(UI.directories['pickles'] + "mcmc_initial_point_parameters")
+            pe.post_burn_in_samples, pe.post_burn_in_log_posteriors_un_normed_vec = pe.last_post_burn_in_samples, pe.last_post_burn_in_log_posteriors_un_normed_vec
+            # the draws of the earlier process are not known here: a stream offset far beyond any exported run keeps them disjoint
+            first_step = int(pes.get('mcmc_continue_first_step', 1 << 24))
         start = np.asarray(pe.mcmc_last_point_sampled, dtype=float).reshape(-1, pe.k)
-        pe.last_post_burn_in_log_posteriors_un_normed_vec = np.array(pe.post_burn_in_log_posteriors_un_normed_vec)
-        pe.last_post_burn_in_samples = np.array(pe.post_burn_in_samples)
-        first_step = getattr(pe, '_mh_steps_done', 0)
+        if start.shape[0] != Cn:
+            start = np.tile(start[-1], (Cn, 1))
     else:
         start = np.tile(np.asarray(UI.InputParameterInitialGuess, dtype=float), (Cn, 1))              # IP.py:2610
     seed = pes.get('mcmc_random_seed')

@@ -908,6 +908,14 @@ def test_on_disk_formats_round_trip(env, golden):
     # the last point of this run, by file name, as the start of a new object (IP.py:355-380)
     PE4 = make_pe(PEUQSE, PEUQSE.QuadraticModel(X00), Y00, S00, [200, 500], [100, 200], InputParameterInitialGuess='mcmc_last_point_sampled.pkl')
     assert np.array_equal(PE4.UserInput.InputParameterInitialGuess, PE.mcmc_last_point_sampled)
+    # a fresh object continues the exported run (mcmc_continueSampling = True reads the pickles, IP.py:2583-2596)
+    PE5 = make_pe(PEUQSE, PEUQSE.QuadraticModel(X00), Y00, S00, [200, 500], [100, 200],
+                  settings={'mcmc_length': 300, 'mcmc_relative_step_length': 0.1, 'mcmc_random_seed': 0, 'mcmc_continueSampling': True,
+                            'mcmc_threshold_filter_samples': False, 'mcmc_info_gain_returned': 'log_ratio', 'mcmc_exportLog': False})
+    r5 = PE5.doMetropolisHastings()
+    n_old = PE.post_burn_in_samples.shape[0]
+    assert r5[5].shape == (n_old + 300, 2) and np.array_equal(r5[5][:n_old], PE.post_burn_in_samples)
+    assert np.array_equal(r5[5][n_old], PE.post_burn_in_samples[-1])         # row 0 of the continuation is the last exported row
     # a fresh object rebuilds the statistics from the files (the filter already ran: the kept rows are what was written)
     PE2 = make_pe(PEUQSE, PEUQSE.QuadraticModel(X00), Y00, S00, [200, 500], [100, 200],
                   settings={'mcmc_length': 800, 'mcmc_threshold_filter_samples': False, 'mcmc_info_gain_returned': 'log_ratio'})
