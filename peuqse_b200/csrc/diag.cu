@@ -19,7 +19,7 @@
 namespace {
 
 #define GW_THREADS 128
-#define GW_U 4
+#define GW_U 8
 
 struct GwGeom {
     long long R, CK, seg_len;
@@ -40,35 +40,44 @@ __global__ void __launch_bounds__(GW_THREADS) k_geweke_prefix(const double* __re
     double p2 = (t0 >= 2) ? x[(t0 - 2) * G.CK + col] - pivot : 0.0;       // x_{t-2}
     int j = seg_first[s];
     const int jend = seg_first[s + 1];
-    long long next = (j < jend) ? pos[j] : -1;
     const size_t qs = (size_t)G.nb * G.CK;
-    for (long long t = t0; t < t1; t += GW_U) {
-        double v[GW_U];
-#pragma unroll
-        for (int u = 0; u < GW_U; ++u) v[u] = (t + u < t1) ? x[(t + u) * G.CK + col] : 0.0;
-#pragma unroll
-        for (int u = 0; u < GW_U; ++u) {
-            if (t + u < t1) {
-                while (next == t + u) {                                   // record the sums over rows < t + u
-                    const size_t o = (size_t)j * G.CK + col;
-                    rec[o] = f0; rec[qs + o] = f2; rec[2 * qs + o] = h1; rec[3 * qs + o] = h2;
-                    ++j;
-                    next = (j < jend) ? pos[j] : -1;
-                }
-                const double xv = v[u] - pivot;
-                f0 += xv;
-                f2 = fma(xv, xv, f2);
-                if (t + u >= 1) h1 = fma(p1, xv, h1);
-                if (t + u >= 2) h2 = fma(p2, xv, h2);
-                p2 = p1; p1 = xv;
-            }
-        }
-    }
-    while (j < jend) {                                                    // position R: sums over every row
+    auto record = [&]() {                                                 // the sums over the rows before the current one
         const size_t o = (size_t)j * G.CK + col;
         rec[o] = f0; rec[qs + o] = f2; rec[2 * qs + o] = h1; rec[3 * qs + o] = h2;
         ++j;
+    };
+    // rows are walked in runs that end at the next recorded row, so the hot loop carries no position test: per element one
+    // load, one subtraction and four accumulations (x_{-1} = x_{-2} = 0 makes the first two lag products vanish)
+    const double* px = x + t0 * G.CK + col;
+    long long t = t0;
+    while (t < t1) {
+        while (j < jend && pos[j] == t) record();
+        const long long stop = (j < jend && pos[j] < t1) ? pos[j] : t1;
+        for (; t + GW_U <= stop; t += GW_U) {
+            double v[GW_U];
+#pragma unroll
+            for (int u = 0; u < GW_U; ++u) v[u] = px[(size_t)u * G.CK];
+            px += (size_t)GW_U * G.CK;
+#pragma unroll
+            for (int u = 0; u < GW_U; ++u) {
+                const double xv = v[u] - pivot;
+                f0 += xv;
+                f2 = fma(xv, xv, f2);
+                h1 = fma(p1, xv, h1);
+                h2 = fma(p2, xv, h2);
+                p2 = p1; p1 = xv;
+            }
+        }
+        for (; t < stop; ++t, px += G.CK) {
+            const double xv = *px - pivot;
+            f0 += xv;
+            f2 = fma(xv, xv, f2);
+            h1 = fma(p1, xv, h1);
+            h2 = fma(p2, xv, h2);
+            p2 = p1; p1 = xv;
+        }
     }
+    while (j < jend) record();                                            // position R: sums over every row
     const size_t ts = (size_t)G.n_seg * G.CK, o = (size_t)s * G.CK + col;
     tot[o] = f0; tot[ts + o] = f2; tot[2 * ts + o] = h1; tot[3 * ts + o] = h2;
 }
@@ -135,10 +144,23 @@ __global__ void __launch_bounds__(GW_THREADS) k_geweke_z(const double* __restric
     z[(size_t)zi * G.CK + col] = (A.mean - B.mean) / sqrt(A.sv / A.n + B.sv / B.n);     // IP.py:4056-4057
 }
 
+int gw_sm_count() {
+    static int sm = 0;
+    if (!sm) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm < 1) sm = 148;
+    }
+    return sm;
+}
+
+// rows are cut into as many segments as give ONE resident wave of CTAs (16 CTAs of 128 threads per SM at 32 registers): with
+// 2496 CTAs on 2368 slots the kernel ran a second, nearly empty wave
 GwGeom gw_geom(long long R, long long CK, int nb) {
     GwGeom G;
     G.R = R; G.CK = CK; G.nb = nb;
-    long long want = (300000 + CK - 1) / CK;                               // enough threads to keep ~4 rows x 300k loads in flight
+    const long long gx = (CK + GW_THREADS - 1) / GW_THREADS;
+    long long want = ((long long)gw_sm_count() * 16) / gx;
     want = std::max(1LL, std::min(want, 256LL));
     long long len = std::max(64LL, (R + want - 1) / want);
     len = (len + GW_U - 1) / GW_U * GW_U;

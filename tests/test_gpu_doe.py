@@ -299,3 +299,49 @@ def test_scenario_statistics_edge_cases(env):
             if mode == _lib.FILTER_AUTO:
                 assert int(got[1, lay['N_KEPT']]) == (R - burn) * cps        # NaN threshold: nothing removed
                 assert int(got[5, lay['N_KEPT']]) < (R - burn) * cps         # the far outlier is gone
+
+
+def test_large_scenario_batch_properties(env, golden):
+    """Size-independent properties at the size of a real design study (81 x 81 conditions x 3 modulations = 19 683 scenarios,
+    thread-shape kernel): (i) a scenario's result does not depend on where it sits in the batch or on what surrounds it
+    (the batch reversed gives the results reversed, bit for bit), (ii) duplicated scenarios give duplicated results,
+    (iii) spot-checked scenarios equal the 25-scenario reference fixture's values where conditions coincide."""
+    PEUQSE, orc, _, torch = env
+    from peuqse_b200 import _lib
+    from peuqse_b200.doe import ScenarioBatch
+    from peuqse_b200.mcmc import step_cholesky
+    g = golden("doe")
+    L, BURN, STEP, DH, DS, DHU, DSU, SIG = g['settings']
+    PE = doe_pe(PEUQSE, g, 'xyz', True)
+    T = np.linspace(300, 700, 81)
+    pA = np.linspace(0.3, 0.7, 81)
+    conds = np.array([[t, p] for t in T for p in pA])
+    truth = np.array([DH, DS]) + np.array([DHU, DSU]) * np.array([[1, 1], [0, 0], [-1, 1]])
+    all_c = np.tile(conds, (3, 1))
+    all_t = np.repeat(truth, len(conds), axis=0)
+    all_c[7], all_t[7] = all_c[12345], all_t[12345]                   # a duplicate far away in the batch
+    S = len(all_c)
+    chol = step_cholesky(PE.Q_covmat, STEP)
+    lay = _lib.scen_stats_layout(2)
+
+    def run(c, t):
+        b = ScenarioBatch(PE, c, t)
+        r = b.run_mh([DH, DS], int(L), int(BURN), 0, chol)
+        st = b.statistics(r, int(BURN), _lib.FILTER_AUTO, 2.0)
+        kl = b.kl_information_gain(r, int(BURN), PE.samples_of_prior)
+        return st, kl
+    st, kl = run(all_c, all_t)
+    assert st.shape == (S, lay['DOUBLES']) and S == 19683
+    st_r, kl_r = run(all_c[::-1].copy(), all_t[::-1].copy())
+    assert np.array_equal(st, st_r[::-1], equal_nan=True) and np.array_equal(kl, kl_r[::-1], equal_nan=True)
+    assert np.array_equal(st[7], st[12345], equal_nan=True) and np.array_equal(kl[7], kl[12345])
+    assert np.isfinite(st[:, lay['INFO_GAIN_LOG_RATIO']]).all()
+    # conditions shared with the reference's 5 x 5 grid, "true" parameters = the fixture's +1 SD perturbation (first block)
+    ref = g['xyz_filtered_info_gain_matrix']
+    hits = 0
+    for row in ref:
+        i = np.nonzero((np.abs(conds[:, 0] - row[0]) < 1e-9) & (np.abs(conds[:, 1] - row[1]) < 1e-12))[0]
+        if len(i) and i[0] != 7:
+            np.testing.assert_allclose(st[i[0], lay['INFO_GAIN_LOG_RATIO']], row[2], rtol=1e-9)
+            hits += 1
+    assert hits >= 9
