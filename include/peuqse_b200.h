@@ -468,6 +468,17 @@ int peuqse_geweke(const double* d_samples, int64_t n_rows, int64_t n_cols, const
                   const int64_t* d_positions, int32_t n_positions, const int32_t* d_slices, int32_t n_z, double* d_z,
                   void* d_work, void* stream);
 
+/*
+ * Integrated autocorrelation time, the layout step.  replaces: the y.reshape(-1) of the (walkers, steps) view inside
+ * zeus.autocorr.AutoCorrTime(samples[:n]) (method 'mk'; called per growing window at IP.py:3916-3930; zeus is a third-party
+ * dependency that the reference does not vendor).  d_samples[>= n_rows][n_chains][k] (row = step; only the first n_rows
+ * rows are read), d_mean[k]: mean of each parameter over those rows and chains.  d_series[k][series_stride]:
+ * series_d[c * n_rows + t] = samples[t][c][d] - mean[d], zero from n_rows * n_chains to series_stride (the padding of the
+ * FFT that follows).
+ */
+int peuqse_act_concat(const double* d_samples, int64_t n_rows, int64_t n_chains, int32_t k, const double* d_mean,
+                      double* d_series, int64_t series_stride, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -836,6 +836,63 @@ def geweke_convergence(chains):
 
 
 # --------------------------------------------------------------------------------------------
+# Convergence diagnostics: integrated autocorrelation time (IP.py:3914-3948) -- PARITY UNPINNED
+# --------------------------------------------------------------------------------------------
+def autocorr_func_1d(x, norm=True):
+    """zeus.autocorr._autocorr_func_1d (zeus-mcmc, pinned '>=2.4.0' only in the reference's setup.py extras, imported at
+    IP.py:3916; neither vendored by the reference nor installed here, so this is a restatement of the published routine --
+    the same one as in emcee's autocorrelation tutorial -- and parity is UNPINNED): autocorrelation function of a 1-D series
+    by FFT, zero-padded to twice the next power of two."""
+    x = np.atleast_1d(x)
+    if len(x.shape) != 1:
+        raise ValueError("invalid dimensions for 1D autocorrelation function")
+    n = 1
+    while n < len(x):
+        n <<= 1
+    f = np.fft.fft(x - np.mean(x), n=2 * n)
+    acf = np.fft.ifft(f * np.conjugate(f))[:len(x)].real
+    acf /= 4 * n
+    if norm:
+        acf /= acf[0]
+    return acf
+
+
+def auto_window(taus, c):
+    """Sokal's automated window: the first lag M with M >= c * tau(M).  np.argmin of a boolean vector is the first False --
+    and 0 when every entry is True (a chain too short for its window then reports tau = taus[0] = 1)."""
+    m = np.arange(len(taus)) < c * taus
+    if np.any(m):
+        return np.argmin(m)
+    return len(taus) - 1
+
+
+def autocorr_time(samples, c=5.0):
+    """zeus.autocorr.AutoCorrTime(samples[nsteps, nwalkers, ndim], c=5.0, method='mk') -> tau[ndim] (PARITY UNPINNED, see
+    autocorr_func_1d): per parameter the walkers' chains are laid end to end (walker-major), the normalised autocorrelation
+    function of that one series is truncated to the first nsteps lags, tau(M) = 2 * cumsum - 1 at the automated window."""
+    samples = np.asarray(samples, dtype=float)
+    nsteps, _, ndim = samples.shape
+    taus = np.empty(ndim)
+    for d in range(ndim):
+        y = samples[:, :, d].T                                             # (walkers, steps)
+        f = autocorr_func_1d(y.reshape((-1), order='C'))[:nsteps]
+        t = 2.0 * np.cumsum(f) - 1.0
+        taus[d] = t[auto_window(t, c)]
+    return taus
+
+
+def autocorr_time_convergence(chains):
+    """The autocorrelation half of calculateAndPlotConvergenceDiagnostics (IP.py:3918-3948) for chains[R, C, k]: taus[20, k]
+    over windows growing on a log scale, the final row, and the product over parameters per window (IP.py:3936-3944)."""
+    with np.errstate(all='ignore'):
+        windows = np.exp(np.linspace(0, np.log(chains.shape[0]), 21)).astype(int)[1:]          # IP.py:3918
+        taus = np.empty((len(windows), chains.shape[2]))
+        for i, n in enumerate(windows):
+            taus[i] = autocorr_time(chains[:n, :, :])                                          # IP.py:3930
+    return dict(window_indices=windows, taus=taus, final_parameter_values=taus[-1, :], combined=np.prod(taus, axis=1))
+
+
+# --------------------------------------------------------------------------------------------
 # Ensemble slice sampling -- published algorithm (parity unpinned, see module header)
 # --------------------------------------------------------------------------------------------
 def ess_run(logp_batch: Callable, start, nsteps, rng: np.random.Generator, mu0=1.0, maxiter=10000,

@@ -98,7 +98,7 @@ EXPORTS = [
     "peuqse_stats_work_bytes", "peuqse_stats_begin", "peuqse_stats_finish", "peuqse_stats_compact",
     "peuqse_scenarios_create", "peuqse_scenarios_destroy", "peuqse_scenarios_synthesize", "peuqse_scenarios_set_observed",
     "peuqse_scenarios_logp", "peuqse_mh_run_scenarios", "peuqse_scenarios_stats",
-    "peuqse_geweke_work_bytes", "peuqse_geweke", "peuqse_scenarios_kl",
+    "peuqse_geweke_work_bytes", "peuqse_geweke", "peuqse_scenarios_kl", "peuqse_act_concat",
 ]
 
 _lib = None
@@ -177,6 +177,7 @@ def load():
     L.peuqse_geweke_work_bytes.restype = i64
     L.peuqse_geweke_work_bytes.argtypes = [i64, i64, i32]
     L.peuqse_geweke.argtypes = [vp, i64, i64, vp, vp, i32, vp, i32, vp, vp, vp]
+    L.peuqse_act_concat.argtypes = [vp, i64, i64, i32, vp, vp, i64, vp]
     for name in EXPORTS:
         if name not in ("peuqse_last_error", "peuqse_version", "peuqse_sweep_work_bytes", "peuqse_ess_work_bytes",
                         "peuqse_stats_work_bytes", "peuqse_peer_max_bytes", "peuqse_geweke_work_bytes"):

@@ -169,6 +169,41 @@ GwGeom gw_geom(long long R, long long CK, int nb) {
     return G;
 }
 
+
+// Integrated autocorrelation time (zeus.autocorr.AutoCorrTime, method 'mk', called at IP.py:3916-3930): the walkers' chains
+// of one parameter are laid end to end into ONE series whose autocorrelation function is taken by FFT.  This kernel is the
+// layout change in front of the transform: samples[t][c][d] (row = step) -> series_d[c * n + t] - mean_d for every
+// parameter in one read of the first n rows, through a 32 x 64 shared-memory tile so that both the reads (along c*k+d)
+// and the writes (along t) are coalesced.  HBM traffic: 8 B read + 8 B written per sample.
+#define AC_TT 32
+#define AC_TC 64
+__global__ void __launch_bounds__(256) k_act_concat(const double* __restrict__ x, long long n, long long C, int k,
+                                                    const double* __restrict__ mean, double* __restrict__ out,
+                                                    long long out_stride, unsigned col_tiles) {
+    __shared__ double tile[AC_TT][AC_TC + 1];
+    const long long CK = C * k;
+    const long long col0 = (long long)(blockIdx.x % col_tiles) * AC_TC, t0 = (long long)(blockIdx.x / col_tiles) * AC_TT;
+    {
+        const int tx = threadIdx.x % AC_TC, ty = threadIdx.x / AC_TC;
+        const long long col = col0 + tx;
+#pragma unroll
+        for (int r = ty; r < AC_TT; r += 256 / AC_TC) {
+            const long long t = t0 + r;
+            tile[r][tx] = (col < CK && t < n) ? x[t * CK + col] : 0.0;
+        }
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long t = t0 + lane;
+    for (int j = w; j < AC_TC; j += 8) {
+        const long long col = col0 + j;
+        if (col >= CK || t >= n) continue;
+        const long long c = col / k;
+        const int d = (int)(col - c * k);
+        out[(long long)d * out_stride + c * n + t] = tile[lane][j] - mean[d];
+    }
+}
+
 }  // namespace
 
 extern "C" int64_t peuqse_geweke_work_bytes(int64_t n_rows, int64_t n_cols, int32_t n_positions) {
@@ -204,6 +239,22 @@ extern "C" int peuqse_geweke(const double* d_samples, int64_t n_rows, int64_t n_
     k_geweke_prefix<<<dim3(gx, G.n_seg), GW_THREADS, 0, st>>>(d_samples, G, (const long long*)d_positions, seg_first, rec, tot);
     k_geweke_carry<<<dim3(gx, 4), GW_THREADS, 0, st>>>(G, tot);
     k_geweke_z<<<dim3(gx, n_z), GW_THREADS, 0, st>>>(rec, tot, G, (const long long*)d_positions, d_slices, n_z, d_z);
+    PQ_CUDA_OK(cudaGetLastError());
+    return PEUQSE_OK;
+}
+
+extern "C" int peuqse_act_concat(const double* d_samples, int64_t n_rows, int64_t n_chains, int32_t k, const double* d_mean,
+                                 double* d_series, int64_t series_stride, void* stream) {
+    if (!d_samples || !d_mean || !d_series) return pq_set_error(PEUQSE_ERR_INVALID, "null argument");
+    if (n_rows < 1 || n_chains < 1 || k < 1 || series_stride < n_rows * n_chains) return pq_set_error(PEUQSE_ERR_INVALID, "bad sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long len = n_rows * n_chains, CK = n_chains * k;
+    const long long gx = (CK + AC_TC - 1) / AC_TC, gy = (n_rows + AC_TT - 1) / AC_TT;
+    if (gx * gy > 2147483647LL) return pq_set_error(PEUQSE_ERR_INVALID, "more than 2^31 tiles");
+    if (series_stride > len)                                               // zero padding of the transform
+        for (int d = 0; d < k; ++d)
+            PQ_CUDA_OK(cudaMemsetAsync(d_series + (size_t)d * series_stride + len, 0, (size_t)(series_stride - len) * sizeof(double), st));
+    k_act_concat<<<(unsigned)(gx * gy), 256, 0, st>>>(d_samples, n_rows, n_chains, k, d_mean, d_series, series_stride, (unsigned)gx);
     PQ_CUDA_OK(cudaGetLastError());
     return PEUQSE_OK;
 }

@@ -3,7 +3,9 @@ getConvergenceDiagnostics / calculateAndPlotConvergenceDiagnostics (PEUQSE/Inver
 with geweke_diagnostic (IP.py:4012-4062), for thousands of chains at once (csrc/diag.cu).
 
 The integrated autocorrelation time (IP.py:3916-3948) is zeus.autocorr.AutoCorrTime, a third-party routine that is neither
-vendored by the reference nor installed here; it is not restated (its entries of PE_object.convergence are None).
+vendored by the reference nor installed here: autocorr_times() follows its published algorithm (method 'mk': the walkers'
+chains laid end to end, FFT autocorrelation function, Sokal's automated window with c = 5) -- PARITY UNPINNED, checked
+against the oracle's numpy restatement only (oracle/peuqse_oracle.py:autocorr_time).
 The spectral variance inside the Geweke score is statsmodels' yule_walker (order 2, 'adjusted', demeaned), restated from
 its published algorithm (oracle/peuqse_oracle.py:yule_walker): parity pinned for everything but that one call.
 """
@@ -83,6 +85,53 @@ def geweke_z_scores(chains, windows=None, initial_window=0.1, comparison_window=
     return z.reshape(len(windows), intervals, C, k).permute(3, 2, 0, 1), windows, starts
 
 
+def autocorr_times(chains, windows=None, c=5.0):
+    """chains[R, C, k] (CUDA float64 tensor or array) -> (taus[W, k] CUDA tensor, windows): zeus.autocorr.AutoCorrTime of
+    chains[:n] for every growing window n (default: the reference's np.exp(np.linspace(0, log R, 21)).astype(int)[1:],
+    IP.py:3918).  Per window: csrc/diag.cu k_act_concat writes, for all parameters in one read, the demeaned walker-major
+    series zero-padded to twice the next power of two; the transform pair is cuFFT (torch.fft -- a plain library FFT, like
+    numpy's in the routine this replaces); the normalisation, running sum and automated window stay on the device (no host
+    synchronisation per window).  Parameters are transformed in groups sized to the free device memory."""
+    L = _lib.load()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    x = chains if torch.is_tensor(chains) else torch.as_tensor(np.ascontiguousarray(np.asarray(chains, dtype=float)))
+    x = x.to(dev, dtype=torch.float64).contiguous()
+    R, C, k = x.shape
+    if windows is None:
+        with np.errstate(all='ignore'):
+            windows = np.exp(np.linspace(0, np.log(R), 21)).astype(int)[1:]          # IP.py:3918
+    windows = np.asarray(windows, dtype=np.int64)
+    taus = torch.empty((len(windows), k), dtype=torch.float64, device=dev)
+    launches = 0
+    for i, n in enumerate(int(w) for w in windows):
+        if n < 1 or n > R:
+            raise ValueError("window sizes must lie in [1, number of samples]")
+        length = n * C
+        n2 = 2
+        while n2 < 2 * length:
+            n2 <<= 1                                                                 # 2 * next power of two >= length
+        mean = (x[:n].sum(dim=(0, 1)) / float(length)).contiguous()               # a true division: a constant column gives 0/0 = NaN as in numpy
+        series = torch.empty((k, n2), dtype=torch.float64, device=dev)
+        _lib.check(L.peuqse_act_concat(_lib.ptr(x), n, C, k, _lib.ptr(mean), _lib.ptr(series), n2, _lib.current_stream()))
+        launches += 1
+        lag = torch.arange(n, device=dev, dtype=torch.float64)
+        for d in range(k):
+            f = torch.fft.rfft(series[d])
+            power = f.real * f.real + f.imag * f.imag
+            del f
+            acf = torch.fft.irfft(power, n=n2)[:n]
+            del power
+            acf = acf / acf[0]
+            t = 2.0 * torch.cumsum(acf, dim=0) - 1.0
+            m = lag < c * t
+            first_false = torch.where(m, torch.full_like(lag, float(n)), lag).min()  # np.argmin(m): the first False ...
+            idx = torch.where(first_false < n, first_false,                          # ... 0 if all True, n-1 if none is
+                              torch.where(m.any(), torch.zeros_like(first_false), torch.full_like(first_false, float(n - 1))))
+            taus[i, d] = t[idx.long()]
+        del series
+    return taus, windows, launches
+
+
 def convergence_diagnostics(pe, discrete_chains_post_burn_in_samples=None):
     """getConvergenceDiagnostics (IP.py:2121-2161): fills PE_object.convergence; returns the reference's output tuple."""
     x = discrete_chains_post_burn_in_samples
@@ -105,9 +154,18 @@ def convergence_diagnostics(pe, discrete_chains_post_burn_in_samples=None):
     nan_safe = torch.where(torch.isnan(comb), torch.zeros_like(comb), comb)
     outlier = ((nan_safe > 1).sum(dim=1).double() / comb.shape[1]).cpu().numpy()    # IP.py:4000
     per_param = a.mean(dim=1)                                                       # [k, W, I]: the per-parameter plots' data
-    pe.convergence = {'AutoCorrTime': {'window_indices': None, 'final_parameter_values': None, 'parameter_act_for_each_window': None},
+    taus, act_windows, n_act = autocorr_times(x)                                    # IP.py:3916-3948
+    pe.gpu_launches += n_act
+    taus = taus.cpu().numpy()
+    names = list(pe.UserInput.model['parameterNamesAndMathTypeExpressionsDict'].keys()) if hasattr(pe, 'UserInput') else []
+    if len(names) != taus.shape[1]:
+        names = ['parameter_%d' % d for d in range(taus.shape[1])]
+    act_each = {name: taus[:, d] for d, name in enumerate(names)}                   # IP.py:3938-3942
+    pe.convergence = {'AutoCorrTime': {'window_indices': act_windows, 'final_parameter_values': taus[-1, :],
+                                       'parameter_act_for_each_window': act_each,
+                                       'combined_parameter_act_for_each_window': np.prod(taus, axis=1)},
                       'Geweke': {'window_indices': windows, 'final_combined_parameter_values': final,
                                  'final_combined_parameter_percent_outlier': outlier,
                                  'interval_start_indices': starts, 'z_scores_each_parameter': per_param.cpu().numpy()}}
     pe.geweke_z_scores = z
-    return (None, None, None, windows, final, outlier)
+    return (act_windows, taus[-1, :], act_each, windows, final, outlier)

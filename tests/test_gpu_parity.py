@@ -995,7 +995,12 @@ def test_geweke_on_device_vs_reference_fixture_and_oracle(env, golden):
                            'mcmc_info_gain_returned': 'log_ratio', 'convergence_diagnostics': True, 'mcmc_exportLog': False})
     PE.doMetropolisHastings()
     G = PE.convergence['Geweke']
-    assert np.array_equal(G['window_indices'], np.linspace(0, 2500, 21).astype(int)[1:]) and PE.convergence['AutoCorrTime']['window_indices'] is None
+    assert np.array_equal(G['window_indices'], np.linspace(0, 2500, 21).astype(int)[1:])
+    A = PE.convergence['AutoCorrTime']                          # the autocorrelation half (unpinned: oracle restatement of zeus)
+    ra = orc.autocorr_time_convergence(PE.discrete_chains_post_burn_in_samples)
+    assert np.array_equal(A['window_indices'], ra['window_indices']) and list(A['parameter_act_for_each_window']) == ['0', '1']
+    np.testing.assert_allclose(A['final_parameter_values'], ra['final_parameter_values'], rtol=1e-9)
+    np.testing.assert_allclose(A['parameter_act_for_each_window']['1'], ra['taus'][:, 1], rtol=1e-9, equal_nan=True)
     zz = PE.geweke_z_scores.cpu().numpy()
     chains = PE.discrete_chains_post_burn_in_samples
     assert chains.shape == (2500, 8, 2) and zz.shape == (2, 8, 20, 20)
@@ -1121,3 +1126,54 @@ def test_geweke_short_and_single_column_chains(env):
         np.testing.assert_allclose(z2[0, 0, 1], orc.geweke_diagnostic(x[:260, 0, 0], 0.2, 0.4, 7)[:, 1], rtol=1e-7)
     with pytest.raises(ValueError):
         geweke_z_scores(x, initial_window=0.6, comparison_window=0.5)
+
+
+@pytest.mark.gpu
+def test_autocorr_time_on_device_vs_oracle(env):
+    """SURVEY 8f rank 4, the integrated-autocorrelation-time half of the convergence diagnostics (IP.py:3916-3948):
+    k_act_concat + FFT autocorrelation + automated window on the device against the oracle's numpy restatement of
+    zeus.autocorr.AutoCorrTime (PARITY UNPINNED at the zeus boundary: zeus is not installed and not vendored).  Tolerance
+    1e-9 relative on tau: cuFFT and numpy's pocketfft round differently; the window index itself must agree (a tau taken at
+    a neighbouring lag differs by far more than the tolerance).  AR(1) chains also pin the estimate to (1+rho)/(1-rho)."""
+    PEUQSE, orc, _, torch = env
+    from peuqse_b200.diagnostics import autocorr_times
+    rng = np.random.default_rng(5)
+    R, C, k = 4000, 37, 5                                                  # ragged: 37 * 5 columns, tiles of 64; rows % 32 != 0
+    rho = np.array([0.0, 0.5, 0.9, 0.99, 0.3])
+    e = rng.standard_normal((R, C, k))
+    x = np.empty_like(e)
+    x[0] = e[0]
+    for t in range(1, R):
+        x[t] = rho * x[t - 1] + e[t]
+    x = x * np.array([1.0, 1e-3, 40.0, 1.0, 1e5]) + np.array([0.0, 7.0, -3e3, 1e2, 1e7])
+    taus, windows, launches = autocorr_times(torch.as_tensor(x).cuda())
+    taus = taus.cpu().numpy()
+    ref = orc.autocorr_time_convergence(x)
+    assert np.array_equal(windows, ref['window_indices']) and launches == 20 and taus.shape == (20, 5)
+    np.testing.assert_allclose(taus, ref['taus'], rtol=1e-9, equal_nan=True)
+    np.testing.assert_allclose(taus[-1, :3], (1 + rho[:3]) / (1 - rho[:3]), rtol=0.1)
+    # the concatenated series itself, bit for bit (the layout kernel subtracts the mean it is given)
+    import ctypes
+    from peuqse_b200 import _lib
+    L = _lib.load()
+    n = 1234
+    d_x = torch.as_tensor(x).cuda()
+    mean = torch.as_tensor(x[:n].mean(axis=(0, 1))).cuda()
+    series = torch.full((k, 65536), 9.0, dtype=torch.float64, device='cuda')
+    _lib.check(L.peuqse_act_concat(_lib.ptr(d_x), n, C, k, _lib.ptr(mean), _lib.ptr(series), 65536, _lib.current_stream()))
+    s = series.cpu().numpy()
+    for d in range(k):
+        assert np.array_equal(s[d, :n * C], x[:n, :, d].T.reshape(-1) - mean[d].item())
+        assert not s[d, n * C:].any()
+    # short and degenerate inputs: one chain, windows of one row, a constant parameter (0/0 -> NaN like numpy)
+    y = rng.standard_normal((50, 1, 2))
+    y[:, :, 1] = 3.0
+    t2, w2, _ = autocorr_times(y)
+    r2 = orc.autocorr_time_convergence(y)
+    assert np.array_equal(w2, r2['window_indices'])
+    np.testing.assert_allclose(t2.cpu().numpy(), r2['taus'], rtol=1e-9, equal_nan=True)
+    t3, _, _ = autocorr_times(x[:, :4, :2], windows=[100, 1000], c=3.0)
+    for i, n in enumerate((100, 1000)):
+        np.testing.assert_allclose(t3[i].cpu().numpy(), orc.autocorr_time(x[:n, :4, :2], c=3.0), rtol=1e-9)
+    with pytest.raises(ValueError):
+        autocorr_times(x, windows=[R + 1])

@@ -331,3 +331,29 @@ def test_geweke_diagnostic_vs_reference(golden):
     r0, r1, r2 = (d * d).sum() / 400, (d[:-1] * d[1:]).sum() / 399, (d[:-2] * d[2:]).sum() / 398
     np.testing.assert_allclose(np.array([[r0, r1], [r1, r0]]) @ rho, [r1, r2], rtol=1e-12)
     np.testing.assert_allclose(sigma ** 2, r0 - r1 * rho[0] - r2 * rho[1], rtol=1e-12)
+
+
+def test_autocorr_time_restatement_known_answers():
+    """oracle.autocorr_time restates zeus.autocorr.AutoCorrTime (method 'mk'), a third-party routine that is neither vendored
+    by the reference nor installed here: PARITY UNPINNED.  What can be checked without zeus: the FFT autocorrelation function
+    equals the direct lag sums, white noise gives tau ~ 1, AR(1) chains give (1+rho)/(1-rho), the automated window is the
+    first lag M >= c tau(M), and the growing windows are those of IP.py:3918."""
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal(300).cumsum()
+    acf = orc.autocorr_func_1d(x, norm=False)
+    xc = x - x.mean()
+    direct = np.array([np.dot(xc[:len(x) - l], xc[l:]) for l in range(len(x))]) / (4 * 512)
+    np.testing.assert_allclose(acf, direct, rtol=1e-9, atol=1e-12 * direct[0])
+    assert orc.auto_window(np.array([1.0, 1.5, 0.3, 0.2]), 5.0) == 2          # 2 >= 5 * 0.3
+    assert orc.auto_window(np.array([1.0, 1.0]), 5.0) == 0                    # never reached: numpy's argmin of all-True
+    R, C = 20000, 6
+    rho = np.array([0.0, 0.6, 0.9])
+    e = rng.standard_normal((R, C, 3))
+    y = np.empty_like(e)
+    y[0] = e[0]
+    for t in range(1, R):
+        y[t] = rho * y[t - 1] + e[t]
+    r = orc.autocorr_time_convergence(y)
+    assert np.array_equal(r['window_indices'], np.exp(np.linspace(0, np.log(R), 21)).astype(int)[1:]) and r['taus'].shape == (20, 3)
+    np.testing.assert_allclose(r['final_parameter_values'], (1 + rho) / (1 - rho), rtol=0.08)
+    np.testing.assert_allclose(r['combined'], np.prod(r['taus'], axis=1))
