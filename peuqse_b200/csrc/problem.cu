@@ -57,6 +57,18 @@ extern "C" int peuqse_problem_create(const peuqse_problem_desc* h, peuqse_proble
     if (h->model_id < PEUQSE_MODEL_EXTERNAL || h->model_id > PEUQSE_MODEL_LANGMUIR_LOG)
         return pq_set_error(PEUQSE_ERR_INVALID, "unknown model_id");
 
+    {
+        // the stream-ordered scratch of the launch functions (cudaMallocAsync) comes from the device's default pool, whose
+        // release threshold of 0 hands freed memory back to the driver at every synchronisation: samplers that synchronise
+        // once per round (ensemble slice sampling) then paid ~80 us per allocation.  Keep the pool's memory.
+        int dev = 0;
+        cudaMemPool_t pool;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     peuqse_problem* p = new peuqse_problem();
     memset(p, 0, sizeof *p);
     DevProblem& d = p->d;

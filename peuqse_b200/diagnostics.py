@@ -110,7 +110,9 @@ def autocorr_times(chains, windows=None, c=5.0):
         n2 = 2
         while n2 < 2 * length:
             n2 <<= 1                                                                 # 2 * next power of two >= length
-        mean = (x[:n].sum(dim=(0, 1)) / float(length)).contiguous()               # a true division: a constant column gives 0/0 = NaN as in numpy
+        # a true division by a device tensor (torch turns division by a host scalar into a multiplication by its reciprocal):
+        # the mean of a constant column is exact, its series is 0 and its tau 0/0 = NaN as in numpy
+        mean = (x[:n].sum(dim=(0, 1)) / torch.full((k,), float(length), dtype=torch.float64, device=dev)).contiguous()
         series = torch.empty((k, n2), dtype=torch.float64, device=dev)
         _lib.check(L.peuqse_act_concat(_lib.ptr(x), n, C, k, _lib.ptr(mean), _lib.ptr(series), n2, _lib.current_stream()))
         launches += 1

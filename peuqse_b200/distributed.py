@@ -102,6 +102,27 @@ def allgather_rows(t):
     return torch.cat([o[:c] for o, c in zip(out, ns)], dim=0).to(t.device)
 
 
+def sharded_rows(fn, x, min_rows_per_rank=1):
+    """fn(rows) -> values, row by row independent: every rank evaluates its contiguous shard of x[B, ...] and the shards are
+    all-gathered back into the full [B] result, identical on all ranks (ensemble slice sampling v2: the walkers
+    of the active half are shared out, one all-gather per stepping-out / shrink round).  The shard sizes follow from B
+    alone, so no sizes are exchanged: one all_gather_into_tensor of the padded shards."""
+    rank, size = world()
+    B = x.shape[0]
+    if size == 1 or B < size * min_rows_per_rank:
+        return fn(x)
+    first, count = shard_range(B, rank, size)
+    mine = fn(x[first:first + count])
+    m = max(shard_range(B, r, size)[1] for r in range(size))
+    dev = _comm_device()
+    pad = torch.zeros((m,) + tuple(mine.shape[1:]), dtype=mine.dtype, device=dev)
+    pad[:count] = mine.to(dev)
+    out = torch.empty((size * m,) + tuple(mine.shape[1:]), dtype=mine.dtype, device=dev)
+    dist.all_gather_into_tensor(out, pad)
+    parts = [out[r * m:r * m + shard_range(B, r, size)[1]] for r in range(size)]
+    return torch.cat(parts, dim=0).to(mine.device)
+
+
 _native_comm = None
 
 

@@ -293,7 +293,7 @@ def ess_launch(pe, start, n_iters, seed, mu0=1.0, tune=True, max_rounds=10000, f
 
 
 def ess_batched(pe, start, n_iters, seed, mu0=1.0, tune=True, max_rounds=10000, store_chain=True, maxsteps=10000,
-                tolerance=0.05, patience=5):
+                tolerance=0.05, patience=5, shard=True):
     """Round-synchronous ensemble slice sampling (same algorithm as csrc/ess.cu) for simulators / likelihoods that must
     be evaluated in batches: every stepping-out or shrink round gathers the still-active walkers and evaluates their
     log-posteriors with ONE batched launch (pe.getLogP_batch -> full-covariance contraction for C4)."""
@@ -303,7 +303,13 @@ def ess_batched(pe, start, n_iters, seed, mu0=1.0, tune=True, max_rounds=10000, 
     X = torch.as_tensor(np.asarray(start, dtype=float), dtype=torch.float64).reshape(-1, pe.k).to(dev).contiguous()
     W, k = X.shape
     H = W // 2
-    Z = pe.getLogP_batch(X).clone()
+    # multi-GPU: every rank runs this driver with the same seed, hence the same draws and the same masks; the
+    # batch of each round is shared out over the ranks row-wise and the log-posteriors are all-gathered (NCCL).  A row's
+    # value does not depend on the batch it is evaluated in, so the chain is the one a single GPU produces.
+    logp_rows = pe.getLogP_batch
+    if shard and D.world()[1] > 1:
+        logp_rows = lambda th: D.sharded_rows(pe.getLogP_batch, th.contiguous(), min_rows_per_rank=8)
+    Z = logp_rows(X).clone()
     if not bool(torch.isfinite(Z).all().item()):
         raise ValueError("Invalid walker initial positions! Initialise walkers from positions of finite log probability.")
     chain = torch.empty((n_iters, W, k), dtype=torch.float64, device=dev) if store_chain else None
@@ -312,7 +318,7 @@ def ess_batched(pe, start, n_iters, seed, mu0=1.0, tune=True, max_rounds=10000, 
     rnd = lambda n: torch.rand(n, dtype=torch.float64, device=dev, generator=g)
     for it in range(n_iters):
         perm = torch.randperm(W, device=dev, generator=g)
-        nexp = ncon = 0
+        n_dev = torch.zeros(2, dtype=torch.int64, device=dev)    # expansions, contractions of this iteration
         for half in (0, 1):
             act, comp = perm[half * H:(half + 1) * H], perm[(1 - half) * H:(2 - half) * H]
             i1 = torch.clamp((rnd(H) * H).long(), max=H - 1)
@@ -325,32 +331,40 @@ def ess_batched(pe, start, n_iters, seed, mu0=1.0, tune=True, max_rounds=10000, 
             Rb = Lb + 1.0
             J = torch.floor(maxsteps * rnd(H))
             K = (maxsteps - 1.0) - J
-            for side in (0, 1):                                   # stepping out: left, then right
-                B, cnt = (Lb, J) if side == 0 else (Rb, K)
-                mask = cnt >= 1
-                rounds = 0
-                while bool(mask.any().item()):
-                    idx = mask.nonzero(as_tuple=True)[0]
-                    z = pe.getLogP_batch(X0[idx] + B[idx, None] * dirs[idx])
-                    neval += idx.numel()
-                    grow = Z0[idx] < z
-                    gi = idx[grow]
-                    B[gi] += (-1.0 if side == 0 else 1.0)
-                    cnt[gi] -= 1.0
-                    nexp += int(grow.sum().item())
-                    mask[idx[~grow]] = False
-                    mask &= cnt >= 1
-                    rounds += 1
-                    if rounds > max_rounds:
-                        raise RuntimeError("Number of expansions exceeded maximum limit! Increase mcmc_maxiter.")
+            # stepping out, both ends at once: the 2H boundaries (left ends, then right ends) are independent tasks, a round
+            # evaluates every boundary that is still moving (no draws are consumed here, so the order of evaluation is free);
+            # the only host synchronisation of a round is the size of its index list
+            Bd, cnt, sgn = torch.cat((Lb, Rb)), torch.cat((J, K)), torch.cat((-torch.ones_like(Lb), torch.ones_like(Rb)))
+            mask = cnt >= 1
+            rounds = 0
+            while True:
+                idx2 = mask.nonzero(as_tuple=True)[0]
+                if idx2.numel() == 0:
+                    break
+                idx = idx2 % H
+                z = logp_rows(X0[idx] + Bd[idx2, None] * dirs[idx])
+                neval += idx2.numel()
+                grow = Z0[idx] < z
+                gi = idx2[grow]
+                Bd[gi] += sgn[gi]
+                cnt[gi] -= 1.0
+                n_dev[0] += grow.sum()
+                mask[idx2[~grow]] = False
+                mask &= cnt >= 1
+                rounds += 1
+                if rounds > max_rounds:
+                    raise RuntimeError("Number of expansions exceeded maximum limit! Increase mcmc_maxiter.")
+            Lb, Rb = Bd[:H].clone(), Bd[H:].clone()
             mask = torch.ones(H, dtype=torch.bool, device=dev)
             Xn, Zn = X0.clone(), Z[act].clone()
             rounds = 0
-            while bool(mask.any().item()):                        # shrinking
+            while True:                                           # shrinking
                 idx = mask.nonzero(as_tuple=True)[0]
+                if idx.numel() == 0:
+                    break
                 wd = Lb[idx] + rnd(idx.numel()) * (Rb[idx] - Lb[idx])
                 cand = X0[idx] + wd[:, None] * dirs[idx]
-                z = pe.getLogP_batch(cand)
+                z = logp_rows(cand)
                 neval += idx.numel()
                 ok = Z0[idx] < z
                 Xn[idx[ok]] = cand[ok]
@@ -359,12 +373,13 @@ def ess_batched(pe, start, n_iters, seed, mu0=1.0, tune=True, max_rounds=10000, 
                 rej, wr = idx[~ok], wd[~ok]
                 Lb[rej[wr < 0]] = wr[wr < 0]
                 Rb[rej[wr > 0]] = wr[wr > 0]
-                ncon += int((~ok).sum().item())
+                n_dev[1] += (~ok).sum()
                 rounds += 1
                 if rounds > max_rounds:
                     raise RuntimeError("Number of contractions exceeded maximum limit! Increase mcmc_maxiter.")
             X[act] = Xn
             Z[act] = Zn
+        nexp, ncon = (int(v) for v in n_dev.tolist())            # one read per ensemble iteration (the tuning needs them)
         tot_exp += nexp
         tot_con += ncon
         if tune:

@@ -95,6 +95,28 @@ A = PE.doeParameterModulationPermutationsScanner()
 ref = gd['scanner_xyz_info_gains_matrices_array']
 assert A.shape == ref.shape and np.array_equal(A[:, :, :2], ref[:, :, :2])
 np.testing.assert_allclose(A[:, :, 2], ref[:, :, 2], rtol=1e-9)
+# 5. ensemble slice sampling v2: the round-synchronous driver with every round's batch shared out over the ranks
+#    and all-gathered must produce the chain of the unsharded driver (full-covariance responses: the C4 path at a small size)
+from oracle import peuqse_oracle as orc
+from peuqse_b200.mcmc import ess_batched
+rng = np.random.default_rng(21)
+kk, nn = 3, 24
+Phi = orc.cos_basis(2 * nn, kk)
+xx = np.linspace(0, 1, nn)
+Sig = 0.1 ** 2 * np.exp(-(xx[:, None] - xx[None, :]) ** 2 / (2 * 0.05 ** 2)) + 0.05 ** 2 * np.eye(nn)
+Lc = np.linalg.cholesky(Sig)
+yy = Phi @ rng.standard_normal(kk) + np.concatenate([Lc @ rng.standard_normal(nn), Lc @ rng.standard_normal(nn)])
+UI = PEUQSE.UserInput.fresh()
+UI.responses['responses_observed'] = [list(yy[:nn]), list(yy[nn:])]
+UI.responses['responses_observed_uncertainties'] = [Sig, Sig]
+UI.model['InputParameterPriorValues'] = [0.0] * kk
+UI.model['InputParametersPriorValuesUncertainties'] = [2.0] * kk
+UI.model['simulateByInputParametersOnlyFunction'] = PEUQSE.LinearModel(Phi)
+PE = PEUQSE.parameter_estimation(UI)
+start = 0.5 * np.random.default_rng(3).standard_normal((64, kk))
+a = ess_batched(PE, start, 25, 11, shard=True)
+b = ess_batched(PE, start, 25, 11, shard=False)
+assert torch.equal(a['chain'], b['chain']) and torch.equal(a['chain_logp'], b['chain_logp']) and torch.equal(a['info'], b['info'])
 dist.barrier()
 if rank == 0:
     print("MGPU_OK", world)

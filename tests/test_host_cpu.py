@@ -189,9 +189,18 @@ def _rank_main(rank, world, port, out):
         mx = D.allreduce_np(th[kept].max(axis=0) if kept.any() else np.full(2, -np.inf), "max")
         cnt = D.allreduce_int_np(np.array([int(kept.sum())]))
         rows = D.allgather_rows(torch.from_numpy(th[:3 + rank]))
+        # ensemble slice sampling v2: a batch of walker positions evaluated shard-wise, gathered back in order (7 rows over 2
+        # ranks: ragged shards of 3 and 4); a batch smaller than the per-rank minimum is evaluated whole on every rank
+        calls = []
+        fn = lambda r: (calls.append(r.shape[0]), orc_rows(r))[1]
+        orc_rows = lambda r: torch.from_numpy(orc.log_p_batch(P, r.numpy(), bt)[0])
+        common = orc.grid_decode(c, h, r, np.arange(0, 7))            # the same batch on every rank
+        sh = D.sharded_rows(fn, torch.from_numpy(common.copy()))
+        sh_small = D.sharded_rows(fn, torch.from_numpy(common.copy()), min_rows_per_rank=4)
         if rank == 0:
             np.savez(out, best_v=best_v, best_i=best_i, W=sums[0], mu=shift + sums[1:] / sums[0], mn=mn, mx=mx, cnt=cnt,
-                     nrows=rows.shape[0])
+                     nrows=rows.shape[0], sharded=sh.numpy(), sharded_small=sh_small.numpy(), shard_calls=np.array(calls),
+                     sharded_want=orc.log_p_batch(P, orc.grid_decode(c, h, r, np.arange(0, 7)), bt)[0])
     finally:
         dist.destroy_process_group()
 
@@ -208,6 +217,8 @@ def test_two_rank_gloo_reductions_match_single_process(tmp_path, golden):
     np.testing.assert_allclose(res['mu'], g['ex00_grid_mu_AP'], rtol=1e-12)
     assert int(res['cnt'][0]) == int((g['ex00_grid_multiplicity'] > 0).sum())
     assert int(res['nrows']) == 3 + 4
+    assert np.array_equal(res['sharded'], res['sharded_want']) and np.array_equal(res['sharded_small'], res['sharded_want'])
+    assert list(res['shard_calls']) == [3, 7]                     # rank 0: its 3-row shard, then the whole small batch
 
 
 def _export_stub(golden):
