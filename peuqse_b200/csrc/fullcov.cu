@@ -75,10 +75,39 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(256) k_quadform_dmma(const double* __restrict__ sim, int ld_sim, int off,
+#define QD_CHUNKS 4    // the K range is always accumulated as 4 separately rounded chunk sums, combined ((c0+c1)+c2)+c3
+
+// row-wise sum of squares of a CTA's 64 x 64 tile held in accumulator-fragment order -> partial[blockIdx.x][row]
+__device__ __forceinline__ void qd_epilogue(const double (&acc)[4][2][2], long long bm, long long B, double* __restrict__ partial) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 2, wn = warp & 3;
+    __shared__ double s_row[4][QD_BM];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) s = fma(acc[i][j][0], acc[i][j][0], fma(acc[i][j][1], acc[i][j][1], s));
+        s += __shfl_xor_sync(0xffffffffu, s, 1);                   // the 4 lanes of a row group hold different columns
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if ((lane & 3) == 0) s_row[wn][wm * 32 + i * 8 + (lane >> 2)] = s;
+    }
+    __syncthreads();
+    if (tid < QD_BM) {
+        const long long row = bm + tid;
+        if (row < B) partial[(size_t)blockIdx.x * B + row] = ((s_row[0][tid] + s_row[1][tid]) + s_row[2][tid]) + s_row[3][tid];
+    }
+}
+
+// SPLIT = false: one CTA per tile walks the four K chunks one after the other.  SPLIT = true (small batches: fewer tiles
+// than SMs, and a 256-step K loop is pure latency): blockIdx.z is the chunk, the chunk's accumulators go to
+// frag[chunk][tile][16][256] and k_quadform_split_finish combines them -- the same additions in the same order, so a
+// row's value does not depend on the size of the batch it is evaluated in.
+template <bool SPLIT>
+__global__ void __launch_bounds__(256, 3) k_quadform_dmma(const double* __restrict__ sim, int ld_sim, int off,
                                                       const int* __restrict__ src, const double* __restrict__ y,
                                                       const double* __restrict__ U, int n, long long B,
-                                                      double* __restrict__ partial /* [gridDim.x][B] */) {
+                                                      double* __restrict__ partial /* [gridDim.x][B] */,
+                                                      double* __restrict__ frag) {
     __shared__ double As[2][QD_BM][QD_LDA];
     __shared__ double Bs[2][QD_BK][QD_LDB];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -106,49 +135,78 @@ __global__ void __launch_bounds__(256) k_quadform_dmma(const double* __restrict_
             Bs[st][br][bc + q] = rb[q];
         }
     };
-    double acc[4][2][2];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     const int nk = (n + QD_BK - 1) / QD_BK;
-    load_tiles(0);
-    store_tiles(0);
-    __syncthreads();
-    for (int kt = 0; kt < nk; ++kt) {
-        const int st = kt & 1;
-        if (kt + 1 < nk) load_tiles((kt + 1) * QD_BK);           // global loads of the next tile fly during the MMAs
+    double tot[4][2][2];
+    const int c_first = SPLIT ? (int)blockIdx.z : 0, c_last = SPLIT ? (int)blockIdx.z + 1 : QD_CHUNKS;
+    for (int ch = c_first; ch < c_last; ++ch) {
+        const int kt0 = (int)((long long)nk * ch / QD_CHUNKS), kt1 = (int)((long long)nk * (ch + 1) / QD_CHUNKS);
+        double acc[4][2][2];
 #pragma unroll
-        for (int ks = 0; ks < QD_BK; ks += 4) {
-            double af[4], bf[2];
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) af[i] = As[st][wm * 32 + i * 8 + (lane >> 2)][ks + (lane & 3)];
+            for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        if (kt0 < kt1) {
+            load_tiles(kt0 * QD_BK);
+            store_tiles(0);
+            __syncthreads();
+            for (int kt = kt0; kt < kt1; ++kt) {
+                const int st = (kt - kt0) & 1;
+                if (kt + 1 < kt1) load_tiles((kt + 1) * QD_BK);      // global loads of the next tile fly during the MMAs
 #pragma unroll
-            for (int j = 0; j < 2; ++j) bf[j] = Bs[st][ks + (lane & 3)][wn * 16 + j * 8 + (lane >> 2)];
+                for (int ks = 0; ks < QD_BK; ks += 4) {
+                    double af[4], bf[2];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) af[i] = As[st][wm * 32 + i * 8 + (lane >> 2)][ks + (lane & 3)];
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) bf[j] = Bs[st][ks + (lane & 3)][wn * 16 + j * 8 + (lane >> 2)];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                }
+                if (kt + 1 < kt1) store_tiles(st ^ 1);
+                __syncthreads();
+            }
+        }
+        if (SPLIT) {
+            double* f = frag + (((size_t)ch * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * (16 * 256) + tid;
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 2; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                for (int j = 0; j < 2; ++j) {
+                    f[((i * 2 + j) * 2 + 0) * 256] = acc[i][j][0];
+                    f[((i * 2 + j) * 2 + 1) * 256] = acc[i][j][1];
+                }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    tot[i][j][0] = (ch == 0) ? acc[i][j][0] : tot[i][j][0] + acc[i][j][0];
+                    tot[i][j][1] = (ch == 0) ? acc[i][j][1] : tot[i][j][1] + acc[i][j][1];
+                }
         }
-        if (kt + 1 < nk) store_tiles(st ^ 1);
-        __syncthreads();
     }
-    // row-wise sum of squares of this CTA's 64 columns -> partial[blockIdx.x][row]
-    __shared__ double s_row[4][QD_BM];
+    if (!SPLIT) qd_epilogue(tot, bm, B, partial);
+}
+
+__global__ void __launch_bounds__(256) k_quadform_split_finish(const double* __restrict__ frag, long long B,
+                                                              double* __restrict__ partial) {
+    const size_t tile = (size_t)blockIdx.y * gridDim.x + blockIdx.x, tiles = (size_t)gridDim.x * gridDim.y;
+    double tot[4][2][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        double s = 0.0;
+    for (int ch = 0; ch < QD_CHUNKS; ++ch) {
+        const double* f = frag + ((size_t)ch * tiles + tile) * (16 * 256) + threadIdx.x;
 #pragma unroll
-        for (int j = 0; j < 2; ++j) s = fma(acc[i][j][0], acc[i][j][0], fma(acc[i][j][1], acc[i][j][1], s));
-        s += __shfl_xor_sync(0xffffffffu, s, 1);                   // the 4 lanes of a row group hold different columns
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        if ((lane & 3) == 0) s_row[wn][wm * 32 + i * 8 + (lane >> 2)] = s;
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const double a0 = f[((i * 2 + j) * 2 + 0) * 256], a1 = f[((i * 2 + j) * 2 + 1) * 256];
+                tot[i][j][0] = (ch == 0) ? a0 : tot[i][j][0] + a0;
+                tot[i][j][1] = (ch == 0) ? a1 : tot[i][j][1] + a1;
+            }
     }
-    __syncthreads();
-    if (tid < QD_BM) {
-        const long long row = bm + tid;
-        if (row < B) partial[(size_t)blockIdx.x * B + row] = ((s_row[0][tid] + s_row[1][tid]) + s_row[2][tid]) + s_row[3][tid];
-    }
+    qd_epilogue(tot, (long long)blockIdx.y * QD_BM, B, partial);
 }
 
 __global__ void k_quadform_reduce(const double* __restrict__ partial, int ntn, long long B, double c, double* __restrict__ ll) {
@@ -191,7 +249,20 @@ int pq_fullcov_logp(const peuqse_problem* p, const double* d_theta, const double
             cudaError_t e = cudaMallocAsync((void**)&part, (size_t)ntn * B * sizeof(double), st);
             if (e != cudaSuccess) { rc = pq_set_cuda_error(e, "cudaMallocAsync(quadform partials)", __LINE__); break; }
             const dim3 grid((unsigned)ntn, (unsigned)((B + QD_BM - 1) / QD_BM));
-            k_quadform_dmma<<<grid, 256, 0, st>>>(d_sim, p->d.n_total, p->d.resp_off[r], p->d.src, p->d.y, p->d.U[r], n, B, part);
+            // fewer tiles than two per SM and a K loop long enough to be worth cutting: one CTA per (tile, K chunk)
+            const bool split = (long long)grid.x * grid.y < 2LL * p->sm_count && n >= 16 * QD_BK;
+            if (split) {
+                double* frag = nullptr;
+                e = cudaMallocAsync((void**)&frag, (size_t)QD_CHUNKS * grid.x * grid.y * 16 * 256 * sizeof(double), st);
+                if (e != cudaSuccess) { cudaFreeAsync(part, st); rc = pq_set_cuda_error(e, "cudaMallocAsync(quadform fragments)", __LINE__); break; }
+                k_quadform_dmma<true><<<dim3(grid.x, grid.y, QD_CHUNKS), 256, 0, st>>>(d_sim, p->d.n_total, p->d.resp_off[r], p->d.src, p->d.y,
+                                                                                      p->d.U[r], n, B, part, frag);
+                k_quadform_split_finish<<<grid, 256, 0, st>>>(frag, B, part);
+                cudaFreeAsync(frag, st);
+            } else {
+                k_quadform_dmma<false><<<grid, 256, 0, st>>>(d_sim, p->d.n_total, p->d.resp_off[r], p->d.src, p->d.y, p->d.U[r], n, B, part,
+                                                            nullptr);
+            }
             k_quadform_reduce<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(part, ntn, B, p->d.resp_c[r], ll);
             e = cudaGetLastError();
             cudaFreeAsync(part, st);

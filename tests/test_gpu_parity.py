@@ -1177,3 +1177,31 @@ def test_autocorr_time_on_device_vs_oracle(env):
         np.testing.assert_allclose(t3[i].cpu().numpy(), orc.autocorr_time(x[:n, :4, :2], c=3.0), rtol=1e-9)
     with pytest.raises(ValueError):
         autocorr_times(x, windows=[R + 1])
+
+
+@pytest.mark.gpu
+def test_full_covariance_value_independent_of_batch_size(env):
+    """The dense-covariance contraction (csrc/fullcov.cu) runs one CTA per tile for large batches and one CTA per (tile,
+    K chunk) for small ones; both accumulate the same four K chunks and combine them in the same order, so a row's
+    log-likelihood must not depend on the batch it is evaluated in (the sharded ensemble-slice rounds rely on it), and both
+    must agree with scipy's logpdf (IP.py:2960) to 1e-12 relative."""
+    PEUQSE, orc, _, torch = env
+    from scipy.stats import multivariate_normal as mvn
+    rng = np.random.default_rng(8)
+    k, n = 3, 300
+    Phi = orc.cos_basis(2 * n, k)
+    x = np.linspace(0, 1, n)
+    Sig = 0.1 ** 2 * np.exp(-(x[:, None] - x[None, :]) ** 2 / (2 * 0.05 ** 2)) + 0.05 ** 2 * np.eye(n)
+    truth = rng.standard_normal(k)
+    y = Phi @ truth + 0.1 * rng.standard_normal(2 * n)
+    PE = make_pe(PEUQSE, PEUQSE.LinearModel(Phi), [list(y[:n]), list(y[n:])], [Sig, Sig], [0.0] * k, [2.0] * k,
+                 settings={'responses_observed_max_covmat_size': 400})
+    B = 64 * 64                                                   # 5 column tiles x 64 row tiles: above two tiles per SM
+    th = torch.from_numpy(truth + 0.1 * rng.standard_normal((B, k))).cuda()
+    big = PE.getLogP_batch(th)
+    for lo, hi in ((0, 100), (1000, 1001), (4000, 4096), (37, 700)):
+        assert torch.equal(PE.getLogP_batch(th[lo:hi].contiguous()), big[lo:hi])
+    _, _, ll = parts(PE, th[:6].cpu().numpy())
+    want = np.array([mvn.logpdf(x=y[:n], mean=(Phi @ t)[:n], cov=Sig) + mvn.logpdf(x=y[n:], mean=(Phi @ t)[n:], cov=Sig)
+                     for t in th[:6].cpu().numpy()])
+    np.testing.assert_allclose(ll, want, rtol=1e-12)
