@@ -692,8 +692,25 @@ def info_gain_kl(prior_samples, post_samples, bins=100):
     return total, each
 
 
+def info_gain_log_ratio_cutoff(logp, logprior, evidence, cutoff):
+    """The truncated log-ratio information gain of calculateInfoGain for mcmc_info_gain_cutoff != 0 (IP.py:1805-1843): rows
+    whose log-prior or log-posterior is NaN or below ln(cutoff) are removed, the rest contribute
+    ln(exp(logP) / evidence) - logPrior (non-finite terms count as 0); the mean of no rows is NaN."""
+    logp = np.asarray(logp, dtype=float).reshape(-1)
+    logprior = np.asarray(logprior, dtype=float).reshape(-1)
+    stacked = np.vstack((logprior, logp))                                  # IP.py:1809
+    with np.errstate(invalid='ignore', divide='ignore'):
+        remove = np.isnan(stacked).any(axis=0) | (stacked < np.log(cutoff)).any(axis=0)      # IP.py:1818-1826
+        kept = stacked[:, ~remove]
+        post = np.log(np.exp(kept[1]) / evidence)                          # IP.py:1834
+        ratios = post - kept[0]
+        ratios[np.isinf(ratios)] = 0
+        ratios = np.nan_to_num(ratios)
+        return np.mean(ratios) if ratios.size else np.nan
+
+
 def post_burn_in_statistics_filtered(samples, logp, logprior, benchmark='auto', coef=2.0, filter_samples=True,
-                                     mu_ap_logp_fn=None, prior_samples=None):
+                                     mu_ap_logp_fn=None, prior_samples=None, info_gain_cutoff=0):
     """calculatePostBurnInStatistics (IP.py:1861-1937) including the tail filter and calculateInfoGain's log-ratio form
     (IP.py:1793-1803).  logp, logprior: (N,1).  Returns a dict with the filtered arrays and the statistics."""
     samples = np.asarray(samples, dtype=float)
@@ -723,6 +740,8 @@ def post_burn_in_statistics_filtered(samples, logp, logprior, benchmark='auto', 
     ratios[np.isinf(ratios)] = 0
     ratios = np.nan_to_num(ratios)
     st.update(samples=samples, logP=logp, log_priors=logprior, threshold=thr, info_gain_log_ratio=np.mean(ratios))
+    if info_gain_cutoff != 0:
+        st['info_gain_log_ratio'] = info_gain_log_ratio_cutoff(logp, logprior, st['evidence'], info_gain_cutoff)
     if prior_samples is not None:
         st['info_gain_KL'], st['info_gain_KL_each_parameter'] = info_gain_kl(np.asarray(prior_samples, dtype=float), samples)
     return st

@@ -230,12 +230,14 @@ def post_burn_in_statistics(pe, calculate_post_burn_in_log_priors_vec=False):
         pe.post_burn_in_log_priors_vec = lp.cpu().numpy().reshape(-1, 1)
     mode, coef = ST.filter_settings(pes)
     want_kl = pes['mcmc_info_gain_returned'] == 'KL_divergence'
-    if not want_kl and pes['mcmc_info_gain_cutoff'] != 0:
-        raise NotImplementedError("mcmc_info_gain_cutoff != 0 is not supported")
     R = ST.device_statistics(dev['samples'], dev['logp'], dev['logprior'], mode, coef,
                              prior_samples=pe.samples_of_prior if want_kl else None, kl_bins=100, logp_fn=pe.getLogP_batch)
     pe.gpu_launches += R.gpu_launches
     pe.device_statistics = R
+    if not want_kl and pes['mcmc_info_gain_cutoff'] != 0:                                             # IP.py:1805-1843
+        _, kl, kp = R.kept_rows()
+        R.info_gain_log_ratio = ST.info_gain_log_ratio_cutoff(kl, kp, R.evidence, float(pes['mcmc_info_gain_cutoff']))
+        pe.gpu_launches += 1
     if mode != _lib.FILTER_NONE or getattr(pe, '_host_arrays_pending', False):                        # IP.py:1919-1921
         ks, kl, kp = R.kept_rows()
         pe.gpu_launches += 1

@@ -94,3 +94,19 @@ def device_statistics(samples, logp, logprior=None, filter_mode=_lib.FILTER_NONE
         return o_s, o_l.reshape(-1, 1), (o_p.reshape(-1, 1) if o_p is not None else None)
     R._compact = compact
     return R
+
+
+def info_gain_log_ratio_cutoff(logp, logprior, evidence, cutoff):
+    """The truncated log-ratio information gain of calculateInfoGain for mcmc_info_gain_cutoff != 0 (IP.py:1805-1843) on the
+    device vectors of the kept rows: rows whose log-prior or log-posterior is NaN or below ln(cutoff) are dropped, the others
+    contribute ln(exp(logP) / evidence) - logPrior with non-finite terms counted as 0; no rows left -> NaN (numpy's mean of
+    an empty array)."""
+    lp, pr = logp.reshape(-1), logprior.reshape(-1)
+    lc = float(np.log(cutoff))
+    keep = ~(torch.isnan(lp) | torch.isnan(pr) | (lp < lc) | (pr < lc))
+    lp, pr = lp[keep], pr[keep]
+    if lp.numel() == 0:
+        return float('nan')
+    ratios = torch.log(torch.exp(lp) / evidence) - pr
+    ratios = torch.where(torch.isfinite(ratios), ratios, torch.zeros_like(ratios))
+    return float(ratios.mean().item())

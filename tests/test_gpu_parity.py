@@ -1205,3 +1205,26 @@ def test_full_covariance_value_independent_of_batch_size(env):
     want = np.array([mvn.logpdf(x=y[:n], mean=(Phi @ t)[:n], cov=Sig) + mvn.logpdf(x=y[n:], mean=(Phi @ t)[n:], cov=Sig)
                      for t in th[:6].cpu().numpy()])
     np.testing.assert_allclose(ll, want, rtol=1e-12)
+
+
+@pytest.mark.gpu
+def test_info_gain_cutoff_vs_reference_fixture(env, golden):
+    """parameter_estimation_settings['mcmc_info_gain_cutoff'] != 0 (IP.py:1805-1843): the truncated log-ratio information gain
+    of the unmodified reference (tests/golden/info_gain_cutoff.npz) from the device vectors of the kept rows; 1e-11 relative
+    (summation order, device exp / log), NaN when the cutoff removes every row."""
+    PEUQSE, orc, _, torch = env
+    g, src = golden("info_gain_cutoff"), golden("post_burn_in_statistics")
+    for key in g.files:
+        filt, cutoff, info_gain, evidence, n_kept = g[key]
+        PE = make_pe(PEUQSE, PEUQSE.QuadraticModel(X00), Y00, S00, [200, 500], [100, 200],
+                     settings={'mcmc_threshold_filter_samples': bool(filt), 'mcmc_threshold_filter_coefficient': 'auto',
+                               'mcmc_threshold_filter_benchmark': 'auto', 'mcmc_info_gain_returned': 'log_ratio',
+                               'mcmc_info_gain_cutoff': float(cutoff)})
+        PE.post_burn_in_samples = src['pbs_samples'].copy()
+        PE.post_burn_in_log_posteriors_un_normed_vec = src['pbs_logP'].copy()
+        PE.post_burn_in_log_priors_vec = src['pbs_log_priors'].copy()
+        res = PE.calculatePostBurnInStatistics()
+        assert len(PE.post_burn_in_samples) == int(n_kept)
+        np.testing.assert_allclose(PE.evidence, evidence, rtol=1e-12)
+        np.testing.assert_allclose(res[4], info_gain, rtol=1e-11, equal_nan=True)
+        np.testing.assert_allclose(PE.info_gain_log_ratio, info_gain, rtol=1e-11, equal_nan=True)

@@ -357,3 +357,15 @@ def test_autocorr_time_restatement_known_answers():
     assert np.array_equal(r['window_indices'], np.exp(np.linspace(0, np.log(R), 21)).astype(int)[1:]) and r['taus'].shape == (20, 3)
     np.testing.assert_allclose(r['final_parameter_values'], (1 + rho) / (1 - rho), rtol=0.08)
     np.testing.assert_allclose(r['combined'], np.prod(r['taus'], axis=1))
+
+
+def test_info_gain_cutoff_vs_reference(golden):
+    """mcmc_info_gain_cutoff != 0 (IP.py:1805-1843): the truncated log-ratio information gain of the unmodified reference
+    (tests/golden/make_golden_cutoff.py) on the sample arrays of the statistics fixture, bit for bit."""
+    g, src = golden("info_gain_cutoff"), golden("post_burn_in_statistics")
+    for key in g.files:
+        filt, cutoff, info_gain, evidence, n_kept = g[key]
+        st = orc.post_burn_in_statistics_filtered(src['pbs_samples'], src['pbs_logP'], src['pbs_log_priors'], 'auto', 2.0,
+                                                  bool(filt), info_gain_cutoff=cutoff)
+        assert len(st['samples']) == int(n_kept) and st['evidence'] == evidence
+        assert np.array_equal(st['info_gain_log_ratio'], info_gain, equal_nan=True), key
