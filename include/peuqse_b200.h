@@ -106,7 +106,8 @@ int peuqse_version(void);
 /* device properties the host layer sizes grids with: out[0]=SM count, out[1]=max smem/block (opt-in), out[2]=cc major*10+minor */
 int peuqse_device_info(int32_t* out3);
 
-/* fp64 pipe microbenchmark: *instr_per_s = device-wide fp64 instruction rate; mode 0 = DFMA chains, 1 = DMUL+DADD pairs.
+/* fp64 pipe microbenchmark: *instr_per_s = device-wide fp64 instruction rate; mode 0 = DFMA chains, 1 = DMUL+DADD pairs;
+ * modes 3 / 4: mma.sync.m8n8k4.f64 (DMMA) from registers, 8 / 4 accumulators per warp -- the result is then FLOP/s.
  * d_scratch: one double of device memory.  Synchronises the stream. */
 int peuqse_bench_fp64(int32_t mode, double* instr_per_s, double* d_scratch, void* stream);
 

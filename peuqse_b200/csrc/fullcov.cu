@@ -2,6 +2,7 @@
 //   maha_b = || (y - sim_b) @ U ||^2,   ll_b += -0.5*(rank*log(2pi) + log_pdet + maha_b)
 // with U = u*sqrt(1/s) from scipy's _PSD (scipy/stats/_multivariate.py:208-236, 590-591) hoisted to set-up.
 // Replaces one multivariate_normal.logpdf (an n x n eigendecomposition) per point (IP.py:2960).
+#include <cstdint>
 #include "common.cuh"
 #include "eval.cuh"
 #include "launch.cuh"
@@ -102,14 +103,14 @@ __device__ __forceinline__ void qd_epilogue(const double (&acc)[4][2][2], long l
 // than SMs, and a 256-step K loop is pure latency): blockIdx.z is the chunk, the chunk's accumulators go to
 // frag[chunk][tile][16][256] and k_quadform_split_finish combines them -- the same additions in the same order, so a
 // row's value does not depend on the size of the batch it is evaluated in.
-template <bool SPLIT>
+template <bool SPLIT, bool VEC>
 __global__ void __launch_bounds__(256, 3) k_quadform_dmma(const double* __restrict__ sim, int ld_sim, int off,
                                                       const int* __restrict__ src, const double* __restrict__ y,
                                                       const double* __restrict__ U, int n, long long B,
                                                       double* __restrict__ partial /* [gridDim.x][B] */,
                                                       double* __restrict__ frag) {
-    __shared__ double As[2][QD_BM][QD_LDA];
-    __shared__ double Bs[2][QD_BK][QD_LDB];
+    __shared__ __align__(16) double As[2][QD_BM][QD_LDA];
+    __shared__ __align__(16) double Bs[2][QD_BK][QD_LDB];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 2, wn = warp & 3;                   // 2 x 4 warps: each owns 32 x 16 of the 64 x 64 tile
     const long long bm = (long long)blockIdx.y * QD_BM;
@@ -120,6 +121,25 @@ __global__ void __launch_bounds__(256, 3) k_quadform_dmma(const double* __restri
     const long long arow = bm + ar;
     double ra[4], rb[4];
     auto load_tiles = [&](int k0) {
+        if (VEC) {
+            // simulated values in place (src is the identity), n a multiple of 4 and every row start 16-byte aligned: the four
+            // consecutive elements of a thread are two 16-byte loads, no index gather in front of them
+            const int kk = k0 + ak, kb = k0 + br, cc = bn + bc;
+            ra[0] = ra[1] = ra[2] = ra[3] = 0.0;
+            rb[0] = rb[1] = rb[2] = rb[3] = 0.0;
+            if (arow < B && kk < n) {
+                const double2* sp = reinterpret_cast<const double2*>(sim + arow * ld_sim + off + kk);
+                const double2* yp = reinterpret_cast<const double2*>(y + off + kk);
+                const double2 s0 = sp[0], s1 = sp[1], y0 = __ldg(yp), y1 = __ldg(yp + 1);
+                ra[0] = y0.x - s0.x; ra[1] = y0.y - s0.y; ra[2] = y1.x - s1.x; ra[3] = y1.y - s1.y;   // x - mean (IP.py:2960)
+            }
+            if (kb < n && cc < n) {
+                const double2* up = reinterpret_cast<const double2*>(U + (size_t)kb * n + cc);
+                const double2 u0 = __ldg(up), u1 = __ldg(up + 1);
+                rb[0] = u0.x; rb[1] = u0.y; rb[2] = u1.x; rb[3] = u1.y;
+            }
+            return;
+        }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int kk = k0 + ak + q;
@@ -129,11 +149,11 @@ __global__ void __launch_bounds__(256, 3) k_quadform_dmma(const double* __restri
         }
     };
     auto store_tiles = [&](int st) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            As[st][ar][ak + q] = ra[q];
-            Bs[st][br][bc + q] = rb[q];
-        }
+        // (ar * QD_LDA + ak) and (br * QD_LDB + bc) are multiples of 2 doubles: two 16-byte stores per operand
+        double2* ap = reinterpret_cast<double2*>(&As[st][ar][ak]);
+        double2* bp = reinterpret_cast<double2*>(&Bs[st][br][bc]);
+        ap[0] = make_double2(ra[0], ra[1]); ap[1] = make_double2(ra[2], ra[3]);
+        bp[0] = make_double2(rb[0], rb[1]); bp[1] = make_double2(rb[2], rb[3]);
     };
     const int nk = (n + QD_BK - 1) / QD_BK;
     double tot[4][2][2];
@@ -251,17 +271,20 @@ int pq_fullcov_logp(const peuqse_problem* p, const double* d_theta, const double
             const dim3 grid((unsigned)ntn, (unsigned)((B + QD_BM - 1) / QD_BM));
             // fewer tiles than two per SM and a K loop long enough to be worth cutting: one CTA per (tile, K chunk)
             const bool split = (long long)grid.x * grid.y < 2LL * p->sm_count && n >= 16 * QD_BK;
+            const bool vec = p->src_identity && n % 4 == 0 && p->d.n_total % 2 == 0 && p->d.resp_off[r] % 2 == 0 &&
+                             ((uintptr_t)d_sim | (uintptr_t)(p->d.y) | (uintptr_t)(p->d.U[r])) % 16 == 0;
             if (split) {
                 double* frag = nullptr;
                 e = cudaMallocAsync((void**)&frag, (size_t)QD_CHUNKS * grid.x * grid.y * 16 * 256 * sizeof(double), st);
                 if (e != cudaSuccess) { cudaFreeAsync(part, st); rc = pq_set_cuda_error(e, "cudaMallocAsync(quadform fragments)", __LINE__); break; }
-                k_quadform_dmma<true><<<dim3(grid.x, grid.y, QD_CHUNKS), 256, 0, st>>>(d_sim, p->d.n_total, p->d.resp_off[r], p->d.src, p->d.y,
-                                                                                      p->d.U[r], n, B, part, frag);
+                auto kern = vec ? k_quadform_dmma<true, true> : k_quadform_dmma<true, false>;
+                kern<<<dim3(grid.x, grid.y, QD_CHUNKS), 256, 0, st>>>(d_sim, p->d.n_total, p->d.resp_off[r], p->d.src, p->d.y, p->d.U[r], n, B,
+                                                                     part, frag);
                 k_quadform_split_finish<<<grid, 256, 0, st>>>(frag, B, part);
                 cudaFreeAsync(frag, st);
             } else {
-                k_quadform_dmma<false><<<grid, 256, 0, st>>>(d_sim, p->d.n_total, p->d.resp_off[r], p->d.src, p->d.y, p->d.U[r], n, B, part,
-                                                            nullptr);
+                auto kern = vec ? k_quadform_dmma<false, true> : k_quadform_dmma<false, false>;
+                kern<<<grid, 256, 0, st>>>(d_sim, p->d.n_total, p->d.resp_off[r], p->d.src, p->d.y, p->d.U[r], n, B, part, nullptr);
             }
             k_quadform_reduce<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(part, ntn, B, p->d.resp_c[r], ll);
             e = cudaGetLastError();

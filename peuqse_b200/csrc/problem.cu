@@ -193,6 +193,10 @@ extern "C" int peuqse_problem_create(const peuqse_problem_desc* h, peuqse_proble
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, p->device);
     p->sm_count = prop.multiProcessorCount;
+    p->src_identity = 1;
+    if (h->src)
+        for (size_t i = 0; i < nt; ++i)
+            if (h->src[i] != (int32_t)i) { p->src_identity = 0; break; }
     p->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     p->obs_smem_bytes = pq_obs_smem_bytes(d);
     *out = p;
@@ -230,6 +234,26 @@ __global__ void __launch_bounds__(256) k_bench_fp64(int iters, int mode, double 
 #pragma unroll
     for (int j = 0; j < 8; ++j) s += a[j];
     if (s == 123.456) out[0] = s;    // keep the chains alive
+}
+
+// DMMA probe: every warp issues rounds of NACC independent mma.sync.m8n8k4.f64 accumulations from registers only (no shared
+// memory, no loads): the ceiling for the dense-covariance contraction (csrc/fullcov.cu).  256 FMA = 512 flop per instruction.
+template <int NACC>
+__global__ void __launch_bounds__(256) k_bench_dmma(int iters, double seed, double* __restrict__ out) {
+    double c[NACC][2];
+#pragma unroll
+    for (int j = 0; j < NACC; ++j) c[j][0] = c[j][1] = 0.0;
+    const double a = seed + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < NACC; ++j)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[j][0]), "+d"(c[j][1]) : "d"(a), "d"(b));
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < NACC; ++j) s += c[j][0] + c[j][1];
+    if (s == 123.456) out[0] = s;
 }
 
 // returns through *instr_per_s the measured fp64 instruction rate (instructions, not flops) of the whole device
@@ -295,6 +319,24 @@ extern "C" int peuqse_bench_fp64(int32_t mode, double* instr_per_s, double* d_sc
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
         *instr_per_s = (double)nb * 256.0 * it * 48.0 / (ms * 1e-3);
+        return PEUQSE_OK;
+    }
+    if (mode == 3 || mode == 4) {   // DMMA m8n8k4: 8 (mode 3) or 4 (mode 4) accumulators per warp, 8 CTAs of 8 warps per SM; result = flop/s
+        const int nb = prop.multiProcessorCount * 8, it = 20000, nacc = mode == 3 ? 8 : 4;
+        auto run = [&](int n_it) {
+            if (mode == 3) k_bench_dmma<8><<<nb, 256, 0, st>>>(n_it, 1.0, d_scratch);
+            else k_bench_dmma<4><<<nb, 256, 0, st>>>(n_it, 1.0, d_scratch);
+        };
+        run(100);
+        PQ_CUDA_OK(cudaEventRecord(e0, st));
+        run(it);
+        PQ_CUDA_OK(cudaEventRecord(e1, st));
+        PQ_CUDA_OK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        PQ_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        *instr_per_s = (double)nb * 8.0 * it * nacc * 512.0 / (ms * 1e-3);
         return PEUQSE_OK;
     }
     if (mode >= 10) {   // 10 + log2(chains): dependent-chain probe, one warp per scheduler; result = DFMA/s of the device

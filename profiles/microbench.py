@@ -38,7 +38,8 @@ ms = timeit(lambda: x.sum())
 out["sum_800MB_read_only_GBs"] = 8 * N / ms / 1e6
 L = _lib.load()
 scratch = torch.zeros(8, dtype=torch.float64, device="cuda")
-for mode, name in ((0, "fp64_dfma_instr_per_s"), (1, "fp64_dmul_dadd_instr_per_s")):
+for mode, name in ((0, "fp64_dfma_instr_per_s"), (1, "fp64_dmul_dadd_instr_per_s"), (3, "fp64_dmma_m8n8k4_flop_per_s_8acc"),
+                   (4, "fp64_dmma_m8n8k4_flop_per_s_4acc")):
     r = C.c_double()
     _lib.check(L.peuqse_bench_fp64(mode, C.byref(r), _lib.ptr(scratch), _lib.current_stream()))
     out[name] = r.value
