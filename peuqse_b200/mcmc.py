@@ -347,11 +347,11 @@ def ess_batched(pe, start, n_iters, seed, mu0=1.0, tune=True, max_rounds=10000, 
                 z = logp_rows(X0[idx] + Bd[idx2, None] * dirs[idx])
                 neval += idx2.numel()
                 grow = Z0[idx] < z
-                gi = idx2[grow]
-                Bd[gi] += sgn[gi]
-                cnt[gi] -= 1.0
+                g1 = grow.to(Bd.dtype)                            # masked updates instead of boolean indexing (a host
+                Bd[idx2] = Bd[idx2] + sgn[idx2] * g1              # synchronisation each): x + 0.0 leaves x as it is
+                cnt[idx2] = cnt[idx2] - g1
                 n_dev[0] += grow.sum()
-                mask[idx2[~grow]] = False
+                mask[idx2] = grow
                 mask &= cnt >= 1
                 rounds += 1
                 if rounds > max_rounds:
@@ -369,13 +369,13 @@ def ess_batched(pe, start, n_iters, seed, mu0=1.0, tune=True, max_rounds=10000, 
                 z = logp_rows(cand)
                 neval += idx.numel()
                 ok = Z0[idx] < z
-                Xn[idx[ok]] = cand[ok]
-                Zn[idx[ok]] = z[ok]
-                mask[idx[ok]] = False
-                rej, wr = idx[~ok], wd[~ok]
-                Lb[rej[wr < 0]] = wr[wr < 0]
-                Rb[rej[wr > 0]] = wr[wr > 0]
-                n_dev[1] += (~ok).sum()
+                rej = ~ok
+                Xn[idx] = torch.where(ok[:, None], cand, Xn[idx])
+                Zn[idx] = torch.where(ok, z, Zn[idx])
+                mask[idx] = rej
+                Lb[idx] = torch.where(rej & (wd < 0), wd, Lb[idx])
+                Rb[idx] = torch.where(rej & (wd > 0), wd, Rb[idx])
+                n_dev[1] += rej.sum()
                 rounds += 1
                 if rounds > max_rounds:
                     raise RuntimeError("Number of contractions exceeded maximum limit! Increase mcmc_maxiter.")
