@@ -91,7 +91,8 @@ def autocorr_times(chains, windows=None, c=5.0):
     IP.py:3918).  Per window: csrc/diag.cu k_act_concat writes, for all parameters in one read, the demeaned walker-major
     series zero-padded to twice the next power of two; the transform pair is cuFFT (torch.fft -- a plain library FFT, like
     numpy's in the routine this replaces); the normalisation, running sum and automated window stay on the device (no host
-    synchronisation per window).  Parameters are transformed in groups sized to the free device memory."""
+    synchronisation per window).  Device memory: k series of 2 * next_pow2(R * C) doubles for the largest window plus three
+    transform buffers of that length (C3 shape: ~80 GB beside the 17.7 GB of samples)."""
     L = _lib.load()
     dev = torch.device("cuda", torch.cuda.current_device())
     x = chains if torch.is_tensor(chains) else torch.as_tensor(np.ascontiguousarray(np.asarray(chains, dtype=float)))
