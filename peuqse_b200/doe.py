@@ -106,6 +106,25 @@ class ScenarioBatch:
         self._d_stats = out
         return out.cpu().numpy()
 
+    def cutoff_information_gain(self, run, burn_in, cutoff):
+        """Log-ratio information gain of every scenario with mcmc_info_gain_cutoff != 0 (IP.py:1805-1843), after statistics():
+        of a scenario's kept rows (logP >= its filter cut) those whose log-prior or log-posterior is NaN or below ln(cutoff)
+        are dropped, the others contribute ln(exp(logP) / evidence) - logPrior (non-finite terms count 0); mean over the rows
+        left, NaN if there are none.  One masked reduction over logp / logprior [R, S, chains] on the device; host array [S]."""
+        L = _lib.scen_stats_layout(self.pe.k)
+        cps = run['chains_per_scenario']
+        lp = run['logp'][int(burn_in):].reshape(-1, self.S, cps)
+        pr = run['logprior'][int(burn_in):].reshape(-1, self.S, cps)
+        cut = self._d_stats[:, L['CUT']].reshape(1, self.S, 1)
+        ev = self._d_stats[:, L['EVIDENCE']].reshape(1, self.S, 1)
+        lc = float(np.log(cutoff))
+        keep = ~(lp < cut) & ~(torch.isnan(lp) | torch.isnan(pr) | (lp < lc) | (pr < lc))
+        ratios = torch.log(torch.exp(lp) / ev) - pr
+        ratios = torch.where(keep & torch.isfinite(ratios), ratios, torch.zeros_like(ratios))
+        n = keep.sum(dim=(0, 2)).to(torch.float64)
+        self.pe.gpu_launches += 1
+        return (ratios.sum(dim=(0, 2)) / n).cpu().numpy()            # 0 / 0 = NaN: numpy's mean of no rows
+
     def kl_information_gain(self, run, burn_in, prior_samples, bins=100):
         """KL-divergence information gain of every scenario (after statistics()): host array [S, 1 + k] = total, each parameter."""
         k = self.pe.k
@@ -186,8 +205,6 @@ def run_info_gain_matrices(pe, modulations, searchType='doMetropolisHastings'):
     chol = step_cholesky(pe.Q_covmat, pes['mcmc_relative_step_length'])
     mode, coef = ST.filter_settings(pes)
     want_kl = pes['mcmc_info_gain_returned'] == 'KL_divergence'
-    if not want_kl and pes['mcmc_info_gain_cutoff'] != 0:
-        raise NotImplementedError("mcmc_info_gain_cutoff != 0 is not supported")
     if mode == _lib.FILTER_MU_AP:
         raise NotImplementedError("design-of-experiments batches support the 'auto' and 'MAP' filter benchmarks")
     want_each = doe.get('info_gains_matrices_multiple_parameters', 'sum') == 'each'
@@ -201,6 +218,8 @@ def run_info_gain_matrices(pe, modulations, searchType='doMetropolisHastings'):
         stats_rows = batch.statistics(run, burn, mode, coef)
         if not want_kl:
             gains = stats_rows[:, _lib.scen_stats_layout(pe.k)['INFO_GAIN_LOG_RATIO']].copy()
+            if pes['mcmc_info_gain_cutoff'] != 0:                                                      # IP.py:1805-1843
+                gains = batch.cutoff_information_gain(run, burn, float(pes['mcmc_info_gain_cutoff']))
         else:
             # the KL form bins prior and posterior samples on scenario-specific joint edges: one CTA per scenario (k_scen_kl)
             kl = batch.kl_information_gain(run, burn, pe.samples_of_prior, bins=100)

@@ -345,3 +345,27 @@ def test_large_scenario_batch_properties(env, golden):
             np.testing.assert_allclose(st[i[0], lay['INFO_GAIN_LOG_RATIO']], row[2], rtol=1e-9)
             hits += 1
     assert hits >= 9
+
+
+def test_info_gain_cutoff_in_scenario_batches(env, golden):
+    """mcmc_info_gain_cutoff != 0 (IP.py:1805-1843) inside design-of-experiments batches: the truncated log-ratio information
+    gain of every scenario against the oracle (whose cutoff routine is pinned bit for bit by tests/golden/info_gain_cutoff.npz)
+    replaying the same draws; a cutoff above every prior density leaves no rows: NaN, as numpy's mean of nothing."""
+    PEUQSE, orc, _, _ = env
+    g = golden("doe")
+    L, BURN, STEP, DH, DS, DHU, DSU, SIG = g['settings']
+    conds = orc.doe_conditions([500, 0.5], [100, 0.1], [2, 2], 'xyz')
+    build = lambda y: orc.build_problem([DH, DS], [DHU, DSU], y, [SIG] * 3)
+    sim = lambda c: orc.sim_langmuir_log(c[0], c[1])
+    plain = doe_pe(PEUQSE, g, 'xyz', True).doeGetInfoGainMatrix(g['theta_true'])
+    for cutoff in (0.13, 0.4):
+        PE = doe_pe(PEUQSE, g, 'xyz', True, mcmc_info_gain_cutoff=cutoff)
+        M = PE.doeGetInfoGainMatrix(g['theta_true'])
+        Mo, _ = orc.doe_info_gain_matrix(build, sim, conds, g['theta_true'], [DH, DS], g['deltas'], g['us'], int(BURN),
+                                         dict(filter_samples=True, benchmark='auto', coef=2.0, info_gain_cutoff=cutoff))
+        np.testing.assert_allclose(M[:, 2], Mo[:, 2], rtol=1e-9, equal_nan=True)
+        if cutoff == 0.13:
+            fin = np.isfinite(M[:, 2])
+            assert 10 <= fin.sum() < 25 and not np.allclose(M[fin, 2], plain[fin, 2])        # the cutoff removed rows, in some scenarios all
+        else:
+            assert np.isnan(M[:, 2]).all()
