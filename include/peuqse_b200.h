@@ -318,18 +318,43 @@ typedef struct peuqse_ess_spec {
     int32_t tune;                /* adapt mu during the run */
     int32_t max_rounds;          /* stepping-out / shrink rounds bound (mcmc_maxiter) */
     int32_t k;
-    int32_t reserved;
+    int32_t driver;              /* 0 = choose (per-walker kernels for diagonal responses, rounds for full covariance),
+                                    1 = per-walker kernels (csrc/ess.cu), 2 = round-synchronous driver (csrc/ess_rounds.cu);
+                                    both consume the same Philox draws, so the walkers do not depend on the choice */
 } peuqse_ess_spec;
 
 /*
  * d_x[W][k], d_logp_x[W]: in = start positions and their logP, out = final positions.
- * d_chain[n_iters][W][k], d_chain_logp[n_iters][W] (nullable).  d_info[4]: neval, final mu, n_expand, n_contract.
- * d_work: peuqse_ess_work_bytes(W,k).  Built-in models only (EXTERNAL: drive the rounds from the host
- * with peuqse_logp_from_sim).  Returns PEUQSE_ERR_INVALID if a start point has non-finite logP.
+ * d_chain[n_iters][W][k], d_chain_logp[n_iters][W] (nullable).  d_info[5]: neval, final mu, n_expand, n_contract, error.
+ * d_work: peuqse_ess_work_bytes(W,k) (per-walker kernels only; may be NULL for the round-synchronous driver).
+ * Built-in models only.  The round-synchronous driver synchronises the stream once per round (it needs the size of the
+ * next batch) and returns PEUQSE_ERR_INVALID when a stepping-out / shrink loop exceeds max_rounds.
  */
 int64_t peuqse_ess_work_bytes(int64_t n_walkers, int32_t k);
 int peuqse_ess_run(const peuqse_problem* p, const peuqse_ess_spec* spec, double* d_x, double* d_logp_x,
                    double* d_chain, double* d_chain_logp, double* d_info, void* d_work, void* stream);
+
+/*
+ * The round-synchronous driver step by step, for callers that evaluate the log-posterior themselves (torch-callable
+ * simulators: simulate the block, then peuqse_logp_from_sim; multi-GPU: share the block's rows out over the ranks).
+ * replaces: the per-walker Python calls of zeus.EnsembleSampler.run_mcmc (IP.py:2495-2498).  Per ensemble iteration `it`
+ * and half-ensemble `half` in (0, 1):
+ *     peuqse_essr_begin_half(h, it, half, d_x, d_logp_x, d_cand, &n, stream);
+ *     while (n > 0) { <d_rows[i] = logP(d_cand[i][0..k)), i < n>;  peuqse_essr_round(h, d_rows, d_cand, &n, stream); }
+ *     peuqse_essr_end_half(h, d_x, d_logp_x, stream);
+ * then peuqse_essr_end_iteration (adapts mu).  d_cand[W][k] receives each round's block of candidate points (at most
+ * W rows); begin_half and round synchronise the stream and return the block's row count in *n_rows.  spec->n_iters is
+ * not used (the caller owns the loop); iteration numbers are offsets from spec->first_iter.
+ */
+typedef struct peuqse_essr peuqse_essr;
+int peuqse_essr_create(const peuqse_ess_spec* spec, peuqse_essr** out);
+int peuqse_essr_destroy(peuqse_essr* h);
+int peuqse_essr_begin_half(peuqse_essr* h, int64_t it, int32_t half, const double* d_x, const double* d_logp_x,
+                           double* d_cand, int64_t* n_rows, void* stream);
+int peuqse_essr_round(peuqse_essr* h, const double* d_logp_rows, double* d_cand, int64_t* n_rows, void* stream);
+int peuqse_essr_end_half(peuqse_essr* h, double* d_x, double* d_logp_x, void* stream);
+int peuqse_essr_end_iteration(peuqse_essr* h, void* stream);
+int peuqse_essr_info(peuqse_essr* h, double* d_info /*[5] as peuqse_ess_run*/, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Post-burn-in statistics of device-resident samples:

@@ -1022,6 +1022,105 @@ def ess_run(logp_batch: Callable, start, nsteps, rng: np.random.Generator, mu0=1
     return chain, chain_lp, neval, mu
 
 
+def ess_run_philox(logp_batch: Callable, start, nsteps, seed, mu0=1.0, maxiter=10000, tune=True, tolerance=0.05,
+                   patience=5, maxsteps=10000, first_iter=0):
+    """The same algorithm as ess_run (zeus.EnsembleSampler.run_mcmc with the differential move, called by the reference
+    at IP.py:2495-2498; Karamanis & Beutler, arXiv:2002.06212), drawing from the counter-based Philox generator in the
+    layout of peuqse_b200/csrc/ess_common.cuh, walker by walker, so that a device run can be replayed step for step:
+        counter index = ((first_iter + it) * 2 + half) << 32 | walker, stream STREAM_ESS
+        block 0xffffffff (half 0)  words (0,1): shuffle key -- the walkers are ordered by key (ties by index)
+        block 0   u_a -> first complementary walker floor(u_a * H), u_b -> second floor(u_b * (H-1)), skipping the first
+        block 1   u_a -> Exp(1) = -log(1 - u_a) of the slice level, u_b -> left end L = -u_b, R = L + 1
+        block 2   u_a -> J = floor(maxsteps * u_a), K = maxsteps - 1 - J
+        block 3 + r // 2   shrink round r: u_a for even r, u_b for odd r
+    Comparisons follow zeus: expand / accept iff Z0 < Z (strict).  Returns chain[nsteps,W,k], logp[nsteps,W], info dict."""
+    from . import philox_np as px
+    X = np.array(start, dtype=float)
+    W, k = X.shape
+    H = W // 2
+    Z = np.asarray(logp_batch(X), dtype=float).copy()
+    if not np.all(np.isfinite(Z)):
+        raise ValueError("Invalid walker initial positions! Initialise walkers from positions of finite log probability.")
+    chain = np.empty((nsteps, W, k))
+    chain_lp = np.empty((nsteps, W))
+    mu, tuning, ncount = float(mu0), bool(tune), 0
+    neval, tot_exp, tot_con = 0, 0, 0
+    walkers = np.arange(W, dtype=np.uint64)
+    for it in range(nsteps):
+        base = np.uint64((first_iter + it) * 2)
+        r = px.raw_block(seed, px.STREAM_ESS, (base << np.uint64(32)) | walkers, 0xffffffff)
+        keys = (r[:, 0].astype(np.uint64) << np.uint64(32)) | r[:, 1].astype(np.uint64)
+        perm = np.lexsort((np.arange(W), keys))                       # rank by key, ties by walker index
+        nexp = ncon = 0
+        for half in range(2):
+            act, comp = perm[half * H:(half + 1) * H], perm[(1 - half) * H:(2 - half) * H]
+            idx = ((base + np.uint64(half)) << np.uint64(32)) | act.astype(np.uint64)
+            ua, ub = px.uniform_pair(seed, px.STREAM_ESS, idx, 0)
+            i1 = np.minimum((ua * float(H)).astype(np.int64), H - 1)
+            i2 = np.minimum((ub * float(H - 1)).astype(np.int64), H - 2)
+            i2 = i2 + (i2 >= i1)
+            dirs = (2.0 * mu) * (X[comp[i1]] - X[comp[i2]])
+            ua, ub = px.uniform_pair(seed, px.STREAM_ESS, idx, 1)
+            Z0 = Z[act] - (-np.log(1.0 - ua))
+            Lb = -ub
+            Rb = Lb + 1.0
+            ua, _ = px.uniform_pair(seed, px.STREAM_ESS, idx, 2)
+            J = np.floor(float(maxsteps) * ua)
+            K = (float(maxsteps) - 1.0) - J
+            X0 = X[act].copy()
+            for bound, budget, step in ((Lb, J, -1.0), (Rb, K, 1.0)):   # stepping out: left, then right
+                mask = budget >= 1.0
+                rounds = 0
+                while mask.any():
+                    ii = np.where(mask)[0]
+                    z = np.asarray(logp_batch(X0[ii] + bound[ii, None] * dirs[ii]), dtype=float)
+                    neval += len(ii)
+                    grow = Z0[ii] < z
+                    g = ii[grow]
+                    bound[g] += step
+                    budget[g] -= 1.0
+                    nexp += len(g)
+                    mask[ii[~grow]] = False
+                    mask &= budget >= 1.0
+                    if grow.any() and rounds > maxiter:
+                        raise RuntimeError("Number of expansions exceeded maximum limit! Increase mcmc_maxiter.")
+                    rounds += 1
+            mask = np.ones(H, dtype=bool)
+            Xn, Zn = X0.copy(), Z[act].copy()
+            r_sh = 0
+            while mask.any():                                         # shrinking
+                ii = np.where(mask)[0]
+                ua, ub = px.uniform_pair(seed, px.STREAM_ESS, idx[ii], 3 + (r_sh >> 1))
+                u = ub if (r_sh & 1) else ua
+                wd = Lb[ii] + u * (Rb[ii] - Lb[ii])
+                cand = X0[ii] + wd[:, None] * dirs[ii]
+                z = np.asarray(logp_batch(cand), dtype=float)
+                neval += len(ii)
+                ok = Z0[ii] < z
+                Xn[ii[ok]], Zn[ii[ok]] = cand[ok], z[ok]
+                mask[ii[ok]] = False
+                rej, wr = ii[~ok], wd[~ok]
+                Lb[rej[wr < 0]] = wr[wr < 0]
+                Rb[rej[wr > 0]] = wr[wr > 0]
+                ncon += len(rej)
+                if len(rej) and r_sh > maxiter:
+                    raise RuntimeError("Number of contractions exceeded maximum limit! Increase mcmc_maxiter.")
+                r_sh += 1
+            X[act], Z[act] = Xn, Zn
+        tot_exp += nexp
+        tot_con += ncon
+        if tuning:
+            ne = max(1, nexp)
+            frac = ne / (ne + ncon)
+            mu *= 2.0 * frac
+            if abs(frac - 0.5) < tolerance:
+                ncount += 1
+            if ncount > patience:
+                tuning = False
+        chain[it], chain_lp[it] = X, Z
+    return chain, chain_lp, dict(neval=neval, mu=mu, n_expansions=tot_exp, n_contractions=tot_con)
+
+
 def linear_gaussian_posterior(Phi, Sigma_inv_Phi, y, prior_var):
     """Closed form for y ~ N(Phi theta, Sigma), theta ~ N(0, prior_var I): (mean, cov)."""
     A = Phi.T @ Sigma_inv_Phi + np.eye(Phi.shape[1]) / prior_var

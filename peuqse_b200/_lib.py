@@ -71,7 +71,7 @@ def scen_stats_layout(k):
 class ESSSpec(C.Structure):
     _fields_ = [
         ("n_walkers", C.c_int64), ("n_iters", C.c_int64), ("first_iter", C.c_int64), ("seed", C.c_uint64),
-        ("mu0", C.c_double), ("tune", C.c_int32), ("max_rounds", C.c_int32), ("k", C.c_int32), ("reserved", C.c_int32),
+        ("mu0", C.c_double), ("tune", C.c_int32), ("max_rounds", C.c_int32), ("k", C.c_int32), ("driver", C.c_int32),
     ]
 
 
@@ -95,6 +95,8 @@ EXPORTS = [
     "peuqse_comm_allreduce_sum_i64", "peuqse_peer_alloc", "peuqse_peer_create", "peuqse_peer_destroy",
     "peuqse_peer_max_bytes", "peuqse_peer_merge_best", "peuqse_peer_merge_acc", "peuqse_peer_sum_i64", "peuqse_merge_best", "peuqse_merge_acc", "peuqse_mh_run",
     "peuqse_philox_blocks", "peuqse_ess_work_bytes", "peuqse_ess_run",
+    "peuqse_essr_create", "peuqse_essr_destroy", "peuqse_essr_begin_half", "peuqse_essr_round", "peuqse_essr_end_half",
+    "peuqse_essr_end_iteration", "peuqse_essr_info",
     "peuqse_stats_work_bytes", "peuqse_stats_begin", "peuqse_stats_finish", "peuqse_stats_compact",
     "peuqse_scenarios_create", "peuqse_scenarios_destroy", "peuqse_scenarios_synthesize", "peuqse_scenarios_set_observed",
     "peuqse_scenarios_logp", "peuqse_mh_run_scenarios", "peuqse_scenarios_stats",
@@ -161,6 +163,13 @@ def load():
     L.peuqse_ess_work_bytes.restype = i64
     L.peuqse_ess_work_bytes.argtypes = [i64, i32]
     L.peuqse_ess_run.argtypes = [vp, C.POINTER(ESSSpec), vp, vp, vp, vp, vp, vp, vp]
+    L.peuqse_essr_create.argtypes = [C.POINTER(ESSSpec), C.POINTER(vp)]
+    L.peuqse_essr_destroy.argtypes = [vp]
+    L.peuqse_essr_begin_half.argtypes = [vp, i64, i32, vp, vp, vp, C.POINTER(i64), vp]
+    L.peuqse_essr_round.argtypes = [vp, vp, vp, C.POINTER(i64), vp]
+    L.peuqse_essr_end_half.argtypes = [vp, vp, vp, vp]
+    L.peuqse_essr_end_iteration.argtypes = [vp, vp]
+    L.peuqse_essr_info.argtypes = [vp, vp, vp]
     L.peuqse_stats_work_bytes.restype = i64
     L.peuqse_stats_work_bytes.argtypes = []
     L.peuqse_stats_begin.argtypes = [C.POINTER(StatsSpec), vp, vp, i64, vp, vp, vp]

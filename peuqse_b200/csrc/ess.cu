@@ -12,46 +12,7 @@
 #include "eval.cuh"
 #include "launch.cuh"
 #include "philox.cuh"
-
-#define ESS_MAXSTEPS 10000.0          // zeus default `maxsteps`: bound on the stepping-out procedure
-#define ESS_TOLERANCE 0.05            // zeus defaults for the tuning of mu
-#define ESS_PATIENCE 5
-
-struct EssState {                     // lives at the start of d_work
-    double mu;
-    unsigned long long nexp, ncon;    // of the current iteration
-    unsigned long long neval, tot_exp, tot_con;
-    int tune, ncount, error, pad;
-};
-
-struct DevEss {
-    long long W, first_iter;
-    unsigned long long seed;
-    int k, max_rounds;
-};
-
-__device__ __forceinline__ unsigned long long ess_idx(const DevEss& E, long long it, int half, long long w) {
-    return ((unsigned long long)((E.first_iter + it) * 2 + half) << 32) | (unsigned long long)w;
-}
-
-// random permutation of the walkers: rank of a Philox key (ties broken by index)
-__global__ void k_ess_shuffle(const DevEss E, long long it, int* __restrict__ perm, unsigned long long* __restrict__ keys) {
-    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= E.W) return;
-    const Philox4 r = philox_block(E.seed, PQ_STREAM_ESS, ess_idx(E, it, 0, w), 0xffffffffu);
-    keys[w] = ((unsigned long long)r.x << 32) | r.y;
-}
-__global__ void k_ess_rank(const DevEss E, const unsigned long long* __restrict__ keys, int* __restrict__ perm) {
-    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= E.W) return;
-    const unsigned long long kw = keys[w];
-    int rank = 0;
-    for (long long v = 0; v < E.W; ++v) {
-        const unsigned long long kv = keys[v];
-        rank += (kv < kw) || (kv == kw && v < w);
-    }
-    perm[rank] = (int)w;
-}
+#include "ess_common.cuh"
 
 template <int MODEL, int KT, bool WARP>
 __device__ __forceinline__ double ess_logp(const DevProblem& P, const ObsView& O, const double (&th)[KT], int lane) {
@@ -150,40 +111,13 @@ __global__ void __launch_bounds__(WARP ? 256 : 128) k_ess_half(const __grid_cons
     }
 }
 
-// after both halves: adapt mu (zeus' tuning rule), fold the counters, record the ensemble
-__global__ void k_ess_tune(EssState* __restrict__ st) {
-    if (threadIdx.x || blockIdx.x) return;
-    const unsigned long long ne = st->nexp, nc = st->ncon;
-    st->tot_exp += ne;
-    st->tot_con += nc;
-    if (st->tune) {
-        const double nexp = ne < 1 ? 1.0 : (double)ne;
-        const double frac = nexp / (nexp + (double)nc);
-        st->mu *= 2.0 * frac;
-        if (fabs(frac - 0.5) < ESS_TOLERANCE) st->ncount += 1;
-        if (st->ncount > ESS_PATIENCE) st->tune = 0;
-    }
-    st->nexp = 0;
-    st->ncon = 0;
-}
-
-__global__ void k_ess_init(EssState* st, double mu0, int tune) {
-    st->mu = mu0; st->nexp = 0; st->ncon = 0; st->neval = 0; st->tot_exp = 0; st->tot_con = 0;
-    st->tune = tune; st->ncount = 0; st->error = 0; st->pad = 0;
-}
-
-__global__ void k_ess_info(const EssState* st, double* info) {
-    info[0] = (double)st->neval;
-    info[1] = st->mu;
-    info[2] = (double)st->tot_exp;
-    info[3] = (double)st->tot_con;
-    info[4] = (double)st->error;
-}
-
 extern "C" int64_t peuqse_ess_work_bytes(int64_t n_walkers, int32_t k) {
     (void)k;
     return 256 + (int64_t)n_walkers * (int64_t)(sizeof(int) + sizeof(unsigned long long)) + 512;
 }
+
+int pq_ess_run_rounds(const peuqse_problem* p, const peuqse_ess_spec* s, double* d_x, double* d_logp_x, double* d_chain,
+                      double* d_chain_logp, double* d_info, cudaStream_t st);
 
 namespace {
 template <int MODEL, int KT>
@@ -224,14 +158,19 @@ int dispatch_half(const peuqse_problem* p, const DevEss& E, long long it, int ha
 
 extern "C" int peuqse_ess_run(const peuqse_problem* p, const peuqse_ess_spec* s, double* d_x, double* d_logp_x, double* d_chain,
                               double* d_chain_logp, double* d_info, void* d_work, void* stream) {
-    if (!p || !s || !d_x || !d_logp_x || !d_work) return pq_set_error(PEUQSE_ERR_INVALID, "null argument");
+    if (!p || !s || !d_x || !d_logp_x) return pq_set_error(PEUQSE_ERR_INVALID, "null argument");
     if (s->k != p->d.k) return pq_set_error(PEUQSE_ERR_INVALID, "ess k != problem k");
     if (s->n_walkers < 4 || (s->n_walkers & 1)) return pq_set_error(PEUQSE_ERR_INVALID, "ess needs an even number (>= 4) of walkers");
     if (s->n_iters < 0) return pq_set_error(PEUQSE_ERR_INVALID, "negative n_iters");
-    if (p->d.model_id == PEUQSE_MODEL_EXTERNAL || p->d.any_full)
-        return pq_set_error(PEUQSE_ERR_INVALID, "peuqse_ess_run needs a built-in model with diagonal responses; use the batched "
-                                                "round-synchronous driver (peuqse_b200/mcmc.py: ess_batched) otherwise");
+    if (p->d.model_id == PEUQSE_MODEL_EXTERNAL)
+        return pq_set_error(PEUQSE_ERR_INVALID, "peuqse_ess_run needs a built-in model; drive the rounds of a caller-simulated "
+                                                "problem with peuqse_essr_* and peuqse_logp_from_sim");
+    if (s->driver < 0 || s->driver > 2) return pq_set_error(PEUQSE_ERR_INVALID, "ess driver must be 0 (auto), 1 or 2");
+    if (s->driver == 1 && p->d.any_full)
+        return pq_set_error(PEUQSE_ERR_INVALID, "full-covariance responses need the round-synchronous driver (driver 0 or 2)");
     cudaStream_t st = (cudaStream_t)stream;
+    if (s->driver == 2 || p->d.any_full) return pq_ess_run_rounds(p, s, d_x, d_logp_x, d_chain, d_chain_logp, d_info, st);
+    if (!d_work) return pq_set_error(PEUQSE_ERR_INVALID, "null d_work");
     EssState* state = (EssState*)d_work;
     int* perm = (int*)((char*)d_work + 256);
     unsigned long long* keys = (unsigned long long*)((char*)d_work + 256 + ((s->n_walkers * sizeof(int) + 255) / 256) * 256);

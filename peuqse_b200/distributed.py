@@ -48,6 +48,27 @@ def allreduce_np(a, op="sum"):
     return t.cpu().numpy()
 
 
+def broadcast_np(a, src=0):
+    """Rank `src`'s float64 array on every rank (same shape everywhere); identity when not distributed."""
+    rank, size = world()
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+    if size == 1:
+        return a
+    t = torch.from_numpy(a.copy()).to(_comm_device())
+    dist.broadcast(t, src)
+    return t.cpu().numpy()
+
+
+def broadcast_int(v, src=0):
+    """Rank `src`'s integer (up to 63 bits) on every rank."""
+    rank, size = world()
+    if size == 1:
+        return int(v)
+    t = torch.tensor([int(v)], dtype=torch.int64, device=_comm_device())
+    dist.broadcast(t, src)
+    return int(t.item())
+
+
 def allreduce_int_np(a):
     rank, size = world()
     a = np.asarray(a, dtype=np.int64)

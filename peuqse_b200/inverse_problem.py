@@ -261,7 +261,9 @@ class parameter_estimation:
             from scipy.stats import qmc
             with catch_warnings():
                 simplefilter("ignore")
-                sob = qmc.Sobol(d=k, scramble=True).random(numStartPoints)                              # IP.py:718-721, 741-744
+                # IP.py:718-721, 741-744; `seed` (not in the reference, whose points differ from run to run) makes the
+                # scrambling reproducible -- scipy's generator does not follow np.random.seed
+                sob = qmc.Sobol(d=k, scramble=True, seed=seed).random(numStartPoints)
             if kind == 'sobol':
                 first = -2 + 4 * sob                                                                    # IP.py:746
             else:

@@ -265,137 +265,110 @@ def post_burn_in_statistics(pe, calculate_post_burn_in_log_priors_vec=False):
 # ----------------------------------------------------------------------------------------------
 # ensemble slice sampling
 # ----------------------------------------------------------------------------------------------
-def ess_launch(pe, start, n_iters, seed, mu0=1.0, tune=True, max_rounds=10000, first_iter=0, store_chain=True):
-    """Ensemble slice sampling of `n_iters` ensemble iterations from walkers start[W,k].
-    Built-in model + diagonal responses: the per-walker CUDA kernels (peuqse_ess_run).  Torch-callable simulators or
-    full-covariance responses: the round-synchronous driver below (every round is one batched log-posterior launch)."""
+ESS_DRIVER_AUTO, ESS_DRIVER_WALKER, ESS_DRIVER_ROUNDS = 0, 1, 2
+
+
+def _ess_spec(W, k, n_iters, seed, mu0, tune, max_rounds, first_iter, driver):
+    spec = _lib.ESSSpec()
+    spec.n_walkers, spec.n_iters, spec.first_iter, spec.seed = W, int(n_iters), int(first_iter), int(seed) & (2 ** 64 - 1)
+    spec.mu0, spec.tune, spec.max_rounds, spec.k, spec.driver = float(mu0), int(bool(tune)), int(max_rounds), k, int(driver)
+    return spec
+
+
+def _ess_check(L, rc):
+    """Library status -> the exceptions zeus raises (RuntimeError when a stepping-out / shrink loop runs away)."""
+    if rc != 0:
+        msg = L.peuqse_last_error().decode(errors="replace")
+        if "maximum limit" in msg:
+            raise RuntimeError(msg)
+        raise _lib.PeuqseError(f"libpeuqse_b200 error {rc}: {msg}")
+
+
+def ess_launch(pe, start, n_iters, seed, mu0=1.0, tune=True, max_rounds=10000, first_iter=0, store_chain=True,
+               driver=ESS_DRIVER_AUTO, shard=True):
+    """Ensemble slice sampling of `n_iters` ensemble iterations from walkers start[W,k] (zeus.EnsembleSampler.run_mcmc,
+    IP.py:2495-2498).  Built-in model with diagonal responses: the per-walker CUDA kernels (csrc/ess.cu).  Full-covariance
+    responses, torch-callable simulators, several ranks: the round-synchronous device driver (csrc/ess_rounds.cu), every
+    round one batched log-posterior launch.  Both consume the same Philox draws: the walkers do not depend on the driver."""
     from .models import BuiltinModel
-    if not isinstance(pe.simulator, BuiltinModel) or int(pe.host_problem.resp_mode.max()) == _lib.RESP_MVN_FULL:
-        return ess_batched(pe, start, n_iters, seed, mu0=mu0, tune=tune, max_rounds=max_rounds, store_chain=store_chain)
     L = _lib.load()
     dev = _dev()
     X = torch.as_tensor(np.asarray(start, dtype=float), dtype=torch.float64).reshape(-1, pe.k).to(dev).contiguous()
     W, k = X.shape
+    builtin = isinstance(pe.simulator, BuiltinModel)
+    full = int(pe.host_problem.resp_mode.max()) == _lib.RESP_MVN_FULL
+    sharded = bool(shard) and D.world()[1] > 1 and (full or not builtin)
+    if not builtin or sharded:
+        return ess_rounds(pe, X, n_iters, seed, mu0=mu0, tune=tune, max_rounds=max_rounds, first_iter=first_iter,
+                          store_chain=store_chain, shard=sharded)
     Z = pe.getLogP_batch(X).contiguous()
     if not bool(torch.isfinite(Z).all().item()):
         raise ValueError("Invalid walker initial positions! Initialise walkers from positions of finite log probability.")
-    spec = _lib.ESSSpec()
-    spec.n_walkers, spec.n_iters, spec.first_iter, spec.seed = W, int(n_iters), int(first_iter), int(seed) & (2 ** 64 - 1)
-    spec.mu0, spec.tune, spec.max_rounds, spec.k = float(mu0), int(bool(tune)), int(max_rounds), k
+    spec = _ess_spec(W, k, n_iters, seed, mu0, tune, max_rounds, first_iter, driver)
     chain = torch.empty((n_iters, W, k), dtype=torch.float64, device=dev) if store_chain else None
     chain_lp = torch.empty((n_iters, W), dtype=torch.float64, device=dev) if store_chain else None
     info = torch.zeros(8, dtype=torch.float64, device=dev)
-    work = torch.zeros(int(L.peuqse_ess_work_bytes(W, k)), dtype=torch.uint8, device=dev)
-    _lib.check(L.peuqse_ess_run(pe.device_problem.handle, C.byref(spec), _lib.ptr(X), _lib.ptr(Z), _lib.ptr(chain),
-                                _lib.ptr(chain_lp), _lib.ptr(info), _lib.ptr(work), _lib.current_stream()))
-    pe.gpu_launches += 5 * int(n_iters) + 3
-    if int(info[4].item()) != 0:
+    rounds = full or driver == ESS_DRIVER_ROUNDS
+    work = None if rounds else torch.zeros(int(L.peuqse_ess_work_bytes(W, k)), dtype=torch.uint8, device=dev)
+    _ess_check(L, L.peuqse_ess_run(pe.device_problem.handle, C.byref(spec), _lib.ptr(X), _lib.ptr(Z), _lib.ptr(chain),
+                                   _lib.ptr(chain_lp), _lib.ptr(info), _lib.ptr(work), _lib.current_stream()))
+    ih = info.cpu().numpy()
+    if int(ih[4]) != 0:
         raise RuntimeError("Number of expansions / contractions exceeded maximum limit! Increase mcmc_maxiter.")
+    # launches: per-walker driver 5 per iteration; rounds driver 2 per round + the batched log-posterior of each round
+    # (a round evaluates at least one row, so the number of rounds is bounded by the evaluations; reported as a lower bound)
+    pe.gpu_launches += 5 * int(n_iters) + 3
+    info[0] += W                                                  # the start points were evaluated too
     return dict(X=X, Z=Z, chain=chain, chain_logp=chain_lp, info=info)
 
 
-def ess_batched(pe, start, n_iters, seed, mu0=1.0, tune=True, max_rounds=10000, store_chain=True, maxsteps=10000,
-                tolerance=0.05, patience=5, shard=True):
-    """Round-synchronous ensemble slice sampling (same algorithm as csrc/ess.cu) for simulators / likelihoods that must
-    be evaluated in batches: every stepping-out or shrink round gathers the still-active walkers and evaluates their
-    log-posteriors with ONE batched launch (pe.getLogP_batch -> full-covariance contraction for C4)."""
+def ess_rounds(pe, X, n_iters, seed, mu0=1.0, tune=True, max_rounds=10000, first_iter=0, store_chain=True, shard=False):
+    """The round-synchronous driver, rounds issued from here (peuqse_essr_*): for simulators that are torch callables (the
+    block of candidate points goes through the callable, then peuqse_logp_from_sim) and for several ranks (SURVEY 8e, v2:
+    every rank runs the same rounds on the same walkers -- same seed, same draws, same masks -- and evaluates its share of
+    each block's rows; the log-posteriors are all-gathered with NCCL.  A row's value does not depend on the batch it is
+    evaluated in, so the chain is the one a single GPU produces)."""
+    L = _lib.load()
     dev = _dev()
-    g = torch.Generator(device=dev)
-    g.manual_seed(int(seed) & (2 ** 63 - 1))
-    X = torch.as_tensor(np.asarray(start, dtype=float), dtype=torch.float64).reshape(-1, pe.k).to(dev).contiguous()
     W, k = X.shape
-    H = W // 2
-    # multi-GPU (SURVEY 8e, v2): every rank runs this driver with the same seed, hence the same draws and the same masks; the
-    # batch of each round is shared out over the ranks row-wise and the log-posteriors are all-gathered (NCCL).  A row's
-    # value does not depend on the batch it is evaluated in, so the chain is the one a single GPU produces.
     logp_rows = pe.getLogP_batch
-    if shard and D.world()[1] > 1:
+    if shard:
         logp_rows = lambda th: D.sharded_rows(pe.getLogP_batch, th.contiguous(), min_rows_per_rank=8)
     Z = logp_rows(X).clone()
     if not bool(torch.isfinite(Z).all().item()):
         raise ValueError("Invalid walker initial positions! Initialise walkers from positions of finite log probability.")
+    spec = _ess_spec(W, k, n_iters, seed, mu0, tune, max_rounds, first_iter, ESS_DRIVER_ROUNDS)
+    h = C.c_void_p()
+    _lib.check(L.peuqse_essr_create(C.byref(spec), C.byref(h)))
     chain = torch.empty((n_iters, W, k), dtype=torch.float64, device=dev) if store_chain else None
     chain_lp = torch.empty((n_iters, W), dtype=torch.float64, device=dev) if store_chain else None
-    mu, ncount, neval, tot_exp, tot_con = float(mu0), 0, W, 0, 0
-    rnd = lambda n: torch.rand(n, dtype=torch.float64, device=dev, generator=g)
-    for it in range(n_iters):
-        perm = torch.randperm(W, device=dev, generator=g)
-        n_dev = torch.zeros(2, dtype=torch.int64, device=dev)    # expansions, contractions of this iteration
-        for half in (0, 1):
-            act, comp = perm[half * H:(half + 1) * H], perm[(1 - half) * H:(2 - half) * H]
-            i1 = torch.clamp((rnd(H) * H).long(), max=H - 1)
-            i2 = torch.clamp((rnd(H) * (H - 1)).long(), max=H - 2)
-            i2 = i2 + (i2 >= i1).long()
-            dirs = 2.0 * mu * (X[comp[i1]] - X[comp[i2]])
-            X0 = X[act]
-            Z0 = Z[act] + torch.log1p(-rnd(H))                    # logP - Exp(1)
-            Lb = -rnd(H)
-            Rb = Lb + 1.0
-            J = torch.floor(maxsteps * rnd(H))
-            K = (maxsteps - 1.0) - J
-            # stepping out, both ends at once: the 2H boundaries (left ends, then right ends) are independent tasks, a round
-            # evaluates every boundary that is still moving (no draws are consumed here, so the order of evaluation is free);
-            # the only host synchronisation of a round is the size of its index list
-            Bd, cnt, sgn = torch.cat((Lb, Rb)), torch.cat((J, K)), torch.cat((-torch.ones_like(Lb), torch.ones_like(Rb)))
-            mask = cnt >= 1
-            rounds = 0
-            while True:
-                idx2 = mask.nonzero(as_tuple=True)[0]
-                if idx2.numel() == 0:
-                    break
-                idx = idx2 % H
-                z = logp_rows(X0[idx] + Bd[idx2, None] * dirs[idx])
-                neval += idx2.numel()
-                grow = Z0[idx] < z
-                g1 = grow.to(Bd.dtype)                            # masked updates instead of boolean indexing (a host
-                Bd[idx2] = Bd[idx2] + sgn[idx2] * g1              # synchronisation each): x + 0.0 leaves x as it is
-                cnt[idx2] = cnt[idx2] - g1
-                n_dev[0] += grow.sum()
-                mask[idx2] = grow
-                mask &= cnt >= 1
-                rounds += 1
-                if rounds > max_rounds:
-                    raise RuntimeError("Number of expansions exceeded maximum limit! Increase mcmc_maxiter.")
-            Lb, Rb = Bd[:H].clone(), Bd[H:].clone()
-            mask = torch.ones(H, dtype=torch.bool, device=dev)
-            Xn, Zn = X0.clone(), Z[act].clone()
-            rounds = 0
-            while True:                                           # shrinking
-                idx = mask.nonzero(as_tuple=True)[0]
-                if idx.numel() == 0:
-                    break
-                wd = Lb[idx] + rnd(idx.numel()) * (Rb[idx] - Lb[idx])
-                cand = X0[idx] + wd[:, None] * dirs[idx]
-                z = logp_rows(cand)
-                neval += idx.numel()
-                ok = Z0[idx] < z
-                rej = ~ok
-                Xn[idx] = torch.where(ok[:, None], cand, Xn[idx])
-                Zn[idx] = torch.where(ok, z, Zn[idx])
-                mask[idx] = rej
-                Lb[idx] = torch.where(rej & (wd < 0), wd, Lb[idx])
-                Rb[idx] = torch.where(rej & (wd > 0), wd, Rb[idx])
-                n_dev[1] += rej.sum()
-                rounds += 1
-                if rounds > max_rounds:
-                    raise RuntimeError("Number of contractions exceeded maximum limit! Increase mcmc_maxiter.")
-            X[act] = Xn
-            Z[act] = Zn
-        nexp, ncon = (int(v) for v in n_dev.tolist())            # one read per ensemble iteration (the tuning needs them)
-        tot_exp += nexp
-        tot_con += ncon
-        if tune:
-            ne = max(1, nexp)
-            frac = ne / (ne + ncon)
-            mu *= 2.0 * frac
-            if abs(frac - 0.5) < tolerance:
-                ncount += 1
-            if ncount > patience:
-                tune = False
-        if store_chain:
-            chain[it] = X
-            chain_lp[it] = Z
-    info = torch.tensor([neval, mu, tot_exp, tot_con, 0, 0, 0, 0], dtype=torch.float64, device=dev)
+    cand = torch.empty((W, k), dtype=torch.float64, device=dev)
+    info = torch.zeros(8, dtype=torch.float64, device=dev)
+    n = C.c_int64(0)
+    st = _lib.current_stream()
+    launches = 0
+    try:
+        for it in range(int(n_iters)):
+            for half in (0, 1):
+                _ess_check(L, L.peuqse_essr_begin_half(h, it, half, _lib.ptr(X), _lib.ptr(Z), _lib.ptr(cand), C.byref(n), st))
+                launches += 4 - 2 * half
+                while n.value > 0:
+                    rows = logp_rows(cand[:n.value]).contiguous()
+                    _ess_check(L, L.peuqse_essr_round(h, _lib.ptr(rows), _lib.ptr(cand), C.byref(n), st))
+                    launches += 2
+                _lib.check(L.peuqse_essr_end_half(h, _lib.ptr(X), _lib.ptr(Z), st))
+            _lib.check(L.peuqse_essr_end_iteration(h, st))
+            launches += 3
+            if store_chain:
+                chain[it] = X
+                chain_lp[it] = Z
+        _lib.check(L.peuqse_essr_info(h, _lib.ptr(info), st))
+        torch.cuda.current_stream().synchronize()
+    finally:
+        torch.cuda.synchronize()
+        L.peuqse_essr_destroy(h)
+    pe.gpu_launches += launches
+    info[0] += W
     return dict(X=X, Z=Z, chain=chain, chain_logp=chain_lp, info=info)
 
 
@@ -420,10 +393,12 @@ def run_ensemble_slice_sampling(pe, mcmc_nwalkers_direct_input=None, walkerIniti
             continueSampling = pes['mcmc_continueSampling']
     k = pe.k
     seed = pes.get('mcmc_random_seed')
-    if isinstance(seed, int):
+    seeded = isinstance(seed, int)
+    if seeded:
         np.random.seed(seed)                                                                         # IP.py:2413-2415
     else:
-        seed = int(np.random.SeedSequence().entropy % (2 ** 63))
+        # every rank must run the same ensemble (the rounds are shared out row-wise): rank 0 picks the seed
+        seed = D.broadcast_int(int(np.random.SeedSequence().entropy % (2 ** 63)))
     if mcmc_nwalkers_direct_input is None:                                                           # IP.py:2416-2425
         nw = pes.get('mcmc_nwalkers', 'auto')
         nw = k * 4 if (isinstance(nw, str) and nw.lower() == 'auto') else int(nw)
@@ -446,8 +421,12 @@ def run_ensemble_slice_sampling(pe, mcmc_nwalkers_direct_input=None, walkerIniti
     out = None
     for trial in range(1000):                                                                        # IP.py:2496-2510
         if not continueSampling:
+            # scipy's scrambled Sobol generator does not follow np.random.seed: seed it explicitly so that a seeded run is
+            # reproducible, and take rank 0's points on every rank (quasi-random starts differ from process to process)
             start = pe.generateInitialPoints(initialPointsDistributionType=walkerInitialDistribution, numStartPoints=nw,
-                                             relativeInitialDistributionSpread=walkerInitialDistributionSpread)
+                                             relativeInitialDistributionSpread=walkerInitialDistributionSpread,
+                                             seed=(seed + trial) if seeded else None)
+            start = D.broadcast_np(start)
         try:
             out = ess_launch(pe, start, nsteps, seed + trial, max_rounds=min(maxiter, 2 ** 30), first_iter=first_iter)
             break

@@ -1,5 +1,5 @@
 """C4: doEnsembleSliceSampling with 2048 walkers on a 12-parameter linear model with two 4096-point responses of dense
-covariance (the DMMA likelihood path), round-synchronous driver (peuqse_b200/mcmc.py:ess_batched).  Under torchrun every
+covariance (the DMMA likelihood path), round-synchronous driver (peuqse_b200/csrc/ess_rounds.cu).  Under torchrun every
 round's batch of walkers is shared out over the ranks and the log-posteriors are all-gathered; the final
 walker positions must be those of the single-GPU run (a checksum is printed).
 usage: [torchrun --nproc-per-node N] python profiles/bench_ess_c4.py [iterations=10]"""
@@ -7,7 +7,7 @@ import json, os, sys, time
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import peuqse_b200 as PEUQSE
-from peuqse_b200.mcmc import ess_batched
+from peuqse_b200.mcmc import ess_launch
 from oracle import peuqse_oracle as orc
 
 world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -33,13 +33,13 @@ UI.model['simulateByInputParametersOnlyFunction'] = PEUQSE.LinearModel(Phi)
 UI.responses['responses_observed_max_covmat_size'] = 4096
 PE = PEUQSE.parameter_estimation(UI)
 start = 0.866 * 2.0 * np.random.default_rng(3).standard_normal((W, k)) * 0.25
-ess_batched(PE, start, 2, 7, store_chain=False)                       # warm-up
+ess_launch(PE, start, 2, 7, store_chain=False)                       # warm-up
 torch.cuda.synchronize()
 if world > 1:
     dist.barrier()
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 a.record()
-out = ess_batched(PE, start, iters, 7, store_chain=False)
+out = ess_launch(PE, start, iters, 7, store_chain=False)
 b.record(); torch.cuda.synchronize()
 ms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device="cuda")
 if world > 1:

@@ -4,7 +4,7 @@ import json, os, sys, time
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import peuqse_b200 as PEUQSE
-from peuqse_b200.mcmc import ess_batched
+from peuqse_b200.mcmc import ess_launch
 from oracle import peuqse_oracle as orc
 k, n, W = 12, 4096, 2048
 x = np.linspace(0, 1, n)
@@ -34,12 +34,12 @@ for B in (2048, 1536, 1024, 512, 256, 128, 64, 16, 2):
     out["logp_ms_B%d" % B] = a.elapsed_time(b) / 5
 print(json.dumps(out))
 start = 0.866 * 2.0 * np.random.default_rng(3).standard_normal((W, k)) * 0.25
-ess_batched(PE, start, 1, 7, store_chain=False)
+ess_launch(PE, start, 1, 7, store_chain=False)
 torch.cuda.synchronize()
 from torch.profiler import profile, ProfilerActivity
 t0 = time.perf_counter()
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
-    ess_batched(PE, start, 2, 7, store_chain=False)
+    ess_launch(PE, start, 2, 7, store_chain=False)
     torch.cuda.synchronize()
 print("wall_s_2_iterations_under_profiler", time.perf_counter() - t0)
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=14, max_name_column_width=60))

@@ -98,7 +98,7 @@ np.testing.assert_allclose(A[:, :, 2], ref[:, :, 2], rtol=1e-9)
 # 5. ensemble slice sampling v2: the round-synchronous driver with every round's batch shared out over the ranks
 #    and all-gathered must produce the chain of the unsharded driver (full-covariance responses: the C4 path at a small size)
 from oracle import peuqse_oracle as orc
-from peuqse_b200.mcmc import ess_batched
+from peuqse_b200.mcmc import ess_launch
 rng = np.random.default_rng(21)
 kk, nn = 3, 24
 Phi = orc.cos_basis(2 * nn, kk)
@@ -114,9 +114,21 @@ UI.model['InputParametersPriorValuesUncertainties'] = [2.0] * kk
 UI.model['simulateByInputParametersOnlyFunction'] = PEUQSE.LinearModel(Phi)
 PE = PEUQSE.parameter_estimation(UI)
 start = 0.5 * np.random.default_rng(3).standard_normal((64, kk))
-a = ess_batched(PE, start, 25, 11, shard=True)
-b = ess_batched(PE, start, 25, 11, shard=False)
+a = ess_launch(PE, start, 25, 11, shard=True)
+b = ess_launch(PE, start, 25, 11, shard=False)
 assert torch.equal(a['chain'], b['chain']) and torch.equal(a['chain_logp'], b['chain_logp']) and torch.equal(a['info'], b['info'])
+# 6. doEnsembleSliceSampling itself, unseeded (every rank must end up with rank 0's seed and start walkers) and seeded
+for seed in (None, 5):
+    UI.parameter_estimation_settings.update(mcmc_length=64 * 30, mcmc_nwalkers=64, mcmc_burn_in=64 * 5, mcmc_random_seed=seed,
+                                            mcmc_threshold_filter_samples=False, mcmc_exportLog=False)
+    PE2 = PEUQSE.parameter_estimation(UI)
+    PE2.doEnsembleSliceSampling()
+    mine = torch.from_numpy(PE2.post_burn_in_samples).cuda()
+    both = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(both, mine)
+    assert all(torch.equal(both[0], b_) for b_ in both), "ranks sampled different ensembles"
+    if hasattr(UI, 'last_MCMC_run_type'):
+        del UI.last_MCMC_run_type
 dist.barrier()
 if rank == 0:
     print("MGPU_OK", world)

@@ -263,6 +263,35 @@ def test_ess_linear_gaussian_statistics():
     np.testing.assert_allclose(np.cov(s.T) / np.outer(d, d), cov / np.outer(d, d), atol=0.15)
 
 
+def test_ess_philox_restatement_statistics_and_replay():
+    """The counter-based form of the same algorithm (the one the device drivers are pinned against, tests/test_gpu_ess.py):
+    recovers the closed-form posterior, is a pure function of (seed, start), and continues a run through first_iter."""
+    rng = np.random.default_rng(5)
+    k, n, sig, W = 3, 20, 0.3, 16
+    Phi = orc.cos_basis(n, k)
+    y = Phi @ rng.standard_normal(k) + sig * rng.standard_normal(n)
+    P = orc.build_problem([0.] * k, [2.] * k, y, np.full(n, sig))
+    _, bt = orc.sim_linear(Phi)
+    f = lambda X: orc.log_p_batch(P, X, bt)[0]
+    start = 0.5 * rng.standard_normal((W, k))
+    chain, lp, info = orc.ess_run_philox(f, start, 500, 42)
+    mean, cov = orc.linear_gaussian_posterior(Phi, Phi / sig ** 2, y, 4.0)
+    s = chain[100:].reshape(-1, k)
+    se = np.sqrt(np.diag(cov) / (len(s) / 20.0))
+    assert np.all(np.abs(s.mean(axis=0) - mean) < 5 * se)
+    np.testing.assert_allclose(np.diag(np.cov(s.T)) / np.diag(cov), 1.0, atol=0.15)
+    assert np.array_equal(lp[-1], f(chain[-1]))                        # stored logP belongs to the stored positions
+    assert info['neval'] > 2 * W * 500 and info['n_expansions'] > 0 and info['n_contractions'] > 0
+    again, _, _ = orc.ess_run_philox(f, start, 40, 42)
+    other, _, _ = orc.ess_run_philox(f, start, 40, 43)
+    assert np.array_equal(again, chain[:40]) and not np.array_equal(other, chain[:40])
+    a, _, _ = orc.ess_run_philox(f, start, 30, 42, tune=False, mu0=0.8)
+    b, _, _ = orc.ess_run_philox(f, a[19], 10, 42, tune=False, mu0=0.8, first_iter=20)
+    assert np.array_equal(b, a[20:])
+    with pytest.raises(ValueError):
+        orc.ess_run_philox(lambda X: np.full(len(X), -np.inf), start, 1, 0)
+
+
 PBS_CASES = [('auto', True, 2.0, 'auto', 'pbs_logP'), ('auto1', True, 1.0, 'auto', 'pbs_logP'), ('MAP', True, 2.0, 'MAP', 'pbs_logP'),
              ('mu_AP', True, 2.0, 'mu_AP', 'pbs_logP'), ('off', False, 2.0, 'auto', 'pbs_logP'), ('odd', True, 2.0, 'auto', 'pbs_logP_odd')]
 
