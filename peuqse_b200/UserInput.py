@@ -15,6 +15,7 @@ responses = {
     'responses_observed': [],
     'responses_observed_uncertainties': [],
     'responses_observed_max_covmat_size': 100,
+    'responses_observed_covmat_whitening': 'eigh',   # peuqse_b200 only: 'eigh' = scipy's _PSD (the reference's arithmetic); 'cholesky' = triangular whitening, half the flops
     'responses_observed_weighting': [],
     'reducedResponseSpace': [],
     'independent_variables_values': [],

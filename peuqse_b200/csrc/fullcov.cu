@@ -1,7 +1,25 @@
 // Full-covariance likelihood (kernel K5 of SURVEY section 2): for a block of B simulated response rows,
 //   maha_b = || (y - sim_b) @ U ||^2,   ll_b += -0.5*(rank*log(2pi) + log_pdet + maha_b)
-// with U = u*sqrt(1/s) from scipy's _PSD (scipy/stats/_multivariate.py:208-236, 590-591) hoisted to set-up.
+// with U = u*sqrt(1/s) from scipy's _PSD (scipy/stats/_multivariate.py:208-236, 590-591) hoisted to set-up -- or, when the
+// caller hands over an upper-triangular whitening (the transposed inverse Cholesky factor), only its non-zero half.
 // Replaces one multivariate_normal.logpdf (an n x n eigendecomposition) per point (IP.py:2960).
+//
+// T[B,n] = Rsd[B,n] @ U[n,n] runs on the fp64 tensor pipe (mma.sync.m8n8k4.f64 = DMMA; there is no tcgen05 kind for fp64)
+// and is never written for large batches: the row-wise sum of squares is fused into the contraction.  Three shapes:
+//   k_qf_tile<false>  enough tiles to fill the device: one CTA per 64 x 128 tile of T, 4-stage cp.async ring,
+//                     8 warps x (32 x 32) accumulators, fused sum of squares;
+//   k_qf_tile<true>   16 < B, fewer tiles than SMs x 2: the same tile per (tile, K chunk) CTA, chunk sums to memory; row
+//                     fragments beyond the batch issue no DMMA, so a padded tile costs what its rows cost;
+//   k_qf_skinny<MF>   B <= 16 (many rounds of an ensemble-slice half-sweep): GEMV-shaped -- every warp streams a
+//                     16-column panel of one K chunk of U exactly once with 16-byte loads straight into DMMA B fragments,
+//                     the (pre-arranged) residual fragments come from L1/L2; bound by the one read of U.
+// All three define a row's value the same way, so that it is bit-identical whatever batch the row is evaluated in (the
+// sharded ensemble-slice rounds and the pinning tests rely on it):
+//   T[b][j]   = ((c0 + c1) + c2) + c3, c_i = DMMA accumulation over the i-th quarter of the column tile's K range
+//               (k ascending, four k per instruction);
+//   leaf      = fma-accumulated squares of the 8 values T[b][128 t + 32 w + 8 j + 2 q + e], j < 4, e < 2  (j, then e, ascending)
+//   quad      = (leaf_0 + leaf_1) + (leaf_2 + leaf_3) over q;  tile_t = ((quad_0 + quad_1) + quad_2) + quad_3 over w;
+//   maha_b    = tile_0 + tile_1 + ... (t ascending).
 #include <cstdint>
 #include "common.cuh"
 #include "eval.cuh"
@@ -10,245 +28,444 @@
 int pq_logp_external(const peuqse_problem* p, const double* th, const double* sim, long long B, double* logp, double* lpr,
                      double* llk, cudaStream_t st);
 
-#define QF_ROWS 8      // rows of the residual block per CTA
-#define QF_THREADS 256
+#define QT_BM 64
+#define QT_BN 128
+#define QT_BK 16
+#define QT_LDA (QT_BK + 4)      // padded leading dimensions (doubles): fragment loads touch every bank exactly twice,
+#define QT_LDB (QT_BN + 8)      // rows stay 16-byte aligned for cp.async
+#define QT_STAGES 4
+#define QT_THREADS 256
+#define QT_CHUNKS 4
+#define QT_STAGE_DOUBLES (QT_BM * QT_LDA + QT_BK * QT_LDB)
+#define QT_SMEM_BYTES (QT_STAGES * QT_STAGE_DOUBLES * 8)
 
-// v0 contraction on the fp64 FMA pipe: a CTA owns QF_ROWS residual rows (staged in shared memory) and its
-// threads stride over the columns of U; every U element loaded feeds QF_ROWS FMAs.
-__global__ void __launch_bounds__(QF_THREADS) k_quadform(const double* __restrict__ sim, int ld_sim, int off,
-                                                        const int* __restrict__ src, const double* __restrict__ y,
-                                                        const double* __restrict__ U, int n, double c, long long B,
-                                                        double* __restrict__ ll) {
-    extern __shared__ double sd[];   // [QF_ROWS][n] residuals
-    __shared__ double s_red[QF_THREADS / 32][QF_ROWS];
-    const long long b0 = (long long)blockIdx.x * QF_ROWS;
-    for (int e = threadIdx.x; e < QF_ROWS * n; e += blockDim.x) {
-        const int r = e / n, i = e - r * n;
-        const long long b = b0 + r;
-        sd[e] = (b < B) ? (y[off + i] - sim[b * ld_sim + src[off + i]]) : 0.0;   // x - mean (IP.py:2960)
-    }
-    __syncthreads();
-    double acc[QF_ROWS];
-#pragma unroll
-    for (int r = 0; r < QF_ROWS; ++r) acc[r] = 0.0;
-    for (int j = threadIdx.x; j < n; j += blockDim.x) {
-        double t[QF_ROWS];
-#pragma unroll
-        for (int r = 0; r < QF_ROWS; ++r) t[r] = 0.0;
-        for (int i = 0; i < n; ++i) {
-            const double u = __ldg(U + (size_t)i * n + j);
-#pragma unroll
-            for (int r = 0; r < QF_ROWS; ++r) t[r] = fma(sd[r * n + i], u, t[r]);
-        }
-#pragma unroll
-        for (int r = 0; r < QF_ROWS; ++r) acc[r] = fma(t[r], t[r], acc[r]);
-    }
-#pragma unroll
-    for (int r = 0; r < QF_ROWS; ++r) {
-        const double v = warp_sum(acc[r]);
-        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5][r] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < QF_ROWS) {
-        double m = 0.0;
-        for (int w = 0; w < QF_THREADS / 32; ++w) m += s_red[w][threadIdx.x];
-        const long long b = b0 + threadIdx.x;
-        if (b < B) ll[b] = ll[b] + (-0.5 * (c + m));
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// v1: tensor-core contraction.  T[B,n] = Rsd[B,n] @ U[n,n] with DMMA (mma.sync.m8n8k4 f64 -- there is no tcgen05 kind
-// for fp64), fused with the row-wise sum of squares so that T is never written: every CTA owns a 64 x 64 tile of T,
-// loops over K in steps of 16 with register-prefetched, double-buffered shared-memory tiles (the residual y - sim
-// is formed while staging A), squares its accumulators and writes one partial row sum per (column tile, row).
-// A second tiny kernel adds the partials in fixed order: ll_b += -0.5*(c + sum).
-// ---------------------------------------------------------------------------------------------------
-#define QD_BM 64
-#define QD_BN 64
-#define QD_BK 16
-#define QD_LDA (QD_BK + 4)     // padded leading dimensions: operand fragment loads hit every bank exactly twice
-#define QD_LDB (QD_BN + 8)
+struct QfResp {
+    const double* U;            // padded whitening: rows n_pad (multiple of 16), leading dimension ldu (multiple of 128), zero filled
+    int n, n_pad, ldu, off;     // off: first entry of the response in the problem's observation order
+    int poff;                   // first column of the response in the padded residual block
+    int tri, ntile;             // upper-triangular U; column tiles of 128
+    double c;                   // rank*log(2pi) + log_pdet
+};
+struct QfBatch {
+    int nresp, NP;              // full-covariance responses; columns of the padded residual block (sum of n_pad)
+    QfResp r[PQ_MAXR];
+};
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
 }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-#define QD_CHUNKS 4    // the K range is always accumulated as 4 separately rounded chunk sums, combined ((c0+c1)+c2)+c3
+// number of 16-row K tiles that column tile t of response R needs (all of them, or the non-zero part of a triangular U)
+__device__ __forceinline__ int qf_ktiles(const QfResp& R, int t) {
+    const int all = R.n_pad / QT_BK;
+    if (!R.tri) return all;
+    const int need = (t + 1) * (QT_BN / QT_BK);
+    return need < all ? need : all;
+}
 
-// row-wise sum of squares of a CTA's 64 x 64 tile held in accumulator-fragment order -> partial[blockIdx.x][row]
-__device__ __forceinline__ void qd_epilogue(const double (&acc)[4][2][2], long long bm, long long B, double* __restrict__ partial) {
+// ---------------------------------------------------------------------------------------------------
+// residuals y - sim (x - mean, IP.py:2960) of every full-covariance response, zero padded:
+//   tile form  Rm[B_pad][NP]   (B_pad multiple of 64)                           -> A operand of k_qf_tile via cp.async
+//   fragment form Af[resp][k/4][MF][32]: lane l of fragment m holds R[8 m + l/4][4 (k/4) + l%4]  -> A operand of k_qf_skinny
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_qf_residual(const QfBatch Q, const double* __restrict__ sim, int ld_sim,
+                                                    const int* __restrict__ src, const double* __restrict__ y, long long B,
+                                                    long long B_pad, double* __restrict__ Rm) {
+    const long long b = blockIdx.x;
+    for (int c = blockIdx.y * blockDim.x + threadIdx.x; c < Q.NP; c += gridDim.y * blockDim.x) {
+        int r = 0;
+        while (r + 1 < Q.nresp && c >= Q.r[r + 1].poff) ++r;
+        const int i = c - Q.r[r].poff;
+        double v = 0.0;
+        if (b < B && i < Q.r[r].n) v = y[Q.r[r].off + i] - sim[b * ld_sim + src[Q.r[r].off + i]];
+        Rm[b * Q.NP + c] = v;
+    }
+}
+
+template <int MF>
+__global__ void __launch_bounds__(256) k_qf_residual_frag(const QfBatch Q, const double* __restrict__ sim, int ld_sim,
+                                                         const int* __restrict__ src, const double* __restrict__ y, long long B,
+                                                         double* __restrict__ Af) {
+    // one thread per (k4 step, fragment, lane) of the concatenated padded responses
+    const long long total = (long long)(Q.NP / 4) * MF * 32;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int lane = (int)(e & 31);
+        const int m = (int)((e >> 5) % MF);
+        const int c = (int)((e >> 5) / MF) * 4 + (lane & 3);       // column of the padded block
+        const long long b = m * 8 + (lane >> 2);
+        int r = 0;
+        while (r + 1 < Q.nresp && c >= Q.r[r + 1].poff) ++r;
+        const int i = c - Q.r[r].poff;
+        double v = 0.0;
+        if (b < B && i < Q.r[r].n) v = y[Q.r[r].off + i] - sim[b * ld_sim + src[Q.r[r].off + i]];
+        Af[e] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// tile kernel
+// ---------------------------------------------------------------------------------------------------
+// SPLIT = false: blockIdx.x = tile (column tile major, heaviest first), blockIdx.z = response; the CTA walks the four K
+// chunks one after the other and writes partial[resp][column tile][row].  SPLIT = true: blockIdx.z = 4 * response + chunk;
+// the chunk's accumulators go to Tc[chunk][row][column] and k_qf_finish_tc combines them -- the same additions in the same
+// order.
+template <bool SPLIT>
+__global__ void __launch_bounds__(QT_THREADS, SPLIT ? 2 : 1) k_qf_tile(const QfBatch Q, const double* __restrict__ Rm, long long B,
+                                                                      long long B_pad, int nrt, double* __restrict__ partial,
+                                                                      double* __restrict__ Tc) {
+    extern __shared__ __align__(16) double sm[];
+    const int resp = SPLIT ? (int)blockIdx.z / QT_CHUNKS : (int)blockIdx.z;
+    const QfResp& R = Q.r[resp];
+    const int ct = R.ntile - 1 - (int)(blockIdx.x / nrt);          // heavy (long K range) column tiles first
+    if (ct < 0) return;
+    const int rt = (int)(blockIdx.x % nrt);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 2, wn = warp & 3;
-    __shared__ double s_row[4][QD_BM];
+    const int wm = warp >> 2, wn = warp & 3;                       // 2 x 4 warps, 32 x 32 of the tile each
+    const long long bm = (long long)rt * QT_BM;
+    const int bn = ct * QT_BN;
+    const int nkt = qf_ktiles(R, ct);
+    int kt_first = 0, kt_last = nkt;
+    if (SPLIT) {
+        const int ch = (int)blockIdx.z % QT_CHUNKS;
+        kt_first = (int)((long long)nkt * ch / QT_CHUNKS);
+        kt_last = (int)((long long)nkt * (ch + 1) / QT_CHUNKS);
+    }
+    // row fragments of this warp that hold rows of the batch (the last row tile is padded): the others issue no DMMA
+    int mfv = (int)((B - bm - wm * 32 + 7) / 8);
+    mfv = mfv < 0 ? 0 : (mfv > 4 ? 4 : mfv);
+    const double* Ag = Rm + bm * Q.NP + R.poff;
+    const double* Bg = R.U + bn;
+    auto issue = [&](int kt, int stage) {
+        double* As = sm + (size_t)stage * QT_STAGE_DOUBLES;
+        double* Bs = As + QT_BM * QT_LDA;
+        const int k0 = kt * QT_BK;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {                              // A: 64 rows x 8 chunks of 16 bytes
+            const int c = tid + QT_THREADS * i, row = c >> 3, ch = c & 7;
+            cp_async16(As + row * QT_LDA + ch * 2, Ag + (long long)row * Q.NP + k0 + ch * 2);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                              // B: 16 rows x 64 chunks
+            const int c = tid + QT_THREADS * i, row = c >> 6, ch = c & 63;
+            cp_async16(Bs + row * QT_LDB + ch * 2, Bg + (size_t)(k0 + row) * R.ldu + ch * 2);
+        }
+    };
+    // operand fragments of k4 step ks of the tile in `stage`
+    const int a_off = (wm * 32 + (lane >> 2)) * QT_LDA + (lane & 3);
+    const int b_off = QT_BM * QT_LDA + (lane & 3) * QT_LDB + wn * 32 + (lane >> 2);
+    auto frags = [&](int stage, int ks, double (&af)[4], double (&bf)[4]) {
+        const double* S = sm + (size_t)stage * QT_STAGE_DOUBLES;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) af[i] = S[a_off + i * 8 * QT_LDA + ks];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bf[j] = S[b_off + ks * QT_LDB + j * 8];
+    };
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    double tot[SPLIT ? 1 : 4][SPLIT ? 1 : 4][2];
+    auto fold = [&](int chunk) {                                   // chunk boundary: tot = chunk sums added in order
+        if (!SPLIT) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    tot[SPLIT ? 0 : i][SPLIT ? 0 : j][0] = chunk == 0 ? acc[i][j][0] : tot[SPLIT ? 0 : i][SPLIT ? 0 : j][0] + acc[i][j][0];
+                    tot[SPLIT ? 0 : i][SPLIT ? 0 : j][1] = chunk == 0 ? acc[i][j][1] : tot[SPLIT ? 0 : i][SPLIT ? 0 : j][1] + acc[i][j][1];
+                    acc[i][j][0] = acc[i][j][1] = 0.0;
+                }
+        }
+    };
+    // ring of 4 stages.  The one barrier per tile sits in the MIDDLE of the tile's four k4 steps: behind it every warp has
+    // left tile kt-1 (its stage is refilled with tile kt+3) and tile kt+1 has landed for everybody, so that the first
+    // fragments of tile kt+1 are fetched during the last step of tile kt and the tensor pipe never waits at a tile boundary;
+    // the fragments of the step behind the barrier are already in registers when the barrier is reached.
+#pragma unroll
+    for (int s = 0; s < QT_STAGES - 1; ++s) {
+        if (kt_first + s < kt_last) issue(kt_first + s, s);
+        cp_async_commit();
+    }
+    int chunk = 0;
+    int chunk_end = SPLIT ? kt_last : (int)((long long)nkt / QT_CHUNKS);
+    double af[2][4], bf[2][4];
+    cp_async_wait<1>();                                            // tiles 0 and 1 of this thread ...
+    __syncthreads();                                               // ... and of everybody
+    if (kt_first < kt_last) frags(0, 0, af[0], bf[0]);
+    for (int kt = kt_first; kt < kt_last; ++kt) {
+        const int stage = (kt - kt_first) % QT_STAGES;
+        if (!SPLIT) {
+            while (kt >= chunk_end) {
+                fold(chunk);
+                ++chunk;
+                chunk_end = (int)((long long)nkt * (chunk + 1) / QT_CHUNKS);
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < QT_BK / 4; ++s) {
+            const int cur = s & 1;
+            if (s == 1) {
+                cp_async_wait<1>();                                // tile kt+1 has landed (tile kt+2 may still be in flight)
+                __syncthreads();
+                const int nx = kt + QT_STAGES - 1;
+                if (nx < kt_last) issue(nx, (nx - kt_first) % QT_STAGES);
+                cp_async_commit();
+            }
+            if (s + 1 < QT_BK / 4) frags(stage, (s + 1) * 4, af[cur ^ 1], bf[cur ^ 1]);
+            else if (kt + 1 < kt_last) frags((stage + 1) % QT_STAGES, 0, af[cur ^ 1], bf[cur ^ 1]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (i < mfv) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
+                }
+        }
+    }
+    cp_async_wait<0>();
+    if (SPLIT) {
+        const int ch = (int)blockIdx.z % QT_CHUNKS;
+        double* out = Tc + ((size_t)ch * B_pad + bm) * Q.NP + R.poff + bn;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int row = wm * 32 + i * 8 + (lane >> 2), col = wn * 32 + j * 8 + (lane & 3) * 2;
+                *reinterpret_cast<double2*>(out + (size_t)row * Q.NP + col) = make_double2(acc[i][j][0], acc[i][j][1]);
+            }
+        return;
+    }
+    // remaining chunk sums (the last chunk, and empty chunks of very short K ranges)
+    for (; chunk < QT_CHUNKS; ++chunk) fold(chunk);
+    __syncthreads();                                               // the ring is drained: reuse it for the row sums
+    double* s_row = sm;                                            // [4][64]
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         double s = 0.0;
 #pragma unroll
-        for (int j = 0; j < 2; ++j) s = fma(acc[i][j][0], acc[i][j][0], fma(acc[i][j][1], acc[i][j][1], s));
-        s += __shfl_xor_sync(0xffffffffu, s, 1);                   // the 4 lanes of a row group hold different columns
+        for (int j = 0; j < 4; ++j) {
+            s = fma(tot[SPLIT ? 0 : i][SPLIT ? 0 : j][0], tot[SPLIT ? 0 : i][SPLIT ? 0 : j][0], s);
+            s = fma(tot[SPLIT ? 0 : i][SPLIT ? 0 : j][1], tot[SPLIT ? 0 : i][SPLIT ? 0 : j][1], s);
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
-        if ((lane & 3) == 0) s_row[wn][wm * 32 + i * 8 + (lane >> 2)] = s;
+        if ((lane & 3) == 0) s_row[wn * QT_BM + wm * 32 + i * 8 + (lane >> 2)] = s;
     }
     __syncthreads();
-    if (tid < QD_BM) {
+    if (tid < QT_BM) {
         const long long row = bm + tid;
-        if (row < B) partial[(size_t)blockIdx.x * B + row] = ((s_row[0][tid] + s_row[1][tid]) + s_row[2][tid]) + s_row[3][tid];
+        if (row < B)
+            partial[((size_t)(R.poff / QT_BN) + ct) * B + row] =
+                ((s_row[tid] + s_row[QT_BM + tid]) + s_row[2 * QT_BM + tid]) + s_row[3 * QT_BM + tid];
     }
 }
 
-// SPLIT = false: one CTA per tile walks the four K chunks one after the other.  SPLIT = true (small batches: fewer tiles
-// than SMs, and a 256-step K loop is pure latency): blockIdx.z is the chunk, the chunk's accumulators go to
-// frag[chunk][tile][16][256] and k_quadform_split_finish combines them -- the same additions in the same order, so a
-// row's value does not depend on the size of the batch it is evaluated in.
-template <bool SPLIT, bool VEC>
-__global__ void __launch_bounds__(256, 3) k_quadform_dmma(const double* __restrict__ sim, int ld_sim, int off,
-                                                      const int* __restrict__ src, const double* __restrict__ y,
-                                                      const double* __restrict__ U, int n, long long B,
-                                                      double* __restrict__ partial /* [gridDim.x][B] */,
-                                                      double* __restrict__ frag) {
-    __shared__ __align__(16) double As[2][QD_BM][QD_LDA];
-    __shared__ __align__(16) double Bs[2][QD_BK][QD_LDB];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 2, wn = warp & 3;                   // 2 x 4 warps: each owns 32 x 16 of the 64 x 64 tile
-    const long long bm = (long long)blockIdx.y * QD_BM;
-    const int bn = blockIdx.x * QD_BN;
-    // staging assignments: A tile 64 x 16 (thread -> row ar, 4 consecutive k), B tile 16 x 64 (thread -> row br, 4 consecutive cols)
-    const int ar = tid >> 2, ak = (tid & 3) * 4;
-    const int br = tid >> 4, bc = (tid & 15) * 4;
-    const long long arow = bm + ar;
-    double ra[4], rb[4];
-    auto load_tiles = [&](int k0) {
-        if (VEC) {
-            // simulated values in place (src is the identity), n a multiple of 4 and every row start 16-byte aligned: the four
-            // consecutive elements of a thread are two 16-byte loads, no index gather in front of them
-            const int kk = k0 + ak, kb = k0 + br, cc = bn + bc;
-            ra[0] = ra[1] = ra[2] = ra[3] = 0.0;
-            rb[0] = rb[1] = rb[2] = rb[3] = 0.0;
-            if (arow < B && kk < n) {
-                const double2* sp = reinterpret_cast<const double2*>(sim + arow * ld_sim + off + kk);
-                const double2* yp = reinterpret_cast<const double2*>(y + off + kk);
-                const double2 s0 = sp[0], s1 = sp[1], y0 = __ldg(yp), y1 = __ldg(yp + 1);
-                ra[0] = y0.x - s0.x; ra[1] = y0.y - s0.y; ra[2] = y1.x - s1.x; ra[3] = y1.y - s1.y;   // x - mean (IP.py:2960)
-            }
-            if (kb < n && cc < n) {
-                const double2* up = reinterpret_cast<const double2*>(U + (size_t)kb * n + cc);
-                const double2 u0 = __ldg(up), u1 = __ldg(up + 1);
-                rb[0] = u0.x; rb[1] = u0.y; rb[2] = u1.x; rb[3] = u1.y;
-            }
-            return;
-        }
+// ---------------------------------------------------------------------------------------------------
+// skinny kernel: B <= 8 MF rows
+// ---------------------------------------------------------------------------------------------------
+template <int MF>
+__global__ void __launch_bounds__(256) k_qf_skinny(const QfBatch Q, const double* __restrict__ Af, long long B_pad,
+                                                  double* __restrict__ Tc) {
+    const int resp = blockIdx.z, ch = blockIdx.y, t = blockIdx.x;
+    const QfResp& R = Q.r[resp];
+    if (t >= R.ntile) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nkt = qf_ktiles(R, t);
+    const int s0 = (int)((long long)nkt * ch / QT_CHUNKS) * (QT_BK / 4), s1 = (int)((long long)nkt * (ch + 1) / QT_CHUNKS) * (QT_BK / 4);
+    const int col0 = t * QT_BN + warp * 16;
+    // lane (kq = lane % 4, c = lane / 4) reads U[4 s + kq][col0 + 2 c .. + 1]: .x feeds the B fragment of the even columns,
+    // .y the one of the odd columns (the assignment of columns to fragment positions is free)
+    const double2* up = reinterpret_cast<const double2*>(R.U + (size_t)(lane & 3) * R.ldu + col0 + 2 * (lane >> 2));
+    const size_t ustep = (size_t)4 * R.ldu / 2;                    // double2 per k4 step
+    const double* ap = Af + ((size_t)(R.poff / 4) * MF) * 32 + lane;
+    double acc[MF][2][2];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int kk = k0 + ak + q;
-            ra[q] = (arow < B && kk < n) ? (y[off + kk] - sim[arow * ld_sim + src[off + kk]]) : 0.0;   // x - mean (IP.py:2960)
-            const int kb = k0 + br, cc = bn + bc + q;
-            rb[q] = (kb < n && cc < n) ? __ldg(U + (size_t)kb * n + cc) : 0.0;
+    for (int m = 0; m < MF; ++m) acc[m][0][0] = acc[m][0][1] = acc[m][1][0] = acc[m][1][1] = 0.0;
+    // the panel is streamed in groups of UN k4 steps, two groups in flight: the loads of group g+1 are issued before the
+    // DMMAs of group g, so that 8 to 16 sixteen-byte loads per lane are outstanding all the time (the kernel is bound by
+    // the latency-bandwidth product of this one read of U)
+    constexpr int UN = 8;
+    auto load_group = [&](int s_, double2 (&u)[UN]) {
+#pragma unroll
+        for (int q = 0; q < UN; ++q) {
+            const int sq = (s_ + q < s1) ? s_ + q : s1 - 1;           // the tail group re-reads the last step (its DMMAs are skipped)
+            const double2* a = up + (size_t)sq * ustep;
+            asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(u[q].x), "=d"(u[q].y) : "l"(a));
         }
     };
-    auto store_tiles = [&](int st) {
-        // (ar * QD_LDA + ak) and (br * QD_LDB + bc) are multiples of 2 doubles: two 16-byte stores per operand
-        double2* ap = reinterpret_cast<double2*>(&As[st][ar][ak]);
-        double2* bp = reinterpret_cast<double2*>(&Bs[st][br][bc]);
-        ap[0] = make_double2(ra[0], ra[1]); ap[1] = make_double2(ra[2], ra[3]);
-        bp[0] = make_double2(rb[0], rb[1]); bp[1] = make_double2(rb[2], rb[3]);
+    auto mma_group = [&](int s_, const double2 (&u)[UN]) {
+#pragma unroll
+        for (int q = 0; q < UN; ++q) {
+            if (s_ + q < s1) {
+#pragma unroll
+                for (int m = 0; m < MF; ++m) {
+                    const double a = __ldg(ap + ((size_t)(s_ + q) * MF + m) * 32);
+                    dmma884(acc[m][0][0], acc[m][0][1], a, u[q].x);
+                    dmma884(acc[m][1][0], acc[m][1][1], a, u[q].y);
+                }
+            }
+        }
     };
-    const int nk = (n + QD_BK - 1) / QD_BK;
-    double tot[4][2][2];
-    const int c_first = SPLIT ? (int)blockIdx.z : 0, c_last = SPLIT ? (int)blockIdx.z + 1 : QD_CHUNKS;
-    for (int ch = c_first; ch < c_last; ++ch) {
-        const int kt0 = (int)((long long)nk * ch / QD_CHUNKS), kt1 = (int)((long long)nk * (ch + 1) / QD_CHUNKS);
-        double acc[4][2][2];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-        if (kt0 < kt1) {
-            load_tiles(kt0 * QD_BK);
-            store_tiles(0);
-            __syncthreads();
-            for (int kt = kt0; kt < kt1; ++kt) {
-                const int st = (kt - kt0) & 1;
-                if (kt + 1 < kt1) load_tiles((kt + 1) * QD_BK);      // global loads of the next tile fly during the MMAs
-#pragma unroll
-                for (int ks = 0; ks < QD_BK; ks += 4) {
-                    double af[4], bf[2];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) af[i] = As[st][wm * 32 + i * 8 + (lane >> 2)][ks + (lane & 3)];
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) bf[j] = Bs[st][ks + (lane & 3)][wn * 16 + j * 8 + (lane >> 2)];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-                }
-                if (kt + 1 < kt1) store_tiles(st ^ 1);
-                __syncthreads();
-            }
-        }
-        if (SPLIT) {
-            double* f = frag + (((size_t)ch * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * (16 * 256) + tid;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    f[((i * 2 + j) * 2 + 0) * 256] = acc[i][j][0];
-                    f[((i * 2 + j) * 2 + 1) * 256] = acc[i][j][1];
-                }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    tot[i][j][0] = (ch == 0) ? acc[i][j][0] : tot[i][j][0] + acc[i][j][0];
-                    tot[i][j][1] = (ch == 0) ? acc[i][j][1] : tot[i][j][1] + acc[i][j][1];
-                }
+    if (s0 < s1) {
+        double2 ua[UN], ub[UN];
+        load_group(s0, ua);
+        for (int s = s0; s < s1; s += 2 * UN) {
+            if (s + UN < s1) load_group(s + UN, ub);
+            mma_group(s, ua);
+            if (s + 2 * UN < s1) load_group(s + 2 * UN, ua);
+            if (s + UN < s1) mma_group(s + UN, ub);
         }
     }
-    if (!SPLIT) qd_epilogue(tot, bm, B, partial);
-}
-
-__global__ void __launch_bounds__(256) k_quadform_split_finish(const double* __restrict__ frag, long long B,
-                                                              double* __restrict__ partial) {
-    const size_t tile = (size_t)blockIdx.y * gridDim.x + blockIdx.x, tiles = (size_t)gridDim.x * gridDim.y;
-    double tot[4][2][2];
+    // accumulator (row = lane / 4, fragment column 2 (lane % 4) + e) of fragment f is column col0 + 4 (lane % 4) + 2 e + f
+    double* out = Tc + (size_t)ch * B_pad * Q.NP + R.poff + col0 + 4 * (lane & 3);
 #pragma unroll
-    for (int ch = 0; ch < QD_CHUNKS; ++ch) {
-        const double* f = frag + ((size_t)ch * tiles + tile) * (16 * 256) + threadIdx.x;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const double a0 = f[((i * 2 + j) * 2 + 0) * 256], a1 = f[((i * 2 + j) * 2 + 1) * 256];
-                tot[i][j][0] = (ch == 0) ? a0 : tot[i][j][0] + a0;
-                tot[i][j][1] = (ch == 0) ? a1 : tot[i][j][1] + a1;
-            }
+    for (int m = 0; m < MF; ++m) {
+        double* o = out + (size_t)(m * 8 + (lane >> 2)) * Q.NP;
+        *reinterpret_cast<double2*>(o) = make_double2(acc[m][0][0], acc[m][1][0]);
+        *reinterpret_cast<double2*>(o + 2) = make_double2(acc[m][0][1], acc[m][1][1]);
     }
-    qd_epilogue(tot, (long long)blockIdx.y * QD_BM, B, partial);
 }
 
-__global__ void k_quadform_reduce(const double* __restrict__ partial, int ntn, long long B, double c, double* __restrict__ ll) {
+// chunk sums Tc[4][B_pad][NP] -> partial[global column tile][row]: combination of the chunks and the sum-of-squares tree of
+// k_qf_tile's epilogue.  grid (column tile, group of 8 rows, response), 128 threads = (warp column w, row, q)
+__global__ void __launch_bounds__(128) k_qf_finish_tc(const QfBatch Q, const double* __restrict__ Tc, long long B, long long B_pad,
+                                                     double* __restrict__ partial) {
+    __shared__ double s_row[4][8];
+    const int resp = blockIdx.z, t = blockIdx.x;
+    const QfResp& R = Q.r[resp];
+    if (t >= R.ntile) return;
+    const int tid = threadIdx.x, w = tid >> 5, rsub = (tid & 31) >> 2, q = tid & 3;
+    const long long row = (long long)blockIdx.y * 8 + rsub;
+    const size_t cs = (size_t)B_pad * Q.NP;
+    const double* base = Tc + (size_t)row * Q.NP + R.poff + t * QT_BN + w * 32 + q * 2;
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const double2 c0 = *reinterpret_cast<const double2*>(base + j * 8);
+        const double2 c1 = *reinterpret_cast<const double2*>(base + cs + j * 8);
+        const double2 c2 = *reinterpret_cast<const double2*>(base + 2 * cs + j * 8);
+        const double2 c3 = *reinterpret_cast<const double2*>(base + 3 * cs + j * 8);
+        const double x0 = ((c0.x + c1.x) + c2.x) + c3.x, x1 = ((c0.y + c1.y) + c2.y) + c3.y;
+        s = fma(x0, x0, s);
+        s = fma(x1, x1, s);
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if (q == 0) s_row[w][rsub] = s;
+    __syncthreads();
+    if (tid < 8) {
+        const long long rr = (long long)blockIdx.y * 8 + tid;
+        if (rr < B) partial[((size_t)(R.poff / QT_BN) + t) * B + rr] = ((s_row[0][tid] + s_row[1][tid]) + s_row[2][tid]) + s_row[3][tid];
+    }
+}
+
+// ll_b += -0.5*(c_r + sum_t partial) for every full-covariance response in order, then the NaN convention and logP
+__global__ void __launch_bounds__(256) k_qf_reduce_finish(const QfBatch Q, const double* __restrict__ partial, long long B,
+                                                         const double* __restrict__ lp, double* __restrict__ ll,
+                                                         double* __restrict__ logp) {
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
-    double m = 0.0;
-    for (int t = 0; t < ntn; ++t) m += partial[(size_t)t * B + b];     // fixed order
-    ll[b] = ll[b] + (-0.5 * (c + m));
+    double l = ll[b];
+    for (int r = 0; r < Q.nresp; ++r) {
+        const double* part = partial + (size_t)(Q.r[r].poff / QT_BN) * B + b;
+        double m = 0.0;
+        for (int t = 0; t < Q.r[r].ntile; ++t) m += part[(size_t)t * B];     // fixed order
+        l = l + (-0.5 * (Q.r[r].c + m));
+    }
+    if (l != l) l = pq_neg_inf();            // NaN simulated values -> -inf (IP.py:2880-2882)
+    ll[b] = l;
+    if (logp) logp[b] = combine_logp(lp[b], l);
 }
 
-__global__ void k_fullcov_finish(long long B, const double* __restrict__ lp, double* __restrict__ ll,
-                                 double* __restrict__ logp) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B) return;
-    double l = ll[i];
-    if (l != l) l = pq_neg_inf();            // NaN simulated values -> -inf (IP.py:2880-2882)
-    ll[i] = l;
-    if (logp) logp[i] = combine_logp(lp[i], l);
+namespace {
+template <int MF>
+void launch_skinny(const QfBatch& Q, int ntile_max, const double* sim, int ld_sim, const int* src, const double* y, long long B,
+                   long long B_pad, double* Af, double* Tc, int sm_count, cudaStream_t st) {
+    const long long total = (long long)(Q.NP / 4) * MF * 32;
+    const int rb = (int)std::min<long long>((total + 255) / 256, (long long)sm_count * 8);
+    k_qf_residual_frag<MF><<<rb, 256, 0, st>>>(Q, sim, ld_sim, src, y, B, Af);
+    k_qf_skinny<MF><<<dim3((unsigned)ntile_max, QT_CHUNKS, (unsigned)Q.nresp), 256, 0, st>>>(Q, Af, B_pad, Tc);
+}
+}  // namespace
+
+// rows [0, B) of one chunk: residuals, contraction, partial sums, likelihood
+static int fullcov_rows(const peuqse_problem* p, const QfBatch& Q, int ntile_max, int ntiles, const double* d_sim, long long B,
+                        const double* lp, double* ll, double* d_logp, cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute((const void*)k_qf_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, QT_SMEM_BYTES);
+        cudaFuncSetAttribute((const void*)k_qf_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, QT_SMEM_BYTES);
+        attr_done = true;
+    }
+    const bool skinny = B <= 16;
+    const int MF = B <= 8 ? 1 : 2;
+    const long long B_pad = skinny ? 8LL * MF : ((B + QT_BM - 1) / QT_BM) * QT_BM;
+    const int nrt = (int)(B_pad / QT_BM);
+    // fewer tiles than two per SM: one CTA per (tile, K chunk) instead of a long K loop on a part of the device
+    const bool split = !skinny && (long long)nrt * ntiles < 2LL * p->sm_count;
+    const size_t n_part = (size_t)ntiles * B, n_res = (size_t)B_pad * Q.NP,
+                 n_tc = (skinny || split) ? (size_t)QT_CHUNKS * B_pad * Q.NP : 0;
+    double* scratch = nullptr;
+    PQ_CUDA_OK(cudaMallocAsync((void**)&scratch, (n_part + n_res + n_tc + 8) * sizeof(double), st));
+    double* part = scratch;
+    double* res = (double*)(((uintptr_t)(part + n_part) + 15) & ~(uintptr_t)15);
+    double* tc = res + n_res;
+    const int ld_sim = p->d.n_total;
+    if (skinny) {
+        if (MF == 1) launch_skinny<1>(Q, ntile_max, d_sim, ld_sim, p->d.src, p->d.y, B, B_pad, res, tc, p->sm_count, st);
+        else launch_skinny<2>(Q, ntile_max, d_sim, ld_sim, p->d.src, p->d.y, B, B_pad, res, tc, p->sm_count, st);
+        k_qf_finish_tc<<<dim3((unsigned)ntile_max, (unsigned)(B_pad / 8), (unsigned)Q.nresp), 128, 0, st>>>(Q, tc, B, B_pad, part);
+    } else {
+        k_qf_residual<<<dim3((unsigned)B_pad, (unsigned)std::min((Q.NP + 255) / 256, 16)), 256, 0, st>>>(Q, d_sim, ld_sim, p->d.src,
+                                                                                                       p->d.y, B, B_pad, res);
+        if (split) {
+            k_qf_tile<true><<<dim3((unsigned)(ntile_max * nrt), 1, (unsigned)(Q.nresp * QT_CHUNKS)), QT_THREADS, QT_SMEM_BYTES, st>>>(
+                Q, res, B, B_pad, nrt, part, tc);
+            k_qf_finish_tc<<<dim3((unsigned)ntile_max, (unsigned)(B_pad / 8), (unsigned)Q.nresp), 128, 0, st>>>(Q, tc, B, B_pad, part);
+        } else {
+            k_qf_tile<false><<<dim3((unsigned)(ntile_max * nrt), 1, (unsigned)Q.nresp), QT_THREADS, QT_SMEM_BYTES, st>>>(Q, res, B, B_pad,
+                                                                                                                     nrt, part, nullptr);
+        }
+    }
+    k_qf_reduce_finish<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(Q, part, B, lp, ll, d_logp);
+    const cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(scratch, st);
+    if (e != cudaSuccess) return pq_set_cuda_error(e, "full-covariance contraction", __LINE__);
+    return PEUQSE_OK;
 }
 
 int pq_fullcov_logp(const peuqse_problem* p, const double* d_theta, const double* d_sim, long long B, double* d_logp,
                     double* d_logprior, double* d_loglik, cudaStream_t st) {
+    // the padded residual block places every response at a multiple of 128 columns (poff / 128 = its first global column tile)
+    QfBatch Q;
+    Q.nresp = 0;
+    int poff = 0, ntile_max = 0, ntiles = 0;
+    for (int r = 0; r < p->d.n_resp; ++r) {
+        if (p->d.resp_mode[r] != PEUQSE_RESP_MVN_FULL) continue;
+        QfResp& R = Q.r[Q.nresp++];
+        R.U = p->d.U[r];
+        R.n = p->d.resp_n[r];
+        R.n_pad = p->U_rows[r];
+        R.ldu = p->U_ld[r];
+        R.off = p->d.resp_off[r];
+        R.poff = poff;
+        R.tri = p->U_tri[r];
+        R.ntile = R.ldu / QT_BN;
+        R.c = p->d.resp_c[r];
+        poff += R.ldu;
+        ntile_max = std::max(ntile_max, R.ntile);
+        ntiles += R.ntile;
+    }
+    Q.NP = poff;
     double* ll = d_loglik;
     double* lp = d_logprior;
     double* tmp = nullptr;
@@ -260,42 +477,13 @@ int pq_fullcov_logp(const peuqse_problem* p, const double* d_theta, const double
     }
     // prior and the diagonal / per-value responses; full responses contribute 0 here
     int rc = pq_logp_external(p, need_lp ? d_theta : nullptr, d_sim, B, nullptr, need_lp ? lp : nullptr, ll, st);
-    if (rc == PEUQSE_OK) {
-        for (int r = 0; r < p->d.n_resp && rc == PEUQSE_OK; ++r) {
-            if (p->d.resp_mode[r] != PEUQSE_RESP_MVN_FULL) continue;
-            const int n = p->d.resp_n[r];
-            const int ntn = (n + QD_BN - 1) / QD_BN;
-            double* part = nullptr;
-            cudaError_t e = cudaMallocAsync((void**)&part, (size_t)ntn * B * sizeof(double), st);
-            if (e != cudaSuccess) { rc = pq_set_cuda_error(e, "cudaMallocAsync(quadform partials)", __LINE__); break; }
-            const dim3 grid((unsigned)ntn, (unsigned)((B + QD_BM - 1) / QD_BM));
-            // fewer tiles than two per SM and a K loop long enough to be worth cutting: one CTA per (tile, K chunk)
-            const bool split = (long long)grid.x * grid.y < 2LL * p->sm_count && n >= 16 * QD_BK;
-            const bool vec = p->src_identity && n % 4 == 0 && p->d.n_total % 2 == 0 && p->d.resp_off[r] % 2 == 0 &&
-                             ((uintptr_t)d_sim | (uintptr_t)(p->d.y) | (uintptr_t)(p->d.U[r])) % 16 == 0;
-            if (split) {
-                double* frag = nullptr;
-                e = cudaMallocAsync((void**)&frag, (size_t)QD_CHUNKS * grid.x * grid.y * 16 * 256 * sizeof(double), st);
-                if (e != cudaSuccess) { cudaFreeAsync(part, st); rc = pq_set_cuda_error(e, "cudaMallocAsync(quadform fragments)", __LINE__); break; }
-                auto kern = vec ? k_quadform_dmma<true, true> : k_quadform_dmma<true, false>;
-                kern<<<dim3(grid.x, grid.y, QD_CHUNKS), 256, 0, st>>>(d_sim, p->d.n_total, p->d.resp_off[r], p->d.src, p->d.y, p->d.U[r], n, B,
-                                                                     part, frag);
-                k_quadform_split_finish<<<grid, 256, 0, st>>>(frag, B, part);
-                cudaFreeAsync(frag, st);
-            } else {
-                auto kern = vec ? k_quadform_dmma<false, true> : k_quadform_dmma<false, false>;
-                kern<<<grid, 256, 0, st>>>(d_sim, p->d.n_total, p->d.resp_off[r], p->d.src, p->d.y, p->d.U[r], n, B, part, nullptr);
-            }
-            k_quadform_reduce<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(part, ntn, B, p->d.resp_c[r], ll);
-            e = cudaGetLastError();
-            cudaFreeAsync(part, st);
-            if (e != cudaSuccess) rc = pq_set_cuda_error(e, "k_quadform_dmma", __LINE__);
-        }
-        if (rc == PEUQSE_OK) {
-            k_fullcov_finish<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(B, lp, ll, d_logp);
-            cudaError_t e = cudaGetLastError();
-            if (e != cudaSuccess) rc = pq_set_cuda_error(e, "k_fullcov_finish", __LINE__);
-        }
+    // row chunks bound the residual block to 1 GiB (a row's value does not depend on the chunk it is evaluated in)
+    long long rows = ((1LL << 27) / Q.NP) / QT_BM * QT_BM;
+    if (rows < QT_BM) rows = QT_BM;
+    for (long long b0 = 0; b0 < B && rc == PEUQSE_OK; b0 += rows) {
+        const long long nb = std::min(rows, B - b0);
+        rc = fullcov_rows(p, Q, ntile_max, ntiles, d_sim + (size_t)b0 * p->d.n_total, nb, lp ? lp + b0 : nullptr, ll + b0,
+                          d_logp ? d_logp + b0 : nullptr, st);
     }
     if (tmp) cudaFreeAsync(tmp, st);
     return rc;

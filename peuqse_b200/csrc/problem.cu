@@ -153,7 +153,19 @@ extern "C" int peuqse_problem_create(const peuqse_problem_desc* h, peuqse_proble
     for (int r = 0; r < h->n_resp; ++r)
         if (h->resp_mode[r] == PEUQSE_RESP_MVN_FULL) {
             if (!h->resp_U || !h->resp_U[r]) { delete p; return pq_set_error(PEUQSE_ERR_INVALID, "MVN_FULL response without resp_U"); }
-            o_U[r] = bb.add(h->resp_U[r], (size_t)h->resp_n[r] * h->resp_n[r] * 8);
+            const size_t n = (size_t)h->resp_n[r], rows = (n + 15) / 16 * 16, ld = (n + 127) / 128 * 128;
+            std::vector<double> pad(rows * ld, 0.0);
+            int tri = 1;
+            for (size_t i = 0; i < n; ++i) {
+                const double* row = h->resp_U[r] + i * n;
+                memcpy(pad.data() + i * ld, row, n * 8);
+                for (size_t j = 0; j < i && tri; ++j)
+                    if (row[j] != 0.0) tri = 0;
+            }
+            o_U[r] = bb.add(pad.data(), pad.size() * 8);
+            p->U_rows[r] = (int)rows;
+            p->U_ld[r] = (int)ld;
+            p->U_tri[r] = tri;
         }
     cudaError_t e = cudaMalloc(&p->blob, bb.host.size() ? bb.host.size() : 256);
     if (e != cudaSuccess) { delete p; return pq_set_cuda_error(e, "cudaMalloc(problem blob)", __LINE__); }

@@ -63,6 +63,22 @@ class parameter_estimation:
             obs_unc = [((np.abs(o) * 0.05) ** 2 + (np.max(np.abs(o)) * 0.02) ** 2) ** 0.5 for o in obs_n]
             if len(obs_n) == 1:
                 obs_unc = obs_unc[0]
+        weighting = UI.responses.get('responses_observed_weighting', [])
+        if len(weighting) > 0:
+            # IP.py:238-256: the observed uncertainties are multiplied by weighting**(-0.5) (zeros become machine epsilon).
+            # (The reference's own code path stops at np.float under numpy >= 1.24; this follows its formula.)
+            from .problem import nest_responses
+            wts = [np.array(w_, dtype=float) for w_ in nest_responses(weighting)]
+            unc_n = nest_responses(obs_unc)
+            if any(np.ndim(u_) != 1 for u_ in unc_n) or len(wts) != len(unc_n) or any(len(w_) != len(u_) for w_, u_ in zip(wts, unc_n)):
+                raise NotImplementedError("responses_observed_weighting needs one weight per observed standard deviation "
+                                          "(not covariance matrices)")
+            for w_ in wts:
+                w_[w_ == 0] = np.finfo(float).eps
+            UI.responses_observed_weight_coefficients = [w_ ** (-0.5) for w_ in wts]
+            obs_unc = [u_ * c_ for u_, c_ in zip(unc_n, UI.responses_observed_weight_coefficients)]
+            if len(obs_unc) == 1:
+                obs_unc = obs_unc[0]
         sim_unc = UI.model.get('responses_simulation_uncertainties')
         if callable(sim_unc):
             raise NotImplementedError("responses_simulation_uncertainties as a function of the parameters is a per-point "
@@ -73,7 +89,8 @@ class parameter_estimation:
                                upper_bounds=UI.model['InputParameterPriorValues_upperBounds'],
                                scaling_type=pes['scaling_uncertainties_type'],
                                simulation_uncertainties=sim_unc,
-                               max_covmat_size=UI.responses['responses_observed_max_covmat_size'])
+                               max_covmat_size=UI.responses['responses_observed_max_covmat_size'],
+                               covmat_whitening=UI.responses.get('responses_observed_covmat_whitening', 'eigh'))
         self.host_problem = H
         # reference-named derived fields, written back into UserInput as the reference does (IP.py:146-350)
         UI.mu_prior, UI.std_prior, UI.var_prior, UI.covmat_prior = H.mu_prior, H.std_prior, H.var_prior, H.covmat_prior

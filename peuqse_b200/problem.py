@@ -51,6 +51,23 @@ def psd(cov) -> PSD:
     return out
 
 
+def psd_cholesky(cov) -> PSD:
+    """Triangular whitening of a dense covariance (responses['responses_observed_covmat_whitening'] = 'cholesky'): with
+    cov = L L^T, U = (L^-1)^T is upper triangular, ||dev @ U||^2 = dev^T cov^-1 dev and log det = 2 sum log L_ii.  The
+    contraction kernel skips the zero half of U (n^2 instead of scipy's 2 n^2 flops per point); the value
+    agrees with scipy's eigen-whitening to ~cond(cov) * eps.  Falls back to scipy's form when cov is not positive definite
+    enough for a Cholesky factorisation (so the error conventions of _PSD are kept)."""
+    cov = np.asarray(cov, dtype=float)
+    try:
+        Lc = scipy.linalg.cholesky(cov, lower=True, check_finite=True)
+    except np.linalg.LinAlgError:
+        return psd(cov)
+    n = cov.shape[0]
+    Linv = scipy.linalg.solve_triangular(Lc, np.eye(n), lower=True)
+    U = np.ascontiguousarray(np.triu(Linv.T))
+    return PSD(rank=n, log_pdet=float(2.0 * np.sum(np.log(np.diagonal(Lc)))), U=U, is_perm=False)
+
+
 def nest_responses(x):
     """makeAtLeast_2dNested for responses: 1-D -> [x]; list of sequences -> list of 1-D arrays."""
     try:
@@ -135,7 +152,7 @@ class HostProblem:
 
 def build_host_problem(prior_values, prior_uncertainties, observed, observed_uncertainties, lower_bounds=(),
                        upper_bounds=(), scaling_type="std", simulation_uncertainties=None,
-                       max_covmat_size=100) -> HostProblem:
+                       max_covmat_size=100, covmat_whitening='eigh') -> HostProblem:
     mu = np.array(prior_values, dtype='float')                             # IP.py:146
     unc = np.array(prior_uncertainties, dtype='float')                     # IP.py:148
     k = len(mu)
@@ -237,7 +254,7 @@ def build_host_problem(prior_values, prior_uncertainties, observed, observed_unc
             srcs.append(off + ident)
             Us.append(None)
         else:
-            ps = psd(cov)
+            ps = psd(cov) if (covmat_whitening == 'eigh' or np.ndim(cov) != 2) else psd_cholesky(cov)
             cs.append(ps.rank * LOG2PI + ps.log_pdet)
             cvals.append(np.zeros(n))
             if ps.is_perm:
