@@ -60,24 +60,84 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU side: the oracle port of the reference's per-point path (checker + reported baseline only)
+# CPU side (checker + reported baseline only).  The UNMODIFIED reference is used when its package can be imported -- from
+# baseline/_ref (pip install --no-deps --target baseline/_ref of a copy of /root/reference; travels to the GPU box) or from
+# /root/reference -- under the import shim of SURVEY 8c (matplotlib is not installed: MagicMock modules; nothing in the
+# reference is modified).  Otherwise the oracle port of its per-point path runs (kind "port").
 # ------------------------------------------------------------------------------------------------
 _W = {}
+
+
+def _import_reference():
+    """-> the reference's PEUQSE package, or None."""
+    if 'ref' in _W:
+        return _W['ref']
+    _W['ref'] = None
+    for cand in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if not os.path.isdir(os.path.join(cand, "PEUQSE")):
+            continue
+        try:
+            import tempfile
+            from unittest.mock import MagicMock
+            for m in ["matplotlib", "matplotlib.pyplot", "matplotlib.cm", "matplotlib.colors", "matplotlib.ticker",
+                      "matplotlib.patches", "mpl_toolkits", "mpl_toolkits.mplot3d"]:
+                sys.modules.setdefault(m, MagicMock())
+            sys.path.insert(0, cand)
+            os.chdir(tempfile.mkdtemp(prefix="peuqse_ref_"))        # the constructor creates ./graphs ./logs_and_csvs ./pickles
+            import PEUQSE as REF
+            _W['ref'], _W['ref_path'] = REF, cand
+            break
+        except Exception as e:                                        # noqa: BLE001
+            _W['ref_error'] = repr(e)
+            if cand in sys.path:
+                sys.path.remove(cand)
+    return _W['ref']
 
 
 def _cpu_init():
     from oracle import peuqse_oracle as orc
     _W['orc'] = orc
-    _W['P'] = orc.build_problem(MU, SD, Y00, S00)
-    _W['pt'] = orc.sim_quadratic(X00)[0]
+    REF = _import_reference()
+    if REF is not None:
+        import contextlib
+        import importlib
+        import io
+        sys.modules.pop('PEUQSE.UserInput', None)
+        UI = importlib.import_module('PEUQSE.UserInput')
+        x = np.asarray(X00, dtype=float)
+        UI.responses['responses_abscissa'] = X00
+        UI.responses['responses_observed'] = Y00
+        UI.responses['responses_observed_uncertainties'] = S00
+        UI.model['InputParameterPriorValues'] = MU
+        UI.model['InputParametersPriorValuesUncertainties'] = SD
+        # the user plugin of Examples/Example00/simulation_model_00.py:6-10 (the example files are not part of the package)
+        UI.model['simulateByInputParametersOnlyFunction'] = lambda th: (x - th[0]) ** 2 + th[1]
+        UI.model['exportResponses'] = False
+        UI.parameter_estimation_settings['convergence_diagnostics'] = False
+        UI.parameter_estimation_settings['mcmc_length'] = 10
+        with contextlib.redirect_stdout(io.StringIO()):
+            _W['PE'] = REF.parameter_estimation(UI)
+        _W['kind'] = "reference"
+    else:
+        _W['P'] = orc.build_problem(MU, SD, Y00, S00)
+        _W['pt'] = orc.sim_quadratic(X00)[0]
+        _W['kind'] = "port"
 
 
 def _cpu_eval_range(args):
-    """getLogP one point at a time through scipy, exactly the reference's loop body (IP.py:860)."""
+    """getLogP one point at a time, the reference's loop body (IP.py:860): the unmodified parameter_estimation.getLogP when
+    the reference is importable, else its oracle port (scipy logpdf per point)."""
     first, count, radii = args
     orc = _W['orc']
     th = orc.grid_decode([float(MU[0]), float(MU[1])], INTERVAL, radii, np.arange(first, first + count))
     best = -np.inf
+    if _W['kind'] == "reference":
+        f = _W['PE'].getLogP
+        for t in th:
+            v = f(t)
+            if v > best:
+                best = v
+        return best
     for t in th:
         v = orc.log_p_point(_W['P'], t, _W['pt'])
         if v > best:
@@ -85,8 +145,17 @@ def _cpu_eval_range(args):
     return best
 
 
+def _cpu_how():
+    if _W.get('kind') == "reference":
+        where = os.path.relpath(_W['ref_path'], ROOT) if _W['ref_path'].startswith(ROOT) else _W['ref_path']
+        return f"the UNMODIFIED reference's parameter_estimation.getLogP (imported from {where} under the matplotlib MagicMock shim)"
+    return "oracle port of IP.py:1647-1654 (scipy.stats.multivariate_normal.logpdf per point; the reference package was not importable)"
+
+
 def cpu_baseline_single_core(radii, budget_s=12.0):
+    cwd = os.getcwd()
     _cpu_init()
+    best0 = _cpu_eval_range((0, 14, radii))                         # includes grid index 13, the MAP of the Example00 grid
     t0 = time.perf_counter()
     _cpu_eval_range((0, 1500, radii))
     rate = 1500 / (time.perf_counter() - t0)
@@ -94,23 +163,25 @@ def cpu_baseline_single_core(radii, budget_s=12.0):
     t0 = time.perf_counter()
     _cpu_eval_range((1500, n, radii))
     dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"first {n} grid points (indices 1500..{1500 + n - 1}) of the same grid, one point at a time through "
-                      f"scipy.stats.multivariate_normal.logpdf as the reference does (oracle/peuqse_oracle.py log_p_point), {dt:.1f} s"}
+    os.chdir(cwd)
+    return {"value": n / dt, "unit": UNIT, "cores": 1, "kind": _W['kind'],
+            "sample": f"grid points 1500..{1500 + n - 1} of the same grid, one point at a time through {_cpu_how()}, {dt:.1f} s",
+            "first_points_max_logP": best0}
 
 
 def run_reference_arm(args, emit=print):
-    """--impl reference: the reference's own CPU algorithm for this path (oracle port; the reference is Python and
-    its tree is not on the GPU box), on all host cores as independent workers each owning a slice of the grid
-    (what the reference's mpiexec mode amounts to, IP.py:845-857)."""
+    """--impl reference: the reference's own CPU implementation of the path on all host cores, as independent workers each
+    owning a slice of the grid (what the reference's mpiexec mode amounts to, IP.py:845-857)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     import multiprocessing as mp
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     radii, total = grid_for(args.gpus)
+    _import_reference()                                              # before the fork: the workers inherit the import
     ctx = mp.get_context("fork")
     pool = ctx.Pool(cores, initializer=_cpu_init)
+    _cpu_init()
     # calibrate
     t0 = time.perf_counter()
     pool.map(_cpu_eval_range, [(i * 300, 300, radii) for i in range(cores)])
@@ -132,12 +203,12 @@ def run_reference_arm(args, emit=print):
     pool.close()
     value = per_step * args.steps / dt
     sample = (f"{per_step} grid points per step ({per_worker} per worker, {cores} fork()ed workers), getLogP one point at a "
-              f"time through scipy logpdf (oracle port of IP.py:1647-1654)")
+              f"time through {_cpu_how()}")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args.gpus), "host": "cpu"},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": _W['kind'], "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(json.dumps(line))
@@ -200,9 +271,10 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 C3 = {"n": 1024, "chains": 4096, "truth": [41.5, 45.0, 13.0, 13.0, 0.1, 0.1], "mu": [41.5, 41.5, 13.0, 13.0, 0.1, 0.1],
       "sd": [20.0, 20.0, 13.0, 13.0, 0.1, 0.1], "step": 2.5e-6, "seed": 0}
-# per chain-step: n x (21 flop + 2 exp) + prior 24 + proposal ~ 21.5 kflop + 2048 exp; one software exp is ~30
-# fp64 instructions, an algorithmic flop at most one: ~97 k fp64 instructions per chain-step
-C3_FP64_INSTR_PER_STEP = 97.0e3
+# per chain-step: n x (21 flop + 2 exp) + prior 24 + proposal ~ 21.5 kflop + 2048 exp.  Executed work, MEASURED:
+# 1780 fp64 warp instructions = 57.0 k thread-level fp64 instructions per chain-step (ncu --set full of k_mh_warp<TPD2SITE,6>,
+# profiles/r1_ncu_full_mh_c3_v2_raw.csv: smsp__inst_executed_pipe_fp64 / chain-steps)
+C3_FP64_INSTR_PER_STEP = 57.0e3
 C3_FLOP_PER_STEP = 23.6e3       # SURVEY 8d algorithmic figure (one exp counted as one flop)
 FP64_INSTR_PEAK = 1.80e13     # measured DFMA / DMUL+DADD issue rate of one B200 (profiles/microbench.py), instructions/s
 
@@ -281,9 +353,10 @@ def mh_secondary(PEUQSE, torch, dist, rank, world, steps):
                         "peak": 2.0 * FP64_INSTR_PEAK / 1e12, "unit": "TFLOP/s", "frac": per_gpu * C3_FLOP_PER_STEP / (2.0 * FP64_INSTR_PEAK),
                         "peak_source": "2 flop x measured fp64 issue rate 1.80e13 instr/s (profiles/microbench.py; MEASURED_PEAKS.json "
                                        "has no fp64 figure; nominal 37 TFLOP/s)",
-                        "note": "SURVEY 8d counts one exp as one flop (23.6 kflop per chain-step); executed work is ~97 k fp64 "
-                                "instructions per chain-step (2048 software exps), i.e. %.2f of the fp64 issue rate; %.3g exp/s"
-                                % (per_gpu * C3_FP64_INSTR_PER_STEP / FP64_INSTR_PEAK, per_gpu * 2.0 * C3["n"]),
+                        "fp64_pipe_frac": per_gpu * C3_FP64_INSTR_PER_STEP / FP64_INSTR_PEAK,
+                        "note": "SURVEY 8d counts one exp as one flop (23.6 kflop per chain-step); the kernel executes 57.0 k fp64 "
+                                "instructions per chain-step (ncu count; 2048 software exps), i.e. fp64_pipe_frac = %.2f of the measured "
+                                "fp64 issue rate; %.3g exp/s" % (per_gpu * C3_FP64_INSTR_PER_STEP / FP64_INSTR_PEAK, per_gpu * 2.0 * C3["n"]),
                         "traffic": None},
            "e2e": {"value": chains * (steps - 1) / float(te.item()), "unit": "chain-steps/s", "api": "PE_object.doMetropolisHastings()",
                    "h2d_bytes_per_step": int(th0.nbytes), "d2h_bytes_per_step": int(out['stats'].numel() * 8)}}
@@ -309,6 +382,244 @@ def mh_cpu_baseline(y, sig, budget_s=8.0):
     dt = time.perf_counter() - t0
     return {"value": done / dt, "unit": "chain-steps/s", "cores": 1, "kind": "port",
             "sample": f"{done} steps of one chain, point at a time (oracle.mh_chain_point), {dt:.1f} s"}
+
+# ------------------------------------------------------------------------------------------------
+# configs[3] ("C4"): doEnsembleSliceSampling, 2048 walkers, 12-parameter linear model, two responses of 4096 observations with
+# full 4096 x 4096 covariances (the reference's route to a full covariance is >= 2 response dimensions); every
+# stepping-out / shrink round is one batched log-posterior launch whose likelihood is the DMMA contraction.
+# ------------------------------------------------------------------------------------------------
+C4 = {"k": 12, "n": 4096, "walkers": 2048, "iters": 10, "seed": 7}
+
+
+def fp64_probe(torch, mode):
+    """The library's register-only probes (peuqse_bench_fp64): mode 0 DFMA instructions/s, mode 3 DMMA m8n8k4 flop/s."""
+    from peuqse_b200 import _lib
+    L = _lib.load()
+    scratch = torch.zeros(64, dtype=torch.float64, device="cuda")
+    best = 0.0
+    for _ in range(2):
+        r = ctypes.c_double()
+        _lib.check(L.peuqse_bench_fp64(mode, ctypes.byref(r), _lib.ptr(scratch), _lib.current_stream()))
+        best = max(best, r.value)
+    return best
+
+
+def c4_problem(PEUQSE, whitening):
+    from oracle import peuqse_oracle as orc                            # only for the cos basis of the synthetic inputs
+    k, n = C4["k"], C4["n"]
+    x = np.linspace(0, 1, n)
+    Phi = orc.cos_basis(2 * n, k)
+    Sig = 0.1 ** 2 * np.exp(-(x[:, None] - x[None, :]) ** 2 / (2 * 0.02 ** 2)) + 0.05 ** 2 * np.eye(n)
+    truth = np.random.default_rng(1).standard_normal(k)
+    y = Phi @ truth + 0.1 * np.random.default_rng(2).standard_normal(2 * n)
+    UI = PEUQSE.UserInput.fresh()
+    UI.responses['responses_observed'] = [list(y[:n]), list(y[n:])]
+    UI.responses['responses_observed_uncertainties'] = [Sig, Sig]
+    UI.responses['responses_observed_max_covmat_size'] = n
+    UI.responses['responses_observed_covmat_whitening'] = whitening
+    UI.model['InputParameterPriorValues'] = [0.0] * k
+    UI.model['InputParametersPriorValuesUncertainties'] = [2.0] * k
+    UI.model['simulateByInputParametersOnlyFunction'] = PEUQSE.LinearModel(Phi)
+    pes = UI.parameter_estimation_settings
+    pes.update({'mcmc_length': C4["walkers"] * C4["iters"], 'mcmc_nwalkers': C4["walkers"], 'mcmc_burn_in': 0,
+                'mcmc_random_seed': C4["seed"], 'mcmc_walkerInitialDistribution': 'sobol', 'mcmc_walkerInitialDistributionSpread': 0.25,
+                'mcmc_threshold_filter_samples': False, 'mcmc_info_gain_returned': 'log_ratio', 'mcmc_exportLog': False})
+    return PEUQSE.parameter_estimation(UI), Phi, Sig, y, truth
+
+
+def c4_secondary(PEUQSE, torch, dist, rank, world):
+    """Strong scaling: the ensemble is one; with N ranks every round's rows are shared out and the log-posteriors all-gathered
+    (NCCL), the walkers stay those of the single-GPU run."""
+    from peuqse_b200.mcmc import ess_launch
+    from peuqse_b200 import _lib
+    k, n, W, iters = C4["k"], C4["n"], C4["walkers"], C4["iters"]
+    dmma_peak = fp64_probe(torch, 3)
+    out = {}
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def tmax(v):
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    for whitening in ("eigh", "cholesky"):
+        PE, Phi, Sig, y, truth = c4_problem(PEUQSE, whitening)
+        flops_eval = 2.0 * (2.0 * n * n if whitening == "eigh" else 1.0 * n * (n + 128))     # executed by the contraction, both responses
+        start = 0.866 * 2.0 * 0.25 * np.random.default_rng(3).standard_normal((W, k))
+        ess_launch(PE, start, 2, C4["seed"], store_chain=False)          # warm-up
+        barrier()
+        a.record()
+        run = ess_launch(PE, start, iters, C4["seed"], store_chain=False)
+        b.record()
+        torch.cuda.synchronize()
+        s = tmax(a.elapsed_time(b)) * 1e-3
+        info = run['info'].cpu().numpy()
+        evals = float(info[0])
+        # the dominant kernel alone: one batched log-posterior of 1024 rows (k_qf_tile<false>), CUDA events around 5 calls
+        L = _lib.load()
+        th = torch.from_numpy(truth + 0.05 * np.random.default_rng(4).standard_normal((1024, k))).cuda()
+        lp = torch.empty(1024, dtype=torch.float64, device="cuda")
+        call = lambda: _lib.check(L.peuqse_logp_batch(PE.device_problem.handle, _lib.ptr(th), 1024, _lib.ptr(lp), None, None, _lib.current_stream()))
+        call(); call(); call()
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(5):
+            call()
+        b.record()
+        torch.cuda.synchronize()
+        ms1024 = a.elapsed_time(b) / 5
+        # end to end: PE_object.doEnsembleSliceSampling() from host settings to host samples and statistics
+        PE.doEnsembleSliceSampling()
+        del PE.UserInput.last_MCMC_run_type, PE.mcmc_last_point_sampled
+        barrier()
+        t0 = time.perf_counter()
+        PE.doEnsembleSliceSampling()
+        torch.cuda.synchronize()
+        te = tmax(time.perf_counter() - t0)
+        blk = {"seconds": s, "logp_evals": evals, "logp_evals_per_s": evals / s, "walker_updates_per_s": W * iters / s,
+               "tflops_executed": evals * flops_eval / s / 1e12, "mu": float(info[1]),
+               "checksum_X": float(run['X'].sum().item()),
+               "kernel": {"name": "k_qf_tile<false> inside peuqse_logp_batch, 1024 rows (simulate + residual + contraction + reduce)",
+                          "ms": ms1024, "tflops": 1024 * flops_eval / (ms1024 * 1e-3) / 1e12,
+                          "frac_of_dmma_peak": 1024 * flops_eval / (ms1024 * 1e-3) / dmma_peak},
+               "e2e": {"seconds": te, "logp_evals_per_s": float(PE.ess_info['n_logp_evaluations']) / te,
+                       "walker_updates_per_s": W * iters / te, "api": "PE_object.doEnsembleSliceSampling()",
+                       "h2d_bytes": int(W * k * 8), "d2h_bytes": int(iters * W * (k + 1) * 8)}}
+        out[whitening] = blk
+        del PE
+        torch.cuda.empty_cache()
+    sec = {"metric": "ess_logp_evals_per_s", "value": out["eigh"]["logp_evals_per_s"], "unit": "evals/s", "scaling": "strong",
+           "config": {"workload": f"doEnsembleSliceSampling: {W} walkers x {iters} ensemble iterations, {k}-parameter linear model, two "
+                                  f"responses of {n} observations with full {n} x {n} covariances, differential move, round-synchronous "
+                                  "device driver (csrc/ess_rounds.cu) over the DMMA contraction (csrc/fullcov.cu)",
+                      "whitening": "eigh = scipy's _PSD arithmetic (the reference's, 2 n^2 flop per response and point); cholesky = "
+                                   "triangular whitening (n^2 flop), same values to 1e-12 (tests/test_gpu_fullcov.py)"},
+           "eigh": out["eigh"], "cholesky": out["cholesky"],
+           "roofline": {"bound": "tensor", "kernel": "k_qf_tile<false,4> (fp64 DMMA m8n8k4)", "achieved": out["eigh"]["kernel"]["tflops"],
+                        "peak": dmma_peak / 1e12, "unit": "TFLOP/s", "frac": out["eigh"]["kernel"]["frac_of_dmma_peak"],
+                        "peak_source": "register-only mma.sync.m8n8k4.f64 probe of this run (peuqse_bench_fp64 mode 3); MEASURED_PEAKS.json "
+                                       "has no fp64 figure", "traffic": None}}
+    return sec
+
+
+def c4_cpu_baseline(budget_evals=2):
+    """The reference's per-point arithmetic at C4: scipy.stats.multivariate_normal.logpdf with the full covariance, which
+    eigendecomposes the 4096 x 4096 matrix on EVERY call (IP.py:2960), two responses per evaluation; all BLAS threads."""
+    from scipy.stats import multivariate_normal as mvn
+    from oracle import peuqse_oracle as orc
+    k, n = C4["k"], C4["n"]
+    x = np.linspace(0, 1, n)
+    Phi = orc.cos_basis(2 * n, k)
+    Sig = 0.1 ** 2 * np.exp(-(x[:, None] - x[None, :]) ** 2 / (2 * 0.02 ** 2)) + 0.05 ** 2 * np.eye(n)
+    truth = np.random.default_rng(1).standard_normal(k)
+    y = Phi @ truth + 0.1 * np.random.default_rng(2).standard_normal(2 * n)
+    t0 = time.perf_counter()
+    for i in range(budget_evals):
+        sim = Phi @ (truth + 0.01 * i)
+        mvn.logpdf(x=y[:n], mean=sim[:n], cov=Sig) + mvn.logpdf(x=y[n:], mean=sim[n:], cov=Sig)
+    dt = time.perf_counter() - t0
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    return {"value": budget_evals / dt, "unit": "evals/s", "cores": cores, "kind": "port",
+            "sample": f"{budget_evals} log-likelihood evaluations (2 scipy logpdf calls each, LAPACK threads on all cores), {dt:.1f} s"}
+
+
+# ------------------------------------------------------------------------------------------------
+# configs[4] ("C5"): doMultiStart uniform sampling, 1e10 points of a 10-parameter linear model (64 observations), sharded over
+# the ranks as contiguous index ranges (strong scaling: the total is fixed), MAP arg-max + weighted moments + histograms.
+# ------------------------------------------------------------------------------------------------
+C5 = {"k": 10, "n": 64, "total": 10_000_000_000, "seed": 0}
+
+
+def c5_secondary(PEUQSE, torch, dist, rank, world, total):
+    from oracle import peuqse_oracle as orc                            # cos basis of the synthetic inputs only
+    from peuqse_b200.sweep import Sweep, make_spec
+    k, n = C5["k"], C5["n"]
+    Phi = orc.cos_basis(n, k)
+    truth = np.random.default_rng(5).standard_normal(k) * 0.5
+    y = Phi @ truth + 0.1 * np.random.default_rng(6).standard_normal(n)
+    UI = PEUQSE.UserInput.fresh()
+    UI.responses['responses_observed'] = list(y)
+    UI.responses['responses_observed_uncertainties'] = list(np.full(n, 0.1))
+    UI.model['InputParameterPriorValues'] = [0.0] * k
+    UI.model['InputParametersPriorValuesUncertainties'] = [1.0] * k
+    UI.model['simulateByInputParametersOnlyFunction'] = PEUQSE.LinearModel(Phi)
+    pes = UI.parameter_estimation_settings
+    pes.update({'multistart_initialPointsDistributionType': 'uniform', 'multistart_numStartPoints': int(total),
+                'multistart_relativeInitialDistributionSpread': 0.866, 'multistart_searchType': 'getLogP', 'exportLog': False,
+                'multistart_random_seed': C5["seed"], 'mcmc_length': 100})
+    PE = PEUQSE.parameter_estimation(UI)
+    spec = make_spec("uniform", k, np.zeros(k), spread=0.866, std_prior=np.ones(k), seed=C5["seed"])
+    sw = Sweep(PE.device_problem, spec, int(total), store_logp=False)
+    lr = float(np.log(10 ** -2.0))
+    a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    warm = Sweep(PE.device_problem, spec, min(int(total), 1 << 24), store_logp=False, shard=(0, 1), local=True)
+    warm.step(lr, True)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    a.record()
+    sw.pass1()
+    b.record()
+    sw.pass2(lr)
+    sw.pass3(lr)
+    c.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(c), a.elapsed_time(b)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms1 = float(t[0].item()), float(t[1].item())
+    R = sw.unpack(sw.res.cpu().numpy(), 2.0)
+    # end to end through the public call
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    PE.doMultiStart()
+    torch.cuda.synchronize()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    assert PE.map_index == R.map_index and PE.map_logP == R.map_logP
+    fp64_instr = fp64_probe(torch, 0)
+    flop_eval = 1.6e3                                                     # SURVEY 8d: simulate 2kn + likelihood 4n + prior 4k + Philox
+    per_gpu = (total / world) / (ms1 * 1e-3)
+    sec = {"metric": "fp64_log_posterior_evals_per_s", "value": total / (ms * 1e-3), "unit": "evals/s", "scaling": "strong",
+           "ms_per_sweep": ms, "pass1_ms": ms1, "pass1_evals_per_s": total / (ms1 * 1e-3),
+           "config": {"workload": f"doMultiStart uniform getLogP: {int(total)} points, {k}-parameter linear model, {n} observations, "
+                                  f"diagonal uncertainties, Philox points keyed by the global index, logP not stored (shortlist of "
+                                  "near-maximal points instead of a second evaluation pass); MAP argmax + weighted moments + histograms",
+                      "points_per_gpu": sw.count, "map_index": R.map_index, "map_logP": R.map_logP, "n_retained": R.n_retained},
+           "roofline": {"bound": "fp64", "kernel": "k_sweep_pass1<LINEAR,k=10>", "achieved": per_gpu * flop_eval / 1e12,
+                        "peak": 2.0 * fp64_instr / 1e12, "unit": "TFLOP/s", "frac": per_gpu * flop_eval / (2.0 * fp64_instr),
+                        "peak_source": "2 flop x DFMA issue rate measured in this run (peuqse_bench_fp64 mode 0)", "traffic": None},
+           "e2e": {"value": total / float(te.item()), "unit": "evals/s", "api": "PE_object.doMultiStart()", "h2d_bytes_per_step": 3 * ctypes.sizeof(__import__('peuqse_b200')._lib.SweepSpec),
+                   "d2h_bytes_per_step": sw.result_bytes()}}
+    return sec, (Phi, y)
+
+
+def c5_cpu_baseline(Phi, y, budget_s=8.0):
+    """getLogP one point at a time through scipy logpdf (oracle port of the reference's loop) on one core."""
+    from oracle import peuqse_oracle as orc
+    from oracle import philox_np
+    k, n = C5["k"], C5["n"]
+    P = orc.build_problem([0.0] * k, [1.0] * k, list(y), list(np.full(n, 0.1)))
+    pt = orc.sim_linear(Phi)[0]
+    u = philox_np.sweep_uniforms(C5["seed"], 0, 200000, k)
+    th = orc.uniform_points(u, 0.866, np.ones(k), np.zeros(k))
+    done, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < budget_s and done < len(th):
+        for t in th[done:done + 500]:
+            orc.log_p_point(P, t, pt)
+        done += 500
+    dt = time.perf_counter() - t0
+    return {"value": done / dt, "unit": "evals/s", "cores": 1, "kind": "port",
+            "sample": f"the first {done} points of the same Philox sequence, one point at a time (oracle.log_p_point), {dt:.1f} s"}
+
 
 # ------------------------------------------------------------------------------------------------
 # GPU arm
@@ -421,10 +732,37 @@ def run_ours(args, emit=print):
     h2d = 3 * ctypes.sizeof(_lib.SweepSpec) + 4 * 8      # sweep spec re-sent as kernel parameters by each pass + scalars
     d2h = sw.result_bytes()                              # packed (best, moments, histogram, edges, MAP point)
     assert PE.map_index >= 0 and np.isfinite(PE.map_logP)
+    # multi-GPU correctness, outside the timed regions: rank 0 runs the WHOLE widened grid alone (no exchanges, logP not stored)
+    # and the merged record of the sharded run must equal it -- MAP index and value, integer weight sum, retained points,
+    # histogram counts
+    multi_gpu_check = None
+    if world > 1:
+        ok = 1
+        if rank == 0:
+            alone = Sweep(PE.device_problem, spec, total, store_logp=False, nbins=10, shard=(0, 1), local=True)
+            alone.step(log_rel, True)
+            Ra = alone.unpack(alone.res.cpu().numpy(), 2.0)
+            Rs = sw.unpack(sw.res.cpu().numpy(), 2.0)
+            same = (Ra.map_index == Rs.map_index == PE.map_index and Ra.map_logP == Rs.map_logP and Ra.sum_weights == Rs.sum_weights
+                    and Ra.n_retained == Rs.n_retained and np.array_equal(Ra.histogram_counts, Rs.histogram_counts)
+                    and np.allclose(Ra.mu_AP_parameter_set, Rs.mu_AP_parameter_set, rtol=1e-12))
+            ok = 1 if same else 0
+            multi_gpu_check = "ok" if same else "MISMATCH: alone %r sharded %r" % ((Ra.map_index, Ra.map_logP, Ra.sum_weights),
+                                                                                   (Rs.map_index, Rs.map_logP, Rs.sum_weights))
+            del alone
+        flag = torch.tensor([ok], device="cuda")
+        dist.broadcast(flag, 0)
+        if int(flag.item()) != 1:
+            raise SystemExit("multi-GPU check failed: " + str(multi_gpu_check))
 
-    secondary = None
+    secondary = sec_c4 = sec_c5 = None
+    c5_inputs = None
     if not args.no_mh:
         secondary = mh_secondary(PEUQSE, torch, dist, rank, world, args.mh_steps)
+    if not args.no_c5:
+        sec_c5, c5_inputs = c5_secondary(PEUQSE, torch, dist, rank, world, args.c5_points)
+    if not args.no_c4:
+        sec_c4 = c4_secondary(PEUQSE, torch, dist, rank, world)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -451,8 +789,18 @@ def run_ours(args, emit=print):
             "gpu_launches": launches}
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if multi_gpu_check is not None:
+        line["multi_gpu_check"] = multi_gpu_check
     if secondary is not None:
         line["secondary"] = secondary
+    if sec_c4 is not None:
+        if n_gpus == 1:
+            sec_c4["cpu_baseline"] = c4_cpu_baseline()
+        line["secondary_c4"] = sec_c4
+    if sec_c5 is not None:
+        if n_gpus == 1:
+            sec_c5["cpu_baseline"] = c5_cpu_baseline(*c5_inputs)
+        line["secondary_c5"] = sec_c5
     emit(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -471,7 +819,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mh-steps", type=int, default=20000, help="steps per chain of the secondary (C3 Metropolis-Hastings) measurement")
-    ap.add_argument("--no-mh", action="store_true", help="skip the secondary measurement")
+    ap.add_argument("--no-mh", action="store_true", help="skip the secondary (C3) measurement")
+    ap.add_argument("--no-c4", action="store_true", help="skip the C4 (ensemble slice sampling, full covariance) measurement")
+    ap.add_argument("--no-c5", action="store_true", help="skip the C5 (uniform multistart) measurement")
+    ap.add_argument("--c5-points", type=float, default=C5["total"], help="points of the C5 sweep (default 1e10)")
     args = ap.parse_args()
     # The contract is ONE JSON line on stdout: libraries that print banners there (NCCL prints its version on the first
     # communicator) are sent to stderr by pointing fd 1 at fd 2 for the duration of the run; the line goes to the real stdout.

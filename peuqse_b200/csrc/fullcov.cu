@@ -21,6 +21,7 @@
 //   quad      = (leaf_0 + leaf_1) + (leaf_2 + leaf_3) over q;  tile_t = ((quad_0 + quad_1) + quad_2) + quad_3 over w;
 //   maha_b    = tile_0 + tile_1 + ... (t ascending).
 #include <cstdint>
+#include <cstdlib>
 #include "common.cuh"
 #include "eval.cuh"
 #include "launch.cuh"
@@ -31,13 +32,16 @@ int pq_logp_external(const peuqse_problem* p, const double* th, const double* si
 #define QT_BM 64
 #define QT_BN 128
 #define QT_BK 16
-#define QT_LDA (QT_BK + 4)      // padded leading dimensions (doubles): fragment loads touch every bank exactly twice,
-#define QT_LDB (QT_BN + 8)      // rows stay 16-byte aligned for cp.async
+#define QT_LDA (QT_BK + 4)      // padded leading dimensions (doubles; B operand: columns + 8): fragment loads touch every bank exactly twice,
+                                // rows stay 16-byte aligned for cp.async
 #define QT_STAGES 4
-#define QT_THREADS 256
 #define QT_CHUNKS 4
-#define QT_STAGE_DOUBLES (QT_BM * QT_LDA + QT_BK * QT_LDB)
-#define QT_SMEM_BYTES (QT_STAGES * QT_STAGE_DOUBLES * 8)
+// a CTA of 2 x WN warps owns 64 rows x 32 WN columns of T (WN = 4: a whole canonical 128-column tile; WN = 2: half of one)
+template <int WN> struct QtCfg {
+    static constexpr int BN = 32 * WN, THREADS = 64 * WN, LDB = BN + 8;
+    static constexpr int STAGE_DOUBLES = QT_BM * QT_LDA + QT_BK * LDB;
+    static constexpr int SMEM_BYTES = QT_STAGES * STAGE_DOUBLES * 8;
+};
 
 struct QfResp {
     const double* U;            // padded whitening: rows n_pad (multiple of 16), leading dimension ldu (multiple of 128), zero filled
@@ -118,20 +122,23 @@ __global__ void __launch_bounds__(256) k_qf_residual_frag(const QfBatch Q, const
 // chunks one after the other and writes partial[resp][column tile][row].  SPLIT = true: blockIdx.z = 4 * response + chunk;
 // the chunk's accumulators go to Tc[chunk][row][column] and k_qf_finish_tc combines them -- the same additions in the same
 // order.
-template <bool SPLIT>
-__global__ void __launch_bounds__(QT_THREADS, SPLIT ? 2 : 1) k_qf_tile(const QfBatch Q, const double* __restrict__ Rm, long long B,
+template <bool SPLIT, int WN>
+__global__ void __launch_bounds__(64 * WN, (SPLIT || WN == 2) ? 2 : 1) k_qf_tile(const QfBatch Q, const double* __restrict__ Rm, long long B,
                                                                       long long B_pad, int nrt, double* __restrict__ partial,
                                                                       double* __restrict__ Tc) {
     extern __shared__ __align__(16) double sm[];
     const int resp = SPLIT ? (int)blockIdx.z / QT_CHUNKS : (int)blockIdx.z;
     const QfResp& R = Q.r[resp];
-    const int ct = R.ntile - 1 - (int)(blockIdx.x / nrt);          // heavy (long K range) column tiles first
-    if (ct < 0) return;
+    using Cfg = QtCfg<WN>;
+    constexpr int BN = Cfg::BN, THREADS = Cfg::THREADS, LDB = Cfg::LDB, STAGE_DOUBLES = Cfg::STAGE_DOUBLES;
+    const int cb = R.ntile * (QT_BN / BN) - 1 - (int)(blockIdx.x / nrt);   // column block; heavy (long K range) ones first
+    if (cb < 0) return;
+    const int ct = cb * BN / QT_BN, w0 = (cb * BN % QT_BN) / 32;    // canonical column tile and first warp column in it
     const int rt = (int)(blockIdx.x % nrt);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 2, wn = warp & 3;                       // 2 x 4 warps, 32 x 32 of the tile each
+    const int wm = warp / WN, wn = warp % WN;                      // 2 x WN warps, 32 x 32 of the tile each
     const long long bm = (long long)rt * QT_BM;
-    const int bn = ct * QT_BN;
+    const int bn = cb * BN;
     const int nkt = qf_ktiles(R, ct);
     int kt_first = 0, kt_last = nkt;
     if (SPLIT) {
@@ -142,32 +149,32 @@ __global__ void __launch_bounds__(QT_THREADS, SPLIT ? 2 : 1) k_qf_tile(const QfB
     // row fragments of this warp that hold rows of the batch (the last row tile is padded): the others issue no DMMA
     int mfv = (int)((B - bm - wm * 32 + 7) / 8);
     mfv = mfv < 0 ? 0 : (mfv > 4 ? 4 : mfv);
-    const double* Ag = Rm + bm * Q.NP + R.poff;
-    const double* Bg = R.U + bn;
-    auto issue = [&](int kt, int stage) {
-        double* As = sm + (size_t)stage * QT_STAGE_DOUBLES;
-        double* Bs = As + QT_BM * QT_LDA;
-        const int k0 = kt * QT_BK;
+    // cp.async sources of this thread as running pointers (one 16-byte chunk of A per 32 rows, of B per 256 / BN * 2 rows)
+    constexpr int A_CP = 512 / THREADS, B_CP = 8 * BN / THREADS, A_ROWS = THREADS / 8, B_ROWS = THREADS / (BN / 2);
+    const double* a_src = Rm + (bm + (tid >> 3)) * Q.NP + R.poff + (tid & 7) * 2 + (size_t)kt_first * QT_BK;
+    const double* b_src = R.U + bn + (size_t)(kt_first * QT_BK + tid / (BN / 2)) * R.ldu + (tid % (BN / 2)) * 2;
+    const size_t a_rstride = (size_t)A_ROWS * Q.NP, b_rstride = (size_t)B_ROWS * R.ldu, b_kstride = (size_t)QT_BK * R.ldu;
+    const int a_dst = (tid >> 3) * QT_LDA + (tid & 7) * 2;
+    const int b_dst = QT_BM * QT_LDA + (tid / (BN / 2)) * LDB + (tid % (BN / 2)) * 2;
+    auto issue_a = [&](int stage) {                                // A: 64 rows x 8 chunks of 16 bytes
+        double* S = sm + (size_t)stage * STAGE_DOUBLES + a_dst;
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {                              // A: 64 rows x 8 chunks of 16 bytes
-            const int c = tid + QT_THREADS * i, row = c >> 3, ch = c & 7;
-            cp_async16(As + row * QT_LDA + ch * 2, Ag + (long long)row * Q.NP + k0 + ch * 2);
-        }
+        for (int i = 0; i < A_CP; ++i) cp_async16(S + i * A_ROWS * QT_LDA, a_src + i * a_rstride);
+    };
+    auto issue_b = [&](int stage, int i0, int i1) {                // B: 16 rows x BN / 2 chunks
+        double* S = sm + (size_t)stage * STAGE_DOUBLES + b_dst;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {                              // B: 16 rows x 64 chunks
-            const int c = tid + QT_THREADS * i, row = c >> 6, ch = c & 63;
-            cp_async16(Bs + row * QT_LDB + ch * 2, Bg + (size_t)(k0 + row) * R.ldu + ch * 2);
-        }
+        for (int i = i0; i < i1; ++i) cp_async16(S + i * B_ROWS * LDB, b_src + i * b_rstride);
     };
     // operand fragments of k4 step ks of the tile in `stage`
     const int a_off = (wm * 32 + (lane >> 2)) * QT_LDA + (lane & 3);
-    const int b_off = QT_BM * QT_LDA + (lane & 3) * QT_LDB + wn * 32 + (lane >> 2);
+    const int b_off = QT_BM * QT_LDA + (lane & 3) * LDB + wn * 32 + (lane >> 2);
     auto frags = [&](int stage, int ks, double (&af)[4], double (&bf)[4]) {
-        const double* S = sm + (size_t)stage * QT_STAGE_DOUBLES;
+        const double* S = sm + (size_t)stage * STAGE_DOUBLES;
 #pragma unroll
         for (int i = 0; i < 4; ++i) af[i] = S[a_off + i * 8 * QT_LDA + ks];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) bf[j] = S[b_off + ks * QT_LDB + j * 8];
+        for (int j = 0; j < 4; ++j) bf[j] = S[b_off + ks * LDB + j * 8];
     };
     double acc[4][4][2];
 #pragma unroll
@@ -189,12 +196,16 @@ __global__ void __launch_bounds__(QT_THREADS, SPLIT ? 2 : 1) k_qf_tile(const QfB
     };
     // ring of 4 stages.  The one barrier per tile sits in the MIDDLE of the tile's four k4 steps: behind it every warp has
     // left tile kt-1 (its stage is refilled with tile kt+3) and tile kt+1 has landed for everybody, so that the first
-    // fragments of tile kt+1 are fetched during the last step of tile kt and the tensor pipe never waits at a tile boundary;
-    // the fragments of the step behind the barrier are already in registers when the barrier is reached.
+    // fragments of tile kt+1 are fetched during the last step of tile kt and the tensor pipe never waits at a tile boundary.
+    // The fragments of the step behind the barrier are in registers when the barrier is reached, and the copies of tile
+    // kt+3 are issued in three portions BEHIND the DMMAs of steps 1, 2 and 3, so that both warps of a scheduler never leave
+    // the tensor pipe without work at the same time.
 #pragma unroll
     for (int s = 0; s < QT_STAGES - 1; ++s) {
-        if (kt_first + s < kt_last) issue(kt_first + s, s);
+        if (kt_first + s < kt_last) { issue_a(s); issue_b(s, 0, B_CP); }
         cp_async_commit();
+        a_src += QT_BK;
+        b_src += b_kstride;
     }
     int chunk = 0;
     int chunk_end = SPLIT ? kt_last : (int)((long long)nkt / QT_CHUNKS);
@@ -203,7 +214,8 @@ __global__ void __launch_bounds__(QT_THREADS, SPLIT ? 2 : 1) k_qf_tile(const QfB
     __syncthreads();                                               // ... and of everybody
     if (kt_first < kt_last) frags(0, 0, af[0], bf[0]);
     for (int kt = kt_first; kt < kt_last; ++kt) {
-        const int stage = (kt - kt_first) % QT_STAGES;
+        const int stage = (kt - kt_first) % QT_STAGES, nstage = (stage + QT_STAGES - 1) % QT_STAGES;
+        const bool more = kt + QT_STAGES - 1 < kt_last;
         if (!SPLIT) {
             while (kt >= chunk_end) {
                 fold(chunk);
@@ -217,9 +229,6 @@ __global__ void __launch_bounds__(QT_THREADS, SPLIT ? 2 : 1) k_qf_tile(const QfB
             if (s == 1) {
                 cp_async_wait<1>();                                // tile kt+1 has landed (tile kt+2 may still be in flight)
                 __syncthreads();
-                const int nx = kt + QT_STAGES - 1;
-                if (nx < kt_last) issue(nx, (nx - kt_first) % QT_STAGES);
-                cp_async_commit();
             }
             if (s + 1 < QT_BK / 4) frags(stage, (s + 1) * 4, af[cur ^ 1], bf[cur ^ 1]);
             else if (kt + 1 < kt_last) frags((stage + 1) % QT_STAGES, 0, af[cur ^ 1], bf[cur ^ 1]);
@@ -229,7 +238,15 @@ __global__ void __launch_bounds__(QT_THREADS, SPLIT ? 2 : 1) k_qf_tile(const QfB
 #pragma unroll
                     for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
                 }
+            if (more) {
+                if (s == 1) issue_a(nstage);
+                if (s == 2) issue_b(nstage, 0, B_CP / 2);
+                if (s == 3) issue_b(nstage, B_CP / 2, B_CP);
+            }
         }
+        cp_async_commit();
+        a_src += QT_BK;
+        b_src += b_kstride;
     }
     cp_async_wait<0>();
     if (SPLIT) {
@@ -246,8 +263,8 @@ __global__ void __launch_bounds__(QT_THREADS, SPLIT ? 2 : 1) k_qf_tile(const QfB
     }
     // remaining chunk sums (the last chunk, and empty chunks of very short K ranges)
     for (; chunk < QT_CHUNKS; ++chunk) fold(chunk);
-    __syncthreads();                                               // the ring is drained: reuse it for the row sums
-    double* s_row = sm;                                            // [4][64]
+    // quad sums of this warp's 32 columns: partial[global column tile][warp column][row]
+    double* pq = partial + (((size_t)(R.poff / QT_BN) + ct) * 4 + w0 + wn) * B;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         double s = 0.0;
@@ -258,14 +275,8 @@ __global__ void __launch_bounds__(QT_THREADS, SPLIT ? 2 : 1) k_qf_tile(const QfB
         }
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
-        if ((lane & 3) == 0) s_row[wn * QT_BM + wm * 32 + i * 8 + (lane >> 2)] = s;
-    }
-    __syncthreads();
-    if (tid < QT_BM) {
-        const long long row = bm + tid;
-        if (row < B)
-            partial[((size_t)(R.poff / QT_BN) + ct) * B + row] =
-                ((s_row[tid] + s_row[QT_BM + tid]) + s_row[2 * QT_BM + tid]) + s_row[3 * QT_BM + tid];
+        const long long row = bm + wm * 32 + i * 8 + (lane >> 2);
+        if ((lane & 3) == 0 && row < B) pq[row] = s;
     }
 }
 
@@ -335,11 +346,10 @@ __global__ void __launch_bounds__(256) k_qf_skinny(const QfBatch Q, const double
     }
 }
 
-// chunk sums Tc[4][B_pad][NP] -> partial[global column tile][row]: combination of the chunks and the sum-of-squares tree of
-// k_qf_tile's epilogue.  grid (column tile, group of 8 rows, response), 128 threads = (warp column w, row, q)
+// chunk sums Tc[4][B_pad][NP] -> partial[global column tile][warp column][row]: combination of the chunks and the quad sums
+// of k_qf_tile's epilogue.  grid (column tile, group of 8 rows, response), 128 threads = (warp column w, row, q)
 __global__ void __launch_bounds__(128) k_qf_finish_tc(const QfBatch Q, const double* __restrict__ Tc, long long B, long long B_pad,
                                                      double* __restrict__ partial) {
-    __shared__ double s_row[4][8];
     const int resp = blockIdx.z, t = blockIdx.x;
     const QfResp& R = Q.r[resp];
     if (t >= R.ntile) return;
@@ -360,12 +370,7 @@ __global__ void __launch_bounds__(128) k_qf_finish_tc(const QfBatch Q, const dou
     }
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
-    if (q == 0) s_row[w][rsub] = s;
-    __syncthreads();
-    if (tid < 8) {
-        const long long rr = (long long)blockIdx.y * 8 + tid;
-        if (rr < B) partial[((size_t)(R.poff / QT_BN) + t) * B + rr] = ((s_row[0][tid] + s_row[1][tid]) + s_row[2][tid]) + s_row[3][tid];
-    }
+    if (q == 0 && row < B) partial[(((size_t)(R.poff / QT_BN) + t) * 4 + w) * B + row] = s;
 }
 
 // ll_b += -0.5*(c_r + sum_t partial) for every full-covariance response in order, then the NaN convention and logP
@@ -376,9 +381,21 @@ __global__ void __launch_bounds__(256) k_qf_reduce_finish(const QfBatch Q, const
     if (b >= B) return;
     double l = ll[b];
     for (int r = 0; r < Q.nresp; ++r) {
-        const double* part = partial + (size_t)(Q.r[r].poff / QT_BN) * B + b;
+        const double* part = partial + (size_t)(Q.r[r].poff / QT_BN) * 4 * B + b;
         double m = 0.0;
-        for (int t = 0; t < Q.r[r].ntile; ++t) m += part[(size_t)t * B];     // fixed order
+        const int nt = Q.r[r].ntile;
+        int t = 0;
+        for (; t + 4 <= nt; t += 4) {                                        // fixed order; 16 independent loads in flight
+            double q[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) q[e] = part[((size_t)t * 4 + e) * B];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) m += ((q[4 * e] + q[4 * e + 1]) + q[4 * e + 2]) + q[4 * e + 3];
+        }
+        for (; t < nt; ++t) {
+            const double* q = part + (size_t)t * 4 * B;
+            m += ((q[0] + q[B]) + q[2 * B]) + q[3 * B];
+        }
         l = l + (-0.5 * (Q.r[r].c + m));
     }
     if (l != l) l = pq_neg_inf();            // NaN simulated values -> -inf (IP.py:2880-2882)
@@ -397,13 +414,19 @@ void launch_skinny(const QfBatch& Q, int ntile_max, const double* sim, int ld_si
 }
 }  // namespace
 
+static int g_qf_wn = 4;      // warps along N of the tile kernel's CTA (PEUQSE_QF_WN=2: 64 x 64 CTAs of 4 warps, two per SM)
+
 // rows [0, B) of one chunk: residuals, contraction, partial sums, likelihood
 static int fullcov_rows(const peuqse_problem* p, const QfBatch& Q, int ntile_max, int ntiles, const double* d_sim, long long B,
                         const double* lp, double* ll, double* d_logp, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute((const void*)k_qf_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, QT_SMEM_BYTES);
-        cudaFuncSetAttribute((const void*)k_qf_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, QT_SMEM_BYTES);
+        cudaFuncSetAttribute((const void*)k_qf_tile<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, QtCfg<4>::SMEM_BYTES);
+        cudaFuncSetAttribute((const void*)k_qf_tile<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, QtCfg<4>::SMEM_BYTES);
+        cudaFuncSetAttribute((const void*)k_qf_tile<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, QtCfg<2>::SMEM_BYTES);
+        cudaFuncSetAttribute((const void*)k_qf_tile<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, QtCfg<2>::SMEM_BYTES);
+        const char* e = getenv("PEUQSE_QF_WN");
+        if (e) g_qf_wn = atoi(e) == 2 ? 2 : 4;
         attr_done = true;
     }
     const bool skinny = B <= 16;
@@ -412,7 +435,7 @@ static int fullcov_rows(const peuqse_problem* p, const QfBatch& Q, int ntile_max
     const int nrt = (int)(B_pad / QT_BM);
     // fewer tiles than two per SM: one CTA per (tile, K chunk) instead of a long K loop on a part of the device
     const bool split = !skinny && (long long)nrt * ntiles < 2LL * p->sm_count;
-    const size_t n_part = (size_t)ntiles * B, n_res = (size_t)B_pad * Q.NP,
+    const size_t n_part = (size_t)ntiles * 4 * B, n_res = (size_t)B_pad * Q.NP,
                  n_tc = (skinny || split) ? (size_t)QT_CHUNKS * B_pad * Q.NP : 0;
     double* scratch = nullptr;
     PQ_CUDA_OK(cudaMallocAsync((void**)&scratch, (n_part + n_res + n_tc + 8) * sizeof(double), st));
@@ -428,12 +451,20 @@ static int fullcov_rows(const peuqse_problem* p, const QfBatch& Q, int ntile_max
         k_qf_residual<<<dim3((unsigned)B_pad, (unsigned)std::min((Q.NP + 255) / 256, 16)), 256, 0, st>>>(Q, d_sim, ld_sim, p->d.src,
                                                                                                        p->d.y, B, B_pad, res);
         if (split) {
-            k_qf_tile<true><<<dim3((unsigned)(ntile_max * nrt), 1, (unsigned)(Q.nresp * QT_CHUNKS)), QT_THREADS, QT_SMEM_BYTES, st>>>(
-                Q, res, B, B_pad, nrt, part, tc);
+            if (g_qf_wn == 4)
+                k_qf_tile<true, 4><<<dim3((unsigned)(ntile_max * nrt), 1, (unsigned)(Q.nresp * QT_CHUNKS)), 256, QtCfg<4>::SMEM_BYTES, st>>>(
+                    Q, res, B, B_pad, nrt, part, tc);
+            else
+                k_qf_tile<true, 2><<<dim3((unsigned)(2 * ntile_max * nrt), 1, (unsigned)(Q.nresp * QT_CHUNKS)), 128, QtCfg<2>::SMEM_BYTES, st>>>(
+                    Q, res, B, B_pad, nrt, part, tc);
             k_qf_finish_tc<<<dim3((unsigned)ntile_max, (unsigned)(B_pad / 8), (unsigned)Q.nresp), 128, 0, st>>>(Q, tc, B, B_pad, part);
         } else {
-            k_qf_tile<false><<<dim3((unsigned)(ntile_max * nrt), 1, (unsigned)Q.nresp), QT_THREADS, QT_SMEM_BYTES, st>>>(Q, res, B, B_pad,
-                                                                                                                     nrt, part, nullptr);
+            if (g_qf_wn == 4)
+                k_qf_tile<false, 4><<<dim3((unsigned)(ntile_max * nrt), 1, (unsigned)Q.nresp), 256, QtCfg<4>::SMEM_BYTES, st>>>(
+                    Q, res, B, B_pad, nrt, part, nullptr);
+            else
+                k_qf_tile<false, 2><<<dim3((unsigned)(2 * ntile_max * nrt), 1, (unsigned)Q.nresp), 128, QtCfg<2>::SMEM_BYTES, st>>>(
+                    Q, res, B, B_pad, nrt, part, nullptr);
         }
     }
     k_qf_reduce_finish<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(Q, part, B, lp, ll, d_logp);

@@ -268,6 +268,33 @@ __global__ void __launch_bounds__(256) k_bench_dmma(int iters, double seed, doub
     if (s == 123.456) out[0] = s;
 }
 
+// DMMA probe in the register pattern of the contraction kernel (csrc/fullcov.cu): 16 accumulators per warp fed by 4 x 4
+// distinct operand fragments, 8 warps per CTA; the grid decides how many CTAs share an SM
+__global__ void __launch_bounds__(256) k_bench_dmma_tile(int iters, double seed, double* __restrict__ out) {
+    double c[4][4][2], a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        a[i] = seed + threadIdx.x * 1e-9 + i;
+        b[i] = 1.0 - threadIdx.x * 1e-9 - i * 1e-3;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) c[i][j][0] = c[i][j][1] = 0.0;
+    }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                             : "+d"(c[i][j][0]), "+d"(c[i][j][1]) : "d"(a[i]), "d"(b[j]));
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s += c[i][j][0] + c[i][j][1];
+    if (s == 123.456) out[0] = s;
+}
+
 // returns through *instr_per_s the measured fp64 instruction rate (instructions, not flops) of the whole device
 // latency probe: NCH dependent DFMA chains per thread, one warp per scheduler (128-thread CTA per SM)
 template <int NCH>
@@ -349,6 +376,20 @@ extern "C" int peuqse_bench_fp64(int32_t mode, double* instr_per_s, double* d_sc
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
         *instr_per_s = (double)nb * 8.0 * it * nacc * 512.0 / (ms * 1e-3);
+        return PEUQSE_OK;
+    }
+    if (mode >= 5 && mode <= 8) {   // DMMA in the contraction kernel's register pattern: 1, 2, 4 or 8 CTAs of 8 warps per SM; result = flop/s
+        const int per_sm = 1 << (mode - 5), nb = prop.multiProcessorCount * per_sm, it = 40000 / per_sm;
+        k_bench_dmma_tile<<<nb, 256, 0, st>>>(100, 1.0, d_scratch);
+        PQ_CUDA_OK(cudaEventRecord(e0, st));
+        k_bench_dmma_tile<<<nb, 256, 0, st>>>(it, 1.0, d_scratch);
+        PQ_CUDA_OK(cudaEventRecord(e1, st));
+        PQ_CUDA_OK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        PQ_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        *instr_per_s = (double)nb * 8.0 * it * 16.0 * 512.0 / (ms * 1e-3);
         return PEUQSE_OK;
     }
     if (mode >= 10) {   // 10 + log2(chains): dependent-chain probe, one warp per scheduler; result = DFMA/s of the device

@@ -57,7 +57,9 @@ def interleaved_ranges(total, rank, size, pieces):
 
 
 class Sweep:
-    def __init__(self, dp, spec, total, store_logp=True, nbins=10, shard=None, pieces=None):
+    def __init__(self, dp, spec, total, store_logp=True, nbins=10, shard=None, pieces=None, local=False):
+        """shard = (rank, size): take that rank's range instead of this process's; local = True: no exchange with the other
+        ranks (with shard = (0, 1): the whole sweep on this GPU alone, e.g. to check a sharded run against)."""
         self.dp = dp
         self.spec = spec
         self.k = k = spec.k
@@ -97,7 +99,7 @@ class Sweep:
         self.acc_init[lay["MAX"]:lay["MAX"] + k] = float("-inf")
         self.launches = 0
         self.use_graph = True
-        self.world = D.world()[1]
+        self.world = 1 if local else D.world()[1]
         self.peer = D.native_peer() if self.world > 1 else None      # push-wait-merge kernels over peer memory
         self.comm = D.native_comm() if (self.world > 1 and self.peer is None) else None
         self.peer_max = int(self.L.peuqse_peer_max_bytes())

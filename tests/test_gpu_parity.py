@@ -1228,3 +1228,107 @@ def test_info_gain_cutoff_vs_reference_fixture(env, golden):
         np.testing.assert_allclose(PE.evidence, evidence, rtol=1e-12)
         np.testing.assert_allclose(res[4], info_gain, rtol=1e-11, equal_nan=True)
         np.testing.assert_allclose(PE.info_gain_log_ratio, info_gain, rtol=1e-11, equal_nan=True)
+
+
+@pytest.mark.gpu
+def test_c3_benched_shape_in_kernel_statistics_vs_oracle(env, golden):
+    """The shape bench.py times for C3: many chains of the 1024-observation TPD model with the samples NOT stored, only the
+    per-chain statistics block of k_mh_warp (accept count, MAP row / logP / theta, last state, first and second moments).  64 chains x
+    300 steps from different start points: the oracle replays the kernel's exported draws (a second launch with the same seed
+    that stores everything) and every statistic is rebuilt from the oracle's rows."""
+    PEUQSE, orc, _, torch = env
+    from peuqse_b200 import _lib
+    from peuqse_b200.mcmc import mh_launch, step_cholesky
+    g = golden("tpd")
+    n, L, C, burn, k = 1024, 300, 64, 30, 6
+    sd = np.array([20, 20, 13, 13, 0.1, 0.1])
+    PE = make_pe(PEUQSE, PEUQSE.Tpd2SiteModel.linear_ramp(n), list(g['tpd1024_y']), list(np.full(n, float(g['tpd1024_sigma']))),
+                 [41.5, 41.5, 13.0, 13.0, 0.1, 0.1], list(sd))
+    truth = np.array([41.5, 45, 13, 13, 0.1, 0.1])
+    start = truth + 2e-4 * sd * np.random.default_rng(12).standard_normal((C, k))
+    chol = step_cholesky(PE.Q_covmat, 2.5e-6)
+    full = mh_launch(PE, start, L, burn, 5, chol, export_draws=True, chain_offset=1000)
+    lean = mh_launch(PE, start, L, burn, 5, chol, store_samples=False, chain_offset=1000)          # the benched shape
+    assert lean['samples'] is None and torch.equal(full['stats'], lean['stats'])
+    kBT, c1, c2 = orc.tpd2site_constants(n)
+    _, bt = orc.sim_tpd2site(kBT, c1, c2)
+    P = orc.build_problem([41.5, 41.5, 13.0, 13.0, 0.1, 0.1], sd, g['tpd1024_y'], np.full(n, float(g['tpd1024_sigma'])))
+    ref = orc.mh_chains_batch(P, start, full['deltas'].cpu().numpy(), full['us'].cpu().numpy(), bt)
+    S, LP = ref['samples'], ref['logP']                                  # [L, C, k], [L, C]
+    assert np.array_equal(full['samples'].cpu().numpy(), S)             # accept / reject step for step, all 64 chains
+    st = lean['stats'].cpu().numpy()
+    lay = _lib.mh_stat_layout(k)
+    nacc = (np.abs(np.diff(S, axis=0)).sum(axis=2) > 0).sum(axis=0)
+    assert np.array_equal(st[:, lay['NACC']], ref['accepted'][1:].sum(axis=0)) and np.all(nacc <= st[:, lay['NACC']])
+    assert 0.05 < st[:, lay['NACC']].mean() / (L - 1) < 0.95
+    assert np.array_equal(st[:, lay['LAST']:lay['LAST'] + k], S[-1])
+    np.testing.assert_allclose(st[:, lay['LASTLOGP']], LP[-1], rtol=1e-12)
+    rows = np.arange(burn, L)
+    lp_dev_order = LP[burn:]                                             # first maximum among rows >= burn_in (IP.py:1925-1927)
+    maprow = burn + np.argmax(lp_dev_order, axis=0)
+    # the device's logP differs from the oracle's in the last digits (n = 1024: warp reduction), so a chain whose two best rows
+    # tie to 1e-12 could legitimately pick the other one: require the same row wherever the oracle's margin is clear
+    srt = np.sort(lp_dev_order, axis=0)
+    clear = (srt[-1] - srt[-2]) > 1e-9 * np.abs(srt[-1])
+    same_state = np.array([np.array_equal(S[int(st[c_, lay['MAPROW']]), c_], S[maprow[c_], c_]) for c_ in range(C)])
+    assert np.all(same_state | ~clear) and clear.sum() > C // 2
+    np.testing.assert_allclose(st[:, lay['MAPLOGP']], lp_dev_order.max(axis=0), rtol=1e-12)
+    assert np.array_equal(st[:, lay['MAPTHETA']:lay['MAPTHETA'] + k][same_state], S[maprow, np.arange(C)][same_state])
+    d = S[burn:] - start[None]                                            # moments about each chain's start point
+    s1 = np.zeros((C, k))
+    for r_ in range(d.shape[0]):                                          # the kernel adds row after row
+        s1 = s1 + d[r_]
+    assert np.array_equal(st[:, lay['S1']:lay['S1'] + k], s1)
+    s2 = np.einsum('rci,rcj->cij', d, d)
+    scale = np.sqrt(np.einsum('cii->ci', s2)[:, :, None] * np.einsum('cii->ci', s2)[:, None, :])      # cross terms may cancel
+    assert np.all(np.abs(st[:, lay['S2']:lay['S2'] + k * k].reshape(C, k, k) - s2) <= 1e-12 * scale)
+    # pooled moments through the public call with store off == numpy over the oracle's rows
+    PE.UserInput.parameter_estimation_settings.update(mcmc_length=L, mcmc_burn_in=burn, mcmc_nchains=C, mcmc_random_seed=5,
+                                                      mcmc_relative_step_length=2.5e-6, mcmc_store_samples=False)
+    PE.UserInput.InputParameterInitialGuess = truth
+    out = PE.doMetropolisHastings()
+    ref2 = orc.mh_chains_batch(P, np.tile(truth, (C, 1)), *(t.cpu().numpy() for t in
+                               (lambda o: (o['deltas'], o['us']))(mh_launch(PE, np.tile(truth, (C, 1)), L, burn, 5, chol, export_draws=True))), bt)
+    rows2 = ref2['samples'][burn:].reshape(-1, k)
+    np.testing.assert_allclose(out[1], rows2.mean(axis=0), rtol=1e-12)
+    np.testing.assert_allclose(out[2], rows2.std(axis=0), rtol=1e-9)
+
+
+@pytest.mark.gpu
+def test_c5_window_above_two_to_the_33(env):
+    """C5 is 1e10 points: global indices beyond 2^33.  A 4096-point window that starts above 2^33 (and one straddling 2^32) must
+    be the oracle's points (Philox counter = the 64-bit global index) and log-posteriors, bit for bit, and the window's best
+    record must carry the global index."""
+    PEUQSE, orc, philox_np, torch = env
+    from peuqse_b200.sweep import Sweep, make_spec
+    k, n = 10, 64
+    Phi = orc.cos_basis(n, k)
+    truth = np.random.default_rng(5).standard_normal(k) * 0.5
+    y = Phi @ truth + 0.1 * np.random.default_rng(6).standard_normal(n)
+    PE = make_pe(PEUQSE, PEUQSE.LinearModel(Phi), list(y), list(np.full(n, 0.1)), [0.0] * k, [1.0] * k)
+    P = orc.build_problem([0.0] * k, [1.0] * k, y, np.full(n, 0.1))
+    _, bt = orc.sim_linear(Phi)
+    spec = make_spec("uniform", k, np.zeros(k), spread=0.866, std_prior=np.ones(k), seed=0)
+    total, pieces = 10_000_000_000, 2441407                      # 1e10 points in pieces of ~4096
+    for piece in (int((2 ** 33 + 12345) * pieces / total) + 1, int(2 ** 32 * pieces / total), pieces - 1):
+        sw = Sweep(PE.device_problem, spec, total, store_logp=True, shard=(piece, pieces), local=True)
+        first, count = sw.ranges[0]
+        assert first == (total * piece) // pieces and 4090 <= count <= 4100
+        if piece == pieces - 1:
+            assert first + count == total
+        sw.step(float(np.log(10 ** -2.0)), True)
+        u = philox_np.sweep_uniforms(0, first, count, k)
+        th = orc.uniform_points(u, 0.866, np.ones(k), np.zeros(k))
+        assert np.array_equal(sw.points(first, count).cpu().numpy(), th)
+        lp = orc.log_p_batch(P, th, bt)[0]
+        assert np.array_equal(sw.logp.cpu().numpy(), lp)
+        R = sw.unpack(sw.res.cpu().numpy(), 2.0)
+        idx, best = orc.first_max_np(lp)
+        assert R.map_index == first + idx and R.map_logP == best and np.array_equal(R.map_parameter_set, th[idx])
+        w, _ = orc.permutation_weights(lp, best)
+        assert R.sum_weights == w.sum()
+        # the no-store path (the one the 1e10-point run uses) finds the same record
+        s2 = Sweep(PE.device_problem, spec, total, store_logp=False, shard=(piece, pieces), local=True)
+        s2.step(float(np.log(10 ** -2.0)), True)
+        R2 = s2.unpack(s2.res.cpu().numpy(), 2.0)
+        assert (R2.map_index, R2.map_logP, R2.sum_weights) == (R.map_index, R.map_logP, R.sum_weights)
