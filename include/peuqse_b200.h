@@ -239,15 +239,17 @@ int peuqse_comm_allreduce_sum_i64(peuqse_comm* c, void* d_buf, int64_t count, vo
  * "keep only the best" / concatenate of consolidate_parallel_sampling_data (IP.py:1209-1319).
  * Setup: every rank calls peuqse_peer_alloc (a zeroed mailbox in its device memory + its 64-byte CUDA IPC handle),
  * the handles are all-gathered by any means, then peuqse_peer_create maps the peers' mailboxes.  Every rank must issue
- * the same exchanges in the same order.  A peer that does not arrive within 5 s poisons the result (NaN / index -1)
- * instead of hanging the device.  The exchange calls are not capturable in a CUDA graph (the sequence number is an
- * argument).
+ * the same exchanges in the same order.  The exchange counter lives in device memory: the calls can be captured in a
+ * CUDA graph and replayed.  A peer that does not arrive within PEUQSE_PEER_TIMEOUT_S seconds (environment, default 60)
+ * poisons the result (NaN / index -1) instead of hanging the device and raises a sticky status that peuqse_peer_status
+ * reports (read it after synchronising the stream; the handle must not be used after a time-out).
  */
 typedef struct peuqse_peer peuqse_peer;
 int peuqse_peer_alloc(void** d_local, void* handle64);
 int peuqse_peer_create(void* d_local, const void* handles /*[world][64]*/, int32_t rank, int32_t world, peuqse_peer** out);
 int peuqse_peer_destroy(peuqse_peer* p);    /* also frees the local mailbox */
 int64_t peuqse_peer_max_bytes(void);        /* largest payload of one exchange */
+int peuqse_peer_status(const peuqse_peer* p); /* 0 = fine, 1 = an exchange timed out */
 int peuqse_peer_merge_best(peuqse_peer* p, peuqse_best* d_best /*in: local, out: merged*/, void* stream);
 int peuqse_peer_merge_acc(peuqse_peer* p, double* d_acc /*PEUQSE_ACC_DOUBLES(k), in/out*/, int32_t k, void* stream);
 int peuqse_peer_sum_i64(peuqse_peer* p, void* d_buf /*count int64, in/out*/, int64_t count, void* stream);

@@ -93,7 +93,7 @@ EXPORTS = [
     "peuqse_sweep_pass1", "peuqse_sweep_best_point", "peuqse_sweep_points", "peuqse_sweep_pass2", "peuqse_sweep_edges", "peuqse_sweep_hist",
     "peuqse_comm_unique_id", "peuqse_comm_create", "peuqse_comm_destroy", "peuqse_comm_allgather",
     "peuqse_comm_allreduce_sum_i64", "peuqse_peer_alloc", "peuqse_peer_create", "peuqse_peer_destroy",
-    "peuqse_peer_max_bytes", "peuqse_peer_merge_best", "peuqse_peer_merge_acc", "peuqse_peer_sum_i64", "peuqse_merge_best", "peuqse_merge_acc", "peuqse_mh_run",
+    "peuqse_peer_max_bytes", "peuqse_peer_status", "peuqse_peer_merge_best", "peuqse_peer_merge_acc", "peuqse_peer_sum_i64", "peuqse_merge_best", "peuqse_merge_acc", "peuqse_mh_run",
     "peuqse_philox_blocks", "peuqse_ess_work_bytes", "peuqse_ess_run",
     "peuqse_essr_create", "peuqse_essr_destroy", "peuqse_essr_begin_half", "peuqse_essr_round", "peuqse_essr_end_half",
     "peuqse_essr_end_iteration", "peuqse_essr_info",
@@ -153,6 +153,7 @@ def load():
     L.peuqse_peer_destroy.argtypes = [vp]
     L.peuqse_peer_max_bytes.argtypes = []
     L.peuqse_peer_max_bytes.restype = i64
+    L.peuqse_peer_status.argtypes = [vp]
     L.peuqse_peer_merge_best.argtypes = [vp, vp, vp]
     L.peuqse_peer_merge_acc.argtypes = [vp, vp, i32, vp]
     L.peuqse_peer_sum_i64.argtypes = [vp, vp, i64, vp]

@@ -10,7 +10,13 @@
 // Exchange number q (1, 2, ... identical on all ranks: every rank issues the same exchanges in the same order) uses
 // slot q & 1.  A rank starts exchange q+2 only after its wait in q+1 saw every peer's flag q+1, i.e. after every peer
 // finished reading slot q & 1 in exchange q (a rank reads before it pushes the next exchange), so two slots suffice.
-// The wait is bounded (PQ_PEER_TIMEOUT_NS): a dead peer poisons the result instead of hanging the GPU.
+// The exchange number lives in DEVICE memory (a counter in the local mailbox that the kernel increments), so the exchange
+// kernels take no host-side sequence argument and a whole sharded multistart can be captured in a CUDA graph and replayed.
+// The wait is bounded (PEUQSE_PEER_TIMEOUT_S seconds, default 60): a peer that never arrives poisons the result (NaN / index
+// -1) instead of hanging the GPU AND raises a sticky status word in mapped host memory that the host layer turns into an
+// error on its next result read (peuqse_peer_status); after a time-out the mailbox protocol is void (a late peer may still
+// be reading a slot) and the handle must not be used again.
+#include <cstdlib>
 #include <cstring>
 #include "common.cuh"
 
@@ -19,17 +25,19 @@
 #define PQ_PEER_DATA_BYTES (2LL * PQ_PEER_MAX_WORLD * PQ_PEER_PAYLOAD)
 #define PQ_PEER_FLAG_BYTES (2LL * PQ_PEER_MAX_WORLD * 8)
 #define PQ_PEER_BYTES (PQ_PEER_DATA_BYTES + PQ_PEER_FLAG_BYTES + 64)
-#define PQ_PEER_TIMEOUT_NS 5000000000ULL
 
 struct PeerView {
     int rank, world;
     unsigned char* box[PQ_PEER_MAX_WORLD];    // box[r]: rank r's mailbox as mapped into this process (box[rank] is local)
+    unsigned long long* seq;                  // exchange counter of this rank (device memory, behind the flags of its mailbox)
+    int* status;                              // mapped host word: 0 = fine, 1 = a wait timed out (sticky)
+    unsigned long long timeout_ns;
 };
 
 struct peuqse_peer {
     PeerView v;
-    unsigned long long seq;
     void* local;
+    int* h_status;
     bool opened[PQ_PEER_MAX_WORLD];
 };
 
@@ -50,10 +58,17 @@ enum { PEER_OP_BEST = 0, PEER_OP_ACC = 1, PEER_OP_SUM_I64 = 2 };
 // io: this rank's payload (n8 8-byte words) in, the merged result out
 template <int OP>
 __global__ void __launch_bounds__(256) k_peer_exchange(const __grid_constant__ PeerView V, unsigned long long* __restrict__ io,
-                                                       int n8, unsigned long long seq, int k) {
+                                                       int n8, int k) {
     __shared__ int s_ok;
+    __shared__ unsigned long long s_seq;
+    if (threadIdx.x == 0) {
+        s_ok = 1;
+        s_seq = *V.seq + 1ULL;                                 // every rank issues the same exchanges in the same order
+        *V.seq = s_seq;
+    }
+    __syncthreads();
+    const unsigned long long seq = s_seq;
     const int slot = (int)(seq & 1ULL), me = V.rank, W = V.world;
-    if (threadIdx.x == 0) s_ok = 1;
     // push my payload into every mailbox (my own included)
     for (int idx = threadIdx.x; idx < W * n8; idx += blockDim.x) {
         const int r = idx / n8, w = idx - r * n8;
@@ -67,7 +82,7 @@ __global__ void __launch_bounds__(256) k_peer_exchange(const __grid_constant__ P
         volatile unsigned long long* f = peer_flag(V.box[me], slot, threadIdx.x);
         const unsigned long long t0 = peer_now();
         while (*f < seq) {
-            if (peer_now() - t0 > PQ_PEER_TIMEOUT_NS) { s_ok = 0; break; }
+            if (peer_now() - t0 > V.timeout_ns) { s_ok = 0; break; }
         }
     }
     __syncthreads();
@@ -76,6 +91,7 @@ __global__ void __launch_bounds__(256) k_peer_exchange(const __grid_constant__ P
     if (!s_ok) {                                               // a peer never arrived: poison the result
         for (int w = threadIdx.x; w < n8; w += blockDim.x) io[w] = 0xFFF8000000000000ULL;
         if (OP == PEER_OP_BEST && threadIdx.x == 0) io[1] = (unsigned long long)(-1LL);
+        if (threadIdx.x == 0) { *(volatile int*)V.status = 1; __threadfence_system(); }
         return;
     }
     if (OP == PEER_OP_BEST) {                                  // highest logP, lowest index among equals (IP.py:933)
@@ -136,8 +152,24 @@ extern "C" int peuqse_peer_create(void* d_local, const void* handles, int32_t ra
     peuqse_peer* p = new peuqse_peer();
     p->v.rank = rank;
     p->v.world = world;
-    p->seq = 0;
+    p->v.seq = reinterpret_cast<unsigned long long*>((unsigned char*)d_local + PQ_PEER_DATA_BYTES + PQ_PEER_FLAG_BYTES);
+    const char* ts = getenv("PEUQSE_PEER_TIMEOUT_S");
+    const double tsec = ts ? atof(ts) : 60.0;
+    p->v.timeout_ns = (unsigned long long)((tsec > 0 ? tsec : 60.0) * 1e9);
     p->local = d_local;
+    p->h_status = nullptr;
+    {
+        cudaError_t e = cudaHostAlloc((void**)&p->h_status, sizeof(int), cudaHostAllocMapped);
+        if (e == cudaSuccess) {
+            *p->h_status = 0;
+            e = cudaHostGetDevicePointer((void**)&p->v.status, p->h_status, 0);
+        }
+        if (e != cudaSuccess) {
+            if (p->h_status) cudaFreeHost(p->h_status);
+            delete p;
+            return pq_set_cuda_error(e, "cudaHostAlloc(peer status)", __LINE__);
+        }
+    }
     for (int r = 0; r < PQ_PEER_MAX_WORLD; ++r) { p->v.box[r] = nullptr; p->opened[r] = false; }
     for (int r = 0; r < world; ++r) {
         if (r == rank) { p->v.box[r] = (unsigned char*)d_local; continue; }
@@ -147,6 +179,7 @@ extern "C" int peuqse_peer_create(void* d_local, const void* handles, int32_t ra
         cudaError_t e = cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess);
         if (e != cudaSuccess) {
             for (int s = 0; s < r; ++s) if (p->opened[s]) cudaIpcCloseMemHandle(p->v.box[s]);
+            cudaFreeHost(p->h_status);
             delete p;
             return pq_set_cuda_error(e, "cudaIpcOpenMemHandle", __LINE__);
         }
@@ -161,8 +194,15 @@ extern "C" int peuqse_peer_destroy(peuqse_peer* p) {
     if (!p) return PEUQSE_OK;
     for (int r = 0; r < p->v.world; ++r) if (p->opened[r]) cudaIpcCloseMemHandle(p->v.box[r]);
     if (p->local) cudaFree(p->local);
+    if (p->h_status) cudaFreeHost(p->h_status);
     delete p;
     return PEUQSE_OK;
+}
+
+// 0 = every exchange so far saw all peers; 1 = a wait timed out (read after synchronising the stream of the exchanges)
+extern "C" int peuqse_peer_status(const peuqse_peer* p) {
+    if (!p || !p->h_status) return 0;
+    return *(volatile int*)p->h_status;
 }
 
 extern "C" int64_t peuqse_peer_max_bytes(void) { return PQ_PEER_PAYLOAD; }
@@ -170,7 +210,7 @@ extern "C" int64_t peuqse_peer_max_bytes(void) { return PQ_PEER_PAYLOAD; }
 // d_best: this rank's record in, the merged record out (every rank ends with the same record)
 extern "C" int peuqse_peer_merge_best(peuqse_peer* p, peuqse_best* d_best, void* stream) {
     if (!p || !d_best) return pq_set_error(PEUQSE_ERR_INVALID, "bad peer_merge_best arguments");
-    k_peer_exchange<PEER_OP_BEST><<<1, 256, 0, (cudaStream_t)stream>>>(p->v, (unsigned long long*)d_best, 2, ++p->seq, 0);
+    k_peer_exchange<PEER_OP_BEST><<<1, 256, 0, (cudaStream_t)stream>>>(p->v, (unsigned long long*)d_best, 2, 0);
     PQ_CUDA_OK(cudaGetLastError());
     return PEUQSE_OK;
 }
@@ -178,7 +218,7 @@ extern "C" int peuqse_peer_merge_best(peuqse_peer* p, peuqse_best* d_best, void*
 // d_acc: PEUQSE_ACC_DOUBLES(k) doubles, combined over ranks like peuqse_merge_acc
 extern "C" int peuqse_peer_merge_acc(peuqse_peer* p, double* d_acc, int32_t k, void* stream) {
     if (!p || !d_acc || k < 1 || k > PQ_MAXK) return pq_set_error(PEUQSE_ERR_INVALID, "bad peer_merge_acc arguments");
-    k_peer_exchange<PEER_OP_ACC><<<1, 256, 0, (cudaStream_t)stream>>>(p->v, (unsigned long long*)d_acc, PEUQSE_ACC_DOUBLES(k), ++p->seq, k);
+    k_peer_exchange<PEER_OP_ACC><<<1, 256, 0, (cudaStream_t)stream>>>(p->v, (unsigned long long*)d_acc, PEUQSE_ACC_DOUBLES(k), k);
     PQ_CUDA_OK(cudaGetLastError());
     return PEUQSE_OK;
 }
@@ -187,7 +227,7 @@ extern "C" int peuqse_peer_merge_acc(peuqse_peer* p, double* d_acc, int32_t k, v
 extern "C" int peuqse_peer_sum_i64(peuqse_peer* p, void* d_buf, int64_t count, void* stream) {
     if (!p || !d_buf || count < 0 || count * 8 > PQ_PEER_PAYLOAD) return pq_set_error(PEUQSE_ERR_INVALID, "bad peer_sum_i64 arguments");
     if (count == 0) return PEUQSE_OK;
-    k_peer_exchange<PEER_OP_SUM_I64><<<1, 256, 0, (cudaStream_t)stream>>>(p->v, (unsigned long long*)d_buf, (int)count, ++p->seq, 0);
+    k_peer_exchange<PEER_OP_SUM_I64><<<1, 256, 0, (cudaStream_t)stream>>>(p->v, (unsigned long long*)d_buf, (int)count, 0);
     PQ_CUDA_OK(cudaGetLastError());
     return PEUQSE_OK;
 }

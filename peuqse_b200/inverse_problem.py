@@ -361,6 +361,11 @@ class parameter_estimation:
         if not isinstance(self.simulator, BuiltinModel) or self.host_problem.resp_mode.max() == _lib.RESP_MVN_FULL:
             # torch-callable simulators / full covariance: decode points in chunks and use the batched path
             return self._multistart_external(spec, n, toSamples and calculatePostBurnInStatistics, coef, nbins, centerPoint)
+        # arrays left by an earlier search of another kind (list of permutations, optimiser or MH multistart, external simulator)
+        # must not be mistaken for this sweep's: the properties below then read the sweep's own device buffers
+        for stale in ('_perm_array', '_list_of_permutations'):
+            if hasattr(self, stale):
+                delattr(self, stale)
         store = pes.get('multistart_store_logP', 'auto')
         store = (n <= 2 ** 31) if store == 'auto' else bool(store)
         pieces = pes.get('multistart_shard_pieces', 'auto')            # multi-GPU: pieces per rank, dealt round-robin

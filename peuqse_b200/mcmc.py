@@ -71,7 +71,7 @@ def chain_moments(stats, theta0, k, n_rows):
     Cn = st.shape[0]
     S1 = st[:, lay['S1']:lay['S1'] + k]
     S2 = st[:, lay['S2']:lay['S2'] + k * k].reshape(Cn, k, k)
-    ref = th0[0]
+    ref = D.broadcast_np(th0[0])                                       # one origin for every rank's sums: rank 0's first chain
     sh = th0 - ref                                                     # shift of each chain's origin
     # sums about the common origin `ref`
     T1 = (S1 + n_rows * sh).sum(axis=0)
@@ -82,10 +82,14 @@ def chain_moments(stats, theta0, k, n_rows):
     N = tot[0]
     m1 = T1 / N
     cov = T2 / N - np.outer(m1, m1)
-    i = int(np.argmax(st[:, lay['MAPLOGP']]))
+    # per-chain columns of every rank, in global chain order (chains are sharded as contiguous blocks)
+    cols = np.concatenate([st[:, [lay['MAPLOGP'], lay['NACC'], lay['SUMEXP']]], st[:, lay['MAPTHETA']:lay['MAPTHETA'] + k]], axis=1)
+    if D.world()[1] > 1:
+        cols = D.allgather_rows(torch.from_numpy(np.ascontiguousarray(cols))).cpu().numpy()
+    i = int(np.argmax(cols[:, 0]))                                     # first chain attaining the highest logP
     return dict(mean=ref + m1, cov=cov, std=np.sqrt(np.maximum(np.diag(cov), 0)), n=N,
-                map_logP=float(st[i, lay['MAPLOGP']]), map_theta=st[i, lay['MAPTHETA']:lay['MAPTHETA'] + k].copy(),
-                map_chain=i, accept_rate=st[:, lay['NACC']], sumexp=float(st[:, lay['SUMEXP']].sum()))
+                map_logP=float(cols[i, 0]), map_theta=cols[i, 3:3 + k].copy(),
+                map_chain=i, accept_rate=cols[:, 1], sumexp=float(cols[:, 2].sum()))
 
 
 def run_metropolis_hastings(pe, calculatePostBurnInStatistics=True, continueSampling='auto', mcmc_exportLog='UserChoice'):
@@ -130,6 +134,10 @@ def run_metropolis_hastings(pe, calculatePostBurnInStatistics=True, continueSamp
     seed = pes.get('mcmc_random_seed')
     seed = int(np.random.SeedSequence().entropy % (2 ** 63)) if not isinstance(seed, int) else seed
     rank, size = D.world()
+    if Cn < size:
+        raise ValueError(f"mcmc_nchains = {Cn} is smaller than the number of ranks ({size}): every rank needs at least one chain")
+    if not isinstance(pes.get('mcmc_random_seed'), int):
+        seed = D.broadcast_int(seed)                                                                  # one Philox key for all ranks
     c0, cn = D.shard_range(Cn, rank, size)
     chol = step_cholesky(pe.Q_covmat, pes['mcmc_relative_step_length'])
     store = pes.get('mcmc_store_samples', 'auto')
@@ -146,7 +154,7 @@ def run_metropolis_hastings(pe, calculatePostBurnInStatistics=True, continueSamp
     pe.mcmc_acceptance_rate = float(np.mean(mom['accept_rate'])) / max(Lm - 1, 1)
     pe.mcmc_chain_moments = mom
     lay = _lib.mh_stat_layout(pe.k)
-    last = out['stats'][:, lay['LAST']:lay['LAST'] + pe.k].cpu().numpy()
+    last = D.allgather_rows(out['stats'][:, lay['LAST']:lay['LAST'] + pe.k].contiguous()).cpu().numpy()   # all Cn chains, global order
     pe.mcmc_last_point_sampled = last[0] if Cn == 1 else last                                        # IP.py:2725
     if not store:
         # statistics from the in-kernel accumulators only (no tail filter: it needs every row)

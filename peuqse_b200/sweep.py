@@ -106,12 +106,21 @@ class Sweep:
 
     # -- individual passes: device-resident in and out (bench.py times these for the kernel-only number)
     def pass1(self):
+        self.pass1_kernels()
+        self.pass1_merge()
+
+    def pass1_kernels(self):
+        """The evaluation kernel(s) of pass 1 alone (what bench.py brackets with CUDA events for the roofline)."""
         multi = len(self.ranges) > 1
         for i, (f, c) in enumerate(self.ranges):
             _lib.check(self.L.peuqse_sweep_pass1(self.dp.handle, C.byref(self.spec), f, c, _lib.ptr(self.logps[i]),
                                                  _lib.ptr(self.bests[i]) if multi else _lib.ptr(self.best),
                                                  _lib.ptr(self.works[i]), _lib.current_stream()))
             self.launches += 1
+
+    def pass1_merge(self):
+        """This rank's pieces -> one record, the exchange of the best record over the ranks, the MAP point."""
+        multi = len(self.ranges) > 1
         if multi:                                           # this rank's pieces -> one record
             _lib.check(self.L.peuqse_merge_best(_lib.ptr(self.bests), len(self.ranges), _lib.ptr(self.best), _lib.current_stream()))
             self.launches += 1
@@ -198,6 +207,46 @@ class Sweep:
             self.pass2(log_rel)
             self.pass3(log_rel)
 
+    def graphable(self):
+        """Every launch of a step can be captured in a CUDA graph: one rank, or every exchange is a peer-memory kernel."""
+        return self.world == 1 or (self.peer is not None and self.hist.numel() * 8 <= self.peer_max)
+
+    def capture(self, fn):
+        """fn() captured on a side stream -> torch.cuda.CUDAGraph (None when capture is not possible)."""
+        if not (self.use_graph and self.graphable()):
+            return None
+        try:
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(g, stream=side):
+                    fn()
+            cur.wait_stream(side)
+            return g
+        except Exception:
+            return None
+
+    def rest_of_step(self, log_rel):
+        """Everything of a step behind the pass-1 kernels (merge / exchange of the best record, pass 2, pass 3 and their
+        exchanges) as ONE graph launch when possible: bench.py times  pass1_kernels(); rest_of_step()  per step."""
+        key = ("rest", float(log_rel))
+        if getattr(self, "_rest_key", None) != key:
+            self._rest_key = key
+            self.pass1_merge(); self.pass2(log_rel); self.pass3(log_rel)       # eager once (also warms every kernel up)
+            self._rest_launches = 0
+            l0 = self.launches
+            self._rest_graph = self.capture(lambda: (self.pass1_merge(), self.pass2(log_rel), self.pass3(log_rel)))
+            self._rest_launches = self.launches - l0 if self._rest_graph is not None else 0
+            self.launches = l0
+            return
+        if self._rest_graph is not None:
+            self._rest_graph.replay()
+            self.launches += self._rest_launches                          # kernels inside the replayed graph
+        else:
+            self.pass1_merge(); self.pass2(log_rel); self.pass3(log_rel)
+
     def points(self, first, count):
         th = torch.empty((count, self.k), dtype=torch.float64, device=self.dev)
         if count:
@@ -219,20 +268,15 @@ class Sweep:
         else:
             self.step(log_rel, statistics)
             self._graph, self._graph_key = None, None
-            if self.world == 1 and self.use_graph:                        # capture the launch sequence for the next call
-                try:
-                    cur = torch.cuda.current_stream()
-                    side = torch.cuda.Stream()
-                    side.wait_stream(cur)
-                    g = torch.cuda.CUDAGraph()
-                    with torch.cuda.stream(side):
-                        with torch.cuda.graph(g, stream=side):
-                            self.step(log_rel, statistics)
-                    cur.wait_stream(side)
-                    self._graph, self._graph_key = g, key
-                except Exception:
-                    self._graph, self._graph_key = None, None
+            # capture the launch sequence for the next call; with several ranks only when every exchange of the step is a
+            # peer-memory kernel (their exchange counter lives in device memory, csrc/peer.cu; NCCL calls are not captured)
+            g = self.capture(lambda: self.step(log_rel, statistics))
+            if g is not None:
+                self._graph, self._graph_key = g, key
         res = self.res.cpu()                                              # the single device->host read
+        if self.peer is not None and self.L.peuqse_peer_status(self.peer) != 0:
+            raise _lib.PeuqseError("multi-GPU exchange timed out: a rank did not reach the exchange within PEUQSE_PEER_TIMEOUT_S "
+                                   "seconds (default 60); the merged result is invalid and the peer mailboxes must not be reused")
         R = self.unpack(res.numpy(), coef, statistics)
         return R
 

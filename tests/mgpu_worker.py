@@ -75,6 +75,24 @@ from peuqse_b200.mcmc import mh_launch, step_cholesky, chain_moments
 all_ = mh_launch(PE, np.tile([200., 500.], (64, 1)), 400, 100, 5, step_cholesky(PE.Q_covmat, 0.5))
 S = all_['samples'][100:].permute(1, 0, 2).reshape(-1, 2).cpu().numpy()
 assert PE.post_burn_in_samples.shape == S.shape and np.array_equal(PE.post_burn_in_samples, S)
+# 3b. the same chains with the samples not stored (in-kernel moments): MAP, last points and acceptance must be those of ALL
+#     chains on every rank (not of the rank's own block), the pooled moments those of the stored run
+from peuqse_b200 import _lib
+PEn = make({'mcmc_length': 400, 'mcmc_burn_in': 100, 'mcmc_nchains': 64, 'mcmc_random_seed': 5, 'mcmc_relative_step_length': 0.5,
+            'mcmc_store_samples': False})
+outn = PEn.doMetropolisHastings()
+lay = _lib.mh_stat_layout(2)
+st = all_['stats'].cpu().numpy()
+ibest = int(np.argmax(st[:, lay['MAPLOGP']]))
+assert PEn.map_logP == st[ibest, lay['MAPLOGP']] and np.array_equal(PEn.map_parameter_set, st[ibest, lay['MAPTHETA']:lay['MAPTHETA'] + 2])
+assert np.array_equal(PEn.mcmc_last_point_sampled, st[:, lay['LAST']:lay['LAST'] + 2])
+np.testing.assert_allclose(outn[1], S.mean(axis=0), rtol=1e-12)
+np.testing.assert_allclose(outn[2], S.std(axis=0), rtol=1e-10)
+try:
+    make({'mcmc_length': 50, 'mcmc_nchains': 1, 'mcmc_random_seed': 5}).doMetropolisHastings()
+    raise AssertionError("one chain on several ranks must be refused")
+except ValueError:
+    pass
 # 4. design of experiments: the 9 x 25 scenarios of the reference's Example13 unit test sharded over the ranks
 gd = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "doe.npz"))
 Ld, Bd, STEP, DH, DS, DHU, DSU, SIG = gd['settings']
