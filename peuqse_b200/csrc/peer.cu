@@ -5,11 +5,15 @@
 // Replaces the pickle-file rendezvous of consolidate_parallel_sampling_data (IP.py:1130-1155, 1209-1319).
 //
 // Mailbox of a rank (device memory it owns, zero-initialised):
-//   data [2 slots][PQ_PEER_MAX_WORLD senders][PQ_PEER_PAYLOAD bytes]
-//   flag [2 slots][PQ_PEER_MAX_WORLD senders]  (uint64 sequence number of the payload in that cell)
+//   line [2 slots][PQ_PEER_MAX_WORLD senders][PQ_PEER_PAYLOAD / 8 words] of 16 bytes {lo32, seq32, hi32, seq32}
+// Low-latency protocol: every 64-bit payload word travels as ONE 16-byte store whose two 8-byte halves each carry 32 bits
+// of data and the 32-bit exchange number, so the receiver polls the data itself (8-byte stores arrive whole) -- no
+// separate flag, no fence between payload and flag: the latency of an exchange is one NVLink store, not a store, a
+// round-trip fence and a second store.
 // Exchange number q (1, 2, ... identical on all ranks: every rank issues the same exchanges in the same order) uses
-// slot q & 1.  A rank starts exchange q+2 only after its wait in q+1 saw every peer's flag q+1, i.e. after every peer
-// finished reading slot q & 1 in exchange q (a rank reads before it pushes the next exchange), so two slots suffice.
+// slot q & 1.  A rank can finish exchange q+1 only after every peer pushed its q+1 payload, which a peer does after it
+// finished reading slot q & 1 in exchange q, so when a rank overwrites that slot in exchange q+2 nobody reads it any more:
+// two slots suffice.
 // The exchange number lives in DEVICE memory (a counter in the local mailbox that the kernel increments), so the exchange
 // kernels take no host-side sequence argument and a whole sharded multistart can be captured in a CUDA graph and replayed.
 // The wait is bounded (PEUQSE_PEER_TIMEOUT_S seconds, default 60): a peer that never arrives poisons the result (NaN / index
@@ -22,9 +26,8 @@
 
 #define PQ_PEER_MAX_WORLD 16
 #define PQ_PEER_PAYLOAD 8192
-#define PQ_PEER_DATA_BYTES (2LL * PQ_PEER_MAX_WORLD * PQ_PEER_PAYLOAD)
-#define PQ_PEER_FLAG_BYTES (2LL * PQ_PEER_MAX_WORLD * 8)
-#define PQ_PEER_BYTES (PQ_PEER_DATA_BYTES + PQ_PEER_FLAG_BYTES + 64)
+#define PQ_PEER_DATA_BYTES (2LL * PQ_PEER_MAX_WORLD * PQ_PEER_PAYLOAD * 2)     /* 16-byte line per 8-byte word */
+#define PQ_PEER_BYTES (PQ_PEER_DATA_BYTES + 64)
 
 struct PeerView {
     int rank, world;
@@ -41,11 +44,18 @@ struct peuqse_peer {
     bool opened[PQ_PEER_MAX_WORLD];
 };
 
-__device__ __forceinline__ unsigned long long* peer_data(unsigned char* box, int slot, int sender) {
-    return reinterpret_cast<unsigned long long*>(box + ((size_t)slot * PQ_PEER_MAX_WORLD + sender) * PQ_PEER_PAYLOAD);
+__device__ __forceinline__ uint4* peer_line(unsigned char* box, int slot, int sender) {
+    return reinterpret_cast<uint4*>(box + ((size_t)slot * PQ_PEER_MAX_WORLD + sender) * (PQ_PEER_PAYLOAD * 2));
 }
-__device__ __forceinline__ unsigned long long* peer_flag(unsigned char* box, int slot, int sender) {
-    return reinterpret_cast<unsigned long long*>(box + PQ_PEER_DATA_BYTES) + slot * PQ_PEER_MAX_WORLD + sender;
+__device__ __forceinline__ void peer_store_line(uint4* p, unsigned long long w, unsigned int seq) {
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned int)w), "r"(seq),
+                 "r"((unsigned int)(w >> 32)), "r"(seq)
+                 : "memory");
+}
+__device__ __forceinline__ uint4 peer_load_line(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
 }
 __device__ __forceinline__ unsigned long long peer_now() {
     unsigned long long t;
@@ -59,6 +69,7 @@ enum { PEER_OP_BEST = 0, PEER_OP_ACC = 1, PEER_OP_SUM_I64 = 2 };
 template <int OP>
 __global__ void __launch_bounds__(256) k_peer_exchange(const __grid_constant__ PeerView V, unsigned long long* __restrict__ io,
                                                        int n8, int k) {
+    extern __shared__ unsigned long long s_got[];             // [world][n8] gathered payloads
     __shared__ int s_ok;
     __shared__ unsigned long long s_seq;
     if (threadIdx.x == 0) {
@@ -68,26 +79,27 @@ __global__ void __launch_bounds__(256) k_peer_exchange(const __grid_constant__ P
     }
     __syncthreads();
     const unsigned long long seq = s_seq;
+    const unsigned int seq32 = (unsigned int)seq;
     const int slot = (int)(seq & 1ULL), me = V.rank, W = V.world;
-    // push my payload into every mailbox (my own included)
+    // push my payload into every mailbox (my own included): one 16-byte line per word, data and exchange number together
     for (int idx = threadIdx.x; idx < W * n8; idx += blockDim.x) {
         const int r = idx / n8, w = idx - r * n8;
-        *(volatile unsigned long long*)(peer_data(V.box[r], slot, me) + w) = io[w];
+        peer_store_line(peer_line(V.box[r], slot, me) + w, io[w], seq32);
     }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < W) {
-        *(volatile unsigned long long*)peer_flag(V.box[threadIdx.x], slot, me) = seq;
-        // wait for sender threadIdx.x's payload in my mailbox
-        volatile unsigned long long* f = peer_flag(V.box[me], slot, threadIdx.x);
-        const unsigned long long t0 = peer_now();
-        while (*f < seq) {
+    // gather: poll every sender's lines in my mailbox until both halves carry this exchange's number
+    unsigned long long* got = s_got;                          // [W][n8] when it fits, else re-read in the merge below
+    const unsigned long long t0 = peer_now();
+    for (int idx = threadIdx.x; idx < W * n8; idx += blockDim.x) {
+        const int r = idx / n8, w = idx - r * n8;
+        const uint4* ln = peer_line(V.box[me], slot, r) + w;
+        uint4 v = peer_load_line(ln);
+        while (v.y != seq32 || v.w != seq32) {
             if (peer_now() - t0 > V.timeout_ns) { s_ok = 0; break; }
+            v = peer_load_line(ln);
         }
+        got[idx] = ((unsigned long long)v.z << 32) | (unsigned long long)v.x;
     }
     __syncthreads();
-    __threadfence_system();
-    unsigned char* mine = V.box[me];
     if (!s_ok) {                                               // a peer never arrived: poison the result
         for (int w = threadIdx.x; w < n8; w += blockDim.x) io[w] = 0xFFF8000000000000ULL;
         if (OP == PEER_OP_BEST && threadIdx.x == 0) io[1] = (unsigned long long)(-1LL);
@@ -98,7 +110,7 @@ __global__ void __launch_bounds__(256) k_peer_exchange(const __grid_constant__ P
         if (threadIdx.x < 32) {
             Best b = best_none();
             for (int r = threadIdx.x; r < W; r += 32) {
-                volatile unsigned long long* d = peer_data(mine, slot, r);
+                const unsigned long long* d = got + (size_t)r * n8;
                 Best o;
                 o.v = __longlong_as_double((long long)d[0]);
                 o.i = (long long)d[1];
@@ -114,9 +126,9 @@ __global__ void __launch_bounds__(256) k_peer_exchange(const __grid_constant__ P
     } else if (OP == PEER_OP_ACC) {                            // sums / minima / maxima by slot, fixed rank order
         const int mn0 = PEUQSE_ACC_MIN(k), mx0 = PEUQSE_ACC_MAX(k);
         for (int a = threadIdx.x; a < n8; a += blockDim.x) {
-            double r = __longlong_as_double((long long)*(volatile unsigned long long*)(peer_data(mine, slot, 0) + a));
+            double r = __longlong_as_double((long long)got[a]);
             for (int q = 1; q < W; ++q) {
-                const double x = __longlong_as_double((long long)*(volatile unsigned long long*)(peer_data(mine, slot, q) + a));
+                const double x = __longlong_as_double((long long)got[(size_t)q * n8 + a]);
                 if (a >= mx0) r = fmax(r, x);
                 else if (a >= mn0) r = fmin(r, x);
                 else r += x;
@@ -126,7 +138,7 @@ __global__ void __launch_bounds__(256) k_peer_exchange(const __grid_constant__ P
     } else {                                                   // integer sums (histograms)
         for (int a = threadIdx.x; a < n8; a += blockDim.x) {
             unsigned long long r = 0ULL;
-            for (int q = 0; q < W; ++q) r += *(volatile unsigned long long*)(peer_data(mine, slot, q) + a);
+            for (int q = 0; q < W; ++q) r += got[(size_t)q * n8 + a];
             io[a] = r;
         }
     }
@@ -152,7 +164,7 @@ extern "C" int peuqse_peer_create(void* d_local, const void* handles, int32_t ra
     peuqse_peer* p = new peuqse_peer();
     p->v.rank = rank;
     p->v.world = world;
-    p->v.seq = reinterpret_cast<unsigned long long*>((unsigned char*)d_local + PQ_PEER_DATA_BYTES + PQ_PEER_FLAG_BYTES);
+    p->v.seq = reinterpret_cast<unsigned long long*>((unsigned char*)d_local + PQ_PEER_DATA_BYTES);
     const char* ts = getenv("PEUQSE_PEER_TIMEOUT_S");
     const double tsec = ts ? atof(ts) : 60.0;
     p->v.timeout_ns = (unsigned long long)((tsec > 0 ? tsec : 60.0) * 1e9);
@@ -186,6 +198,11 @@ extern "C" int peuqse_peer_create(void* d_local, const void* handles, int32_t ra
         p->v.box[r] = (unsigned char*)q;
         p->opened[r] = true;
     }
+    // the gathered payloads of the largest exchange (world x PQ_PEER_PAYLOAD bytes) live in dynamic shared memory
+    const int smem = PQ_PEER_MAX_WORLD * PQ_PEER_PAYLOAD;
+    cudaFuncSetAttribute((const void*)k_peer_exchange<PEER_OP_BEST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute((const void*)k_peer_exchange<PEER_OP_ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute((const void*)k_peer_exchange<PEER_OP_SUM_I64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     *out = p;
     return PEUQSE_OK;
 }
@@ -210,7 +227,7 @@ extern "C" int64_t peuqse_peer_max_bytes(void) { return PQ_PEER_PAYLOAD; }
 // d_best: this rank's record in, the merged record out (every rank ends with the same record)
 extern "C" int peuqse_peer_merge_best(peuqse_peer* p, peuqse_best* d_best, void* stream) {
     if (!p || !d_best) return pq_set_error(PEUQSE_ERR_INVALID, "bad peer_merge_best arguments");
-    k_peer_exchange<PEER_OP_BEST><<<1, 256, 0, (cudaStream_t)stream>>>(p->v, (unsigned long long*)d_best, 2, 0);
+    k_peer_exchange<PEER_OP_BEST><<<1, 64, (size_t)p->v.world * 2 * 8, (cudaStream_t)stream>>>(p->v, (unsigned long long*)d_best, 2, 0);
     PQ_CUDA_OK(cudaGetLastError());
     return PEUQSE_OK;
 }
@@ -218,7 +235,7 @@ extern "C" int peuqse_peer_merge_best(peuqse_peer* p, peuqse_best* d_best, void*
 // d_acc: PEUQSE_ACC_DOUBLES(k) doubles, combined over ranks like peuqse_merge_acc
 extern "C" int peuqse_peer_merge_acc(peuqse_peer* p, double* d_acc, int32_t k, void* stream) {
     if (!p || !d_acc || k < 1 || k > PQ_MAXK) return pq_set_error(PEUQSE_ERR_INVALID, "bad peer_merge_acc arguments");
-    k_peer_exchange<PEER_OP_ACC><<<1, 256, 0, (cudaStream_t)stream>>>(p->v, (unsigned long long*)d_acc, PEUQSE_ACC_DOUBLES(k), k);
+    k_peer_exchange<PEER_OP_ACC><<<1, 256, (size_t)p->v.world * PEUQSE_ACC_DOUBLES(k) * 8, (cudaStream_t)stream>>>(p->v, (unsigned long long*)d_acc, PEUQSE_ACC_DOUBLES(k), k);
     PQ_CUDA_OK(cudaGetLastError());
     return PEUQSE_OK;
 }
@@ -227,7 +244,7 @@ extern "C" int peuqse_peer_merge_acc(peuqse_peer* p, double* d_acc, int32_t k, v
 extern "C" int peuqse_peer_sum_i64(peuqse_peer* p, void* d_buf, int64_t count, void* stream) {
     if (!p || !d_buf || count < 0 || count * 8 > PQ_PEER_PAYLOAD) return pq_set_error(PEUQSE_ERR_INVALID, "bad peer_sum_i64 arguments");
     if (count == 0) return PEUQSE_OK;
-    k_peer_exchange<PEER_OP_SUM_I64><<<1, 256, 0, (cudaStream_t)stream>>>(p->v, (unsigned long long*)d_buf, (int)count, 0);
+    k_peer_exchange<PEER_OP_SUM_I64><<<1, 256, (size_t)p->v.world * count * 8, (cudaStream_t)stream>>>(p->v, (unsigned long long*)d_buf, (int)count, 0);
     PQ_CUDA_OK(cudaGetLastError());
     return PEUQSE_OK;
 }
