@@ -231,12 +231,37 @@ struct MhwLayout {
     static constexpr int WDOUBLES = 2 * KPAD + 64;       // cur[KPAD] | th0[KPAD] | draws[32][2]
 };
 
+// the draws of one lane for four steps of its chain (lane = 8 * step offset + block): a pair of normals (blocks 0..6) or the
+// accept uniform and its logarithm (block 7).  Not inlined: the large-argument paths of sincos and log would otherwise set
+// the register budget of the whole kernel although they run once every four steps.
+__device__ __noinline__ double2 mhw_draw(unsigned long long seed, unsigned long long gchain, unsigned long long step, int blk, int k) {
+    const Philox4 r = philox_block(seed, PQ_STREAM_MH, gchain, (uint32_t)(8ULL * step + (unsigned)blk));
+    double a = 0.0, b2 = 0.0;
+    if (blk < 7) {
+        if (2 * blk < k) philox_normal_pair(r, a, b2);
+    } else {
+        a = philox_u53(r.x, r.y);
+        b2 = log(a);
+    }
+    return make_double2(a, b2);
+}
+__device__ __noinline__ double mhw_exp(double x) { return exp(x); }
+template <int KT>
+__device__ __noinline__ double mhw_prior(const DevProblem& P, const double (&th)[KT]) { return eval_prior<KT>(P, th); }
+
 // TEVAL: every lane evaluates the whole likelihood in the thread shape's order (few observations, few chains):
 // the values are bit-identical to k_mh's, and what the warp buys is latency -- draws for four steps per pass and
 // lane-spread moments cut a chain step from ~4000 to a few hundred cycles when there are too few chains to fill
 // the machine with one thread each.
-template <int MODEL, int KT, int U, int SMEM, bool TEVAL = false, int MINB = 4, bool SCEN = false>
-__global__ void __launch_bounds__(32 * MHW_WARPS, MINB) k_mh_warp(const __grid_constant__ DevProblem P,
+// FAST (two-site rate-law model, one response with diagonal covariance, constants staged; config C3): the observation loop
+// is the kernel's own -- per observation {y w, w}, {cov1, cov2} and 1/kBT come from shared memory as two 16-byte and one
+// 8-byte load, the exponent of each site is two FMAs, the exp is table-driven (eval.cuh: pq_exp_tab), site sum, residual and
+// square are three FMAs: 28 fp64 instructions per observation where the general path issues 52.  The arguments of all exps
+// of a proposal are bounded ONCE from the extrema of the constants; a proposal beyond the bound (practically never) goes
+// through the general, range-checked path on the constants in global memory.  Values agree with the general path to a few
+// ulp of the simulated response (log-posterior ~1e-15 relative; accept / reject sequences of the tests are unchanged).
+template <int MODEL, int KT, int U, int SMEM, bool TEVAL = false, int MINB = 4, bool SCEN = false, bool FAST = false, int NW = MHW_WARPS>
+__global__ void __launch_bounds__(32 * NW, MINB) k_mh_warp(const __grid_constant__ DevProblem P,
                                                                const __grid_constant__ DevMH M,
                                                                const double* __restrict__ theta0, const MHOut out,
                                                                int use_smem, const DevScen SC) {
@@ -246,8 +271,75 @@ __global__ void __launch_bounds__(32 * MHW_WARPS, MINB) k_mh_warp(const __grid_c
     double* cur = smem + warp * L::WDOUBLES;
     double* th0s = cur + L::KPAD;
     double2* dr = reinterpret_cast<double2*>(th0s + L::KPAD);
-    ObsView O = stage_obs<SMEM>(P, smem + MHW_WARPS * L::WDOUBLES, use_smem);
-    const long long c = (long long)blockIdx.x * MHW_WARPS + warp;
+    ObsView O;
+    __shared__ double s_exp_tab[FAST ? 64 : 1];
+    __shared__ double s_ext[4];
+    if constexpr (FAST) {
+        static_assert(MODEL == PEUQSE_MODEL_TPD2SITE && !TEVAL && !SCEN && KT >= 6, "FAST is the two-site rate-law shape");
+        O.y = P.y; O.w = P.w; O.cval = P.cval; O.mc = P.mconst; O.tab = nullptr;     // general path: constants in global memory
+        const int n = P.n_total;
+        double2* yw = reinterpret_cast<double2*>(smem + NW * L::WDOUBLES);
+        double2* cc = yw + n;
+        double* rk = reinterpret_cast<double*>(cc + n);
+        double m0 = 0.0, m1 = 0.0, m2 = 0.0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const double y = P.y[i], w = P.w[i], c1 = P.mconst[n + i], c2 = P.mconst[2 * n + i], r = P.mconst[3 * n + i];
+            yw[i] = make_double2(y * w, w);
+            cc[i] = make_double2(c1, c2);
+            rk[i] = r;
+            m0 = fmax(m0, fabs(r)); m1 = fmax(m1, fabs(c1)); m2 = fmax(m2, fabs(c2));
+        }
+        if (threadIdx.x < 64) s_exp_tab[threadIdx.x] = c_exp_tab64[threadIdx.x];
+        if (threadIdx.x < 4) s_ext[threadIdx.x] = 0.0;
+        __syncthreads();
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            m0 = fmax(m0, __shfl_xor_sync(0xffffffffu, m0, o));
+            m1 = fmax(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+            m2 = fmax(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+        }
+        if (lane == 0) {                                         // non-negative doubles order like their bit patterns
+            atomicMax(reinterpret_cast<unsigned long long*>(&s_ext[0]), (unsigned long long)__double_as_longlong(m0));
+            atomicMax(reinterpret_cast<unsigned long long*>(&s_ext[1]), (unsigned long long)__double_as_longlong(m1));
+            atomicMax(reinterpret_cast<unsigned long long*>(&s_ext[2]), (unsigned long long)__double_as_longlong(m2));
+        }
+        __syncthreads();
+    } else {
+        O = stage_obs<SMEM>(P, smem + NW * L::WDOUBLES, use_smem);
+    }
+    // log-likelihood of a parameter vector (every lane ends with the same value)
+    auto loglik = [&](const double (&p)[KT]) -> double {
+        if constexpr (TEVAL) {
+            return eval_loglik_thread<MODEL, KT>(P, O, p, nullptr);
+        } else if constexpr (FAST) {
+            const double rkm = s_ext[0];
+            const double b1 = fabs(p[2]) + (fabs(p[4]) * s_ext[1] + fabs(p[0])) * rkm;
+            const double b2 = fabs(p[3]) + (fabs(p[5]) * s_ext[2] + fabs(p[1])) * rkm;
+            if (!(fmax(b1, b2) < 700.0)) return eval_loglik_warp_checked<MODEL, KT, 2>(P, O, p, nullptr, lane);   // a call, not inlined
+            const double E1 = -p[0], E2 = -p[1], A1 = p[2], A2 = p[3], g1 = p[4], g2 = p[5];
+            const int n = P.n_total;
+            // the staged constants, addressed from the shared-memory array itself (LDS with immediate offsets, no generic loads)
+            const double2* f_yw = reinterpret_cast<const double2*>(smem + NW * L::WDOUBLES);
+            const double2* f_cc = f_yw + n;
+            const double* f_rk = reinterpret_cast<const double*>(f_cc + n);
+            double part = 0.0;
+#pragma unroll 2
+            for (int j = lane; j < n; j += 32) {
+                const double2 yw = f_yw[j], c = f_cc[j];
+                const double r = f_rk[j];
+                const double e1 = pq_exp_tab_bounded(P, s_exp_tab, fma(fma(g1, c.x, E1), r, A1));
+                const double e2 = pq_exp_tab_bounded(P, s_exp_tab, fma(fma(g2, c.y, E2), r, A2));
+                const double s = fma(c.y, e2, c.x * e1);
+                const double t = fma(-s, yw.y, yw.x);           // (y - sim) * w
+                part = fma(t, t, part);
+            }
+            const double total = -0.5 * (P.resp_c[0] + warp_sum(part));
+            return (total != total) ? pq_neg_inf() : total;
+        } else {
+            return eval_loglik_warp<MODEL, KT, U>(P, O, p, nullptr, lane);
+        }
+    };
+    const long long c = (long long)blockIdx.x * NW + warp;
     if (c >= M.n_chains) return;
     const int k = P.k;
     const long long C = M.n_chains;
@@ -288,7 +380,7 @@ __global__ void __launch_bounds__(32 * MHW_WARPS, MINB) k_mh_warp(const __grid_c
     double nacc = 0.0, maplogp = pq_neg_inf(), maprow = -1.0, sumexp = 0.0, mapth = 0.0;
 
     double cur_lp = eval_prior<KT>(P, th);
-    double cur_ll = TEVAL ? eval_loglik_thread<MODEL, KT>(P, O, th, nullptr) : eval_loglik_warp<MODEL, KT, U>(P, O, th, nullptr, lane);
+    double cur_ll = loglik(th);
     double cur_sum = cur_ll + cur_lp;
     auto add_row = [&](long long row, double lp, double explp) {
         if (lp > maplogp) {                                       // first maximum (IP.py:1925-1927)
@@ -320,16 +412,9 @@ __global__ void __launch_bounds__(32 * MHW_WARPS, MINB) k_mh_warp(const __grid_c
         const int g = (int)((i - 1) & 3);
         if (g == 0) {
             const unsigned long long step = (unsigned long long)(M.first_step + i + sub);
-            const Philox4 r = philox_block(M.seed, PQ_STREAM_MH, gchain, (uint32_t)(8ULL * step + (unsigned)blk));
-            double a = 0.0, b2 = 0.0;
-            if (blk < 7) {
-                if (2 * blk < k) philox_normal_pair(r, a, b2);
-            } else {
-                a = philox_u53(r.x, r.y);
-                b2 = log(a);
-            }
+            const double2 d2 = mhw_draw(M.seed, gchain, step, blk, k);
             __syncwarp();
-            dr[lane] = make_double2(a, b2);
+            dr[lane] = d2;
             __syncwarp();
         }
         double z[KT], delta[KT], prop[KT];
@@ -343,9 +428,8 @@ __global__ void __launch_bounds__(32 * MHW_WARPS, MINB) k_mh_warp(const __grid_c
         make_delta<KT>(M, z, delta);
 #pragma unroll
         for (int d = 0; d < KT; ++d) prop[d] = th[d] + delta[d];  // IP.py:2630
-        const double lp_p = eval_prior<KT>(P, prop);
-        const double ll_p = TEVAL ? eval_loglik_thread<MODEL, KT>(P, O, prop, nullptr)
-                                  : eval_loglik_warp<MODEL, KT, U>(P, O, prop, nullptr, lane);
+        const double lp_p = FAST ? mhw_prior<KT>(P, prop) : eval_prior<KT>(P, prop);
+        const double ll_p = loglik(prop);
         const double sum_p = ll_p + lp_p;
         double la = sum_p - cur_sum;                              // IP.py:2641
         if (M.modulate != 0.0) la = (1.0 / M.modulate) * la;      // IP.py:2649
@@ -354,7 +438,7 @@ __global__ void __launch_bounds__(32 * MHW_WARPS, MINB) k_mh_warp(const __grid_c
 #pragma unroll
             for (int d = 0; d < KT; ++d) th[d] = prop[d];
             cur_lp = lp_p; cur_ll = ll_p; cur_sum = sum_p;
-            cur_exp = exp(cur_sum);
+            cur_exp = mhw_exp(cur_sum);
             nacc += 1.0;
             __syncwarp();
             if (lane == 0) {
@@ -464,10 +548,36 @@ int launch_mh(const peuqse_problem* p, const DevMH& M, const double* th0, const 
         if (p->d.n_total <= PQ_THREAD_SHAPE_MAX_N) kern = k_mh_warp<MODEL, KT, 2, -1, true>;
         // 3 CTAs (12 chains) per SM at 168 registers: the 4-CTA shape spills inside the observation loop and is 8 % slower
         else if (use_smem) kern = k_mh_warp<MODEL, KT, 2, 1, false, 3>;
-        const size_t wsmem = smem + (size_t)MHW_WARPS * MhwLayout<KT>::WDOUBLES * sizeof(double);
+        int nw = MHW_WARPS;
+        if constexpr (MODEL == PEUQSE_MODEL_TPD2SITE) {
+            // the fast rate-law shape (see k_mh_warp).  A chain occupies its warp for the whole run, so the launch is a
+            // sequence of WAVES of (resident warps per SM) x (SMs) chains and a partly filled last wave is lost time (4096
+            // chains on 148 SMs at 12 warps per SM: 2.31 -> 3 waves).  Among the compiled shapes -- 3 CTAs of 4 warps, 2 CTAs
+            // of 7 warps, 2 CTAs of 8 warps -- take the one with the smallest waves x warps-per-SM product (time per wave
+            // grows with the resident warps: the SM is throughput-bound).
+            const bool fast_ok = use_smem && p->d.n_resp == 1 && p->d.resp_mode[0] == PEUQSE_RESP_MVN_DIAG && !p->d.any_per_value;
+            if (fast_ok) {
+                static int forced = -1;
+                if (forced < 0) { const char* e = getenv("PEUQSE_MH_SHAPE"); forced = e ? atoi(e) : 0; }
+                const int shapes[3][2] = {{4, 3}, {7, 2}, {8, 2}};
+                int best = 0;
+                double best_cost = 1e300;
+                for (int q = 0; q < 3; ++q) {
+                    const long long per_wave = (long long)p->sm_count * shapes[q][0] * shapes[q][1];
+                    const double cost = (double)((M.n_chains + per_wave - 1) / per_wave) * shapes[q][0] * shapes[q][1];
+                    if (cost < best_cost - 1e-9) { best_cost = cost; best = q; }
+                }
+                if (forced >= 1 && forced <= 3) best = forced - 1;
+                nw = shapes[best][0];
+                if (best == 0) kern = k_mh_warp<MODEL, KT, 2, 1, false, 3, false, true, 4>;
+                if (best == 1) kern = k_mh_warp<MODEL, KT, 2, 1, false, 2, false, true, 7>;
+                if (best == 2) kern = k_mh_warp<MODEL, KT, 2, 1, false, 2, false, true, 8>;
+            }
+        }
+        const size_t wsmem = smem + (size_t)nw * MhwLayout<KT>::WDOUBLES * sizeof(double);
         PQ_CUDA_OK(pq_allow_smem((const void*)kern, wsmem));
-        const long long blocks = (M.n_chains + MHW_WARPS - 1) / MHW_WARPS;
-        kern<<<(unsigned)blocks, 32 * MHW_WARPS, wsmem, st>>>(p->d, M, th0, out, use_smem, SC);
+        const long long blocks = (M.n_chains + nw - 1) / nw;
+        kern<<<(unsigned)blocks, 32 * nw, wsmem, st>>>(p->d, M, th0, out, use_smem, SC);
     } else {
         auto kern = k_mh<MODEL, KT>;
         PQ_CUDA_OK(pq_allow_smem((const void*)kern, smem));

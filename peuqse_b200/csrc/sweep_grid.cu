@@ -838,40 +838,34 @@ __device__ __forceinline__ double pq_exp_pos(double x) {
     return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
 }
 
-struct KTile {            // one retained tile of a CTA's batch
-    int row;              // row - b_lo
-    short chunk;
-    unsigned short mask;  // warps whose tile maximum is above the threshold
-};
-
-__device__ __forceinline__ TileSpan tile_span_rc(const GridTiling& T, long long first, long long count, int row, int chunk) {
-    TileSpan s;
-    s.start = T.ML + (T.b_lo + row) * T.r2 + (long long)chunk * GR_CH - first;
-    const long long rem = T.r2 - (long long)chunk * GR_CH;
-    s.len = (int)(rem < GR_CH ? rem : GR_CH);
-    s.lo = s.start > 0 ? s.start : 0;
-    s.hi = s.start + s.len < count ? s.start + s.len : count;
-    if (s.hi < s.lo) s.hi = s.lo;
-    s.a0 = s.lo & ~1LL;
-    s.a1 = (s.hi + 1) & ~1LL;
-    if (s.a1 > count) s.a1 = s.hi & ~1LL;          // never read past the caller's buffer
-    if (s.a1 < s.a0) s.a1 = s.a0;
-    return s;
-}
+// ---------------------------------------------------------------------------------------------
+// pass 2, warp-autonomous version (the one the C2 step uses).  Its predecessor moved whole 2048-point tiles through one
+// CTA-wide ring: one __syncthreads per tile (ncu, profiles/r2_ncu_c2_pass2_before_after.md: 22 % of the warp samples waiting
+// at that barrier).  Here every WARP is its own consumer: it walks a strided sequence of warp tiles, tests their pass-1
+// maxima 32 at a time (one candidate per lane, one ballot), and streams only the retained ones through its private
+// 4-stage ring of 2 KB bulk copies (cp.async.bulk + mbarrier) -- no CTA-level synchronisation inside the loop, copies of up
+// to four tiles in flight per warp.  Per retained point: exp, trunc, the weight sums of its row and column; the column
+// of a point is no longer owned by one thread, so the per-CTA column sums are shared-memory reductions (RED.shared).
+// The last-axis offset of a column is rebuilt from one int-to-double conversion per warp tile (the eight columns of a
+// lane are 16 half-steps apart: exact additions), not from one per point.  Integer weights are exact in any order, the
+// products accumulate per lane in the order the warp meets its tiles (fixed assignment: deterministic).
+// ---------------------------------------------------------------------------------------------
+#define P2W_STAGES 4
+#define P2W_STAGE_DOUBLES 260          // 256 points + alignment slack (copies start and end on 16-byte boundaries)
 
 template <int KT>
-__global__ void __launch_bounds__(GR_THREADS) k_grid_pass2_tma2(const __grid_constant__ DevSweep S,
+__global__ void __launch_bounds__(GR_THREADS, 2) k_grid_pass2_w(const __grid_constant__ DevSweep S,
                                                                 const __grid_constant__ GridTiling T, long long first,
                                                                 long long count, const double* __restrict__ logp_in,
                                                                 const GridAux aux, const peuqse_best* __restrict__ best_in,
                                                                 double log_rel, double* __restrict__ partial,
                                                                 double* __restrict__ acc_out, unsigned int* __restrict__ ticket) {
     extern __shared__ __align__(16) unsigned char s_raw[];
-    double* s_buf = (double*)s_raw;                                              // [P2_STAGES][P2_STAGE_DOUBLES]
-    KTile* s_klist = (KTile*)(s_buf + P2_STAGES * P2_STAGE_DOUBLES);             // [P2_KLIST]
-    unsigned int* s_col = (unsigned int*)(s_klist + P2_KLIST);                   // [nchunks*GR_CH] column weight sums
-    __shared__ __align__(8) unsigned long long s_full[P2_STAGES];
-    __shared__ int s_nk;
+    double* s_buf = (double*)s_raw;                                              // [GR_WARPS][P2W_STAGES][P2W_STAGE_DOUBLES]
+    unsigned int* s_col = (unsigned int*)(s_buf + GR_WARPS * P2W_STAGES * P2W_STAGE_DOUBLES);   // [nchunks*GR_CH] column weight sums
+    __shared__ __align__(8) unsigned long long s_full[GR_WARPS][P2W_STAGES];
+    __shared__ long long s_mstart[GR_WARPS][P2W_STAGES];                         // per stage: first element of the warp tile ...
+    __shared__ int2 s_mrc[GR_WARPS][P2W_STAGES];                                 // ... its row and first column
     __shared__ double s_red[GR_WARPS];
     __shared__ bool s_last;
     constexpr int L = KT - 1;
@@ -882,131 +876,134 @@ __global__ void __launch_bounds__(GR_THREADS) k_grid_pass2_tma2(const __grid_con
     grid_point<KT>(S, (unsigned long long)(none ? 0 : best_index), shift, KT);   // moments about the MAP point
     const double shiftL = shift[L], cL = S.center[L], hL = S.interval[L];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long ntiles = (T.b_hi - T.b_lo) * T.nchunks;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < P2_STAGES; ++s) mbar_init(&s_full[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const int wpr = T.nchunks * GR_WARPS;                                        // warp tiles per row
+    const long long nwt = none ? 0 : (T.b_hi - T.b_lo) * wpr;                    // warp tiles of the range
+    if (lane == 0) {
+        for (int s = 0; s < P2W_STAGES; ++s) mbar_init(&s_full[warp][s], 1);
     }
+    if (threadIdx.x == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     for (int a = threadIdx.x; a < T.nchunks * GR_CH; a += blockDim.x) s_col[a] = 0u;
     __syncthreads();
-    double a_wr = 0.0, a_nk = 0.0;
-    const long long nt_blk = none ? 0 : (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;   // tiles blockIdx.x + i*gridDim.x
-    unsigned int it = 0;                                             // stages consumed so far (ring position / phase)
-    for (long long base = 0; base < nt_blk; base += P2_KLIST) {
-        // (1) list the tiles of this batch that hold retained points (row / chunk resolved here, once per tile)
-        if (threadIdx.x == 0) s_nk = 0;
-        __syncthreads();
-        for (int i = threadIdx.x; i < P2_KLIST && base + i < nt_blk; i += blockDim.x) {
-            const long long t = blockIdx.x + (base + i) * gridDim.x;
-            const uint4 k0 = __ldg((const uint4*)(aux.tilemax + (size_t)t * GR_WARPS));
-            const uint4 k1 = __ldg((const uint4*)(aux.tilemax + (size_t)t * GR_WARPS) + 1);
-            const unsigned int ks[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
-            int mask = 0;
+    double* wbuf = s_buf + (size_t)warp * P2W_STAGES * P2W_STAGE_DOUBLES;
+    const double shl = (lane & 1) ? hL : -hL;                      // c + (h i) or c - (h i), CombinationGeneratorModule.py:59,71
+    const long long r2 = T.r2, base_el = T.ML + T.b_lo * T.r2 - first;
+    double a_wr = 0.0;
+    int a_nk = 0;
+    unsigned int issued = 0, consumed = 0;
+    const long long gw = (long long)blockIdx.x * GR_WARPS + warp, nw = (long long)gridDim.x * GR_WARPS;
+
+    // element range of a warp tile inside logp_in: [lo, hi) valid points, [a0, a1) the 16-byte aligned copy range
+    auto span = [&](long long start, int col, long long& lo, long long& hi, long long& a0, long long& a1) {
+        const long long rem = r2 - col;
+        const int len = (int)(rem < 256 ? (rem > 0 ? rem : 0) : 256);
+        lo = start > 0 ? start : 0;
+        hi = start + len < count ? start + len : count;
+        if (hi < lo) hi = lo;
+        a0 = lo & ~1LL;
+        a1 = (hi + 1) & ~1LL;
+        if (a1 > count) a1 = hi & ~1LL;          // never read past the caller's buffer
+        if (a1 < a0) a1 = a0;
+        return len;
+    };
+
+    auto consume = [&]() {
+        const int st = (int)(consumed % P2W_STAGES);
+        const long long start = s_mstart[warp][st];
+        const int2 rc = s_mrc[warp][st];
+        long long lo, hi, a0, a1;
+        const int len = span(start, rc.y, lo, hi, a0, a1);
+        while (!mbar_try_wait(&s_full[warp][st], (consumed / P2W_STAGES) & 1)) {}
+        const double* buf = wbuf + st * P2W_STAGE_DOUBLES;
+        const int j0 = rc.y + lane;                                 // column of this lane's first point
+        const double d0 = (double)((j0 >> 1) + 1);                  // its half-step count; the lane's other points: + 16 m
+        double roww = 0.0, rowwL = 0.0;
+        const bool whole = len == 256 && lo == start && hi == start + 256 && a1 >= hi;
+        if (whole) {
+            const double* bufw = buf + (start - a0) + lane;
+            double x[GR_JPT], reps[GR_JPT];
+            bool kp[GR_JPT];
 #pragma unroll
-            for (int w = 0; w < 8; ++w)
-                if (key_value(ks[w]) > thr) mask |= 1 << w;
-            if (mask) {
-                const long long row = t / T.nchunks;
-                KTile kt;
-                kt.row = (int)row;
-                kt.chunk = (short)(t - row * T.nchunks);
-                kt.mask = (unsigned short)mask;
-                s_klist[atomicAdd(&s_nk, 1)] = kt;
+            for (int m = 0; m < GR_JPT; ++m) {
+                const double v = bufw[m * 32];
+                kp[m] = v > thr;                                   // IP.py:3481
+                x[m] = kp[m] ? (v - thr) : 0.0;
             }
-        }
-        __syncthreads();
-        const int nk = s_nk;
-        // (2) prologue: P2_STAGES-1 copies in flight
-        if (threadIdx.x == 0) {
-            for (int q = 0; q < P2_STAGES - 1 && q < nk; ++q) {
-                const TileSpan sp = tile_span_rc(T, first, count, s_klist[q].row, s_klist[q].chunk);
-                const int st = (it + q) % P2_STAGES;
-                const uint32_t bytes = (uint32_t)((sp.a1 - sp.a0) * 8);
-                mbar_arrive_expect_tx(&s_full[st], bytes);
-                if (bytes) tma_load_1d(s_buf + st * P2_STAGE_DOUBLES, logp_in + sp.a0, bytes, &s_full[st]);
+#pragma unroll
+            for (int m = 0; m < GR_JPT; ++m) reps[m] = pq_exp_pos(x[m]);          // IP.py:3485
+#pragma unroll
+            for (int m = 0; m < GR_JPT; ++m) {
+                const double wt_ = kp[m] ? trunc(reps[m]) : 0.0;                  // IP.py:3486
+                const double dl = (cL + shl * (d0 + 16.0 * m)) - shiftL;
+                a_wr = fma(wt_, reps[m], a_wr);
+                a_nk += kp[m] ? 1 : 0;
+                roww += wt_;
+                rowwL = fma(wt_, dl, rowwL);
+                if (kp[m]) atomicAdd(&s_col[j0 + m * 32], (unsigned int)wt_);
             }
-        }
-        // (3) consume
-        for (int q = 0; q < nk; ++q, ++it) {
-            const int st = it % P2_STAGES;
-            if (threadIdx.x == 0 && q + P2_STAGES - 1 < nk) {        // refill the stage freed at the end of the previous iteration
-                const int qn = q + P2_STAGES - 1;
-                const TileSpan sp = tile_span_rc(T, first, count, s_klist[qn].row, s_klist[qn].chunk);
-                const int stn = (it + P2_STAGES - 1) % P2_STAGES;
-                const uint32_t bytes = (uint32_t)((sp.a1 - sp.a0) * 8);
-                mbar_arrive_expect_tx(&s_full[stn], bytes);
-                if (bytes) tma_load_1d(s_buf + stn * P2_STAGE_DOUBLES, logp_in + sp.a0, bytes, &s_full[stn]);
-            }
-            const KTile kt = s_klist[q];
-            const bool mine = (kt.mask >> warp) & 1;                 // this warp's tile maximum is above the threshold
-            while (!mbar_try_wait(&s_full[st], (it / P2_STAGES) & 1)) {}
-            if (mine) {
-                const TileSpan sp = tile_span_rc(T, first, count, kt.row, kt.chunk);
-                const int jt = kt.chunk * GR_CH + GR_JL0;
-                const double* buf = s_buf + st * P2_STAGE_DOUBLES;
-                double roww = 0.0, rowwL = 0.0;                      // sum_m w, sum_m w*(theta_L - shift_L)
-                // a complete tile whose copy covers every point (all but the ragged last chunk and a rank's first / last rows)
-                const bool whole = sp.len == GR_CH && sp.lo == sp.start && sp.hi == sp.start + GR_CH && sp.a1 >= sp.hi;
-                if (whole) {
-                    // branch-free: the eight exp chains of a thread interleave in the fp64 pipe (a branch around each one
-                    // serialises them: 13 dependent DFMAs per point); points below the threshold get x = 0 and weight 0,
-                    // which adds exact zeros in the same order, so the sums are bit-identical to the guarded form.
-                    const double* bufw = buf + (sp.start - sp.a0) + GR_JL0;
-                    double x[GR_JPT], reps[GR_JPT];
-                    bool kp[GR_JPT];
+        } else {
 #pragma unroll
-                    for (int m = 0; m < GR_JPT; ++m) {
-                        const double v = bufw[m * GR_MSTRIDE];
-                        kp[m] = v > thr;                             // IP.py:3481
-                        x[m] = kp[m] ? (v - thr) : 0.0;
-                    }
-#pragma unroll
-                    for (int m = 0; m < GR_JPT; ++m) reps[m] = pq_exp_pos(x[m]);    // IP.py:3485
-#pragma unroll
-                    for (int m = 0; m < GR_JPT; ++m) {
-                        const double wt = kp[m] ? trunc(reps[m]) : 0.0;             // IP.py:3486
-                        const int j = jt + m * GR_MSTRIDE;
-                        const double step = hL * (double)((j >> 1) + 1);
-                        const double dl = ((j & 1) ? (cL + step) : (cL - step)) - shiftL;
-                        a_wr = fma(wt, reps[m], a_wr);
-                        a_nk += kp[m] ? 1.0 : 0.0;
-                        roww += wt;
-                        rowwL = fma(wt, dl, rowwL);
-                        s_col[j] += (unsigned int)wt;                // j always belongs to this thread
-                    }
-                } else {
-#pragma unroll
-                    for (int m = 0; m < GR_JPT; ++m) {
-                        const long long e = sp.start + GR_JL0 + m * GR_MSTRIDE;
-                        double v = pq_neg_inf();
-                        if (GR_JL0 + m * GR_MSTRIDE < sp.len && e >= sp.lo && e < sp.hi)
-                            v = (e < sp.a1) ? buf[e - sp.a0] : __ldcs(logp_in + e);
-                        if (v > thr) {                                  // IP.py:3481
-                            const double reps = pq_exp_pos(v - thr);    // IP.py:3485
-                            const double wt = trunc(reps);              // IP.py:3486
-                            const int j = jt + m * GR_MSTRIDE;
-                            const double step = hL * (double)((j >> 1) + 1);
-                            const double dl = ((j & 1) ? (cL + step) : (cL - step)) - shiftL;
-                            a_wr = fma(wt, reps, a_wr);
-                            a_nk += 1.0;
-                            roww += wt;
-                            rowwL = fma(wt, dl, rowwL);
-                            s_col[j] += (unsigned int)wt;                // j always belongs to this thread
-                        }
-                    }
-                }
-                const double rw = warp_sum(roww);                    // integers < 2^53: exact in fp64
-                if (rw > 0.0) {
-                    const double rwl = warp_sum(rowwL);
-                    if (lane == 0) {
-                        atomicAdd(aux.rowsum + kt.row, rw);
-                        atomicAdd(aux.rowsumL + kt.row, rwl);
-                    }
+            for (int m = 0; m < GR_JPT; ++m) {
+                const long long e = start + lane + m * 32;
+                double v = pq_neg_inf();
+                if (lane + m * 32 < len && e >= lo && e < hi) v = (e < a1) ? buf[e - a0] : __ldcs(logp_in + e);
+                if (v > thr) {
+                    const double r_ = pq_exp_pos(v - thr);
+                    const double wt_ = trunc(r_);
+                    const double dl = (cL + shl * (d0 + 16.0 * m)) - shiftL;
+                    a_wr = fma(wt_, r_, a_wr);
+                    a_nk += 1;
+                    roww += wt_;
+                    rowwL = fma(wt_, dl, rowwL);
+                    atomicAdd(&s_col[j0 + m * 32], (unsigned int)wt_);
                 }
             }
-            __syncthreads();                                         // stage st may be refilled from now on
+        }
+        const double rw = warp_sum(roww);                           // integers < 2^53: exact in fp64
+        if (rw > 0.0) {
+            const double rwl = warp_sum(rowwL);
+            if (lane == 0) {
+                atomicAdd(aux.rowsum + rc.x, rw);
+                atomicAdd(aux.rowsumL + rc.x, rwl);
+            }
+        }
+        __syncwarp();                                               // every lane has read the stage: it may be refilled
+        ++consumed;
+    };
+
+    for (long long base = 0; gw + base * nw < nwt; base += 32) {
+        // one candidate warp tile per lane: retained iff the upper bound of its pass-1 maximum is above the threshold;
+        // the lane also resolves its candidate's row and first column (one division per lane per 32 candidates)
+        const long long mywt = gw + (base + lane) * nw;
+        bool keep = false;
+        int myrow = 0, mycol = 0;
+        if (mywt < nwt) {
+            keep = key_value(__ldg(aux.tilemax + mywt)) > thr;
+            myrow = (nwt < 0x7fffffffLL) ? (int)((unsigned int)mywt / (unsigned int)wpr) : (int)(mywt / wpr);
+            mycol = (int)(mywt - (long long)myrow * wpr) * 256;     // (chunk * 8 + w) * 256 = chunk * GR_CH + w * 256
+        }
+        unsigned int mask = __ballot_sync(0xffffffffu, keep);
+        while (mask) {
+            if (issued - consumed == P2W_STAGES) consume();
+            const int b = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const int row = __shfl_sync(0xffffffffu, myrow, b), col = __shfl_sync(0xffffffffu, mycol, b);
+            if (lane == 0) {
+                const long long start = base_el + (long long)row * r2 + col;
+                long long lo, hi, a0, a1;
+                span(start, col, lo, hi, a0, a1);
+                const int st = (int)(issued % P2W_STAGES);
+                const uint32_t bytes = (uint32_t)((a1 - a0) * 8);
+                s_mstart[warp][st] = start;
+                s_mrc[warp][st] = make_int2(row, col);
+                mbar_arrive_expect_tx(&s_full[warp][st], bytes);
+                if (bytes) tma_load_1d(wbuf + st * P2W_STAGE_DOUBLES, logp_in + a0, bytes, &s_full[warp][st]);
+            }
+            __syncwarp();
+            ++issued;
         }
     }
+    while (consumed < issued) consume();
+    __syncthreads();
     for (long long j = threadIdx.x; j < T.r2; j += blockDim.x) {
         const unsigned int cw = s_col[j];
         if (cw) atomicAdd(aux.colsum + j, (double)cw);
@@ -1014,7 +1011,7 @@ __global__ void __launch_bounds__(GR_THREADS) k_grid_pass2_tma2(const __grid_con
     double* mine_p = partial + (size_t)blockIdx.x * PQ_ACC_MAX;
     double r;
     r = blk_sum(a_wr, s_red); if (threadIdx.x == 0) mine_p[0] = none ? 0.0 : r * exp(thr);
-    r = blk_sum(a_nk, s_red); if (threadIdx.x == 0) mine_p[1] = r;
+    r = blk_sum((double)a_nk, s_red); if (threadIdx.x == 0) mine_p[1] = r;
     if (threadIdx.x == 0) {
         __threadfence();
         const unsigned int tkt = atomicAdd(ticket, 1u);
@@ -1511,12 +1508,12 @@ int pq_grid_pass2(const peuqse_problem* p, const DevSweep& S, long long first, l
             if (e != cudaSuccess) return pq_set_cuda_error(e, "cudaMemsetAsync", __LINE__);                                       \
         }                                                                                                                        \
         if (use_tma && fuse) {                                                                                                   \
-            const size_t sm2 = (size_t)P2_STAGES * P2_STAGE_DOUBLES * sizeof(double) + P2_KLIST * sizeof(KTile) +                 \
+            const size_t sm2 = (size_t)GR_WARPS * P2W_STAGES * P2W_STAGE_DOUBLES * sizeof(double) +                               \
                                (size_t)T.nchunks * GR_CH * sizeof(unsigned int);                                                   \
-            cudaError_t e = pq_allow_smem((const void*)k_grid_pass2_tma2<K>, sm2);                                                \
+            cudaError_t e = pq_allow_smem((const void*)k_grid_pass2_w<K>, sm2);                                                   \
             if (e != cudaSuccess) return pq_set_cuda_error(e, "cudaFuncSetAttribute", __LINE__);                                  \
-            const int g = flat_grid(T, resident_blocks(p, k_grid_pass2_tma2<K>, sm2));                                            \
-            k_grid_pass2_tma2<K><<<g, GR_THREADS, sm2, st>>>(S, T, first, count, logp, aux, best, log_rel, partial, acc, ticket);  \
+            const int g = resident_blocks(p, k_grid_pass2_w<K>, sm2);                                                             \
+            k_grid_pass2_w<K><<<g, GR_THREADS, sm2, st>>>(S, T, first, count, logp, aux, best, log_rel, partial, acc, ticket);     \
             k_grid_finish<K><<<16, GR_THREADS, 0, st>>>(S, T, first, logp, aux, best, log_rel, partial, acc, ticket);             \
         } else if (use_tma) {                                                                                                    \
             G2T(K, false)                                                                                                        \
