@@ -132,6 +132,10 @@ int peuqse_logp_batch(const peuqse_problem* p, const double* d_theta, int64_t B,
 int peuqse_logp_from_sim(const peuqse_problem* p, const double* d_theta, const double* d_sim, int64_t B,
                          double* d_logp, double* d_logprior, double* d_loglik, void* stream);
 
+/* replaces: getLogPrior alone (IP.py:2756-2794, bounds 2796-2805) -- for callers whose likelihood is their own
+ * (UserInput.model['custom_logLikelihood'], IP.py:2854-2857).  d_logprior[B]. */
+int peuqse_logprior_batch(const peuqse_problem* p, const double* d_theta, int64_t B, double* d_logprior, void* stream);
+
 /* simulate only (getSimulatedResponses, IP.py:2822-2848) for a built-in model: d_sim[B][n_total], natural order */
 int peuqse_simulate_batch(const peuqse_problem* p, const double* d_theta, int64_t B, double* d_sim, void* stream);
 
@@ -277,6 +281,11 @@ typedef struct peuqse_mh_spec {
     int32_t k;
     int32_t thin;                /* store every thin-th row (1 = all) */
     double step_chol[PEUQSE_MAX_K * PEUQSE_MAX_K]; /* row-major lower Cholesky factor of Q_covmat*step (IP.py:2630) */
+    int32_t map_finding;         /* mcmc_mode 'MAP_finding' (IP.py:2631-2635, 2688-2713): the proposal covariance is multiplied by
+                                    dyn * m_i, m_i = u + 0.5 a fresh uniform per step, dyn adapted every 100 steps by the sign of the
+                                    slope of (proposal log-posterior against m) over the previous hundred proposals (x 1.05 below 10,
+                                    x 0.95 above 0.1); 0 = 'unbiased' */
+    int32_t reserved;
 } peuqse_mh_spec;
 
 /* per-chain statistics block written by the kernel: PEUQSE_MH_STAT_DOUBLES(k) doubles per chain */
@@ -289,7 +298,8 @@ typedef struct peuqse_mh_spec {
 #define PEUQSE_MH_STAT_LAST(k) (5 + (k))                /* [k] last state                          */
 #define PEUQSE_MH_STAT_S1(k) (5 + 2 * (k))              /* [k] sum (th - th0) over rows >= burn_in */
 #define PEUQSE_MH_STAT_S2(k) (5 + 3 * (k))              /* [k*k] sum (th-th0)(th-th0)^T            */
-#define PEUQSE_MH_STAT_DOUBLES(k) (5 + 3 * (k) + (k) * (k))
+#define PEUQSE_MH_STAT_DYN(k) (5 + 3 * (k) + (k) * (k)) /* final step coefficient of 'MAP_finding' (1 when unbiased) */
+#define PEUQSE_MH_STAT_DOUBLES(k) (6 + 3 * (k) + (k) * (k))
 
 /*
  * d_theta0[C][k]: start points.  Outputs, all nullable except d_stats:
@@ -297,6 +307,7 @@ typedef struct peuqse_mh_spec {
  *   (layout = discrete_chains_post_burn_in_samples (nsteps, nchains, k), IP.py:2719);
  *   d_deltas[n_steps-1][C][k], d_us[n_steps-1][C]: the proposal increments and accept uniforms actually
  *   used (for feeding the reference the same draws); d_stats[C][PEUQSE_MH_STAT_DOUBLES(k)].
+ *   With map_finding, d_us holds TWO values per step, d_us[n_steps-1][C][2] = (accept uniform, modulation uniform + 0.5).
  */
 int peuqse_mh_run(const peuqse_problem* p, const peuqse_mh_spec* spec, const double* d_theta0,
                   double* d_samples, double* d_logp, double* d_logprior, double* d_loglik,

@@ -649,6 +649,59 @@ def mh_chains_batch(P: OracleProblem, theta0, deltas, us, simulate_batch: Callab
     return dict(samples=samples, logP=logp, log_priors=lps, log_likelihoods=lls, accepted=acc)
 
 
+def mh_chain_map_finding(P: OracleProblem, theta0, deltas, mods, us, simulate_batch: Callable, modulate=0.0, scaled=True):
+    """doMetropolisHastings with mcmc_mode 'MAP_finding' (IP.py:2631-2635, 2688-2713) for ONE chain fed its draws:
+    mods[i] = np.random.uniform() + 0.5 of step i+1, us[i] its accept uniform, deltas[i] the proposal increment -- already
+    multiplied by sqrt(dyn * mod) (scaled=True: what np.random.multivariate_normal(0, Q*dyn*mod*step) returned / what the
+    kernel exports) or the unbiased increment L z, which is then scaled here.  Every 100 steps the slope of a straight-line
+    fit (np.polynomial.polynomial.polyfit, as the reference) of the previous hundred proposals' log-posteriors against
+    their mods adapts dyn: x 1.05 while < 10 if positive, x 0.95 while > 0.1 if negative.  The history arrays start as
+    zeros, so the first window holds the entry (0, 0) of index 0 (IP.py:2608, 2616).
+    Returns samples[L,k], logP[L], dyn[L] (the coefficient used by each step; dyn[0] unused) and the final coefficient."""
+    th = np.array(theta0, dtype=float).reshape(1, -1)
+    L = len(us) + 1
+    k = th.shape[1]
+    samples = np.zeros((L, k))
+    logp = np.zeros(L)
+    drawn = np.zeros(L)
+    hist = np.zeros(L)
+    dyn_used = np.ones(L)
+    cur_p, cur_lp, cur_ll = log_p_batch(P, th, simulate_batch)
+    samples[0], logp[0] = th[0], cur_p[0]
+    cur_sum = float(cur_ll[0] + cur_lp[0])
+    dyn = 1
+    for i in range(1, L):
+        m = mods[i - 1]
+        hist[i] = m
+        dyn_used[i] = dyn
+        d = np.asarray(deltas[i - 1], dtype=float)
+        if not scaled:
+            d = np.sqrt(dyn * m) * d
+        prop = th + d
+        _, lp_p, ll_p = log_p_batch(P, prop, simulate_batch)
+        sum_p = float(ll_p[0] + lp_p[0])
+        with np.errstate(invalid='ignore', divide='ignore'):
+            la = sum_p - cur_sum
+            if modulate != 0:
+                la = (1 / float(modulate)) * la
+            acc = la > np.log(us[i - 1])
+        drawn[i] = sum_p
+        if acc:
+            th, cur_sum = prop, sum_p
+        samples[i], logp[i] = th[0], cur_sum
+        if i % 100 == 0:                                             # IP.py:2688-2713
+            y, x = drawn[i - 100:i], hist[i - 100:i]
+            ok = np.isfinite(y)
+            fit = np.polynomial.polynomial.polyfit(x[ok], y[ok], 1)
+            if fit[1] > 0:
+                if dyn < 10:
+                    dyn = dyn * 1.05
+            if fit[1] < 0:
+                if dyn > 0.1:
+                    dyn = dyn * 0.95
+    return dict(samples=samples, logP=logp, dyn=dyn_used, dyn_final=dyn, drawn=drawn)
+
+
 def post_burn_in_statistics(samples, logp):
     """IP.py:1923-1931 without the tail filter."""
     mu = np.mean(samples, axis=0)

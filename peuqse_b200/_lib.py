@@ -48,6 +48,7 @@ class MHSpec(C.Structure):
         ("n_chains", C.c_int64), ("n_steps", C.c_int64), ("burn_in", C.c_int64), ("first_step", C.c_int64),
         ("chain_offset", C.c_int64), ("seed", C.c_uint64), ("modulate", C.c_double),
         ("k", C.c_int32), ("thin", C.c_int32), ("step_chol", C.c_double * (MAX_K * MAX_K)),
+        ("map_finding", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -84,12 +85,12 @@ def acc_layout(k):
 def mh_stat_layout(k):
     """Offsets inside one chain's statistics block (PEUQSE_MH_STAT_* macros)."""
     return dict(NACC=0, MAPLOGP=1, MAPROW=2, LASTLOGP=3, SUMEXP=4, MAPTHETA=5, LAST=5 + k, S1=5 + 2 * k,
-                S2=5 + 3 * k, SIZE=5 + 3 * k + k * k)
+                S2=5 + 3 * k, DYN=5 + 3 * k + k * k, SIZE=6 + 3 * k + k * k)
 
 
 EXPORTS = [
     "peuqse_last_error", "peuqse_version", "peuqse_device_info", "peuqse_bench_fp64", "peuqse_problem_create", "peuqse_problem_destroy",
-    "peuqse_logp_batch", "peuqse_logp_from_sim", "peuqse_simulate_batch", "peuqse_sweep_work_bytes",
+    "peuqse_logp_batch", "peuqse_logprior_batch", "peuqse_logp_from_sim", "peuqse_simulate_batch", "peuqse_sweep_work_bytes",
     "peuqse_sweep_pass1", "peuqse_sweep_best_point", "peuqse_sweep_points", "peuqse_sweep_pass2", "peuqse_sweep_edges", "peuqse_sweep_hist",
     "peuqse_comm_unique_id", "peuqse_comm_create", "peuqse_comm_destroy", "peuqse_comm_allgather",
     "peuqse_comm_allreduce_sum_i64", "peuqse_peer_alloc", "peuqse_peer_create", "peuqse_peer_destroy",
@@ -133,6 +134,7 @@ def load():
     L.peuqse_problem_create.argtypes = [C.POINTER(ProblemDesc), C.POINTER(vp)]
     L.peuqse_problem_destroy.argtypes = [vp]
     L.peuqse_logp_batch.argtypes = [vp, vp, i64, vp, vp, vp, vp]
+    L.peuqse_logprior_batch.argtypes = [vp, vp, i64, vp, vp]
     L.peuqse_logp_from_sim.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp]
     L.peuqse_simulate_batch.argtypes = [vp, vp, i64, vp, vp]
     L.peuqse_sweep_work_bytes.restype = i64

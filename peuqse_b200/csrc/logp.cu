@@ -69,6 +69,19 @@ __global__ void __launch_bounds__(256) k_simulate(const __grid_constant__ DevPro
     }
 }
 
+// getLogPrior alone (IP.py:2756-2794): for callers that supply the likelihood themselves (custom_logLikelihood, IP.py:2854-2857)
+template <int KT>
+__global__ void __launch_bounds__(256) k_logprior(const __grid_constant__ DevProblem P, const double* __restrict__ theta, long long B,
+                                                  double* __restrict__ lprior) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < B; i += stride) {
+        double th[KT];
+#pragma unroll
+        for (int d = 0; d < KT; ++d) th[d] = (d < P.k) ? theta[i * P.k + d] : 0.0;
+        lprior[i] = eval_prior<KT>(P, th);
+    }
+}
+
 namespace {
 
 template <int MODEL, int KT>
@@ -174,6 +187,18 @@ extern "C" int peuqse_logp_batch(const peuqse_problem* p, const double* d_theta,
         default: break;
     }
     return pq_set_error(PEUQSE_ERR_INVALID, "unknown model");
+}
+
+extern "C" int peuqse_logprior_batch(const peuqse_problem* p, const double* d_theta, int64_t B, double* d_logprior, void* stream) {
+    if (!p || !d_theta || !d_logprior || B < 0) return pq_set_error(PEUQSE_ERR_INVALID, "bad argument");
+    if (B == 0) return PEUQSE_OK;
+    const int kb = pq_k_bucket(p->d.k);
+    const int grid = (int)std::min<long long>((B + 255) / 256, (long long)p->sm_count * 8);
+#define PQ_LPRIOR(KT, ...) k_logprior<KT><<<grid, 256, 0, (cudaStream_t)stream>>>(p->d, d_theta, B, d_logprior)
+    PQ_DISPATCH_K(kb, PQ_LPRIOR, 0)
+#undef PQ_LPRIOR
+    PQ_CUDA_OK(cudaGetLastError());
+    return PEUQSE_OK;
 }
 
 extern "C" int peuqse_logp_from_sim(const peuqse_problem* p, const double* d_theta, const double* d_sim, int64_t B,

@@ -15,8 +15,34 @@ struct DevMH {
     long long n_chains, n_steps, burn_in, first_step, chain_offset;
     unsigned long long seed;
     double modulate;
-    int k, thin, chol_diag, pad;
+    int k, thin, chol_diag, map_finding;
     double chol[PQ_MAXK * PQ_MAXK];
+};
+
+// mcmc_mode 'MAP_finding' (IP.py:2631-2635, 2688-2713): every step draws a modulation m = u + 0.5 and proposes with the
+// covariance Q * dyn * m * step, i.e. the increment of the unbiased mode times sqrt(dyn * m).  After every hundredth step the
+// previous hundred (m, proposal log-posterior) pairs with a finite log-posterior are fitted by a straight line
+// (np.polynomial.polynomial.polyfit, degree 1): positive slope -> dyn *= 1.05 while dyn < 10, negative -> dyn *= 0.95 while
+// dyn > 0.1.  Only the SIGN of the slope matters: n sum(xy) - sum(x) sum(y) over the window, with y taken relative to the
+// window's first finite value (no cancellation against |logP| ~ 1e4).  The first window starts with the entry (0, 0): index 0
+// of the reference's zero-initialised history arrays lies inside its slice [i-100:i] at i = 100.
+struct MapFind {
+    double dyn, n, sx, sy, sxy, y0;
+    __device__ __forceinline__ void init() { dyn = 1.0; n = 1.0; sx = 0.0; sy = 0.0; sxy = 0.0; y0 = 0.0; }
+    __device__ __forceinline__ double scale(double m) const { return sqrt(dyn * m); }
+    __device__ __forceinline__ void after_step(long long i, double m, double logp_drawn) {
+        if (i % 100 == 0) {
+            const double num = n * sxy - sx * sy;
+            if (num > 0.0) { if (dyn < 10.0) dyn = dyn * 1.05; }
+            else if (num < 0.0) { if (dyn > 0.1) dyn = dyn * 0.95; }
+            n = 0.0; sx = 0.0; sy = 0.0; sxy = 0.0;
+        }
+        if (fabs(logp_drawn) < pq_pos_inf()) {                     // finite (NaN compares false)
+            if (n == 0.0) y0 = logp_drawn;
+            const double y = logp_drawn - y0;
+            n += 1.0; sx += m; sy += y; sxy = fma(m, y, sxy);
+        }
+    }
 };
 
 struct MHOut {
@@ -110,7 +136,7 @@ __device__ __forceinline__ void make_delta(const DevMH& M, const double (&z)[KT]
 // draws for (chain, step): normals from blocks 8*step + j, accept uniform from block 8*step + 7
 template <int KT>
 __device__ __forceinline__ void draws_thread(const DevMH& M, unsigned long long chain, unsigned long long step,
-                                             double (&z)[KT], double& u) {
+                                             double (&z)[KT], double& u, double& um) {
 #pragma unroll
     for (int b = 0; b < (KT + 1) / 2; ++b) {
         double z0 = 0.0, z1 = 0.0;
@@ -120,6 +146,7 @@ __device__ __forceinline__ void draws_thread(const DevMH& M, unsigned long long 
     }
     const Philox4 r = philox_block(M.seed, PQ_STREAM_MH, chain, (uint32_t)(8ULL * step + 7ULL));
     u = philox_u53(r.x, r.y);
+    um = philox_u53(r.z, r.w);                                     // the other half of the block: 'MAP_finding' modulation
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -169,11 +196,19 @@ __global__ void __launch_bounds__(128) k_mh(const __grid_constant__ DevProblem P
     double cur_exp = exp(cur_sum);                               // exp(logP) of the current state, for the evidence sum
     long long next_row = 1;                                      // rows are written every thin-th step
     int until_row = M.thin;
+    MapFind mf;
+    mf.init();
     for (long long i = 1; i < M.n_steps; ++i) {
-        double z[KT], delta[KT], prop[KT], u;
+        double z[KT], delta[KT], prop[KT], u, um;
         const unsigned long long step = (unsigned long long)(M.first_step + i);
-        draws_thread<KT>(M, gchain, step, z, u);
+        draws_thread<KT>(M, gchain, step, z, u, um);
         make_delta<KT>(M, z, delta);
+        const double mod = um + 0.5;                              // IP.py:2633
+        if (M.map_finding) {
+            const double sc = mf.scale(mod);
+#pragma unroll
+            for (int d = 0; d < KT; ++d) delta[d] = sc * delta[d];
+        }
 #pragma unroll
         for (int d = 0; d < KT; ++d) prop[d] = th[d] + delta[d];  // IP.py:2630
         const double lp_p = eval_prior<KT>(P, prop);
@@ -193,7 +228,11 @@ __global__ void __launch_bounds__(128) k_mh(const __grid_constant__ DevProblem P
 #pragma unroll
             for (int d = 0; d < KT; ++d) if (d < k) out.deltas[((i - 1) * C + c) * k + d] = delta[d];
         }
-        if (out.us) out.us[(i - 1) * C + c] = u;
+        if (out.us) {
+            if (M.map_finding) { out.us[((i - 1) * C + c) * 2] = u; out.us[((i - 1) * C + c) * 2 + 1] = mod; }
+            else out.us[(i - 1) * C + c] = u;
+        }
+        if (M.map_finding) mf.after_step(i, mod, sum_p);
         if (--until_row == 0) {
             until_row = M.thin;
             const long long row = next_row++;
@@ -208,6 +247,7 @@ __global__ void __launch_bounds__(128) k_mh(const __grid_constant__ DevProblem P
         if (i >= M.burn_in) st.add_row(k, i, th, th0, cur_sum, cur_exp);
     }
     st.store(k, out.stats + c * PEUQSE_MH_STAT_DOUBLES(k), th, cur_sum);
+    out.stats[c * PEUQSE_MH_STAT_DOUBLES(k) + PEUQSE_MH_STAT_DYN(k)] = mf.dyn;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -232,7 +272,7 @@ struct MhwLayout {
 };
 
 // the draws of one lane for four steps of its chain (lane = 8 * step offset + block): a pair of normals (blocks 0..6) or the
-// accept uniform and its logarithm (block 7).  Not inlined: the large-argument paths of sincos and log would otherwise set
+// accept uniform and the modulation uniform of 'MAP_finding' (block 7).  Not inlined: the large-argument paths of sincos and log would otherwise set
 // the register budget of the whole kernel although they run once every four steps.
 __device__ __noinline__ double2 mhw_draw(unsigned long long seed, unsigned long long gchain, unsigned long long step, int blk, int k) {
     const Philox4 r = philox_block(seed, PQ_STREAM_MH, gchain, (uint32_t)(8ULL * step + (unsigned)blk));
@@ -240,11 +280,12 @@ __device__ __noinline__ double2 mhw_draw(unsigned long long seed, unsigned long 
     if (blk < 7) {
         if (2 * blk < k) philox_normal_pair(r, a, b2);
     } else {
-        a = philox_u53(r.x, r.y);
-        b2 = log(a);
+        a = philox_u53(r.x, r.y);                                  // accept uniform
+        b2 = philox_u53(r.z, r.w);                                 // 'MAP_finding' modulation uniform
     }
     return make_double2(a, b2);
 }
+__device__ __noinline__ double mhw_log(double x) { return log(x); }
 __device__ __noinline__ double mhw_exp(double x) { return exp(x); }
 template <int KT>
 __device__ __noinline__ double mhw_prior(const DevProblem& P, const double (&th)[KT]) { return eval_prior<KT>(P, th); }
@@ -407,6 +448,8 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_mh_warp(const __grid_constant
     double cur_exp = exp(cur_sum);
     long long next_row = 1;
     int until_row = M.thin;
+    MapFind mf;
+    mf.init();
     const int sub = lane >> 3, blk = lane & 7;
     for (long long i = 1; i < M.n_steps; ++i) {
         const int g = (int)((i - 1) & 3);
@@ -424,8 +467,14 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_mh_warp(const __grid_constant
             z[2 * j] = zz.x;
             if (2 * j + 1 < KT) z[2 * j + 1] = zz.y;
         }
-        const double2 uu = dr[g * 8 + 7];                         // (u, log u)
+        const double2 uu = dr[g * 8 + 7];                         // (accept uniform, modulation uniform)
         make_delta<KT>(M, z, delta);
+        const double mod = uu.y + 0.5;                            // IP.py:2633
+        if (M.map_finding) {
+            const double sc = mf.scale(mod);
+#pragma unroll
+            for (int d = 0; d < KT; ++d) delta[d] = sc * delta[d];
+        }
 #pragma unroll
         for (int d = 0; d < KT; ++d) prop[d] = th[d] + delta[d];  // IP.py:2630
         const double lp_p = FAST ? mhw_prior<KT>(P, prop) : eval_prior<KT>(P, prop);
@@ -433,7 +482,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_mh_warp(const __grid_constant
         const double sum_p = ll_p + lp_p;
         double la = sum_p - cur_sum;                              // IP.py:2641
         if (M.modulate != 0.0) la = (1.0 / M.modulate) * la;      // IP.py:2649
-        const bool accept = la > uu.y;                            // IP.py:2651-2652; NaN -> reject
+        const bool accept = la > mhw_log(uu.x);                   // IP.py:2651-2652; NaN -> reject
         if (accept) {                                             // the same in every lane
 #pragma unroll
             for (int d = 0; d < KT; ++d) th[d] = prop[d];
@@ -459,8 +508,12 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_mh_warp(const __grid_constant
 #pragma unroll
                 for (int d = 0; d < KT; ++d) if (d < k) out.deltas[((i - 1) * C + c) * k + d] = delta[d];
             }
-            if (out.us) out.us[(i - 1) * C + c] = uu.x;
+            if (out.us) {
+                if (M.map_finding) { out.us[((i - 1) * C + c) * 2] = uu.x; out.us[((i - 1) * C + c) * 2 + 1] = mod; }
+                else out.us[(i - 1) * C + c] = uu.x;
+            }
         }
+        if (M.map_finding) mf.after_step(i, mod, sum_p);
         if (--until_row == 0) {
             until_row = M.thin;
             const long long row = next_row++;
@@ -483,6 +536,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_mh_warp(const __grid_constant
         so[PEUQSE_MH_STAT_MAPROW] = maprow;
         so[PEUQSE_MH_STAT_LASTLOGP] = cur_sum;
         so[PEUQSE_MH_STAT_SUMEXP] = sumexp;
+        so[PEUQSE_MH_STAT_DYN(k)] = mf.dyn;
     }
     if (lane < k) {
         so[PEUQSE_MH_STAT_MAPTHETA + lane] = mapth;
@@ -602,7 +656,7 @@ static int mh_run_impl(const peuqse_problem* p, const peuqse_mh_spec* s, const D
     if (p->d.any_full) return pq_set_error(PEUQSE_ERR_INVALID, "mh does not support full-covariance responses");
     DevMH M;
     M.n_chains = s->n_chains; M.n_steps = s->n_steps; M.burn_in = s->burn_in; M.first_step = s->first_step;
-    M.chain_offset = s->chain_offset; M.seed = s->seed; M.modulate = s->modulate; M.k = s->k; M.thin = s->thin; M.pad = 0;
+    M.chain_offset = s->chain_offset; M.seed = s->seed; M.modulate = s->modulate; M.k = s->k; M.thin = s->thin; M.map_finding = s->map_finding ? 1 : 0;
     M.chol_diag = 1;
     for (int i = 0; i < PQ_MAXK * PQ_MAXK; ++i) M.chol[i] = 0.0;
     for (int d = 0; d < s->k; ++d)

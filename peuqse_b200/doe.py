@@ -62,7 +62,8 @@ class ScenarioBatch:
         self.pe.gpu_launches += 1
         return tuple(outs) if return_parts else outs[0]
 
-    def run_mh(self, theta0, n_steps, burn_in, seed, step_chol, chains_per_scenario=1, modulate=0.0, export_draws=False):
+    def run_mh(self, theta0, n_steps, burn_in, seed, step_chol, chains_per_scenario=1, modulate=0.0, export_draws=False,
+               map_finding=False):
         """One launch of peuqse_mh_run_scenarios: S x chains_per_scenario chains.  Returns a dict of device tensors
         (samples[R, S*cps, k], logp / logprior / loglik [R, S*cps], stats)."""
         pe = self.pe
@@ -76,6 +77,7 @@ class ScenarioBatch:
         spec = _lib.MHSpec()
         spec.n_chains, spec.n_steps, spec.burn_in, spec.first_step = Cn, int(n_steps), int(burn_in), 0
         spec.chain_offset, spec.seed, spec.modulate, spec.k, spec.thin = 0, int(seed) & (2 ** 64 - 1), float(modulate), pe.k, 1
+        spec.map_finding = 1 if map_finding else 0
         for i, v in enumerate(np.asarray(step_chol, dtype=float).reshape(-1)):
             spec.step_chol[i] = float(v)
         dev = _dev()
@@ -85,7 +87,8 @@ class ScenarioBatch:
                    logprior=torch.empty((R, Cn), dtype=torch.float64, device=dev),
                    loglik=torch.empty((R, Cn), dtype=torch.float64, device=dev),
                    deltas=torch.empty((max(R - 1, 0), Cn, pe.k), dtype=torch.float64, device=dev) if export_draws else None,
-                   us=torch.empty((max(R - 1, 0), Cn), dtype=torch.float64, device=dev) if export_draws else None,
+                   us=torch.empty((max(R - 1, 0), Cn, 2) if map_finding else (max(R - 1, 0), Cn), dtype=torch.float64,
+                                  device=dev) if export_draws else None,
                    stats=torch.empty((Cn, _lib.mh_stat_layout(pe.k)['SIZE']), dtype=torch.float64, device=dev))
         _lib.check(self._L.peuqse_mh_run_scenarios(pe.device_problem.handle, self.handle, C.byref(spec), cps, _lib.ptr(th0),
                                                    _lib.ptr(out['samples']), _lib.ptr(out['logp']), _lib.ptr(out['logprior']),
@@ -186,8 +189,6 @@ def run_info_gain_matrices(pe, modulations, searchType='doMetropolisHastings'):
     pes, doe = UI.parameter_estimation_settings, UI.doe_settings
     if searchType != 'doMetropolisHastings':
         raise NotImplementedError(f"design of experiments with searchType '{searchType}': only doMetropolisHastings is batched")
-    if pes['mcmc_mode'] != 'unbiased':
-        raise NotImplementedError("mcmc_mode 'MAP_finding' is outside the accelerated path")
     pes['mcmc_continueSampling'] = False                                                               # IP.py:1367
     modulations = np.asarray(modulations, dtype=float).reshape(-1, pe.k)
     conds = conditions_grid(pe, doe)
@@ -214,7 +215,7 @@ def run_info_gain_matrices(pe, modulations, searchType='doMetropolisHastings'):
     if sn:
         batch = ScenarioBatch(pe, all_conds[s0:s0 + sn], all_true[s0:s0 + sn])
         run = batch.run_mh(np.asarray(UI.InputParameterInitialGuess, dtype=float), Lm, burn, seed, chol, chains_per_scenario=cps,
-                           modulate=float(pes['mcmc_modulate_accept_probability']))
+                           modulate=float(pes['mcmc_modulate_accept_probability']), map_finding=pes['mcmc_mode'] == 'MAP_finding')
         stats_rows = batch.statistics(run, burn, mode, coef)
         if not want_kl:
             gains = stats_rows[:, _lib.scen_stats_layout(pe.k)['INFO_GAIN_LOG_RATIO']].copy()

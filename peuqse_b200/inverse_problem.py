@@ -37,9 +37,12 @@ class parameter_estimation:
                              ('multistart_store_logP', 'auto'), ('multistart_random_seed', None), ('multistart_shard_pieces', 'auto'),
                              ('multistart_histogram_bins', 10)):
             pes.setdefault(key, default)
-        if UI.model.get('custom_logLikelihood') is not None or UI.model.get('custom_logPrior') is not None:
-            raise NotImplementedError("custom_logLikelihood / custom_logPrior are Python callbacks per point; "
-                                      "not part of the accelerated path")
+        # custom_logPrior(theta) -> logPrior and custom_logLikelihood(theta) -> (logLikelihood, simulatedResponses) replace the
+        # built-in prior (bounds check included) / simulation + likelihood (IP.py:2757-2759, 2854-2857).  Here they are VECTORISED
+        # torch callables over a block of points: custom_logPrior(theta[B,k]) -> [B], custom_logLikelihood(theta[B,k]) ->
+        # ([B], sim[B,n] or None), evaluated on the batched paths (getLogP*, multistart, ensemble slice sampling, optimisers).
+        self.custom_logLikelihood = UI.model.get('custom_logLikelihood')
+        self.custom_logPrior = UI.model.get('custom_logPrior')
         if len(UI.model.get('reducedParameterSpace', [])) or len(UI.responses.get('reducedResponseSpace', [])):
             raise NotImplementedError("reduced parameter/response spaces are out of scope (DESIGN.md)")
         if UI.responses.get('data_overcategory', '') != '':
@@ -133,6 +136,8 @@ class parameter_estimation:
         UI.InputParameterInitialGuess = np.array(guess, dtype='float').reshape(-1)
 
         sim = UI.model['simulateByInputParametersOnlyFunction']
+        if sim is None and self.custom_logLikelihood is not None:
+            sim = TorchSimulator(None)         # never called: the custom likelihood does its own simulation
         if sim is None:
             raise ValueError("UserInput.model['simulateByInputParametersOnlyFunction'] must be provided")
         if UI.model.get('simulationOutputProcessingFunction') is not None and isinstance(sim, BuiltinModel):
@@ -188,6 +193,8 @@ class parameter_estimation:
         if B == 0:
             e = torch.empty(0, dtype=torch.float64, device=th.device)
             return (e, e.clone(), e.clone()) if return_parts else e
+        if self.custom_logLikelihood is not None or self.custom_logPrior is not None:
+            return self._getLogP_batch_custom(th, return_parts)
         logp = torch.empty(B, dtype=torch.float64, device=th.device)
         lp = torch.empty(B, dtype=torch.float64, device=th.device) if return_parts else None
         ll = torch.empty(B, dtype=torch.float64, device=th.device) if return_parts else None
@@ -200,6 +207,37 @@ class parameter_estimation:
             _lib.check(self._L.peuqse_logp_from_sim(h, _lib.ptr(th), _lib.ptr(sim), B, _lib.ptr(logp), _lib.ptr(lp),
                                                     _lib.ptr(ll), _lib.current_stream()))
         self.gpu_launches += 1
+        return (logp, lp, ll) if return_parts else logp
+
+    def _getLogP_batch_custom(self, th, return_parts):
+        """getLogP with a user-supplied prior and / or likelihood (vectorised torch callables, see __init__): the part the user
+        did not supply still comes from the kernels; logP = logLikelihood + logPrior, -inf where the prior is -inf (IP.py:1647-1654)."""
+        B = th.shape[0]
+        h = self.device_problem.handle
+        as_vec = lambda v: torch.as_tensor(v, dtype=torch.float64, device=th.device).reshape(B).contiguous()
+        ll = lp = None
+        if self.custom_logLikelihood is not None:
+            out = self.custom_logLikelihood(th)
+            ll_raw, sim = out if isinstance(out, (tuple, list)) else (out, None)
+            ll = as_vec(ll_raw)
+            self._last_custom_sim = sim
+        if self.custom_logPrior is not None:
+            lp = as_vec(self.custom_logPrior(th))
+        if ll is None:                         # built-in likelihood (and the prior, if it is not the user's)
+            ll = torch.empty(B, dtype=torch.float64, device=th.device)
+            lpk = torch.empty(B, dtype=torch.float64, device=th.device) if lp is None else None
+            if isinstance(self.simulator, BuiltinModel):
+                _lib.check(self._L.peuqse_logp_batch(h, _lib.ptr(th), B, None, _lib.ptr(lpk), _lib.ptr(ll), _lib.current_stream()))
+            else:
+                sim = self.simulate_batch(th)
+                _lib.check(self._L.peuqse_logp_from_sim(h, _lib.ptr(th), _lib.ptr(sim), B, None, _lib.ptr(lpk), _lib.ptr(ll),
+                                                        _lib.current_stream()))
+            lp = lpk if lp is None else lp
+        elif lp is None:                       # the user's likelihood with the built-in prior
+            lp = torch.empty(B, dtype=torch.float64, device=th.device)
+            _lib.check(self._L.peuqse_logprior_batch(h, _lib.ptr(th), B, _lib.ptr(lp), _lib.current_stream()))
+        self.gpu_launches += 1
+        logp = torch.where(lp == float('-inf'), lp, ll + lp)
         return (logp, lp, ll) if return_parts else logp
 
     # ------------------------------------------------------------------------------------------
@@ -215,6 +253,10 @@ class parameter_estimation:
         return float(self.getLogP_batch(discreteParameterVector, return_parts=True)[1][0].item())
 
     def getSimulatedResponses(self, discreteParameterVector):              # IP.py:2822
+        if self.custom_logLikelihood is not None:                           # IP.py:2855-2857: the callable returns them
+            out = self.custom_logLikelihood(self._as_theta(discreteParameterVector))
+            sim = out[1] if isinstance(out, (tuple, list)) else None
+            return None if sim is None else np.asarray(torch.as_tensor(sim).cpu()).reshape(-1)
         sim = self.simulate_batch(discreteParameterVector)[0].cpu().numpy()
         out, off = [], 0
         for r in self.host_problem.responses_observed:
@@ -358,8 +400,10 @@ class parameter_estimation:
                                              centerPoint=centerPoint)
             return self.doListOfPermutationsSearch(pts, searchType='getLogP', permutationsToSamples=toSamples,
                                                    calculatePostBurnInStatistics=calculatePostBurnInStatistics, centerPoint=centerPoint)
-        if not isinstance(self.simulator, BuiltinModel) or self.host_problem.resp_mode.max() == _lib.RESP_MVN_FULL:
-            # torch-callable simulators / full covariance: decode points in chunks and use the batched path
+        custom = self.custom_logLikelihood is not None or self.custom_logPrior is not None
+        if custom or not isinstance(self.simulator, BuiltinModel) or self.host_problem.resp_mode.max() == _lib.RESP_MVN_FULL:
+            # torch-callable simulators / full covariance / user-supplied prior or likelihood: decode points in chunks and
+            # use the batched path
             return self._multistart_external(spec, n, toSamples and calculatePostBurnInStatistics, coef, nbins, centerPoint)
         # arrays left by an earlier search of another kind (list of permutations, optimiser or MH multistart, external simulator)
         # must not be mistaken for this sweep's: the properties below then read the sweep's own device buffers
@@ -479,8 +523,6 @@ class parameter_estimation:
         from .sweep import SweepResult
         UI = self.UserInput
         pes = UI.parameter_estimation_settings
-        if pes['mcmc_mode'] != 'unbiased':
-            raise NotImplementedError("mcmc_mode 'MAP_finding' is outside the accelerated path")
         pts = np.asarray(pts, dtype=float).reshape(-1, self.k)
         self._list_of_permutations = pts
         Lm = int(pes['mcmc_length'])
@@ -491,7 +533,7 @@ class parameter_estimation:
         c0, cn = D.shard_range(len(pts), rank, size)
         from .mcmc import step_cholesky as _chol
         out = mh_launch(self, pts[c0:c0 + cn], Lm, burn, seed, _chol(self.Q_covmat, pes['mcmc_relative_step_length']), chain_offset=c0,
-                        modulate=float(pes['mcmc_modulate_accept_probability']))
+                        modulate=float(pes['mcmc_modulate_accept_probability']), map_finding=pes['mcmc_mode'] == 'MAP_finding')
         lay = _lib.mh_stat_layout(self.k)
         st = out['stats']
         rows = torch.cat([st[:, lay['MAPLOGP']:lay['MAPLOGP'] + 1], st[:, lay['MAPTHETA']:lay['MAPTHETA'] + self.k]], dim=1)

@@ -26,7 +26,7 @@ def step_cholesky(Q_covmat, step):
 
 
 def mh_launch(pe, theta0, n_steps, burn_in, seed, step_chol, first_step=0, chain_offset=0, modulate=0.0, thin=1,
-              store_samples=True, store_parts=True, export_draws=False):
+              store_samples=True, store_parts=True, export_draws=False, map_finding=False):
     """One call of peuqse_mh_run for C chains starting at theta0[C,k].  Returns a dict of device tensors."""
     L = _lib.load()
     dev = _dev()
@@ -35,6 +35,7 @@ def mh_launch(pe, theta0, n_steps, burn_in, seed, step_chol, first_step=0, chain
     spec = _lib.MHSpec()
     spec.n_chains, spec.n_steps, spec.burn_in, spec.first_step = Cn, int(n_steps), int(burn_in), int(first_step)
     spec.chain_offset, spec.seed, spec.modulate, spec.k, spec.thin = int(chain_offset), int(seed) & (2 ** 64 - 1), float(modulate), k, int(thin)
+    spec.map_finding = 1 if map_finding else 0
     flat = np.asarray(step_chol, dtype=float).reshape(-1)
     for i, v in enumerate(flat):
         spec.step_chol[i] = float(v)
@@ -46,7 +47,9 @@ def mh_launch(pe, theta0, n_steps, burn_in, seed, step_chol, first_step=0, chain
     out['logprior'] = torch.empty((R, Cn), dtype=torch.float64, device=dev) if (store_samples and store_parts) else None
     out['loglik'] = torch.empty((R, Cn), dtype=torch.float64, device=dev) if (store_samples and store_parts) else None
     out['deltas'] = torch.empty((max(n_steps - 1, 0), Cn, k), dtype=torch.float64, device=dev) if export_draws else None
-    out['us'] = torch.empty((max(n_steps - 1, 0), Cn), dtype=torch.float64, device=dev) if export_draws else None
+    # accept uniforms; with map_finding (accept uniform, modulation uniform + 0.5) per step
+    us_shape = (max(n_steps - 1, 0), Cn, 2) if map_finding else (max(n_steps - 1, 0), Cn)
+    out['us'] = torch.empty(us_shape, dtype=torch.float64, device=dev) if export_draws else None
     out['stats'] = torch.empty((Cn, lay['SIZE']), dtype=torch.float64, device=dev)
     _lib.check(L.peuqse_mh_run(pe.device_problem.handle, C.byref(spec), _lib.ptr(th0), _lib.ptr(out['samples']),
                                _lib.ptr(out['logp']), _lib.ptr(out['logprior']), _lib.ptr(out['loglik']),
@@ -97,8 +100,12 @@ def run_metropolis_hastings(pe, calculatePostBurnInStatistics=True, continueSamp
     pes = UI.parameter_estimation_settings
     if hasattr(UI, 'last_MCMC_run_type') and UI.last_MCMC_run_type != 'MH':                       # IP.py:2565-2569
         print("ERROR: Two different algorithms of MCMC runs were attempted with the same UserInput."); raise SystemExit
-    if pes['mcmc_mode'] != 'unbiased':
-        raise NotImplementedError("mcmc_mode 'MAP_finding' (polyfit-driven step adaptation, IP.py:2631-2713) is outside the accelerated path")
+    if getattr(pe, 'custom_logLikelihood', None) is not None or getattr(pe, 'custom_logPrior', None) is not None:
+        raise NotImplementedError("doMetropolisHastings runs as one persistent kernel and cannot call custom_logLikelihood / "
+                                  "custom_logPrior; use doEnsembleSliceSampling or doMultiStart (batched paths) with them")
+    if pes['mcmc_mode'] not in ('unbiased', 'MAP_finding'):
+        raise ValueError("mcmc_mode must be 'unbiased' or 'MAP_finding' (IP.py:2629-2631)")
+    map_finding = pes['mcmc_mode'] == 'MAP_finding'                                                  # IP.py:2631-2635, 2688-2713
     if continueSampling == 'auto':                                                                   # IP.py:2572-2578
         if ('mcmc_continueSampling' not in pes) or pes['mcmc_continueSampling'] == 'auto':
             continueSampling = hasattr(pe, 'mcmc_last_point_sampled')
@@ -145,7 +152,8 @@ def run_metropolis_hastings(pe, calculatePostBurnInStatistics=True, continueSamp
     if store == 'auto':
         store = (Lm // thin) * cn * (pe.k + 3) * 8 <= 64 * 2 ** 30
     out = mh_launch(pe, start[c0:c0 + cn], Lm, burn, seed, chol, first_step=first_step, chain_offset=c0,
-                    modulate=float(pes['mcmc_modulate_accept_probability']), thin=thin, store_samples=bool(store))
+                    modulate=float(pes['mcmc_modulate_accept_probability']), thin=thin, store_samples=bool(store),
+                    map_finding=map_finding)
     pe._mh_steps_done = first_step + Lm
     pe._mh_out = out
     UI.last_MCMC_run_type = 'MH'                                                                     # IP.py:2729
@@ -303,7 +311,8 @@ def ess_launch(pe, start, n_iters, seed, mu0=1.0, tune=True, max_rounds=10000, f
     dev = _dev()
     X = torch.as_tensor(np.asarray(start, dtype=float), dtype=torch.float64).reshape(-1, pe.k).to(dev).contiguous()
     W, k = X.shape
-    builtin = isinstance(pe.simulator, BuiltinModel)
+    custom = getattr(pe, 'custom_logLikelihood', None) is not None or getattr(pe, 'custom_logPrior', None) is not None
+    builtin = isinstance(pe.simulator, BuiltinModel) and not custom      # user callables: the rounds are issued from Python
     full = int(pe.host_problem.resp_mode.max()) == _lib.RESP_MVN_FULL
     sharded = bool(shard) and D.world()[1] > 1 and (full or not builtin)
     if not builtin or sharded:

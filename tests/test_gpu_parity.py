@@ -1336,3 +1336,99 @@ def test_c5_window_above_two_to_the_33(env):
         s2.step(float(np.log(10 ** -2.0)), True)
         R2 = s2.unpack(s2.res.cpu().numpy(), 2.0)
         assert (R2.map_index, R2.map_logP, R2.sum_weights) == (R.map_index, R.map_logP, R.sum_weights)
+
+
+@pytest.mark.gpu
+def test_mh_map_finding_vs_reference_fixture_and_oracle(env, golden):
+    """mcmc_mode 'MAP_finding' (IP.py:2631-2635, 2688-2713) inside the Metropolis-Hastings kernels.  (i) The kernel's draws are the
+    fixture's (the unmodified reference ran on them): same modulations and accept uniforms bit for bit, increments to 1e-12.  (ii) The
+    oracle replays the kernel's own exported draws: chain, log-posteriors and the final step coefficient identical, and every
+    exported increment is sqrt(dyn * mod) times the increment of the unbiased mode with the oracle's dyn.  (iii) Both kernel shapes
+    (thread per chain, warp per chain) agree; the reference-named API returns the chain."""
+    PEUQSE, orc, philox_np, torch = env
+    from peuqse_b200 import _lib
+    from peuqse_b200.mcmc import mh_launch, step_cholesky
+    g = golden("mapfinding")
+    L, seed, step = int(g['L']), int(g['seed']), float(g['step'])
+    PE = make_pe(PEUQSE, PEUQSE.QuadraticModel(X00), Y00, S00, [200, 500], [100, 200],
+                 settings={'mcmc_length': L, 'mcmc_burn_in': 100, 'mcmc_relative_step_length': step, 'mcmc_random_seed': seed,
+                           'mcmc_mode': 'MAP_finding', 'mcmc_threshold_filter_samples': False, 'mcmc_info_gain_returned': 'log_ratio'})
+    chol = step_cholesky(PE.Q_covmat, step)
+    out = mh_launch(PE, [[200., 500.]], L, 100, seed, chol, export_draws=True, map_finding=True)
+    plain = mh_launch(PE, [[200., 500.]], L, 100, seed, chol, export_draws=True)
+    us, mods = out['us'].cpu().numpy()[:, 0, 0], out['us'].cpu().numpy()[:, 0, 1]
+    deltas, base = out['deltas'].cpu().numpy()[:, 0], plain['deltas'].cpu().numpy()[:, 0]
+    assert np.array_equal(us, g['us']) and np.array_equal(mods, g['mods']) and np.array_equal(us, plain['us'].cpu().numpy()[:, 0])
+    np.testing.assert_allclose(base, g['base_deltas'], rtol=1e-13, atol=1e-11)
+    P = orc.build_problem([200, 500], [100, 200], Y00, S00)
+    _, bt = orc.sim_quadratic(X00)
+    ref = orc.mh_chain_map_finding(P, [200.0, 500.0], deltas, mods, us, bt, scaled=True)
+    assert np.array_equal(out['samples'].cpu().numpy()[:, 0], ref['samples'])
+    assert np.array_equal(out['logp'].cpu().numpy()[:, 0], ref['logP'])
+    lay = _lib.mh_stat_layout(2)
+    assert float(out['stats'][0, lay['DYN']].item()) == ref['dyn_final'] and float(plain['stats'][0, lay['DYN']].item()) == 1.0
+    assert len(np.unique(ref['dyn'])) > 5
+    assert np.array_equal(deltas, np.sqrt(ref['dyn'][1:] * mods)[:, None] * base)
+    if np.array_equal(base, g['base_deltas']):                        # identical draws: the reference's own chain
+        assert np.array_equal(ref['samples'], g['samples']) and ref['dyn_final'] == float(g['dyn_final'])
+    # warp-per-chain shape (<= 8192 chains of a small problem) against thread-per-chain (more chains): same chains
+    th0 = np.array([200.0, 500.0]) + np.random.default_rng(4).standard_normal((8200, 2)) * [30.0, 60.0]
+    few = mh_launch(PE, th0[:64], 450, 50, 9, chol, store_samples=False, map_finding=True)
+    many = mh_launch(PE, th0, 450, 50, 9, chol, store_samples=False, map_finding=True)
+    assert torch.equal(few['stats'], many['stats'][:64])
+    assert len(torch.unique(many['stats'][:, lay['DYN']])) > 3
+    res = PE.doMetropolisHastings()
+    assert np.array_equal(PE.post_burn_in_samples, out['samples'].cpu().numpy()[100:, 0]) and len(res) == 7
+
+
+@pytest.mark.gpu
+def test_custom_log_prior_and_log_likelihood(env):
+    """UserInput.model['custom_logPrior'] / ['custom_logLikelihood'] (IP.py:2757-2759, 2854-2857) as vectorised torch callables: a
+    custom prior / likelihood that restates the built-in one must give the built-in log-posterior; the drivers that evaluate in
+    batches (multistart, ensemble slice sampling) run on them; the persistent Metropolis-Hastings kernel refuses."""
+    PEUQSE, orc, _, torch = env
+    rng = np.random.default_rng(3)
+    k, n, sig = 3, 20, 0.3
+    Phi = orc.cos_basis(n, k)
+    y = Phi @ rng.standard_normal(k) + sig * rng.standard_normal(n)
+    PhiT, yt = torch.from_numpy(Phi.T.copy()).cuda(), torch.from_numpy(y).cuda()
+    LOG2PI = float(np.log(2 * np.pi))
+
+    def my_prior(th):                                                  # N(0, 2^2) in the reference's scaled form (SURVEY Q1)
+        z = th / 2.0
+        return -0.5 * (k * LOG2PI + (z * z).sum(dim=1))
+
+    def my_lik(th):
+        sim = th @ PhiT
+        r = (yt - sim) / sig
+        return -0.5 * (n * LOG2PI + n * float(np.log(sig ** 2)) + (r * r).sum(dim=1)), sim
+    base = make_pe(PEUQSE, PEUQSE.LinearModel(Phi), list(y), list(np.full(n, sig)), [0.0] * k, [2.0] * k)
+    th = rng.standard_normal((500, k))
+    want = parts(base, th)
+    for kw in (dict(custom_logPrior=my_prior), dict(custom_logLikelihood=my_lik), dict(custom_logPrior=my_prior, custom_logLikelihood=my_lik)):
+        model = None if 'custom_logLikelihood' in kw else PEUQSE.LinearModel(Phi)
+        PE = make_pe(PEUQSE, model, list(y), list(np.full(n, sig)), [0.0] * k, [2.0] * k,
+                     settings={'mcmc_length': 16 * 40, 'mcmc_nwalkers': 16, 'mcmc_burn_in': 16 * 5, 'mcmc_random_seed': 2,
+                               'mcmc_threshold_filter_samples': False, 'multistart_initialPointsDistributionType': 'uniform',
+                               'multistart_numStartPoints': 5000, 'multistart_random_seed': 1, 'exportLog': False}, **kw)
+        got = parts(PE, th)
+        for a, b in zip(got, want):
+            np.testing.assert_allclose(a, b, rtol=1e-12)
+        assert abs(PE.getLogP(th[0]) - want[0][0]) <= 1e-12 * abs(want[0][0])
+        ll, sim = PE.getLogLikelihood(th[0])
+        assert abs(ll - want[2][0]) <= 1e-12 * abs(want[2][0])
+        if 'custom_logLikelihood' in kw:
+            np.testing.assert_allclose(sim, Phi @ th[0], rtol=1e-12)
+        PE.doMultiStart()
+        base.UserInput.parameter_estimation_settings.update({'multistart_initialPointsDistributionType': 'uniform',
+                                                             'multistart_numStartPoints': 5000, 'multistart_random_seed': 1, 'exportLog': False})
+        base.doMultiStart()
+        assert np.array_equal(PE.map_parameter_set, base.map_parameter_set) and abs(PE.map_logP - base.map_logP) < 1e-9
+        PE.doEnsembleSliceSampling()
+        assert PE.post_burn_in_samples.shape == (16 * 35, k) and np.all(np.isfinite(PE.post_burn_in_log_posteriors_un_normed_vec))
+        with pytest.raises(NotImplementedError):
+            PE.doMetropolisHastings()
+    # a custom prior replaces the bounds check too (IP.py:2757-2759 returns before doInputParameterBoundsChecks)
+    PEb = make_pe(PEUQSE, PEUQSE.LinearModel(Phi), list(y), list(np.full(n, sig)), [0.0] * k, [2.0] * k, custom_logPrior=my_prior,
+                  InputParameterPriorValues_lowerBounds=[-0.1] * k, InputParameterPriorValues_upperBounds=[0.1] * k)
+    assert np.isfinite(PEb.getLogP([1.0, 1.0, 1.0]))

@@ -34,7 +34,7 @@ def test_ctypes_struct_layouts_match_header_sizes():
     # sizes implied by the header (LP64): checked so that a field added on one side only is caught
     assert ctypes.sizeof(_lib.Best) == 16
     assert ctypes.sizeof(_lib.SweepSpec) == 8 + 16 * 8 * 3 + 8 + 16 * 8 + 8
-    assert ctypes.sizeof(_lib.MHSpec) == 7 * 8 + 8 + 256 * 8
+    assert ctypes.sizeof(_lib.MHSpec) == 7 * 8 + 8 + 256 * 8 + 8
     assert ctypes.sizeof(_lib.ESSSpec) == 5 * 8 + 4 * 4
     assert ctypes.sizeof(_lib.ProblemDesc) == 16 + 32 + 8 + 24 + 8 + 8 + 24 + 32 + 8 + 8 + 8
 

@@ -398,3 +398,20 @@ def test_info_gain_cutoff_vs_reference(golden):
                                                   bool(filt), info_gain_cutoff=cutoff)
         assert len(st['samples']) == int(n_kept) and st['evidence'] == evidence
         assert np.array_equal(st['info_gain_log_ratio'], info_gain, equal_nan=True), key
+
+
+def test_map_finding_restatement_vs_reference(golden):
+    """mcmc_mode 'MAP_finding' (IP.py:2631-2635, 2688-2713): the oracle fed the fixture's draws reproduces the unmodified
+    reference's chain, log-posteriors and step-coefficient history (the reference's own coefficient is recovered from the
+    covariance it handed to np.random.multivariate_normal) bit for bit."""
+    g = golden("mapfinding")
+    P = orc.build_problem([200, 500], [100, 200], Y00, S00)
+    _, bt = orc.sim_quadratic(X00)
+    for scaled, deltas in ((False, g['base_deltas']), (True, g['scaled_deltas'])):
+        out = orc.mh_chain_map_finding(P, [200.0, 500.0], deltas, g['mods'], g['us'], bt, scaled=scaled)
+        assert np.array_equal(out['samples'], g['samples']) and np.array_equal(out['logP'], g['logP'])
+        assert np.array_equal(out['dyn'], g['dyn']) and out['dyn_final'] == float(g['dyn_final'])
+    step = float(g['step'])
+    want = np.array([((100.0 ** 2 * g['dyn'][i + 1]) * g['mods'][i]) * step for i in range(len(g['mods']))])
+    assert np.array_equal(g['ref_cov00'], want)
+    assert len(np.unique(g['dyn'])) > 5
