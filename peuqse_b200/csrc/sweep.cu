@@ -4,6 +4,7 @@
 // CombinationGeneratorModule.combinationGenerator (CombinationGeneratorModule.py:40-81),
 // convertPermutationsToSamples (IP.py:3463-3491) and the moment part of calculatePostBurnInStatistics
 // (IP.py:1923-1931).
+#include <cstdlib>
 #include "common.cuh"
 #include "eval.cuh"
 #include "launch.cuh"
@@ -48,6 +49,132 @@ __device__ __forceinline__ void short_push(ShortHdr* sh, long long* c_idx, doubl
 }
 __device__ __forceinline__ bool short_usable(const ShortHdr* sh, int margin_ok) {
     return sh && margin_ok && sh->valid == 1u && sh->count <= (unsigned long long)PQ_SHORT_CAP;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass 1 of a sweep whose logP is NOT kept (config C5: 1e10 uniform points), linear model, one diagonal-covariance
+// response of 8 NF observations: the simulation Theta[32 points, k] Phi^T[k, n] of a warp's 32 points runs on the fp64
+// TENSOR pipe (mma.sync.m8n8k4.f64, 4 row fragments x NF column fragments x ceil(k/4) steps), which works beside the fp64
+// pipe that keeps the point generation (Philox -> theta), the prior and the residual / square / sum of the likelihood:
+// the scalar kernel below spends 2 k n of its ~1.6 k fp64 instructions per point on that product.  Per lane: its own point's
+// theta and prior; the B fragments of Phi^T and {y w, w} live in shared memory, the warp's thetas pass through a shared-memory
+// tile to become A fragments; a lane ends up with 2 NF simulated values of each of 4 points, squares and sums its residuals,
+// the 4 lanes of a point combine, the point's owner picks the sum up.  Summation order differs from the scalar kernel's
+// (the reference's): values agree to ~1e-13 relative, inside the 1e-12 budget -- which is why only the no-store sweep, whose
+// per-point values never reach the caller, takes this path; sweeps that return logP keep the bit-exact scalar order.
+// ---------------------------------------------------------------------------------------------
+#define P1D_THREADS 128
+template <int KT, int NF>
+__global__ void __launch_bounds__(P1D_THREADS, 4) k_sweep_pass1_lin_dmma(const __grid_constant__ DevProblem P,
+                                                                         const __grid_constant__ DevSweep S, long long first,
+                                                                         long long count, peuqse_best* __restrict__ best_out,
+                                                                         Best* __restrict__ partial, unsigned int* __restrict__ ticket,
+                                                                         ShortHdr* __restrict__ sh, long long* __restrict__ c_idx,
+                                                                         double* __restrict__ c_logp) {
+    constexpr int KS = (KT + 3) / 4, KP = KS * 4, NW = P1D_THREADS / 32;
+    __shared__ double s_bf[KS][NF][32];                 // B fragments: lane l of (s, f) holds Phi[8 f + l/4][4 s + l%4]
+    __shared__ double2 s_yw[NF * 8];                    // {y w, w} per observation
+    __shared__ double s_th[NW][32][KP];                 // the warp's 32 points, zero padded to 4 KS parameters
+    __shared__ Best s_best[NW];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int k = P.k;
+    for (int idx = threadIdx.x; idx < KS * NF * 32; idx += blockDim.x) {
+        const int l = idx & 31, f = (idx >> 5) % NF, sstep = idx / (32 * NF);
+        const int j = 8 * f + (l >> 2), kk = 4 * sstep + (l & 3);
+        s_bf[sstep][f][l] = (kk < k) ? P.mconst[(size_t)j * k + kk] : 0.0;
+    }
+    for (int j = threadIdx.x; j < NF * 8; j += blockDim.x) s_yw[j] = make_double2(P.y[j] * P.w[j], P.w[j]);
+    __syncthreads();
+    Best best = best_none();
+    const long long wstride = (long long)gridDim.x * NW * 32;
+    for (long long base = ((long long)blockIdx.x * NW + warp) * 32; base < count; base += wstride) {
+        const long long i = base + lane;
+        const bool valid = i < count;
+        const long long g = first + (valid ? i : base);
+        double gm = pq_neg_inf();                               // best logP published so far (shortlist mode)
+        if (sh) {
+            const unsigned long long key = *(volatile unsigned long long*)&sh->gmax_key;
+            if (key) gm = short_key_to_double(key);
+        }
+        double th[KT];
+        sweep_point<KT>(S, (unsigned long long)g, th);
+        const double lp = eval_prior<KT>(P, th);
+#pragma unroll
+        for (int d = 0; d < KP; ++d) s_th[warp][lane][d] = (d < KT) ? th[d < KT ? d : 0] : 0.0;
+        __syncwarp();
+        double maha = 0.0;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            double acc[NF][2];
+#pragma unroll
+            for (int f = 0; f < NF; ++f) acc[f][0] = acc[f][1] = 0.0;
+#pragma unroll
+            for (int sstep = 0; sstep < KS; ++sstep) {
+                const double a = s_th[warp][8 * m + (lane >> 2)][4 * sstep + (lane & 3)];
+#pragma unroll
+                for (int f = 0; f < NF; ++f) pq_dmma884(acc[f][0], acc[f][1], a, s_bf[sstep][f][lane]);
+            }
+            double part = 0.0;
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {
+                const double2 q0 = s_yw[8 * f + 2 * (lane & 3)], q1 = s_yw[8 * f + 2 * (lane & 3) + 1];
+                const double t0 = fma(-acc[f][0], q0.y, q0.x), t1 = fma(-acc[f][1], q1.y, q1.x);   // (y - sim) w
+                part = fma(t0, t0, part);
+                part = fma(t1, t1, part);
+            }
+            part += __shfl_xor_sync(0xffffffffu, part, 1);
+            part += __shfl_xor_sync(0xffffffffu, part, 2);      // the 4 lanes of row lane/4 hold the sum of point 8 m + lane/4
+            const double v = __shfl_sync(0xffffffffu, part, 4 * (lane & 7));
+            if ((lane >> 3) == m) maha = v;                     // this lane's own point
+        }
+        __syncwarp();
+        double ll = -0.5 * (P.resp_c[0] + maha);
+        if (ll != ll) ll = pq_neg_inf();                        // IP.py:2880-2882
+        const double va = pq_is_neg_inf(lp) ? lp : (ll + lp);   // IP.py:1649-1653
+        if (valid) {
+            if (va > best.v) { best.v = va; best.i = g; }       // strict '>', increasing g: first maximum
+            if (sh) {
+                if (va > gm - PQ_SHORT_MARGIN) short_push(sh, c_idx, c_logp, g, va);
+                if (va > gm) atomicMax(&sh->gmax_key, short_double_to_key(va));
+            }
+        }
+    }
+    best = warp_best(best);
+    if (lane == 0) s_best[warp] = best;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        Best b = (threadIdx.x < NW) ? s_best[threadIdx.x] : best_none();
+        b = warp_best(b);
+        if (threadIdx.x == 0) {
+            partial[blockIdx.x] = b;
+            __threadfence();
+            const unsigned int t = atomicAdd(ticket, 1u);
+            s_last = (t == gridDim.x - 1);
+        }
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x < 32) {
+        __threadfence();
+        Best b = best_none();
+        for (int j = threadIdx.x; j < (int)gridDim.x; j += 32) {
+            Best o;
+            o.v = __ldcg(&partial[j].v);
+            o.i = __ldcg(&partial[j].i);
+            b = best_merge(b, o);
+        }
+        b = warp_best(b);
+        if (threadIdx.x == 0) {
+            Best cur;
+            cur.v = best_out->logp;
+            cur.i = best_out->index < 0 ? 0x7fffffffffffffffLL : best_out->index;
+            b = best_merge(cur, b);
+            best_out->logp = b.v;
+            best_out->index = (b.i == 0x7fffffffffffffffLL) ? -1 : b.i;
+            *ticket = 0;
+            if (sh) sh->valid = 1u;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -552,6 +679,25 @@ int launch_pass1(const peuqse_problem* p, const DevSweep& S, long long first, lo
     PQ_CUDA_OK(pq_allow_smem((const void*)kern, smem));
     unsigned int* ticket = (unsigned int*)work;
     Best* partial = (Best*)((char*)work + PQ_SWEEP_TICKET_BYTES);
+    if constexpr (MODEL == PEUQSE_MODEL_LINEAR) {
+        // logP not kept + linear model + one diagonal-covariance response of 32 / 64 / 128 observations: tensor-pipe simulation
+        static int off = -1;
+        if (off < 0) { const char* e = getenv("PEUQSE_SWEEP_NO_DMMA"); off = (e && e[0] == '1') ? 1 : 0; }
+        const int n = p->d.n_total;
+        if (!off && !logp && p->d.n_resp == 1 && p->d.resp_mode[0] == PEUQSE_RESP_MVN_DIAG && !p->d.any_per_value &&
+            (n == 32 || n == 64 || n == 128) && KT <= 12) {
+            ShortHdr* shd = (ShortHdr*)((char*)work + PQ_SHORT_HDR_OFFSET);
+            long long* ci = (long long*)((char*)work + PQ_SWEEP_BASE_BYTES);
+            double* cl = (double*)(ci + PQ_SHORT_CAP);
+            const long long wantd = (count + 127) / 128;
+            const int gd = (int)std::max<long long>(1, std::min<long long>(wantd, std::min<long long>((long long)p->sm_count * 4, PQ_SWEEP_MAX_BLOCKS)));
+            if (n == 32) k_sweep_pass1_lin_dmma<KT, 4><<<gd, P1D_THREADS, 0, st>>>(p->d, S, first, count, best, partial, ticket, shd, ci, cl);
+            else if (n == 64) k_sweep_pass1_lin_dmma<KT, 8><<<gd, P1D_THREADS, 0, st>>>(p->d, S, first, count, best, partial, ticket, shd, ci, cl);
+            else k_sweep_pass1_lin_dmma<KT, 16><<<gd, P1D_THREADS, 0, st>>>(p->d, S, first, count, best, partial, ticket, shd, ci, cl);
+            PQ_CUDA_OK(cudaGetLastError());
+            return PEUQSE_OK;
+        }
+    }
     // 128-thread CTAs, three per SM (168 registers for the two points a thread carries); 12 CTAs queued per SM
     const long long want = (count + 2 * P1_THREADS - 1) / (2 * P1_THREADS);
     const int grid = (int)std::max<long long>(1, std::min<long long>(want, std::min<long long>((long long)p->sm_count * 12, PQ_SWEEP_MAX_BLOCKS)));

@@ -98,11 +98,11 @@ def chain_moments(stats, theta0, k, n_rows):
 def run_metropolis_hastings(pe, calculatePostBurnInStatistics=True, continueSampling='auto', mcmc_exportLog='UserChoice'):
     UI = pe.UserInput
     pes = UI.parameter_estimation_settings
-    if hasattr(UI, 'last_MCMC_run_type') and UI.last_MCMC_run_type != 'MH':                       # IP.py:2565-2569
-        print("ERROR: Two different algorithms of MCMC runs were attempted with the same UserInput."); raise SystemExit
     if getattr(pe, 'custom_logLikelihood', None) is not None or getattr(pe, 'custom_logPrior', None) is not None:
         raise NotImplementedError("doMetropolisHastings runs as one persistent kernel and cannot call custom_logLikelihood / "
                                   "custom_logPrior; use doEnsembleSliceSampling or doMultiStart (batched paths) with them")
+    if hasattr(UI, 'last_MCMC_run_type') and UI.last_MCMC_run_type != 'MH':                       # IP.py:2565-2569
+        print("ERROR: Two different algorithms of MCMC runs were attempted with the same UserInput."); raise SystemExit
     if pes['mcmc_mode'] not in ('unbiased', 'MAP_finding'):
         raise ValueError("mcmc_mode must be 'unbiased' or 'MAP_finding' (IP.py:2629-2631)")
     map_finding = pes['mcmc_mode'] == 'MAP_finding'                                                  # IP.py:2631-2635, 2688-2713

@@ -251,7 +251,9 @@ def test_scenarios_with_many_observations_tpd(env, golden):
         PE1 = make_pe(PEUQSE, m, list(obs[s]), sig, mu, sd, settings={'mcmc_length': 60, 'responses_observed_max_covmat_size': 5000})
         one = mh_launch(PE1, np.tile(truth, (2, 1)), 60, 10, 5, chol)
         assert np.array_equal(run['samples'][:, 2 * s:2 * s + 2].cpu().numpy(), one['samples'].cpu().numpy())
-        assert np.array_equal(run['logp'][:, 2 * s:2 * s + 2].cpu().numpy(), one['logp'].cpu().numpy())
+        # the stand-alone kernel of this model takes the fast rate-law form (csrc/mh.cu: FAST; fused exponent, table-driven
+        # exp), the scenario kernel the reference's operation order: same accept / reject decisions, log-posteriors to 1e-12
+        np.testing.assert_allclose(run['logp'][:, 2 * s:2 * s + 2].cpu().numpy(), one['logp'].cpu().numpy(), rtol=1e-12)
 
 
 def test_scenario_statistics_edge_cases(env):
