@@ -64,8 +64,8 @@ __device__ __forceinline__ bool short_usable(const ShortHdr* sh, int margin_ok) 
 // per-point values never reach the caller, takes this path; sweeps that return logP keep the bit-exact scalar order.
 // ---------------------------------------------------------------------------------------------
 #define P1D_THREADS 128
-template <int KT, int NF>
-__global__ void __launch_bounds__(P1D_THREADS, 4) k_sweep_pass1_lin_dmma(const __grid_constant__ DevProblem P,
+template <int KT, int NF, int MINB>
+__global__ void __launch_bounds__(P1D_THREADS, MINB) k_sweep_pass1_lin_dmma(const __grid_constant__ DevProblem P,
                                                                          const __grid_constant__ DevSweep S, long long first,
                                                                          long long count, peuqse_best* __restrict__ best_out,
                                                                          Best* __restrict__ partial, unsigned int* __restrict__ ticket,
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(P1D_THREADS, 4) k_sweep_pass1_lin_dmma(const _
                                                                          double* __restrict__ c_logp) {
     constexpr int KS = (KT + 3) / 4, KP = KS * 4, NW = P1D_THREADS / 32;
     __shared__ double s_bf[KS][NF][32];                 // B fragments: lane l of (s, f) holds Phi[8 f + l/4][4 s + l%4]
-    __shared__ double2 s_yw[NF * 8];                    // {y w, w} per observation
+    __shared__ __align__(32) double2 s_yw[NF * 8];      // {y w, w} per observation
     __shared__ double s_th[NW][32][KP];                 // the warp's 32 points, zero padded to 4 KS parameters
     __shared__ Best s_best[NW];
     __shared__ bool s_last;
@@ -86,6 +86,11 @@ __global__ void __launch_bounds__(P1D_THREADS, 4) k_sweep_pass1_lin_dmma(const _
     }
     for (int j = threadIdx.x; j < NF * 8; j += blockDim.x) s_yw[j] = make_double2(P.y[j] * P.w[j], P.w[j]);
     __syncthreads();
+    // diagonal prior in natural order (the usual case): z = theta / scale - mu_scaled as a multiplication by 1/scale
+    const bool fast_prior = P.prior_mode == PEUQSE_PRIOR_DIAG && P.prior_identity && P.kp == k;
+    double rs[KT];                                              // 1 / scale, once (a division per use otherwise)
+#pragma unroll
+    for (int d = 0; d < KT; ++d) rs[d] = (d < k && P.scaling_on) ? 1.0 / P.scale[d] : 1.0;
     Best best = best_none();
     const long long wstride = (long long)gridDim.x * NW * 32;
     for (long long base = ((long long)blockIdx.x * NW + warp) * 32; base < count; base += wstride) {
@@ -99,34 +104,63 @@ __global__ void __launch_bounds__(P1D_THREADS, 4) k_sweep_pass1_lin_dmma(const _
         }
         double th[KT];
         sweep_point<KT>(S, (unsigned long long)g, th);
-        const double lp = eval_prior<KT>(P, th);
+        double lp;
+        if (fast_prior) {
+            bool ok = true;
+            double q0 = 0.0, q1 = 0.0;
+#pragma unroll
+            for (int d = 0; d < KT; ++d) {
+                if (d < k) {
+                    if (P.has_ub) ok = ok && (th[d] <= P.ub[d]);
+                    if (P.has_lb) ok = ok && (th[d] >= P.lb[d]);
+                    const double zz = th[d] * rs[d] - P.mus[d];
+                    const double t = zz * P.pw[d];
+                    if (d & 1) q1 = fma(t, t, q1); else q0 = fma(t, t, q0);
+                }
+            }
+            lp = ok ? -0.5 * (P.prior_c + (q0 + q1)) : pq_neg_inf();
+        } else {
+            lp = eval_prior<KT>(P, th);
+        }
 #pragma unroll
         for (int d = 0; d < KP; ++d) s_th[warp][lane][d] = (d < KT) ? th[d < KT ? d : 0] : 0.0;
         __syncwarp();
         double maha = 0.0;
+        // two row fragments (16 points) at a time: every B fragment read feeds two DMMAs, four independent epilogue chains
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
-            double acc[NF][2];
+        for (int m = 0; m < 4; m += 2) {
+            double acc0[NF][2], acc1[NF][2];
 #pragma unroll
-            for (int f = 0; f < NF; ++f) acc[f][0] = acc[f][1] = 0.0;
+            for (int f = 0; f < NF; ++f) acc0[f][0] = acc0[f][1] = acc1[f][0] = acc1[f][1] = 0.0;
 #pragma unroll
             for (int sstep = 0; sstep < KS; ++sstep) {
-                const double a = s_th[warp][8 * m + (lane >> 2)][4 * sstep + (lane & 3)];
+                const double a0 = s_th[warp][8 * m + (lane >> 2)][4 * sstep + (lane & 3)];
+                const double a1 = s_th[warp][8 * m + 8 + (lane >> 2)][4 * sstep + (lane & 3)];
 #pragma unroll
-                for (int f = 0; f < NF; ++f) pq_dmma884(acc[f][0], acc[f][1], a, s_bf[sstep][f][lane]);
+                for (int f = 0; f < NF; ++f) {
+                    const double bq = s_bf[sstep][f][lane];
+                    pq_dmma884(acc0[f][0], acc0[f][1], a0, bq);
+                    pq_dmma884(acc1[f][0], acc1[f][1], a1, bq);
+                }
             }
-            double part = 0.0;
+            double pa0 = 0.0, pb0 = 0.0, pa1 = 0.0, pb1 = 0.0;  // even / odd observation of the lane's pair, per fragment
 #pragma unroll
             for (int f = 0; f < NF; ++f) {
-                const double2 q0 = s_yw[8 * f + 2 * (lane & 3)], q1 = s_yw[8 * f + 2 * (lane & 3) + 1];
-                const double t0 = fma(-acc[f][0], q0.y, q0.x), t1 = fma(-acc[f][1], q1.y, q1.x);   // (y - sim) w
-                part = fma(t0, t0, part);
-                part = fma(t1, t1, part);
+                const double4 q = *reinterpret_cast<const double4*>(&s_yw[8 * f + 2 * (lane & 3)]);   // {y w, w} of both
+                const double t00 = fma(-acc0[f][0], q.y, q.x), t01 = fma(-acc0[f][1], q.w, q.z);       // (y - sim) w
+                const double t10 = fma(-acc1[f][0], q.y, q.x), t11 = fma(-acc1[f][1], q.w, q.z);
+                pa0 = fma(t00, t00, pa0); pb0 = fma(t01, t01, pb0);
+                pa1 = fma(t10, t10, pa1); pb1 = fma(t11, t11, pb1);
             }
-            part += __shfl_xor_sync(0xffffffffu, part, 1);
-            part += __shfl_xor_sync(0xffffffffu, part, 2);      // the 4 lanes of row lane/4 hold the sum of point 8 m + lane/4
-            const double v = __shfl_sync(0xffffffffu, part, 4 * (lane & 7));
-            if ((lane >> 3) == m) maha = v;                     // this lane's own point
+            double part0 = pa0 + pb0, part1 = pa1 + pb1;
+            part0 += __shfl_xor_sync(0xffffffffu, part0, 1);
+            part1 += __shfl_xor_sync(0xffffffffu, part1, 1);
+            part0 += __shfl_xor_sync(0xffffffffu, part0, 2);    // the 4 lanes of row lane/4 hold the sum of point 8 m + lane/4
+            part1 += __shfl_xor_sync(0xffffffffu, part1, 2);
+            const double v0 = __shfl_sync(0xffffffffu, part0, 4 * (lane & 7));
+            const double v1 = __shfl_sync(0xffffffffu, part1, 4 * (lane & 7));
+            if ((lane >> 3) == m) maha = v0;                    // this lane's own point
+            if ((lane >> 3) == m + 1) maha = v1;
         }
         __syncwarp();
         double ll = -0.5 * (P.resp_c[0] + maha);
@@ -689,11 +723,15 @@ int launch_pass1(const peuqse_problem* p, const DevSweep& S, long long first, lo
             ShortHdr* shd = (ShortHdr*)((char*)work + PQ_SHORT_HDR_OFFSET);
             long long* ci = (long long*)((char*)work + PQ_SWEEP_BASE_BYTES);
             double* cl = (double*)(ci + PQ_SHORT_CAP);
+            static int minb = -1;
+            if (minb < 0) { const char* e = getenv("PEUQSE_SWEEP_DMMA_CTAS"); minb = e ? atoi(e) : 4; }
             const long long wantd = (count + 127) / 128;
-            const int gd = (int)std::max<long long>(1, std::min<long long>(wantd, std::min<long long>((long long)p->sm_count * 4, PQ_SWEEP_MAX_BLOCKS)));
-            if (n == 32) k_sweep_pass1_lin_dmma<KT, 4><<<gd, P1D_THREADS, 0, st>>>(p->d, S, first, count, best, partial, ticket, shd, ci, cl);
-            else if (n == 64) k_sweep_pass1_lin_dmma<KT, 8><<<gd, P1D_THREADS, 0, st>>>(p->d, S, first, count, best, partial, ticket, shd, ci, cl);
-            else k_sweep_pass1_lin_dmma<KT, 16><<<gd, P1D_THREADS, 0, st>>>(p->d, S, first, count, best, partial, ticket, shd, ci, cl);
+            const int per_sm = minb == 4 ? 4 : 3;
+            const int gd = (int)std::max<long long>(1, std::min<long long>(wantd, std::min<long long>((long long)p->sm_count * per_sm, PQ_SWEEP_MAX_BLOCKS)));
+            if (n == 32) k_sweep_pass1_lin_dmma<KT, 4, 4><<<gd, P1D_THREADS, 0, st>>>(p->d, S, first, count, best, partial, ticket, shd, ci, cl);
+            else if (n == 64 && per_sm == 4) k_sweep_pass1_lin_dmma<KT, 8, 4><<<gd, P1D_THREADS, 0, st>>>(p->d, S, first, count, best, partial, ticket, shd, ci, cl);
+            else if (n == 64) k_sweep_pass1_lin_dmma<KT, 8, 3><<<gd, P1D_THREADS, 0, st>>>(p->d, S, first, count, best, partial, ticket, shd, ci, cl);
+            else k_sweep_pass1_lin_dmma<KT, 16, 3><<<gd, P1D_THREADS, 0, st>>>(p->d, S, first, count, best, partial, ticket, shd, ci, cl);
             PQ_CUDA_OK(cudaGetLastError());
             return PEUQSE_OK;
         }
