@@ -574,7 +574,8 @@ def c5_secondary(PEUQSE, torch, dist, rank, world, total):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms1 = float(t[0].item()), float(t[1].item())
     R = sw.unpack(sw.res.cpu().numpy(), 2.0)
-    # end to end through the public call
+    # end to end through the public call (one small untimed call first: module loading, allocator warm-up)
+    PE.doMultiStart(numStartPoints=1 << 24)
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
@@ -594,7 +595,8 @@ def c5_secondary(PEUQSE, torch, dist, rank, world, total):
                                   f"diagonal uncertainties, Philox points keyed by the global index, logP not stored (shortlist of "
                                   "near-maximal points instead of a second evaluation pass); MAP argmax + weighted moments + histograms",
                       "points_per_gpu": sw.count, "map_index": R.map_index, "map_logP": R.map_logP, "n_retained": R.n_retained},
-           "roofline": {"bound": "fp64", "kernel": "k_sweep_pass1<LINEAR,k=10>", "achieved": per_gpu * flop_eval / 1e12,
+           "roofline": {"bound": "fp64", "kernel": "k_sweep_pass1_lin_dmma<k=10,n=64> (simulation as mma.sync.m8n8k4.f64, which shares the fp64 pipe)",
+                        "achieved": per_gpu * flop_eval / 1e12,
                         "peak": 2.0 * fp64_instr / 1e12, "unit": "TFLOP/s", "frac": per_gpu * flop_eval / (2.0 * fp64_instr),
                         "peak_source": "2 flop x DFMA issue rate measured in this run (peuqse_bench_fp64 mode 0)", "traffic": None},
            "e2e": {"value": total / float(te.item()), "unit": "evals/s", "api": "PE_object.doMultiStart()", "h2d_bytes_per_step": 3 * ctypes.sizeof(__import__('peuqse_b200')._lib.SweepSpec),
@@ -717,6 +719,7 @@ def run_ours(args, emit=print):
     # end-to-end through the public API: PE.doMultiStart() from host inputs to host results
     Ke = max(3, min(K, 50))
     PE.doMultiStart()
+    PE.doMultiStart()                                   # the second identical call captures the launch sequence as a graph
     barrier()
     t0 = time.perf_counter()
     for _ in range(Ke):

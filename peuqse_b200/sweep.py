@@ -225,7 +225,9 @@ class Sweep:
                     fn()
             cur.wait_stream(side)
             return g
-        except Exception:
+        except Exception as e:                                            # noqa: BLE001
+            self._graph_error = repr(e)                                   # kept for diagnosis; the eager path is used instead
+            torch.cuda.synchronize()
             return None
 
     def rest_of_step(self, log_rel):
@@ -267,12 +269,20 @@ class Sweep:
             self._graph.replay()                                          # the same sweep again: one graph launch
         else:
             self.step(log_rel, statistics)
-            self._graph, self._graph_key = None, None
-            # capture the launch sequence for the next call; with several ranks only when every exchange of the step is a
-            # peer-memory kernel (their exchange counter lives in device memory, csrc/peer.cu; NCCL calls are not captured)
-            g = self.capture(lambda: self.step(log_rel, statistics))
-            if g is not None:
-                self._graph, self._graph_key = g, key
+            # The launch sequence is captured when the SAME sweep is asked for a second time (a one-off sweep never pays for
+            # a capture; repeated ones replay one graph from their third call on); with several ranks only when every
+            # exchange of the step is a peer-memory kernel (their exchange counter lives in device memory, csrc/peer.cu;
+            # NCCL calls are not captured).  A failed capture is not retried.
+            seen = getattr(self, "_seen_key", None) == key
+            self._seen_key = key
+            if getattr(self, "_graph_key", None) != key:
+                self._graph, self._graph_key = None, None
+            if seen and self._graph is None and not getattr(self, "_graph_failed", False):
+                g = self.capture(lambda: self.step(log_rel, statistics))
+                if g is not None:
+                    self._graph, self._graph_key = g, key
+                else:
+                    self._graph_failed = True
         res = self.res.cpu()                                              # the single device->host read
         if self.peer is not None and self.L.peuqse_peer_status(self.peer) != 0:
             raise _lib.PeuqseError("multi-GPU exchange timed out: a rank did not reach the exchange within PEUQSE_PEER_TIMEOUT_S "
