@@ -837,6 +837,25 @@ __device__ __forceinline__ double pq_exp_pos(double x) {
     p = fma(p, r, 1.0);
     return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
 }
+// the same value within 1 ulp from a 64-entry table of 2^(j/64) in shared memory (eval.cuh: c_exp_tab64) and a degree-5
+// polynomial on |r| <= ln2/128: 10 fp64 instructions instead of 18 (pass 2 spends most of its fp64 work in this exp)
+__constant__ double c_exp_pos_tab[8] = {92.332482616893656 /* 64/ln2 */, -0.01083042469326756 /* -(ln2/64) hi */,
+                                        -2.9815858269852933e-12 /* lo */, 8.3333333333333332e-03, 4.1666666666666664e-02,
+                                        1.6666666666666666e-01, 0.5, 1.0};
+__device__ __forceinline__ double pq_exp_pos_tab(const double* __restrict__ tab, double x) {
+    const double t = fma(x, c_exp_pos_tab[0], 6755399441055744.0);
+    const int k = __double2loint(t);
+    const double fn = t - 6755399441055744.0;
+    double r = fma(fn, c_exp_pos_tab[1], x);
+    r = fma(fn, c_exp_pos_tab[2], r);
+    double q = fma(r, c_exp_pos_tab[3], c_exp_pos_tab[4]);
+    q = fma(r, q, c_exp_pos_tab[5]);
+    q = fma(r, q, c_exp_pos_tab[6]);
+    q = fma(r, q, c_exp_pos_tab[7]);
+    const double T = tab[k & 63];
+    const double v = fma(T, r * q, T);
+    return __hiloint2double(__double2hiint(v) + ((k >> 6) << 20), __double2loint(v));
+}
 
 // ---------------------------------------------------------------------------------------------
 // pass 2, warp-autonomous version (the one the C2 step uses).  Its predecessor moved whole 2048-point tiles through one
@@ -867,6 +886,7 @@ __global__ void __launch_bounds__(GR_THREADS, 2) k_grid_pass2_w(const __grid_con
     __shared__ long long s_mstart[GR_WARPS][P2W_STAGES];                         // per stage: first element of the warp tile ...
     __shared__ int2 s_mrc[GR_WARPS][P2W_STAGES];                                 // ... its row and first column
     __shared__ double s_red[GR_WARPS];
+    __shared__ double s_tab[64];
     __shared__ bool s_last;
     constexpr int L = KT - 1;
     const long long best_index = best_in->index;
@@ -876,6 +896,7 @@ __global__ void __launch_bounds__(GR_THREADS, 2) k_grid_pass2_w(const __grid_con
     grid_point<KT>(S, (unsigned long long)(none ? 0 : best_index), shift, KT);   // moments about the MAP point
     const double shiftL = shift[L], cL = S.center[L], hL = S.interval[L];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x < 64) s_tab[threadIdx.x] = c_exp_tab64[threadIdx.x];
     const int wpr = T.nchunks * GR_WARPS;                                        // warp tiles per row
     const long long nwt = none ? 0 : (T.b_hi - T.b_lo) * wpr;                    // warp tiles of the range
     if (lane == 0) {
@@ -929,7 +950,7 @@ __global__ void __launch_bounds__(GR_THREADS, 2) k_grid_pass2_w(const __grid_con
                 x[m] = kp[m] ? (v - thr) : 0.0;
             }
 #pragma unroll
-            for (int m = 0; m < GR_JPT; ++m) reps[m] = pq_exp_pos(x[m]);          // IP.py:3485
+            for (int m = 0; m < GR_JPT; ++m) reps[m] = pq_exp_pos_tab(s_tab, x[m]);          // IP.py:3485
 #pragma unroll
             for (int m = 0; m < GR_JPT; ++m) {
                 const double wt_ = kp[m] ? trunc(reps[m]) : 0.0;                  // IP.py:3486
@@ -947,7 +968,7 @@ __global__ void __launch_bounds__(GR_THREADS, 2) k_grid_pass2_w(const __grid_con
                 double v = pq_neg_inf();
                 if (lane + m * 32 < len && e >= lo && e < hi) v = (e < a1) ? buf[e - a0] : __ldcs(logp_in + e);
                 if (v > thr) {
-                    const double r_ = pq_exp_pos(v - thr);
+                    const double r_ = pq_exp_pos_tab(s_tab, v - thr);
                     const double wt_ = trunc(r_);
                     const double dl = (cL + shl * (d0 + 16.0 * m)) - shiftL;
                     a_wr = fma(wt_, r_, a_wr);
