@@ -340,8 +340,8 @@ typedef struct peuqse_ess_spec {
  * d_x[W][k], d_logp_x[W]: in = start positions and their logP, out = final positions.
  * d_chain[n_iters][W][k], d_chain_logp[n_iters][W] (nullable).  d_info[5]: neval, final mu, n_expand, n_contract, error.
  * d_work: peuqse_ess_work_bytes(W,k) (per-walker kernels only; may be NULL for the round-synchronous driver).
- * Built-in models only.  The round-synchronous driver synchronises the stream once per round (it needs the size of the
- * next batch) and returns PEUQSE_ERR_INVALID when a stepping-out / shrink loop exceeds max_rounds.
+ * Built-in models only.  The round-synchronous driver waits on the host once per round (it needs the size of the next
+ * batch) and returns PEUQSE_ERR_INVALID when a stepping-out / shrink loop exceeds max_rounds.
  */
 int64_t peuqse_ess_work_bytes(int64_t n_walkers, int32_t k);
 int peuqse_ess_run(const peuqse_problem* p, const peuqse_ess_spec* spec, double* d_x, double* d_logp_x,
@@ -356,7 +356,8 @@ int peuqse_ess_run(const peuqse_problem* p, const peuqse_ess_spec* spec, double*
  *     while (n > 0) { <d_rows[i] = logP(d_cand[i][0..k)), i < n>;  peuqse_essr_round(h, d_rows, d_cand, &n, stream); }
  *     peuqse_essr_end_half(h, d_x, d_logp_x, stream);
  * then peuqse_essr_end_iteration (adapts mu).  d_cand[W][k] receives each round's block of candidate points (at most
- * W rows); begin_half and round synchronise the stream and return the block's row count in *n_rows.  spec->n_iters is
+ * W rows); begin_half and round wait (spinning on a word of mapped pinned memory that the device writes last, not through
+ * a stream synchronisation) until the block is packed and return its row count in *n_rows.  spec->n_iters is
  * not used (the caller owns the loop); iteration numbers are offsets from spec->first_iter.
  */
 typedef struct peuqse_essr peuqse_essr;

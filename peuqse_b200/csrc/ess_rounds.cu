@@ -10,8 +10,10 @@
 // free); shrinking: one fresh point per walker that has not accepted yet -- the caller evaluates the block with ONE
 // batched launch, and the next round's kernels apply the results (masked updates) and pack the next block.  Two small
 // kernels per round (apply + count, scatter), whatever the ensemble size; the only host traffic is the row count of the
-// block (one 8-byte read of mapped pinned memory after the stream synchronisation the batched launch needs anyway).
+// block (mapped pinned memory, announced by a ticket word the host spins on: no stream synchronisation per round).
 // The order of the rows in a block is deterministic (left ends by slot, right ends by slot / walkers by slot).
+#include <atomic>
+#include <chrono>
 #include <cstring>
 #include <new>
 #include "common.cuh"
@@ -34,7 +36,7 @@ struct EssrDev {
     int *rowL, *rowR, *rowS;        // [H] row of the current candidate block that holds the task's point
     int *cntL, *cntR, *cntS;        // [G] per-CTA numbers of active tasks
     int* ctl;                       // [0] phase of the block just written (0 stepping out, 1 shrinking) [1] rows [2] stepping-out round
-    long long* h_status;            // mapped pinned host memory: [0] rows of the block, [1] phase, [2] error code
+    long long* h_status;            // mapped pinned host memory: [0] rows of the block, [1] phase, [2] error code, [3] ticket
 };
 
 struct peuqse_essr {
@@ -45,6 +47,7 @@ struct peuqse_essr {
     void* d_work;
     long long* h_status;
     long long it;
+    long long ticket;               // number of candidate blocks announced so far (the host waits for h_status[3] == ticket)
     int half;
 };
 
@@ -116,7 +119,7 @@ __device__ __forceinline__ int essr_rank(bool f, int base, int* s_warp) {
 
 // pack the next block of candidate rows: stepping out while any interval end is still moving, shrinking afterwards
 __global__ void __launch_bounds__(ER_THREADS) k_essr_scatter(const EssrDev D, const DevEss E, long long it, int half,
-                                                            double* __restrict__ cand) {
+                                                            double* __restrict__ cand, long long ticket) {
     __shared__ int s_red[6][ER_THREADS / 32];
     __shared__ int s_tot[6];
     __shared__ int s_warp[ER_THREADS / 32];
@@ -184,6 +187,18 @@ __global__ void __launch_bounds__(ER_THREADS) k_essr_scatter(const EssrDev D, co
         D.h_status[1] = stepping ? 0 : 1;
         D.h_status[2] = D.st->error;
         __threadfence_system();
+    }
+    // the ticket goes out when EVERY CTA has written its candidate rows: last CTA to arrive announces the block to the host
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int done = atomicAdd(reinterpret_cast<unsigned int*>(D.ctl + 3), 1u);
+        if (done == gridDim.x - 1) {
+            D.ctl[3] = 0;
+            __threadfence_system();
+            *(volatile long long*)(D.h_status + 3) = ticket;
+            __threadfence_system();
+        }
     }
 }
 
@@ -345,9 +360,24 @@ extern "C" int peuqse_essr_destroy(peuqse_essr* h) {
     return PEUQSE_OK;
 }
 
+// The host learns the size of the next block from mapped pinned memory: it SPINS on the ticket word the scatter kernel writes
+// last (a stream synchronisation per round goes through the driver's blocking wait, whose wake-up latency -- tens of
+// microseconds, far more on a busy host -- would be paid ~40 times per ensemble iteration); the kernels that follow are
+// stream-ordered behind the scatter kernel anyway.  If the ticket does not arrive within 20 s the stream is synchronised
+// to surface the error.
 static int essr_read_status(peuqse_essr* h, int64_t* n_rows, int32_t* phase, cudaStream_t st) {
-    PQ_CUDA_OK(cudaStreamSynchronize(st));
     const volatile long long* hs = h->h_status;
+    {
+        const auto t0 = std::chrono::steady_clock::now();
+        unsigned long long spins = 0;
+        while (hs[3] != h->ticket) {
+            if ((++spins & 0xfffffULL) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(20)) {
+                PQ_CUDA_OK(cudaStreamSynchronize(st));
+                if (hs[3] != h->ticket) return pq_set_error(PEUQSE_ERR_CUDA, "ensemble slice sampling: the device did not announce the next round");
+            }
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+    }
     if (n_rows) *n_rows = hs[0];
     if (phase) *phase = (int32_t)hs[1];
     if (hs[2] == 1) return pq_set_error(PEUQSE_ERR_INVALID, "Number of expansions exceeded maximum limit! Increase mcmc_maxiter.");
@@ -367,7 +397,7 @@ extern "C" int peuqse_essr_begin_half(peuqse_essr* h, int64_t it, int32_t half, 
         k_ess_rank<<<wb, 128, 0, st>>>(h->E, h->D.keys, h->D.perm);
     }
     k_essr_setup<<<h->G, ER_THREADS, 0, st>>>(h->D, h->E, it, half, d_x, d_logp_x);
-    k_essr_scatter<<<h->G, ER_THREADS, 0, st>>>(h->D, h->E, it, half, d_cand);
+    k_essr_scatter<<<h->G, ER_THREADS, 0, st>>>(h->D, h->E, it, half, d_cand, ++h->ticket);
     PQ_CUDA_OK(cudaGetLastError());
     return essr_read_status(h, n_rows, nullptr, st);
 }
@@ -376,7 +406,7 @@ extern "C" int peuqse_essr_round(peuqse_essr* h, const double* d_logp_rows, doub
     if (!h || !d_logp_rows || !d_cand || !n_rows) return pq_set_error(PEUQSE_ERR_INVALID, "bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     k_essr_apply<<<h->G, ER_THREADS, 0, st>>>(h->D, h->E, d_logp_rows);
-    k_essr_scatter<<<h->G, ER_THREADS, 0, st>>>(h->D, h->E, h->it, h->half, d_cand);
+    k_essr_scatter<<<h->G, ER_THREADS, 0, st>>>(h->D, h->E, h->it, h->half, d_cand, ++h->ticket);
     PQ_CUDA_OK(cudaGetLastError());
     return essr_read_status(h, n_rows, nullptr, st);
 }

@@ -115,6 +115,71 @@ __global__ void __launch_bounds__(256) k_qf_residual_frag(const QfBatch Q, const
     }
 }
 
+// The same two forms for the built-in LINEAR model when every response has a full covariance (config C4): the simulated
+// value sum_d Phi[j][d] theta_d (d ascending, multiply then add: the operation order of Sim<PEUQSE_MODEL_LINEAR>, eval.cuh)
+// is formed here instead of being written to and read back from a [B][n] block by a separate simulation kernel.  A thread
+// keeps its observation's row of Phi in registers (read from the transposed copy: coalesced) and walks over 8 rows of the
+// batch (thetas in shared memory).
+#define QR_ROWS 8
+__global__ void __launch_bounds__(256) k_qf_residual_lin(const QfBatch Q, const double* __restrict__ theta, int k,
+                                                        const double* __restrict__ PhiT, int n_total,
+                                                        const double* __restrict__ y, long long B, long long B_pad,
+                                                        double* __restrict__ Rm) {
+    __shared__ double s_th[QR_ROWS][PQ_MAXK];
+    const long long b0 = (long long)blockIdx.x * QR_ROWS;
+    for (int e = threadIdx.x; e < QR_ROWS * k; e += blockDim.x) {
+        const int r = e / k, d = e - r * k;
+        s_th[r][d] = (b0 + r < B) ? theta[(b0 + r) * k + d] : 0.0;
+    }
+    __syncthreads();
+    for (int c = blockIdx.y * blockDim.x + threadIdx.x; c < Q.NP; c += gridDim.y * blockDim.x) {
+        int r = 0;
+        while (r + 1 < Q.nresp && c >= Q.r[r + 1].poff) ++r;
+        const int i = c - Q.r[r].poff;
+        const bool in = i < Q.r[r].n;
+        double row[PQ_MAXK];
+        const int j = Q.r[r].off + (in ? i : 0);
+#pragma unroll
+        for (int d = 0; d < PQ_MAXK; ++d) row[d] = (d < k) ? PhiT[(size_t)d * n_total + j] : 0.0;   // neighbours read neighbours
+        const double yj = y[j];
+#pragma unroll
+        for (int q = 0; q < QR_ROWS; ++q) {
+            if (b0 + q >= B_pad) break;
+            double acc = row[0] * s_th[q][0];
+#pragma unroll
+            for (int d = 1; d < PQ_MAXK; ++d)
+                if (d < k) acc = acc + row[d] * s_th[q][d];
+            Rm[(b0 + q) * Q.NP + c] = (in && b0 + q < B) ? (yj - acc) : 0.0;
+        }
+    }
+}
+
+template <int MF>
+__global__ void __launch_bounds__(256) k_qf_residual_frag_lin(const QfBatch Q, const double* __restrict__ theta, int k,
+                                                             const double* __restrict__ Phi, const double* __restrict__ y,
+                                                             long long B, double* __restrict__ Af) {
+    const long long total = (long long)(Q.NP / 4) * MF * 32;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int lane = (int)(e & 31);
+        const int m = (int)((e >> 5) % MF);
+        const int c = (int)((e >> 5) / MF) * 4 + (lane & 3);
+        const long long b = m * 8 + (lane >> 2);
+        int r = 0;
+        while (r + 1 < Q.nresp && c >= Q.r[r + 1].poff) ++r;
+        const int i = c - Q.r[r].poff;
+        double v = 0.0;
+        if (b < B && i < Q.r[r].n) {
+            const int j = Q.r[r].off + i;
+            const double* row = Phi + (size_t)j * k;
+            const double* th = theta + b * k;
+            double acc = row[0] * th[0];
+            for (int d = 1; d < k; ++d) acc = acc + row[d] * th[d];
+            v = y[j] - acc;
+        }
+        Af[e] = v;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // tile kernel
 // ---------------------------------------------------------------------------------------------------
@@ -373,43 +438,51 @@ __global__ void __launch_bounds__(128) k_qf_finish_tc(const QfBatch Q, const dou
     if (q == 0 && row < B) partial[(((size_t)(R.poff / QT_BN) + t) * 4 + w) * B + row] = s;
 }
 
-// ll_b += -0.5*(c_r + sum_t partial) for every full-covariance response in order, then the NaN convention and logP
+// ll_b += -0.5*(c_r + sum_t tile_t) for every full-covariance response in order, then the NaN convention and logP.
+// One WARP per row: the lanes fetch and combine the quad sums of the column tiles in parallel (the loads are what takes
+// time), lane 0 adds the tile sums in ascending tile order -- the fixed order every kernel shape shares.
 __global__ void __launch_bounds__(256) k_qf_reduce_finish(const QfBatch Q, const double* __restrict__ partial, long long B,
                                                          const double* __restrict__ lp, double* __restrict__ ll,
                                                          double* __restrict__ logp) {
-    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ double s_tile[8][128];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long b = (long long)blockIdx.x * 8 + warp;
     if (b >= B) return;
     double l = ll[b];
     for (int r = 0; r < Q.nresp; ++r) {
         const double* part = partial + (size_t)(Q.r[r].poff / QT_BN) * 4 * B + b;
-        double m = 0.0;
         const int nt = Q.r[r].ntile;
-        int t = 0;
-        for (; t + 4 <= nt; t += 4) {                                        // fixed order; 16 independent loads in flight
-            double q[16];
-#pragma unroll
-            for (int e = 0; e < 16; ++e) q[e] = part[((size_t)t * 4 + e) * B];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) m += ((q[4 * e] + q[4 * e + 1]) + q[4 * e + 2]) + q[4 * e + 3];
+        double m = 0.0;
+        for (int t0 = 0; t0 < nt; t0 += 128) {                               // 128 tiles (16384 columns) per round
+            const int nn = nt - t0 < 128 ? nt - t0 : 128;
+            for (int t = lane; t < nn; t += 32) {
+                const double* q = part + (size_t)(t0 + t) * 4 * B;
+                s_tile[warp][t] = ((q[0] + q[B]) + q[2 * B]) + q[3 * B];
+            }
+            __syncwarp();
+            if (lane == 0)
+                for (int t = 0; t < nn; ++t) m += s_tile[warp][t];
+            __syncwarp();
         }
-        for (; t < nt; ++t) {
-            const double* q = part + (size_t)t * 4 * B;
-            m += ((q[0] + q[B]) + q[2 * B]) + q[3 * B];
-        }
+        m = __shfl_sync(0xffffffffu, m, 0);
         l = l + (-0.5 * (Q.r[r].c + m));
     }
-    if (l != l) l = pq_neg_inf();            // NaN simulated values -> -inf (IP.py:2880-2882)
-    ll[b] = l;
-    if (logp) logp[b] = combine_logp(lp[b], l);
+    if (lane == 0) {
+        if (l != l) l = pq_neg_inf();            // NaN simulated values -> -inf (IP.py:2880-2882)
+        ll[b] = l;
+        if (logp) logp[b] = combine_logp(lp[b], l);
+    }
 }
 
 namespace {
 template <int MF>
 void launch_skinny(const QfBatch& Q, int ntile_max, const double* sim, int ld_sim, const int* src, const double* y, long long B,
-                   long long B_pad, double* Af, double* Tc, int sm_count, cudaStream_t st) {
+                   long long B_pad, double* Af, double* Tc, int sm_count, cudaStream_t st, const double* theta, int k,
+                   const double* Phi) {
     const long long total = (long long)(Q.NP / 4) * MF * 32;
     const int rb = (int)std::min<long long>((total + 255) / 256, (long long)sm_count * 8);
-    k_qf_residual_frag<MF><<<rb, 256, 0, st>>>(Q, sim, ld_sim, src, y, B, Af);
+    if (!sim) k_qf_residual_frag_lin<MF><<<rb, 256, 0, st>>>(Q, theta, k, Phi, y, B, Af);
+    else k_qf_residual_frag<MF><<<rb, 256, 0, st>>>(Q, sim, ld_sim, src, y, B, Af);
     k_qf_skinny<MF><<<dim3((unsigned)ntile_max, QT_CHUNKS, (unsigned)Q.nresp), 256, 0, st>>>(Q, Af, B_pad, Tc);
 }
 }  // namespace
@@ -418,7 +491,7 @@ static int g_qf_wn = 4;      // warps along N of the tile kernel's CTA (PEUQSE_Q
 
 // rows [0, B) of one chunk: residuals, contraction, partial sums, likelihood
 static int fullcov_rows(const peuqse_problem* p, const QfBatch& Q, int ntile_max, int ntiles, const double* d_sim, long long B,
-                        const double* lp, double* ll, double* d_logp, cudaStream_t st) {
+                        const double* lp, double* ll, double* d_logp, cudaStream_t st, const double* d_theta) {
     static bool attr_done = false;
     if (!attr_done) {
         cudaFuncSetAttribute((const void*)k_qf_tile<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, QtCfg<4>::SMEM_BYTES);
@@ -444,12 +517,16 @@ static int fullcov_rows(const peuqse_problem* p, const QfBatch& Q, int ntile_max
     double* tc = res + n_res;
     const int ld_sim = p->d.n_total;
     if (skinny) {
-        if (MF == 1) launch_skinny<1>(Q, ntile_max, d_sim, ld_sim, p->d.src, p->d.y, B, B_pad, res, tc, p->sm_count, st);
-        else launch_skinny<2>(Q, ntile_max, d_sim, ld_sim, p->d.src, p->d.y, B, B_pad, res, tc, p->sm_count, st);
+        if (MF == 1) launch_skinny<1>(Q, ntile_max, d_sim, ld_sim, p->d.src, p->d.y, B, B_pad, res, tc, p->sm_count, st, d_theta, p->d.k, p->d.mconst);
+        else launch_skinny<2>(Q, ntile_max, d_sim, ld_sim, p->d.src, p->d.y, B, B_pad, res, tc, p->sm_count, st, d_theta, p->d.k, p->d.mconst);
         k_qf_finish_tc<<<dim3((unsigned)ntile_max, (unsigned)(B_pad / 8), (unsigned)Q.nresp), 128, 0, st>>>(Q, tc, B, B_pad, part);
     } else {
-        k_qf_residual<<<dim3((unsigned)B_pad, (unsigned)std::min((Q.NP + 255) / 256, 16)), 256, 0, st>>>(Q, d_sim, ld_sim, p->d.src,
-                                                                                                       p->d.y, B, B_pad, res);
+        if (!d_sim)
+            k_qf_residual_lin<<<dim3((unsigned)((B_pad + QR_ROWS - 1) / QR_ROWS), (unsigned)((Q.NP + 255) / 256)), 256, 0, st>>>(
+                Q, d_theta, p->d.k, p->mconstT, p->d.n_total, p->d.y, B, B_pad, res);
+        else
+            k_qf_residual<<<dim3((unsigned)B_pad, (unsigned)std::min((Q.NP + 255) / 256, 16)), 256, 0, st>>>(Q, d_sim, ld_sim, p->d.src,
+                                                                                                           p->d.y, B, B_pad, res);
         if (split) {
             if (g_qf_wn == 4)
                 k_qf_tile<true, 4><<<dim3((unsigned)(ntile_max * nrt), 1, (unsigned)(Q.nresp * QT_CHUNKS)), 256, QtCfg<4>::SMEM_BYTES, st>>>(
@@ -467,15 +544,18 @@ static int fullcov_rows(const peuqse_problem* p, const QfBatch& Q, int ntile_max
                     Q, res, B, B_pad, nrt, part, nullptr);
         }
     }
-    k_qf_reduce_finish<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(Q, part, B, lp, ll, d_logp);
+    k_qf_reduce_finish<<<(unsigned)((B + 7) / 8), 256, 0, st>>>(Q, part, B, lp, ll, d_logp);
     const cudaError_t e = cudaGetLastError();
     cudaFreeAsync(scratch, st);
     if (e != cudaSuccess) return pq_set_cuda_error(e, "full-covariance contraction", __LINE__);
     return PEUQSE_OK;
 }
 
+// d_sim == nullptr: built-in LINEAR model whose responses all have full covariances -- the residual kernels simulate (d_theta
+// is needed then)
 int pq_fullcov_logp(const peuqse_problem* p, const double* d_theta, const double* d_sim, long long B, double* d_logp,
                     double* d_logprior, double* d_loglik, cudaStream_t st) {
+    if (!d_sim && (!d_theta || p->d.model_id != PEUQSE_MODEL_LINEAR)) return pq_set_error(PEUQSE_ERR_INVALID, "fullcov: no simulated values");
     // the padded residual block places every response at a multiple of 128 columns (poff / 128 = its first global column tile)
     QfBatch Q;
     Q.nresp = 0;
@@ -513,8 +593,8 @@ int pq_fullcov_logp(const peuqse_problem* p, const double* d_theta, const double
     if (rows < QT_BM) rows = QT_BM;
     for (long long b0 = 0; b0 < B && rc == PEUQSE_OK; b0 += rows) {
         const long long nb = std::min(rows, B - b0);
-        rc = fullcov_rows(p, Q, ntile_max, ntiles, d_sim + (size_t)b0 * p->d.n_total, nb, lp ? lp + b0 : nullptr, ll + b0,
-                          d_logp ? d_logp + b0 : nullptr, st);
+        rc = fullcov_rows(p, Q, ntile_max, ntiles, d_sim ? d_sim + (size_t)b0 * p->d.n_total : nullptr, nb, lp ? lp + b0 : nullptr,
+                          ll + b0, d_logp ? d_logp + b0 : nullptr, st, d_theta ? d_theta + (size_t)b0 * p->d.k : nullptr);
     }
     if (tmp) cudaFreeAsync(tmp, st);
     return rc;

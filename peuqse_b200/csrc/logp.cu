@@ -163,6 +163,10 @@ extern "C" int peuqse_logp_batch(const peuqse_problem* p, const double* d_theta,
     if (p->d.model_id == PEUQSE_MODEL_EXTERNAL)
         return pq_set_error(PEUQSE_ERR_INVALID, "logp_batch needs a built-in model; use peuqse_logp_from_sim");
     if (p->d.any_full) {
+        bool all_full = true;
+        for (int r = 0; r < p->d.n_resp; ++r) all_full = all_full && p->d.resp_mode[r] == PEUQSE_RESP_MVN_FULL;
+        // linear model, every response dense: the residual kernels of the contraction simulate themselves (csrc/fullcov.cu)
+        if (all_full && p->d.model_id == PEUQSE_MODEL_LINEAR) return pq_fullcov_logp(p, d_theta, nullptr, B, d_logp, d_logprior, d_loglik, st);
         // built-in simulate -> full-covariance contraction on the simulated block
         double* sim = nullptr;
         PQ_CUDA_OK(cudaMallocAsync((void**)&sim, (size_t)B * p->d.n_total * sizeof(double), st));

@@ -147,6 +147,13 @@ extern "C" int peuqse_problem_create(const peuqse_problem_desc* h, peuqse_proble
     } else {
         o_m = bb.add(h->model_const, (size_t)h->n_model_const * 8);
     }
+    size_t o_mT = 0;
+    if (h->model_id == PEUQSE_MODEL_LINEAR) {
+        std::vector<double> t((size_t)h->k * nt);
+        for (size_t j = 0; j < nt; ++j)
+            for (int d = 0; d < h->k; ++d) t[(size_t)d * nt + j] = h->model_const[j * h->k + d];
+        o_mT = bb.add(t.data(), t.size() * 8);
+    }
     size_t o_pU = 0;
     if (h->prior_mode == PEUQSE_PRIOR_DENSE) o_pU = bb.add(h->prior_U, (size_t)h->kp * h->kp * 8);
     size_t o_U[PQ_MAXR] = {0};
@@ -178,6 +185,7 @@ extern "C" int peuqse_problem_create(const peuqse_problem_desc* h, peuqse_proble
     d.cval = (const double*)(base + o_c);
     d.src = (const int*)(base + o_s);
     d.mconst = (const double*)(base + o_m);
+    p->mconstT = h->model_id == PEUQSE_MODEL_LINEAR ? (const double*)(base + o_mT) : nullptr;
     d.pU = h->prior_mode == PEUQSE_PRIOR_DENSE ? (const double*)(base + o_pU) : nullptr;
     for (int r = 0; r < h->n_resp; ++r)
         d.U[r] = (h->resp_mode[r] == PEUQSE_RESP_MVN_FULL) ? (const double*)(base + o_U[r]) : nullptr;
