@@ -268,24 +268,26 @@ struct MhwLayout {
     static constexpr int NSLOT = NPAIR + KT;
     static constexpr int NACC = (NSLOT + 31) / 32;
     static constexpr int KPAD = (KT + 1) & ~1;
-    static constexpr int WDOUBLES = 2 * KPAD + 64;       // cur[KPAD] | th0[KPAD] | draws[32][2]
+    // cur[KPAD] | th0[KPAD] | proposal[KPAD] | draws[32][2] | modulation uniforms[4] | 'MAP_finding' state[6]
+    static constexpr int WDOUBLES = 3 * KPAD + 64 + 4 + 6;
 };
 
 // the draws of one lane for four steps of its chain (lane = 8 * step offset + block): a pair of normals (blocks 0..6) or the
 // accept uniform and the modulation uniform of 'MAP_finding' (block 7).  Not inlined: the large-argument paths of sincos and log would otherwise set
 // the register budget of the whole kernel although they run once every four steps.
-__device__ __noinline__ double2 mhw_draw(unsigned long long seed, unsigned long long gchain, unsigned long long step, int blk, int k) {
+__device__ __noinline__ double2 mhw_draw(unsigned long long seed, unsigned long long gchain, unsigned long long step, int blk, int k,
+                                         double* um) {
     const Philox4 r = philox_block(seed, PQ_STREAM_MH, gchain, (uint32_t)(8ULL * step + (unsigned)blk));
     double a = 0.0, b2 = 0.0;
     if (blk < 7) {
         if (2 * blk < k) philox_normal_pair(r, a, b2);
     } else {
-        a = philox_u53(r.x, r.y);                                  // accept uniform
-        b2 = philox_u53(r.z, r.w);                                 // 'MAP_finding' modulation uniform
+        a = philox_u53(r.x, r.y);                                  // accept uniform ...
+        b2 = log(a);                                               // ... and its logarithm (IP.py:2651)
+        *um = philox_u53(r.z, r.w);                                // 'MAP_finding' modulation uniform
     }
     return make_double2(a, b2);
 }
-__device__ __noinline__ double mhw_log(double x) { return log(x); }
 __device__ __noinline__ double mhw_exp(double x) { return exp(x); }
 template <int KT>
 __device__ __noinline__ double mhw_prior(const DevProblem& P, const double (&th)[KT]) { return eval_prior<KT>(P, th); }
@@ -311,7 +313,11 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_mh_warp(const __grid_constant
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* cur = smem + warp * L::WDOUBLES;
     double* th0s = cur + L::KPAD;
-    double2* dr = reinterpret_cast<double2*>(th0s + L::KPAD);
+    double* prp = th0s + L::KPAD;
+    double2* dr = reinterpret_cast<double2*>(prp + L::KPAD);
+    double* dmod = reinterpret_cast<double*>(dr + 32);
+    MapFind* mf = reinterpret_cast<MapFind*>(dmod + 4);
+    __shared__ double s_rs[KT];                                  // 1 / scale of the fast prior
     ObsView O;
     __shared__ double s_exp_tab[FAST ? 64 : 1];
     __shared__ double s_ext[4];
@@ -332,6 +338,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_mh_warp(const __grid_constant
         }
         if (threadIdx.x < 64) s_exp_tab[threadIdx.x] = c_exp_tab64[threadIdx.x];
         if (threadIdx.x < 4) s_ext[threadIdx.x] = 0.0;
+        if (threadIdx.x < KT) s_rs[threadIdx.x] = (threadIdx.x < P.k && P.scaling_on) ? 1.0 / P.scale[threadIdx.x] : 1.0;
         __syncthreads();
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -392,13 +399,12 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_mh_warp(const __grid_constant
         gchain = (unsigned long long)(M.chain_offset + (c - s * SC.per));
     }
 
-    double th[KT];
-#pragma unroll
-    for (int d = 0; d < KT; ++d) th[d] = (d < k) ? theta0[c * k + d] : 0.0;
-    if (lane == 0) {
-#pragma unroll
-        for (int d = 0; d < KT; ++d) { cur[d] = th[d]; th0s[d] = th[d]; }
+    // the chain's point lives in shared memory (cur) and so does the proposal (prp): registers are for the observation loop
+    if (lane < KT) {
+        const double t0 = (lane < k) ? theta0[c * k + lane] : 0.0;
+        cur[lane] = t0; th0s[lane] = t0; prp[lane] = t0;
     }
+    if (lane == 0) mf->init();
     __syncwarp();
     // accumulator slots of this lane
     int sa[L::NACC], sb[L::NACC];
@@ -420,8 +426,14 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_mh_warp(const __grid_constant
     }
     double nacc = 0.0, maplogp = pq_neg_inf(), maprow = -1.0, sumexp = 0.0, mapth = 0.0;
 
-    double cur_lp = eval_prior<KT>(P, th);
-    double cur_ll = loglik(th);
+    double cur_lp, cur_ll;
+    {
+        double th[KT];
+#pragma unroll
+        for (int d = 0; d < KT; ++d) th[d] = cur[d];
+        cur_lp = eval_prior<KT>(P, th);
+        cur_ll = loglik(th);
+    }
     double cur_sum = cur_ll + cur_lp;
     auto add_row = [&](long long row, double lp, double explp) {
         if (lp > maplogp) {                                       // first maximum (IP.py:1925-1927)
@@ -434,11 +446,8 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_mh_warp(const __grid_constant
     };
     {
         const double lp0 = combine_logp(cur_lp, cur_ll);
+        if (out.samples && lane < k) out.samples[c * k + lane] = cur[lane];
         if (lane == 0) {
-            if (out.samples) {
-#pragma unroll
-                for (int d = 0; d < KT; ++d) if (d < k) out.samples[c * k + d] = th[d];
-            }
             if (out.logp) out.logp[c] = lp0;
             if (out.lprior) out.lprior[c] = 0.0;
             if (out.llik) out.llik[c] = 0.0;
@@ -448,16 +457,17 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_mh_warp(const __grid_constant
     double cur_exp = exp(cur_sum);
     long long next_row = 1;
     int until_row = M.thin;
-    MapFind mf;
-    mf.init();
+    const bool fast_prior = FAST && P.prior_mode == PEUQSE_PRIOR_DIAG && P.prior_identity && P.kp == k;
     const int sub = lane >> 3, blk = lane & 7;
     for (long long i = 1; i < M.n_steps; ++i) {
         const int g = (int)((i - 1) & 3);
         if (g == 0) {
             const unsigned long long step = (unsigned long long)(M.first_step + i + sub);
-            const double2 d2 = mhw_draw(M.seed, gchain, step, blk, k);
+            double um = 0.0;
+            const double2 d2 = mhw_draw(M.seed, gchain, step, blk, k, &um);
             __syncwarp();
             dr[lane] = d2;
+            if (blk == 7) dmod[sub] = um;
             __syncwarp();
         }
         double z[KT], delta[KT], prop[KT];
@@ -467,43 +477,19 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_mh_warp(const __grid_constant
             z[2 * j] = zz.x;
             if (2 * j + 1 < KT) z[2 * j + 1] = zz.y;
         }
-        const double2 uu = dr[g * 8 + 7];                         // (accept uniform, modulation uniform)
+        const double2 uu = dr[g * 8 + 7];                         // (accept uniform, its logarithm)
         make_delta<KT>(M, z, delta);
-        const double mod = uu.y + 0.5;                            // IP.py:2633
+        const double mod = dmod[g] + 0.5;                         // IP.py:2633
         if (M.map_finding) {
-            const double sc = mf.scale(mod);
+            const double sc = mf->scale(mod);
 #pragma unroll
             for (int d = 0; d < KT; ++d) delta[d] = sc * delta[d];
         }
 #pragma unroll
-        for (int d = 0; d < KT; ++d) prop[d] = th[d] + delta[d];  // IP.py:2630
-        const double lp_p = FAST ? mhw_prior<KT>(P, prop) : eval_prior<KT>(P, prop);
-        const double ll_p = loglik(prop);
-        const double sum_p = ll_p + lp_p;
-        double la = sum_p - cur_sum;                              // IP.py:2641
-        if (M.modulate != 0.0) la = (1.0 / M.modulate) * la;      // IP.py:2649
-        const bool accept = la > mhw_log(uu.x);                   // IP.py:2651-2652; NaN -> reject
-        if (accept) {                                             // the same in every lane
-#pragma unroll
-            for (int d = 0; d < KT; ++d) th[d] = prop[d];
-            cur_lp = lp_p; cur_ll = ll_p; cur_sum = sum_p;
-            cur_exp = mhw_exp(cur_sum);
-            nacc += 1.0;
-            __syncwarp();
-            if (lane == 0) {
-#pragma unroll
-                for (int d = 0; d < KT; ++d) cur[d] = th[d];
-            }
-            __syncwarp();
-#pragma unroll
-            for (int q = 0; q < L::NACC; ++q) {
-                if (sa[q] >= 0) {
-                    va[q] = cur[sa[q]] - th0s[sa[q]];
-                    if (sb[q] >= 0) vb[q] = cur[sb[q]] - th0s[sb[q]];
-                }
-            }
-        }
+        for (int d = 0; d < KT; ++d) prop[d] = cur[d] + delta[d]; // IP.py:2630
         if (lane == 0) {
+#pragma unroll
+            for (int d = 0; d < KT; ++d) prp[d] = prop[d];
             if (out.deltas) {
 #pragma unroll
                 for (int d = 0; d < KT; ++d) if (d < k) out.deltas[((i - 1) * C + c) * k + d] = delta[d];
@@ -513,15 +499,54 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_mh_warp(const __grid_constant
                 else out.us[(i - 1) * C + c] = uu.x;
             }
         }
-        if (M.map_finding) mf.after_step(i, mod, sum_p);
+        double lp_p;
+        if (FAST && fast_prior) {
+            // diagonal prior in natural order: theta / scale as a multiplication by the reciprocal (the log-prior moves in its
+            // last digit; the fast form's budget is 1e-12)
+            bool ok = true;
+            double q0 = 0.0, q1 = 0.0;
+#pragma unroll
+            for (int d = 0; d < KT; ++d) {
+                if (d < k) {
+                    if (P.has_ub) ok = ok && (prop[d] <= P.ub[d]);
+                    if (P.has_lb) ok = ok && (prop[d] >= P.lb[d]);
+                    const double t = (prop[d] * s_rs[d] - P.mus[d]) * P.pw[d];
+                    if (d & 1) q1 = fma(t, t, q1); else q0 = fma(t, t, q0);
+                }
+            }
+            lp_p = ok ? -0.5 * (P.prior_c + (q0 + q1)) : pq_neg_inf();
+        } else {
+            lp_p = FAST ? mhw_prior<KT>(P, prop) : eval_prior<KT>(P, prop);
+        }
+        const double ll_p = loglik(prop);
+        const double sum_p = ll_p + lp_p;
+        double la = sum_p - cur_sum;                              // IP.py:2641
+        if (M.modulate != 0.0) la = (1.0 / M.modulate) * la;      // IP.py:2649
+        const bool accept = la > dr[g * 8 + 7].y;                 // IP.py:2651-2652; NaN -> reject
+        if (accept) {                                             // the same in every lane
+            cur_lp = lp_p; cur_ll = ll_p; cur_sum = sum_p;
+            cur_exp = mhw_exp(cur_sum);
+            nacc += 1.0;
+            __syncwarp();
+            if (lane < KT) cur[lane] = prp[lane];
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < L::NACC; ++q) {
+                if (sa[q] >= 0) {
+                    va[q] = cur[sa[q]] - th0s[sa[q]];
+                    if (sb[q] >= 0) vb[q] = cur[sb[q]] - th0s[sb[q]];
+                }
+            }
+        }
+        if (M.map_finding) {
+            if (lane == 0) mf->after_step(i, dmod[g] + 0.5, sum_p);
+            __syncwarp();
+        }
         if (--until_row == 0) {
             until_row = M.thin;
             const long long row = next_row++;
+            if (out.samples && lane < k) out.samples[(row * C + c) * k + lane] = cur[lane];
             if (lane == 0) {
-                if (out.samples) {
-#pragma unroll
-                    for (int d = 0; d < KT; ++d) if (d < k) out.samples[(row * C + c) * k + d] = th[d];
-                }
                 if (out.logp) out.logp[row * C + c] = cur_sum;      // IP.py:2661, 2673
                 if (out.lprior) out.lprior[row * C + c] = cur_lp;
                 if (out.llik) out.llik[row * C + c] = cur_ll;
@@ -536,7 +561,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_mh_warp(const __grid_constant
         so[PEUQSE_MH_STAT_MAPROW] = maprow;
         so[PEUQSE_MH_STAT_LASTLOGP] = cur_sum;
         so[PEUQSE_MH_STAT_SUMEXP] = sumexp;
-        so[PEUQSE_MH_STAT_DYN(k)] = mf.dyn;
+        so[PEUQSE_MH_STAT_DYN(k)] = mf->dyn;
     }
     if (lane < k) {
         so[PEUQSE_MH_STAT_MAPTHETA + lane] = mapth;
