@@ -580,6 +580,406 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_mh_warp(const __grid_constant
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// config C3 shape: the two-site rate-law model with one diagonal-covariance response, up to CPW chains per warp, ONE CTA per SM.
+//
+// What bounds this kernel is instruction ISSUE: an fp64 instruction holds a sub-partition's issue port for two cycles and every
+// other instruction for one (profiles/fp64_latency.py: 8 DFMA + 12 integer instructions take 28 cycles, not 16), so the cost of a
+// chain step is 2 x (fp64 instructions) + (all others), and the warps of a sub-partition share one port.  Hence:
+//   * a lane evaluates its observations for ALL chains of its warp from one read of the constants (three 16-byte loads per
+//     observation whatever the number of chains) with 2 x chains independent exp chains in flight, and what is per chain --
+//     draws, proposal, prior, accept, moments, output rows -- belongs to a GROUP of 32/CPW lanes (group g = lane / GL owns chain
+//     g of the warp; its state sits in a per-chain shared-memory block);
+//   * the rate-law exponents are evaluated in units of ln2/256 from parameters scaled once per proposal, y = (A + (g cov - E)/kBT)
+//     * 256/ln2 as two FMAs; k = rint(y) and f = y - k (exact) by the 1.5 * 2^52 shift; exp = 2^(k>>8) T[k & 255] p(f) with a
+//     quartic p (truncation 4e-17); T comes from a table with one copy per lane (entry j of copy l at byte 256 j + 8 l of a
+//     64 KB block at shared address 65536: never a bank conflict, and the address is ONE byte permute of k and the lane's base);
+//     the entry's high word has (j << 12) subtracted so that adding (k << 12) applies 2^(k>>8) without isolating the exponent:
+//     8 fp64 + 3 other instructions per exp (the library's exp: ~45 + 25);
+//   * the residual uses cov w premultiplied: (y - sim) w = y w - (cov1 w) e1 - (cov2 w) e2, two FMAs;
+//   => 23 fp64 + ~8 other instructions per chain-observation (k_mh_warp's general path: 52 + ~30);
+//   * the chains are dealt to the SMs and, inside an SM, to the four sub-partitions as evenly as they go (4096 chains on 148 SMs:
+//     28 per SM, 7 per sub-partition as warps of 4 + 3 chains).
+// The per-chain sums of the lanes' partial sums are reduced with the butterfly of warp_sum, the first log2(CPW) levels
+// exchanging the other groups' partials: a chain's value does not depend on CPW or on which warp it landed in.
+// Values agree with the general path to a few ulp of the simulated response (log-posterior ~1e-14 relative).
+// ---------------------------------------------------------------------------------------------
+#define MHT_TAB_SA 65536u          // shared address of the exp table (64 KB: byte 1 of a lookup address is the table index)
+#define MHT_OBS_SA 131072u         // shared address of the staged observations
+template <int KT>
+struct MhtLayout {
+    using W = MhwLayout<KT>;
+    static constexpr int KPAD = W::KPAD;
+    // cur[KPAD] | th0[KPAD] | proposal[KPAD] | scaled proposal[KPAD] | draws[32][2] | modulation uniforms[4] | 'MAP_finding' state[6]
+    static constexpr int CDOUBLES = 4 * KPAD + 64 + 4 + 6;
+    static constexpr int O_PRP = 2 * KPAD, O_PRS = 3 * KPAD, O_DR = 4 * KPAD;
+};
+static inline size_t mht_smem_bytes(int n_total) { return (size_t)MHT_OBS_SA + 48u * (size_t)((n_total + 31) & ~31); }
+
+// exp of y * ln2/256 (header above); tab_lane = MHT_TAB_SA + 8 * lane
+__device__ __forceinline__ double mht_exp(const DevProblem& P, unsigned int tab_lane, double y) {
+    const double t = y + P.mathc3[4];
+    const double fn = t - P.mathc3[4];
+    const double f = y - fn;                                         // exact, |f| <= 1/2
+    const int k = __double2loint(t);
+    double Tb;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(Tb) : "r"(__byte_perm((unsigned int)k, tab_lane, 0x7604)));
+    const double T = __hiloint2double(__double2hiint(Tb) + (int)((unsigned int)k << 12), __double2loint(Tb));
+    double u = fma(f, P.mathc3[0], P.mathc3[1]);
+    u = fma(f, u, P.mathc3[2]);
+    u = fma(f, u, P.mathc3[3]);
+    return fma(T, f * u, T);
+}
+
+template <int KT, int CPW, int NW, int UNR, int MAXL = CPW>
+__global__ void __launch_bounds__(32 * NW, 1) k_mh_tpd(const __grid_constant__ DevProblem P, const __grid_constant__ DevMH M,
+                                                       const double* __restrict__ theta0, const MHOut out, int cpc) {
+    using L = MhtLayout<KT>;
+    constexpr int GL = 32 / CPW;
+    constexpr int NACC = (L::W::NSLOT + GL - 1) / GL;
+    constexpr int MODEL = PEUQSE_MODEL_TPD2SITE;
+    static_assert(KT >= 6 && KT <= GL && (CPW == 1 || CPW == 2 || CPW == 4), "a group of lanes holds one chain's parameters");
+    extern __shared__ double smem[];
+    __shared__ double s_ext[4];
+    __shared__ double s_rs[KT];                                  // 1 / scale of the fast prior
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int grp = lane / GL, gl = lane % GL;
+    const unsigned gmask = (CPW == 1) ? 0xffffffffu : (((1u << GL) - 1u) << (grp * GL));
+    const unsigned int sa0 = (unsigned int)__cvta_generic_to_shared(smem);
+    double* wbase = smem + (size_t)warp * CPW * L::CDOUBLES;
+    double* cur = wbase + grp * L::CDOUBLES;                     // this group's chain
+    double* th0s = cur + L::KPAD;
+    double* prp = cur + L::O_PRP;
+    double* prs = cur + L::O_PRS;
+    double2* dr = reinterpret_cast<double2*>(cur + L::O_DR);
+    double* dmod = reinterpret_cast<double*>(dr + 32);
+    MapFind* mf = reinterpret_cast<MapFind*>(dmod + 4);
+    ObsView O;
+    O.y = P.y; O.w = P.w; O.cval = P.cval; O.mc = P.mconst; O.tab = nullptr;         // general path: constants in global memory
+    const int n = P.n_total;
+    const int ngrp = (n + 31) >> 5;
+    {
+        // staged observations, in groups of 32: 32 x {y w, 1/kBT} | 32 x {cov1, cov2} | 32 x {cov1 w, cov2 w} (1536 bytes a group;
+        // a lane's three loads are 512 bytes apart and the lanes' 16 bytes are contiguous); zero rows pad the last group
+        double2* ob = reinterpret_cast<double2*>(reinterpret_cast<char*>(smem) + (MHT_OBS_SA - sa0));
+        double* tab = reinterpret_cast<double*>(reinterpret_cast<char*>(smem) + (MHT_TAB_SA - sa0));
+        double m0 = 0.0, m1 = 0.0, m2 = 0.0;
+        for (int i = threadIdx.x; i < 32 * ngrp; i += blockDim.x) {
+            double y = 0.0, w = 0.0, c1 = 0.0, c2 = 0.0, r = 0.0;
+            if (i < n) { y = P.y[i]; w = P.w[i]; c1 = P.mconst[n + i]; c2 = P.mconst[2 * n + i]; r = P.mconst[3 * n + i]; }
+            double2* g = ob + 96 * (i >> 5) + (i & 31);
+            g[0] = make_double2(y * w, r);
+            g[32] = make_double2(c1, c2);
+            g[64] = make_double2(c1 * w, c2 * w);
+            m0 = fmax(m0, fabs(r)); m1 = fmax(m1, fabs(c1)); m2 = fmax(m2, fabs(c2));
+        }
+        for (int e = threadIdx.x; e < 256 * 32; e += blockDim.x) {
+            const int j = e >> 5;
+            const double T = g_exp_tab2048[8 * j];               // 2^(j/256)
+            tab[e] = __hiloint2double(__double2hiint(T) - (j << 12), __double2loint(T));
+        }
+        if (threadIdx.x < 4) s_ext[threadIdx.x] = 0.0;
+        if (threadIdx.x < KT) s_rs[threadIdx.x] = (threadIdx.x < P.k && P.scaling_on) ? 1.0 / P.scale[threadIdx.x] : 1.0;
+        __syncthreads();
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            m0 = fmax(m0, __shfl_xor_sync(0xffffffffu, m0, o));
+            m1 = fmax(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+            m2 = fmax(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+        }
+        if (lane == 0) {                                         // non-negative doubles order like their bit patterns
+            atomicMax(reinterpret_cast<unsigned long long*>(&s_ext[0]), (unsigned long long)__double_as_longlong(m0));
+            atomicMax(reinterpret_cast<unsigned long long*>(&s_ext[1]), (unsigned long long)__double_as_longlong(m1));
+            atomicMax(reinterpret_cast<unsigned long long*>(&s_ext[2]), (unsigned long long)__double_as_longlong(m2));
+        }
+        __syncthreads();
+    }
+    // the CTA's cpc chains are dealt to its warps as evenly as they go (warp w sits on sub-partition w % 4: with cpc = 28 and
+    // eight warps every sub-partition gets 4 + 3 chains); a warp evaluates only the chains it has
+    const int wq = cpc / NW, wr = cpc % NW;
+    const int nlw = wq + (warp < wr ? 1 : 0);
+    const long long cbase = (long long)blockIdx.x * cpc + warp * wq + min(warp, wr);
+    if (nlw == 0 || cbase >= M.n_chains) return;
+    const long long C = M.n_chains;
+    const bool live = grp < nlw && cbase + grp < C;
+    const long long c = (cbase + grp < C) ? cbase + grp : C - 1;  // a group without a chain repeats one and stores nothing
+    const int k = P.k;
+
+    // log-likelihoods of the proposals in the chains' prs (scaled) / prp blocks; a lane returns its own group's.  `bad`: this
+    // group's proposal is outside the bound of the fast form.
+    auto loglik_all = [&](bool bad) -> double {
+        double pr[MAXL][6];
+#pragma unroll
+        for (int q = 0; q < MAXL; ++q) {
+            const double* pq = wbase + q * L::CDOUBLES + L::O_PRS;
+#pragma unroll
+            for (int d = 0; d < 6; ++d) pr[q][d] = pq[d];
+        }
+        const unsigned int tab_lane = MHT_TAB_SA + 8u * lane;
+        double part[CPW];
+#pragma unroll
+        for (int q = 0; q < CPW; ++q) part[q] = 0.0;
+        auto sweep = [&](auto nl) {
+            constexpr int NL = decltype(nl)::value;
+            const double2* po = reinterpret_cast<const double2*>(reinterpret_cast<const char*>(smem) + (MHT_OBS_SA - sa0)) + lane;
+            const double2* const po_end = po + 96 * ngrp;
+#pragma unroll UNR
+            for (; po < po_end; po += 96) {
+                const double2 yr = po[0], cv = po[32], cw = po[64];
+#pragma unroll
+                for (int q = 0; q < NL; ++q) {
+                    const double e1 = mht_exp(P, tab_lane, fma(fma(pr[q][4], cv.x, pr[q][0]), yr.y, pr[q][2]));
+                    const double e2 = mht_exp(P, tab_lane, fma(fma(pr[q][5], cv.y, pr[q][1]), yr.y, pr[q][3]));
+                    const double t = fma(-cw.y, e2, fma(-cw.x, e1, yr.x));   // (y - sim) * w
+                    part[q] = fma(t, t, part[q]);
+                }
+            }
+        };
+        // MAXL: the launcher deals at most MAXL chains to a warp (the wider sweeps are not compiled)
+        if (MAXL == CPW && (CPW == 1 || nlw == CPW)) sweep(std::integral_constant<int, CPW>());
+        else if (CPW > 2 && MAXL >= CPW - 1 && nlw == CPW - 1) sweep(std::integral_constant<int, (CPW > 2 ? CPW - 1 : 1)>());
+        else if (CPW > 2 && MAXL >= CPW - 2 && nlw == CPW - 2) sweep(std::integral_constant<int, (CPW > 2 ? CPW - 2 : 1)>());
+        else sweep(std::integral_constant<int, 1>());
+        double v;
+        if constexpr (CPW == 1) {
+            v = part[0];
+        } else if constexpr (CPW == 2) {
+            const bool hi = (lane & 16) != 0;
+            v = (hi ? part[1] : part[0]) + __shfl_xor_sync(0xffffffffu, hi ? part[0] : part[1], 16);
+        } else {
+            const bool hi = (lane & 16) != 0, h8 = (lane & 8) != 0;
+            const double a0 = (hi ? part[2] : part[0]) + __shfl_xor_sync(0xffffffffu, hi ? part[0] : part[2], 16);
+            const double a1 = (hi ? part[3] : part[1]) + __shfl_xor_sync(0xffffffffu, hi ? part[1] : part[3], 16);
+            v = (h8 ? a1 : a0) + __shfl_xor_sync(0xffffffffu, h8 ? a0 : a1, 8);
+        }
+#pragma unroll
+        for (int o = GL / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        const double total = -0.5 * (P.resp_c[0] + v);
+        double ll = (total != total) ? pq_neg_inf() : total;
+        const unsigned badm = __ballot_sync(0xffffffffu, bad);
+        if (badm) {                                              // practically never: the general, range-checked path, a chain at a time
+#pragma unroll 1
+            for (int q = 0; q < CPW; ++q) {
+                if ((badm >> (q * GL)) & 1u) {
+                    const double* pq = wbase + q * L::CDOUBLES + L::O_PRP;
+                    double th[KT];
+#pragma unroll
+                    for (int d = 0; d < KT; ++d) th[d] = pq[d];
+                    const double g = eval_loglik_warp_checked<MODEL, KT, 2>(P, O, th, nullptr, lane);
+                    if (grp == q) ll = g;
+                }
+            }
+        }
+        return ll;
+    };
+    // stores the proposal and its scaled form {-E1, -E2, A1, A2, g1, g2} * 256/ln2 (group leader); returns `bad`
+    auto put_proposal = [&](const double (&p)[KT]) -> bool {
+        const double sc = P.mathc3[5];
+        if (gl == 0) {
+#pragma unroll
+            for (int d = 0; d < KT; ++d) prp[d] = p[d];
+            prs[0] = -p[0] * sc; prs[1] = -p[1] * sc; prs[2] = p[2] * sc; prs[3] = p[3] * sc; prs[4] = p[4] * sc; prs[5] = p[5] * sc;
+        }
+        const double rkm = s_ext[0];
+        const double b1 = fabs(p[2]) + (fabs(p[4]) * s_ext[1] + fabs(p[0])) * rkm;
+        const double b2 = fabs(p[3]) + (fabs(p[5]) * s_ext[2] + fabs(p[1])) * rkm;
+        return !(fmax(b1, b2) < 700.0);
+    };
+
+    if (gl < KT) {
+        const double t0 = (gl < k) ? theta0[c * k + gl] : 0.0;
+        cur[gl] = t0; th0s[gl] = t0;
+    }
+    if (gl == 0) mf->init();
+    for (int e = gl; e < 68; e += GL) reinterpret_cast<double*>(dr)[e] = 0.0;
+    __syncwarp();
+    // accumulator slots of this lane (slot s of the chain lives in lane s % GL of its group)
+    int sa[NACC], sb[NACC];
+    double acc[NACC], va[NACC], vb[NACC];
+#pragma unroll
+    for (int q = 0; q < NACC; ++q) {
+        const int s = gl + GL * q;
+        int a = -1, b = -1;
+        if (s < L::W::NPAIR) {
+            int e = 0;
+            for (int d = 0; d < KT; ++d)
+                for (int d2 = d; d2 < KT; ++d2) { if (e == s) { a = d; b = d2; } ++e; }
+            if (a >= k || b >= k) a = -1;
+        } else if (s < L::W::NSLOT) {
+            a = s - L::W::NPAIR; b = -1;
+            if (a >= k) a = -1;
+        }
+        sa[q] = a; sb[q] = b; acc[q] = 0.0; va[q] = 0.0; vb[q] = (a >= 0 && b < 0) ? 1.0 : 0.0;
+    }
+    double nacc = 0.0, maplogp = pq_neg_inf(), maprow = -1.0, sumexp = 0.0, mapth = 0.0;
+    double cur_lp, cur_ll;
+    {
+        double th[KT];
+#pragma unroll
+        for (int d = 0; d < KT; ++d) th[d] = cur[d];
+        cur_lp = eval_prior<KT>(P, th);
+        const bool bad = put_proposal(th);
+        __syncwarp();
+        cur_ll = loglik_all(bad);
+    }
+    double cur_sum = cur_ll + cur_lp;
+    auto add_row = [&](long long row, double lp, double explp) {
+        if (lp > maplogp) {                                       // first maximum (IP.py:1925-1927)
+            maplogp = lp; maprow = (double)row;
+            if (gl < KT) mapth = cur[gl];
+        }
+        sumexp += explp;
+#pragma unroll
+        for (int q = 0; q < NACC; ++q) acc[q] = fma(va[q], vb[q], acc[q]);   // first moments: fma(dd, 1, s1) == s1 + dd
+    };
+    {
+        const double lp0 = combine_logp(cur_lp, cur_ll);
+        if (live) {
+            if (out.samples && gl < k) out.samples[c * k + gl] = cur[gl];
+            if (gl == 0) {
+                if (out.logp) out.logp[c] = lp0;
+                if (out.lprior) out.lprior[c] = 0.0;
+                if (out.llik) out.llik[c] = 0.0;
+            }
+        }
+        if (M.burn_in <= 0) add_row(0, lp0, exp(lp0));
+    }
+    double cur_exp = exp(cur_sum);
+    long long next_row = 1;
+    int until_row = M.thin;
+    const bool fast_prior = P.prior_mode == PEUQSE_PRIOR_DIAG && P.prior_identity && P.kp == k;
+    const int sub = lane >> 3, blk = lane & 7;
+    for (long long i = 1; i < M.n_steps; ++i) {
+        const int g = (int)((i - 1) & 3);
+        if (g == 0) {                                             // the draws of the next four steps, a chain at a time
+            const unsigned long long step = (unsigned long long)(M.first_step + i + sub);
+            __syncwarp();
+#pragma unroll 1
+            for (int q = 0; q < nlw; ++q) {
+                const long long cq = (cbase + q < C) ? cbase + q : C - 1;
+                double um = 0.0;
+                const double2 d2 = mhw_draw(M.seed, (unsigned long long)(M.chain_offset + cq), step, blk, k, &um);
+                double* bq = wbase + q * L::CDOUBLES + L::O_DR;
+                reinterpret_cast<double2*>(bq)[lane] = d2;
+                if (blk == 7) bq[64 + sub] = um;
+            }
+            __syncwarp();
+        }
+        double lp_p;
+        bool bad;
+        {
+            double z[KT], delta[KT], prop[KT];
+#pragma unroll
+            for (int j = 0; j < (KT + 1) / 2; ++j) {
+                const double2 zz = dr[g * 8 + (j < 7 ? j : 0)];
+                z[2 * j] = zz.x;
+                if (2 * j + 1 < KT) z[2 * j + 1] = zz.y;
+            }
+            make_delta<KT>(M, z, delta);
+            const double mod = dmod[g] + 0.5;                     // IP.py:2633
+            if (M.map_finding) {
+                const double sc = mf->scale(mod);
+#pragma unroll
+                for (int d = 0; d < KT; ++d) delta[d] = sc * delta[d];
+            }
+#pragma unroll
+            for (int d = 0; d < KT; ++d) prop[d] = cur[d] + delta[d]; // IP.py:2630
+            bad = put_proposal(prop);
+            if (gl == 0) {
+                if (live && out.deltas) {
+#pragma unroll
+                    for (int d = 0; d < KT; ++d) if (d < k) out.deltas[((i - 1) * C + c) * k + d] = delta[d];
+                }
+                if (live && out.us) {
+                    const double u = dr[g * 8 + 7].x;
+                    if (M.map_finding) { out.us[((i - 1) * C + c) * 2] = u; out.us[((i - 1) * C + c) * 2 + 1] = mod; }
+                    else out.us[(i - 1) * C + c] = u;
+                }
+            }
+            if (fast_prior) {
+                // diagonal prior in natural order: theta / scale as a multiplication by the reciprocal (the log-prior moves in its
+                // last digit; the fast form's budget is 1e-12)
+                bool ok = true;
+                double q0 = 0.0, q1 = 0.0;
+#pragma unroll
+                for (int d = 0; d < KT; ++d) {
+                    if (d < k) {
+                        if (P.has_ub) ok = ok && (prop[d] <= P.ub[d]);
+                        if (P.has_lb) ok = ok && (prop[d] >= P.lb[d]);
+                        const double t = (prop[d] * s_rs[d] - P.mus[d]) * P.pw[d];
+                        if (d & 1) q1 = fma(t, t, q1); else q0 = fma(t, t, q0);
+                    }
+                }
+                lp_p = ok ? -0.5 * (P.prior_c + (q0 + q1)) : pq_neg_inf();
+            } else {
+                lp_p = mhw_prior<KT>(P, prop);
+            }
+        }
+        __syncwarp();
+        const double ll_p = loglik_all(bad);
+        const double sum_p = ll_p + lp_p;
+        double la = sum_p - cur_sum;                              // IP.py:2641
+        if (M.modulate != 0.0) la = (1.0 / M.modulate) * la;      // IP.py:2649
+        const bool accept = la > dr[g * 8 + 7].y;                 // IP.py:2651-2652; NaN -> reject
+        if (accept) {                                             // the same in every lane of the group
+            cur_lp = lp_p; cur_ll = ll_p; cur_sum = sum_p;
+            cur_exp = mhw_exp(cur_sum);
+            nacc += 1.0;
+            if (gl < KT) cur[gl] = prp[gl];
+            __syncwarp(gmask);
+#pragma unroll
+            for (int q = 0; q < NACC; ++q) {
+                if (sa[q] >= 0) {
+                    va[q] = cur[sa[q]] - th0s[sa[q]];
+                    if (sb[q] >= 0) vb[q] = cur[sb[q]] - th0s[sb[q]];
+                }
+            }
+        }
+        if (M.map_finding) {
+            if (gl == 0) mf->after_step(i, dmod[g] + 0.5, sum_p);
+        }
+        __syncwarp();
+        if (--until_row == 0) {
+            until_row = M.thin;
+            const long long row = next_row++;
+            if (live) {
+                if (out.samples && gl < k) out.samples[(row * C + c) * k + gl] = cur[gl];
+                if (gl == 0) {
+                    if (out.logp) out.logp[row * C + c] = cur_sum;      // IP.py:2661, 2673
+                    if (out.lprior) out.lprior[row * C + c] = cur_lp;
+                    if (out.llik) out.llik[row * C + c] = cur_ll;
+                }
+            }
+        }
+        if (i >= M.burn_in) add_row(i, cur_sum, cur_exp);
+    }
+    if (!live) return;
+    double* so = out.stats + c * PEUQSE_MH_STAT_DOUBLES(k);
+    if (gl == 0) {
+        so[PEUQSE_MH_STAT_NACC] = nacc;
+        so[PEUQSE_MH_STAT_MAPLOGP] = maplogp;
+        so[PEUQSE_MH_STAT_MAPROW] = maprow;
+        so[PEUQSE_MH_STAT_LASTLOGP] = cur_sum;
+        so[PEUQSE_MH_STAT_SUMEXP] = sumexp;
+        so[PEUQSE_MH_STAT_DYN(k)] = mf->dyn;
+    }
+    if (gl < k) {
+        so[PEUQSE_MH_STAT_MAPTHETA + gl] = mapth;
+        so[PEUQSE_MH_STAT_LAST(k) + gl] = cur[gl];
+    }
+#pragma unroll
+    for (int q = 0; q < NACC; ++q) {
+        if (sa[q] >= 0) {
+            if (sb[q] >= 0) {
+                so[PEUQSE_MH_STAT_S2(k) + sa[q] * k + sb[q]] = acc[q];
+                so[PEUQSE_MH_STAT_S2(k) + sb[q] * k + sa[q]] = acc[q];
+            } else {
+                so[PEUQSE_MH_STAT_S1(k) + sa[q]] = acc[q];
+            }
+        }
+    }
+}
+
 namespace {
 // tuning override for the shape crossover (profiles/mh_variants.py): PEUQSE_MH_FEW_CHAINS=<n>
 long long mh_few_chains() {
@@ -636,8 +1036,8 @@ int launch_mh(const peuqse_problem* p, const DevMH& M, const double* th0, const 
             // grows with the resident warps: the SM is throughput-bound).
             const bool fast_ok = use_smem && p->d.n_resp == 1 && p->d.resp_mode[0] == PEUQSE_RESP_MVN_DIAG && !p->d.any_per_value;
             if (fast_ok) {
-                static int forced = -1;
-                if (forced < 0) { const char* e = getenv("PEUQSE_MH_SHAPE"); forced = e ? atoi(e) : 0; }
+                const char* fe = getenv("PEUQSE_MH_SHAPE");        // tuning override (profiles/c3_variants.sh)
+                const int forced = fe ? atoi(fe) : 0;
                 const int shapes[3][2] = {{4, 3}, {7, 2}, {8, 2}};
                 int best = 0;
                 double best_cost = 1e300;
@@ -651,6 +1051,27 @@ int launch_mh(const peuqse_problem* p, const DevMH& M, const double* th0, const 
                 if (best == 0) kern = k_mh_warp<MODEL, KT, 2, 1, false, 3, false, true, 4>;
                 if (best == 1) kern = k_mh_warp<MODEL, KT, 2, 1, false, 2, false, true, 7>;
                 if (best == 2) kern = k_mh_warp<MODEL, KT, 2, 1, false, 2, false, true, 8>;
+                if constexpr (KT <= 8) {
+                    // many chains (k_mh_tpd): ONE CTA per SM, the chains dealt evenly to the SMs and their sub-partitions.
+                    // 4: up to four chains per warp, 8 warps; 5: up to two, 16 warps; 7: one chain per warp, 12 warps
+                    if (forced >= 4 && forced <= 9 && mht_smem_bytes(p->d.n_total) <= (size_t)p->max_smem_optin) {
+                        void (*tk)(const DevProblem, const DevMH, const double*, const MHOut, int) = k_mh_tpd<KT, 4, 8, 1>;
+                        int tnw = 8, maxl = 4;
+                        if (forced == 5) { tk = k_mh_tpd<KT, 2, 16, 1>; tnw = 16; maxl = 2; }
+                        if (forced == 7) { tk = k_mh_tpd<KT, 1, 12, 2>; tnw = 12; maxl = 1; }
+                        if (forced == 8) { tk = k_mh_tpd<KT, 4, 12, 1, 3>; tnw = 12; maxl = 3; }
+                        const long long cap = (long long)tnw * maxl;
+                        const long long slots = (long long)p->sm_count;
+                        const long long waves = (M.n_chains + cap * slots - 1) / (cap * slots);
+                        const long long ctas0 = waves * slots;
+                        const int cpc = (int)((M.n_chains + ctas0 - 1) / ctas0);
+                        const size_t tsmem = mht_smem_bytes(p->d.n_total);
+                        PQ_CUDA_OK(pq_allow_smem((const void*)tk, tsmem));
+                        tk<<<(unsigned)((M.n_chains + cpc - 1) / cpc), 32 * tnw, tsmem, st>>>(p->d, M, th0, out, cpc);
+                        PQ_CUDA_OK(cudaGetLastError());
+                        return PEUQSE_OK;
+                    }
+                }
             }
         }
         const size_t wsmem = smem + (size_t)nw * MhwLayout<KT>::WDOUBLES * sizeof(double);

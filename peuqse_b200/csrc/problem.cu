@@ -256,6 +256,42 @@ __global__ void __launch_bounds__(256) k_bench_fp64(int iters, int mode, double 
     if (s == 123.456) out[0] = s;    // keep the chains alive
 }
 
+// issue-mix probe: 8 independent DFMA chains per thread with NI integer instructions (IMAD / LOP3 chains on their own
+// registers) and NL shared-memory loads (8 bytes, conflict-free) per 8 DFMAs; result = DFMA instructions/s.  Answers whether the
+// half-rate fp64 pipe leaves issue slots for the other pipes (config C3's loop issues 17 non-fp64 per 28 fp64 instructions).
+template <int NI, int NL>
+__global__ void __launch_bounds__(256) k_bench_fp64_mix(int iters, double seed, double* __restrict__ out) {
+    __shared__ double sh[512];
+    sh[threadIdx.x] = seed; sh[threadIdx.x + 256] = seed;
+    __syncthreads();
+    double a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = seed + threadIdx.x * 1e-9 + j;
+    const double m = 1.0000000001, c = 1e-12;
+    unsigned x[4] = {threadIdx.x, threadIdx.x + 1u, threadIdx.x + 2u, threadIdx.x + 3u};
+    double ld = 0.0;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            a[j] = fma(a[j], m, c);
+            if (j * NI / 8 != (j + 1) * NI / 8) {
+#pragma unroll
+                for (int q = j * NI / 8; q < (j + 1) * NI / 8; ++q)
+                    x[q & 3] = (q & 1) ? ((x[q & 3] ^ x[(q + 1) & 3]) & 0x7fffffffu) : x[q & 3] * 1664525u + 1013904223u;
+            }
+            if (j * NL / 8 != (j + 1) * NL / 8) {
+#pragma unroll
+                for (int q = j * NL / 8; q < (j + 1) * NL / 8; ++q)
+                    ld += sh[(threadIdx.x + 32 * q + (x[0] & 0x100u)) & 511];
+            }
+        }
+    }
+    double s = ld + (double)(x[0] ^ x[1] ^ x[2] ^ x[3]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += a[j];
+    if (s == 123.456) out[0] = s;    // keep the chains alive
+}
+
 // DMMA probe: every warp issues rounds of NACC independent mma.sync.m8n8k4.f64 accumulations from registers only (no shared
 // memory, no loads): the ceiling for the dense-covariance contraction (csrc/fullcov.cu).  256 FMA = 512 flop per instruction.
 template <int NACC>
@@ -398,6 +434,28 @@ extern "C" int peuqse_bench_fp64(int32_t mode, double* instr_per_s, double* d_sc
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
         *instr_per_s = (double)nb * 8.0 * it * 16.0 * 512.0 / (ms * 1e-3);
+        return PEUQSE_OK;
+    }
+    if (mode >= 20 && mode <= 25) {   // issue mix: DFMA with 4 / 8 / 16 integer instructions or 2 / 4 shared loads per 8 DFMAs
+        const int nb = prop.multiProcessorCount * 8, it = 10000;
+        auto run = [&](int n_it) {
+            if (mode == 20) k_bench_fp64_mix<4, 0><<<nb, 256, 0, st>>>(n_it, 1.0, d_scratch);
+            else if (mode == 21) k_bench_fp64_mix<8, 0><<<nb, 256, 0, st>>>(n_it, 1.0, d_scratch);
+            else if (mode == 22) k_bench_fp64_mix<16, 0><<<nb, 256, 0, st>>>(n_it, 1.0, d_scratch);
+            else if (mode == 23) k_bench_fp64_mix<0, 2><<<nb, 256, 0, st>>>(n_it, 1.0, d_scratch);
+            else if (mode == 24) k_bench_fp64_mix<0, 4><<<nb, 256, 0, st>>>(n_it, 1.0, d_scratch);
+            else k_bench_fp64_mix<5, 2><<<nb, 256, 0, st>>>(n_it, 1.0, d_scratch);
+        };
+        run(100);
+        PQ_CUDA_OK(cudaEventRecord(e0, st));
+        run(it);
+        PQ_CUDA_OK(cudaEventRecord(e1, st));
+        PQ_CUDA_OK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        PQ_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        *instr_per_s = (double)nb * 256.0 * it * 8.0 / (ms * 1e-3);
         return PEUQSE_OK;
     }
     if (mode >= 10) {   // 10 + log2(chains): dependent-chain probe, one warp per scheduler; result = DFMA/s of the device

@@ -19,4 +19,8 @@ for m in (0, 1):
     r = C.c_double()
     _lib.check(L.peuqse_bench_fp64(m, C.byref(r), C.c_void_p(scratch.data_ptr()), None))
     out[f"mode{m}_full_occupancy_instr_per_s"] = r.value
+for m, name in ((20, "4_int"), (21, "8_int"), (22, "16_int"), (23, "2_lds"), (24, "4_lds"), (25, "5_int_2_lds")):
+    r = C.c_double()
+    _lib.check(L.peuqse_bench_fp64(m, C.byref(r), C.c_void_p(scratch.data_ptr()), None))
+    out[f"dfma_per_s_with_{name}_per_8_dfma"] = r.value
 print(json.dumps(out, indent=1))

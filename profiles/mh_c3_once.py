@@ -21,7 +21,9 @@ UI.model['simulateByInputParametersOnlyFunction'] = PEUQSE.Tpd2SiteModel.linear_
 PE = PEUQSE.parameter_estimation(UI)
 C, Lm = 4096, int(sys.argv[1]) if len(sys.argv) > 1 else 200
 th0 = np.tile(truth, (C, 1))
-for _ in range(2):
+# PEUQSE_MH_SHAPES="1 7": one launch per listed CTA shape (see launch_mh) after a warm-up launch
+for shape in os.environ.get('PEUQSE_MH_SHAPES', '0 0').split():
+    os.environ['PEUQSE_MH_SHAPE'] = shape
     st = mh_launch(PE, th0, Lm, 20, 0, step_cholesky(PE.Q_covmat, 1e-5), store_samples=False)
 torch.cuda.synchronize()
 print("accept", float(st['stats'][:, 0].mean()) / (Lm - 1))
