@@ -296,15 +296,8 @@ __device__ __noinline__ double mhw_prior(const DevProblem& P, const double (&th)
 // the values are bit-identical to k_mh's, and what the warp buys is latency -- draws for four steps per pass and
 // lane-spread moments cut a chain step from ~4000 to a few hundred cycles when there are too few chains to fill
 // the machine with one thread each.
-// FAST (two-site rate-law model, one response with diagonal covariance, constants staged; config C3): the observation loop
-// is the kernel's own -- per observation {y w, w}, {cov1, cov2} and 1/kBT come from shared memory as two 16-byte and one
-// 8-byte load, the exponent of each site is two FMAs, the exp is table-driven (eval.cuh: pq_exp_tab), site sum, residual and
-// square are three FMAs: 28 fp64 instructions per observation where the general path issues 52.  The arguments of all exps
-// of a proposal are bounded ONCE from the extrema of the constants; a proposal beyond the bound (practically never) goes
-// through the general, range-checked path on the constants in global memory.  Values agree with the general path to a few
-// ulp of the simulated response (log-posterior ~1e-15 relative; accept / reject sequences of the tests are unchanged).
-template <int MODEL, int KT, int U, int SMEM, bool TEVAL = false, int MINB = 4, bool SCEN = false, bool FAST = false, int NW = MHW_WARPS>
-__global__ void __launch_bounds__(32 * NW, MINB) k_mh_warp(const __grid_constant__ DevProblem P,
+template <int MODEL, int KT, int U, int SMEM, bool TEVAL = false, int MINB = 4, bool SCEN = false>
+__global__ void __launch_bounds__(32 * MHW_WARPS, MINB) k_mh_warp(const __grid_constant__ DevProblem P,
                                                                const __grid_constant__ DevMH M,
                                                                const double* __restrict__ theta0, const MHOut out,
                                                                int use_smem, const DevScen SC) {
@@ -317,77 +310,17 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_mh_warp(const __grid_constant
     double2* dr = reinterpret_cast<double2*>(prp + L::KPAD);
     double* dmod = reinterpret_cast<double*>(dr + 32);
     MapFind* mf = reinterpret_cast<MapFind*>(dmod + 4);
-    __shared__ double s_rs[KT];                                  // 1 / scale of the fast prior
     ObsView O;
-    __shared__ double s_exp_tab[FAST ? 64 : 1];
-    __shared__ double s_ext[4];
-    if constexpr (FAST) {
-        static_assert(MODEL == PEUQSE_MODEL_TPD2SITE && !TEVAL && !SCEN && KT >= 6, "FAST is the two-site rate-law shape");
-        O.y = P.y; O.w = P.w; O.cval = P.cval; O.mc = P.mconst; O.tab = nullptr;     // general path: constants in global memory
-        const int n = P.n_total;
-        double2* yw = reinterpret_cast<double2*>(smem + NW * L::WDOUBLES);
-        double2* cc = yw + n;
-        double* rk = reinterpret_cast<double*>(cc + n);
-        double m0 = 0.0, m1 = 0.0, m2 = 0.0;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            const double y = P.y[i], w = P.w[i], c1 = P.mconst[n + i], c2 = P.mconst[2 * n + i], r = P.mconst[3 * n + i];
-            yw[i] = make_double2(y * w, w);
-            cc[i] = make_double2(c1, c2);
-            rk[i] = r;
-            m0 = fmax(m0, fabs(r)); m1 = fmax(m1, fabs(c1)); m2 = fmax(m2, fabs(c2));
-        }
-        if (threadIdx.x < 64) s_exp_tab[threadIdx.x] = c_exp_tab64[threadIdx.x];
-        if (threadIdx.x < 4) s_ext[threadIdx.x] = 0.0;
-        if (threadIdx.x < KT) s_rs[threadIdx.x] = (threadIdx.x < P.k && P.scaling_on) ? 1.0 / P.scale[threadIdx.x] : 1.0;
-        __syncthreads();
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            m0 = fmax(m0, __shfl_xor_sync(0xffffffffu, m0, o));
-            m1 = fmax(m1, __shfl_xor_sync(0xffffffffu, m1, o));
-            m2 = fmax(m2, __shfl_xor_sync(0xffffffffu, m2, o));
-        }
-        if (lane == 0) {                                         // non-negative doubles order like their bit patterns
-            atomicMax(reinterpret_cast<unsigned long long*>(&s_ext[0]), (unsigned long long)__double_as_longlong(m0));
-            atomicMax(reinterpret_cast<unsigned long long*>(&s_ext[1]), (unsigned long long)__double_as_longlong(m1));
-            atomicMax(reinterpret_cast<unsigned long long*>(&s_ext[2]), (unsigned long long)__double_as_longlong(m2));
-        }
-        __syncthreads();
-    } else {
-        O = stage_obs<SMEM>(P, smem + NW * L::WDOUBLES, use_smem);
-    }
+    O = stage_obs<SMEM>(P, smem + MHW_WARPS * L::WDOUBLES, use_smem);
     // log-likelihood of a parameter vector (every lane ends with the same value)
     auto loglik = [&](const double (&p)[KT]) -> double {
         if constexpr (TEVAL) {
             return eval_loglik_thread<MODEL, KT>(P, O, p, nullptr);
-        } else if constexpr (FAST) {
-            const double rkm = s_ext[0];
-            const double b1 = fabs(p[2]) + (fabs(p[4]) * s_ext[1] + fabs(p[0])) * rkm;
-            const double b2 = fabs(p[3]) + (fabs(p[5]) * s_ext[2] + fabs(p[1])) * rkm;
-            if (!(fmax(b1, b2) < 700.0)) return eval_loglik_warp_checked<MODEL, KT, 2>(P, O, p, nullptr, lane);   // a call, not inlined
-            const double E1 = -p[0], E2 = -p[1], A1 = p[2], A2 = p[3], g1 = p[4], g2 = p[5];
-            const int n = P.n_total;
-            // the staged constants, addressed from the shared-memory array itself (LDS with immediate offsets, no generic loads)
-            const double2* f_yw = reinterpret_cast<const double2*>(smem + NW * L::WDOUBLES);
-            const double2* f_cc = f_yw + n;
-            const double* f_rk = reinterpret_cast<const double*>(f_cc + n);
-            double part = 0.0;
-#pragma unroll 2
-            for (int j = lane; j < n; j += 32) {
-                const double2 yw = f_yw[j], c = f_cc[j];
-                const double r = f_rk[j];
-                const double e1 = pq_exp_tab_bounded(P, s_exp_tab, fma(fma(g1, c.x, E1), r, A1));
-                const double e2 = pq_exp_tab_bounded(P, s_exp_tab, fma(fma(g2, c.y, E2), r, A2));
-                const double s = fma(c.y, e2, c.x * e1);
-                const double t = fma(-s, yw.y, yw.x);           // (y - sim) * w
-                part = fma(t, t, part);
-            }
-            const double total = -0.5 * (P.resp_c[0] + warp_sum(part));
-            return (total != total) ? pq_neg_inf() : total;
         } else {
             return eval_loglik_warp<MODEL, KT, U>(P, O, p, nullptr, lane);
         }
     };
-    const long long c = (long long)blockIdx.x * NW + warp;
+    const long long c = (long long)blockIdx.x * MHW_WARPS + warp;
     if (c >= M.n_chains) return;
     const int k = P.k;
     const long long C = M.n_chains;
@@ -457,7 +390,6 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_mh_warp(const __grid_constant
     double cur_exp = exp(cur_sum);
     long long next_row = 1;
     int until_row = M.thin;
-    const bool fast_prior = FAST && P.prior_mode == PEUQSE_PRIOR_DIAG && P.prior_identity && P.kp == k;
     const int sub = lane >> 3, blk = lane & 7;
     for (long long i = 1; i < M.n_steps; ++i) {
         const int g = (int)((i - 1) & 3);
@@ -499,25 +431,7 @@ __global__ void __launch_bounds__(32 * NW, MINB) k_mh_warp(const __grid_constant
                 else out.us[(i - 1) * C + c] = uu.x;
             }
         }
-        double lp_p;
-        if (FAST && fast_prior) {
-            // diagonal prior in natural order: theta / scale as a multiplication by the reciprocal (the log-prior moves in its
-            // last digit; the fast form's budget is 1e-12)
-            bool ok = true;
-            double q0 = 0.0, q1 = 0.0;
-#pragma unroll
-            for (int d = 0; d < KT; ++d) {
-                if (d < k) {
-                    if (P.has_ub) ok = ok && (prop[d] <= P.ub[d]);
-                    if (P.has_lb) ok = ok && (prop[d] >= P.lb[d]);
-                    const double t = (prop[d] * s_rs[d] - P.mus[d]) * P.pw[d];
-                    if (d & 1) q1 = fma(t, t, q1); else q0 = fma(t, t, q0);
-                }
-            }
-            lp_p = ok ? -0.5 * (P.prior_c + (q0 + q1)) : pq_neg_inf();
-        } else {
-            lp_p = FAST ? mhw_prior<KT>(P, prop) : eval_prior<KT>(P, prop);
-        }
+        const double lp_p = eval_prior<KT>(P, prop);
         const double ll_p = loglik(prop);
         const double sum_p = ll_p + lp_p;
         double la = sum_p - cur_sum;                              // IP.py:2641
@@ -1027,53 +941,36 @@ int launch_mh(const peuqse_problem* p, const DevMH& M, const double* th0, const 
         if (p->d.n_total <= PQ_THREAD_SHAPE_MAX_N) kern = k_mh_warp<MODEL, KT, 2, -1, true>;
         // 3 CTAs (12 chains) per SM at 168 registers: the 4-CTA shape spills inside the observation loop and is 8 % slower
         else if (use_smem) kern = k_mh_warp<MODEL, KT, 2, 1, false, 3>;
-        int nw = MHW_WARPS;
-        if constexpr (MODEL == PEUQSE_MODEL_TPD2SITE) {
-            // the fast rate-law shape (see k_mh_warp).  A chain occupies its warp for the whole run, so the launch is a
-            // sequence of WAVES of (resident warps per SM) x (SMs) chains and a partly filled last wave is lost time (4096
-            // chains on 148 SMs at 12 warps per SM: 2.31 -> 3 waves).  Among the compiled shapes -- 3 CTAs of 4 warps, 2 CTAs
-            // of 7 warps, 2 CTAs of 8 warps -- take the one with the smallest waves x warps-per-SM product (time per wave
-            // grows with the resident warps: the SM is throughput-bound).
-            const bool fast_ok = use_smem && p->d.n_resp == 1 && p->d.resp_mode[0] == PEUQSE_RESP_MVN_DIAG && !p->d.any_per_value;
-            if (fast_ok) {
-                const char* fe = getenv("PEUQSE_MH_SHAPE");        // tuning override (profiles/c3_variants.sh)
-                const int forced = fe ? atoi(fe) : 0;
-                const int shapes[3][2] = {{4, 3}, {7, 2}, {8, 2}};
-                int best = 0;
-                double best_cost = 1e300;
-                for (int q = 0; q < 3; ++q) {
-                    const long long per_wave = (long long)p->sm_count * shapes[q][0] * shapes[q][1];
-                    const double cost = (double)((M.n_chains + per_wave - 1) / per_wave) * shapes[q][0] * shapes[q][1];
-                    if (cost < best_cost - 1e-9) { best_cost = cost; best = q; }
-                }
-                if (forced >= 1 && forced <= 3) best = forced - 1;
-                nw = shapes[best][0];
-                if (best == 0) kern = k_mh_warp<MODEL, KT, 2, 1, false, 3, false, true, 4>;
-                if (best == 1) kern = k_mh_warp<MODEL, KT, 2, 1, false, 2, false, true, 7>;
-                if (best == 2) kern = k_mh_warp<MODEL, KT, 2, 1, false, 2, false, true, 8>;
-                if constexpr (KT <= 8) {
-                    // many chains (k_mh_tpd): ONE CTA per SM, the chains dealt evenly to the SMs and their sub-partitions.
-                    // 4: up to four chains per warp, 8 warps; 5: up to two, 16 warps; 7: one chain per warp, 12 warps
-                    if (forced >= 4 && forced <= 9 && mht_smem_bytes(p->d.n_total) <= (size_t)p->max_smem_optin) {
-                        void (*tk)(const DevProblem, const DevMH, const double*, const MHOut, int) = k_mh_tpd<KT, 4, 8, 1>;
-                        int tnw = 8, maxl = 4;
-                        if (forced == 5) { tk = k_mh_tpd<KT, 2, 16, 1>; tnw = 16; maxl = 2; }
-                        if (forced == 7) { tk = k_mh_tpd<KT, 1, 12, 2>; tnw = 12; maxl = 1; }
-                        if (forced == 8) { tk = k_mh_tpd<KT, 4, 12, 1, 3>; tnw = 12; maxl = 3; }
-                        const long long cap = (long long)tnw * maxl;
-                        const long long slots = (long long)p->sm_count;
-                        const long long waves = (M.n_chains + cap * slots - 1) / (cap * slots);
-                        const long long ctas0 = waves * slots;
-                        const int cpc = (int)((M.n_chains + ctas0 - 1) / ctas0);
-                        const size_t tsmem = mht_smem_bytes(p->d.n_total);
-                        PQ_CUDA_OK(pq_allow_smem((const void*)tk, tsmem));
-                        tk<<<(unsigned)((M.n_chains + cpc - 1) / cpc), 32 * tnw, tsmem, st>>>(p->d, M, th0, out, cpc);
-                        PQ_CUDA_OK(cudaGetLastError());
-                        return PEUQSE_OK;
-                    }
-                }
+        if constexpr (MODEL == PEUQSE_MODEL_TPD2SITE && KT <= 8) {
+            // the rate-law model with one diagonal-covariance response (config C3): k_mh_tpd, ONE CTA per SM, the chains dealt evenly to
+            // the SMs and their sub-partitions.  Up to 12 chains per SM: a warp each (12 warps); more: up to four chains per warp
+            // (8 warps) -- measured on 256 ... 16384 chains (profiles/c3_shapes_sweep.py).  PEUQSE_MH_SHAPE=4|5|7|8 forces a shape,
+            // 1 the general kernel.
+            const bool fast_ok = p->d.n_total > PQ_THREAD_SHAPE_MAX_N && p->d.n_resp == 1 && p->d.resp_mode[0] == PEUQSE_RESP_MVN_DIAG &&
+                                 !p->d.any_per_value &&
+                                 mht_smem_bytes(p->d.n_total) <= (size_t)p->max_smem_optin;
+            const char* fe = getenv("PEUQSE_MH_SHAPE");
+            int shape = fe ? atoi(fe) : 0;
+            if (shape == 0) shape = (M.n_chains <= 12LL * p->sm_count) ? 7 : 4;
+            if (fast_ok && shape >= 4) {
+                void (*tk)(const DevProblem, const DevMH, const double*, const MHOut, int) = k_mh_tpd<KT, 4, 8, 1>;
+                int tnw = 8, maxl = 4;
+                if (shape == 5) { tk = k_mh_tpd<KT, 2, 16, 1>; tnw = 16; maxl = 2; }
+                if (shape == 7) { tk = k_mh_tpd<KT, 1, 12, 2>; tnw = 12; maxl = 1; }
+                if (shape == 8) { tk = k_mh_tpd<KT, 4, 12, 1, 3>; tnw = 12; maxl = 3; }
+                const long long cap = (long long)tnw * maxl;
+                const long long slots = (long long)p->sm_count;
+                const long long waves = (M.n_chains + cap * slots - 1) / (cap * slots);
+                const long long ctas0 = waves * slots;
+                const int cpc = (int)((M.n_chains + ctas0 - 1) / ctas0);
+                const size_t tsmem = mht_smem_bytes(p->d.n_total);
+                PQ_CUDA_OK(pq_allow_smem((const void*)tk, tsmem));
+                tk<<<(unsigned)((M.n_chains + cpc - 1) / cpc), 32 * tnw, tsmem, st>>>(p->d, M, th0, out, cpc);
+                PQ_CUDA_OK(cudaGetLastError());
+                return PEUQSE_OK;
             }
         }
+        const int nw = MHW_WARPS;
         const size_t wsmem = smem + (size_t)nw * MhwLayout<KT>::WDOUBLES * sizeof(double);
         PQ_CUDA_OK(pq_allow_smem((const void*)kern, wsmem));
         const long long blocks = (M.n_chains + nw - 1) / nw;

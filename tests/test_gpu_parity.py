@@ -1307,6 +1307,50 @@ def test_c3_benched_shape_in_kernel_statistics_vs_oracle(env, golden):
 
 
 @pytest.mark.gpu
+def test_c3_many_chain_kernel_shapes_agree(env, golden, monkeypatch):
+    """k_mh_tpd (config C3: rate-law model, one diagonal response) deals up to four chains to a warp, the chains of an SM evenly to
+    its sub-partitions.  A chain's trajectory must not depend on the dealing: 4100 chains (warps of 4 + 3 chains, a last CTA
+    that is not full) x 40 steps on 160 observations (not a multiple of the 32 a warp strides over) through every compiled shape
+    give bit-identical rows, draws and statistics, and agree with the general kernel k_mh_warp (library exp, other summation
+    grouping): same accept / reject decisions, log-posteriors to 1e-12."""
+    PEUQSE, orc, _, torch = env
+    from peuqse_b200 import _lib
+    from peuqse_b200.mcmc import mh_launch, step_cholesky
+    n, L, C, burn, k = 160, 40, 4100, 5, 6
+    kBT, c1, c2 = orc.tpd2site_constants(n)
+    truth = np.array([41.5, 45, 13, 13, 0.1, 0.1])
+    sim_t = orc.sim_tpd2site(kBT, c1, c2)[0](truth)
+    sig = 0.02 * np.max(sim_t)
+    y = sim_t + sig * np.random.default_rng(3).standard_normal(n)
+    sd = np.array([20, 20, 13, 13, 0.1, 0.1])
+    PE = make_pe(PEUQSE, PEUQSE.Tpd2SiteModel.linear_ramp(n), list(y), list(np.full(n, sig)), [41.5, 41.5, 13.0, 13.0, 0.1, 0.1], list(sd))
+    start = truth + 5e-4 * sd * np.random.default_rng(4).standard_normal((C, k))
+    chol = step_cholesky(PE.Q_covmat, 2e-5)
+    runs = {}
+    for shape in (1, 4, 5, 7, 8):
+        monkeypatch.setenv("PEUQSE_MH_SHAPE", str(shape))
+        runs[shape] = mh_launch(PE, start, L, burn, 9, chol, thin=2, export_draws=True, chain_offset=77)
+    monkeypatch.delenv("PEUQSE_MH_SHAPE")
+    ref = runs[4]
+    for shape in (5, 7, 8):
+        for key in ('samples', 'logp', 'logprior', 'loglik', 'deltas', 'us', 'stats'):
+            assert torch.equal(ref[key], runs[shape][key]), (shape, key)
+    gen = runs[1]
+    for key in ('samples', 'deltas', 'us'):
+        assert torch.equal(ref[key], gen[key]), key
+    np.testing.assert_allclose(ref['logp'].cpu().numpy(), gen['logp'].cpu().numpy(), rtol=1e-12)
+    lay = _lib.mh_stat_layout(k)
+    a, b = ref['stats'].cpu().numpy(), gen['stats'].cpu().numpy()
+    assert np.array_equal(a[:, lay['NACC']], b[:, lay['NACC']]) and 0.02 < a[:, lay['NACC']].mean() / (L - 1) < 0.98
+    assert np.array_equal(a[:, lay['LAST']:lay['LAST'] + k], b[:, lay['LAST']:lay['LAST'] + k])
+    np.testing.assert_allclose(a[:, lay['MAPLOGP']], b[:, lay['MAPLOGP']], rtol=1e-12)
+    assert np.array_equal(a[:, lay['S1']:lay['S1'] + k], b[:, lay['S1']:lay['S1'] + k])
+    # the launcher's own choice: one chain per warp up to 12 chains per SM, the dealt shape above
+    few = mh_launch(PE, start[:200], L, burn, 9, chol, thin=2, export_draws=True, chain_offset=77)
+    assert torch.equal(few['samples'], ref['samples'][:, :200]) and torch.equal(few['stats'], ref['stats'][:200])
+
+
+@pytest.mark.gpu
 def test_c5_window_above_two_to_the_33(env):
     """C5 is 1e10 points: global indices beyond 2^33.  A 4096-point window that starts above 2^33 (and one straddling 2^32) must
     be the oracle's points (Philox counter = the 64-bit global index) and log-posteriors, bit for bit, and the window's best
