@@ -29,7 +29,7 @@ L = _lib.load()
 out = {"whitening": wh}
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 flops = 2 * (2.0 * n * n if wh == 'eigh' else 1.0 * n * (n + 128))     # executed per row, both responses
-for B in (2048, 1024, 200, 64, 16, 2):
+for B in [int(v) for v in os.environ.get('FULLCOV_BS', '2048 1024 200 64 16 2').split()]:   # FULLCOV_BS="1024 2": the ncu captures
     th = torch.from_numpy(truth + 0.05 * np.random.default_rng(3).standard_normal((B, k))).cuda()
     lp = torch.empty(B, dtype=torch.float64, device="cuda")
     st = _lib.current_stream()
