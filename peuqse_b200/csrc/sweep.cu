@@ -71,9 +71,9 @@ __global__ void __launch_bounds__(P1D_THREADS, MINB) k_sweep_pass1_lin_dmma(cons
                                                                          Best* __restrict__ partial, unsigned int* __restrict__ ticket,
                                                                          ShortHdr* __restrict__ sh, long long* __restrict__ c_idx,
                                                                          double* __restrict__ c_logp) {
-    constexpr int KS = (KT + 3) / 4, KP = KS * 4, NW = P1D_THREADS / 32;
-    __shared__ double s_bf[KS][NF][32];                 // B fragments: lane l of (s, f) holds Phi[8 f + l/4][4 s + l%4]
-    __shared__ __align__(32) double2 s_yw[NF * 8];      // {y w, w} per observation
+    // the product is augmented by one column: [theta, 1] [Phi^T w ; -y w] = (sim - y) w, the weighted residual itself
+    constexpr int KS = (KT + 4) / 4, KP = KS * 4, NW = P1D_THREADS / 32;
+    __shared__ double s_bf[KS][NF][32];                 // B fragments: lane l of (s, f) holds w_j Phi[j = 8 f + l/4][4 s + l%4], -y_j w_j at column k
     __shared__ double s_th[NW][32][KP];                 // the warp's 32 points, zero padded to 4 KS parameters
     __shared__ Best s_best[NW];
     __shared__ bool s_last;
@@ -82,9 +82,8 @@ __global__ void __launch_bounds__(P1D_THREADS, MINB) k_sweep_pass1_lin_dmma(cons
     for (int idx = threadIdx.x; idx < KS * NF * 32; idx += blockDim.x) {
         const int l = idx & 31, f = (idx >> 5) % NF, sstep = idx / (32 * NF);
         const int j = 8 * f + (l >> 2), kk = 4 * sstep + (l & 3);
-        s_bf[sstep][f][l] = (kk < k) ? P.mconst[(size_t)j * k + kk] : 0.0;
+        s_bf[sstep][f][l] = (kk < k) ? P.mconst[(size_t)j * k + kk] * P.w[j] : (kk == k ? -(P.y[j] * P.w[j]) : 0.0);
     }
-    for (int j = threadIdx.x; j < NF * 8; j += blockDim.x) s_yw[j] = make_double2(P.y[j] * P.w[j], P.w[j]);
     __syncthreads();
     // diagonal prior in natural order (the usual case): z = theta / scale - mu_scaled as a multiplication by 1/scale
     const bool fast_prior = P.prior_mode == PEUQSE_PRIOR_DIAG && P.prior_identity && P.kp == k;
@@ -123,7 +122,7 @@ __global__ void __launch_bounds__(P1D_THREADS, MINB) k_sweep_pass1_lin_dmma(cons
             lp = eval_prior<KT>(P, th);
         }
 #pragma unroll
-        for (int d = 0; d < KP; ++d) s_th[warp][lane][d] = (d < KT) ? th[d < KT ? d : 0] : 0.0;
+        for (int d = 0; d < KP; ++d) s_th[warp][lane][d] = (d < KT) ? ((d < k) ? th[d < KT ? d : 0] : (d == k ? 1.0 : 0.0)) : (d == k ? 1.0 : 0.0);
         __syncwarp();
         double maha = 0.0;
         // two row fragments (16 points) at a time: every B fragment read feeds two DMMAs, four independent epilogue chains
@@ -146,11 +145,8 @@ __global__ void __launch_bounds__(P1D_THREADS, MINB) k_sweep_pass1_lin_dmma(cons
             double pa0 = 0.0, pb0 = 0.0, pa1 = 0.0, pb1 = 0.0;  // even / odd observation of the lane's pair, per fragment
 #pragma unroll
             for (int f = 0; f < NF; ++f) {
-                const double4 q = *reinterpret_cast<const double4*>(&s_yw[8 * f + 2 * (lane & 3)]);   // {y w, w} of both
-                const double t00 = fma(-acc0[f][0], q.y, q.x), t01 = fma(-acc0[f][1], q.w, q.z);       // (y - sim) w
-                const double t10 = fma(-acc1[f][0], q.y, q.x), t11 = fma(-acc1[f][1], q.w, q.z);
-                pa0 = fma(t00, t00, pa0); pb0 = fma(t01, t01, pb0);
-                pa1 = fma(t10, t10, pa1); pb1 = fma(t11, t11, pb1);
+                pa0 = fma(acc0[f][0], acc0[f][0], pa0); pb0 = fma(acc0[f][1], acc0[f][1], pb0);     // ((sim - y) w)^2
+                pa1 = fma(acc1[f][0], acc1[f][0], pa1); pb1 = fma(acc1[f][1], acc1[f][1], pb1);
             }
             double part0 = pa0 + pb0, part1 = pa1 + pb1;
             part0 += __shfl_xor_sync(0xffffffffu, part0, 1);
