@@ -64,7 +64,7 @@ __device__ __forceinline__ bool short_usable(const ShortHdr* sh, int margin_ok) 
 // per-point values never reach the caller, takes this path; sweeps that return logP keep the bit-exact scalar order.
 // ---------------------------------------------------------------------------------------------
 #define P1D_THREADS 128
-template <int KT, int NF, int MINB>
+template <int KT, int NF, int MINB, int MG = 2>
 __global__ void __launch_bounds__(P1D_THREADS, MINB) k_sweep_pass1_lin_dmma(const __grid_constant__ DevProblem P,
                                                                          const __grid_constant__ DevSweep S, long long first,
                                                                          long long count, peuqse_best* __restrict__ best_out,
@@ -125,38 +125,40 @@ __global__ void __launch_bounds__(P1D_THREADS, MINB) k_sweep_pass1_lin_dmma(cons
         for (int d = 0; d < KP; ++d) s_th[warp][lane][d] = (d < KT) ? ((d < k) ? th[d < KT ? d : 0] : (d == k ? 1.0 : 0.0)) : (d == k ? 1.0 : 0.0);
         __syncwarp();
         double maha = 0.0;
-        // two row fragments (16 points) at a time: every B fragment read feeds two DMMAs, four independent epilogue chains
+        // MG row fragments (8 MG points) at a time: every B fragment read feeds MG DMMAs, 2 MG independent epilogue chains
 #pragma unroll
-        for (int m = 0; m < 4; m += 2) {
-            double acc0[NF][2], acc1[NF][2];
+        for (int m = 0; m < 4; m += MG) {
+            double acc[MG][NF][2];
 #pragma unroll
-            for (int f = 0; f < NF; ++f) acc0[f][0] = acc0[f][1] = acc1[f][0] = acc1[f][1] = 0.0;
+            for (int r = 0; r < MG; ++r)
+#pragma unroll
+                for (int f = 0; f < NF; ++f) acc[r][f][0] = acc[r][f][1] = 0.0;
 #pragma unroll
             for (int sstep = 0; sstep < KS; ++sstep) {
-                const double a0 = s_th[warp][8 * m + (lane >> 2)][4 * sstep + (lane & 3)];
-                const double a1 = s_th[warp][8 * m + 8 + (lane >> 2)][4 * sstep + (lane & 3)];
+                double a[MG];
+#pragma unroll
+                for (int r = 0; r < MG; ++r) a[r] = s_th[warp][8 * (m + r) + (lane >> 2)][4 * sstep + (lane & 3)];
 #pragma unroll
                 for (int f = 0; f < NF; ++f) {
                     const double bq = s_bf[sstep][f][lane];
-                    pq_dmma884(acc0[f][0], acc0[f][1], a0, bq);
-                    pq_dmma884(acc1[f][0], acc1[f][1], a1, bq);
+#pragma unroll
+                    for (int r = 0; r < MG; ++r) pq_dmma884(acc[r][f][0], acc[r][f][1], a[r], bq);
                 }
             }
-            double pa0 = 0.0, pb0 = 0.0, pa1 = 0.0, pb1 = 0.0;  // even / odd observation of the lane's pair, per fragment
 #pragma unroll
-            for (int f = 0; f < NF; ++f) {
-                pa0 = fma(acc0[f][0], acc0[f][0], pa0); pb0 = fma(acc0[f][1], acc0[f][1], pb0);     // ((sim - y) w)^2
-                pa1 = fma(acc1[f][0], acc1[f][0], pa1); pb1 = fma(acc1[f][1], acc1[f][1], pb1);
+            for (int r = 0; r < MG; ++r) {
+                double pa = 0.0, pb = 0.0;                          // even / odd observation of the lane's pair, per fragment
+#pragma unroll
+                for (int f = 0; f < NF; ++f) {
+                    pa = fma(acc[r][f][0], acc[r][f][0], pa);       // ((sim - y) w)^2
+                    pb = fma(acc[r][f][1], acc[r][f][1], pb);
+                }
+                double part = pa + pb;
+                part += __shfl_xor_sync(0xffffffffu, part, 1);
+                part += __shfl_xor_sync(0xffffffffu, part, 2);      // the 4 lanes of row lane/4 hold the sum of point 8 (m + r) + lane/4
+                const double v = __shfl_sync(0xffffffffu, part, 4 * (lane & 7));
+                if ((lane >> 3) == m + r) maha = v;                 // this lane's own point
             }
-            double part0 = pa0 + pb0, part1 = pa1 + pb1;
-            part0 += __shfl_xor_sync(0xffffffffu, part0, 1);
-            part1 += __shfl_xor_sync(0xffffffffu, part1, 1);
-            part0 += __shfl_xor_sync(0xffffffffu, part0, 2);    // the 4 lanes of row lane/4 hold the sum of point 8 m + lane/4
-            part1 += __shfl_xor_sync(0xffffffffu, part1, 2);
-            const double v0 = __shfl_sync(0xffffffffu, part0, 4 * (lane & 7));
-            const double v1 = __shfl_sync(0xffffffffu, part1, 4 * (lane & 7));
-            if ((lane >> 3) == m) maha = v0;                    // this lane's own point
-            if ((lane >> 3) == m + 1) maha = v1;
         }
         __syncwarp();
         double ll = -0.5 * (P.resp_c[0] + maha);
@@ -722,9 +724,10 @@ int launch_pass1(const peuqse_problem* p, const DevSweep& S, long long first, lo
             static int minb = -1;
             if (minb < 0) { const char* e = getenv("PEUQSE_SWEEP_DMMA_CTAS"); minb = e ? atoi(e) : 4; }
             const long long wantd = (count + 127) / 128;
-            const int per_sm = minb == 4 ? 4 : 3;
-            const int gd = (int)std::max<long long>(1, std::min<long long>(wantd, std::min<long long>((long long)p->sm_count * per_sm, PQ_SWEEP_MAX_BLOCKS)));
+            const int per_sm = minb == 4 ? 4 : (minb == 5 ? 5 : 3);    // 5: three CTAs per SM, all four row fragments of a warp at once
+            const int gd = (int)std::max<long long>(1, std::min<long long>(wantd, std::min<long long>((long long)p->sm_count * (per_sm == 5 ? 3 : per_sm), PQ_SWEEP_MAX_BLOCKS)));
             if (n == 32) k_sweep_pass1_lin_dmma<KT, 4, 4><<<gd, P1D_THREADS, 0, st>>>(p->d, S, first, count, best, partial, ticket, shd, ci, cl);
+            else if (n == 64 && per_sm == 5) k_sweep_pass1_lin_dmma<KT, 8, 3, 4><<<gd, P1D_THREADS, 0, st>>>(p->d, S, first, count, best, partial, ticket, shd, ci, cl);
             else if (n == 64 && per_sm == 4) k_sweep_pass1_lin_dmma<KT, 8, 4><<<gd, P1D_THREADS, 0, st>>>(p->d, S, first, count, best, partial, ticket, shd, ci, cl);
             else if (n == 64) k_sweep_pass1_lin_dmma<KT, 8, 3><<<gd, P1D_THREADS, 0, st>>>(p->d, S, first, count, best, partial, ticket, shd, ci, cl);
             else k_sweep_pass1_lin_dmma<KT, 16, 3><<<gd, P1D_THREADS, 0, st>>>(p->d, S, first, count, best, partial, ticket, shd, ci, cl);
