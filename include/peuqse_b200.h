@@ -108,6 +108,9 @@ int peuqse_device_info(int32_t* out3);
 
 /* fp64 pipe microbenchmark: *instr_per_s = device-wide fp64 instruction rate; mode 0 = DFMA chains, 1 = DMUL+DADD pairs;
  * modes 3 / 4: mma.sync.m8n8k4.f64 (DMMA) from registers, 8 / 4 accumulators per warp -- the result is then FLOP/s.
+ * modes 5-8: DMMA in the contraction kernel's 4 x 4 fragment pattern at 8 / 16 / 32 / 64 warps per SM; modes 10-14: 1 ... 16 dependent
+ * DFMA chains per thread, one warp per scheduler (latency); modes 20-25: 8 DFMA chains with 4 / 8 / 16 integer instructions, 2 / 4
+ * shared loads or 5 + 2 of them per 8 DFMAs (issue mix; the result is DFMA instructions/s).
  * d_scratch: one double of device memory.  Synchronises the stream. */
 int peuqse_bench_fp64(int32_t mode, double* instr_per_s, double* d_scratch, void* stream);
 
