@@ -278,13 +278,22 @@ struct MhwLayout {
 __device__ __noinline__ double2 mhw_draw(unsigned long long seed, unsigned long long gchain, unsigned long long step, int blk, int k,
                                          double* um) {
     const Philox4 r = philox_block(seed, PQ_STREAM_MH, gchain, (uint32_t)(8ULL * step + (unsigned)blk));
+    // ONE log for every lane: of 1 - u_a for a pair of normals (philox_normal_pair's radius), of u_a for the accept uniform
+    const double ua = philox_u53(r.x, r.y), ub = philox_u53(r.z, r.w);
+    const double lg = log(blk < 7 ? 1.0 - ua : ua);
     double a = 0.0, b2 = 0.0;
     if (blk < 7) {
-        if (2 * blk < k) philox_normal_pair(r, a, b2);
+        if (2 * blk < k) {                                         // Box-Muller, the operations of philox_normal_pair
+            const double rad = sqrt(-2.0 * lg);
+            double sn, cs;
+            sincos(6.283185307179586 * ub, &sn, &cs);
+            a = rad * cs;
+            b2 = rad * sn;
+        }
     } else {
-        a = philox_u53(r.x, r.y);                                  // accept uniform ...
-        b2 = log(a);                                               // ... and its logarithm (IP.py:2651)
-        *um = philox_u53(r.z, r.w);                                // 'MAP_finding' modulation uniform
+        a = ua;                                                    // accept uniform ...
+        b2 = lg;                                                   // ... and its logarithm (IP.py:2651)
+        *um = ub;                                                  // 'MAP_finding' modulation uniform
     }
     return make_double2(a, b2);
 }
@@ -524,8 +533,10 @@ template <int KT>
 struct MhtLayout {
     using W = MhwLayout<KT>;
     static constexpr int KPAD = W::KPAD;
-    // cur[KPAD] | th0[KPAD] | proposal[KPAD] | scaled proposal[KPAD] | draws[32][2] | modulation uniforms[4] | 'MAP_finding' state[6]
-    static constexpr int CDOUBLES = 4 * KPAD + 64 + 4 + 6;
+    // cur[KPAD] | th0[KPAD] | proposal[KPAD] | scaled proposal[KPAD] | draws[32][2] | modulation uniforms[16] | 'MAP_finding' state[6]
+    static constexpr int CDOUBLES = 4 * KPAD + 64 + 16 + 6;
+    // a step uses (KT + 1) / 2 blocks of normals and one of uniforms: NBP lanes per step, 32 / NBP steps per pass of draws
+    static constexpr int NBP = (KT <= 2) ? 2 : (KT <= 6 ? 4 : 8), SPC = 32 / NBP;
     static constexpr int O_PRP = 2 * KPAD, O_PRS = 3 * KPAD, O_DR = 4 * KPAD;
 };
 static inline size_t mht_smem_bytes(int n_total) { return (size_t)MHT_OBS_SA + 48u * (size_t)((n_total + 31) & ~31); }
@@ -567,9 +578,9 @@ __global__ void __launch_bounds__(32 * NW, 1) k_mh_tpd(const __grid_constant__ D
     double* prs = cur + L::O_PRS;
     double2* dr = reinterpret_cast<double2*>(cur + L::O_DR);
     double* dmod = reinterpret_cast<double*>(dr + 32);
-    MapFind* mf = reinterpret_cast<MapFind*>(dmod + 4);
+    MapFind* mf = reinterpret_cast<MapFind*>(dmod + 16);
     ObsView O;
-    O.y = P.y; O.w = P.w; O.cval = P.cval; O.mc = P.mconst; O.tab = nullptr;         // general path: constants in global memory
+    O.y = P.y; O.w = P.w; O.cval = P.cval; O.mc = P.mconst;                          // general path: constants in global memory
     const int n = P.n_total;
     const int ngrp = (n + 31) >> 5;
     {
@@ -705,7 +716,7 @@ __global__ void __launch_bounds__(32 * NW, 1) k_mh_tpd(const __grid_constant__ D
         cur[gl] = t0; th0s[gl] = t0;
     }
     if (gl == 0) mf->init();
-    for (int e = gl; e < 68; e += GL) reinterpret_cast<double*>(dr)[e] = 0.0;
+    for (int e = gl; e < 80; e += GL) reinterpret_cast<double*>(dr)[e] = 0.0;
     __syncwarp();
     // accumulator slots of this lane (slot s of the chain lives in lane s % GL of its group)
     int sa[NACC], sb[NACC];
@@ -762,10 +773,10 @@ __global__ void __launch_bounds__(32 * NW, 1) k_mh_tpd(const __grid_constant__ D
     long long next_row = 1;
     int until_row = M.thin;
     const bool fast_prior = P.prior_mode == PEUQSE_PRIOR_DIAG && P.prior_identity && P.kp == k;
-    const int sub = lane >> 3, blk = lane & 7;
+    const int sub = lane / L::NBP, blk = ((lane % L::NBP) == L::NBP - 1) ? 7 : (lane % L::NBP);
     for (long long i = 1; i < M.n_steps; ++i) {
-        const int g = (int)((i - 1) & 3);
-        if (g == 0) {                                             // the draws of the next four steps, a chain at a time
+        const int g = (int)((i - 1) % L::SPC);
+        if (g == 0) {                                             // the draws of the next SPC steps, a chain at a time
             const unsigned long long step = (unsigned long long)(M.first_step + i + sub);
             __syncwarp();
 #pragma unroll 1
@@ -785,7 +796,7 @@ __global__ void __launch_bounds__(32 * NW, 1) k_mh_tpd(const __grid_constant__ D
             double z[KT], delta[KT], prop[KT];
 #pragma unroll
             for (int j = 0; j < (KT + 1) / 2; ++j) {
-                const double2 zz = dr[g * 8 + (j < 7 ? j : 0)];
+                const double2 zz = dr[g * L::NBP + j];
                 z[2 * j] = zz.x;
                 if (2 * j + 1 < KT) z[2 * j + 1] = zz.y;
             }
@@ -805,7 +816,7 @@ __global__ void __launch_bounds__(32 * NW, 1) k_mh_tpd(const __grid_constant__ D
                     for (int d = 0; d < KT; ++d) if (d < k) out.deltas[((i - 1) * C + c) * k + d] = delta[d];
                 }
                 if (live && out.us) {
-                    const double u = dr[g * 8 + 7].x;
+                    const double u = dr[g * L::NBP + L::NBP - 1].x;
                     if (M.map_finding) { out.us[((i - 1) * C + c) * 2] = u; out.us[((i - 1) * C + c) * 2 + 1] = mod; }
                     else out.us[(i - 1) * C + c] = u;
                 }
@@ -814,12 +825,19 @@ __global__ void __launch_bounds__(32 * NW, 1) k_mh_tpd(const __grid_constant__ D
                 // diagonal prior in natural order: theta / scale as a multiplication by the reciprocal (the log-prior moves in its
                 // last digit; the fast form's budget is 1e-12)
                 bool ok = true;
+                if (P.has_ub | P.has_lb) {
+#pragma unroll
+                    for (int d = 0; d < KT; ++d) {
+                        if (d < k) {
+                            if (P.has_ub) ok = ok && (prop[d] <= P.ub[d]);
+                            if (P.has_lb) ok = ok && (prop[d] >= P.lb[d]);
+                        }
+                    }
+                }
                 double q0 = 0.0, q1 = 0.0;
 #pragma unroll
                 for (int d = 0; d < KT; ++d) {
                     if (d < k) {
-                        if (P.has_ub) ok = ok && (prop[d] <= P.ub[d]);
-                        if (P.has_lb) ok = ok && (prop[d] >= P.lb[d]);
                         const double t = (prop[d] * s_rs[d] - P.mus[d]) * P.pw[d];
                         if (d & 1) q1 = fma(t, t, q1); else q0 = fma(t, t, q0);
                     }
@@ -834,7 +852,7 @@ __global__ void __launch_bounds__(32 * NW, 1) k_mh_tpd(const __grid_constant__ D
         const double sum_p = ll_p + lp_p;
         double la = sum_p - cur_sum;                              // IP.py:2641
         if (M.modulate != 0.0) la = (1.0 / M.modulate) * la;      // IP.py:2649
-        const bool accept = la > dr[g * 8 + 7].y;                 // IP.py:2651-2652; NaN -> reject
+        const bool accept = la > dr[g * L::NBP + L::NBP - 1].y;   // IP.py:2651-2652; NaN -> reject
         if (accept) {                                             // the same in every lane of the group
             cur_lp = lp_p; cur_ll = ll_p; cur_sum = sum_p;
             cur_exp = mhw_exp(cur_sum);
