@@ -272,12 +272,12 @@ class ClockSampler:
 C3 = {"n": 1024, "chains": 4096, "truth": [41.5, 45.0, 13.0, 13.0, 0.1, 0.1], "mu": [41.5, 41.5, 13.0, 13.0, 0.1, 0.1],
       "sd": [20.0, 20.0, 13.0, 13.0, 0.1, 0.1], "step": 2.5e-6, "seed": 0}
 # per chain-step: n x (21 flop + 2 exp) + prior 24 + proposal ~ 21.5 kflop + 2048 exp.  Executed work, MEASURED
-# (ncu --set full of k_mh_tpd<6,4,8,1>, profiles/r2_ncu_full_mh_c3_tpd_raw.csv, 4096 chains x 199 steps): 1257 warp instructions per
-# chain-step of which 788 fp64 (25.2 k thread-level fp64 instructions; round 1: 3547 / 1780).  An fp64 warp instruction holds the
-# sub-partition's issue port for two cycles, any other for one (profiles/fp64_latency.py), so a chain-step costs 2 x 788 + 469 = 2045
+# (ncu --set full of k_mh_tpd<6,4,8,1>, profiles/r2_ncu_full_mh_c3_tpd_raw.csv, 4096 chains x 199 steps): 1169 warp instructions per
+# chain-step of which 767 fp64 (24.6 k thread-level fp64 instructions; round 1: 3547 / 1780).  An fp64 warp instruction holds the
+# sub-partition's issue port for two cycles, any other for one (profiles/fp64_latency.py), so a chain-step costs 2 x 767 + 402 = 1937
 # issue cycles and the issue ports of one B200 deliver 2 x (fp64 warp-instruction peak) cycles per second.
-C3_FP64_INSTR_PER_STEP = 25.2e3
-C3_ISSUE_CYCLES_PER_STEP = 2045.0
+C3_FP64_INSTR_PER_STEP = 24.6e3
+C3_ISSUE_CYCLES_PER_STEP = 1937.0
 C3_FLOP_PER_STEP = 23.6e3       # SURVEY 8d algorithmic figure (one exp counted as one flop)
 FP64_INSTR_PEAK = 1.80e13     # measured DFMA / DMUL+DADD issue rate of one B200 (profiles/microbench.py), instructions/s
 
@@ -358,9 +358,9 @@ def mh_secondary(PEUQSE, torch, dist, rank, world, steps):
                                        "has no fp64 figure; nominal 37 TFLOP/s)",
                         "fp64_pipe_frac": per_gpu * C3_FP64_INSTR_PER_STEP / FP64_INSTR_PEAK,
                         "issue_frac": per_gpu * C3_ISSUE_CYCLES_PER_STEP / (2.0 * FP64_INSTR_PEAK / 32.0),
-                        "note": "SURVEY 8d counts one exp as one flop (23.6 kflop per chain-step); the kernel executes 25.2 k fp64 "
+                        "note": "SURVEY 8d counts one exp as one flop (23.6 kflop per chain-step); the kernel executes 24.6 k fp64 "
                                 "instructions per chain-step (ncu count; 2048 table-driven exps of 8 fp64 instructions), i.e. "
-                                "fp64_pipe_frac = %.2f of the measured fp64 issue rate, and 2045 issue cycles per chain-step (fp64 = 2, "
+                                "fp64_pipe_frac = %.2f of the measured fp64 issue rate, and 1937 issue cycles per chain-step (fp64 = 2, "
                                 "others = 1): issue_frac = %.2f of the issue ports -- the bound of this kernel; %.3g exp/s"
                                 % (per_gpu * C3_FP64_INSTR_PER_STEP / FP64_INSTR_PEAK,
                                    per_gpu * C3_ISSUE_CYCLES_PER_STEP / (2.0 * FP64_INSTR_PEAK / 32.0), per_gpu * 2.0 * C3["n"]),
