@@ -265,10 +265,13 @@ class Sweep:
         k, nbins, lay = self.k, self.nbins, self.lay
         log_rel = float(np.log(10 ** (-1 * coef)))                       # IP.py:1016, 3477
         key = (log_rel, bool(statistics))
+        if getattr(self, "_res_host", None) is None:                     # pinned: the packed record comes back by an async copy
+            self._res_host = torch.empty(self.res.shape, dtype=torch.float64, pin_memory=True)
+        whole = lambda: (self.step(log_rel, statistics), self._res_host.copy_(self.res, non_blocking=True))
         if getattr(self, "_graph_key", None) == key and self._graph is not None:
             self._graph.replay()                                          # the same sweep again: one graph launch
         else:
-            self.step(log_rel, statistics)
+            whole()
             # The launch sequence is captured when the SAME sweep is asked for a second time (a one-off sweep never pays for
             # a capture; repeated ones replay one graph from their third call on); with several ranks only when every
             # exchange of the step is a peer-memory kernel (their exchange counter lives in device memory, csrc/peer.cu;
@@ -278,12 +281,13 @@ class Sweep:
             if getattr(self, "_graph_key", None) != key:
                 self._graph, self._graph_key = None, None
             if seen and self._graph is None and not getattr(self, "_graph_failed", False):
-                g = self.capture(lambda: self.step(log_rel, statistics))
+                g = self.capture(whole)
                 if g is not None:
                     self._graph, self._graph_key = g, key
                 else:
                     self._graph_failed = True
-        res = self.res.cpu()                                              # the single device->host read
+        torch.cuda.current_stream().synchronize()                        # the single device->host read has landed
+        res = self._res_host
         if self.peer is not None and self.L.peuqse_peer_status(self.peer) != 0:
             raise _lib.PeuqseError("multi-GPU exchange timed out: a rank did not reach the exchange within PEUQSE_PEER_TIMEOUT_S "
                                    "seconds (default 60); the merged result is invalid and the peer mailboxes must not be reused")
