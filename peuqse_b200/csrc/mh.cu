@@ -571,6 +571,9 @@ __global__ void __launch_bounds__(32 * NW, 1) k_mh_tpd(const __grid_constant__ D
     const int grp = lane / GL, gl = lane % GL;
     const unsigned gmask = (CPW == 1) ? 0xffffffffu : (((1u << GL) - 1u) << (grp * GL));
     const unsigned int sa0 = (unsigned int)__cvta_generic_to_shared(smem);
+    // shared-memory map: [sa0, 64 KB) the chains' blocks, [64 KB, 128 KB) the exp table, [128 KB, ...) the staged observations
+    static_assert((size_t)NW * CPW * L::CDOUBLES * sizeof(double) + 4096 <= MHT_TAB_SA, "the chains' blocks must end below the exp table");
+    if (sa0 + (unsigned int)(NW * CPW * L::CDOUBLES * sizeof(double)) > MHT_TAB_SA) __trap();
     double* wbase = smem + (size_t)warp * CPW * L::CDOUBLES;
     double* cur = wbase + grp * L::CDOUBLES;                     // this group's chain
     double* th0s = cur + L::KPAD;
@@ -966,7 +969,7 @@ int launch_mh(const peuqse_problem* p, const DevMH& M, const double* th0, const 
             // 1 the general kernel.
             const bool fast_ok = p->d.n_total > PQ_THREAD_SHAPE_MAX_N && p->d.n_resp == 1 && p->d.resp_mode[0] == PEUQSE_RESP_MVN_DIAG &&
                                  !p->d.any_per_value &&
-                                 mht_smem_bytes(p->d.n_total) <= (size_t)p->max_smem_optin;
+                                 mht_smem_bytes(p->d.n_total) + 1024 <= (size_t)p->max_smem_optin;   // + the kernel's static shared memory
             const char* fe = getenv("PEUQSE_MH_SHAPE");
             int shape = fe ? atoi(fe) : 0;
             if (shape == 0) shape = (M.n_chains <= 12LL * p->sm_count) ? 7 : 4;
