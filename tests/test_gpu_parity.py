@@ -1250,8 +1250,10 @@ def test_c3_benched_shape_in_kernel_statistics_vs_oracle(env, golden):
     g = golden("tpd")
     n, L, C, burn, k = 1024, 300, 64, 30, 6
     sd = np.array([20, 20, 13, 13, 0.1, 0.1])
+    # as in bench.py the 1024 observations are ONE response with a diagonal covariance (responses_observed_max_covmat_size above n;
+    # the default 100 would make it a sum of per-observation densities, which the general kernel k_mh_warp evaluates)
     PE = make_pe(PEUQSE, PEUQSE.Tpd2SiteModel.linear_ramp(n), list(g['tpd1024_y']), list(np.full(n, float(g['tpd1024_sigma']))),
-                 [41.5, 41.5, 13.0, 13.0, 0.1, 0.1], list(sd))
+                 [41.5, 41.5, 13.0, 13.0, 0.1, 0.1], list(sd), settings={'responses_observed_max_covmat_size': 5000})
     truth = np.array([41.5, 45, 13, 13, 0.1, 0.1])
     start = truth + 2e-4 * sd * np.random.default_rng(12).standard_normal((C, k))
     chol = step_cholesky(PE.Q_covmat, 2.5e-6)
@@ -1260,7 +1262,7 @@ def test_c3_benched_shape_in_kernel_statistics_vs_oracle(env, golden):
     assert lean['samples'] is None and torch.equal(full['stats'], lean['stats'])
     kBT, c1, c2 = orc.tpd2site_constants(n)
     _, bt = orc.sim_tpd2site(kBT, c1, c2)
-    P = orc.build_problem([41.5, 41.5, 13.0, 13.0, 0.1, 0.1], sd, g['tpd1024_y'], np.full(n, float(g['tpd1024_sigma'])))
+    P = orc.build_problem([41.5, 41.5, 13.0, 13.0, 0.1, 0.1], sd, g['tpd1024_y'], np.full(n, float(g['tpd1024_sigma'])), max_covmat_size=5000)
     ref = orc.mh_chains_batch(P, start, full['deltas'].cpu().numpy(), full['us'].cpu().numpy(), bt)
     S, LP = ref['samples'], ref['logP']                                  # [L, C, k], [L, C]
     assert np.array_equal(full['samples'].cpu().numpy(), S)             # accept / reject step for step, all 64 chains
@@ -1323,7 +1325,8 @@ def test_c3_many_chain_kernel_shapes_agree(env, golden, monkeypatch):
     sig = 0.02 * np.max(sim_t)
     y = sim_t + sig * np.random.default_rng(3).standard_normal(n)
     sd = np.array([20, 20, 13, 13, 0.1, 0.1])
-    PE = make_pe(PEUQSE, PEUQSE.Tpd2SiteModel.linear_ramp(n), list(y), list(np.full(n, sig)), [41.5, 41.5, 13.0, 13.0, 0.1, 0.1], list(sd))
+    PE = make_pe(PEUQSE, PEUQSE.Tpd2SiteModel.linear_ramp(n), list(y), list(np.full(n, sig)), [41.5, 41.5, 13.0, 13.0, 0.1, 0.1], list(sd),
+                 settings={'responses_observed_max_covmat_size': 5000})       # one response with a diagonal covariance, as in bench.py
     start = truth + 5e-4 * sd * np.random.default_rng(4).standard_normal((C, k))
     chol = step_cholesky(PE.Q_covmat, 2e-5)
     runs = {}
@@ -1339,6 +1342,7 @@ def test_c3_many_chain_kernel_shapes_agree(env, golden, monkeypatch):
     for key in ('samples', 'deltas', 'us'):
         assert torch.equal(ref[key], gen[key]), key
     np.testing.assert_allclose(ref['logp'].cpu().numpy(), gen['logp'].cpu().numpy(), rtol=1e-12)
+    assert PE.host_problem.resp_mode[0] == _lib.RESP_MVN_DIAG and not torch.equal(ref['logp'], gen['logp'])   # two kernels did run
     lay = _lib.mh_stat_layout(k)
     a, b = ref['stats'].cpu().numpy(), gen['stats'].cpu().numpy()
     assert np.array_equal(a[:, lay['NACC']], b[:, lay['NACC']]) and 0.02 < a[:, lay['NACC']].mean() / (L - 1) < 0.98
@@ -1348,6 +1352,37 @@ def test_c3_many_chain_kernel_shapes_agree(env, golden, monkeypatch):
     # the launcher's own choice: one chain per warp up to 12 chains per SM, the dealt shape above
     few = mh_launch(PE, start[:200], L, burn, 9, chol, thin=2, export_draws=True, chain_offset=77)
     assert torch.equal(few['samples'], ref['samples'][:, :200]) and torch.equal(few['stats'], ref['stats'][:200])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [2050, 2300])
+def test_c3_many_observations_shared_memory_limit(env, monkeypatch, n):
+    """k_mh_tpd stages 48 bytes per observation above its 128 KB of per-chain blocks and exp table: 2050 observations still fit
+    the 227 KB of an SM (zero rows pad the last group of 32), 2300 do not and the launcher must take the general kernel.  Either
+    way the chains are the general kernel's: same accept / reject decisions, log-posteriors to 1e-12."""
+    PEUQSE, orc, _, torch = env
+    from peuqse_b200.mcmc import mh_launch, step_cholesky
+    L, C, k = 25, 70, 6
+    kBT, c1, c2 = orc.tpd2site_constants(n)
+    truth = np.array([41.5, 45, 13, 13, 0.1, 0.1])
+    sim_t = orc.sim_tpd2site(kBT, c1, c2)[0](truth)
+    sig = 0.02 * np.max(sim_t)
+    y = sim_t + sig * np.random.default_rng(8).standard_normal(n)
+    sd = np.array([20, 20, 13, 13, 0.1, 0.1])
+    PE = make_pe(PEUQSE, PEUQSE.Tpd2SiteModel.linear_ramp(n), list(y), list(np.full(n, sig)), [41.5, 41.5, 13.0, 13.0, 0.1, 0.1], list(sd),
+                 settings={'responses_observed_max_covmat_size': 5000})       # one response with a diagonal covariance, as in bench.py
+    start = truth + 2e-4 * sd * np.random.default_rng(9).standard_normal((C, k))
+    chol = step_cholesky(PE.Q_covmat, 2e-6)
+    auto = mh_launch(PE, start, L, 3, 4, chol, export_draws=True)
+    monkeypatch.setenv("PEUQSE_MH_SHAPE", "1")
+    gen = mh_launch(PE, start, L, 3, 4, chol, export_draws=True)
+    monkeypatch.delenv("PEUQSE_MH_SHAPE")
+    for key in ('samples', 'deltas', 'us'):
+        assert torch.equal(auto[key], gen[key]), key
+    np.testing.assert_allclose(auto['logp'].cpu().numpy(), gen['logp'].cpu().numpy(), rtol=1e-12)
+    assert torch.equal(auto['logp'], gen['logp']) == (n > 2080)          # the general kernel ran both times only above the limit
+    acc = (np.abs(np.diff(auto['samples'].cpu().numpy(), axis=0)).sum(axis=2) > 0).mean()
+    assert 0.02 < acc < 0.98
 
 
 @pytest.mark.gpu
