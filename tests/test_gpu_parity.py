@@ -1349,6 +1349,16 @@ def test_c3_many_chain_kernel_shapes_agree(env, golden, monkeypatch):
     assert np.array_equal(a[:, lay['LAST']:lay['LAST'] + k], b[:, lay['LAST']:lay['LAST'] + k])
     np.testing.assert_allclose(a[:, lay['MAPLOGP']], b[:, lay['MAPLOGP']], rtol=1e-12)
     assert np.array_equal(a[:, lay['S1']:lay['S1'] + k], b[:, lay['S1']:lay['S1'] + k])
+    # mcmc_mode 'MAP_finding' (per-chain step coefficient adapted every hundred steps) in the dealt kernel: the general kernel's chains
+    mf = {}
+    for shape in (1, 4, 7):
+        monkeypatch.setenv("PEUQSE_MH_SHAPE", str(shape))
+        mf[shape] = mh_launch(PE, start, 230, 10, 9, chol, store_samples=False, map_finding=True)['stats'].cpu().numpy()
+    monkeypatch.delenv("PEUQSE_MH_SHAPE")
+    assert np.array_equal(mf[4], mf[7])
+    for key, width in (('NACC', 1), ('DYN', 1), ('LAST', k), ('MAPROW', 1)):
+        assert np.array_equal(mf[4][:, lay[key]:lay[key] + width], mf[1][:, lay[key]:lay[key] + width]), key
+    assert len(np.unique(mf[4][:, lay['DYN']])) >= 3                 # two adaptations in 230 steps: 0.95^2, 0.95 x 1.05, 1.05^2
     # the launcher's own choice: one chain per warp up to 12 chains per SM, the dealt shape above
     few = mh_launch(PE, start[:200], L, burn, 9, chol, thin=2, export_draws=True, chain_offset=77)
     assert torch.equal(few['samples'], ref['samples'][:, :200]) and torch.equal(few['stats'], ref['stats'][:200])
