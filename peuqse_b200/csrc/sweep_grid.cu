@@ -937,7 +937,9 @@ __global__ void __launch_bounds__(GR_THREADS, 2) k_grid_pass2_w(const __grid_con
         const double* buf = wbuf + st * P2W_STAGE_DOUBLES;
         const int j0 = rc.y + lane;                                 // column of this lane's first point
         const double d0 = (double)((j0 >> 1) + 1);                  // its half-step count; the lane's other points: + 16 m
-        double roww = 0.0, rowwL = 0.0;
+        // last-axis moment of the tile's points about the MAP point: sum wt ((cL + shl i) - shiftL) with i = d0 + 16 m taken as
+        // (cL - shiftL) sum wt + shl (d0 sum wt + 16 sum m wt): the sums over m are of integers (exact), one FMA per point
+        double roww = 0.0, rowm = 0.0;
         const bool whole = len == 256 && lo == start && hi == start + 256 && a1 >= hi;
         if (whole) {
             const double* bufw = buf + (start - a0) + lane;
@@ -954,11 +956,10 @@ __global__ void __launch_bounds__(GR_THREADS, 2) k_grid_pass2_w(const __grid_con
 #pragma unroll
             for (int m = 0; m < GR_JPT; ++m) {
                 const double wt_ = kp[m] ? trunc(reps[m]) : 0.0;                  // IP.py:3486
-                const double dl = (cL + shl * (d0 + 16.0 * m)) - shiftL;
                 a_wr = fma(wt_, reps[m], a_wr);
                 a_nk += kp[m] ? 1 : 0;
                 roww += wt_;
-                rowwL = fma(wt_, dl, rowwL);
+                rowm = fma(wt_, (double)m, rowm);
                 if (kp[m]) atomicAdd(&s_col[j0 + m * 32], (unsigned int)wt_);
             }
         } else {
@@ -970,18 +971,18 @@ __global__ void __launch_bounds__(GR_THREADS, 2) k_grid_pass2_w(const __grid_con
                 if (v > thr) {
                     const double r_ = pq_exp_pos_tab(s_tab, v - thr);
                     const double wt_ = trunc(r_);
-                    const double dl = (cL + shl * (d0 + 16.0 * m)) - shiftL;
                     a_wr = fma(wt_, r_, a_wr);
                     a_nk += 1;
                     roww += wt_;
-                    rowwL = fma(wt_, dl, rowwL);
+                    rowm = fma(wt_, (double)m, rowm);
                     atomicAdd(&s_col[j0 + m * 32], (unsigned int)wt_);
                 }
             }
         }
         const double rw = warp_sum(roww);                           // integers < 2^53: exact in fp64
         if (rw > 0.0) {
-            const double rwl = warp_sum(rowwL);
+            const double rowi = fma(d0, roww, 16.0 * rowm);         // sum wt i: integers, exact below 2^53
+            const double rwl = warp_sum(fma(shl, rowi, (cL - shiftL) * roww));
             if (lane == 0) {
                 atomicAdd(aux.rowsum + rc.x, rw);
                 atomicAdd(aux.rowsumL + rc.x, rwl);
