@@ -620,6 +620,17 @@ __global__ void __launch_bounds__(32 * NW, 1) k_mh_tpd(const __grid_constant__ D
             atomicMax(reinterpret_cast<unsigned long long*>(&s_ext[1]), (unsigned long long)__double_as_longlong(m1));
             atomicMax(reinterpret_cast<unsigned long long*>(&s_ext[2]), (unsigned long long)__double_as_longlong(m2));
         }
+        // the additive constant of the log-likelihood: the response's (one diagonal-covariance density), or -- a response longer
+        // than responses_observed_max_covmat_size is a SUM of per-observation densities, sum_j -(c_j + t_j^2)/2 (IP.py:2969-2978) --
+        // the sum of the per-observation constants, taken once in a fixed order; the value agrees with the term-by-term sum of the
+        // general kernel to ~1e-15 relative
+        if (warp == 0) {
+            const bool per_value = P.resp_mode[0] == PEUQSE_RESP_PER_VALUE;
+            double cs = 0.0;
+            if (per_value) for (int j = lane; j < n; j += 32) cs += P.cval[j];
+            cs = warp_sum(cs);
+            if (lane == 0) s_ext[3] = per_value ? cs : P.resp_c[0];
+        }
         __syncthreads();
     }
     // the CTA's cpc chains are dealt to its warps as evenly as they go (warp w sits on sub-partition w % 4: with cpc = 28 and
@@ -682,7 +693,7 @@ __global__ void __launch_bounds__(32 * NW, 1) k_mh_tpd(const __grid_constant__ D
         }
 #pragma unroll
         for (int o = GL / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        const double total = -0.5 * (P.resp_c[0] + v);
+        const double total = -0.5 * (s_ext[3] + v);
         double ll = (total != total) ? pq_neg_inf() : total;
         const unsigned badm = __ballot_sync(0xffffffffu, bad);
         if (badm) {                                              // practically never: the general, range-checked path, a chain at a time
@@ -967,8 +978,8 @@ int launch_mh(const peuqse_problem* p, const DevMH& M, const double* th0, const 
             // the SMs and their sub-partitions.  Up to 12 chains per SM: a warp each (12 warps); more: up to four chains per warp
             // (8 warps) -- measured on 256 ... 16384 chains (profiles/c3_shapes_sweep.py).  PEUQSE_MH_SHAPE=4|5|7|8 forces a shape,
             // 1 the general kernel.
-            const bool fast_ok = p->d.n_total > PQ_THREAD_SHAPE_MAX_N && p->d.n_resp == 1 && p->d.resp_mode[0] == PEUQSE_RESP_MVN_DIAG &&
-                                 !p->d.any_per_value &&
+            const bool fast_ok = p->d.n_total > PQ_THREAD_SHAPE_MAX_N && p->d.n_resp == 1 &&
+                                 (p->d.resp_mode[0] == PEUQSE_RESP_MVN_DIAG || p->d.resp_mode[0] == PEUQSE_RESP_PER_VALUE) &&
                                  mht_smem_bytes(p->d.n_total) + 1024 <= (size_t)p->max_smem_optin;   // + the kernel's static shared memory
             const char* fe = getenv("PEUQSE_MH_SHAPE");
             int shape = fe ? atoi(fe) : 0;

@@ -1251,7 +1251,7 @@ def test_c3_benched_shape_in_kernel_statistics_vs_oracle(env, golden):
     n, L, C, burn, k = 1024, 300, 64, 30, 6
     sd = np.array([20, 20, 13, 13, 0.1, 0.1])
     # as in bench.py the 1024 observations are ONE response with a diagonal covariance (responses_observed_max_covmat_size above n;
-    # the default 100 would make it a sum of per-observation densities, which the general kernel k_mh_warp evaluates)
+    # the default 100 makes it a sum of per-observation densities: test_mh_tpd_step_for_step and test_c3_many_chain_kernel_shapes_agree)
     PE = make_pe(PEUQSE, PEUQSE.Tpd2SiteModel.linear_ramp(n), list(g['tpd1024_y']), list(np.full(n, float(g['tpd1024_sigma']))),
                  [41.5, 41.5, 13.0, 13.0, 0.1, 0.1], list(sd), settings={'responses_observed_max_covmat_size': 5000})
     truth = np.array([41.5, 45, 13, 13, 0.1, 0.1])
@@ -1309,7 +1309,8 @@ def test_c3_benched_shape_in_kernel_statistics_vs_oracle(env, golden):
 
 
 @pytest.mark.gpu
-def test_c3_many_chain_kernel_shapes_agree(env, golden, monkeypatch):
+@pytest.mark.parametrize("max_covmat", [5000, 100], ids=["one_diagonal_response", "per_observation_densities"])
+def test_c3_many_chain_kernel_shapes_agree(env, golden, monkeypatch, max_covmat):
     """k_mh_tpd (config C3: rate-law model, one diagonal response) deals up to four chains to a warp, the chains of an SM evenly to
     its sub-partitions.  A chain's trajectory must not depend on the dealing: 4100 chains (warps of 4 + 3 chains, a last CTA
     that is not full) x 40 steps on 160 observations (not a multiple of the 32 a warp strides over) through every compiled shape
@@ -1326,7 +1327,8 @@ def test_c3_many_chain_kernel_shapes_agree(env, golden, monkeypatch):
     y = sim_t + sig * np.random.default_rng(3).standard_normal(n)
     sd = np.array([20, 20, 13, 13, 0.1, 0.1])
     PE = make_pe(PEUQSE, PEUQSE.Tpd2SiteModel.linear_ramp(n), list(y), list(np.full(n, sig)), [41.5, 41.5, 13.0, 13.0, 0.1, 0.1], list(sd),
-                 settings={'responses_observed_max_covmat_size': 5000})       # one response with a diagonal covariance, as in bench.py
+                 settings={'responses_observed_max_covmat_size': max_covmat})   # 5000: one response with a diagonal covariance, as in
+    # bench.py; 100 (the reference's default): the 160 observations are a sum of per-observation densities (IP.py:2969-2978)
     start = truth + 5e-4 * sd * np.random.default_rng(4).standard_normal((C, k))
     chol = step_cholesky(PE.Q_covmat, 2e-5)
     runs = {}
@@ -1342,7 +1344,8 @@ def test_c3_many_chain_kernel_shapes_agree(env, golden, monkeypatch):
     for key in ('samples', 'deltas', 'us'):
         assert torch.equal(ref[key], gen[key]), key
     np.testing.assert_allclose(ref['logp'].cpu().numpy(), gen['logp'].cpu().numpy(), rtol=1e-12)
-    assert PE.host_problem.resp_mode[0] == _lib.RESP_MVN_DIAG and not torch.equal(ref['logp'], gen['logp'])   # two kernels did run
+    assert PE.host_problem.resp_mode[0] == (_lib.RESP_MVN_DIAG if max_covmat > n else _lib.RESP_PER_VALUE)
+    assert not torch.equal(ref['logp'], gen['logp'])                    # two kernels did run
     lay = _lib.mh_stat_layout(k)
     a, b = ref['stats'].cpu().numpy(), gen['stats'].cpu().numpy()
     assert np.array_equal(a[:, lay['NACC']], b[:, lay['NACC']]) and 0.02 < a[:, lay['NACC']].mean() / (L - 1) < 0.98
