@@ -5,6 +5,10 @@
 // log_accept = (ll_p + lp_p) - (ll_c + lp_c) (2641), optional 1/N flattening (2644-2649),
 // accept iff log_accept > log(u) (2650-2652).  The reference re-simulates the current point each step
 // (2638-2639); re-evaluating an unchanged point reproduces the same doubles, so the cached value is used.
+// Three kernels, one trajectory per (seed, chain): k_mh (a thread per chain: small problems, many chains), k_mh_warp (a warp per
+// chain: many observations, any built-in model; also the scenario batches of the design of experiments) and k_mh_tpd (the
+// rate-law model with one response of many observations -- config C3: up to four chains per warp, exponents through a per-lane
+// table; see its header for the issue-port arithmetic that shaped it).
 #include <cstdlib>
 #include "common.cuh"
 #include "eval.cuh"
@@ -272,8 +276,8 @@ struct MhwLayout {
     static constexpr int WDOUBLES = 3 * KPAD + 64 + 4 + 6;
 };
 
-// the draws of one lane for four steps of its chain (lane = 8 * step offset + block): a pair of normals (blocks 0..6) or the
-// accept uniform and the modulation uniform of 'MAP_finding' (block 7).  Not inlined: the large-argument paths of sincos and log would otherwise set
+// the draws of one lane (k_mh_warp: lane = 8 * step offset + block, four steps a pass; k_mh_tpd: 32 / NBP steps a pass): a pair of
+// normals (blocks 0..6) or the accept uniform, its logarithm and the modulation uniform of 'MAP_finding' (block 7).  Not inlined: the large-argument paths of sincos and log would otherwise set
 // the register budget of the whole kernel although they run once every four steps.
 __device__ __noinline__ double2 mhw_draw(unsigned long long seed, unsigned long long gchain, unsigned long long step, int blk, int k,
                                          double* um) {
