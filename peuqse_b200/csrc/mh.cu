@@ -531,6 +531,11 @@ __global__ void __launch_bounds__(32 * MHW_WARPS, MINB) k_mh_warp(const __grid_c
 // exchanging the other groups' partials: a chain's value does not depend on CPW or on which warp it landed in.
 // Values agree with the general path to a few ulp of the simulated response (log-posterior ~1e-14 relative).
 // ---------------------------------------------------------------------------------------------
+// 2^(j/2048), j = 0..2047, correctly rounded (gen_exp_tab2048.py); k_mh_tpd stages every eighth entry (mht_exp)
+__device__ const double g_exp_tab2048[2048] = {
+#include "exp_tab2048.inc"
+};
+
 #define MHT_TAB_SA 65536u          // shared address of the exp table (64 KB: byte 1 of a lookup address is the table index)
 #define MHT_OBS_SA 131072u         // shared address of the staged observations
 template <int KT>
