@@ -531,9 +531,9 @@ __global__ void __launch_bounds__(32 * MHW_WARPS, MINB) k_mh_warp(const __grid_c
 // exchanging the other groups' partials: a chain's value does not depend on CPW or on which warp it landed in.
 // Values agree with the general path to a few ulp of the simulated response (log-posterior ~1e-14 relative).
 // ---------------------------------------------------------------------------------------------
-// 2^(j/2048), j = 0..2047, correctly rounded (gen_exp_tab2048.py); k_mh_tpd stages every eighth entry (mht_exp)
-__device__ const double g_exp_tab2048[2048] = {
-#include "exp_tab2048.inc"
+// 2^(j/256), j = 0..255, correctly rounded (gen_exp_tab256.py); k_mh_tpd stages 32 copies of it (mht_exp)
+__device__ const double g_exp_tab256[256] = {
+#include "exp_tab256.inc"
 };
 
 #define MHT_TAB_SA 65536u          // shared address of the exp table (64 KB: byte 1 of a lookup address is the table index)
@@ -612,7 +612,7 @@ __global__ void __launch_bounds__(32 * NW, 1) k_mh_tpd(const __grid_constant__ D
         }
         for (int e = threadIdx.x; e < 256 * 32; e += blockDim.x) {
             const int j = e >> 5;
-            const double T = g_exp_tab2048[8 * j];               // 2^(j/256)
+            const double T = g_exp_tab256[j];                    // 2^(j/256)
             tab[e] = __hiloint2double(__double2hiint(T) - (j << 12), __double2loint(T));
         }
         if (threadIdx.x < 4) s_ext[threadIdx.x] = 0.0;
