@@ -6,7 +6,7 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false -Xcompiler -fPIC -Xptxas -v"
 mkdir -p ../_build
 pids=()
-for f in problem logp sweep sweep_grid mh fullcov ess ess_rounds comm peer stats doe diag; do
+for f in problem logp sweep sweep_grid mh mh_steps fullcov ess ess_rounds comm peer stats doe diag; do
   ( $NVCC $FLAGS -c $f.cu -o ../_build/$f.o > ../_build/$f.log 2>&1 || { cat ../_build/$f.log; exit 1; } ) &
   pids+=($!)
 done

@@ -316,6 +316,31 @@ int peuqse_mh_run(const peuqse_problem* p, const peuqse_mh_spec* spec, const dou
                   double* d_samples, double* d_logp, double* d_logprior, double* d_loglik,
                   double* d_deltas, double* d_us, double* d_stats, void* stream);
 
+/*
+ * Lock-step form of the same sampler (csrc/mh_steps.cu) for what cannot run inside the persistent kernel: a simulator outside the
+ * library (the reference's simulateByInputParametersOnlyFunction as a torch callable), custom_logPrior / custom_logLikelihood
+ * (IP.py:2757-2759, 2854-2857) and responses with a full covariance matrix.  The caller evaluates log-prior and log-likelihood of
+ * every chain's proposal between the two kernels of a step:
+ *     peuqse_mhs_begin(spec, d_theta0, d_lp0, d_ll0, d_state, d_stats, outputs...);            row 0
+ *     for (i = 1; i < n_steps; ++i) {
+ *         peuqse_mhs_propose(spec, i, d_state, d_stats, d_prop, d_deltas, d_us);                d_prop[C][k] = proposals of step i
+ *         <d_lp[c] = logPrior(d_prop[c]), d_ll[c] = logLikelihood(d_prop[c])>
+ *         peuqse_mhs_accept(spec, i, d_prop, d_lp, d_ll, d_state, d_stats, outputs...); }
+ *     peuqse_mhs_finish(spec, d_state, d_stats);
+ * Draws, arithmetic, outputs and the statistics block are those of peuqse_mh_run (identical trajectories for a built-in model).
+ * d_state: C * peuqse_mhs_state_doubles(k) doubles of scratch; d_stats[C][PEUQSE_MH_STAT_DOUBLES(k)] carries the running state.
+ */
+int64_t peuqse_mhs_state_doubles(int32_t k);
+int peuqse_mhs_begin(const peuqse_mh_spec* spec, const double* d_theta0, const double* d_logprior0, const double* d_loglik0,
+                     double* d_state, double* d_stats, double* d_samples, double* d_logp, double* d_logprior, double* d_loglik,
+                     void* stream);
+int peuqse_mhs_propose(const peuqse_mh_spec* spec, int64_t step, double* d_state, const double* d_stats, double* d_prop,
+                       double* d_deltas, double* d_us, void* stream);
+int peuqse_mhs_accept(const peuqse_mh_spec* spec, int64_t step, const double* d_prop, const double* d_logprior_prop,
+                      const double* d_loglik_prop, double* d_state, double* d_stats, double* d_samples, double* d_logp,
+                      double* d_logprior, double* d_loglik, void* stream);
+int peuqse_mhs_finish(const peuqse_mh_spec* spec, const double* d_state, double* d_stats, void* stream);
+
 /* raw generator access (tests): d_out[count][4] uint32 Philox4x32-10 blocks for (seed, stream, idx=first+i, block) */
 int peuqse_philox_blocks(uint64_t seed, uint32_t rng_stream, int64_t first, int64_t count, uint32_t block,
                          uint32_t* d_out, void* stream);

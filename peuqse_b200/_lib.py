@@ -95,6 +95,7 @@ EXPORTS = [
     "peuqse_comm_unique_id", "peuqse_comm_create", "peuqse_comm_destroy", "peuqse_comm_allgather",
     "peuqse_comm_allreduce_sum_i64", "peuqse_peer_alloc", "peuqse_peer_create", "peuqse_peer_destroy",
     "peuqse_peer_max_bytes", "peuqse_peer_status", "peuqse_peer_merge_best", "peuqse_peer_merge_acc", "peuqse_peer_sum_i64", "peuqse_merge_best", "peuqse_merge_acc", "peuqse_mh_run",
+    "peuqse_mhs_state_doubles", "peuqse_mhs_begin", "peuqse_mhs_propose", "peuqse_mhs_accept", "peuqse_mhs_finish",
     "peuqse_philox_blocks", "peuqse_ess_work_bytes", "peuqse_ess_run",
     "peuqse_essr_create", "peuqse_essr_destroy", "peuqse_essr_begin_half", "peuqse_essr_round", "peuqse_essr_end_half",
     "peuqse_essr_end_iteration", "peuqse_essr_info",
@@ -162,6 +163,12 @@ def load():
     L.peuqse_merge_best.argtypes = [vp, i32, vp, vp]
     L.peuqse_merge_acc.argtypes = [vp, i32, i32, vp, vp]
     L.peuqse_mh_run.argtypes = [vp, C.POINTER(MHSpec), vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.peuqse_mhs_state_doubles.argtypes = [i32]
+    L.peuqse_mhs_state_doubles.restype = i64
+    L.peuqse_mhs_begin.argtypes = [C.POINTER(MHSpec), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.peuqse_mhs_propose.argtypes = [C.POINTER(MHSpec), i64, vp, vp, vp, vp, vp, vp]
+    L.peuqse_mhs_accept.argtypes = [C.POINTER(MHSpec), i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.peuqse_mhs_finish.argtypes = [C.POINTER(MHSpec), vp, vp, vp]
     L.peuqse_philox_blocks.argtypes = [u64, u32, i64, i64, u32, vp, vp]
     L.peuqse_ess_work_bytes.restype = i64
     L.peuqse_ess_work_bytes.argtypes = [i64, i32]

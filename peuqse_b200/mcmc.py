@@ -26,10 +26,14 @@ def step_cholesky(Q_covmat, step):
 
 
 def mh_launch(pe, theta0, n_steps, burn_in, seed, step_chol, first_step=0, chain_offset=0, modulate=0.0, thin=1,
-              store_samples=True, store_parts=True, export_draws=False, map_finding=False):
-    """One call of peuqse_mh_run for C chains starting at theta0[C,k].  Returns a dict of device tensors."""
+              store_samples=True, store_parts=True, export_draws=False, map_finding=False, lockstep=None):
+    """C chains starting at theta0[C,k]: one call of peuqse_mh_run (the persistent kernel), or -- for what cannot run inside
+    it, see mh_needs_lockstep -- the lock-step form peuqse_mhs_* with the batched log-posterior between its two kernels per
+    step.  Same draws, same arithmetic, same outputs.  Returns a dict of device tensors."""
     L = _lib.load()
     dev = _dev()
+    if lockstep is None:
+        lockstep = mh_needs_lockstep(pe)
     th0 = torch.as_tensor(np.asarray(theta0, dtype=float), dtype=torch.float64).reshape(-1, pe.k).to(dev).contiguous()
     Cn, k = th0.shape
     spec = _lib.MHSpec()
@@ -51,11 +55,47 @@ def mh_launch(pe, theta0, n_steps, burn_in, seed, step_chol, first_step=0, chain
     us_shape = (max(n_steps - 1, 0), Cn, 2) if map_finding else (max(n_steps - 1, 0), Cn)
     out['us'] = torch.empty(us_shape, dtype=torch.float64, device=dev) if export_draws else None
     out['stats'] = torch.empty((Cn, lay['SIZE']), dtype=torch.float64, device=dev)
+    out['theta0'] = th0
+    if lockstep:
+        return _mh_lockstep(pe, L, spec, th0, out)
     _lib.check(L.peuqse_mh_run(pe.device_problem.handle, C.byref(spec), _lib.ptr(th0), _lib.ptr(out['samples']),
                                _lib.ptr(out['logp']), _lib.ptr(out['logprior']), _lib.ptr(out['loglik']),
                                _lib.ptr(out['deltas']), _lib.ptr(out['us']), _lib.ptr(out['stats']), _lib.current_stream()))
     pe.gpu_launches += 1
-    out['theta0'] = th0
+    return out
+
+
+def mh_needs_lockstep(pe):
+    """What the persistent kernel cannot evaluate itself: a simulator that is a torch callable, custom_logPrior /
+    custom_logLikelihood (IP.py:2757-2759, 2854-2857), a response with a full covariance matrix; or on request
+    (parameter_estimation_settings['mcmc_lockstep'] = True)."""
+    from .models import BuiltinModel
+    return bool(not isinstance(pe.simulator, BuiltinModel) or getattr(pe, 'custom_logLikelihood', None) is not None
+                or getattr(pe, 'custom_logPrior', None) is not None
+                or np.any(np.asarray(pe.device_problem.H.resp_mode) == _lib.RESP_MVN_FULL)
+                or pe.UserInput.parameter_estimation_settings.get('mcmc_lockstep', False))
+
+
+def _mh_lockstep(pe, L, spec, th0, out):
+    """doMetropolisHastings' loop (IP.py:2626-2675) with every chain's step taken together: k_mhs_propose, the batched
+    log-prior / log-likelihood of the proposals (pe.getLogP_batch: built-in kernels, a torch simulator, the user's callables),
+    k_mhs_accept.  Everything stays on the device and on one stream; nothing is read back inside the loop."""
+    Cn, k = th0.shape
+    dev = th0.device
+    st = _lib.current_stream()
+    state = torch.empty((Cn, int(L.peuqse_mhs_state_doubles(k))), dtype=torch.float64, device=dev)
+    prop = torch.empty((Cn, k), dtype=torch.float64, device=dev)
+    rows = (_lib.ptr(out['samples']), _lib.ptr(out['logp']), _lib.ptr(out['logprior']), _lib.ptr(out['loglik']))
+    _, lp, ll = pe.getLogP_batch(th0, return_parts=True)
+    _lib.check(L.peuqse_mhs_begin(C.byref(spec), _lib.ptr(th0), _lib.ptr(lp), _lib.ptr(ll), _lib.ptr(state), _lib.ptr(out['stats']), *rows, st))
+    for i in range(1, int(spec.n_steps)):
+        _lib.check(L.peuqse_mhs_propose(C.byref(spec), i, _lib.ptr(state), _lib.ptr(out['stats']), _lib.ptr(prop),
+                                        _lib.ptr(out['deltas']), _lib.ptr(out['us']), st))
+        _, lp, ll = pe.getLogP_batch(prop, return_parts=True)
+        _lib.check(L.peuqse_mhs_accept(C.byref(spec), i, _lib.ptr(prop), _lib.ptr(lp), _lib.ptr(ll), _lib.ptr(state),
+                                       _lib.ptr(out['stats']), *rows, st))
+    _lib.check(L.peuqse_mhs_finish(C.byref(spec), _lib.ptr(state), _lib.ptr(out['stats']), st))
+    pe.gpu_launches += 2 * int(spec.n_steps)          # begin, finish, two kernels per step; getLogP_batch counts its own
     return out
 
 
@@ -98,9 +138,6 @@ def chain_moments(stats, theta0, k, n_rows):
 def run_metropolis_hastings(pe, calculatePostBurnInStatistics=True, continueSampling='auto', mcmc_exportLog='UserChoice'):
     UI = pe.UserInput
     pes = UI.parameter_estimation_settings
-    if getattr(pe, 'custom_logLikelihood', None) is not None or getattr(pe, 'custom_logPrior', None) is not None:
-        raise NotImplementedError("doMetropolisHastings runs as one persistent kernel and cannot call custom_logLikelihood / "
-                                  "custom_logPrior; use doEnsembleSliceSampling or doMultiStart (batched paths) with them")
     if hasattr(UI, 'last_MCMC_run_type') and UI.last_MCMC_run_type != 'MH':                       # IP.py:2565-2569
         print("ERROR: Two different algorithms of MCMC runs were attempted with the same UserInput."); raise SystemExit
     if pes['mcmc_mode'] not in ('unbiased', 'MAP_finding'):

@@ -1501,7 +1501,7 @@ def test_mh_map_finding_vs_reference_fixture_and_oracle(env, golden):
 def test_custom_log_prior_and_log_likelihood(env):
     """UserInput.model['custom_logPrior'] / ['custom_logLikelihood'] (IP.py:2757-2759, 2854-2857) as vectorised torch callables: a
     custom prior / likelihood that restates the built-in one must give the built-in log-posterior; the drivers that evaluate in
-    batches (multistart, ensemble slice sampling) run on them; the persistent Metropolis-Hastings kernel refuses."""
+    batches (multistart, ensemble slice sampling, lock-step Metropolis-Hastings) run on them."""
     PEUQSE, orc, _, torch = env
     rng = np.random.default_rng(3)
     k, n, sig = 3, 20, 0.3
@@ -1542,8 +1542,10 @@ def test_custom_log_prior_and_log_likelihood(env):
         assert np.array_equal(PE.map_parameter_set, base.map_parameter_set) and abs(PE.map_logP - base.map_logP) < 1e-9
         PE.doEnsembleSliceSampling()
         assert PE.post_burn_in_samples.shape == (16 * 35, k) and np.all(np.isfinite(PE.post_burn_in_log_posteriors_un_normed_vec))
-        with pytest.raises(NotImplementedError):
-            PE.doMetropolisHastings()
+        PE.UserInput.parameter_estimation_settings.update({'mcmc_length': 300, 'mcmc_burn_in': 30, 'mcmc_relative_step_length': 0.01})
+        del PE.UserInput.last_MCMC_run_type                            # another sampler on the same UserInput is refused (IP.py:2565-2569)
+        PE.doMetropolisHastings()                                      # the lock-step form (tests/test_gpu_mh_lockstep.py)
+        assert PE.post_burn_in_samples.shape == (270, k)
     # a custom prior replaces the bounds check too (IP.py:2757-2759 returns before doInputParameterBoundsChecks)
     PEb = make_pe(PEUQSE, PEUQSE.LinearModel(Phi), list(y), list(np.full(n, sig)), [0.0] * k, [2.0] * k, custom_logPrior=my_prior,
                   InputParameterPriorValues_lowerBounds=[-0.1] * k, InputParameterPriorValues_upperBounds=[0.1] * k)
