@@ -365,9 +365,10 @@ class parameter_estimation:
         if numStartPoints == 0: numStartPoints = len(self.UserInput.InputParameterInitialGuess) * 3     # IP.py:1101-1102
         if relativeInitialDistributionSpread == 0: relativeInitialDistributionSpread = 0.866           # IP.py:1103-1104
         if searchType in ('doGetLogP', 'doSinglePoint'): searchType = 'getLogP'                        # IP.py:1105-1106
-        if searchType not in ('getLogP', 'doOptimizeNegLogP', 'doOptimizeLogP', 'doMetropolisHastings'):
-            raise NotImplementedError(f"multistart searchType '{searchType}' (an ensemble sampler or an SSR fit per start point) is outside "
-                                      "the accelerated path; use 'getLogP', 'doMetropolisHastings', 'doOptimizeNegLogP' or 'doOptimizeLogP'")
+        if searchType not in ('getLogP', 'doOptimizeNegLogP', 'doOptimizeLogP', 'doMetropolisHastings', 'doEnsembleSliceSampling'):
+            raise NotImplementedError(f"multistart searchType '{searchType}' (the emcee sampler or an SSR fit per start point) is outside the "
+                                      "accelerated path; use 'getLogP', 'doMetropolisHastings', 'doEnsembleSliceSampling', 'doOptimizeNegLogP' "
+                                      "or 'doOptimizeLogP'")
         if str(keep_cumulative_post_burn_in_data) == 'UserChoice':
             keep_cumulative_post_burn_in_data = pes.get('multistart_keep_cumulative_post_burn_in_data', False)
         if str(passThroughArgs) == 'UserChoice': passThroughArgs = pes.get('multistart_passThroughArgs', {})
@@ -386,6 +387,9 @@ class parameter_estimation:
                                              gridsearchSamplingInterval=gridsearchSamplingInterval, gridsearchSamplingRadii=gridsearchSamplingRadii)
             if searchType == 'doMetropolisHastings':
                 return self._multistart_mh(pts, bool(calculatePostBurnInStatistics), bool(keep_cumulative_post_burn_in_data), centerPoint)
+            if searchType == 'doEnsembleSliceSampling':
+                return self._multistart_ess(pts, bool(calculatePostBurnInStatistics), bool(keep_cumulative_post_burn_in_data), centerPoint,
+                                            walkerInitialDistribution)
             return self._multistart_optimize(searchType, pts, passThroughArgs, centerPoint)
         if kind == 'grid':
             c, h, r, n = self.getGridPermutations(centerPoint, gridsearchSamplingInterval, gridsearchSamplingRadii)
@@ -586,6 +590,83 @@ class parameter_estimation:
             exportMultistart(self, centerPoint, best, R.statistics, initial_point=pts[i], mcmc=True)
             self.map_index = saved if saved is not None else i
         return best
+
+    def _multistart_ess(self, pts, calculatePostBurnInStatistics, keep_cumulative, centerPoint, walkerInitialDistribution):
+        """Multistart with searchType 'doEnsembleSliceSampling' (IP.py:832-836, 880-895, 933-947, 971-990): one ensemble per start
+        point, one after the other as in the reference -- an ensemble is a batch already, its rounds are what fills the device.  The
+        walkers of a run are spread around its start point (InputParameterInitialGuess = the start point, IP.py:858); 2k walkers when
+        mcmc_nwalkers is 'auto' (IP.py:833-836); the start whose run holds the highest logP wins (strict '>', IP.py:933) and its rows
+        go through calculatePostBurnInStatistics once more (IP.py:979-982).  With an integer mcmc_random_seed start i draws from
+        seed + 1000003 i, so the runs are reproducible and distinct."""
+        from .mcmc import _export_if_requested
+        from .sweep import SweepResult
+        UI = self.UserInput
+        pes = UI.parameter_estimation_settings
+        pts = np.asarray(pts, dtype=float).reshape(-1, self.k)
+        self._list_of_permutations = pts
+        nw = pes.get('mcmc_nwalkers', 'auto')
+        nw = 2 * self.k if str(nw).lower() == 'auto' else int(nw)
+        seed0 = pes.get('mcmc_random_seed')
+        rows, best, best_i, best_state = [], None, -1, None
+        self.highest_logP = float('-inf')                                                              # IP.py:824
+        cum = []
+        kept = ('post_burn_in_samples', 'post_burn_in_log_posteriors_un_normed_vec', 'post_burn_in_log_priors_vec',
+                'discrete_chains_post_burn_in_samples', 'mcmc_last_point_sampled', 'ess_info')
+        try:
+            for i, pt in enumerate(pts):
+                UI.InputParameterInitialGuess = pt                                                     # IP.py:858
+                if isinstance(seed0, int):
+                    pes['mcmc_random_seed'] = seed0 + 1000003 * i
+                self.map_logP = float('-inf')                                                          # IP.py:881
+                res = self.doEnsembleSliceSampling(mcmc_nwalkers_direct_input=nw, calculatePostBurnInStatistics=calculatePostBurnInStatistics,
+                                                   walkerInitialDistribution=walkerInitialDistribution, continueSampling=False,
+                                                   mcmc_exportLog=False)
+                lp_i = float(np.ravel(self.map_logP)[0])
+                rows.append(np.hstack((lp_i, np.asarray(self.map_parameter_set, dtype=float))))        # IP.py:947
+                if keep_cumulative:                                                                    # IP.py:884-895
+                    cum.append((self.post_burn_in_samples, self.discrete_chains_post_burn_in_samples,
+                                getattr(self, 'post_burn_in_log_priors_vec', None), self.post_burn_in_log_posteriors_un_normed_vec))
+                if lp_i > self.highest_logP:                                                           # IP.py:933-941
+                    self.highest_logP, best, best_i = lp_i, res, i
+                    best_map = np.array(self.map_parameter_set, dtype=float)
+                    best_state = {n: getattr(self, n) for n in kept if hasattr(self, n)}
+        finally:
+            pes['mcmc_random_seed'] = seed0
+            UI.InputParameterInitialGuess = centerPoint                                                # IP.py:971
+        self._perm_array = np.vstack(rows)
+        R = SweepResult()
+        R.total, R.statistics, R.optimizer = len(pts), False, False
+        if best is None:
+            R.map_logP, R.map_index, R.map_parameter_set = float('-inf'), -1, np.full(self.k, np.nan)
+            return self._adopt_sweep_result(R, centerPoint)
+        for n, v in best_state.items():
+            setattr(self, n, v)
+        if keep_cumulative:
+            self.cumulative_post_burn_in_samples = np.vstack([c[0] for c in cum])
+            self.cumulative_discrete_chains_post_burn_in_samples = np.vstack([c[1] for c in cum])
+            if all(c[2] is not None for c in cum):
+                self.cumulative_post_burn_in_log_priors_vec = np.vstack([c[2] for c in cum])
+            self.cumulative_post_burn_in_log_posteriors_un_normed_vec = np.vstack([c[3] for c in cum])
+        self.map_logP, self.map_parameter_set = self.highest_logP, best_map                            # IP.py:973-974
+        R.map_logP, R.map_index, R.map_parameter_set, R.initial_point = self.highest_logP, best_i, best_map, pts[best_i]
+        out = [best_map, None, None, None, None, self.post_burn_in_samples, self.post_burn_in_log_posteriors_un_normed_vec]
+        if calculatePostBurnInStatistics:
+            self._dev_post = None
+            self.calculatePostBurnInStatistics(calculate_post_burn_in_log_priors_vec=True)             # IP.py:979-982
+            UI.InputParameterInitialGuess = pts[best_i]       # what the best start's own run recorded (mcmc_log_file.txt, IP.py:1971)
+            _export_if_requested(self, 'UserChoice')
+            UI.InputParameterInitialGuess = centerPoint
+            out = [self.map_parameter_set, self.mu_AP_parameter_set, self.stdap_parameter_set, self.evidence, self.info_gain,
+                   self.post_burn_in_samples, self.post_burn_in_log_posteriors_un_normed_vec]
+            R.statistics, R.mcmc = True, True
+        self.sweep_result = R
+        self.map_index_of_start = best_i
+        if bool(pes.get('exportLog', True)):
+            from .export import exportMultistart
+            saved, self.map_index = getattr(self, 'map_index', None), best_i
+            exportMultistart(self, centerPoint, out, R.statistics, initial_point=pts[best_i], mcmc=True)
+            self.map_index = saved if saved is not None else best_i
+        return out
 
     def doGridSearch(self, searchType='getLogP', gridSamplingAbsoluteIntervalSize=[], gridSamplingNumOfIntervals=[], **kw):
         """Deprecated alias kept by the reference (IP.py:1120-1128)."""

@@ -222,3 +222,38 @@ def test_do_ensemble_slice_sampling_reproducible(env):
         PE.doEnsembleSliceSampling()
         runs.append(PE.post_burn_in_samples.copy())
     assert np.array_equal(runs[0], runs[1])
+
+
+def test_multistart_of_ensemble_slice_runs(env):
+    """doMultiStart(searchType='doEnsembleSliceSampling') (IP.py:832-836, 880-895, 933-947, 971-990): one ensemble per start point,
+    walkers spread around it, 2k walkers by default; the start with the highest logP wins and its run is what a direct
+    doEnsembleSliceSampling from that start (same seed) produces."""
+    PEUQSE, orc, torch = env
+    rng = np.random.default_rng(6)
+    k, n, sig = 3, 30, 0.3
+    Phi = orc.cos_basis(n, k)
+    y = Phi @ rng.standard_normal(k) + sig * rng.standard_normal(n)
+    settings = dict(mcmc_length=6 * 60, mcmc_burn_in=6 * 10, mcmc_random_seed=3, mcmc_threshold_filter_samples=False,
+                    mcmc_info_gain_returned='log_ratio', multistart_searchType='doEnsembleSliceSampling',
+                    multistart_initialPointsDistributionType='grid', multistart_gridsearchSamplingInterval=[0.5, 0.5, 0.5],
+                    multistart_gridsearchSamplingRadii=[1, 0, 1], multistart_keep_cumulative_post_burn_in_data=True, exportLog=False)
+    runs = []
+    for _ in range(2):
+        PE = make_pe(PEUQSE, PEUQSE.LinearModel(Phi), list(y), list(np.full(n, sig)), [0.0] * k, [2.0] * k, **settings)
+        best = PE.doMultiStart()
+        runs.append((PE.permutations_MAP_logP_and_parameters_values.copy(), PE.post_burn_in_samples.copy()))
+    assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[0][1], runs[1][1])
+    rows = runs[0][0]
+    pts = PE.listOfPermutations
+    assert rows.shape == (9, 1 + k) and pts.shape == (9, k) and PE.mcmc_nwalkers == 2 * k
+    i = int(np.argmax(rows[:, 0]))
+    assert PE.map_logP == rows[i, 0] and np.array_equal(PE.map_parameter_set, rows[i, 1:]) and len(best) == 7
+    assert PE.post_burn_in_samples.shape == (6 * 50, k) and PE.cumulative_post_burn_in_samples.shape == (9 * 6 * 50, k)
+    assert np.array_equal(PE.UserInput.InputParameterInitialGuess, [0.0] * k)
+    assert len(np.unique(rows[:, 0])) == 9                               # every start ran its own ensemble
+    one = make_pe(PEUQSE, PEUQSE.LinearModel(Phi), list(y), list(np.full(n, sig)), [0.0] * k, [2.0] * k,
+                  **dict(settings, mcmc_random_seed=3 + 1000003 * i, mcmc_nwalkers=2 * k))
+    one.UserInput.InputParameterInitialGuess = pts[i]
+    one.doEnsembleSliceSampling()
+    assert np.array_equal(one.post_burn_in_samples, PE.post_burn_in_samples)
+    assert abs(float(np.ravel(one.map_logP)[0]) - PE.map_logP) == 0
