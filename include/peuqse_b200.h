@@ -328,6 +328,8 @@ int peuqse_mh_run(const peuqse_problem* p, const peuqse_mh_spec* spec, const dou
  *         peuqse_mhs_accept(spec, i, d_prop, d_lp, d_ll, d_state, d_stats, outputs...); }
  *     peuqse_mhs_finish(spec, d_state, d_stats);
  * Draws, arithmetic, outputs and the statistics block are those of peuqse_mh_run (identical trajectories for a built-in model).
+ * step < 0 in propose / accept: the step index is a per-chain counter kept in d_state (starts at 1, advanced by accept; calls beyond
+ * n_steps - 1 do nothing), so that one captured propose -> evaluate -> accept sequence can be replayed as a CUDA graph.
  * d_state: C * peuqse_mhs_state_doubles(k) doubles of scratch; d_stats[C][PEUQSE_MH_STAT_DOUBLES(k)] carries the running state.
  */
 int64_t peuqse_mhs_state_doubles(int32_t k);

@@ -6,6 +6,8 @@
 // block are those of k_mh (same Philox addressing, same operation order): for a built-in model both forms walk the same
 // trajectory, which is how the tests pin this one.
 //   step i of every chain:  k_mhs_propose  ->  <lp[c], ll[c] of d_prop[c][0..k)>  ->  k_mhs_accept
+// The step index is a kernel argument, or (argument < 0) a per-chain counter in the state, so that one captured step can be replayed
+// as a CUDA graph.
 #include "common.cuh"
 #include "eval.cuh"
 #include "mh_common.cuh"
@@ -14,7 +16,7 @@ namespace {
 
 // per-chain scratch behind the statistics block (which itself carries the current point, its logP and the running sums)
 enum { MHS_CUR_LP = 0, MHS_CUR_LL, MHS_CUR_EXP, MHS_U, MHS_MOD, MHS_MF_DYN, MHS_MF_N, MHS_MF_SX, MHS_MF_SY, MHS_MF_SXY, MHS_MF_Y0,
-       MHS_TH0 /* [k] */ };
+       MHS_STEP /* the chain's next step (counter mode: step argument < 0, e.g. inside a replayed CUDA graph) */, MHS_TH0 /* [k] */ };
 __host__ __device__ inline int mhs_state_doubles(int k) { return MHS_TH0 + k; }
 
 struct StepOut {
@@ -73,7 +75,7 @@ __global__ void __launch_bounds__(128) k_mhs_begin(const __grid_constant__ DevMH
     if (M.burn_in <= 0) mhs_add_row(sb, sx + MHS_TH0, k, 0, th, lpr, exp(lpr));
     sb[PEUQSE_MH_STAT_LASTLOGP] = cur_sum;
     sx[MHS_CUR_LP] = cur_lp; sx[MHS_CUR_LL] = cur_ll; sx[MHS_CUR_EXP] = exp(cur_sum);
-    sx[MHS_U] = 0.0; sx[MHS_MOD] = 1.0;
+    sx[MHS_U] = 0.0; sx[MHS_MOD] = 1.0; sx[MHS_STEP] = 1.0;
     MapFind mf;
     mf.init();
     sx[MHS_MF_DYN] = mf.dyn; sx[MHS_MF_N] = mf.n; sx[MHS_MF_SX] = mf.sx; sx[MHS_MF_SY] = mf.sy; sx[MHS_MF_SXY] = mf.sxy; sx[MHS_MF_Y0] = mf.y0;
@@ -86,6 +88,8 @@ __global__ void __launch_bounds__(128) k_mhs_propose(const __grid_constant__ Dev
     const int k = M.k;
     const double* sb = stats + c * PEUQSE_MH_STAT_DOUBLES(k);
     double* sx = state + c * mhs_state_doubles(k);
+    if (i < 0) i = (long long)sx[MHS_STEP];
+    if (i >= M.n_steps) return;                                   // a replay beyond the run's last step does nothing
     double z[PQ_MAXK], delta[PQ_MAXK], u, um;
     draws_thread<PQ_MAXK>(M, (unsigned long long)(M.chain_offset + c), (unsigned long long)(M.first_step + i), z, u, um);
     make_delta<PQ_MAXK>(M, z, delta);
@@ -114,6 +118,10 @@ __global__ void __launch_bounds__(128) k_mhs_accept(const __grid_constant__ DevM
     const long long C = M.n_chains;
     double* sb = stats + c * PEUQSE_MH_STAT_DOUBLES(k);
     double* sx = state + c * mhs_state_doubles(k);
+    const bool counter = i < 0;
+    if (counter) i = (long long)sx[MHS_STEP];
+    if (i >= M.n_steps) return;
+    if (counter) sx[MHS_STEP] = (double)(i + 1);
     double cur_sum = sb[PEUQSE_MH_STAT_LASTLOGP];
     const double lp_p = lp_prop[c], ll_p = ll_prop[c];
     const double sum_p = ll_p + lp_p;
@@ -198,7 +206,7 @@ extern "C" int peuqse_mhs_propose(const peuqse_mh_spec* s, int64_t step, double*
                                   double* d_deltas, double* d_us, void* stream) {
     DevMH M;
     if (int rc = mhs_spec(s, M)) return rc;
-    if (!d_state || !d_stats || !d_prop || step < 1 || step >= s->n_steps) return pq_set_error(PEUQSE_ERR_INVALID, "bad argument");
+    if (!d_state || !d_stats || !d_prop || step == 0 || step >= s->n_steps) return pq_set_error(PEUQSE_ERR_INVALID, "bad argument");
     const StepOut out{nullptr, nullptr, nullptr, nullptr, d_deltas, d_us};
     k_mhs_propose<<<mhs_blocks(M), 128, 0, (cudaStream_t)stream>>>(M, step, d_state, d_stats, d_prop, out);
     PQ_CUDA_OK(cudaGetLastError());
@@ -210,7 +218,7 @@ extern "C" int peuqse_mhs_accept(const peuqse_mh_spec* s, int64_t step, const do
                                  double* d_logprior, double* d_loglik, void* stream) {
     DevMH M;
     if (int rc = mhs_spec(s, M)) return rc;
-    if (!d_prop || !d_logprior_prop || !d_loglik_prop || !d_state || !d_stats || step < 1 || step >= s->n_steps)
+    if (!d_prop || !d_logprior_prop || !d_loglik_prop || !d_state || !d_stats || step == 0 || step >= s->n_steps)
         return pq_set_error(PEUQSE_ERR_INVALID, "bad argument");
     const StepOut out{d_samples, d_logp, d_logprior, d_loglik, nullptr, nullptr};
     k_mhs_accept<<<mhs_blocks(M), 128, 0, (cudaStream_t)stream>>>(M, step, d_prop, d_logprior_prop, d_loglik_prop, d_state, d_stats, out);

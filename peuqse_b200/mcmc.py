@@ -79,24 +79,57 @@ def mh_needs_lockstep(pe):
 def _mh_lockstep(pe, L, spec, th0, out):
     """doMetropolisHastings' loop (IP.py:2626-2675) with every chain's step taken together: k_mhs_propose, the batched
     log-prior / log-likelihood of the proposals (pe.getLogP_batch: built-in kernels, a torch simulator, the user's callables),
-    k_mhs_accept.  Everything stays on the device and on one stream; nothing is read back inside the loop."""
+    k_mhs_accept.  Everything stays on the device and on one stream; nothing is read back inside the loop.  The step index lives
+    in the device state (counter mode), so after one eager step the propose -> evaluate -> accept sequence is captured ONCE as a
+    CUDA graph and replayed for the remaining steps (parameter_estimation_settings['mcmc_lockstep_graph'] = False keeps the eager
+    loop; a simulator or callable that cannot be captured -- it synchronises, say -- falls back to it by itself)."""
     Cn, k = th0.shape
     dev = th0.device
-    st = _lib.current_stream()
+    n = int(spec.n_steps)
     state = torch.empty((Cn, int(L.peuqse_mhs_state_doubles(k))), dtype=torch.float64, device=dev)
     prop = torch.empty((Cn, k), dtype=torch.float64, device=dev)
     rows = (_lib.ptr(out['samples']), _lib.ptr(out['logp']), _lib.ptr(out['logprior']), _lib.ptr(out['loglik']))
-    _, lp, ll = pe.getLogP_batch(th0, return_parts=True)
-    _lib.check(L.peuqse_mhs_begin(C.byref(spec), _lib.ptr(th0), _lib.ptr(lp), _lib.ptr(ll), _lib.ptr(state), _lib.ptr(out['stats']), *rows, st))
-    for i in range(1, int(spec.n_steps)):
-        _lib.check(L.peuqse_mhs_propose(C.byref(spec), i, _lib.ptr(state), _lib.ptr(out['stats']), _lib.ptr(prop),
+
+    def step():
+        st = _lib.current_stream()
+        _lib.check(L.peuqse_mhs_propose(C.byref(spec), -1, _lib.ptr(state), _lib.ptr(out['stats']), _lib.ptr(prop),
                                         _lib.ptr(out['deltas']), _lib.ptr(out['us']), st))
         _, lp, ll = pe.getLogP_batch(prop, return_parts=True)
-        _lib.check(L.peuqse_mhs_accept(C.byref(spec), i, _lib.ptr(prop), _lib.ptr(lp), _lib.ptr(ll), _lib.ptr(state),
+        _lib.check(L.peuqse_mhs_accept(C.byref(spec), -1, _lib.ptr(prop), _lib.ptr(lp), _lib.ptr(ll), _lib.ptr(state),
                                        _lib.ptr(out['stats']), *rows, st))
-    _lib.check(L.peuqse_mhs_finish(C.byref(spec), _lib.ptr(state), _lib.ptr(out['stats']), st))
-    pe.gpu_launches += 2 * int(spec.n_steps)          # begin, finish, two kernels per step; getLogP_batch counts its own
+        return lp, ll
+    _, lp, ll = pe.getLogP_batch(th0, return_parts=True)
+    _lib.check(L.peuqse_mhs_begin(C.byref(spec), _lib.ptr(th0), _lib.ptr(lp), _lib.ptr(ll), _lib.ptr(state), _lib.ptr(out['stats']), *rows,
+                                  _lib.current_stream()))
+    done = 1
+    if n > 1:
+        step()                                            # eager: allocator pools, library workspaces and the user's callables warm up
+        done = 2
+    use_graph = pe.UserInput.parameter_estimation_settings.get('mcmc_lockstep_graph', 'auto')
+    out['graph'] = False
+    if use_graph is not False and str(use_graph).lower() != 'false' and n - done >= 16:
+        launches = pe.gpu_launches
+        try:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                keep = step()                             # noqa: F841  (the graph's pool owns these buffers)
+            per_step = pe.gpu_launches - launches
+            for _ in range(n - done):
+                g.replay()
+            pe.gpu_launches = launches + per_step * (n - done)
+            done = n
+            out['graph'] = True
+        except Exception as e:                            # not capturable: the eager loop below takes over from the same state
+            torch.cuda.synchronize()
+            pe.gpu_launches = launches
+            out['graph_error'] = repr(e)
+    for _ in range(done, n):
+        step()
+    _lib.check(L.peuqse_mhs_finish(C.byref(spec), _lib.ptr(state), _lib.ptr(out['stats']), _lib.current_stream()))
+    pe.gpu_launches += 2 * n                              # begin, finish, two kernels per step; getLogP_batch counts its own
     return out
+
 
 
 class _RowsOnDevice:

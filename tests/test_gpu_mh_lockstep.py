@@ -29,6 +29,13 @@ def test_lockstep_walks_the_persistent_kernels_trajectory(env):
             assert np.array_equal(a[n], b[n]), (kw, n)
         np.testing.assert_allclose(b['stats'], a['stats'], rtol=1e-12, atol=0, err_msg=str(kw))
         assert 0.05 < a['stats'][:, 0].mean() / 699 < 0.95
+    # the remaining steps run as replays of ONE captured step (CUDA graph); the eager loop gives the same rows
+    g = mh_launch(PE, start, 700, 60, 11, chol, lockstep=True)
+    assert g['graph'] is True, g.get('graph_error')
+    PE.UserInput.parameter_estimation_settings['mcmc_lockstep_graph'] = False
+    e = mh_launch(PE, start, 700, 60, 11, chol, lockstep=True)
+    assert e['graph'] is False and torch.equal(e['samples'], g['samples']) and torch.equal(e['stats'], g['stats'])
+    PE.UserInput.parameter_estimation_settings['mcmc_lockstep_graph'] = 'auto'
     # a non-diagonal proposal covariance (full lower-triangular factor)
     Lf = np.linalg.cholesky(np.array([[400., 300.], [300., 1600.]]))
     a = _mh_out(mh_launch(PE, start, 300, 0, 3, Lf, export_draws=True, lockstep=False))
@@ -82,7 +89,9 @@ def test_lockstep_torch_simulator_custom_functions_and_full_covariance_against_t
                                'mcmc_relative_step_length': 0.002, 'mcmc_random_seed': 4, 'mcmc_threshold_filter_samples': False,
                                'mcmc_info_gain_returned': 'log_ratio', 'exportLog': False}, **kw)
         assert mh_needs_lockstep(PE), name
-        out = _mh_out(mh_launch(PE, start, 250, 30, 6, step_cholesky(PE.Q_covmat, 0.002), export_draws=True))
+        raw = mh_launch(PE, start, 250, 30, 6, step_cholesky(PE.Q_covmat, 0.002), export_draws=True)
+        assert raw['graph'] is True, (name, raw.get('graph_error'))           # every one of these is capturable
+        out = _mh_out(raw)
         ref = orc.mh_chains_batch(P, start, out['deltas'], out['us'], sim)
         acc = np.any(out['samples'][1:] != out['samples'][:-1], axis=2)
         assert np.array_equal(acc, ref['accepted'][1:]), name
@@ -117,3 +126,26 @@ def test_lockstep_multistart_of_chains(env):
     assert np.array_equal(A.permutations_MAP_logP_and_parameters_values, B.permutations_MAP_logP_and_parameters_values)
     assert np.array_equal(A.map_parameter_set, B.map_parameter_set) and A.map_logP == B.map_logP
     assert np.array_equal(A.post_burn_in_samples, B.post_burn_in_samples)
+
+
+def test_lockstep_falls_back_to_the_eager_loop_when_the_simulator_cannot_be_captured(env):
+    """A simulator that synchronises with the host (here: .item()) cannot be recorded into a CUDA graph: the driver notices, keeps the
+    state and finishes the run with the eager loop -- same chain as a capturable simulator of the same function."""
+    PEUQSE, orc, _, torch = env
+    from peuqse_b200.mcmc import mh_launch, step_cholesky
+    X = torch.tensor(X00, dtype=torch.float64, device='cuda')
+    f = lambda t: (X[None, :] - t[:, :1]) ** 2 + t[:, 1:2]
+
+    def f_sync(t):
+        float(t.sum().item())                                          # a host round trip
+        return f(t)
+    runs = []
+    for fn in (f, f_sync):
+        PE = make_pe(PEUQSE, PEUQSE.TorchSimulator(fn), Y00, S00, [200, 500], [100, 200])
+        runs.append(mh_launch(PE, np.tile([200., 500.], (3, 1)), 120, 10, 2, step_cholesky(PE.Q_covmat, 0.2)))
+    assert runs[0]['graph'] is True and runs[1]['graph'] is False and 'graph_error' in runs[1]
+    assert torch.equal(runs[0]['samples'], runs[1]['samples']) and torch.equal(runs[0]['logp'], runs[1]['logp'])
+    # and the chain is the built-in model's (same function): same accept / reject decisions
+    PEb = make_pe(PEUQSE, PEUQSE.QuadraticModel(X00), Y00, S00, [200, 500], [100, 200])
+    b = mh_launch(PEb, np.tile([200., 500.], (3, 1)), 120, 10, 2, step_cholesky(PEb.Q_covmat, 0.2))
+    np.testing.assert_allclose(runs[0]['samples'].cpu().numpy(), b['samples'].cpu().numpy(), rtol=1e-12)
