@@ -409,9 +409,9 @@ def c1_secondary(PEUQSE, torch, dist, rank, world):
     UI.model['InputParametersPriorValuesUncertainties'] = SD
     UI.model['simulateByInputParametersOnlyFunction'] = PEUQSE.QuadraticModel(X00)
     UI.parameter_estimation_settings.update({'mcmc_length': L, 'mcmc_relative_step_length': C1["step"], 'mcmc_random_seed': C1["seed"],
-                                             'mcmc_exportLog': False, 'exportLog': False})
+                                             'mcmc_exportLog': False, 'exportLog': False, 'mcmc_nchains': world})
     PE = PEUQSE.parameter_estimation(UI)
-    # one chain, end to end: host settings in, [MAP, mu_AP, stdap, evidence, info_gain, samples, logP] on the host out
+    # one chain (per GPU: chains are what shards), end to end: host settings in, [MAP, mu_AP, stdap, evidence, info_gain, samples, logP] on the host out
     times = []
     for i in range(7):
         torch.cuda.synchronize()
@@ -419,7 +419,10 @@ def c1_secondary(PEUQSE, torch, dist, rank, world):
         res = PE.doMetropolisHastings()
         torch.cuda.synchronize()
         times.append(time.perf_counter() - t0)
-    one_s = float(np.median(times[2:]))
+    te = torch.tensor([float(np.median(times[2:]))], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    one_s = float(te.item())
     rows = int(np.shape(res[5])[0])
     # the same chain as 65 536 replicas per GPU, in-kernel moments
     cn = C1["replicas"]
@@ -456,7 +459,7 @@ def c1_secondary(PEUQSE, torch, dist, rank, world):
                                 "is small by construction; the kernel's SASS holds 1205 fp64 instructions statically (slow paths of the "
                                 "transcendentals included), no dynamic count was captured",
                         "traffic": None},
-           "e2e": {"value": (L - 1) / one_s, "unit": "chain-steps/s", "api": "PE_object.doMetropolisHastings()", "chains": 1,
+           "e2e": {"value": world * (L - 1) / one_s, "unit": "chain-steps/s", "api": "PE_object.doMetropolisHastings()", "chains": world,
                    "seconds_per_call": one_s, "post_burn_in_rows_returned": rows,
                    "h2d_bytes_per_step": 16, "d2h_bytes_per_step": int(rows * 8 * (PE.k + 2))}}
     if world == 1 and rank == 0:
