@@ -135,6 +135,17 @@ int peuqse_logp_batch(const peuqse_problem* p, const double* d_theta, int64_t B,
 int peuqse_logp_from_sim(const peuqse_problem* p, const double* d_theta, const double* d_sim, int64_t B,
                          double* d_logp, double* d_logprior, double* d_loglik, void* stream);
 
+/*
+ * replaces: getLogLikelihood_byResponses (IP.py:2899-2980) when model['responses_simulation_uncertainties'] is a FUNCTION of the
+ * parameters (IP.py:563-572, 2883-2896): the caller evaluated d_sim[B][n_total] and the simulation's standard deviations
+ * d_sim_sd[B][n_total]; their squares are added to the observed variances d_var_obs[n_total] point by point (IP.py:2925-2927), so
+ * the density has no hoistable part.  Responses with 1-D (variance) uncertainties only.  resp_n[n_resp]: values per response
+ * (host); per_value[r] != 0: the response is longer than responses_observed_max_covmat_size and is a sum of one scalar density per
+ * value, -inf replaced by -1E100 (IP.py:2961-2975).  A NaN among a row's simulated values gives -inf (IP.py:2866-2882).  d_loglik[B].
+ */
+int peuqse_loglik_simvar(const double* d_sim, const double* d_sim_sd, const double* d_y, const double* d_var_obs,
+                         const int32_t* resp_n, const int32_t* per_value, int32_t n_resp, int64_t B, double* d_loglik, void* stream);
+
 /* replaces: getLogPrior alone (IP.py:2756-2794, bounds 2796-2805) -- for callers whose likelihood is their own
  * (UserInput.model['custom_logLikelihood'], IP.py:2854-2857).  d_logprior[B]. */
 int peuqse_logprior_batch(const peuqse_problem* p, const double* d_theta, int64_t B, double* d_logprior, void* stream);

@@ -304,6 +304,32 @@ def log_likelihood_point(P: OracleProblem, sim) -> float:
     return total
 
 
+def log_likelihood_simvar_point(P: OracleProblem, sim, sim_sd) -> float:
+    """getLogLikelihood when model['responses_simulation_uncertainties'] is a function of the parameters (IP.py:563-572,
+    2883-2896): `sim_sd` (standard deviations, shaped like `sim`) is squared by returnShapedResponseCovMat and ADDED to the
+    observed variances (IP.py:2925-2927) before the same per-response densities as log_likelihood_point.  Responses with 1-D
+    (variance) uncertainties."""
+    if sim is None:
+        return float('-inf')
+    sims, sds = _nest(sim), _nest(sim_sd)
+    if any(np.isnan(s).any() for s in sims):
+        return float('-inf')
+    total = 0
+    for r, blk in enumerate(P.responses):
+        cov = np.asarray(blk.cov, dtype=float) + np.square(np.asarray(sds[r], dtype=float))      # IP.py:2927
+        if not blk.per_value:
+            ll = multivariate_normal.logpdf(mean=sims[r], x=blk.y, cov=cov)
+        else:
+            ll = 0
+            for j in range(len(sims[r])):
+                cur = multivariate_normal.logpdf(mean=sims[r][j], x=blk.y[j], cov=cov[j])
+                if float(cur) == float('-inf'):
+                    cur = -1E100
+                ll = cur + ll
+        total = total + ll
+    return total
+
+
 def log_p_point(P: OracleProblem, theta, simulate: Callable) -> float:
     """getLogP, IP.py:1647-1654."""
     lp = log_prior_point(P, theta)

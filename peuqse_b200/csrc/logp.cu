@@ -218,3 +218,77 @@ extern "C" int peuqse_logp_from_sim(const peuqse_problem* p, const double* d_the
 #undef PQ_LOGP_EXT
     return PEUQSE_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Likelihood whose variances change with the point: model['responses_simulation_uncertainties'] as a FUNCTION of the parameters
+// (IP.py:563-572, 2883-2896).  The simulation's standard deviations are squared and added to the observed variances
+// (IP.py:2925-2927), so nothing of the density can be hoisted: per point and response
+//     -0.5 (n_r log 2pi + sum_j log v_j + sum_j (y_j - sim_j)^2 / v_j),  v_j = var_obs_j + sd_j^2          (one logpdf, IP.py:2956)
+// or, for a response longer than responses_observed_max_covmat_size, the sum of one scalar density per value with -inf replaced by
+// -1E100 (IP.py:2961-2975).  A NaN among a point's simulated values makes its likelihood -inf (IP.py:2866-2882).
+// One warp per point, lanes strided over the observations; sums in a fixed tree (deterministic, independent of the batch).
+// ---------------------------------------------------------------------------------------------
+#define PQ_SIMVAR_MAX_RESP 64
+struct SimVarResp {
+    int n_resp;
+    int off[PQ_SIMVAR_MAX_RESP + 1];
+    int per_value[PQ_SIMVAR_MAX_RESP];
+};
+
+__global__ void __launch_bounds__(128) k_loglik_simvar(const __grid_constant__ SimVarResp R, const double* __restrict__ sim,
+                                                       const double* __restrict__ sd, const double* __restrict__ y,
+                                                       const double* __restrict__ var_obs, long long B, double* __restrict__ out) {
+    const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (b >= B) return;
+    const int n_total = R.off[R.n_resp];
+    const double* s = sim + b * n_total;
+    const double* e = sd + b * n_total;
+    const double LOG2PI = 1.8378770664093453;
+    double ll = 0.0;
+    int bad = 0;
+    for (int r = 0; r < R.n_resp; ++r) {
+        const int lo = R.off[r], hi = R.off[r + 1];
+        double a_log = 0.0, a_q = 0.0, a_pv = 0.0;
+        for (int j = lo + lane; j < hi; j += 32) {
+            const double sj = s[j], ej = e[j];
+            bad |= (sj != sj);
+            const double v = var_obs[j] + ej * ej;
+            const double d = y[j] - sj;
+            const double lg = log(v), q = d * d / v;
+            if (R.per_value[r]) {
+                double t = -0.5 * (LOG2PI + lg + q);
+                if (pq_is_neg_inf(t)) t = -1E100;                      // IP.py:2973-2975
+                a_pv += t;
+            } else {
+                a_log += lg;
+                a_q += q;
+            }
+        }
+        if (R.per_value[r]) ll += warp_sum(a_pv);
+        else ll += -0.5 * ((double)(hi - lo) * LOG2PI + warp_sum(a_log) + warp_sum(a_q));
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) out[b] = bad ? pq_neg_inf() : ll;
+}
+
+extern "C" int peuqse_loglik_simvar(const double* d_sim, const double* d_sim_sd, const double* d_y, const double* d_var_obs,
+                                    const int32_t* resp_n, const int32_t* per_value, int32_t n_resp, int64_t B, double* d_loglik,
+                                    void* stream) {
+    if (!d_sim || !d_sim_sd || !d_y || !d_var_obs || !resp_n || !per_value || !d_loglik || B < 0)
+        return pq_set_error(PEUQSE_ERR_INVALID, "bad argument");
+    if (n_resp < 1 || n_resp > PQ_SIMVAR_MAX_RESP) return pq_set_error(PEUQSE_ERR_INVALID, "1 <= n_resp <= 64");
+    if (B == 0) return PEUQSE_OK;
+    SimVarResp R;
+    R.n_resp = n_resp;
+    R.off[0] = 0;
+    for (int r = 0; r < n_resp; ++r) {
+        if (resp_n[r] < 1) return pq_set_error(PEUQSE_ERR_INVALID, "empty response");
+        R.off[r + 1] = R.off[r] + resp_n[r];
+        R.per_value[r] = per_value[r] ? 1 : 0;
+    }
+    const long long blocks = (B * 32 + 127) / 128;
+    k_loglik_simvar<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(R, d_sim, d_sim_sd, d_y, d_var_obs, B, d_loglik);
+    PQ_CUDA_OK(cudaGetLastError());
+    return PEUQSE_OK;
+}

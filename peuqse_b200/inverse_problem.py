@@ -83,9 +83,13 @@ class parameter_estimation:
             if len(obs_unc) == 1:
                 obs_unc = obs_unc[0]
         sim_unc = UI.model.get('responses_simulation_uncertainties')
-        if callable(sim_unc):
-            raise NotImplementedError("responses_simulation_uncertainties as a function of the parameters is a per-point "
-                                      "Python callback; not part of the accelerated path")
+        # a FUNCTION of the parameters (IP.py:563-572): here a VECTORISED torch callable f(theta[B,k]) -> standard deviations
+        # [B, n_total] (or a list of [B, n_r] per response); its squares are added to the observed variances point by point
+        # (IP.py:2925-2927) by peuqse_loglik_simvar -- installed below as the likelihood of every batched path
+        self._sim_unc_fn = sim_unc if callable(sim_unc) else None
+        if self._sim_unc_fn is not None:
+            sim_unc = None
+            UI.responses_simulation_uncertainties = self._sim_unc_fn                                   # IP.py:276
         H = build_host_problem(UI.model['InputParameterPriorValues'], UI.model['InputParametersPriorValuesUncertainties'],
                                observed, obs_unc,
                                lower_bounds=UI.model['InputParameterPriorValues_lowerBounds'],
@@ -151,6 +155,8 @@ class parameter_estimation:
             sim._owner = self
         self._L = _lib.load()
         self.k = H.k
+        if self._sim_unc_fn is not None and self.custom_logLikelihood is None:
+            self._setup_simulation_uncertainty_function(H)
         self.prepareResponsesForSplitLikelihood = False   # the reference's fall-back mode is not replicated
         self.gpu_launches = 0
 
@@ -208,6 +214,42 @@ class parameter_estimation:
                                                     _lib.ptr(ll), _lib.current_stream()))
         self.gpu_launches += 1
         return (logp, lp, ll) if return_parts else logp
+
+    def _setup_simulation_uncertainty_function(self, H):
+        var = []
+        for r, c in enumerate(H.responses_cov):
+            c = np.asarray(c, dtype=float)
+            if c.ndim == 2:
+                if np.count_nonzero(c - np.diag(np.diagonal(c))):
+                    raise NotImplementedError("responses_simulation_uncertainties as a function of the parameters next to a full "
+                                              "observed covariance matrix needs a factorisation per point; not part of the accelerated path")
+                c = np.diagonal(c)
+            var.append(c.reshape(-1))
+        dev = _dev()
+        self._simvar_y = torch.as_tensor(np.concatenate([np.asarray(y, dtype=float).reshape(-1) for y in H.responses_observed]), device=dev)
+        self._simvar_var = torch.as_tensor(np.concatenate(var), device=dev)
+        n = [int(len(v)) for v in var]
+        maxcov = self.UserInput.responses['responses_observed_max_covmat_size']
+        self._simvar_n = (C.c_int32 * len(n))(*n)
+        self._simvar_pv = (C.c_int32 * len(n))(*[1 if m > maxcov else 0 for m in n])                  # IP.py:2952
+        self._simvar_total = int(sum(n))
+        self.custom_logLikelihood = self._loglik_with_simulation_uncertainties
+
+    def _loglik_with_simulation_uncertainties(self, th):
+        """(logLikelihood[B], sim[B, n_total]) with the covariance observed variances + f(theta)^2 (IP.py:2883-2896, 2925-2927)."""
+        B = th.shape[0]
+        sim = self.simulate_batch(th).contiguous()
+        sd = self._sim_unc_fn(th)
+        if isinstance(sd, (list, tuple)):
+            sd = torch.cat([torch.as_tensor(x, dtype=torch.float64, device=th.device).reshape(B, -1) for x in sd], dim=1)
+        sd = torch.as_tensor(sd, dtype=torch.float64, device=th.device).reshape(B, self._simvar_total).contiguous()
+        if sim.shape != sd.shape:
+            raise ValueError(f"responses_simulation_uncertainties returned {tuple(sd.shape)}, the simulation {tuple(sim.shape)}")
+        ll = torch.empty(B, dtype=torch.float64, device=th.device)
+        _lib.check(self._L.peuqse_loglik_simvar(_lib.ptr(sim), _lib.ptr(sd), _lib.ptr(self._simvar_y), _lib.ptr(self._simvar_var),
+                                                self._simvar_n, self._simvar_pv, len(self._simvar_n), B, _lib.ptr(ll),
+                                                _lib.current_stream()))
+        return ll, sim
 
     def _getLogP_batch_custom(self, th, return_parts):
         """getLogP with a user-supplied prior and / or likelihood (vectorised torch callables, see __init__): the part the user

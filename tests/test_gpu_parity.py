@@ -1550,3 +1550,48 @@ def test_custom_log_prior_and_log_likelihood(env):
     PEb = make_pe(PEUQSE, PEUQSE.LinearModel(Phi), list(y), list(np.full(n, sig)), [0.0] * k, [2.0] * k, custom_logPrior=my_prior,
                   InputParameterPriorValues_lowerBounds=[-0.1] * k, InputParameterPriorValues_upperBounds=[0.1] * k)
     assert np.isfinite(PEb.getLogP([1.0, 1.0, 1.0]))
+
+
+def test_simulation_uncertainties_as_a_function_of_the_parameters(env, golden):
+    """model['responses_simulation_uncertainties'] = f(theta) (IP.py:563-572, 2883-2896, 2925-2927) as a vectorised torch callable: the
+    covariance of the likelihood changes with every point (peuqse_loglik_simvar).  Against the unmodified reference's getLogP /
+    getLogPrior / getLogLikelihood (tests/golden/simunc.npz), one logpdf per response and one per value; with a built-in model and with
+    a torch simulator; then the batched drivers run on it."""
+    PEUQSE, orc, _, torch = env
+    g = golden("simunc")
+    X = torch.tensor(X00, dtype=torch.float64, device='cuda')
+    f = lambda t: (X[None, :] - t[:, :1]) ** 2 + t[:, 1:2]
+    sd = lambda t: 0.03 * torch.abs(f(t)) + 50.0 * (1.0 + torch.abs(t[:, 1:2]) / 500.0)
+    th = g['simunc_thetas']
+    for tag, maxcov in (('mvn', 100), ('per_value', 2)):
+        for model in (PEUQSE.QuadraticModel(X00), PEUQSE.TorchSimulator(f)):
+            PE = make_pe(PEUQSE, model, Y00, S00, [200, 500], [100, 200], responses_simulation_uncertainties=sd,
+                         settings={'responses_observed_max_covmat_size': maxcov, 'mcmc_length': 400, 'mcmc_burn_in': 40,
+                                   'mcmc_relative_step_length': 0.2, 'mcmc_random_seed': 1, 'mcmc_nchains': 2, 'exportLog': False,
+                                   'multistart_initialPointsDistributionType': 'grid', 'multistart_gridsearchSamplingInterval': [20, 40],
+                                   'multistart_gridsearchSamplingRadii': [5, 5]})
+            lp, pr, ll = parts(PE, th)
+            want = g['simunc_' + tag]
+            np.testing.assert_allclose(ll, want[:, 2], rtol=1e-12)
+            np.testing.assert_allclose(lp, want[:, 0], rtol=1e-12)
+            assert np.array_equal(pr, want[:, 1])
+            assert abs(PE.getLogP(th[3]) - want[3, 0]) <= 1e-12 * abs(want[3, 0])
+            l1, s1 = PE.getLogLikelihood(th[3])
+            assert abs(l1 - want[3, 2]) <= 1e-12 * abs(want[3, 2]) and np.allclose(np.ravel(s1), (np.asarray(X00) - th[3, 0]) ** 2 + th[3, 1])
+    # a NaN among the simulated values: zero likelihood (IP.py:2866-2882)
+    bad = th[:4].copy()
+    bad[1, 0] = np.nan
+    assert parts(PE, bad)[2][1] == float('-inf')
+    # the drivers: grid multistart (MAP = the best grid point by the reference's formula), lock-step Metropolis-Hastings, ensemble slice sampling
+    PE.doMultiStart()
+    grid = orc.grid_decode([200., 500.], [20, 40], [5, 5], np.arange(121))
+    P = orc.build_problem([200, 500], [100, 200], Y00, S00, max_covmat_size=2)
+    pt, _ = orc.sim_quadratic(X00)
+    x = np.asarray(X00, dtype=float)
+    sd_np = lambda t: 0.03 * np.abs((x - t[0]) ** 2 + t[1]) + 50.0 * (1.0 + np.abs(t[1]) / 500.0)
+    ref = np.array([orc.log_likelihood_simvar_point(P, pt(tuple(t)), sd_np(t)) + orc.log_prior_point(P, t) for t in grid])
+    assert PE.map_index == int(np.argmax(ref)) and abs(PE.map_logP - ref.max()) <= 1e-12 * abs(ref.max())
+    res = PE.doMetropolisHastings()
+    assert len(res) == 7 and np.all(np.isfinite(PE.post_burn_in_log_posteriors_un_normed_vec))
+    lp2 = parts(PE, PE.post_burn_in_samples[:50])[0]
+    np.testing.assert_allclose(lp2, np.ravel(PE.post_burn_in_log_posteriors_un_normed_vec)[:50], rtol=1e-12)

@@ -71,6 +71,22 @@ def test_example00_points(golden):
     check_vals(ex00(), pt, bt, g['ex00_thetas'], g['ex00_logP_prior_lik'])
 
 
+def test_simulation_uncertainties_as_a_function_vs_reference(golden):
+    """responses_simulation_uncertainties = f(theta) (tests/golden/make_golden_simunc.py ran the unmodified reference): the
+    restatement reproduces the reference's likelihood bit for bit, one logpdf per response and one per value."""
+    g = golden("simunc")
+    pt, _ = orc.sim_quadratic(X00)
+    x = np.asarray(X00, dtype=float)
+    sd = lambda th: 0.03 * np.abs((x - th[0]) ** 2 + th[1]) + 50.0 * (1.0 + np.abs(th[1]) / 500.0)
+    for tag, maxcov in (('mvn', 100), ('per_value', 2)):
+        P = orc.build_problem([200, 500], [100, 200], Y00, S00, max_covmat_size=maxcov)
+        rows = g['simunc_' + tag]
+        for th, row in zip(g['simunc_thetas'], rows):
+            ll = orc.log_likelihood_simvar_point(P, pt(tuple(th)), sd(th))
+            assert ll == row[2] and orc.log_prior_point(P, th) == row[1]
+            assert (ll + row[1] == row[0]) or (row[1] == float('-inf') and row[0] == float('-inf'))
+
+
 def test_grid_order(golden):
     g = golden("example00")
     for name in ("g3", "g3d"):
