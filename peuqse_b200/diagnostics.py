@@ -160,7 +160,7 @@ def convergence_diagnostics(pe, discrete_chains_post_burn_in_samples=None):
     taus, act_windows, n_act = autocorr_times(x)                                    # IP.py:3916-3948
     pe.gpu_launches += n_act
     taus = taus.cpu().numpy()
-    names = list(pe.UserInput.model['parameterNamesAndMathTypeExpressionsDict'].keys()) if hasattr(pe, 'UserInput') else []
+    names = list(getattr(pe.UserInput, 'parameterNamesList', pe.UserInput.model['parameterNamesAndMathTypeExpressionsDict'])) if hasattr(pe, 'UserInput') else []
     if len(names) != taus.shape[1]:
         names = ['parameter_%d' % d for d in range(taus.shape[1])]
     act_each = {name: taus[:, d] for d, name in enumerate(names)}                   # IP.py:3938-3942

@@ -32,6 +32,79 @@ class parameter_estimation:
 
     def __init__(self, UserInput=None):
         self.UserInput = UI = UserInput
+        reduced = list(UI.model.get('reducedParameterSpace', []))
+        if len(reduced) and not getattr(UI, '_reduced_inner', False):
+            # model['reducedParameterSpace'] (IP.py:406-408, 519-561, 574-606): the engine is built on the reduced problem; UserInput.model
+            # itself stays the user's full-space dictionary, as in the reference
+            full_model = UI.model
+            UI.model = self._reduced_model(UI, reduced)
+            try:
+                self._init(UI)
+            finally:
+                UI.model = full_model
+            self.reducedParameterSpaceOn = True                                                        # IP.py:52
+            return
+        self._init(UI)
+        self.reducedParameterSpaceOn = False
+
+    @staticmethod
+    def _reduced_model(UI, idx):
+        """The model dictionary of the reduced problem.  Priors, bounds and names keep the ORIGINAL order of the selected entries
+        (returnReducedIterable tests membership, IP.py:3559-3564) while reduced value j is placed at full index idx[j] by the
+        simulation wrapper (IP.py:585-589); the two differ only for an unsorted index list, and the reference's behaviour is kept.
+        The other parameters stay at model['InputParameterInitialGuess'] (the prior values when no guess is given)."""
+        import copy
+        full = UI.model
+        kfull = len(full['InputParameterPriorValues'])
+        keep = [i for i in range(kfull) if i in idx]
+        guess = full.get('InputParameterInitialGuess', [])
+        if isinstance(guess, str):
+            raise NotImplementedError("reducedParameterSpace with a pickled initial guess")
+        guess = np.array(full['InputParameterPriorValues'] if guess is None or len(guess) == 0 else guess, dtype=float).reshape(-1)
+        m = dict(full)
+        take = lambda a: [a[i] for i in keep]
+        m['reducedParameterSpace'] = []
+        m['InputParameterPriorValues'] = take(list(full['InputParameterPriorValues']))
+        unc = np.asarray(full['InputParametersPriorValuesUncertainties'], dtype=float)
+        m['InputParametersPriorValuesUncertainties'] = unc[np.ix_(keep, keep)] if unc.ndim == 2 else list(unc[keep])
+        for b in ('InputParameterPriorValues_lowerBounds', 'InputParameterPriorValues_upperBounds'):
+            if len(full[b]):
+                m[b] = take(list(full[b]))
+        m['InputParameterInitialGuess'] = list(guess[keep])
+        names = full['parameterNamesAndMathTypeExpressionsDict']
+        if len(names) == 0:
+            names = {str(i): 'ParInd_' + str(i) for i in range(kfull)}                                 # IP.py:68-71
+        m['parameterNamesAndMathTypeExpressionsDict'] = {key: names[key] for j, key in enumerate(names) if j in idx}
+        sim, post = full['simulateByInputParametersOnlyFunction'], full.get('simulationOutputProcessingFunction')
+        m['simulationOutputProcessingFunction'] = None                       # applied inside the wrapper (IP.py:522-523, 600-603)
+        cols = torch.as_tensor(list(idx), dtype=torch.long)
+        base = torch.as_tensor(guess, dtype=torch.float64)
+        if isinstance(sim, BuiltinModel):
+            if post is not None:
+                raise NotImplementedError("simulationOutputProcessingFunction cannot follow a built-in CUDA model; fold it into a TorchSimulator")
+            # a built-in model evaluates full parameter vectors: an inner engine on the full space does the simulation
+            import types
+            inner_ui = types.SimpleNamespace(**{n: (copy.copy(v) if isinstance(v, dict) else v) for n, v in vars(UI).items()
+                                                if not n.startswith('__')})
+            inner_ui.model = dict(full, reducedParameterSpace=[])
+            inner_ui._reduced_inner = True
+            inner = parameter_estimation(inner_ui)
+            fn = inner.simulate_batch
+        else:
+            fn = sim if not isinstance(sim, TorchSimulator) else sim.fn
+
+        def subset_simulator(th):                                            # simulateWithSubsetOfParameters, IP.py:574-606
+            fullth = base.to(th.device).repeat(th.shape[0], 1)
+            fullth[:, cols.to(th.device)] = th
+            out = fn(fullth)
+            return out if post is None else post(out)
+        m['simulateByInputParametersOnlyFunction'] = TorchSimulator(subset_simulator)
+        for f in ('custom_logLikelihood', 'custom_logPrior', 'responses_simulation_uncertainties'):
+            if callable(full.get(f)):
+                raise NotImplementedError(f"reducedParameterSpace together with a callable model['{f}']")
+        return m
+
+    def _init(self, UI):
         pes = UI.parameter_estimation_settings
         for key, default in (('mcmc_nchains', 1), ('mcmc_store_samples', 'auto'), ('mcmc_thin', 1),
                              ('multistart_store_logP', 'auto'), ('multistart_random_seed', None), ('multistart_shard_pieces', 'auto'),
@@ -43,8 +116,8 @@ class parameter_estimation:
         # ([B], sim[B,n] or None), evaluated on the batched paths (getLogP*, multistart, ensemble slice sampling, optimisers).
         self.custom_logLikelihood = UI.model.get('custom_logLikelihood')
         self.custom_logPrior = UI.model.get('custom_logPrior')
-        if len(UI.model.get('reducedParameterSpace', [])) or len(UI.responses.get('reducedResponseSpace', [])):
-            raise NotImplementedError("reduced parameter/response spaces are out of scope (DESIGN.md)")
+        if len(UI.responses.get('reducedResponseSpace', [])):
+            raise NotImplementedError("reduced response spaces are out of scope (DESIGN.md)")
         if UI.responses.get('data_overcategory', '') != '':
             raise NotImplementedError("response transforms (data_overcategory) are out of scope (DESIGN.md)")
         self.parameterBoundsOn = bool(len(UI.model['InputParameterPriorValues_upperBounds']) +
@@ -149,6 +222,7 @@ class parameter_estimation:
         if not isinstance(sim, (BuiltinModel, TorchSimulator)):
             sim = TorchSimulator(sim)      # a bare callable is taken as a vectorised torch simulator (no CPU path)
         self.simulator = sim
+        self._post_fn = UI.model.get('simulationOutputProcessingFunction')     # None in a reduced space: applied inside the wrapper
         _dev()
         self.device_problem = DeviceProblem(H, sim)
         if isinstance(sim, BuiltinModel):
@@ -183,7 +257,7 @@ class parameter_estimation:
             self.gpu_launches += 1
             return out
         out = self.simulator(th)
-        post = self.UserInput.model.get('simulationOutputProcessingFunction')
+        post = self._post_fn
         if post is not None:
             out = post(out)
         out = torch.as_tensor(out, dtype=torch.float64, device=th.device)

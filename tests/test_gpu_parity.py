@@ -1595,3 +1595,44 @@ def test_simulation_uncertainties_as_a_function_of_the_parameters(env, golden):
     assert len(res) == 7 and np.all(np.isfinite(PE.post_burn_in_log_posteriors_un_normed_vec))
     lp2 = parts(PE, PE.post_burn_in_samples[:50])[0]
     np.testing.assert_allclose(lp2, np.ravel(PE.post_burn_in_log_posteriors_un_normed_vec)[:50], rtol=1e-12)
+
+
+def test_reduced_parameter_space(env, golden):
+    """model['reducedParameterSpace'] (IP.py:406-408, 519-561, 574-606): only the listed parameters vary, the rest stay at the initial
+    guess.  getLogP / getLogPrior / getLogLikelihood against the unmodified reference (tests/golden/reduced.npz) for a built-in model
+    (an inner full-space engine simulates) and a torch simulator, incl. the reference's handling of an unsorted index list; then the
+    samplers run in the reduced space and UserInput.model is left as the user wrote it."""
+    PEUQSE, orc, _, torch = env
+    g = golden("reduced")
+    X = torch.tensor(X00, dtype=torch.float64, device='cuda')
+    f = lambda t: (X[None, :] - t[:, :1]) ** 2 + t[:, 1:2]
+    for tag, idx in (('b', [1]), ('a', [0]), ('ba', [1, 0])):
+        for model in (PEUQSE.QuadraticModel(X00), PEUQSE.TorchSimulator(f), f):
+            PE = make_pe(PEUQSE, model, Y00, S00, [200, 500], [100, 200], InputParameterInitialGuess=[210.0, 480.0], reducedParameterSpace=idx,
+                         settings={'mcmc_length': 600, 'mcmc_burn_in': 60, 'mcmc_relative_step_length': 0.3, 'mcmc_random_seed': 2,
+                                   'mcmc_nwalkers': 8, 'exportLog': False})
+            assert PE.k == len(idx) and PE.reducedParameterSpaceOn and PE.UserInput.model['reducedParameterSpace'] == idx
+            assert len(PE.UserInput.model['InputParameterPriorValues']) == 2
+            lp, pr, ll = parts(PE, g['reduced_%s_thetas' % tag])
+            want = g['reduced_%s_vals' % tag]
+            np.testing.assert_allclose(ll, want[:, 2], rtol=1e-12)
+            np.testing.assert_allclose(lp, want[:, 0], rtol=1e-12)
+            assert np.array_equal(pr, want[:, 1])
+    assert list(PE.UserInput.parameterNamesList) == ['0', '1'] and np.array_equal(PE.UserInput.InputParameterInitialGuess, [210.0, 480.0])
+    PE1 = make_pe(PEUQSE, PEUQSE.QuadraticModel(X00), Y00, S00, [200, 500], [100, 200], InputParameterInitialGuess=[210.0, 480.0],
+                  reducedParameterSpace=[1], settings={'mcmc_length': 2000, 'mcmc_burn_in': 200, 'mcmc_relative_step_length': 0.3,
+                                                       'mcmc_random_seed': 2, 'exportLog': False, 'mcmc_threshold_filter_samples': False})
+    res = PE1.doMetropolisHastings()
+    assert PE1.post_burn_in_samples.shape == (1800, 1) and len(res[0]) == 1
+    # the posterior of b given a = 210: Gaussian prior N(500, 200^2) times three Gaussian observations of b + (x - 210)^2
+    x = np.asarray(X00, dtype=float)
+    w = 1.0 / np.asarray(S00, dtype=float) ** 2
+    prec = w.sum() + 1 / 200.0 ** 2
+    mean = (np.sum(w * (np.asarray(Y00) - (x - 210.0) ** 2)) + 500.0 / 200.0 ** 2) / prec
+    assert abs(PE1.mu_AP_parameter_set[0] - mean) < 6 * prec ** -0.5 / np.sqrt(1800 / 20)
+    PE1.UserInput.parameter_estimation_settings.update({'multistart_initialPointsDistributionType': 'grid',
+                                                        'multistart_gridsearchSamplingInterval': [10.0], 'multistart_gridsearchSamplingRadii': [30]})
+    PE1.doMultiStart()
+    grid = 480.0 + 10.0 * np.arange(-30, 31)
+    lpg = parts(PE1, grid[:, None])[0]
+    assert PE1.map_parameter_set[0] == grid[int(np.argmax(lpg))]

@@ -87,6 +87,26 @@ def test_simulation_uncertainties_as_a_function_vs_reference(golden):
             assert (ll + row[1] == row[0]) or (row[1] == float('-inf') and row[0] == float('-inf'))
 
 
+def test_reduced_parameter_space_vs_reference(golden):
+    """model['reducedParameterSpace'] (IP.py:519-561, 574-606; tests/golden/make_golden_reduced.py ran the unmodified reference): the
+    problem built from the selected priors with a simulator that fills the other parameters from the initial guess is the reference's."""
+    g = golden("reduced")
+    pt, _ = orc.sim_quadratic(X00)
+    guess = g['reduced_guess']
+    for tag, idx in (('b', [1]), ('a', [0]), ('ba', [1, 0])):
+        keep = sorted(idx)            # returnReducedIterable keeps the ORIGINAL order of the selected priors (IP.py:3559-3564) ...
+        P = orc.build_problem(list(np.array([200., 500.])[keep]), list(np.array([100., 200.])[keep]), Y00, S00)
+
+        def sim(th, idx=idx):         # ... while the simulation wrapper places value j at index idx[j] (IP.py:585-589)
+            full = guess.copy()
+            full[idx] = th
+            return pt(tuple(full))
+        for th, row in zip(g['reduced_%s_thetas' % tag], g['reduced_%s_vals' % tag]):
+            assert orc.log_prior_point(P, th) == row[1]
+            assert orc.log_likelihood_point(P, sim(th)) == row[2]
+            assert orc.log_p_point(P, th, sim) == row[0]
+
+
 def test_grid_order(golden):
     g = golden("example00")
     for name in ("g3", "g3d"):
