@@ -104,6 +104,35 @@ class parameter_estimation:
                 raise NotImplementedError(f"reducedParameterSpace together with a callable model['{f}']")
         return m
 
+    @staticmethod
+    def _response_subset_simulator(UI, sim, post, keep):
+        """extractReducedResponsesOutputsWrapper (IP.py:483-499): the full simulation (and the user's output processing) runs, then only
+        the response dimensions named in responses['reducedResponseSpace'] are kept (by membership, in their original order).  A
+        built-in model simulates through an inner engine on the full response set."""
+        import copy
+        import types
+        from .problem import nest_responses
+        nfull = [len(o) for o in nest_responses(UI.responses['responses_observed'])]
+        offs = np.concatenate(([0], np.cumsum(nfull)))
+        cols = torch.as_tensor(np.concatenate([np.arange(offs[r], offs[r + 1]) for r in range(len(nfull)) if r in keep]), dtype=torch.long)
+        if isinstance(sim, BuiltinModel):
+            inner_ui = types.SimpleNamespace(**{n: (copy.copy(v) if isinstance(v, dict) else v) for n, v in vars(UI).items()
+                                                if not n.startswith('__')})
+            inner_ui.responses['reducedResponseSpace'] = []
+            fn = parameter_estimation(inner_ui).simulate_batch
+        else:
+            fn = sim.fn
+
+        def subset(th):
+            out = fn(th)
+            if post is not None:
+                out = post(out)
+            if isinstance(out, (list, tuple)):
+                out = torch.cat([torch.as_tensor(o, dtype=torch.float64, device=th.device).reshape(th.shape[0], -1) for o in out], dim=1)
+            out = torch.as_tensor(out, dtype=torch.float64, device=th.device).reshape(th.shape[0], -1)
+            return out[:, cols.to(th.device)]
+        return TorchSimulator(subset)
+
     def _init(self, UI):
         pes = UI.parameter_estimation_settings
         for key, default in (('mcmc_nchains', 1), ('mcmc_store_samples', 'auto'), ('mcmc_thin', 1),
@@ -116,8 +145,7 @@ class parameter_estimation:
         # ([B], sim[B,n] or None), evaluated on the batched paths (getLogP*, multistart, ensemble slice sampling, optimisers).
         self.custom_logLikelihood = UI.model.get('custom_logLikelihood')
         self.custom_logPrior = UI.model.get('custom_logPrior')
-        if len(UI.responses.get('reducedResponseSpace', [])):
-            raise NotImplementedError("reduced response spaces are out of scope (DESIGN.md)")
+        keep_resp = list(UI.responses.get('reducedResponseSpace', []))
         if UI.responses.get('data_overcategory', '') != '':
             raise NotImplementedError("response transforms (data_overcategory) are out of scope (DESIGN.md)")
         self.parameterBoundsOn = bool(len(UI.model['InputParameterPriorValues_upperBounds']) +
@@ -170,7 +198,8 @@ class parameter_estimation:
                                scaling_type=pes['scaling_uncertainties_type'],
                                simulation_uncertainties=sim_unc,
                                max_covmat_size=UI.responses['responses_observed_max_covmat_size'],
-                               covmat_whitening=UI.responses.get('responses_observed_covmat_whitening', 'eigh'))
+                               covmat_whitening=UI.responses.get('responses_observed_covmat_whitening', 'eigh'),
+                               keep_responses=keep_resp)
         self.host_problem = H
         # reference-named derived fields, written back into UserInput as the reference does (IP.py:146-350)
         UI.mu_prior, UI.std_prior, UI.var_prior, UI.covmat_prior = H.mu_prior, H.std_prior, H.var_prior, H.covmat_prior
@@ -221,8 +250,12 @@ class parameter_estimation:
             raise NotImplementedError("simulationOutputProcessingFunction cannot follow a built-in CUDA model; fold it into a TorchSimulator")
         if not isinstance(sim, (BuiltinModel, TorchSimulator)):
             sim = TorchSimulator(sim)      # a bare callable is taken as a vectorised torch simulator (no CPU path)
-        self.simulator = sim
         self._post_fn = UI.model.get('simulationOutputProcessingFunction')     # None in a reduced space: applied inside the wrapper
+        if len(keep_resp):
+            if self._sim_unc_fn is not None or self.custom_logLikelihood is not None:
+                raise NotImplementedError("reducedResponseSpace together with a callable likelihood / simulation-uncertainty function")
+            sim, self._post_fn = self._response_subset_simulator(UI, sim, self._post_fn, keep_resp), None
+        self.simulator = sim
         _dev()
         self.device_problem = DeviceProblem(H, sim)
         if isinstance(sim, BuiltinModel):

@@ -152,7 +152,7 @@ class HostProblem:
 
 def build_host_problem(prior_values, prior_uncertainties, observed, observed_uncertainties, lower_bounds=(),
                        upper_bounds=(), scaling_type="std", simulation_uncertainties=None,
-                       max_covmat_size=100, covmat_whitening='eigh') -> HostProblem:
+                       max_covmat_size=100, covmat_whitening='eigh', keep_responses=()) -> HostProblem:
     mu = np.array(prior_values, dtype='float')                             # IP.py:146
     unc = np.array(prior_uncertainties, dtype='float')                     # IP.py:148
     k = len(mu)
@@ -209,6 +209,12 @@ def build_host_problem(prior_values, prior_uncertainties, observed, observed_unc
             raise NotImplementedError("a single response with a full covariance matrix never reaches scipy in the "
                                       "reference (IP.py:2938-2945 raises and falls through); split it into >= 2 responses")
         covs.append(np.asarray(cov, dtype=float))
+    if len(keep_responses):
+        # responses['reducedResponseSpace'] (reduceResponseSpace, IP.py:470-512): the observed values and covariances are reduced by
+        # MEMBERSHIP after they were shaped on the full response set -- a vector of sigmas of a multi-response problem stays "as
+        # variances" (shaped_response_cov) even when one response is left
+        sel = [r for r in range(len(obs)) if r in keep_responses]
+        obs, covs = [obs[r] for r in sel], [covs[r] for r in sel]
 
     H = HostProblem(k=k, mu_prior=mu, std_prior=std, var_prior=var, covmat_prior=covmat, scaling=scaling,
                     mu_prior_scaled=mu_s, var_prior_scaled=var_s, covmat_prior_scaled=cov_s,

@@ -1636,3 +1636,33 @@ def test_reduced_parameter_space(env, golden):
     grid = 480.0 + 10.0 * np.arange(-30, 31)
     lpg = parts(PE1, grid[:, None])[0]
     assert PE1.map_parameter_set[0] == grid[int(np.argmax(lpg))]
+
+
+def test_reduced_response_space(env, golden):
+    """responses['reducedResponseSpace'] (IP.py:410-413, 470-512): the full simulation runs and only the listed response dimensions enter
+    the likelihood.  Against the unmodified reference (tests/golden/reduced_responses.npz): three responses, keeping [0, 2] and keeping
+    [1] (whose sigmas stay "as variances", the multi-response behaviour of returnShapedResponseCovMat); built-in model (an inner engine
+    on the full response set simulates), torch simulator returning the concatenated block, and one returning a list per response."""
+    PEUQSE, orc, _, torch = env
+    g = golden("reduced_responses")
+    Phi, y, sig, th = g['rr_Phi'], g['rr_y'], g['rr_sig'], g['rr_thetas']
+    n = 6
+    Phi_t = torch.from_numpy(Phi).cuda()
+    obs = [list(y[r * n:(r + 1) * n]) for r in range(3)]
+    unc = [list(sig[r * n:(r + 1) * n]) for r in range(3)]
+    as_list = lambda t: [(t @ Phi_t.T)[:, r * n:(r + 1) * n] for r in range(3)]
+    for tag, keep in (('02', [0, 2]), ('1', [1])):
+        for model in (PEUQSE.LinearModel(Phi), PEUQSE.TorchSimulator(lambda t: t @ Phi_t.T), PEUQSE.TorchSimulator(as_list)):
+            PE = make_pe(PEUQSE, model, obs, unc, [0.0, 0.0, 0.0], [2.0, 2.0, 3.0],
+                         settings={'reducedResponseSpace': keep, 'mcmc_length': 500, 'mcmc_burn_in': 50, 'mcmc_relative_step_length': 0.01,
+                                   'mcmc_random_seed': 2, 'exportLog': False})
+            assert PE.UserInput.num_response_dimensions == len(keep) and PE.host_problem.n_total == n * len(keep)
+            lp, pr, ll = parts(PE, th)
+            want = g['rr_%s_vals' % tag]
+            np.testing.assert_allclose(ll, want[:, 2], rtol=1e-12)
+            np.testing.assert_allclose(lp, want[:, 0], rtol=1e-12)
+            assert np.array_equal(pr, want[:, 1])
+            sim = PE.simulate_batch(th[:2]).cpu().numpy()
+            np.testing.assert_allclose(sim, np.hstack([(th[:2] @ Phi.T)[:, r * n:(r + 1) * n] for r in keep]), rtol=1e-12)
+    res = PE.doMetropolisHastings()
+    assert len(res) == 7 and PE.post_burn_in_samples.shape[1] == 3 and np.all(np.isfinite(PE.post_burn_in_log_posteriors_un_normed_vec))

@@ -107,6 +107,33 @@ def test_reduced_parameter_space_vs_reference(golden):
             assert orc.log_p_point(P, th, sim) == row[0]
 
 
+def test_reduced_response_space_vs_reference(golden):
+    """responses['reducedResponseSpace'] (IP.py:470-512; tests/golden/make_golden_reduced_responses.py ran the unmodified reference):
+    the kept responses' blocks of the problem shaped on the FULL response set give the reference's likelihood bit for bit -- with one
+    response left its sigmas are still used as variances, the multi-response behaviour of returnShapedResponseCovMat -- and the host
+    problem of the package selects the same blocks."""
+    import dataclasses
+    from peuqse_b200.problem import build_host_problem
+    g = golden("reduced_responses")
+    Phi, y, sig, th = g['rr_Phi'], g['rr_y'], g['rr_sig'], g['rr_thetas']
+    n = 6
+    pt, _ = orc.sim_linear(Phi)
+    obs = [list(y[r * n:(r + 1) * n]) for r in range(3)]
+    unc = [list(sig[r * n:(r + 1) * n]) for r in range(3)]
+    full = orc.build_problem([0.0, 0.0, 0.0], [2.0, 2.0, 3.0], obs, unc)
+    for tag, keep in (('02', [0, 2]), ('1', [1])):
+        P = dataclasses.replace(full, responses=[full.responses[r] for r in keep])
+        want = g['rr_%s_vals' % tag]
+        for t, row in zip(th, want):
+            sim = pt(tuple(t))
+            assert orc.log_likelihood_point(P, [sim[r * n:(r + 1) * n] for r in keep]) == row[2]
+            assert orc.log_prior_point(P, t) == row[1]
+        H = build_host_problem([0.0, 0.0, 0.0], [2.0, 2.0, 3.0], obs, unc, keep_responses=keep)
+        assert len(H.responses_observed) == len(keep) and H.n_total == n * len(keep)
+        for j, r in enumerate(keep):
+            assert np.array_equal(H.responses_observed[j], y[r * n:(r + 1) * n]) and np.array_equal(H.responses_cov[j], sig[r * n:(r + 1) * n])
+
+
 def test_grid_order(golden):
     g = golden("example00")
     for name in ("g3", "g3d"):
