@@ -146,6 +146,16 @@ int peuqse_logp_from_sim(const peuqse_problem* p, const double* d_theta, const d
 int peuqse_loglik_simvar(const double* d_sim, const double* d_sim_sd, const double* d_y, const double* d_var_obs,
                          const int32_t* resp_n, const int32_t* per_value, int32_t n_resp, int64_t B, double* d_loglik, void* stream);
 
+/*
+ * replaces: the simulated side of transform_responses for responses['data_overcategory'] = 'transient_kinetics' (IP.py:609-658,
+ * called per evaluation at IP.py:2890): in place on d_sim[B][n_total], response r is replaced passes[r] times (0, 1 or 2) by its
+ * explicit-Euler integral over the abscissa, y[0] = 0, y[j+1] = y[j] + v[j] * d_dt[j] (littleEulerGivenArray, IP.py:3501-3513);
+ * d_dt[n_total]: t[j+1] - t[j] per response (the last entry of a response is not used).  Sequential per row: bit-identical to the
+ * reference's loop.  The observed side is transformed once on the host (peuqse_b200/problem.py:transform_transient).
+ */
+int peuqse_transform_transient(double* d_sim, const double* d_dt, const int32_t* resp_n, const int32_t* passes, int32_t n_resp,
+                               int64_t B, void* stream);
+
 /* replaces: getLogPrior alone (IP.py:2756-2794, bounds 2796-2805) -- for callers whose likelihood is their own
  * (UserInput.model['custom_logLikelihood'], IP.py:2854-2857).  d_logprior[B]. */
 int peuqse_logprior_batch(const peuqse_problem* p, const double* d_theta, int64_t B, double* d_logprior, void* stream);

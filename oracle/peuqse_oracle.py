@@ -330,6 +330,51 @@ def log_likelihood_simvar_point(P: OracleProblem, sim, sim_sd) -> float:
     return total
 
 
+def little_euler(t, dydt):
+    """littleEulerGivenArray with y_initial = 0 (IP.py:3501-3513): explicit Euler integral of dydt over t, sequential."""
+    y = np.zeros(len(t))
+    for j in range(len(t) - 1):
+        y[j + 1] = y[j] + dydt[j] * (t[j + 1] - t[j])
+    return y
+
+
+def little_euler_uncertainty(unc, t, initial):
+    """littleEulerUncertaintyPropagation (IP.py:3516-3525)."""
+    unc = np.asarray(unc, dtype=float)
+    out = unc * 0.0
+    out[0] = initial
+    for j in range(len(unc) - 1):
+        out[j + 1] = ((out[j]) ** 2 + (unc[j] * (t[j + 1] - t[j])) ** 2) ** 0.5
+    if initial == 0:
+        out[0] = out[1]
+    return out
+
+
+def transient_passes(response_type, data_type):
+    """How often transform_responses integrates a response of data_overcategory 'transient_kinetics' (IP.py:620-657): an intermediate
+    given as a concentration once and as a rate twice, a reactant or product given as a rate once, everything else not at all."""
+    if response_type == 'I':
+        return {'c': 1, 'r': 2}.get(data_type, 0)
+    if response_type in ('R', 'P'):
+        return 1 if data_type == 'r' else 0
+    return 0
+
+
+def transform_responses(abscissa, types, data_types, responses, uncertainties=None):
+    """transform_responses for 'transient_kinetics' (IP.py:609-658).  abscissa: one per response, or a single shared one."""
+    resp = [np.array(r, dtype=float) for r in _nest(responses)]
+    ab = _nest(abscissa)
+    unc = None if uncertainties is None else [np.array(u, dtype=float) for u in _nest_unc(uncertainties, len(resp))]
+    for r in range(len(resp)):
+        t = ab[0] if len(ab) == 1 else ab[r]
+        base = None if unc is None else np.mean(unc[r]) / 10                     # of the UNtransformed uncertainties, both passes
+        for _ in range(transient_passes(types[r], data_types[r])):
+            resp[r] = little_euler(t, resp[r])
+            if unc is not None:
+                unc[r] = little_euler_uncertainty(unc[r], t, base)
+    return resp, unc
+
+
 def log_p_point(P: OracleProblem, theta, simulate: Callable) -> float:
     """getLogP, IP.py:1647-1654."""
     lp = log_prior_point(P, theta)

@@ -90,7 +90,7 @@ def mh_stat_layout(k):
 
 EXPORTS = [
     "peuqse_last_error", "peuqse_version", "peuqse_device_info", "peuqse_bench_fp64", "peuqse_problem_create", "peuqse_problem_destroy",
-    "peuqse_logp_batch", "peuqse_logprior_batch", "peuqse_logp_from_sim", "peuqse_loglik_simvar", "peuqse_simulate_batch", "peuqse_sweep_work_bytes",
+    "peuqse_logp_batch", "peuqse_logprior_batch", "peuqse_logp_from_sim", "peuqse_loglik_simvar", "peuqse_transform_transient", "peuqse_simulate_batch", "peuqse_sweep_work_bytes",
     "peuqse_sweep_pass1", "peuqse_sweep_best_point", "peuqse_sweep_points", "peuqse_sweep_pass2", "peuqse_sweep_edges", "peuqse_sweep_hist",
     "peuqse_comm_unique_id", "peuqse_comm_create", "peuqse_comm_destroy", "peuqse_comm_allgather",
     "peuqse_comm_allreduce_sum_i64", "peuqse_peer_alloc", "peuqse_peer_create", "peuqse_peer_destroy",
@@ -138,6 +138,7 @@ def load():
     L.peuqse_logprior_batch.argtypes = [vp, vp, i64, vp, vp]
     L.peuqse_logp_from_sim.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp]
     L.peuqse_loglik_simvar.argtypes = [vp, vp, vp, vp, C.POINTER(i32), C.POINTER(i32), i32, i64, vp, vp]
+    L.peuqse_transform_transient.argtypes = [vp, vp, C.POINTER(i32), C.POINTER(i32), i32, i64, vp]
     L.peuqse_simulate_batch.argtypes = [vp, vp, i64, vp, vp]
     L.peuqse_sweep_work_bytes.restype = i64
     L.peuqse_sweep_work_bytes.argtypes = [vp, C.POINTER(SweepSpec), i64, i64]

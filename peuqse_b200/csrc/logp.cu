@@ -292,3 +292,46 @@ extern "C" int peuqse_loglik_simvar(const double* d_sim, const double* d_sim_sd,
     PQ_CUDA_OK(cudaGetLastError());
     return PEUQSE_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// The simulated side of transform_responses for data_overcategory 'transient_kinetics' (IP.py:609-658, applied per evaluation at
+// IP.py:2890): every pass replaces a response by its explicit-Euler integral over the abscissa, y[0] = 0, y[j+1] = y[j] + v[j] dt[j]
+// (littleEulerGivenArray, IP.py:3501-3513).  A running sum in the reference's order -- one thread per (point, response), in place --
+// so the transformed values are the reference's to the last bit (a parallel scan would reorder the additions).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_transform_transient(const __grid_constant__ SimVarResp R, const double* __restrict__ dt,
+                                                             long long B, double* __restrict__ sim) {
+    const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= B * R.n_resp) return;
+    const long long b = id / R.n_resp;
+    const int r = (int)(id - b * R.n_resp);
+    const int lo = R.off[r], hi = R.off[r + 1];
+    double* s = sim + b * R.off[R.n_resp];
+    for (int pass = 0; pass < R.per_value[r]; ++pass) {           // per_value carries the number of passes here
+        double acc = 0.0;
+        for (int j = lo; j < hi; ++j) {
+            const double v = s[j];
+            s[j] = acc;
+            acc = acc + v * dt[j];
+        }
+    }
+}
+
+extern "C" int peuqse_transform_transient(double* d_sim, const double* d_dt, const int32_t* resp_n, const int32_t* passes,
+                                          int32_t n_resp, int64_t B, void* stream) {
+    if (!d_sim || !d_dt || !resp_n || !passes || B < 0) return pq_set_error(PEUQSE_ERR_INVALID, "bad argument");
+    if (n_resp < 1 || n_resp > PQ_SIMVAR_MAX_RESP) return pq_set_error(PEUQSE_ERR_INVALID, "1 <= n_resp <= 64");
+    if (B == 0) return PEUQSE_OK;
+    SimVarResp R;
+    R.n_resp = n_resp;
+    R.off[0] = 0;
+    for (int r = 0; r < n_resp; ++r) {
+        if (resp_n[r] < 1 || passes[r] < 0 || passes[r] > 2) return pq_set_error(PEUQSE_ERR_INVALID, "bad response description");
+        R.off[r + 1] = R.off[r] + resp_n[r];
+        R.per_value[r] = passes[r];
+    }
+    const long long blocks = (B * n_resp + 127) / 128;
+    k_transform_transient<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(R, d_dt, B, d_sim);
+    PQ_CUDA_OK(cudaGetLastError());
+    return PEUQSE_OK;
+}

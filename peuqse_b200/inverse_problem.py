@@ -104,6 +104,41 @@ class parameter_estimation:
                 raise NotImplementedError(f"reducedParameterSpace together with a callable model['{f}']")
         return m
 
+    def _transient_simulator(self, UI, sim, post, H):
+        """The simulated side of transform_responses (IP.py:2890): the simulation (and the user's output processing) runs, then
+        peuqse_transform_transient integrates the rate-type responses in place.  A built-in model simulates through an inner engine
+        without the transform."""
+        import copy
+        import types
+        n = [int(len(o)) for o in H.responses_observed]
+        resp_n = (C.c_int32 * len(n))(*n)
+        passes = (C.c_int32 * len(n))(*self._transient_passes)
+        L = _lib.load()
+        dt = {}
+        if isinstance(sim, BuiltinModel):
+            inner_ui = types.SimpleNamespace(**{a: (copy.copy(v) if isinstance(v, dict) else v) for a, v in vars(UI).items()
+                                                if not a.startswith('__')})
+            inner_ui.responses['data_overcategory'] = ''
+            fn = parameter_estimation(inner_ui).simulate_batch
+        else:
+            fn = sim.fn
+
+        def transformed(th):
+            out = fn(th)
+            if post is not None:
+                out = post(out)
+            if isinstance(out, (list, tuple)):
+                out = torch.cat([torch.as_tensor(o, dtype=torch.float64, device=th.device).reshape(th.shape[0], -1) for o in out], dim=1)
+            out = torch.as_tensor(out, dtype=torch.float64, device=th.device).reshape(th.shape[0], -1).contiguous().clone()
+            if out.shape[1] != sum(n):
+                raise ValueError(f"the simulation returned {out.shape[1]} values per point, the observed responses hold {sum(n)}")
+            if th.device not in dt:
+                dt[th.device] = torch.as_tensor(self._transient_dt, device=th.device)
+            _lib.check(L.peuqse_transform_transient(_lib.ptr(out), _lib.ptr(dt[th.device]), resp_n, passes, len(n), out.shape[0],
+                                                    _lib.current_stream()))
+            return out
+        return TorchSimulator(transformed)
+
     @staticmethod
     def _response_subset_simulator(UI, sim, post, keep):
         """extractReducedResponsesOutputsWrapper (IP.py:483-499): the full simulation (and the user's output processing) runs, then only
@@ -146,8 +181,7 @@ class parameter_estimation:
         self.custom_logLikelihood = UI.model.get('custom_logLikelihood')
         self.custom_logPrior = UI.model.get('custom_logPrior')
         keep_resp = list(UI.responses.get('reducedResponseSpace', []))
-        if UI.responses.get('data_overcategory', '') != '':
-            raise NotImplementedError("response transforms (data_overcategory) are out of scope (DESIGN.md)")
+        self._transient = UI.responses.get('data_overcategory', '') == 'transient_kinetics'      # other categories transform nothing (IP.py:664-676)
         self.parameterBoundsOn = bool(len(UI.model['InputParameterPriorValues_upperBounds']) +
                                       len(UI.model['InputParameterPriorValues_lowerBounds']))          # IP.py:49
         UI.InputParameterPriorValues_lowerBounds = UI.model['InputParameterPriorValues_lowerBounds']
@@ -191,6 +225,23 @@ class parameter_estimation:
         if self._sim_unc_fn is not None:
             sim_unc = None
             UI.responses_simulation_uncertainties = self._sim_unc_fn                                   # IP.py:276
+        raw_observed = observed
+        if self._transient:
+            # transform_responses on the observed side (IP.py:295, 609-658), once; the simulated side is peuqse_transform_transient
+            from .problem import nest_responses, transform_transient, transient_passes
+            if len(keep_resp) or sim_unc is not None or self._sim_unc_fn is not None or self.custom_logLikelihood is not None:
+                raise NotImplementedError("data_overcategory 'transient_kinetics' together with reducedResponseSpace, simulation "
+                                          "uncertainties or a custom likelihood")
+            nresp = len(nest_responses(observed))
+            types, dtypes = list(UI.responses['response_types']), list(UI.responses['response_data_types'])
+            if len(types) != nresp or len(dtypes) != nresp:
+                raise ValueError("responses['response_types'] and ['response_data_types'] need one entry per response")
+            ab = nest_responses(UI.responses['responses_abscissa'])
+            obs_t, unc_t = transform_transient(ab, types, dtypes, observed, obs_unc)
+            self._transient_passes = [transient_passes(a, b) for a, b in zip(types, dtypes)]
+            self._transient_dt = np.concatenate([np.append(np.diff(np.asarray(ab[0] if len(ab) == 1 else ab[r], dtype=float)), 0.0)
+                                                 for r in range(nresp)])
+            observed, obs_unc = (obs_t, unc_t) if nresp > 1 else (obs_t[0], unc_t[0])
         H = build_host_problem(UI.model['InputParameterPriorValues'], UI.model['InputParametersPriorValuesUncertainties'],
                                observed, obs_unc,
                                lower_bounds=UI.model['InputParameterPriorValues_lowerBounds'],
@@ -208,7 +259,7 @@ class parameter_estimation:
             UI.scaling_uncertainties = H.scaling
         if H.uniform_idx is not None:
             UI.InputParametersPriorValuesUniformDistributionsIndices = H.uniform_idx
-        UI.responses_observed = H.responses_observed
+        UI.responses_observed = H.responses_observed if not self._transient else nest_responses(raw_observed)
         UI.responses_observed_transformed = H.responses_observed
         UI.num_response_dimensions = len(H.responses_observed)
         UI.num_data_points = int(sum(len(r) for r in H.responses_observed))
@@ -251,6 +302,8 @@ class parameter_estimation:
         if not isinstance(sim, (BuiltinModel, TorchSimulator)):
             sim = TorchSimulator(sim)      # a bare callable is taken as a vectorised torch simulator (no CPU path)
         self._post_fn = UI.model.get('simulationOutputProcessingFunction')     # None in a reduced space: applied inside the wrapper
+        if self._transient and any(self._transient_passes):
+            sim, self._post_fn = self._transient_simulator(UI, sim, self._post_fn, H), None
         if len(keep_resp):
             if self._sim_unc_fn is not None or self.custom_logLikelihood is not None:
                 raise NotImplementedError("reducedResponseSpace together with a callable likelihood / simulation-uncertainty function")

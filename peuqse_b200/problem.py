@@ -112,6 +112,42 @@ def shaped_response_cov(unc_list, r):
     return u
 
 
+def transient_passes(response_type, data_type):
+    """How often transform_responses integrates a response of data_overcategory 'transient_kinetics' (IP.py:620-657): an intermediate
+    given as a concentration once and as a rate twice, a reactant or product given as a rate once, everything else not at all."""
+    if response_type == 'I':
+        return {'c': 1, 'r': 2}.get(data_type, 0)
+    if response_type in ('R', 'P'):
+        return 1 if data_type == 'r' else 0
+    return 0
+
+
+def transform_transient(abscissa, types, data_types, responses, uncertainties):
+    """The observed side of transform_responses (IP.py:609-658), done once at construction: every pass replaces a response by its
+    explicit-Euler integral over the abscissa starting at 0 (littleEulerGivenArray, IP.py:3501-3513) and propagates its standard
+    deviations alongside (littleEulerUncertaintyPropagation, IP.py:3516-3525; the first point takes a tenth of the mean of the
+    UNtransformed uncertainties).  The simulated side is the kernel behind peuqse_transform_transient."""
+    resp = [np.array(r, dtype=float) for r in nest_responses(responses)]
+    ab = nest_responses(abscissa)
+    unc = [np.array(u, dtype=float) for u in nest_uncertainties(uncertainties, len(resp))]
+    for r in range(len(resp)):
+        if unc[r].ndim != 1:
+            raise NotImplementedError("data_overcategory 'transient_kinetics' needs standard deviations per value, not a covariance matrix")
+        t = ab[0] if len(ab) == 1 else ab[r]
+        base = np.mean(unc[r]) / 10
+        for _ in range(transient_passes(types[r], data_types[r])):
+            y, u = np.zeros(len(t)), unc[r] * 0.0
+            u[0] = base
+            for j in range(len(t) - 1):
+                dt = t[j + 1] - t[j]
+                y[j + 1] = y[j] + resp[r][j] * dt
+                u[j + 1] = ((u[j]) ** 2 + (unc[r][j] * dt) ** 2) ** 0.5
+            if base == 0:
+                u[0] = u[1]
+            resp[r], unc[r] = y, u
+    return resp, unc
+
+
 @dataclass
 class HostProblem:
     """Everything the kernels need, in host memory, plus the reference-named derived quantities."""

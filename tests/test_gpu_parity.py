@@ -1666,3 +1666,62 @@ def test_reduced_response_space(env, golden):
             np.testing.assert_allclose(sim, np.hstack([(th[:2] @ Phi.T)[:, r * n:(r + 1) * n] for r in keep]), rtol=1e-12)
     res = PE.doMetropolisHastings()
     assert len(res) == 7 and PE.post_burn_in_samples.shape[1] == 3 and np.all(np.isfinite(PE.post_burn_in_log_posteriors_un_normed_vec))
+
+
+def test_transient_kinetics_response_transforms(env, golden):
+    """responses['data_overcategory'] = 'transient_kinetics' (transform_responses, IP.py:609-658): rate-type responses are integrated
+    over their abscissa (explicit Euler from 0; an intermediate's rate twice) on the observed side once and on the simulated side per
+    evaluation (peuqse_transform_transient, sequential per row = the reference's loop).  Against the unmodified reference
+    (tests/golden/transient.npz): one product rate; an intermediate rate + a reactant concentration + a product rate on three unevenly
+    spaced abscissas.  A built-in model goes through an inner engine and gives what the same function as a torch simulator gives."""
+    PEUQSE, orc, _, torch = env
+    g = golden("transient")
+    t, th = g['tr_t'], g['tr_thetas']
+    T = torch.from_numpy(t).cuda()
+
+    def rates(p, resp):
+        a, b = p[:, :1], p[:, 1:2]
+        r = [a * torch.exp(-b * T[0][None, :]), 1.0 - 0.5 * a * T[1][None, :] / (1.0 + b * T[1][None, :]), a * b * torch.exp(-b * T[2][None, :])]
+        return torch.cat([r[i] for i in resp], dim=1)
+    for tag, resp, types, dtypes in (('P_r', [0], ['P'], ['r']), ('mixed', [0, 1, 2], ['I', 'R', 'P'], ['r', 'c', 'r'])):
+        y, sig = g['tr_%s_y' % tag], g['tr_%s_sig' % tag]
+        one = len(resp) == 1
+        PE = make_pe(PEUQSE, PEUQSE.TorchSimulator(lambda p, resp=resp: rates(p, resp)), list(y[0]) if one else [list(v) for v in y],
+                     list(sig[0]) if one else [list(v) for v in sig], [2.0, 1.5], [0.5, 0.4],
+                     settings={'responses_abscissa': list(t[resp[0]]) if one else [list(t[r]) for r in resp],
+                               'data_overcategory': 'transient_kinetics', 'response_types': types, 'response_data_types': dtypes,
+                               'mcmc_length': 400, 'mcmc_burn_in': 40, 'mcmc_relative_step_length': 0.05, 'mcmc_random_seed': 1,
+                               'exportLog': False})
+        for a, b in zip(PE.UserInput.responses_observed_transformed, g['tr_%s_obs_transformed' % tag]):
+            assert np.array_equal(a, b)
+        for a, b in zip(PE.observed_responses_covmat_transformed, g['tr_%s_cov_transformed' % tag]):
+            assert np.array_equal(a, b)
+        lp, pr, ll = parts(PE, th)
+        want = g['tr_%s_vals' % tag]
+        np.testing.assert_allclose(ll, want[:, 2], rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(lp, want[:, 0], rtol=1e-12, atol=1e-12)
+        assert np.array_equal(pr, want[:, 1])
+        # the transformed simulation is the oracle's sequential Euler sum (torch's exp differs from numpy's in the last ulp)
+        sim = PE.simulate_batch(th[:3]).cpu().numpy()
+        raw = rates(torch.from_numpy(th[:3]).cuda(), resp).cpu().numpy()
+        n = t.shape[1]
+        for i in range(3):
+            st, _ = orc.transform_responses([t[r] for r in resp], types, dtypes, raw[i] if one else [raw[i][j * n:(j + 1) * n] for j in range(len(resp))])
+            assert np.array_equal(sim[i], np.concatenate(st))
+    res = PE.doMetropolisHastings()
+    assert len(res) == 7 and np.all(np.isfinite(PE.post_burn_in_log_posteriors_un_normed_vec))
+    # built-in model == the same function as a torch simulator
+    rng = np.random.default_rng(2)
+    n, k = 12, 3
+    Phi = orc.cos_basis(n, k)
+    tt = np.cumsum(0.1 + 0.1 * rng.random(n))
+    yy = Phi @ np.array([1.0, 0.5, -0.3]) + 0.05 * rng.standard_normal(n)
+    Phi_t = torch.from_numpy(Phi).cuda()
+    pts = rng.standard_normal((40, k))
+    vals = []
+    for model in (PEUQSE.LinearModel(Phi), PEUQSE.TorchSimulator(lambda p: p @ Phi_t.T)):
+        PEl = make_pe(PEUQSE, model, list(yy), list(np.full(n, 0.05)), [0.0] * k, [2.0] * k,
+                      settings={'responses_abscissa': list(tt), 'data_overcategory': 'transient_kinetics', 'response_types': ['I'],
+                                'response_data_types': ['r']})
+        vals.append(parts(PEl, pts)[0])
+    np.testing.assert_allclose(vals[0], vals[1], rtol=1e-12)

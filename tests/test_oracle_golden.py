@@ -134,6 +134,30 @@ def test_reduced_response_space_vs_reference(golden):
             assert np.array_equal(H.responses_observed[j], y[r * n:(r + 1) * n]) and np.array_equal(H.responses_cov[j], sig[r * n:(r + 1) * n])
 
 
+def test_transient_kinetics_transforms_vs_reference(golden):
+    """responses['data_overcategory'] = 'transient_kinetics' (transform_responses, IP.py:609-658; tests/golden/make_golden_transient.py
+    ran the unmodified reference): transformed observations, transformed covariances and the likelihood of transformed simulations,
+    bit for bit; the package's host-side restatement (peuqse_b200/problem.py) gives the same arrays."""
+    from peuqse_b200.problem import transform_transient
+    g = golden("transient")
+    t, th = g['tr_t'], g['tr_thetas']
+    rates = lambda p: [p[0] * np.exp(-p[1] * t[0]), 1.0 - 0.5 * p[0] * t[1] / (1.0 + p[1] * t[1]), p[0] * p[1] * np.exp(-p[1] * t[2])]
+    for tag, resp, types, dtypes in (('P_r', [0], ['P'], ['r']), ('mixed', [0, 1, 2], ['I', 'R', 'P'], ['r', 'c', 'r'])):
+        y, sig = g['tr_%s_y' % tag], g['tr_%s_sig' % tag]
+        ab = [t[r] for r in resp]
+        one = len(resp) == 1
+        yt, ut = orc.transform_responses(ab, types, dtypes, y[0] if one else list(y), sig[0] if one else list(sig))
+        assert np.array_equal(np.array(yt), g['tr_%s_obs_transformed' % tag])
+        yp, up = transform_transient(ab, types, dtypes, y[0] if one else list(y), sig[0] if one else list(sig))
+        assert all(np.array_equal(a, b) for a, b in zip(yp, yt)) and all(np.array_equal(a, b) for a, b in zip(up, ut))
+        P = orc.build_problem([2.0, 1.5], [0.5, 0.4], yt[0] if one else yt, ut[0] if one else ut)
+        assert all(np.array_equal(np.asarray(b.cov), c) for b, c in zip(P.responses, g['tr_%s_cov_transformed' % tag]))
+        for p_, row in zip(th, g['tr_%s_vals' % tag]):
+            sims = [rates(p_)[r] for r in resp]
+            st, _ = orc.transform_responses(ab, types, dtypes, sims[0] if one else sims)
+            assert orc.log_likelihood_point(P, st[0] if one else st) == row[2] and orc.log_prior_point(P, p_) == row[1]
+
+
 def test_grid_order(golden):
     g = golden("example00")
     for name in ("g3", "g3d"):
