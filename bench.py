@@ -690,7 +690,9 @@ def c5_secondary(PEUQSE, torch, dist, rank, world, total):
     te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    assert PE.map_index == R.map_index and PE.map_logP == R.map_logP
+    # same MAP through the public call; below 2^31 points doMultiStart keeps logP and runs the bit-exact scalar kernel, whose
+    # values agree with the no-store tensor-pipe kernel to 1e-13 (at the default 1e10 points both are the no-store kernel)
+    assert PE.map_index == R.map_index and abs(PE.map_logP - R.map_logP) <= 1e-12 * abs(R.map_logP)
     fp64_instr = fp64_probe(torch, 0)
     flop_eval = 1.6e3                                                     # simulate 2kn + likelihood 4n + prior 4k + Philox
     per_gpu = (total / world) / (ms1 * 1e-3)
