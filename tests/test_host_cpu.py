@@ -319,3 +319,36 @@ def test_lockstep_nelder_mead_equals_scipy():
         for i in range(B):
             s = scipy.optimize.minimize(rosen, X0[i], method='Nelder-Mead', options=({'maxiter': kw['maxiter']} if kw else None))
             assert np.array_equal(s.x, r['x'][i]) and s.fun == r['fun'][i] and s.nit == r['nit'][i] and s.nfev == r['nfev'][i]
+
+
+def test_reduced_space_wrappers_on_the_host():
+    """The simulator wrappers of model['reducedParameterSpace'] (IP.py:574-606) and responses['reducedResponseSpace'] (IP.py:483-499) are
+    plain torch code: reduced value j goes to full index idx[j], the other parameters come from the initial guess, priors / bounds / names
+    are selected by membership in their original order; the response wrapper keeps the listed responses' columns."""
+    import torch
+    import peuqse_b200 as PEUQSE
+    from peuqse_b200.inverse_problem import parameter_estimation
+    UI = PEUQSE.UserInput.fresh()
+    UI.model['InputParameterPriorValues'] = [1.0, 2.0, 3.0, 4.0]
+    UI.model['InputParametersPriorValuesUncertainties'] = [0.1, 0.2, 0.3, 0.4]
+    UI.model['InputParameterPriorValues_lowerBounds'] = [0.0, None, 0.0, 0.0]
+    UI.model['InputParameterInitialGuess'] = [1.5, 2.5, 3.5, 4.5]
+    UI.model['simulateByInputParametersOnlyFunction'] = PEUQSE.TorchSimulator(lambda th: th * 10.0)
+    UI.model['simulationOutputProcessingFunction'] = lambda out: out + 1.0
+    m = parameter_estimation._reduced_model(UI, [2, 0])
+    assert m['InputParameterPriorValues'] == [1.0, 3.0] and list(m['InputParametersPriorValuesUncertainties']) == [0.1, 0.3]
+    assert m['InputParameterPriorValues_lowerBounds'] == [0.0, 0.0] and m['InputParameterPriorValues_upperBounds'] == []
+    assert m['InputParameterInitialGuess'] == [1.5, 3.5] and list(m['parameterNamesAndMathTypeExpressionsDict']) == ['0', '2']
+    assert m['reducedParameterSpace'] == [] and m['simulationOutputProcessingFunction'] is None
+    out = m['simulateByInputParametersOnlyFunction'](torch.tensor([[7.0, 8.0], [9.0, 6.0]], dtype=torch.float64))
+    assert torch.equal(out, torch.tensor([[81.0, 26.0, 71.0, 46.0], [61.0, 26.0, 91.0, 46.0]], dtype=torch.float64))
+    assert UI.model['reducedParameterSpace'] == [] and len(UI.model['InputParameterPriorValues']) == 4      # the user's dictionary is untouched
+    cov = np.diag([0.1, 0.2, 0.3, 0.4]) ** 2
+    cov[0, 2] = cov[2, 0] = 0.01
+    UI.model['InputParametersPriorValuesUncertainties'] = cov
+    m = parameter_estimation._reduced_model(UI, [0, 2])
+    assert np.array_equal(m['InputParametersPriorValuesUncertainties'], cov[np.ix_([0, 2], [0, 2])])
+    UI.responses['responses_observed'] = [[1.0, 2.0], [3.0, 4.0, 5.0], [6.0]]
+    sub = parameter_estimation._response_subset_simulator(UI, PEUQSE.TorchSimulator(lambda th: torch.arange(12.0, dtype=torch.float64).reshape(2, 6)),
+                                                          lambda o: o * 2.0, [2, 0])
+    assert torch.equal(sub(torch.zeros((2, 1), dtype=torch.float64)), torch.tensor([[0.0, 2.0, 10.0], [12.0, 14.0, 22.0]], dtype=torch.float64))
