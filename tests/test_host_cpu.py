@@ -352,3 +352,26 @@ def test_reduced_space_wrappers_on_the_host():
     sub = parameter_estimation._response_subset_simulator(UI, PEUQSE.TorchSimulator(lambda th: torch.arange(12.0, dtype=torch.float64).reshape(2, 6)),
                                                           lambda o: o * 2.0, [2, 0])
     assert torch.equal(sub(torch.zeros((2, 1), dtype=torch.float64)), torch.tensor([[0.0, 2.0, 10.0], [12.0, 14.0, 22.0]], dtype=torch.float64))
+
+
+def test_transient_transform_properties():
+    """Size-independent properties of the 'transient_kinetics' transform (IP.py:609-658, 3501-3525): the Euler integral starts at 0, is
+    linear in the response, equals the prefix sum of v[j] (t[j+1] - t[j]); two passes for an intermediate's rate; concentrations of
+    reactants / products are untouched; the propagated uncertainty never decreases along the abscissa and starts at mean(sigma) / 10."""
+    from peuqse_b200.problem import transform_transient, transient_passes
+    assert [transient_passes(a, b) for a, b in (('I', 'c'), ('I', 'r'), ('R', 'c'), ('R', 'r'), ('P', 'c'), ('P', 'r'), ('O', 'o'), ('T', 'r'))] == \
+        [1, 2, 0, 1, 0, 1, 0, 0]
+    rng = np.random.default_rng(0)
+    for n in (2, 3, 17, 400):
+        t = np.cumsum(0.01 + rng.random(n))
+        x, y = rng.standard_normal(n), rng.standard_normal(n)
+        sig = 0.1 + rng.random(n)
+        one = lambda v, ty='P', dt='r': transform_transient([t], [ty], [dt], v, sig)
+        tx, ux = one(x)
+        assert tx[0][0] == 0.0 and np.allclose(tx[0][1:], np.cumsum(x[:-1] * np.diff(t)), rtol=1e-13, atol=1e-13)
+        assert np.allclose(one(2.0 * x - 3.0 * y)[0][0], 2.0 * tx[0] - 3.0 * one(y)[0][0], rtol=1e-12, atol=1e-12)
+        assert ux[0][0] == np.mean(sig) / 10 and np.all(np.diff(ux[0]) >= 0)
+        twice = one(x, 'I', 'r')[0][0]
+        assert np.allclose(twice, one(tx[0], 'P', 'r')[0][0], rtol=1e-13, atol=1e-13)
+        same, usame = one(x, 'R', 'c')
+        assert np.array_equal(same[0], x) and np.array_equal(usame[0], sig)
